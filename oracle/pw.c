@@ -1,0 +1,605 @@
+/*
+ * pw.c -- oracle (TEST INFRASTRUCTURE, see sgw_oracle.h) for the plane-wave half of the hot path:
+ *   algo/linear_solver/src/linear_op.f90        (H + omega S + alpha_pv P_v)
+ *   phys/coul/src/solve_linter.f90 (direct branch :215-374,462-562,594-599), dvqpsi_us.f90,
+ *   coulomb.f90, coulomb_q0G0.f90, invert_epsilon.f90, algo/symmetry/src/unfold_w.f90:84,
+ *   phys/green/src/green.f90:105-226
+ * plus the Quantum ESPRESSO 6.3 (@7357cdb, un-vendored) routines they call, restated from their
+ * published semantics: h_psi/vloc_psi_k/calbec/add_vuspsi/s_psi (NC-PP, nspin=1),
+ * orthogonalize (insulator), incdrhoscf, dv_of_drho (lrpa=.TRUE.), invfft/fwfft conventions
+ * (invfft: unscaled sum_G f(G) e^{+iGr}; fwfft: scaled by 1/nnr).
+ * PARITY UNPINNED by the reference's own tests for this half -- anchored by numpy in tests/test_oracle_pw.py.
+ */
+#include "sgw_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ================================================================ mixed-radix FFT (Stockham autosort) */
+#define MAXFAC 32
+typedef struct {
+  int n, nfac, fac[MAXFAC];
+  zcplx *w; /* w[k] = exp(-2 pi i k / n) */
+} fft_plan;
+
+static fft_plan g_plans[64];
+static int g_nplans = 0;
+
+static const fft_plan *get_plan(int n) {
+  const fft_plan *res = NULL;
+#pragma omp critical(orc_fft_plan)
+  {
+    for (int i = 0; i < g_nplans; ++i)
+      if (g_plans[i].n == n) res = &g_plans[i];
+    if (!res && g_nplans < 64) {
+      fft_plan *p = &g_plans[g_nplans];
+      p->n = n;
+      p->nfac = 0;
+      int m = n;
+      while (m % 4 == 0) { p->fac[p->nfac++] = 4; m /= 4; }
+      while (m % 2 == 0) { p->fac[p->nfac++] = 2; m /= 2; }
+      while (m % 3 == 0) { p->fac[p->nfac++] = 3; m /= 3; }
+      while (m % 5 == 0) { p->fac[p->nfac++] = 5; m /= 5; }
+      for (int f = 7; m > 1; f += 2)
+        while (m % f == 0) { p->fac[p->nfac++] = f; m /= f; }
+      p->w = malloc(sizeof(zcplx) * n);
+      for (int k = 0; k < n; ++k) {
+        double a = -2.0 * M_PI * (double)k / (double)n;
+        p->w[k] = cos(a) + I * sin(a);
+      }
+      ++g_nplans;
+      res = p;
+    }
+  }
+  return res;
+}
+
+/* forward (sign=-1) or backward (sign=+1) unscaled 1-D DFT of length n; x is overwritten, y is scratch */
+static void fft1d(const fft_plan *p, zcplx *x, zcplx *y, int sign) {
+  const int n = p->n;
+  zcplx *in = x, *out = y;
+  int Ns = 1;
+  for (int s = 0; s < p->nfac; ++s) {
+    const int R = p->fac[s];
+    const int nb = n / R;
+    const int tw_step = n / (Ns * R);
+    for (int j = 0; j < nb; ++j) {
+      const int k = j % Ns;
+      zcplx v[MAXFAC];
+      for (int r = 0; r < R; ++r) {
+        int ti = (int)(((long)r * k * tw_step) % n);
+        zcplx w = p->w[ti];
+        if (sign > 0) w = conj(w);
+        v[r] = in[j + r * nb] * w;
+      }
+      const int base = (j / Ns) * Ns * R + k;
+      if (R == 2) {
+        out[base] = v[0] + v[1];
+        out[base + Ns] = v[0] - v[1];
+      } else if (R == 4) {
+        zcplx a = v[0] + v[2], b = v[0] - v[2], c = v[1] + v[3], d = v[1] - v[3];
+        zcplx id = (sign > 0) ? I * d : -I * d;
+        out[base] = a + c;
+        out[base + Ns] = b + id;
+        out[base + 2 * Ns] = a - c;
+        out[base + 3 * Ns] = b - id;
+      } else {
+        for (int q = 0; q < R; ++q) {
+          zcplx acc = 0.0;
+          for (int r = 0; r < R; ++r) {
+            int ti = (int)(((long)q * r * (n / R)) % n);
+            zcplx w = p->w[ti];
+            if (sign > 0) w = conj(w);
+            acc += v[r] * w;
+          }
+          out[base + q * Ns] = acc;
+        }
+      }
+    }
+    Ns *= R;
+    zcplx *t = in; in = out; out = t;
+  }
+  if (in != x) memcpy(x, in, sizeof(zcplx) * n);
+}
+
+/* 3-D FFT on a column-major (nr1,nr2,nr3) box, optionally pruned like QE's serial cfft3ds:
+ * colmask[i1 + nr1*i2] != 0 marks (i1,i2) columns that hold sphere data, xmask[i1] planes.
+ * sign=+1 (invfft): z for marked columns, y for marked planes, x for all.  sign=-1 (fwfft): reverse
+ * order, only marked outputs are complete, then scaled by 1/nnr.  NULL masks = full transform. */
+static void fft3d_pruned(zcplx *f, int nr1, int nr2, int nr3, int sign, const unsigned char *colmask,
+                         const unsigned char *xmask) {
+  const fft_plan *p1 = get_plan(nr1), *p2 = get_plan(nr2), *p3 = get_plan(nr3);
+  int nmax = nr1 > nr2 ? nr1 : nr2;
+  if (nr3 > nmax) nmax = nr3;
+  zcplx *line = malloc(sizeof(zcplx) * 2 * nmax);
+  zcplx *scr = line + nmax;
+  const size_t s2 = (size_t)nr1, s3 = (size_t)nr1 * nr2;
+  if (sign > 0) {
+    for (int i2 = 0; i2 < nr2; ++i2)
+      for (int i1 = 0; i1 < nr1; ++i1) {
+        if (colmask && !colmask[i1 + nr1 * i2]) continue;
+        zcplx *b = f + i1 + s2 * i2;
+        for (int k = 0; k < nr3; ++k) line[k] = b[s3 * k];
+        fft1d(p3, line, scr, sign);
+        for (int k = 0; k < nr3; ++k) b[s3 * k] = line[k];
+      }
+    for (int i3 = 0; i3 < nr3; ++i3)
+      for (int i1 = 0; i1 < nr1; ++i1) {
+        if (xmask && !xmask[i1]) continue;
+        zcplx *b = f + i1 + s3 * i3;
+        for (int k = 0; k < nr2; ++k) line[k] = b[s2 * k];
+        fft1d(p2, line, scr, sign);
+        for (int k = 0; k < nr2; ++k) b[s2 * k] = line[k];
+      }
+    for (int i3 = 0; i3 < nr3; ++i3)
+      for (int i2 = 0; i2 < nr2; ++i2) fft1d(p1, f + s2 * i2 + s3 * i3, scr, sign);
+  } else {
+    for (int i3 = 0; i3 < nr3; ++i3)
+      for (int i2 = 0; i2 < nr2; ++i2) fft1d(p1, f + s2 * i2 + s3 * i3, scr, sign);
+    for (int i3 = 0; i3 < nr3; ++i3)
+      for (int i1 = 0; i1 < nr1; ++i1) {
+        if (xmask && !xmask[i1]) continue;
+        zcplx *b = f + i1 + s3 * i3;
+        for (int k = 0; k < nr2; ++k) line[k] = b[s2 * k];
+        fft1d(p2, line, scr, sign);
+        for (int k = 0; k < nr2; ++k) b[s2 * k] = line[k];
+      }
+    for (int i2 = 0; i2 < nr2; ++i2)
+      for (int i1 = 0; i1 < nr1; ++i1) {
+        if (colmask && !colmask[i1 + nr1 * i2]) continue;
+        zcplx *b = f + i1 + s2 * i2;
+        for (int k = 0; k < nr3; ++k) line[k] = b[s3 * k];
+        fft1d(p3, line, scr, sign);
+        for (int k = 0; k < nr3; ++k) b[s3 * k] = line[k];
+      }
+    const double sc = 1.0 / ((double)nr1 * nr2 * nr3);
+    const size_t nnr = (size_t)nr1 * nr2 * nr3;
+    for (size_t i = 0; i < nnr; ++i) f[i] *= sc;
+  }
+  free(line);
+}
+
+void orc_fft3d(zcplx *f, int nr1, int nr2, int nr3, int sign) { fft3d_pruned(f, nr1, nr2, nr3, sign, NULL, NULL); }
+
+/* masks of a plane-wave sphere (what QE's 'Wave' FFT descriptor knows as sticks / planes) */
+static void sphere_masks(int nr1, int nr2, int npw, const int32_t *nl, unsigned char *colmask, unsigned char *xmask) {
+  memset(colmask, 0, (size_t)nr1 * nr2);
+  memset(xmask, 0, (size_t)nr1);
+  for (int ig = 0; ig < npw; ++ig) {
+    int idx = nl[ig] - 1;
+    int i1 = idx % nr1, i2 = (idx / nr1) % nr2;
+    colmask[i1 + nr1 * i2] = 1;
+    xmask[i1] = 1;
+  }
+}
+
+/* ================================================================ h_psi [QE], linear_op.f90 */
+void orc_h_psi(const orc_grid *g, const orc_kpoint *kp, const zcplx *psi, zcplx *hpsi, zcplx *work, zcplx *becp) {
+  const int npw = kp->npw, npwx = kp->npwx, nkb = kp->nkb;
+  const size_t nnr = (size_t)g->nr1 * g->nr2 * g->nr3;
+  /* kinetic: hpsi = g2kin * psi */
+  for (int ig = 0; ig < npw; ++ig) hpsi[ig] = kp->g2kin[ig] * psi[ig];
+  for (int ig = npw; ig < npwx; ++ig) hpsi[ig] = 0.0;
+  /* vloc_psi_k: scatter -> invfft('Wave') -> * vrs -> fwfft('Wave') -> gather */
+  unsigned char *colmask = malloc((size_t)g->nr1 * g->nr2 + g->nr1);
+  unsigned char *xmask = colmask + (size_t)g->nr1 * g->nr2;
+  sphere_masks(g->nr1, g->nr2, npw, kp->nl_igk, colmask, xmask);
+  memset(work, 0, nnr * sizeof(zcplx));
+  for (int ig = 0; ig < npw; ++ig) work[kp->nl_igk[ig] - 1] = psi[ig];
+  fft3d_pruned(work, g->nr1, g->nr2, g->nr3, +1, colmask, xmask);
+  for (size_t ir = 0; ir < nnr; ++ir) work[ir] *= g->vrs[ir];
+  fft3d_pruned(work, g->nr1, g->nr2, g->nr3, -1, colmask, xmask);
+  for (int ig = 0; ig < npw; ++ig) hpsi[ig] += work[kp->nl_igk[ig] - 1];
+  free(colmask);
+  /* calbec: becp = vkb^H psi ; add_vuspsi: hpsi += vkb (D becp) */
+  if (nkb > 0) {
+    zcplx *ps = becp + nkb;
+    for (int ikb = 0; ikb < nkb; ++ikb) {
+      const zcplx *v = kp->vkb + (size_t)ikb * npwx;
+      zcplx s = 0.0;
+      for (int ig = 0; ig < npw; ++ig) s += conj(v[ig]) * psi[ig];
+      becp[ikb] = s;
+    }
+    for (int ikb = 0; ikb < nkb; ++ikb) {
+      zcplx s = 0.0;
+      for (int jkb = 0; jkb < nkb; ++jkb) s += kp->dion[ikb + (size_t)nkb * jkb] * becp[jkb];
+      ps[ikb] = s;
+    }
+    for (int ikb = 0; ikb < nkb; ++ikb) {
+      const zcplx *v = kp->vkb + (size_t)ikb * npwx;
+      const zcplx c = ps[ikb];
+      for (int ig = 0; ig < npw; ++ig) hpsi[ig] += v[ig] * c;
+    }
+  }
+}
+
+void orc_linear_op(const orc_grid *g, const orc_kpoint *kp, zcplx omega, double alpha_pv, const zcplx *psi,
+                   zcplx *apsi, zcplx *work, zcplx *becp) {
+  const int npw = kp->npw, npwx = kp->npwx, nb = kp->nbnd_occ;
+  orc_h_psi(g, kp, psi, apsi, work, becp);                              /* linear_op.f90:116 */
+  /* s_psi: NC -> copy ; :123 A_psi += omega * S psi */
+  for (int ig = 0; ig < npw; ++ig) apsi[ig] += omega * psi[ig];
+  if (fabs(alpha_pv) > 1e-14) {                                         /* :131 */
+    /* projector_psi :147-206 : proj = alpha evq^H spsi ; P = evq proj (full npwx rows, zero padded) */
+    zcplx *proj = becp;
+    for (int ib = 0; ib < nb; ++ib) {
+      const zcplx *e = kp->evq + (size_t)ib * npwx;
+      zcplx s = 0.0;
+      for (int ig = 0; ig < npw; ++ig) s += conj(e[ig]) * psi[ig];
+      proj[ib] = alpha_pv * s;                                          /* :195 */
+    }
+    for (int ib = 0; ib < nb; ++ib) {
+      const zcplx *e = kp->evq + (size_t)ib * npwx;
+      const zcplx c = proj[ib];
+      for (int ig = 0; ig < npw; ++ig) apsi[ig] += e[ig] * c;           /* :199, :134 */
+    }
+  }
+}
+
+/* coulomb_operator (solve_linter.f90:657-716) / green_operator (green.f90:231-291) */
+void orc_pw_apply(void *ctx, zcplx sigma, const zcplx *x, zcplx *ax, int n) {
+  orc_pw_op *op = (orc_pw_op *)ctx;
+  const int npwx = op->kp->npwx;
+  zcplx *psi_ = malloc(sizeof(zcplx) * 2 * npwx), *apsi_ = psi_ + npwx;
+  memcpy(psi_, x, sizeof(zcplx) * n);
+  for (int ig = n; ig < npwx; ++ig) psi_[ig] = 0.0;
+  orc_linear_op(op->grid, op->kp, sigma, op->alpha_pv, psi_, apsi_, op->work, op->becp);
+  memcpy(ax, apsi_, sizeof(zcplx) * n);
+  free(psi_);
+}
+
+/* ================================================================ solve_linter.f90 (direct branch) */
+int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
+                     const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads) {
+  const orc_grid *g = &sys->grid;
+  const size_t nnr = (size_t)g->nr1 * g->nr2 * g->nr3;
+  const int zero_freq = cabs(freq[0]) < 1e-14;                          /* :217 */
+  const int num_omega = zero_freq ? 2 * nfreq - 1 : 2 * nfreq;          /* :238-242 */
+  zcplx *omega = malloc(sizeof(zcplx) * num_omega);
+  for (int i = 0; i < nfreq; ++i) omega[i] = freq[i];                   /* :247 */
+  if (zero_freq) for (int i = 1; i < nfreq; ++i) omega[nfreq + i - 1] = -freq[i]; /* :249 */
+  else for (int i = 0; i < nfreq; ++i) omega[nfreq + i] = -freq[i];     /* :251 */
+  int ierr_all = 0;
+  long nop_all = 0;
+  int nouter_max = 0;
+  if (nthreads < 1) nthreads = 1;
+
+  memset(drhoscf, 0, sizeof(zcplx) * nnr * nfreq);                      /* :283 */
+
+  for (int ik = 0; ik < sys->nks; ++ik) {                               /* :288 */
+    const orc_kpair *kp = &sys->kp[ik];
+    const orc_kpoint *kq = &kp->kq;
+    const int npwx = kq->npwx, npwq = kq->npw, nbnd = kp->nbnd, nocc = kq->nbnd_occ;
+    zcplx *dvpsi = calloc((size_t)npwx * nbnd, sizeof(zcplx));
+    zcplx *dpsi = calloc((size_t)npwx * nbnd * num_omega, sizeof(zcplx)); /* :256,341 */
+
+    /* dvqpsi_us.f90:99-130 : all nbnd bands, full 'Rho' FFTs */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
+    for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
+      zcplx *aux2 = calloc(nnr, sizeof(zcplx));
+      for (int ig = 0; ig < kp->npw_k; ++ig) aux2[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
+      orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, +1);
+      for (size_t ir = 0; ir < nnr; ++ir) aux2[ir] *= dvbarein[ir];
+      orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, -1);
+      for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ibnd] = aux2[kq->nl_igk[ig] - 1];
+      free(aux2);
+    }
+    /* orthogonalize [QE], insulator: ps = evq^H dvpsi ; dvpsi <- evq ps - dvpsi  (= -P_c^+ dV psi) :337 */
+    {
+      zcplx *ps = calloc((size_t)nocc * nocc, sizeof(zcplx));
+      for (int jb = 0; jb < nocc; ++jb)
+        for (int ib = 0; ib < nocc; ++ib) {
+          zcplx s = 0.0;
+          for (int ig = 0; ig < npwq; ++ig) s += conj(kq->evq[ig + (size_t)npwx * ib]) * dvpsi[ig + (size_t)npwx * jb];
+          ps[ib + (size_t)nocc * jb] = s;
+        }
+      for (int jb = 0; jb < nocc; ++jb)
+        for (int ig = 0; ig < npwq; ++ig) {
+          zcplx s = 0.0;
+          for (int ib = 0; ib < nocc; ++ib) s += kq->evq[ig + (size_t)npwx * ib] * ps[ib + (size_t)nocc * jb];
+          dvpsi[ig + (size_t)npwx * jb] = s - dvpsi[ig + (size_t)npwx * jb];
+        }
+      free(ps);
+    }
+    /* band loop :367-374 */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop_all) reduction(max : nouter_max)
+    for (int ibnd = 0; ibnd < nocc; ++ibnd) {
+      orc_pw_op op;
+      op.grid = g;
+      op.kp = kq;
+      op.alpha_pv = kq->alpha_pv;
+      op.work = malloc(sizeof(zcplx) * nnr);
+      op.becp = malloc(sizeof(zcplx) * 2 * (kq->nkb + kq->nbnd_occ + 1));
+      zcplx *sig = malloc(sizeof(zcplx) * num_omega);
+      for (int io = 0; io < num_omega; ++io) sig[io] = -(kp->et[ibnd] + omega[io]);    /* :369 */
+      zcplx *xx = calloc((size_t)npwq * num_omega, sizeof(zcplx));
+      orc_stats s1 = {0, 0, 0};
+      int ierr = orc_select_solver(cfg, orc_pw_apply, &op, npwq, dvpsi + (size_t)npwx * ibnd, num_omega, sig, xx, &s1);
+      if (ierr != 0) {
+#pragma omp critical(orc_ierr)
+        ierr_all = ierr;                                                /* :370 errore */
+      }
+      /* dpsi *= wg/wk (=1: fully occupied insulator bands)  :373 */
+      for (int io = 0; io < num_omega; ++io)
+        memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx + (size_t)npwq * io, sizeof(zcplx) * npwq);
+      nop_all += s1.n_op;
+      if (s1.n_outer > nouter_max) nouter_max = s1.n_outer;
+      free(xx); free(sig); free(op.work); free(op.becp);
+    }
+    /* average +-omega :464-480 */
+    {
+      const size_t blk = (size_t)npwx * nbnd;
+      const int first = zero_freq ? 1 : 0;
+      const size_t cnt = blk * (nfreq - first);
+      zcplx *a = dpsi + blk * first, *b = dpsi + blk * nfreq;
+      for (size_t i = 0; i < cnt; ++i) a[i] = 0.5 * a[i];
+      for (size_t i = 0; i < cnt; ++i) a[i] += 0.5 * b[i];
+    }
+    /* incdrhoscf [QE] :489-497 */
+    {
+      const double wgt = 2.0 * kp->wk / sys->omega_cell;
+      unsigned char *mk = malloc(2 * ((size_t)g->nr1 * g->nr2 + g->nr1));
+      unsigned char *mkx = mk + (size_t)g->nr1 * g->nr2;
+      unsigned char *mq = mkx + g->nr1, *mqx = mq + (size_t)g->nr1 * g->nr2;
+      sphere_masks(g->nr1, g->nr2, kp->npw_k, kp->nl_igk_k, mk, mkx);
+      sphere_masks(g->nr1, g->nr2, npwq, kq->nl_igk, mq, mqx);
+      zcplx *psir = malloc(sizeof(zcplx) * nnr * nocc);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
+      for (int ibnd = 0; ibnd < nocc; ++ibnd) {
+        zcplx *p = psir + nnr * ibnd;
+        memset(p, 0, sizeof(zcplx) * nnr);
+        for (int ig = 0; ig < kp->npw_k; ++ig) p[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
+        fft3d_pruned(p, g->nr1, g->nr2, g->nr3, +1, mk, mkx);
+      }
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
+      for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
+        zcplx *dpsic = malloc(sizeof(zcplx) * nnr);
+        zcplx *drho = drhoscf + nnr * ifreq;
+        for (int ibnd = 0; ibnd < nocc; ++ibnd) {
+          const zcplx *dp = dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * ifreq);
+          const zcplx *p = psir + nnr * ibnd;
+          memset(dpsic, 0, sizeof(zcplx) * nnr);
+          for (int ig = 0; ig < npwq; ++ig) dpsic[kq->nl_igk[ig] - 1] = dp[ig];
+          fft3d_pruned(dpsic, g->nr1, g->nr2, g->nr3, +1, mq, mqx);
+          for (size_t ir = 0; ir < nnr; ++ir) drho[ir] += wgt * conj(p[ir]) * dpsic[ir];
+        }
+        free(dpsic);
+      }
+      free(psir);
+      free(mk);
+    }
+    free(dvpsi);
+    free(dpsi);
+  }
+  /* mp_sum over pools :521 -- single pool here */
+
+  /* meandvb :532 ; zero-mean fix :544-550 ; dv_of_drho (lrpa) :556 ; drhoscf = -dvscfout :598 */
+  double s2 = 0.0;
+  for (size_t ir = 0; ir < nnr; ++ir) s2 += creal(dvbarein[ir]) * creal(dvbarein[ir]) + cimag(dvbarein[ir]) * cimag(dvbarein[ir]);
+  const double meandvb = sqrt(s2) / (double)nnr;
+  const double e2 = 2.0, fpi = 4.0 * M_PI;
+  zcplx *dvhart = malloc(sizeof(zcplx) * nnr);
+  for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
+    zcplx *dv = drhoscf + nnr * ifreq;
+    if (meandvb < 1e-10) {
+      orc_fft3d(dv, g->nr1, g->nr2, g->nr3, -1);
+      dv[sys->nl[0] - 1] = 0.0;
+      orc_fft3d(dv, g->nr1, g->nr2, g->nr3, +1);
+    }
+    orc_fft3d(dv, g->nr1, g->nr2, g->nr3, -1);
+    memset(dvhart, 0, sizeof(zcplx) * nnr);
+    for (int ig = 0; ig < sys->ngm; ++ig) {
+      double q0 = sys->g[3 * ig] + sys->xq[0], q1 = sys->g[3 * ig + 1] + sys->xq[1], q2 = sys->g[3 * ig + 2] + sys->xq[2];
+      double qg2 = q0 * q0 + q1 * q1 + q2 * q2;
+      if (qg2 > 1e-8) dvhart[sys->nl[ig] - 1] = e2 * fpi * dv[sys->nl[ig] - 1] / (sys->tpiba2 * qg2);
+    }
+    orc_fft3d(dvhart, g->nr1, g->nr2, g->nr3, +1);
+    for (size_t ir = 0; ir < nnr; ++ir) dv[ir] = -dvhart[ir];
+  }
+  free(dvhart);
+  free(omega);
+  if (st) {
+    st->n_op += nop_all;
+    if (nouter_max > st->n_outer) st->n_outer = nouter_max;
+  }
+  return ierr_all;
+}
+
+/* ================================================================ coulomb.f90:29-176 */
+static int coulomb_one(const orc_system *sys, const orc_solver_cfg *cfg, int ig_global /*1-based*/, int ngc,
+                       int nfs, const zcplx *fiu, zcplx *scr /* ngc x nfs */, orc_stats *st, int nthreads) {
+  const orc_grid *g = &sys->grid;
+  const size_t nnr = (size_t)g->nr1 * g->nr2 * g->nr3;
+  const double *gv = sys->g + 3 * (ig_global - 1);
+  double q0 = gv[0] + sys->xq[0], q1 = gv[1] + sys->xq[1], q2 = gv[2] + sys->xq[2];
+  if (q0 * q0 + q1 * q1 + q2 * q2 < 1e-8) return 0;                     /* :126 CYCLE */
+  zcplx *dvbare = calloc(nnr, sizeof(zcplx));
+  zcplx *drhoscfs = calloc(nnr * nfs, sizeof(zcplx));
+  dvbare[sys->nl[ig_global - 1] - 1] = 1.0;                             /* :131 */
+  orc_fft3d(dvbare, g->nr1, g->nr2, g->nr3, +1);                        /* :134 */
+  int ierr = orc_solve_linter(sys, cfg, dvbare, nfs, fiu, drhoscfs, st, nthreads); /* :137 */
+  orc_fft3d(dvbare, g->nr1, g->nr2, g->nr3, -1);                        /* :140 */
+  for (int iw = 0; iw < nfs; ++iw) {
+    zcplx *d = drhoscfs + nnr * iw;
+    orc_fft3d(d, g->nr1, g->nr2, g->nr3, -1);                           /* :146 */
+    for (int igp = 0; igp < ngc; ++igp) scr[igp + (size_t)ngc * iw] = d[sys->nl[igp] - 1]; /* :149-151 */
+    int igp = ig_global - 1;                                            /* :154-157 (solve_direct) */
+    if (igp < ngc) scr[igp + (size_t)ngc * iw] += dvbare[sys->nl[igp] - 1];
+  }
+  free(dvbare);
+  free(drhoscfs);
+  return ierr;
+}
+
+int orc_coulomb(const orc_system *sys, const orc_solver_cfg *cfg, int igstart, int ngc, int ntask,
+                const int32_t *ig_unique, int nfs, const zcplx *fiu, zcplx *scrcoul, orc_stats *st,
+                int nthreads) {
+  int ierr_all = 0;
+  memset(scrcoul, 0, sizeof(zcplx) * (size_t)ngc * nfs * ntask);        /* :98 */
+  if (nthreads < 1) nthreads = 1;
+  long nop = 0;
+  int nouter = 0;
+  if (ntask >= nthreads && nthreads > 1) {
+    /* perturbations = the reference's "images" (do_stern.f90:199): independent, one per thread */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop) reduction(max : nouter)
+    for (int indx = 0; indx < ntask; ++indx) {
+      orc_stats s1 = {0, 0, 0};
+      int ig = ig_unique[igstart - 1 + indx];
+      int ierr = coulomb_one(sys, cfg, ig, ngc, nfs, fiu, scrcoul + (size_t)ngc * nfs * indx, &s1, 1);
+      if (ierr) {
+#pragma omp critical(orc_ierr2)
+        ierr_all = ierr;
+      }
+      nop += s1.n_op;
+      if (s1.n_outer > nouter) nouter = s1.n_outer;
+    }
+  } else {
+    for (int indx = 0; indx < ntask; ++indx) {
+      orc_stats s1 = {0, 0, 0};
+      int ig = ig_unique[igstart - 1 + indx];
+      int ierr = coulomb_one(sys, cfg, ig, ngc, nfs, fiu, scrcoul + (size_t)ngc * nfs * indx, &s1, nthreads);
+      if (ierr) ierr_all = ierr;
+      nop += s1.n_op;
+      if (s1.n_outer > nouter) nouter = s1.n_outer;
+    }
+  }
+  if (st) {
+    st->n_op += nop;
+    if (nouter > st->n_outer) st->n_outer = nouter;
+  }
+  return ierr_all;
+}
+
+/* coulomb_q0G0.f90:31-158 : head at the shifted q, G = G' = 0 (ig = 1) */
+int orc_coulomb_q0G0(const orc_system *sys, const orc_solver_cfg *cfg, int nfs, const zcplx *fiu, zcplx *eps_m,
+                     orc_stats *st) {
+  zcplx *scr = calloc((size_t)nfs, sizeof(zcplx));
+  int ierr = coulomb_one(sys, cfg, 1, 1, nfs, fiu, scr, st, 1);
+  for (int iw = 0; iw < nfs; ++iw) eps_m[iw] = scr[iw];
+  free(scr);
+  return ierr;
+}
+
+/* unfold_w.f90:84 : out(ig_unique(ig), igp, iw) = CONJG(in(igp, iw, ig)); identity symmetry only */
+void orc_unfold_w(int ngc, int nfs, int ngmunique, const int32_t *ig_unique, const zcplx *in, zcplx *out) {
+  for (int ig = 0; ig < ngmunique; ++ig)
+    for (int iw = 0; iw < nfs; ++iw)
+      for (int igp = 0; igp < ngc; ++igp)
+        out[(ig_unique[ig] - 1) + (size_t)ngc * (igp + (size_t)ngc * iw)] = conj(in[igp + (size_t)ngc * (iw + (size_t)nfs * ig)]);
+}
+
+/* invert_epsilon.f90:23-90 : wings zeroed at Gamma, LU inverse (ZGETRF+ZGETRI semantics), -1 on the diagonal */
+static int zinverse(int n, zcplx *a) {
+  int *piv = malloc(sizeof(int) * n);
+  /* LU with partial pivoting (ZGETF2 order) */
+  for (int j = 0; j < n; ++j) {
+    int p = j;
+    double best = fabs(creal(a[j + (size_t)n * j])) + fabs(cimag(a[j + (size_t)n * j]));
+    for (int i = j + 1; i < n; ++i) {
+      double v = fabs(creal(a[i + (size_t)n * j])) + fabs(cimag(a[i + (size_t)n * j])); /* IZAMAX uses |re|+|im| */
+      if (v > best) { best = v; p = i; }
+    }
+    piv[j] = p;
+    if (best == 0.0) { free(piv); return j + 1; }
+    if (p != j)
+      for (int k = 0; k < n; ++k) { zcplx t = a[j + (size_t)n * k]; a[j + (size_t)n * k] = a[p + (size_t)n * k]; a[p + (size_t)n * k] = t; }
+    zcplx inv = 1.0 / a[j + (size_t)n * j];
+    for (int i = j + 1; i < n; ++i) a[i + (size_t)n * j] *= inv;
+    for (int k = j + 1; k < n; ++k) {
+      zcplx akj = a[j + (size_t)n * k];
+      for (int i = j + 1; i < n; ++i) a[i + (size_t)n * k] -= a[i + (size_t)n * j] * akj;
+    }
+  }
+  /* inverse: solve A X = I column by column using P, L, U */
+  zcplx *inv = malloc(sizeof(zcplx) * (size_t)n * n);
+  zcplx *col = malloc(sizeof(zcplx) * n);
+  for (int c = 0; c < n; ++c) {
+    for (int i = 0; i < n; ++i) col[i] = (i == c) ? 1.0 : 0.0;
+    for (int j = 0; j < n; ++j) if (piv[j] != j) { zcplx t = col[j]; col[j] = col[piv[j]]; col[piv[j]] = t; }
+    for (int j = 0; j < n; ++j) {
+      zcplx cj = col[j];
+      if (cj != 0.0) for (int i = j + 1; i < n; ++i) col[i] -= a[i + (size_t)n * j] * cj;
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      col[j] /= a[j + (size_t)n * j];
+      zcplx cj = col[j];
+      for (int i = 0; i < j; ++i) col[i] -= a[i + (size_t)n * j] * cj;
+    }
+    memcpy(inv + (size_t)n * c, col, sizeof(zcplx) * n);
+  }
+  memcpy(a, inv, sizeof(zcplx) * (size_t)n * n);
+  free(inv); free(col); free(piv);
+  return 0;
+}
+
+int orc_invert_epsilon(int ngc, int nfs, zcplx *s, int lgamma) {
+  const size_t blk = (size_t)ngc * ngc;
+  int info = 0;
+  for (int iw = 0; iw < nfs; ++iw) {
+    zcplx *a = s + blk * iw;
+    if (lgamma) {                                                       /* :46-56 */
+      for (int ig = 1; ig < ngc; ++ig) a[ig] = 0.0;
+      for (int igp = 1; igp < ngc; ++igp) a[(size_t)ngc * igp] = 0.0;
+    }
+    int e = zinverse(ngc, a);                                           /* :59-66 */
+    if (e) info = e;
+    if (lgamma) {                                                       /* :72-81 */
+      for (int ig = 1; ig < ngc; ++ig) a[ig] = 0.0;
+      for (int igp = 1; igp < ngc; ++igp) a[(size_t)ngc * igp] = 0.0;
+    }
+    for (int ig = 0; ig < ngc; ++ig) a[ig + (size_t)ngc * ig] -= 1.0;   /* :84-88 */
+  }
+  return info;
+}
+
+/* ================================================================ green.f90:105-226 */
+int orc_green_function(const orc_grid *g, const orc_kpoint *kp, const orc_solver_cfg *cfg, int ngc,
+                       const int32_t *map, int ngp, const int32_t *fft_map, int nfreq, const zcplx *omega,
+                       zcplx *green, orc_stats *st, int nthreads) {
+  const int num_g = kp->npw;
+  const size_t nnr = (size_t)g->nr1 * g->nr2 * g->nr3;
+  int ierr_all = 0;
+  long nop = 0;
+  int nouter = 0;
+  if (nthreads < 1) nthreads = 1;
+  memset(green, 0, sizeof(zcplx) * (size_t)ngc * ngp * nfreq);          /* :184 */
+  zcplx *msig = malloc(sizeof(zcplx) * nfreq);
+  for (int i = 0; i < nfreq; ++i) msig[i] = -omega[i];                  /* :207 */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop) reduction(max : nouter)
+  for (int igp = 0; igp < ngp; ++igp) {                                 /* :196 */
+    int ig = map[fft_map[igp] - 1];                                     /* :199 */
+    if (ig == 0) continue;
+    orc_pw_op op;
+    op.grid = g;
+    op.kp = kp;
+    op.alpha_pv = 0.0;                                                  /* green_operator :283 */
+    op.work = malloc(sizeof(zcplx) * nnr);
+    op.becp = malloc(sizeof(zcplx) * 2 * (kp->nkb + kp->nbnd_occ + 1));
+    zcplx *bb = calloc(num_g, sizeof(zcplx));
+    zcplx *part = calloc((size_t)num_g * nfreq, sizeof(zcplx));
+    bb[ig - 1] = -1.0;                                                  /* :203-204 */
+    orc_stats s1 = {0, 0, 0};
+    int ierr = orc_select_solver(cfg, orc_pw_apply, &op, num_g, bb, nfreq, msig, part, &s1);
+    if (ierr) {
+#pragma omp critical(orc_ierr3)
+      ierr_all = ierr;
+    }
+    for (int ifreq = 0; ifreq < nfreq; ++ifreq)                         /* :211-213 strict '<' */
+      for (int k = 0; k < ngc; ++k)
+        if (map[k] > 0 && map[k] < num_g)
+          green[k + (size_t)ngc * (igp + (size_t)ngp * ifreq)] = part[(map[k] - 1) + (size_t)num_g * ifreq];
+    nop += s1.n_op;
+    if (s1.n_outer > nouter) nouter = s1.n_outer;
+    free(bb); free(part); free(op.work); free(op.becp);
+  }
+  free(msig);
+  if (st) {
+    st->n_op += nop;
+    if (nouter > st->n_outer) st->n_outer = nouter;
+  }
+  return ierr_all;
+}
