@@ -1,0 +1,142 @@
+/*
+ * sgw_b200.h -- C ABI of the B200-native (sm_100a) Sternheimer hot path.
+ *
+ * Drop-in boundary for QEF/SternheimerGW v0.15: the Fortran driver (phys/coul, phys/green, phys/corr)
+ * stays the host and calls these entry points through ISO_C_BINDING in place of
+ * algo/linear_solver (multishift BiCGStab(l) / SGW subspace solver) and the H.psi it applies.
+ * The reference's plugin point is the procedure-argument callback AA(sigma, x, Ax)
+ * (algo/linear_solver/src/select_solver.f90:77-87); because H.psi lives on the GPU too, the library takes
+ * the operator's DATA at the places where the reference installs it into QE module globals
+ * (phys/coul/src/solve_linter.f90:315-316, phys/green/src/green.f90:88-91, algo/setup/src/gwq_setup.f90:92).
+ *
+ * Conventions:
+ *  - all arrays are HOST pointers owned by the caller (the library copies in/out and owns device memory);
+ *  - Fortran column-major, COMPLEX(dp) = interleaved double[2], index arrays 1-based int32;
+ *  - plane-wave vectors have leading dimension npwx and are zero padded beyond npw;
+ *  - calls are blocking and non-re-entrant per context (the reference keeps its operator in QE globals);
+ *  - solver error codes follow the reference: 0 converged, 1 max_iter reached (bicgstab.f90:249-253,
+ *    linear_solver.f90:176-180), 2 NaN in the solution (bicgstab.f90:264-267, linear_solver.f90:186-190);
+ *    API/CUDA failures are NEGATIVE return values (SGW_E_*), never confused with solver codes;
+ *  - there is NO CPU fallback: without a CUDA device sgw_create fails with SGW_E_CUDA.
+ */
+#ifndef SGW_B200_H
+#define SGW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgw_ctx sgw_ctx;
+typedef struct { double re, im; } sgw_cplx; /* COMPLEX(dp) */
+
+#define SGW_OK 0
+#define SGW_E_ARG (-1)     /* invalid argument */
+#define SGW_E_CUDA (-2)    /* CUDA runtime / driver error (see sgw_last_error) */
+#define SGW_E_STATE (-3)   /* required set_* call missing */
+#define SGW_E_UNSUPPORTED (-4)
+
+/* select_solver_type (algo/linear_solver/src/select_solver.f90:48-62) */
+typedef struct {
+  int32_t npriority;
+  int32_t priority[4]; /* 1 bicgstab multishift, 2 bicgstab without multishift, 3 SGW subspace solver */
+  int32_t max_iter;    /* 10000 */
+  double threshold;    /* 1e-4 */
+  int32_t bicg_lmax;   /* 4 */
+} sgw_solver_cfg;
+
+/* per-call statistics (device counters; labels follow data/timing/src/timing.f90) */
+typedef struct {
+  int64_t n_linear_op;     /* H.psi applications, summed over right-hand sides ("linear operator") */
+  int64_t n_kernel_launch; /* kernels of THIS library launched during the call */
+  int32_t n_outer_max;     /* max outer BiCGStab iterations over the batch */
+  int32_t n_fallback;      /* right-hand sides that fell through to the next solver in the priority list */
+  double ms_solver;        /* device time of the solver part ("coul solver" / "green") */
+  double ms_linear_op;     /* device time inside H.psi (only when profiling is enabled) */
+  double ms_total;         /* device time of the whole call (CUDA events on the library's stream) */
+} sgw_stats;
+
+/* ---- context (once per MPI rank / GPU, after mp_startup, main/src/gw.f90:83) ---- */
+int sgw_create(int device, sgw_ctx **ctx);
+int sgw_destroy(sgw_ctx *ctx);
+const char *sgw_last_error(const sgw_ctx *ctx);
+int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out);        /* stats of the last solver-level call */
+int sgw_set_profiling(sgw_ctx *ctx, int on);                  /* time H.psi separately (adds syncs) */
+int sgw_device_synchronize(sgw_ctx *ctx);
+
+/* ---- L0: FFT grid and local potential (result of set_vrs, gwq_setup.f90:92; QE dffts) ---- */
+int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, int nr3x);
+int sgw_set_vloc(sgw_ctx *ctx, const double *vrs /* nnr */);
+
+/* ---- L1: operator data of one k-point = init_us_2 + g2_kin + globals evq/alpha_pv/nbnd_occ
+ *      (solve_linter.f90:315-316, green.f90:88-91).  slot: caller-chosen id >= 0. ---- */
+int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_igk /* npw, 1-based */,
+                   const double *g2kin /* npw */, int nkb, const sgw_cplx *vkb /* npwx x nkb */,
+                   const double *dion /* nkb x nkb */, int nbnd_occ, const sgw_cplx *evq /* npwx x nbnd_occ */,
+                   double alpha_pv);
+/* dense fake backend of the reference's unit test (linear_solver.pf:106: Ax = MATMUL(A,x) + sigma x) */
+int sgw_set_dense_operator(sgw_ctx *ctx, int slot, int n, const sgw_cplx *A /* n x n */, int lda);
+
+/* linear_op (algo/linear_solver/src/linear_op.f90:46): A_psi = (H + omega S + alpha_pv P_v) psi, batched */
+int sgw_linear_op(sgw_ctx *ctx, int slot, int nvec, const sgw_cplx *omega /* nvec */, double alpha_pv,
+                  const sgw_cplx *psi, int ldpsi, sgw_cplx *apsi, int ldapsi);
+
+/* select_solver (select_solver.f90:67), batched over right-hand sides.
+ * b: ldb x nrhs; sigma: nshift x nrhs (sigma(1,:) = seed system); x element (ig, ishift, irhs) at
+ * x[ig + stride_shift*ishift + stride_rhs*irhs] so that x may alias dpsi(npwx, nbnd, num_omega)
+ * (solve_linter.f90:368-369: stride_rhs = npwx, stride_shift = npwx*nbnd).  use_alpha_pv = 0 gives
+ * green_operator (green.f90:283), 1 coulomb_operator (solve_linter.f90:708).  ierr: nrhs entries. */
+int sgw_solve_multishift(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int use_alpha_pv, int nrhs,
+                         const sgw_cplx *b, int ldb, int nshift, const sgw_cplx *sigma, sgw_cplx *x,
+                         int64_t stride_shift, int64_t stride_rhs, int32_t *ierr);
+
+/* ---- L2/L3: screened Coulomb (phys/coul) ---- */
+/* cell + density-sphere data used by dv_of_drho / coulomb: gvect g, dffts%nl, qpoint xq, cell omega, tpiba2 */
+int sgw_set_system(sgw_ctx *ctx, double omega_cell, double tpiba2, int ngm, const double *g /* 3 x ngm */,
+                   const int32_t *nl /* ngm, 1-based */);
+int sgw_set_q(sgw_ctx *ctx, const double *xq /* 3 */);
+/* number of (k, k+q) pairs of this pool (qpoint nksq) and the data of one pair: slot_kq must have been
+ * set with sgw_set_kpoint; evc(npwx, nbnd) at k with its nl map, eigenvalues et(nbnd), weight wk(ikk) */
+int sgw_set_nksq(sgw_ctx *ctx, int nksq);
+int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *nl_igk_k, int nbnd,
+                  const sgw_cplx *evc, const double *et, double wk);
+
+/* solve_linter (phys/coul/src/solve_linter.f90:55), direct branch (num_iter = 1):
+ * dvbarein(nnr) real-space perturbation, freq(nfreq) -> drhoscf(nnr, nfreq) = -dV_H.  ierr_out: solver code. */
+int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, const sgw_cplx *dvbarein, int nfreq,
+                     const sgw_cplx *freq, sgw_cplx *drhoscf, int32_t *ierr_out);
+/* coulomb (phys/coul/src/coulomb.f90:29): perturbations igstart..igstart+ntask-1 of ig_unique, batched over
+ * perturbations x k x bands.  scrcoul(ngc, nfs, ntask). */
+int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, int ntask,
+                const int32_t *ig_unique, int nfs, const sgw_cplx *fiu, sgw_cplx *scrcoul, int32_t *ierr_out);
+/* coulomb_q0G0 (phys/coul/src/coulomb_q0G0.f90:31): head element at the (shifted) q currently set */
+int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw_cplx *fiu, sgw_cplx *eps_m,
+                     int32_t *ierr_out);
+/* unfold_w (algo/symmetry/src/unfold_w.f90:84, identity-symmetry case) and invert_epsilon
+ * (phys/coul/src/invert_epsilon.f90:23): scrcoul_g(ngc, ngc, nfs) in place */
+int sgw_unfold_w(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *ig_unique,
+                 const sgw_cplx *scrcoul_in /* ngc x nfs x ngmunique */, sgw_cplx *scrcoul_out /* ngc x ngc x nfs */);
+int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrcoul_g, int lgamma);
+
+/* ---- L2': Green's function (phys/green/src/green.f90:105) ----
+ * green(ngc, ngp, nfreq): for every igp, b = -e_{map(fft_map(igp))}, shifts -omega; rows scattered through map
+ * with the reference's strict mask (map > 0 .AND. map < num_g, green.f90:212). */
+int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ngc, const int32_t *map,
+                       int ngp, const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green,
+                       int32_t *ierr_out);
+
+/* ---- data/parallel/src/parallel.f90:80 parallel_task: contiguous blocks, remainder to the LAST ranks.
+ * rank 0-based; first/last 1-based; num_task[nproc]. ---- */
+int sgw_parallel_task(int nproc, int rank, int num_task_total, int32_t *first_task, int32_t *last_task,
+                      int32_t *num_task);
+
+/* micro-benchmark hooks (device-resident, no host copies inside): apply the operator `reps` times to
+ * nvec resident random vectors; returns device milliseconds per repetition of each part. */
+int sgw_bench_linear_op(sgw_ctx *ctx, int slot, int nvec, int reps, double *ms_total, double *ms_fft,
+                        double *ms_gemm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGW_B200_H */

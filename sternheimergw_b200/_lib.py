@@ -1,0 +1,76 @@
+"""ctypes binding of libsgw_b200.so -- exactly the entry points include/sgw_b200.h declares."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libsgw_b200.so"
+
+c_int, c_double, c_void_p, c_int64 = C.c_int, C.c_double, C.c_void_p, C.c_int64
+
+# every symbol of include/sgw_b200.h (tests/test_abi.py checks the list against the header)
+SYMBOLS = [
+    "sgw_create", "sgw_destroy", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_device_synchronize",
+    "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
+    "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_solve_linter",
+    "sgw_coulomb", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
+    "sgw_parallel_task", "sgw_bench_linear_op",
+]
+
+
+class SolverCfg(C.Structure):
+    """sgw_solver_cfg == select_solver_type (select_solver.f90:48-62)."""
+    _fields_ = [("npriority", C.c_int32), ("priority", C.c_int32 * 4), ("max_iter", C.c_int32),
+                ("threshold", c_double), ("bicg_lmax", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_linear_op", c_int64), ("n_kernel_launch", c_int64), ("n_outer_max", C.c_int32),
+                ("n_fallback", C.c_int32), ("ms_solver", c_double), ("ms_linear_op", c_double), ("ms_total", c_double)]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.sgw_last_error.restype = C.c_char_p
+        L.sgw_last_error.argtypes = [c_void_p]
+        L.sgw_create.argtypes = [c_int, C.POINTER(c_void_p)]
+        L.sgw_destroy.argtypes = [c_void_p]
+        L.sgw_get_stats.argtypes = [c_void_p, C.POINTER(Stats)]
+        L.sgw_set_profiling.argtypes = [c_void_p, c_int]
+        L.sgw_device_synchronize.argtypes = [c_void_p]
+        L.sgw_set_grid.argtypes = [c_void_p] + [c_int] * 6
+        L.sgw_set_vloc.argtypes = [c_void_p, c_void_p]
+        L.sgw_set_kpoint.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_int, c_void_p, c_double]
+        L.sgw_set_dense_operator.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int]
+        L.sgw_linear_op.argtypes = [c_void_p, c_int, c_int, c_void_p, c_double, c_void_p, c_int, c_void_p, c_int]
+        L.sgw_solve_multishift.argtypes = [c_void_p, c_int, C.POINTER(SolverCfg), c_int, c_int, c_void_p, c_int, c_int,
+                                           c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+        L.sgw_set_system.argtypes = [c_void_p, c_double, c_double, c_int, c_void_p, c_void_p]
+        L.sgw_set_q.argtypes = [c_void_p, c_void_p]
+        L.sgw_set_nksq.argtypes = [c_void_p, c_int]
+        L.sgw_set_kpair.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_double]
+        L.sgw_solve_linter.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p]
+        L.sgw_coulomb.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_void_p]
+        L.sgw_coulomb_q0G0.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_void_p, c_void_p, c_void_p]
+        L.sgw_unfold_w.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.sgw_invert_epsilon.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int]
+        L.sgw_green_function.argtypes = [c_void_p, c_int, C.POINTER(SolverCfg), c_int, c_void_p, c_int, c_void_p,
+                                         c_int, c_void_p, c_void_p, c_void_p]
+        L.sgw_parallel_task.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.sgw_bench_linear_op.argtypes = [c_void_p, c_int, c_int, c_int, C.POINTER(c_double), C.POINTER(c_double),
+                                          C.POINTER(c_double)]
+        _lib = L
+    return _lib

@@ -1,0 +1,416 @@
+// api.cu -- C-ABI entry points (include/sgw_b200.h): context, operator installation, linear_op and
+// the batched select_solver replacement.  Host arrays in, host arrays out; all device memory is owned here.
+#include "internal.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+using namespace sgw;
+
+namespace sgw {
+
+int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 16;
+  auto it = ctx->ws.bufs.find(name);
+  if (it != ctx->ws.bufs.end() && it->second.second >= bytes) {
+    *out = it->second.first;
+    return SGW_OK;
+  }
+  if (it != ctx->ws.bufs.end()) {
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(it->second.first);
+    ctx->ws.bufs.erase(it);
+  }
+  void *p = nullptr;
+  size_t want = bytes + bytes / 8;   // a little slack so that slowly growing batches do not reallocate every call
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes for workspace '%s' failed: %s", bytes, name, cudaGetErrorString(e));
+    ctx->err = buf;
+    return SGW_E_CUDA;
+  }
+  ctx->ws.bufs[name] = std::make_pair(p, want);
+  *out = p;
+  return SGW_OK;
+}
+
+void ws_free_all(sgw_ctx *ctx) {
+  for (auto &kv : ctx->ws.bufs) cudaFree(kv.second.first);
+  ctx->ws.bufs.clear();
+}
+
+static void free_slot(KSlot &k) {
+  free_sphere(&k.sph);
+  if (k.d_g2kin) cudaFree(k.d_g2kin);
+  if (k.d_P) cudaFree(k.d_P);
+  if (k.d_dion) cudaFree(k.d_dion);
+  if (k.d_A) cudaFree(k.d_A);
+  k = KSlot();
+}
+
+static void free_pair(KPair &p) {
+  free_sphere(&p.sph_k);
+  if (p.d_evc) cudaFree(p.d_evc);
+  p = KPair();
+}
+
+void begin_call(sgw_ctx *ctx) {
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->launches = 0;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+}
+
+void end_call(sgw_ctx *ctx) {
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  cudaEventSynchronize(ctx->ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.ms_total = ms;
+  ctx->stats.n_kernel_launch = ctx->launches;
+}
+
+}  // namespace sgw
+
+extern "C" {
+
+int sgw_create(int device, sgw_ctx **out) {
+  if (!out) return SGW_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SGW_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SGW_E_CUDA;
+  sgw_ctx *ctx = new sgw_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SGW_E_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGW_E_CUDA; }
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  *out = ctx;
+  return SGW_OK;
+}
+
+int sgw_destroy(sgw_ctx *ctx) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &k : ctx->slots) free_slot(k);
+  for (auto &p : ctx->pairs) free_pair(p);
+  for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
+  ws_free_all(ctx);
+  if (ctx->d_twx) cudaFree(ctx->d_twx);
+  if (ctx->d_twy) cudaFree(ctx->d_twy);
+  if (ctx->d_twz) cudaFree(ctx->d_twz);
+  if (ctx->d_vperm) cudaFree(ctx->d_vperm);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SGW_OK;
+}
+
+const char *sgw_last_error(const sgw_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out) {
+  if (!ctx || !out) return SGW_E_ARG;
+  *out = ctx->stats;
+  return SGW_OK;
+}
+
+int sgw_set_profiling(sgw_ctx *ctx, int on) {
+  if (!ctx) return SGW_E_ARG;
+  ctx->profiling = on != 0;
+  return SGW_OK;
+}
+
+int sgw_device_synchronize(sgw_ctx *ctx) {
+  if (!ctx) return SGW_E_ARG;
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGW_OK;
+}
+
+static int upload_twiddle(sgw_ctx *ctx, int n, cplx **d) {
+  std::vector<cplx> tw(n);
+  for (int m = 0; m < n; ++m) {
+    // exact quadrant symmetry via sincospi-like evaluation in long double
+    const long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)m / (long double)n;
+    tw[m].x = (double)cosl(a);
+    tw[m].y = (double)sinl(a);
+  }
+  return upload(ctx, d, tw.data(), tw.size());
+}
+
+int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, int nr3x) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(nr1 > 0 && nr2 > 0 && nr3 > 0, "grid dimensions must be positive");
+  if (nr1x != nr1 || nr2x != nr2 || nr3x != nr3) {
+    ctx->err = "padded FFT boxes (nr1x != nr1) are not supported";
+    return SGW_E_UNSUPPORTED;
+  }
+  if (!make_plan(nr1, &ctx->px) || !make_plan(nr2, &ctx->py) || !make_plan(nr3, &ctx->pz)) {
+    ctx->err = "FFT dimension not of the form r1*r2 with radices in {1,2,3,4,5,6,8,9,10,12,15,16}";
+    return SGW_E_UNSUPPORTED;
+  }
+  ctx->nr1 = nr1; ctx->nr2 = nr2; ctx->nr3 = nr3;
+  SGW_CHECK(upload_twiddle(ctx, nr1, &ctx->d_twx));
+  SGW_CHECK(upload_twiddle(ctx, nr2, &ctx->d_twy));
+  SGW_CHECK(upload_twiddle(ctx, nr3, &ctx->d_twz));
+  auto mk = [](const Plan1D &p, std::vector<int> &perm) {
+    perm.resize(p.n);
+    for (int i = 0; i < p.n; ++i) perm[i] = perm_index(p.r1, p.r2, i);
+  };
+  mk(ctx->px, ctx->permx); mk(ctx->py, ctx->permy); mk(ctx->pz, ctx->permz);
+  ctx->grid_set = true;
+  ctx->vloc_set = false;
+  for (auto &k : ctx->slots) free_slot(k);
+  for (auto &p : ctx->pairs) free_pair(p);
+  for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
+  ctx->rho_spheres.clear();
+  return SGW_OK;
+}
+
+int sgw_set_vloc(sgw_ctx *ctx, const double *vrs) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(vrs != nullptr, "vrs is null");
+  if (!ctx->grid_set) { ctx->err = "sgw_set_grid must be called first"; return SGW_E_STATE; }
+  const int nx = ctx->nr1, ny = ctx->nr2, nz = ctx->nr3;
+  std::vector<double> vp((size_t)nx * ny * nz);
+  for (int pz = 0; pz < nz; ++pz)
+    for (int py = 0; py < ny; ++py)
+      for (int pxi = 0; pxi < nx; ++pxi)
+        vp[((size_t)pz * ny + py) * nx + pxi] = vrs[ctx->permx[pxi] + (size_t)nx * (ctx->permy[py] + (size_t)ny * ctx->permz[pz])];
+  SGW_CHECK(upload(ctx, &ctx->d_vperm, vp.data(), vp.size()));
+  ctx->vloc_set = true;
+  return SGW_OK;
+}
+
+static KSlot *get_slot(sgw_ctx *ctx, int slot) {
+  if (slot < 0 || slot > (1 << 20)) return nullptr;
+  if ((int)ctx->slots.size() <= slot) ctx->slots.resize(slot + 1);
+  return &ctx->slots[slot];
+}
+
+int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_igk, const double *g2kin, int nkb,
+                   const sgw_cplx *vkb, const double *dion, int nbnd_occ, const sgw_cplx *evq, double alpha_pv) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->grid_set) { ctx->err = "sgw_set_grid must be called first"; return SGW_E_STATE; }
+  SGW_ARG(npw > 0 && npwx >= npw, "need 0 < npw <= npwx");
+  SGW_ARG(nl_igk && g2kin, "nl_igk / g2kin null");
+  SGW_ARG(nkb >= 0 && nbnd_occ >= 0, "negative nkb / nbnd_occ");
+  SGW_ARG(nkb == 0 || (vkb && dion), "vkb / dion null");
+  SGW_ARG(nbnd_occ == 0 || evq, "evq null");
+  KSlot *k = get_slot(ctx, slot);
+  SGW_ARG(k != nullptr, "bad slot");
+  free_slot(*k);
+  SGW_CHECK(build_sphere(ctx, npw, nl_igk, &k->sph));
+  k->npw = npw; k->npwx = npwx; k->nkb = nkb; k->nbnd = nbnd_occ; k->alpha_pv = alpha_pv;
+  const std::vector<int> &perm = k->sph.perm;
+  std::vector<double> g2(npwx, 0.0);
+  for (int p = 0; p < npw; ++p) g2[p] = g2kin[perm[p]];
+  SGW_CHECK(upload(ctx, &k->d_g2kin, g2.data(), g2.size()));
+  const int m = nkb + nbnd_occ;
+  if (m > 0) {
+    std::vector<cplx> P((size_t)npwx * m, cmake(0.0, 0.0));
+    const cplx *v = (const cplx *)vkb, *e = (const cplx *)evq;
+    for (int j = 0; j < nkb; ++j)
+      for (int p = 0; p < npw; ++p) P[(size_t)j * npwx + p] = v[(size_t)j * npwx + perm[p]];
+    for (int j = 0; j < nbnd_occ; ++j)
+      for (int p = 0; p < npw; ++p) P[(size_t)(nkb + j) * npwx + p] = e[(size_t)j * npwx + perm[p]];
+    SGW_CHECK(upload(ctx, &k->d_P, P.data(), P.size()));
+  }
+  if (nkb > 0) SGW_CHECK(upload(ctx, &k->d_dion, dion, (size_t)nkb * nkb));
+  k->set = true;
+  k->dense = false;
+  return SGW_OK;
+}
+
+int sgw_set_dense_operator(sgw_ctx *ctx, int slot, int n, const sgw_cplx *A, int lda) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(n > 0 && A && lda >= n, "bad dense operator");
+  KSlot *k = get_slot(ctx, slot);
+  SGW_ARG(k != nullptr, "bad slot");
+  free_slot(*k);
+  std::vector<cplx> a((size_t)n * n);
+  for (int j = 0; j < n; ++j) memcpy(&a[(size_t)j * n], (const cplx *)A + (size_t)j * lda, sizeof(cplx) * n);
+  SGW_CHECK(upload(ctx, &k->d_A, a.data(), a.size()));
+  k->npw = k->npwx = n;
+  k->sph.npw = n;
+  k->sph.perm.resize(n);
+  std::vector<int> id(n);
+  for (int i = 0; i < n; ++i) id[i] = k->sph.perm[i] = i;
+  SGW_CHECK(upload(ctx, &k->sph.d_perm, id.data(), id.size()));
+  k->dense = true;
+  k->set = true;
+  return SGW_OK;
+}
+
+int sgw_linear_op(sgw_ctx *ctx, int slot, int nvec, const sgw_cplx *omega, double alpha_pv, const sgw_cplx *psi, int ldpsi,
+                  sgw_cplx *apsi, int ldapsi) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(nvec > 0 && omega && psi && apsi, "null argument");
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
+  const KSlot &k = ctx->slots[slot];
+  SGW_ARG(ldpsi >= k.npw && ldapsi >= k.npw, "leading dimension smaller than npw");
+  begin_call(ctx);
+  const long n = k.npwx;
+  cplx *d_in = nullptr, *d_psi = nullptr, *d_out = nullptr, *d_om = nullptr;
+  SGW_CHECK(ws(ctx, "io_in", (size_t)std::max(ldpsi, ldapsi) * nvec, &d_in));
+  SGW_CHECK(ws(ctx, "lo_psi", (size_t)n * nvec, &d_psi));
+  SGW_CHECK(ws(ctx, "lo_out", (size_t)n * nvec, &d_out));
+  SGW_CHECK(ws(ctx, "lo_om", (size_t)nvec, &d_om));
+  SGW_CUDA(cudaMemcpyAsync(d_in, psi, sizeof(cplx) * (size_t)ldpsi * nvec, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(d_om, omega, sizeof(cplx) * nvec, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CHECK(permute_in(ctx, k.sph, nvec, d_in, ldpsi, d_psi, n, (int)n));
+  SGW_CHECK(apply_operator(ctx, slot, alpha_pv, nvec, d_psi, n, d_om, 1, d_out, n, nullptr));
+  // A_psi is INTENT(OUT): rows beyond npw are defined (zero) like the reference's zero padded arrays
+  SGW_CUDA(cudaMemsetAsync(d_in, 0, sizeof(cplx) * (size_t)ldapsi * nvec, ctx->stream));
+  SGW_CHECK(permute_out(ctx, k.sph, nvec, d_out, n, d_in, ldapsi));
+  SGW_CUDA(cudaMemcpyAsync(apsi, d_in, sizeof(cplx) * (size_t)ldapsi * nvec, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.n_linear_op = nvec;
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_solve_multishift(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int use_alpha_pv, int nrhs, const sgw_cplx *b,
+                         int ldb, int nshift, const sgw_cplx *sigma, sgw_cplx *x, int64_t stride_shift, int64_t stride_rhs,
+                         int32_t *ierr) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(cfg && b && sigma && x && ierr, "null argument");
+  SGW_ARG(nrhs > 0 && nshift > 0, "need nrhs > 0 and nshift > 0");
+  SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");   // select_solver.f90:116-118
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
+  const KSlot &k = ctx->slots[slot];
+  SGW_ARG(ldb >= k.npw, "ldb smaller than npw");
+  SGW_ARG(stride_shift >= k.npw || nshift == 1, "stride_shift smaller than npw");
+  begin_call(ctx);
+  const long n = k.npwx;
+  cplx *d_in = nullptr, *d_b = nullptr, *d_sig = nullptr, *d_x = nullptr;
+  int *d_ierr = nullptr;
+  SGW_CHECK(ws(ctx, "io_in", (size_t)ldb * nrhs, &d_in));
+  SGW_CHECK(ws(ctx, "sv_b", (size_t)n * nrhs, &d_b));
+  SGW_CHECK(ws(ctx, "sv_sig", (size_t)nshift * nrhs, &d_sig));
+  SGW_CHECK(ws(ctx, "sv_x", (size_t)n * nshift * nrhs, &d_x));
+  SGW_CHECK(ws(ctx, "sv_ierr", (size_t)nrhs, &d_ierr));
+  SGW_CUDA(cudaMemcpyAsync(d_in, b, sizeof(cplx) * (size_t)ldb * nrhs, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(d_sig, sigma, sizeof(cplx) * (size_t)nshift * nrhs, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CHECK(permute_in(ctx, k.sph, nrhs, d_in, ldb, d_b, n, (int)n));
+  SolveBatch sb;
+  sb.slot = slot;
+  sb.alpha_pv = use_alpha_pv ? k.alpha_pv : 0.0;
+  sb.nrhs = nrhs; sb.nshift = nshift; sb.n = (int)n;
+  sb.d_b = d_b; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  SGW_CHECK(select_solver_batched(ctx, sb, cfg));
+  cudaEventRecord(ctx->ev3, ctx->stream);
+  // x is INTENT(OUT): un-permute every (rhs, shift) vector into the caller's strided layout
+  cplx *d_xo = nullptr;
+  SGW_CHECK(ws(ctx, "sv_xo", (size_t)k.npw * nshift * nrhs, &d_xo));
+  SGW_CHECK(permute_out(ctx, k.sph, nrhs * nshift, d_x, n, d_xo, k.npw));
+  std::vector<cplx> hx((size_t)k.npw * nshift * nrhs);
+  SGW_CUDA(cudaMemcpyAsync(hx.data(), d_xo, sizeof(cplx) * hx.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(ierr, d_ierr, sizeof(int) * nrhs, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < nrhs; ++r)
+    for (int s = 0; s < nshift; ++s)
+      memcpy((cplx *)x + (size_t)r * stride_rhs + (size_t)s * stride_shift, &hx[((size_t)r * nshift + s) * k.npw],
+             sizeof(cplx) * k.npw);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+  end_call(ctx);
+  ctx->stats.ms_solver = ms;
+  return SGW_OK;
+}
+
+int sgw_parallel_task(int nproc, int rank, int num_task_total, int32_t *first_task, int32_t *last_task, int32_t *num_task) {
+  if (nproc <= 0 || rank < 0 || rank >= nproc || num_task_total < 0 || !first_task || !last_task || !num_task) return SGW_E_ARG;
+  const int nmin = num_task_total / nproc;          // parallel.f90:121
+  const int nrem = num_task_total % nproc;          // :124
+  const int last_proc = nproc - nrem;               // :127  (the LAST ranks take the extra task)
+  int sum = 0;
+  for (int p = 0; p < nproc; ++p) {
+    num_task[p] = p < last_proc ? nmin : nmin + 1;
+    if (p <= rank) sum += num_task[p];
+  }
+  *last_task = sum;                                 // :133
+  *first_task = sum - num_task[rank] + 1;           // :134
+  return SGW_OK;
+}
+
+int sgw_bench_linear_op(sgw_ctx *ctx, int slot, int nvec, int reps, double *ms_total, double *ms_fft, double *ms_gemm) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(nvec > 0 && reps > 0, "nvec, reps must be positive");
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set || ctx->slots[slot].dense) { ctx->err = "plane-wave slot not set"; return SGW_E_STATE; }
+  const KSlot &k = ctx->slots[slot];
+  const long n = k.npwx;
+  cplx *d_psi = nullptr, *d_out = nullptr, *d_om = nullptr, *T1 = nullptr, *T2 = nullptr;
+  SGW_CHECK(ws(ctx, "lo_psi", (size_t)n * nvec, &d_psi));
+  SGW_CHECK(ws(ctx, "lo_out", (size_t)n * nvec, &d_out));
+  SGW_CHECK(ws(ctx, "lo_om", (size_t)nvec, &d_om));
+  {
+    std::vector<cplx> h((size_t)n * nvec, cmake(0.0, 0.0));
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    for (int v = 0; v < nvec; ++v)
+      for (int p = 0; p < k.npw; ++p) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const double a = (double)((st >> 11) & 0xFFFFF) / 1048576.0 - 0.5;
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const double b2 = (double)((st >> 11) & 0xFFFFF) / 1048576.0 - 0.5;
+        h[(size_t)v * n + p] = cmake(a, b2);
+      }
+    SGW_CUDA(cudaMemcpyAsync(d_psi, h.data(), sizeof(cplx) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<cplx> om(nvec, cmake(0.1, 0.05));
+    SGW_CUDA(cudaMemcpyAsync(d_om, om.data(), sizeof(cplx) * nvec, cudaMemcpyHostToDevice, ctx->stream));
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  const size_t tsz = (size_t)nvec * ctx->nr3 * k.sph.ncol;
+  SGW_CHECK(ws(ctx, "fft_T1", tsz, &T1));
+  SGW_CHECK(ws(ctx, "fft_T2", tsz, &T2));
+  float ms = 0.f;
+  // warm-up
+  for (int r = 0; r < 3; ++r) SGW_CHECK(apply_operator(ctx, slot, k.alpha_pv, nvec, d_psi, n, d_om, 1, d_out, n, nullptr));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  for (int r = 0; r < reps; ++r) SGW_CHECK(apply_operator(ctx, slot, k.alpha_pv, nvec, d_psi, n, d_om, 1, d_out, n, nullptr));
+  cudaEventRecord(ctx->ev3, ctx->stream);
+  SGW_CUDA(cudaEventSynchronize(ctx->ev3));
+  cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+  if (ms_total) *ms_total = ms / reps;
+  ZEpilogue epi;
+  epi.mode = 1; epi.g2kin = k.d_g2kin; epi.psi = d_psi; epi.sigma = d_om; epi.sigma_stride = 1; epi.keep_out = 1;
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  for (int r = 0; r < reps; ++r) {
+    SGW_CHECK(fft_zpass_g2r(ctx, k.sph, nvec, d_psi, n, T1, nullptr));
+    SGW_CHECK(fft_plane(ctx, PLANE_VLOC, &k.sph, &k.sph, nvec, T1, T2, nullptr, 1, nullptr, nullptr));
+    SGW_CHECK(fft_zpass_r2g(ctx, k.sph, nvec, T2, d_out, n, epi, nullptr));
+  }
+  cudaEventRecord(ctx->ev3, ctx->stream);
+  SGW_CUDA(cudaEventSynchronize(ctx->ev3));
+  cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+  if (ms_fft) *ms_fft = ms / reps;
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  for (int r = 0; r < reps; ++r) SGW_CHECK(nonlocal_apply(ctx, k, k.alpha_pv, nvec, d_psi, n, d_out, n, nullptr));
+  cudaEventRecord(ctx->ev3, ctx->stream);
+  SGW_CUDA(cudaEventSynchronize(ctx->ev3));
+  cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+  if (ms_gemm) *ms_gemm = ms / reps;
+  return SGW_OK;
+}
+
+}  // extern "C"

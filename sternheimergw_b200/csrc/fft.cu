@@ -1,0 +1,334 @@
+// fft.cu -- batched, sphere-pruned 3-D complex-FP64 FFT pipeline for the local-potential part of H.psi,
+// dV.psi (dvqpsi_us.f90:99-130) and the Delta-rho accumulation ([QE] vloc_psi_k / incdrhoscf semantics).
+//
+// Decomposition (per vector):   z-pass over sphere columns  ->  fused 2-D plane kernel  ->  z-pass
+//   k_zpass_g2r : gather a chunk of (x,y) columns of the sphere into shared memory, inverse 1-D FFT along z,
+//                 write T[vec][pz][col]                    (only the ~pi r^2 non-empty columns are touched)
+//   k_plane     : one CTA per (vec, z-plane): scatter the columns into an nx*ny shared-memory plane, inverse
+//                 FFT along y (only x-columns that hold data) and x, multiply by v(r) (or a complex field),
+//                 forward FFT along x and y (only needed columns), gather the output sphere's columns
+//   k_zpass_r2g : forward 1-D FFT along z per column, scale 1/nnr, fused H.psi epilogue
+//                 (kinetic + sigma*psi + non-local part already in `out`)
+// Real space is held in the radix-permuted order of fft_core.h; nothing leaves the chip between the inverse
+// and the forward 2-D transform, so per vector the HBM traffic is ~4 x ncol*nz*16 B instead of the 12 full
+// box sweeps of an unfused 3-D FFT (SURVEY.md section 8d counts 192*nnr + 32*N algorithmic bytes).
+#include "internal.cuh"
+
+#include <algorithm>
+
+namespace sgw {
+
+constexpr int ZCB = 16;        // columns per CTA in the z passes
+constexpr int ZTHREADS = 128;
+constexpr int PTHREADS = 256;
+
+__global__ void __launch_bounds__(ZTHREADS) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
+                                                         cplx *__restrict__ T, const int *__restrict__ active) {
+  const int vec = blockIdx.y;
+  if (active && !active[vec]) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int c0 = blockIdx.x * ZCB;
+  const int nc = min(ZCB, s.ncol - c0);
+  extern __shared__ cplx sm[];
+  const int pitch = g.nz | 1;
+  cplx *lines = sm;
+  cplx *tw = sm + ZCB * pitch;
+  for (int i = tid; i < ZCB * pitch; i += nt) lines[i] = cmake(0.0, 0.0);
+  for (int i = tid; i < g.nz; i += nt) tw[i] = g.twz[i];
+  __syncthreads();
+  const int p0 = s.col_ptr[c0], p1 = s.col_ptr[c0 + nc];
+  const cplx *src = in + (long)vec * ld;
+  for (int p = p0 + tid; p < p1; p += nt) lines[(s.colof[p] - c0) * pitch + s.zof[p]] = src[p];
+  __syncthreads();
+  run_strided<+1>(g.rz1, lines, nc, nullptr, pitch, 1, g.rz2, tw, g.rz2 > 1, tid, nt);
+  __syncthreads();
+  if (g.rz2 > 1) {
+    run_contig<+1>(g.rz2, lines, nc, nullptr, pitch, 1, g.rz1, tw, false, tid, nt);
+    __syncthreads();
+  }
+  cplx *dst = T + (long)vec * g.nz * s.ncol + c0;
+  for (int i = tid; i < nc * g.nz; i += nt) {
+    const int c = i % nc, pz = i / nc;
+    dst[(long)pz * s.ncol + c] = lines[c * pitch + pz];
+  }
+}
+
+__global__ void __launch_bounds__(ZTHREADS) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
+                                                         cplx *__restrict__ out, long ld, ZEpilogue epi, double scale,
+                                                         const int *__restrict__ active) {
+  const int vec = blockIdx.y;
+  if (active && !active[vec]) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int c0 = blockIdx.x * ZCB;
+  const int nc = min(ZCB, s.ncol - c0);
+  extern __shared__ cplx sm[];
+  const int pitch = g.nz | 1;
+  cplx *lines = sm;
+  cplx *tw = sm + ZCB * pitch;
+  for (int i = tid; i < g.nz; i += nt) tw[i] = g.twz[i];
+  const cplx *src = T + (long)vec * g.nz * s.ncol + c0;
+  for (int i = tid; i < nc * g.nz; i += nt) {
+    const int c = i % nc, pz = i / nc;
+    lines[c * pitch + pz] = src[(long)pz * s.ncol + c];
+  }
+  __syncthreads();
+  if (g.rz2 > 1) {
+    run_contig<-1>(g.rz2, lines, nc, nullptr, pitch, 1, g.rz1, tw, true, tid, nt);
+    __syncthreads();
+  }
+  run_strided<-1>(g.rz1, lines, nc, nullptr, pitch, 1, g.rz2, tw, false, tid, nt);
+  __syncthreads();
+  const int p0 = s.col_ptr[c0], p1 = s.col_ptr[c0 + nc];
+  cplx *dst = out + (long)vec * ld;
+  cplx sg = cmake(0.0, 0.0);
+  if (epi.mode == 1 && epi.sigma) sg = epi.sigma[(long)vec * epi.sigma_stride];
+  for (int p = p0 + tid; p < p1; p += nt) {
+    cplx val = cscale(scale, lines[(s.colof[p] - c0) * pitch + s.zof[p]]);
+    if (epi.mode == 0) {
+      dst[p] = val;
+    } else if (epi.mode == 1) {
+      const cplx ps = epi.psi[(long)vec * ld + p];
+      cplx o = epi.keep_out ? dst[p] : cmake(0.0, 0.0);
+      // (H + sigma) psi = g2kin psi + V_loc psi + [non-local, already in o] + sigma psi
+      val = cadd(cscale(epi.g2kin[p], ps), val);
+      val = cadd(val, o);
+      dst[p] = cfma(sg, ps, val);
+    } else {
+      dst[p] = cadd(dst[p], val);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
+                                                     cplx *__restrict__ Tout, const double *__restrict__ vperm,
+                                                     const cplx *__restrict__ field, int vec_per_field, cplx *R,
+                                                     const int *__restrict__ active) {
+  const int vec = blockIdx.y, pz = blockIdx.x;
+  if (active && !active[vec]) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  extern __shared__ cplx sm[];
+  const int pitch = g.pitchx, nx = g.nx, ny = g.ny;
+  cplx *plane = sm;
+  cplx *twx = sm + ny * pitch;
+  cplx *twy = twx + nx;
+  for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
+  for (int i = tid; i < ny; i += nt) twy[i] = g.twy[i];
+  const long nxy = (long)nx * ny;
+
+  if (MODE != PLANE_FROM_R) {
+    for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
+    __syncthreads();
+    const cplx *row = Tin + ((long)vec * g.nz + pz) * sin.ncol;
+    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_y[c] * pitch + sin.col_x[c]] = row[c];
+    __syncthreads();
+    // inverse along y for the x columns that hold data (x still in natural order)
+    run_strided<+1>(g.ry1, plane, sin.nxs, sin.xs, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
+    __syncthreads();
+    if (g.ry2 > 1) {
+      run_contig<+1>(g.ry2, plane, sin.nxs, sin.xs, 1, pitch, g.ry1, twy, false, tid, nt);
+      __syncthreads();
+    }
+    // inverse along x for all rows
+    run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
+    __syncthreads();
+    if (g.rx2 > 1) {
+      run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+      __syncthreads();
+    }
+  } else {
+    __syncthreads();
+  }
+
+  if (MODE == PLANE_VLOC) {
+    const double *v = vperm + (long)pz * nxy;
+    for (int i = tid; i < nx * ny; i += nt) {
+      const int ix = i % nx, iy = i / nx;
+      plane[iy * pitch + ix] = cscale(v[i], plane[iy * pitch + ix]);
+    }
+  } else if (MODE == PLANE_FIELD) {
+    const cplx *f = field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy;
+    for (int i = tid; i < nx * ny; i += nt) {
+      const int ix = i % nx, iy = i / nx;
+      plane[iy * pitch + ix] = cmul(f[i], plane[iy * pitch + ix]);
+    }
+  } else if (MODE == PLANE_TO_R) {
+    cplx *r = R + ((long)vec * g.nz + pz) * nxy;
+    for (int i = tid; i < nx * ny; i += nt) {
+      const int ix = i % nx, iy = i / nx;
+      r[i] = plane[iy * pitch + ix];
+    }
+    return;
+  } else {  // PLANE_FROM_R
+    const cplx *r = R + ((long)vec * g.nz + pz) * nxy;
+    for (int i = tid; i < nx * ny; i += nt) {
+      const int ix = i % nx, iy = i / nx;
+      plane[iy * pitch + ix] = r[i];
+    }
+  }
+  __syncthreads();
+
+  // forward along x (permuted in -> natural out), all rows
+  if (g.rx2 > 1) {
+    run_contig<-1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
+    __syncthreads();
+  }
+  run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
+  __syncthreads();
+  // forward along y only for the x columns of the output sphere
+  if (g.ry2 > 1) {
+    run_contig<-1>(g.ry2, plane, sout.nxs, sout.xs, 1, pitch, g.ry1, twy, true, tid, nt);
+    __syncthreads();
+  }
+  run_strided<-1>(g.ry1, plane, sout.nxs, sout.xs, 1, pitch, g.ry2, twy, false, tid, nt);
+  __syncthreads();
+  cplx *orow = Tout + ((long)vec * g.nz + pz) * sout.ncol;
+  for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_y[c] * pitch + sout.col_x[c]];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+GridDev grid_dev(const sgw_ctx *ctx) {
+  GridDev g;
+  g.nx = ctx->nr1; g.ny = ctx->nr2; g.nz = ctx->nr3;
+  g.rx1 = ctx->px.r1; g.rx2 = ctx->px.r2;
+  g.ry1 = ctx->py.r1; g.ry2 = ctx->py.r2;
+  g.rz1 = ctx->pz.r1; g.rz2 = ctx->pz.r2;
+  g.pitchx = ctx->nr1 | 1;
+  g.twx = ctx->d_twx; g.twy = ctx->d_twy; g.twz = ctx->d_twz;
+  return g;
+}
+
+static size_t zpass_smem(const sgw_ctx *ctx) { return (size_t)(ZCB * (ctx->nr3 | 1) + ctx->nr3) * sizeof(cplx); }
+static size_t plane_smem(const sgw_ctx *ctx) {
+  return (size_t)(ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx);
+}
+
+template <typename K>
+static int set_smem(sgw_ctx *ctx, K kernel, size_t bytes) {
+  if (bytes > ctx->smem_optin) {
+    ctx->err = "FFT plane does not fit in shared memory";
+    return SGW_E_UNSUPPORTED;
+  }
+  if (bytes > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return SGW_OK;
+}
+
+int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active) {
+  if (nvec <= 0) return SGW_OK;
+  const size_t smem = zpass_smem(ctx);
+  SGW_CHECK(set_smem(ctx, k_zpass_g2r, smem));
+  dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
+  k_zpass_g2r<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), in, ld, T, active);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *out, long ld, const ZEpilogue &epi,
+                  const int *active) {
+  if (nvec <= 0) return SGW_OK;
+  const size_t smem = zpass_smem(ctx);
+  SGW_CHECK(set_smem(ctx, k_zpass_r2g, smem));
+  dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
+  const double scale = 1.0 / ((double)ctx->nr1 * ctx->nr2 * ctx->nr3);
+  k_zpass_r2g<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), T, out, ld, epi, scale, active);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
+              const cplx *field, int vec_per_field, cplx *R, const int *active) {
+  if (nvec <= 0) return SGW_OK;
+  const size_t smem = plane_smem(ctx);
+  dim3 grid(ctx->nr3, nvec);
+  GridDev g = grid_dev(ctx);
+  SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
+  if (vec_per_field < 1) vec_per_field = 1;
+  switch (mode) {
+    case PLANE_VLOC:
+      SGW_CHECK(set_smem(ctx, k_plane<PLANE_VLOC>, smem));
+      k_plane<PLANE_VLOC><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      break;
+    case PLANE_FIELD:
+      SGW_CHECK(set_smem(ctx, k_plane<PLANE_FIELD>, smem));
+      k_plane<PLANE_FIELD><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      break;
+    case PLANE_TO_R:
+      SGW_CHECK(set_smem(ctx, k_plane<PLANE_TO_R>, smem));
+      k_plane<PLANE_TO_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      break;
+    case PLANE_FROM_R:
+      SGW_CHECK(set_smem(ctx, k_plane<PLANE_FROM_R>, smem));
+      k_plane<PLANE_FROM_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      break;
+  }
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+// Column structure of a sphere: entries sorted by (y, x, z); perm maps internal -> caller order.
+int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
+  free_sphere(sph);
+  const int nx = ctx->nr1, ny = ctx->nr2, nz = ctx->nr3;
+  std::vector<int> order(npw);
+  std::vector<long> key(npw);
+  for (int i = 0; i < npw; ++i) {
+    const long idx = (long)nl[i] - 1;
+    if (idx < 0 || idx >= (long)nx * ny * nz) {
+      ctx->err = "nl index outside the FFT box";
+      return SGW_E_ARG;
+    }
+    const long x = idx % nx, y = (idx / nx) % ny, z = idx / ((long)nx * ny);
+    key[i] = (y * nx + x) * nz + z;
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  for (int i = 1; i < npw; ++i)
+    if (key[order[i]] == key[order[i - 1]]) {
+      ctx->err = "duplicate nl index in plane-wave list";
+      return SGW_E_ARG;
+    }
+  std::vector<int> col_x, col_y, col_ptr, colof(npw), zof(npw);
+  std::vector<char> xused(nx, 0);
+  long last = -1;
+  for (int p = 0; p < npw; ++p) {
+    const long k = key[order[p]];
+    const long colkey = k / nz;
+    if (colkey != last) {
+      col_ptr.push_back(p);
+      col_x.push_back((int)(colkey % nx));
+      col_y.push_back((int)(colkey / nx));
+      xused[colkey % nx] = 1;
+      last = colkey;
+    }
+    colof[p] = (int)col_x.size() - 1;
+    zof[p] = (int)(k % nz);
+  }
+  col_ptr.push_back(npw);
+  std::vector<int> xs;
+  for (int x = 0; x < nx; ++x)
+    if (xused[x]) xs.push_back(x);
+  sph->npw = npw;
+  sph->ncol = (int)col_x.size();
+  sph->nxs = (int)xs.size();
+  sph->perm = order;
+  SGW_CHECK(upload(ctx, &sph->d_col_x, col_x.data(), col_x.size()));
+  SGW_CHECK(upload(ctx, &sph->d_col_y, col_y.data(), col_y.size()));
+  SGW_CHECK(upload(ctx, &sph->d_col_ptr, col_ptr.data(), col_ptr.size()));
+  SGW_CHECK(upload(ctx, &sph->d_colof, colof.data(), colof.size()));
+  SGW_CHECK(upload(ctx, &sph->d_zof, zof.data(), zof.size()));
+  SGW_CHECK(upload(ctx, &sph->d_xs, xs.data(), xs.size()));
+  SGW_CHECK(upload(ctx, &sph->d_perm, order.data(), order.size()));
+  return SGW_OK;
+}
+
+void free_sphere(Sphere *s) {
+  int **ptrs[] = {&s->d_col_x, &s->d_col_y, &s->d_col_ptr, &s->d_colof, &s->d_zof, &s->d_xs, &s->d_perm};
+  for (auto p : ptrs) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  s->npw = s->ncol = s->nxs = 0;
+  s->perm.clear();
+}
+
+}  // namespace sgw

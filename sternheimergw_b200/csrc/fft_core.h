@@ -1,0 +1,142 @@
+// fft_core.h -- radix plans and per-thread line-FFT stages shared by the sm_100a kernels (fft.cu) and the
+// CPU unit test (tests/cpu_harness/fft_core_test.cpp).  Plain C++: SGW_HD is __host__ __device__ under nvcc.
+//
+// A 1-D length-n transform (n = r1*r2, radices from fft_codelets.h) is done in place in two stages with
+// no digit-reversal pass:
+//   nat2perm  (used for G->r):  [strided DFT_r1 + twiddle]  ->  [contiguous DFT_r2]
+//             natural-order input, output position p holds natural index  perm(p) = p / r2 + r1 * (p % r2)
+//   perm2nat  (used for r->G):  [contiguous DFT_r2 + twiddle] -> [strided DFT_r1]
+//             input in that same permuted order, natural-order output.
+// Each butterfly touches only its own index set, so a stage needs no intra-stage synchronisation; real
+// space therefore lives in "permuted" order everywhere inside the library (the local potential and all
+// real-space fields are stored pre-permuted), which is invisible at the C-ABI.
+#pragma once
+#include "fft_codelets.h"
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+struct double2 { double x, y; };
+#endif
+
+namespace sgw {
+
+struct Plan1D {
+  int n, r1, r2;
+};
+
+inline bool radix_ok(int r) {
+  switch (r) {
+    case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 9: case 10: case 12: case 15: case 16: return true;
+    default: return false;
+  }
+}
+
+// balanced two-radix plan; returns false if n is not representable (n <= 256, factors 2,3,5)
+inline bool make_plan(int n, Plan1D* p) {
+  p->n = n;
+  if (n <= 16 && radix_ok(n)) { p->r1 = n; p->r2 = 1; return true; }
+  int best = -1, bestmax = 1 << 30;
+  for (int r1 = 2; r1 <= 16; ++r1) {
+    if (n % r1 || !radix_ok(r1)) continue;
+    int r2 = n / r1;
+    if (r2 > 16 || !radix_ok(r2) || r2 < 2) continue;
+    int m = r1 > r2 ? r1 : r2;
+    if (m < bestmax || (m == bestmax && r1 < r2)) { bestmax = m; best = r1; }
+  }
+  if (best < 0) return false;
+  p->r1 = best; p->r2 = n / best;
+  return true;
+}
+
+SGW_HD int perm_index(int r1, int r2, int pos) { return pos / r2 + r1 * (pos % r2); }
+
+// ---- one stage over a set of lines; thread `tid` of `nthreads` takes tasks tid, tid+nthreads, ...
+// line l starts at x + (line_ids ? line_ids[l] : l) * ls ; element e of a line at + e * es.
+template <int R, int DIR>
+SGW_HD void stage_strided(double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                          const double2* tw, bool do_tw, int tid, int nthreads) {
+  const int ntasks = nlines * r_other;
+  const int st = r_other * es;
+  for (int t = tid; t < ntasks; t += nthreads) {
+    const int l = t % nlines, j2 = t / nlines;
+    double2* base = x + (long)(line_ids ? line_ids[l] : l) * ls + (long)j2 * es;
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const double2 v = base[(long)j * st]; re[j] = v.x; im[j] = v.y; }
+    if (DIR < 0) dft_fwd<R>(re, im); else dft_fwd<R>(im, re);
+    if (do_tw) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) {
+        const double2 w = tw[j2 * k];
+        const double c = w.x, s = DIR < 0 ? w.y : -w.y;
+        const double a = re[k], b = im[k];
+        re[k] = a * c - b * s;
+        im[k] = a * s + b * c;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[(long)k * st] = v; }
+  }
+}
+
+template <int R, int DIR>
+SGW_HD void stage_contig(double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                         const double2* tw, bool do_tw, int tid, int nthreads) {
+  const int ntasks = nlines * r_other;
+  for (int t = tid; t < ntasks; t += nthreads) {
+    const int l = t % nlines, a = t / nlines;
+    double2* base = x + (long)(line_ids ? line_ids[l] : l) * ls + (long)a * R * es;
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const double2 v = base[(long)j * es]; re[j] = v.x; im[j] = v.y; }
+    if (DIR < 0) dft_fwd<R>(re, im); else dft_fwd<R>(im, re);
+    if (do_tw) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) {
+        const double2 w = tw[a * k];
+        const double c = w.x, s = DIR < 0 ? w.y : -w.y;
+        const double p = re[k], q = im[k];
+        re[k] = p * c - q * s;
+        im[k] = p * s + q * c;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[(long)k * es] = v; }
+  }
+}
+
+// runtime radix dispatch (uniform across the block)
+template <int DIR>
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void run_strided(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                 const double2* tw, bool do_tw, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_strided<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+    SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
+}
+
+template <int DIR>
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void run_contig(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                const double2* tw, bool do_tw, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_contig<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+    SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
+}
+
+}  // namespace sgw

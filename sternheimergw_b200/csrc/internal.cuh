@@ -1,0 +1,233 @@
+// internal.cuh -- context, device descriptors and helpers of libsgw_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sgw_b200.h"
+#include "fft_core.h"
+
+namespace sgw {
+
+typedef double2 cplx;
+
+// ---------------------------------------------------------------- complex helpers
+__host__ __device__ __forceinline__ cplx cmake(double a, double b) { cplx r; r.x = a; r.y = b; return r; }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ __forceinline__ cplx cneg(cplx a) { return cmake(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(double s, cplx a) { return cmake(s * a.x, s * a.y); }
+// y + a*x
+__host__ __device__ __forceinline__ cplx cfma(cplx a, cplx x, cplx y) {
+  return cmake(y.x + (a.x * x.x - a.y * x.y), y.y + (a.x * x.y + a.y * x.x));
+}
+// Smith's algorithm is what gfortran emits for complex division; plain formula is within 1-2 ulp here
+__host__ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+  double r, d;
+  if (fabs(b.x) >= fabs(b.y)) {
+    r = b.y / b.x; d = b.x + b.y * r;
+    return cmake((a.x + a.y * r) / d, (a.y - a.x * r) / d);
+  }
+  r = b.x / b.y; d = b.y + b.x * r;
+  return cmake((a.x * r + a.y) / d, (a.y * r - a.x) / d);
+}
+
+// ---------------------------------------------------------------- device descriptors
+struct GridDev {
+  int nx, ny, nz;
+  int rx1, rx2, ry1, ry2, rz1, rz2;
+  int pitchx;              // plane row pitch in smem (odd)
+  const cplx *twx, *twy, *twz;
+};
+
+// Column structure of a plane-wave sphere on the FFT box.  Coefficient vectors that the library keeps on
+// the device are stored in "column order": entry p belongs to column colof[p] (columns sorted by (y,x)),
+// z index zof[p]; col_ptr delimits columns.
+struct SphereDev {
+  int npw, ncol, nxs;
+  const int *col_x, *col_y, *col_ptr, *colof, *zof, *xs;
+};
+
+struct Sphere {
+  int npw = 0, ncol = 0, nxs = 0;
+  std::vector<int> perm;   // perm[p] = caller's 0-based index of internal entry p
+  int *d_col_x = nullptr, *d_col_y = nullptr, *d_col_ptr = nullptr, *d_colof = nullptr, *d_zof = nullptr,
+      *d_xs = nullptr, *d_perm = nullptr;
+  SphereDev dev() const {
+    SphereDev s; s.npw = npw; s.ncol = ncol; s.nxs = nxs; s.col_x = d_col_x; s.col_y = d_col_y;
+    s.col_ptr = d_col_ptr; s.colof = d_colof; s.zof = d_zof; s.xs = d_xs; return s;
+  }
+};
+
+struct KSlot {
+  bool set = false, dense = false;
+  int npw = 0, npwx = 0, nkb = 0, nbnd = 0;
+  double alpha_pv = 0.0;
+  Sphere sph;
+  double *d_g2kin = nullptr;   // npwx (column order, zero padded)
+  cplx *d_P = nullptr;         // npwx x (nkb + nbnd): [vkb | evq] rows in column order
+  double *d_dion = nullptr;    // nkb x nkb
+  cplx *d_A = nullptr;         // dense backend n x n
+};
+
+struct KPair {
+  bool set = false;
+  int slot = -1, npw_k = 0, nbnd = 0;
+  double wk = 0.0;
+  Sphere sph_k;
+  cplx *d_evc = nullptr;       // npwx x nbnd rows in sph_k column order
+  std::vector<double> et;
+};
+
+struct Workspace {
+  std::map<std::string, std::pair<void *, size_t>> bufs;
+};
+
+}  // namespace sgw
+
+struct sgw_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // grid
+  bool grid_set = false, vloc_set = false, system_set = false;
+  int nr1 = 0, nr2 = 0, nr3 = 0;
+  sgw::Plan1D px, py, pz;
+  sgw::cplx *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
+  double *d_vperm = nullptr;    // local potential in permuted real-space order [pz][py][px]
+  std::vector<int> permx, permy, permz;  // position -> natural index
+  std::vector<sgw::KSlot> slots;
+  std::vector<sgw::KPair> pairs;
+  // system
+  double omega_cell = 0.0, tpiba2 = 0.0, xq[3] = {0, 0, 0};
+  int ngm = 0;
+  std::vector<double> g;        // 3 x ngm
+  std::vector<int32_t> nl;      // ngm, 1-based
+  std::map<int, sgw::Sphere> rho_spheres;  // density-sphere column structures keyed by ngc
+  sgw::Workspace ws;
+  sgw_stats stats;
+  bool profiling = false;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+};
+
+namespace sgw {
+
+#define SGW_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      char buf_[512];                                                                      \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                     \
+      return SGW_E_CUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define SGW_CHECK(expr)                    \
+  do {                                     \
+    int r_ = (expr);                       \
+    if (r_ < 0) return r_;                 \
+  } while (0)
+
+#define SGW_ARG(cond, msg)                 \
+  do {                                     \
+    if (!(cond)) {                         \
+      ctx->err = std::string("invalid argument: ") + msg; \
+      return SGW_E_ARG;                    \
+    }                                      \
+  } while (0)
+
+#define SGW_LAUNCH_CHECK()                 \
+  do {                                     \
+    ctx->launches++;                       \
+    SGW_CUDA(cudaGetLastError());          \
+  } while (0)
+
+// workspace: named growable device buffers owned by the context
+int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out);
+template <typename T>
+inline int ws(sgw_ctx *ctx, const char *name, size_t count, T **out) {
+  void *p = nullptr;
+  int r = ws_get(ctx, name, count * sizeof(T), &p);
+  *out = (T *)p;
+  return r;
+}
+void ws_free_all(sgw_ctx *ctx);
+
+template <typename T>
+inline int upload(sgw_ctx *ctx, T **dptr, const T *h, size_t count) {
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  if (count == 0) return SGW_OK;
+  SGW_CUDA(cudaMalloc((void **)dptr, count * sizeof(T)));
+  SGW_CUDA(cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGW_OK;
+}
+
+void begin_call(sgw_ctx *ctx);
+void end_call(sgw_ctx *ctx);
+GridDev grid_dev(const sgw_ctx *ctx);
+int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl_1based, Sphere *sph);
+void free_sphere(Sphere *s);
+
+// ---- fft.cu : batched local-potential pipeline ----
+enum PlaneMode { PLANE_VLOC = 0, PLANE_FIELD = 1, PLANE_TO_R = 2, PLANE_FROM_R = 3 };
+// G (column order, nvec vectors with leading dim ld) -> T1[vec][pz][col]
+int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active);
+// plane stage: T_in (sphere sin) -> 2-D inverse -> (x v | x field | store R) ; (load R) -> 2-D forward -> T_out (sphere sout)
+int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
+              const cplx *field, int vec_per_field, cplx *R, const int *active);
+// epilogue modes of the final z pass
+struct ZEpilogue {
+  int mode;              // 0: out = val ; 1: out = out*keep + g2kin*psi + sigma*psi + val (H.psi) ; 2: out += val
+  const double *g2kin;   // npwx
+  const cplx *psi;       // nvec x ld
+  const cplx *sigma;     // per vector shift (device) or null
+  long sigma_stride;
+  int keep_out;          // 1: add to existing out (non-local part already there)
+};
+int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *out, long ld, const ZEpilogue &epi,
+                  const int *active);
+
+// ---- gemm.cu : non-local projectors and valence projector (complex FP64, DMMA) ----
+// out[:, v] = P * (W .* (P^H psi[:, v]))  with W = blockdiag(dion, alpha_pv * I_nbnd); out overwritten (npwx rows)
+int nonlocal_apply(sgw_ctx *ctx, const KSlot &k, double alpha_pv, int nvec, const cplx *psi, long ldpsi, cplx *out,
+                   long ldout, const int *active);
+// generic helpers used by the Coulomb pipeline
+int gemm_ch_n(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, const cplx *B, long ldb, cplx *C, long ldc);
+int gemm_n_n(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, const cplx *B, long ldb, cplx beta,
+             cplx *C, long ldc);
+int dense_apply(sgw_ctx *ctx, const KSlot &k, int nvec, const cplx *psi, long ldpsi, const cplx *sigma, long sigma_stride,
+                cplx *out, long ldout, const int *active);
+
+// ---- operator.cu ----
+// apsi[:, v] = (H + sigma_v + alpha_pv P_v) psi[:, v] for vectors in column order (device resident)
+int apply_operator(sgw_ctx *ctx, int slot, double alpha_pv, int nvec, const cplx *psi, long ldpsi, const cplx *sigma,
+                   long sigma_stride, cplx *apsi, long ldapsi, const int *active);
+int permute_in(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *src, long lds, cplx *dst, long ldd, int npwx);
+int permute_out(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *src, long lds, cplx *dst, long ldd);
+
+// ---- bicgstab.cu / subspace.cu / select.cu ----
+struct SolveBatch {
+  int slot;
+  double alpha_pv;
+  int nrhs, nshift, n;       // n = vector length used (npwx of the slot or dense n)
+  const cplx *d_b; long ldb; // device, column order
+  const cplx *d_sigma;       // device nshift x nrhs
+  cplx *d_x;                 // device: x[(irhs*nshift + ishift)*n + ig]
+  int *d_ierr;               // device nrhs
+};
+int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo);
+int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo);
+int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_cfg *cfg);
+
+}  // namespace sgw

@@ -1,0 +1,354 @@
+// subspace.cu -- batched SGW Krylov-subspace solver, restating algo/linear_solver/src/linear_solver.f90:82-503
+// with data/algebra/src/gram_schmidt.f90:35-135 (modified Gram-Schmidt carrying the second vector set) and
+// select.cu's priority/fallback chain of algo/linear_solver/src/select_solver.f90:67-161.
+//
+// Shifts are processed sequentially and carry the subspace (V, W = (A + sigma) V) from shift to shift exactly
+// like the reference (:153-192); the batch axis is the right-hand side.  One CTA owns one RHS:
+//   k_sub_shift    : W += (sigma - sigma_old) V, then gram_schmidt(1, W, V)           (:272-300)
+//   k_sub_residual : r = b - sum_i w_i <w_i|b>, convergence on the RELATIVE threshold,  (:312-383)
+//                    and on convergence x = sum_i v_i <w_i|b> + NaN scan                (:453-503, :186-190)
+//   apply_operator : new = (A + sigma) r  for the RHS that still iterate                (:168)
+//   k_sub_expand   : append (new, r), gram_schmidt(m+1, W, V)                           (:391-440)
+// Inside the re-orthonormalisation the columns j > i are independent, so each warp takes its own columns
+// (dot + two axpys) between two block barriers; the dependency order is the reference's MGS order.
+#include "internal.cuh"
+
+namespace sgw {
+
+constexpr int ST = 512;   // threads per RHS CTA
+
+struct SubState {
+  int n, nrhs, nshift, cap, max_iter;
+  cplx *V, *W;              // [nrhs][cap][n]
+  cplx *Rv, *New;           // [nrhs][n]
+  const cplx *b; long ldb;
+  const cplx *sigma;        // nshift x nrhs
+  cplx *sig_old;            // [nrhs]
+  cplx *x;                  // [(rhs*nshift + ishift)*n]
+  double *absthr;           // [nrhs]
+  int *m, *act, *alive, *done, *iter, *ierr, *count;
+  long *nop;                // [1] operator applications
+};
+
+__device__ __forceinline__ cplx *colV(const SubState &s, int b, int i) { return s.V + ((long)b * s.cap + i) * s.n; }
+__device__ __forceinline__ cplx *colW(const SubState &s, int b, int i) { return s.W + ((long)b * s.cap + i) * s.n; }
+
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+
+__device__ __forceinline__ cplx block_sum(cplx v, cplx *sm) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < nw ? sm[lane] : cmake(0.0, 0.0);
+    v = warp_sum(v);
+    if (lane == 0) sm[0] = v;
+  }
+  __syncthreads();
+  return sm[0];
+}
+
+// 2-norm of a column (norm.f90: ZLANGE 'F'); plain sum of squares
+__device__ __forceinline__ double block_norm(const cplx *x, int n, cplx *sm) {
+  cplx acc = cmake(0.0, 0.0);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { acc.x += x[e].x * x[e].x; acc.y += x[e].y * x[e].y; }
+  acc = block_sum(acc, sm);
+  return sqrt(acc.x + acc.y);
+}
+
+__global__ void __launch_bounds__(ST) k_sub_init(SubState s, double threshold, const int *__restrict__ todo) {
+  const int b = blockIdx.x;
+  __shared__ cplx sm[32];
+  const double nb = block_norm(s.b + (long)b * s.ldb, s.n, sm);
+  if (threadIdx.x == 0) {
+    s.absthr[b] = threshold * nb;                       // linear_solver.f90:213
+    s.m[b] = 0;
+    s.sig_old[b] = cmake(0.0, 0.0);                     // :242
+    s.alive[b] = todo ? (todo[b] != 0) : 1;
+    s.act[b] = 0;
+    s.done[b] = 0;
+    s.iter[b] = 0;
+  }
+  const int alive = todo ? (todo[b] != 0) : 1;
+  if (alive)
+    for (long i = threadIdx.x; i < (long)s.nshift * s.n; i += blockDim.x) s.x[(long)b * s.nshift * s.n + i] = cmake(0.0, 0.0);
+}
+
+// gram_schmidt(first = 1): normalise column i, then remove it from all later columns (warp per column)
+__device__ void gs_full(const SubState &s, int b, int m, cplx *sm) {
+  const int n = s.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = 0; i < m; ++i) {
+    cplx *wi = colW(s, b, i), *vi = colV(s, b, i);
+    const double inv = 1.0 / block_norm(wi, n, sm);     // gram_schmidt.f90:114
+    for (int e = threadIdx.x; e < n; e += blockDim.x) { wi[e] = cscale(inv, wi[e]); vi[e] = cscale(inv, vi[e]); }
+    __syncthreads();
+    for (int j = i + 1 + w; j < m; j += nw) {           // :121-132
+      cplx *wj = colW(s, b, j), *vj = colV(s, b, j);
+      cplx acc = cmake(0.0, 0.0);
+      for (int e = lane; e < n; e += 32) acc = cfma(cconj(wi[e]), wj[e], acc);
+      acc = cneg(warp_sum(acc));
+      for (int e = lane; e < n; e += 32) { wj[e] = cfma(acc, wi[e], wj[e]); vj[e] = cfma(acc, vi[e], vj[e]); }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(ST) k_sub_shift(SubState s, int ishift) {
+  const int b = blockIdx.x;
+  if (!s.alive[b]) return;
+  __shared__ cplx sm[32];
+  const int m = s.m[b], n = s.n;
+  const cplx sg = s.sigma[(long)b * s.nshift + ishift];
+  const cplx d = csub(sg, s.sig_old[b]);                // :289
+  for (int i = 0; i < m; ++i) {
+    cplx *wi = colW(s, b, i);
+    const cplx *vi = colV(s, b, i);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) wi[e] = cfma(d, vi[e], wi[e]);   // :292
+  }
+  __syncthreads();
+  gs_full(s, b, m, sm);                                 // :295
+  if (threadIdx.x == 0) {
+    s.sig_old[b] = sg;                                  // :298
+    s.done[b] = 0;
+    s.iter[b] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(ST) k_sub_residual(SubState s, int ishift) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s.act[b] = 0;
+  if (!s.alive[b] || s.done[b]) return;
+  extern __shared__ cplx dyn[];       // overlaps c[cap]
+  __shared__ cplx sm[32];
+  __shared__ int flag;
+  const int m = s.m[b], n = s.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const cplx *bb = s.b + (long)b * s.ldb;
+  if (s.iter[b] >= s.max_iter) {                        // loop ran out without convergence (:176-180)
+    if (threadIdx.x == 0) { s.ierr[b] = 1; s.alive[b] = 0; }
+    return;
+  }
+  for (int i = w; i < m; i += nw) {                     // overlap_i = <w_i | b>  (:367)
+    const cplx *wi = colW(s, b, i);
+    cplx acc = cmake(0.0, 0.0);
+    for (int e = lane; e < n; e += 32) acc = cfma(cconj(wi[e]), bb[e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) dyn[i] = acc;
+  }
+  __syncthreads();
+  cplx *r = s.Rv + (long)b * n;
+  cplx acc = cmake(0.0, 0.0);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    cplx v = bb[e];
+    for (int i = 0; i < m; ++i) v = cfma(cneg(dyn[i]), colW(s, b, i)[e], v);   // :368
+    r[e] = v;
+    acc.x += v.x * v.x; acc.y += v.y * v.y;
+  }
+  acc = block_sum(acc, sm);
+  const double nrm = sqrt(acc.x + acc.y);               // :373
+  const bool conv = nrm < s.absthr[b];                  // :374
+  if (conv) {
+    // obtain_result :486-501 and NaN scan :186-190
+    cplx *x = s.x + ((long)b * s.nshift + ishift) * n;
+    int bad = 0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      cplx v = cmake(0.0, 0.0);
+      for (int i = 0; i < m; ++i) v = cfma(dyn[i], colV(s, b, i)[e], v);
+      x[e] = v;
+      bad |= (v.x != v.x) || (v.y != v.y);
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+      s.done[b] = 1;
+      if (bad) { s.ierr[b] = 2; s.alive[b] = 0; }
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    flag = 0;
+    if (n == m) {                                       // :376-378 sets 3, :176-180 overwrites it with 1
+      s.ierr[b] = 1; s.alive[b] = 0;
+    } else {
+      s.act[b] = 1;
+      s.iter[b] += 1;
+      atomicAdd(s.count, 1);
+      atomicAdd((unsigned long long *)s.nop, 1ull);
+    }
+  }
+  (void)flag;
+}
+
+__global__ void __launch_bounds__(ST) k_sub_expand(SubState s) {
+  const int b = blockIdx.x;
+  if (!s.act[b]) return;
+  __shared__ cplx sm[32];
+  __shared__ cplx coef;
+  const int m = s.m[b], n = s.n;
+  cplx *wm = colW(s, b, m), *vm = colV(s, b, m);
+  const cplx *nw = s.New + (long)b * n, *r = s.Rv + (long)b * n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { wm[e] = nw[e]; vm[e] = r[e]; }   // :426,:432
+  __syncthreads();
+  for (int j = 0; j < m; ++j) {                          // gram_schmidt.f90:94-106 (first = m+1)
+    const cplx *wj = colW(s, b, j), *vj = colV(s, b, j);
+    cplx acc = cmake(0.0, 0.0);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) acc = cfma(cconj(wj[e]), wm[e], acc);
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) coef = cneg(acc);
+    __syncthreads();
+    const cplx c = coef;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) { wm[e] = cfma(c, wj[e], wm[e]); vm[e] = cfma(c, vj[e], vm[e]); }
+    __syncthreads();
+  }
+  const double inv = 1.0 / block_norm(wm, n, sm);        // :114
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { wm[e] = cscale(inv, wm[e]); vm[e] = cscale(inv, vm[e]); }
+  if (threadIdx.x == 0) s.m[b] = m + 1;
+}
+
+__global__ void k_sub_finish(SubState s, const int *__restrict__ todo) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.nrhs) return;
+  if (todo && !todo[b]) return;
+  if (s.alive[b]) s.ierr[b] = 0;
+}
+
+__global__ void k_copy_cols(int n, int ncol, const cplx *__restrict__ src, long src_rhs_stride, cplx *__restrict__ dst,
+                            long dst_rhs_stride) {
+  const int b = blockIdx.y;
+  const long tot = (long)n * ncol;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x)
+    dst[(long)b * dst_rhs_stride + i] = src[(long)b * src_rhs_stride + i];
+}
+
+int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
+  if (sb.nrhs <= 0) return SGW_OK;
+  SubState s;
+  s.n = sb.n; s.nrhs = sb.nrhs; s.nshift = sb.nshift; s.max_iter = max_iter;
+  s.b = sb.d_b; s.ldb = sb.ldb; s.sigma = sb.d_sigma; s.x = sb.d_x; s.ierr = sb.d_ierr;
+  const long n = s.n, nr = s.nrhs;
+  s.cap = 32;
+  if (s.cap > s.n) s.cap = s.n;
+  SGW_CHECK(ws(ctx, "ss_V", (size_t)(nr * s.cap * n), &s.V));
+  SGW_CHECK(ws(ctx, "ss_W", (size_t)(nr * s.cap * n), &s.W));
+  SGW_CHECK(ws(ctx, "ss_R", (size_t)(nr * n), &s.Rv));
+  SGW_CHECK(ws(ctx, "ss_New", (size_t)(nr * n), &s.New));
+  SGW_CHECK(ws(ctx, "ss_sig", (size_t)nr, &s.sig_old));
+  SGW_CHECK(ws(ctx, "ss_thr", (size_t)nr, &s.absthr));
+  int *ints = nullptr;
+  SGW_CHECK(ws(ctx, "ss_int", (size_t)(5 * nr + 1), &ints));
+  s.m = ints; s.act = ints + nr; s.alive = ints + 2 * nr; s.done = ints + 3 * nr; s.iter = ints + 4 * nr; s.count = ints + 5 * nr;
+  SGW_CHECK(ws(ctx, "ss_nop", (size_t)1, &s.nop));
+  cudaStream_t st = ctx->stream;
+  SGW_CUDA(cudaMemsetAsync(s.nop, 0, sizeof(long), st));
+  int *h_count = nullptr;
+  SGW_CUDA(cudaMallocHost((void **)&h_count, sizeof(int)));
+  k_sub_init<<<(unsigned)nr, ST, 0, st>>>(s, threshold, d_todo);
+  SGW_LAUNCH_CHECK();
+  int total_cols = 0;   // upper bound of the basis size of any RHS
+  int rc = SGW_OK;
+  for (int ishift = 0; ishift < s.nshift && rc == SGW_OK; ++ishift) {
+    k_sub_shift<<<(unsigned)nr, ST, 0, st>>>(s, ishift);
+    SGW_LAUNCH_CHECK();
+    for (int it = 0; it <= max_iter; ++it) {
+      SGW_CUDA(cudaMemsetAsync(s.count, 0, sizeof(int), st));
+      const size_t dyn = (size_t)(s.cap + 1) * sizeof(cplx);
+      if (dyn > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_sub_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      k_sub_residual<<<(unsigned)nr, ST, dyn, st>>>(s, ishift);
+      SGW_LAUNCH_CHECK();
+      SGW_CUDA(cudaMemcpyAsync(h_count, s.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+      if (*h_count == 0) break;
+      rc = apply_operator(ctx, sb.slot, sb.alpha_pv, s.nrhs, s.Rv, n, s.sigma + ishift, s.nshift, s.New, n, s.act);
+      if (rc != SGW_OK) break;
+      if (total_cols + 1 > s.cap) {   // grow the subspace storage (the reference reallocates every iteration, :424-433)
+        int ncap = s.cap * 2;
+        if (ncap > s.n) ncap = s.n;
+        if (ncap <= s.cap || (size_t)(ncap + 1) * sizeof(cplx) > ctx->smem_optin) {
+          ctx->err = "subspace solver: basis capacity exhausted";
+          rc = SGW_E_UNSUPPORTED;
+          break;
+        }
+        cplx *nV = nullptr, *nW = nullptr;
+        const char *nameV = (s.V == (cplx *)ctx->ws.bufs["ss_V"].first) ? "ss_V2" : "ss_V";
+        const char *nameW = (s.W == (cplx *)ctx->ws.bufs["ss_W"].first) ? "ss_W2" : "ss_W";
+        rc = ws(ctx, nameV, (size_t)(nr * ncap * n), &nV);
+        if (rc == SGW_OK) rc = ws(ctx, nameW, (size_t)(nr * ncap * n), &nW);
+        if (rc != SGW_OK) break;
+        dim3 g(64, (unsigned)nr);
+        k_copy_cols<<<g, 256, 0, st>>>(s.n, s.cap, s.V, (long)s.cap * n, nV, (long)ncap * n);
+        SGW_LAUNCH_CHECK();
+        k_copy_cols<<<g, 256, 0, st>>>(s.n, s.cap, s.W, (long)s.cap * n, nW, (long)ncap * n);
+        SGW_LAUNCH_CHECK();
+        s.V = nV; s.W = nW; s.cap = ncap;
+      }
+      k_sub_expand<<<(unsigned)nr, ST, 0, st>>>(s);
+      SGW_LAUNCH_CHECK();
+      ++total_cols;
+    }
+  }
+  cudaFreeHost(h_count);
+  if (rc != SGW_OK) return rc;
+  k_sub_finish<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(s, d_todo);
+  SGW_LAUNCH_CHECK();
+  long nop = 0;
+  SGW_CUDA(cudaMemcpyAsync(&nop, s.nop, sizeof(long), cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.n_linear_op += nop;
+  return SGW_OK;
+}
+
+// ---------------------------------------------------------------- select_solver.f90:67-161
+__global__ void k_sel_init(int nrhs, int *ierr, int *todo) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nrhs) return;
+  ierr[b] = 1;     // :121
+  todo[b] = 1;
+}
+__global__ void k_sel_update(int nrhs, const int *ierr, int *todo, int *nleft) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nrhs) return;
+  todo[b] = ierr[b] != 0;      // :157 only systems that did not converge try the next solver
+  if (todo[b]) atomicAdd(nleft, 1);
+}
+
+int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_cfg *cfg) {
+  int *todo = nullptr, *nleft = nullptr;
+  SGW_CHECK(ws(ctx, "sel_todo", (size_t)sb.nrhs, &todo));
+  SGW_CHECK(ws(ctx, "sel_nleft", (size_t)1, &nleft));
+  const int gb = (sb.nrhs + 127) / 128;
+  k_sel_init<<<gb, 128, 0, ctx->stream>>>(sb.nrhs, sb.d_ierr, todo);
+  SGW_LAUNCH_CHECK();
+  for (int is = 0; is < cfg->npriority; ++is) {
+    switch (cfg->priority[is]) {
+      case 1:   // bicgstab_multi :134-138
+      case 2:   // bicgstab_no_multi :140-146 calls the multishift routine with the whole sigma/xx num_shift times:
+                // identical inputs -> identical outputs, so one call reproduces its result
+        SGW_CHECK(bicgstab_batched(ctx, sb, cfg->bicg_lmax, cfg->threshold, cfg->max_iter, todo));
+        break;
+      case 3:   // sgw_linear_solver :148-152
+        SGW_CHECK(subspace_batched(ctx, sb, cfg->threshold, cfg->max_iter, todo));
+        break;
+      default:
+        ctx->err = "unknown solver in priority list";
+        return SGW_E_ARG;
+    }
+    SGW_CUDA(cudaMemsetAsync(nleft, 0, sizeof(int), ctx->stream));
+    k_sel_update<<<gb, 128, 0, ctx->stream>>>(sb.nrhs, sb.d_ierr, todo, nleft);
+    SGW_LAUNCH_CHECK();
+    int h = 0;
+    SGW_CUDA(cudaMemcpyAsync(&h, nleft, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h == 0) break;
+    if (is + 1 < cfg->npriority) ctx->stats.n_fallback += h;
+  }
+  return SGW_OK;
+}
+
+}  // namespace sgw

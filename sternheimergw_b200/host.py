@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference's operator/plugin interface for the Sternheimer path (see __init__)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+class SgwError(RuntimeError):
+    pass
+
+
+@dataclass
+class select_solver_type:
+    """Configuration of the linear solver (select_solver.f90:48-62); same names and defaults."""
+    priority: tuple = (1, 3)       # main/src/gw_input.yml:151-159 default priority_coul / priority_green
+    max_iter: int = 10000
+    threshold: float = 1e-4
+    bicg_lmax: int = 4
+
+    def c(self) -> _lib.SolverCfg:
+        if not self.priority:
+            raise SgwError("priority of the solvers not specified")     # select_solver.f90:116-118
+        cfg = _lib.SolverCfg()
+        cfg.npriority = len(self.priority)
+        for i, p in enumerate(self.priority):
+            cfg.priority[i] = int(p)
+        cfg.max_iter, cfg.threshold, cfg.bicg_lmax = int(self.max_iter), float(self.threshold), int(self.bicg_lmax)
+        return cfg
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c16(a):
+    return np.require(a, dtype=np.complex128, requirements=["F_CONTIGUOUS", "ALIGNED"])
+
+
+def parallel_task(nproc: int, rank: int, num_task_total: int):
+    """parallel.f90:80-138: returns (first_task, last_task, num_task[nproc]); first/last 1-based, rank 0-based."""
+    L = _lib.load()
+    first, last = C.c_int32(), C.c_int32()
+    num = (C.c_int32 * nproc)()
+    rc = L.sgw_parallel_task(nproc, rank, num_task_total, C.byref(first), C.byref(last), num)
+    if rc != 0:
+        raise SgwError(f"parallel_task: invalid argument ({rc})")
+    return first.value, last.value, list(num)
+
+
+class Context:
+    """One GPU context = the state the reference keeps in QE module globals for one MPI rank."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._L.sgw_create(device, C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise SgwError(f"sgw_create(device={device}) failed ({rc}): no usable CUDA device -- there is no CPU fallback")
+        self.npw = {}
+        self.npwx = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sgw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            raise SgwError(f"{what} failed ({rc}): {self._L.sgw_last_error(self._h).decode()}")
+        return rc
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        self._L.sgw_get_stats(self._h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def synchronize(self):
+        self._chk(self._L.sgw_device_synchronize(self._h), "synchronize")
+
+    # ---- L0 / L1: operator installation -------------------------------------------------------------
+    def set_grid(self, nr1, nr2, nr3, nr1x=None, nr2x=None, nr3x=None):
+        self._chk(self._L.sgw_set_grid(self._h, nr1, nr2, nr3, nr1x or nr1, nr2x or nr2, nr3x or nr3), "set_grid")
+
+    def set_vloc(self, vrs):
+        vrs = np.ascontiguousarray(vrs, dtype=np.float64)
+        self._chk(self._L.sgw_set_vloc(self._h, _p(vrs)), "set_vloc")
+
+    def set_kpoint(self, slot, npw, npwx, nl_igk, g2kin, vkb, dion, evq, alpha_pv):
+        nl_igk = np.ascontiguousarray(nl_igk, dtype=np.int32)
+        g2kin = np.ascontiguousarray(g2kin, dtype=np.float64)
+        vkb, evq = _c16(vkb), _c16(evq)
+        dion = np.asfortranarray(dion, dtype=np.float64)
+        nkb = vkb.shape[1] if vkb.ndim == 2 else 0
+        nb = evq.shape[1] if evq.ndim == 2 else 0
+        assert nkb == 0 or vkb.shape[0] == npwx
+        assert nb == 0 or evq.shape[0] == npwx
+        self._chk(self._L.sgw_set_kpoint(self._h, slot, npw, npwx, _p(nl_igk), _p(g2kin), nkb, _p(vkb), _p(dion), nb,
+                                         _p(evq), float(alpha_pv)), "set_kpoint")
+        self.npw[slot], self.npwx[slot] = npw, npwx
+
+    def set_dense_operator(self, slot, A):
+        A = _c16(A)
+        n = A.shape[0]
+        self._chk(self._L.sgw_set_dense_operator(self._h, slot, n, _p(A), n), "set_dense_operator")
+        self.npw[slot], self.npwx[slot] = n, n
+
+    def install_system(self, syn):
+        """Install a synth.SynthSystem the way the Fortran host would (gwq_setup, solve_linter.f90:300-316)."""
+        self.set_grid(*syn.nr)
+        self.set_vloc(syn.vrs)
+        self._chk(self._L.sgw_set_system(self._h, syn.omega_cell, syn.tpiba2, syn.ngm,
+                                         _p(np.ascontiguousarray(syn.g.T, dtype=np.float64)),
+                                         _p(np.ascontiguousarray(syn.nl, dtype=np.int32))), "set_system")
+        self.set_q(syn.xq)
+        self._chk(self._L.sgw_set_nksq(self._h, len(syn.kpairs)), "set_nksq")
+        for ik, kp in enumerate(syn.kpairs):
+            kq = kp.kq
+            self.set_kpoint(ik, kq.npw, kq.npwx, kq.nl_igk, kq.g2kin, kq.vkb, kq.dion, kq.evq, kq.alpha_pv)
+            evc = _c16(kp.evc)
+            et = np.ascontiguousarray(kp.et, dtype=np.float64)
+            nl = np.ascontiguousarray(kp.nl_igk_k, dtype=np.int32)
+            self._chk(self._L.sgw_set_kpair(self._h, ik, ik, kp.npw_k, _p(nl), evc.shape[1], _p(evc), _p(et), float(kp.wk)),
+                      "set_kpair")
+
+    def set_q(self, xq):
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        self._chk(self._L.sgw_set_q(self._h, _p(xq)), "set_q")
+
+    # ---- linear_op(current_k, num_g, omega, alpha_pv, psi, A_psi) ------------------------------------
+    def linear_op(self, slot, omega, alpha_pv, psi):
+        psi = _c16(psi)
+        if psi.ndim == 1:
+            psi = psi.reshape(-1, 1, order="F")
+        omega = _c16(np.atleast_1d(omega))
+        nvec = psi.shape[1]
+        if omega.size != nvec:
+            raise SgwError("Second dimension of vector psi should be num_band")      # linear_op.f90:101-102
+        out = np.zeros_like(psi, order="F")
+        self._chk(self._L.sgw_linear_op(self._h, slot, nvec, _p(omega), float(alpha_pv), _p(psi), psi.shape[0], _p(out),
+                                        out.shape[0]), "linear_op")
+        return out
+
+    # ---- select_solver(config, AA, bb, sigma, xx, ierr), batched over right-hand sides ----------------
+    def select_solver(self, config: select_solver_type, slot, bb, sigma, use_alpha_pv=True):
+        """bb: (n,) or (n, nrhs); sigma: (nshift,) or (nshift, nrhs).  Returns xx (n, nshift[, nrhs]) and ierr."""
+        bb = _c16(bb)
+        single = bb.ndim == 1
+        if single:
+            bb = bb.reshape(-1, 1, order="F")
+        n, nrhs = bb.shape
+        sigma = _c16(sigma)
+        if sigma.ndim == 1:
+            sigma = np.asfortranarray(np.repeat(sigma.reshape(-1, 1), nrhs, axis=1))
+        nshift = sigma.shape[0]
+        if sigma.shape[1] != nrhs:
+            raise SgwError("we need one shift list per right-hand side")
+        xx = np.zeros((n, nshift, nrhs), dtype=np.complex128, order="F")
+        ierr = np.zeros(nrhs, dtype=np.int32)
+        cfg = config.c()
+        self._chk(self._L.sgw_solve_multishift(self._h, slot, C.byref(cfg), 1 if use_alpha_pv else 0, nrhs, _p(bb), n,
+                                               nshift, _p(sigma), _p(xx), n, n * nshift, _p(ierr)), "select_solver")
+        if single:
+            return xx[:, :, 0], int(ierr[0])
+        return xx, ierr
+
+    # ---- phys/coul -------------------------------------------------------------------------------------
+    def solve_linter(self, config: select_solver_type, num_iter, dvbarein, freq):
+        dvbarein, freq = _c16(np.ravel(dvbarein, order="F")), _c16(freq)
+        drho = np.zeros((dvbarein.size, freq.size), dtype=np.complex128, order="F")
+        ierr = C.c_int32(0)
+        cfg = config.c()
+        self._chk(self._L.sgw_solve_linter(self._h, C.byref(cfg), num_iter, _p(dvbarein), freq.size, _p(freq), _p(drho),
+                                           C.byref(ierr)), "solve_linter")
+        if ierr.value != 0:
+            raise SgwError(f"solver did not converge (ierr={ierr.value})")          # solve_linter.f90:370
+        return drho
+
+    def coulomb(self, config: select_solver_type, igstart, num_g_corr, num_task, ig_unique, fiu, check=True):
+        fiu = _c16(fiu)
+        ig_unique = np.ascontiguousarray(ig_unique, dtype=np.int32)
+        scr = np.zeros((num_g_corr, fiu.size, num_task), dtype=np.complex128, order="F")
+        ierr = C.c_int32(0)
+        cfg = config.c()
+        self._chk(self._L.sgw_coulomb(self._h, C.byref(cfg), igstart, num_g_corr, num_task, _p(ig_unique), fiu.size,
+                                      _p(fiu), _p(scr), C.byref(ierr)), "coulomb")
+        if check and ierr.value != 0:
+            raise SgwError(f"solver did not converge (ierr={ierr.value})")
+        return scr
+
+    def coulomb_q0G0(self, config: select_solver_type, fiu):
+        fiu = _c16(fiu)
+        eps = np.zeros(fiu.size, dtype=np.complex128)
+        ierr = C.c_int32(0)
+        cfg = config.c()
+        self._chk(self._L.sgw_coulomb_q0G0(self._h, C.byref(cfg), fiu.size, _p(fiu), _p(eps), C.byref(ierr)), "coulomb_q0G0")
+        if ierr.value != 0:
+            raise SgwError(f"solver did not converge (ierr={ierr.value})")
+        return eps
+
+    def unfold_w(self, num_g_corr, ig_unique, scrcoul_in):
+        scr_in = _c16(scrcoul_in)
+        ig_unique = np.ascontiguousarray(ig_unique, dtype=np.int32)
+        nfs = scr_in.shape[1]
+        out = np.zeros((num_g_corr, num_g_corr, nfs), dtype=np.complex128, order="F")
+        self._chk(self._L.sgw_unfold_w(self._h, num_g_corr, nfs, ig_unique.size, _p(ig_unique), _p(scr_in), _p(out)), "unfold_w")
+        return out
+
+    def invert_epsilon(self, scrcoul_g, lgamma=False):
+        scr = _c16(scrcoul_g).copy(order="F")
+        ngc, _, nfs = scr.shape
+        self._chk(self._L.sgw_invert_epsilon(self._h, ngc, nfs, _p(scr), 1 if lgamma else 0), "invert_epsilon")
+        return scr
+
+    # ---- phys/green ------------------------------------------------------------------------------------
+    def green_function(self, config: select_solver_type, slot, map_, fft_map, omega):
+        map_ = np.ascontiguousarray(map_, dtype=np.int32)
+        fft_map = np.ascontiguousarray(fft_map, dtype=np.int32)
+        omega = _c16(omega)
+        green = np.zeros((map_.size, fft_map.size, omega.size), dtype=np.complex128, order="F")
+        ierr = C.c_int32(0)
+        cfg = config.c()
+        self._chk(self._L.sgw_green_function(self._h, slot, C.byref(cfg), map_.size, _p(map_), fft_map.size, _p(fft_map),
+                                             omega.size, _p(omega), _p(green), C.byref(ierr)), "green_function")
+        if ierr.value != 0:
+            raise SgwError(f"the linear solver for G did not converge (ierr={ierr.value})")   # green.f90:208
+        return green
+
+    def bench_linear_op(self, slot, nvec, reps=10):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self._L.sgw_bench_linear_op(self._h, slot, nvec, reps, C.byref(a), C.byref(b), C.byref(c)), "bench_linear_op")
+        return {"ms_total": a.value, "ms_fft": b.value, "ms_gemm": c.value}
