@@ -1,15 +1,777 @@
-// coulomb.cu -- stubs (first GPU bring-up); replaced by the batched Coulomb pipeline
+// coulomb.cu -- the screened-Coulomb and Green's-function pipelines around the batched solver:
+//   solve_linter   phys/coul/src/solve_linter.f90:55-624 (direct branch)   -> sgw_solve_linter
+//   coulomb        phys/coul/src/coulomb.f90:29-176                        -> sgw_coulomb
+//   coulomb_q0G0   phys/coul/src/coulomb_q0G0.f90:31-158                   -> sgw_coulomb_q0G0
+//   unfold_w       algo/symmetry/src/unfold_w.f90:84 (identity symmetry)   -> sgw_unfold_w
+//   invert_epsilon phys/coul/src/invert_epsilon.f90:23-90                  -> sgw_invert_epsilon
+//   green_function phys/green/src/green.f90:105-226                        -> sgw_green_function
+// One call handles a whole block of perturbations: dV_bare psi (dvqpsi_us.f90:99-130), -P_c^+ ([QE] orthogonalize),
+// the multishift solves batched over perturbations x bands, the +-omega average (solve_linter.f90:464-480),
+// the Delta-rho accumulation ([QE] incdrhoscf) and the Hartree kernel ([QE] dv_of_drho, lrpa) all stay on the
+// device; only wavefunction tables go in and scrcoul comes out.
 #include "internal.cuh"
-extern "C" {
-#define STUB { if (ctx) ctx->err = "not implemented yet"; return SGW_E_UNSUPPORTED; }
-int sgw_set_system(sgw_ctx *ctx, double, double, int, const double *, const int32_t *) STUB
-int sgw_set_q(sgw_ctx *ctx, const double *) STUB
-int sgw_set_nksq(sgw_ctx *ctx, int) STUB
-int sgw_set_kpair(sgw_ctx *ctx, int, int, int, const int32_t *, int, const sgw_cplx *, const double *, double) STUB
-int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *, int, const sgw_cplx *, int, const sgw_cplx *, sgw_cplx *, int32_t *) STUB
-int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *, int, int, int, const int32_t *, int, const sgw_cplx *, sgw_cplx *, int32_t *) STUB
-int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *, int, const sgw_cplx *, sgw_cplx *, int32_t *) STUB
-int sgw_unfold_w(sgw_ctx *ctx, int, int, int, const int32_t *, const sgw_cplx *, sgw_cplx *) STUB
-int sgw_invert_epsilon(sgw_ctx *ctx, int, int, sgw_cplx *, int) STUB
-int sgw_green_function(sgw_ctx *ctx, int, const sgw_solver_cfg *, int, const int32_t *, int, const int32_t *, int, const sgw_cplx *, sgw_cplx *, int32_t *) STUB
+
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+using namespace sgw;
+
+namespace sgw {
+
+__device__ __forceinline__ int perm_dev(int r1, int r2, int pos) { return pos / r2 + r1 * (pos % r2); }
+
+// dvbare(r) of a delta perturbation at G (coulomb.f90:129-134: invfft of a unit coefficient) in the library's
+// permuted real-space order: exp(+i G.r) as a product of three twiddle-table entries.
+__global__ void k_delta_field(GridDev g, int np, const int *__restrict__ mill /* 3 x np, wrapped to 0..n-1 */,
+                              cplx *__restrict__ field) {
+  const long nnr = (long)g.nx * g.ny * g.nz;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (i >= nnr || p >= np) return;
+  const int px = (int)(i % g.nx), py = (int)((i / g.nx) % g.ny), pz = (int)(i / ((long)g.nx * g.ny));
+  const int x = perm_dev(g.rx1, g.rx2, px), y = perm_dev(g.ry1, g.ry2, py), z = perm_dev(g.rz1, g.rz2, pz);
+  const cplx a = cconj(g.twx[(int)(((long)mill[3 * p] * x) % g.nx)]);
+  const cplx b = cconj(g.twy[(int)(((long)mill[3 * p + 1] * y) % g.ny)]);
+  const cplx c = cconj(g.twz[(int)(((long)mill[3 * p + 2] * z) % g.nz)]);
+  field[(long)p * nnr + i] = cmul(cmul(a, b), c);
 }
+
+// natural (column-major nr1,nr2,nr3) <-> permuted [pz][py][px] real-space order
+__global__ void k_nat2perm(GridDev g, int nvec, const cplx *__restrict__ nat, cplx *__restrict__ prm) {
+  const long nnr = (long)g.nx * g.ny * g.nz;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (i >= nnr) return;
+  const int px = (int)(i % g.nx), py = (int)((i / g.nx) % g.ny), pz = (int)(i / ((long)g.nx * g.ny));
+  const long j = perm_dev(g.rx1, g.rx2, px) + (long)g.nx * (perm_dev(g.ry1, g.ry2, py) + (long)g.ny * perm_dev(g.rz1, g.rz2, pz));
+  prm[(long)v * nnr + i] = nat[(long)v * nnr + j];
+}
+__global__ void k_perm2nat(GridDev g, int nvec, const cplx *__restrict__ prm, cplx *__restrict__ nat, double scale) {
+  const long nnr = (long)g.nx * g.ny * g.nz;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (i >= nnr) return;
+  const int px = (int)(i % g.nx), py = (int)((i / g.nx) % g.ny), pz = (int)(i / ((long)g.nx * g.ny));
+  const long j = perm_dev(g.rx1, g.rx2, px) + (long)g.nx * (perm_dev(g.ry1, g.ry2, py) + (long)g.ny * perm_dev(g.rz1, g.rz2, pz));
+  nat[(long)v * nnr + j] = cscale(scale, prm[(long)v * nnr + i]);
+}
+
+// +-omega average (solve_linter.f90:464-480) fused with the reordering the Delta-rho stage wants:
+// dst[((pf - pf0) * nocc + ib) * n + e],  pf = p * nfreq + ifreq,  from x[((p * nocc + ib) * nshift + is) * n + e]
+__global__ void k_average(int n, int nocc, int nfreq, int nshift, int zero_freq, int pf0, const cplx *__restrict__ x,
+                          cplx *__restrict__ dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int ib = blockIdx.y, pfl = blockIdx.z;
+  const int pf = pf0 + pfl, p = pf / nfreq, ifreq = pf % nfreq;
+  const cplx *xr = x + ((long)(p * nocc + ib) * nshift) * n;
+  cplx v = xr[(long)ifreq * n + e];
+  const int first = zero_freq ? 1 : 0;
+  if (ifreq >= first) {
+    const cplx w = xr[(long)(nfreq + ifreq - first) * n + e];
+    v = cscale(0.5, v);                          // ZSCAL 0.5 then ZAXPY 0.5 (:469-478)
+    v = cmake(v.x + 0.5 * w.x, v.y + 0.5 * w.y);
+  }
+  dst[((long)pfl * nocc + ib) * n + e] = v;
+}
+
+// [QE] dv_of_drho with lrpa: dv(G) = e2 fpi drho(G) / (tpiba2 |q+G|^2); out = -dv (solve_linter.f90:598)
+__global__ void k_hartree(int npw, int nvec, const double *__restrict__ fac /* column order */, cplx *__restrict__ drho,
+                          int zero_pos) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (e >= npw) return;
+  cplx d = drho[(long)v * npw + e];
+  if (e == zero_pos) d = cmake(0.0, 0.0);       // zero-mean fix (:544-550)
+  drho[(long)v * npw + e] = cscale(-fac[e], d);
+}
+
+// coulomb.f90:143-157: scrcoul(igp, iw, indx) = -dV_H(G_igp) + delta(igp, ig)
+__global__ void k_scr_extract(int ngc, int nfs, int np, const int *__restrict__ perm, const double *__restrict__ fac,
+                              const int *__restrict__ ig0 /* 0-based perturbation G per task */,
+                              const cplx *__restrict__ drho /* [p][iw][pos] */, cplx *__restrict__ scr /* ngc x nfs x np */) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iw = blockIdx.y, p = blockIdx.z;
+  if (pos >= ngc) return;
+  const int igp = perm[pos];
+  cplx v = cscale(-fac[pos], drho[((long)p * nfs + iw) * ngc + pos]);
+  if (igp == ig0[p]) v.x += 1.0;
+  scr[(long)igp + (long)ngc * (iw + (long)nfs * p)] = v;
+}
+
+// unfold_w.f90:84: out(ig_unique(ig), igp, iw) = CONJG(in(igp, iw, ig))
+__global__ void k_unfold(int ngc, int nfs, int nuniq, const int *__restrict__ ig_unique, const cplx *__restrict__ in,
+                         cplx *__restrict__ out) {
+  const int igp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iw = blockIdx.y, ig = blockIdx.z;
+  if (igp >= ngc) return;
+  const int row = ig_unique[ig] - 1;
+  if (row < 0 || row >= ngc) return;
+  out[(long)row + (long)ngc * (igp + (long)ngc * iw)] = cconj(in[(long)igp + (long)ngc * (iw + (long)nfs * ig)]);
+}
+
+// ---------------------------------------------------------------- invert_epsilon: batched in-place Gauss-Jordan
+// (ZGETRF/ZGETRI semantics: partial pivoting with the IZAMAX |re|+|im| criterion), one matrix per frequency.
+__global__ void k_eps_wings(int n, cplx *__restrict__ a) {          // invert_epsilon.f90:46-56, :72-81
+  cplx *m = a + (long)blockIdx.y * n * n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || i == 0) return;
+  m[i] = cmake(0.0, 0.0);
+  m[(long)n * i] = cmake(0.0, 0.0);
+}
+__global__ void k_eps_diag(int n, cplx *__restrict__ a) {           // :84-88
+  cplx *m = a + (long)blockIdx.y * n * n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  m[(long)i + (long)n * i].x -= 1.0;
+}
+__global__ void __launch_bounds__(1024) k_gj_pivot(int n, int k, cplx *__restrict__ a, int *__restrict__ piv,
+                                                    cplx *__restrict__ colk, int *__restrict__ info) {
+  cplx *m = a + (long)blockIdx.x * n * n;
+  int *pv = piv + (long)blockIdx.x * n;
+  cplx *ck = colk + (long)blockIdx.x * n;
+  __shared__ double sval[32];
+  __shared__ int sidx[32];
+  __shared__ int s_p;
+  __shared__ cplx s_inv;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  double best = -1.0;
+  int bi = n;
+  for (int i = k + tid; i < n; i += blockDim.x) {
+    const cplx v = m[(long)i + (long)n * k];
+    const double s = fabs(v.x) + fabs(v.y);
+    if (s > best) { best = s; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { sval[w] = best; sidx[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = lane < nw ? sval[lane] : -1.0;
+    bi = lane < nw ? sidx[lane] : n;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      s_p = bi;
+      pv[k] = bi;
+      if (!(best > 0.0)) { atomicMax(info, k + 1); s_inv = cmake(0.0, 0.0); }
+      else s_inv = cdiv(cmake(1.0, 0.0), m[(long)bi + (long)n * k]);
+    }
+  }
+  __syncthreads();
+  const int p = s_p;
+  const cplx inv = s_inv;
+  for (int j = tid; j < n; j += blockDim.x) {                 // swap rows k <-> p, scale row k
+    cplx akj = m[(long)p + (long)n * j];
+    if (p != k) m[(long)p + (long)n * j] = m[(long)k + (long)n * j];
+    m[(long)k + (long)n * j] = (j == k) ? inv : cmul(akj, inv);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {                 // multipliers; column k of the other rows restarts at 0
+    if (i == k) { ck[i] = cmake(0.0, 0.0); continue; }
+    ck[i] = m[(long)i + (long)n * k];
+    m[(long)i + (long)n * k] = cmake(0.0, 0.0);
+  }
+}
+__global__ void __launch_bounds__(256) k_gj_elim(int n, int k, cplx *__restrict__ a, const cplx *__restrict__ colk) {
+  cplx *m = a + (long)blockIdx.z * n * n;
+  const cplx *ck = colk + (long)blockIdx.z * n;
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int j0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * 8;
+  if (i >= n || i == k) return;
+  const cplx f = cneg(ck[i]);
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = j0 + jj;
+    if (j < n) m[(long)i + (long)n * j] = cfma(f, m[(long)k + (long)n * j], m[(long)i + (long)n * j]);
+  }
+}
+__global__ void k_gj_colswap(int n, cplx *__restrict__ a, const int *__restrict__ piv) {
+  cplx *m = a + (long)blockIdx.y * n * n;
+  const int *pv = piv + (long)blockIdx.y * n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = n - 1; k >= 0; --k) {
+    const int p = pv[k];
+    if (p != k) {
+      const cplx t = m[(long)i + (long)n * k];
+      m[(long)i + (long)n * k] = m[(long)i + (long)n * p];
+      m[(long)i + (long)n * p] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- green_function helpers
+__global__ void k_green_rhs(int n, int nrhs, const int *__restrict__ pos /* column-order position of e_G', -1 = skip */,
+                            cplx *__restrict__ b) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (e >= n) return;
+  b[(long)r * n + e] = (e == pos[r]) ? cmake(-1.0, 0.0) : cmake(0.0, 0.0);    // green.f90:203-204
+}
+// green(k, igp, ifreq) = green_part(map(k), ifreq) WHERE map > 0 .AND. map < num_g (green.f90:211-213)
+__global__ void k_green_scatter(int ngc, int ngp, int nfreq, int num_g, int n, const int *__restrict__ map,
+                                const int *__restrict__ invperm, const int *__restrict__ col /* igp of each RHS */,
+                                const cplx *__restrict__ x, cplx *__restrict__ green) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ifreq = blockIdx.y, r = blockIdx.z;
+  if (k >= ngc) return;
+  const int mk = map[k];
+  if (mk > 0 && mk < num_g)
+    green[(long)k + (long)ngc * (col[r] + (long)ngp * ifreq)] = x[((long)r * nfreq + ifreq) * n + invperm[mk - 1]];
+}
+
+static int get_rho_sphere(sgw_ctx *ctx, int ngc, Sphere **out) {
+  auto it = ctx->rho_spheres.find(ngc);
+  if (it == ctx->rho_spheres.end()) {
+    Sphere s;
+    SGW_CHECK(build_sphere(ctx, ngc, ctx->nl.data(), &s));
+    it = ctx->rho_spheres.emplace(ngc, s).first;
+  }
+  *out = &it->second;
+  return SGW_OK;
+}
+
+// e2 fpi / (tpiba2 |q+G|^2) for the first ngc G vectors, in the column order of `sph` ([QE] dv_of_drho, lrpa)
+static int hartree_factor(sgw_ctx *ctx, const Sphere &sph, int ngc, const char *wsname, double **d_fac) {
+  std::vector<double> fac(ngc);
+  const double e2 = 2.0, fpi = 4.0 * M_PI;
+  for (int pos = 0; pos < ngc; ++pos) {
+    const int ig = sph.perm[pos];
+    const double q0 = ctx->g[3 * ig] + ctx->xq[0], q1 = ctx->g[3 * ig + 1] + ctx->xq[1], q2 = ctx->g[3 * ig + 2] + ctx->xq[2];
+    const double qg2 = q0 * q0 + q1 * q1 + q2 * q2;
+    fac[pos] = qg2 > 1e-8 ? e2 * fpi / (ctx->tpiba2 * qg2) : 0.0;
+  }
+  SGW_CHECK(ws(ctx, wsname, (size_t)ngc, d_fac));
+  SGW_CUDA(cudaMemcpyAsync(*d_fac, fac.data(), sizeof(double) * ngc, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGW_OK;
+}
+
+struct FreqList {
+  int nfreq, num_omega, zero_freq;
+  std::vector<cplx> omega;
+};
+static FreqList make_omega(int nfreq, const sgw_cplx *freq) {   // solve_linter.f90:217-252
+  FreqList f;
+  f.nfreq = nfreq;
+  f.zero_freq = std::hypot(freq[0].re, freq[0].im) < 1e-14;
+  f.num_omega = f.zero_freq ? 2 * nfreq - 1 : 2 * nfreq;
+  f.omega.resize(f.num_omega);
+  for (int i = 0; i < nfreq; ++i) f.omega[i] = cmake(freq[i].re, freq[i].im);
+  if (f.zero_freq) for (int i = 1; i < nfreq; ++i) f.omega[nfreq + i - 1] = cmake(-freq[i].re, -freq[i].im);
+  else for (int i = 0; i < nfreq; ++i) f.omega[nfreq + i] = cmake(-freq[i].re, -freq[i].im);
+  return f;
+}
+
+static size_t solver_bytes_per_rhs(const sgw_ctx *ctx, const KSlot &ks, int lmax, int nshift) {
+  const size_t n = ks.npwx, L1 = lmax + 1, ns = nshift - 1;
+  size_t v = 2 * L1 * n + 2 * n + ns * L1 * n + ns * n + (size_t)nshift * n + n;          // bicgstab state + sv_x + rhs
+  v += 2 * (size_t)ctx->nr3 * ks.sph.ncol;                                                // H.psi column buffers
+  v += 4 * (size_t)(ks.nkb + ks.nbnd);                                                    // projector coefficients
+  return v * sizeof(cplx);
+}
+
+// Delta-rho of `np` perturbations whose dvbare(r) sit in d_field (permuted order): d_drhoG[(p*nfreq+ifreq)*rho.npw + pos]
+// = fwfft(drho)(G) in the column order of `rho`, summed over the k-points of this pool.
+static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cplx *d_field, const FreqList &fl,
+                      const Sphere &rho, cplx *d_drhoG, int *ierr_any) {
+  const int nfreq = fl.nfreq, nshift = fl.num_omega;
+  const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  const int npf = np * nfreq;
+  cplx *Trho = nullptr;
+  SGW_CHECK(ws(ctx, "co_Trho", (size_t)npf * ctx->nr3 * rho.ncol, &Trho));
+  cudaStream_t st = ctx->stream;
+  for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {                                     // solve_linter.f90:288
+    const KPair &kp = ctx->pairs[ik];
+    if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size() || !ctx->slots[kp.slot].set) {
+      ctx->err = "k-point pair not set (sgw_set_kpair / sgw_set_kpoint)";
+      return SGW_E_STATE;
+    }
+    const KSlot &ks = ctx->slots[kp.slot];
+    const int n = ks.npwx, nocc = ks.nbnd;
+    if (nocc > kp.nbnd) { ctx->err = "evc holds fewer bands than nbnd_occ"; return SGW_E_ARG; }
+    const int nrhs = np * nocc;
+    // psi_v(r) for the occupied bands: used by dV psi and again by the Delta-rho accumulation
+    cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *dvpsi = nullptr, *ps = nullptr, *d_sig = nullptr, *d_x = nullptr;
+    int *d_ierr = nullptr;
+    SGW_CHECK(ws(ctx, "co_Tk", (size_t)nocc * ctx->nr3 * kp.sph_k.ncol, &Tk));
+    SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));
+    SGW_CHECK(fft_zpass_g2r(ctx, kp.sph_k, nocc, kp.d_evc, n, Tk, nullptr));
+    SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &kp.sph_k, nullptr, nocc, Tk, nullptr, nullptr, 1, psir, nullptr));
+    // dvqpsi_us.f90:99-130: dvpsi = fwfft(dvbare(r) psi(r)) on the k+q sphere (only the bands the solver uses)
+    SGW_CHECK(ws(ctx, "co_Tq", (size_t)nrhs * ctx->nr3 * ks.sph.ncol, &Tq));
+    SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nrhs * n, &dvpsi));
+    SGW_CHECK(fft_plane(ctx, PLANE_FROM_R, nullptr, &ks.sph, nrhs, nullptr, Tq, d_field, nocc, psir, nullptr, nocc));
+    SGW_CUDA(cudaMemsetAsync(dvpsi, 0, sizeof(cplx) * (size_t)nrhs * n, st));
+    ZEpilogue epi;
+    epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
+    SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nrhs, Tq, dvpsi, n, epi, nullptr));
+    // [QE] orthogonalize (insulator): ps = evq^H dvpsi ; dvpsi <- evq ps - dvpsi   (solve_linter.f90:337)
+    const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
+    SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nrhs, &ps));
+    SGW_CHECK(gemm_ch_n(ctx, nocc, nrhs, ks.npw, evq, n, dvpsi, n, ps, nocc));
+    SGW_CHECK(gemm_n_n(ctx, n, nrhs, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), dvpsi, n));
+    // band loop :367-374 -> one batch; sigma = -(et + omega) :369
+    {
+      std::vector<cplx> sig((size_t)nshift * nrhs);
+      for (int p = 0; p < np; ++p)
+        for (int ib = 0; ib < nocc; ++ib)
+          for (int is = 0; is < nshift; ++is)
+            sig[(size_t)(p * nocc + ib) * nshift + is] = cmake(-(kp.et[ib] + fl.omega[is].x), -fl.omega[is].y);
+      SGW_CHECK(ws(ctx, "sv_sig", (size_t)nshift * nrhs, &d_sig));
+      SGW_CUDA(cudaMemcpyAsync(d_sig, sig.data(), sizeof(cplx) * sig.size(), cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+    }
+    SGW_CHECK(ws(ctx, "sv_x", (size_t)n * nshift * nrhs, &d_x));
+    SGW_CHECK(ws(ctx, "sv_ierr", (size_t)nrhs, &d_ierr));
+    SolveBatch sb;
+    sb.slot = kp.slot; sb.alpha_pv = ks.alpha_pv; sb.nrhs = nrhs; sb.nshift = nshift; sb.n = n;
+    sb.d_b = dvpsi; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
+    cudaEventRecord(ctx->ev2, st);
+    SGW_CHECK(select_solver_batched(ctx, sb, cfg));
+    cudaEventRecord(ctx->ev3, st);
+    {
+      std::vector<int> ie(nrhs);
+      SGW_CUDA(cudaMemcpyAsync(ie.data(), d_ierr, sizeof(int) * nrhs, cudaMemcpyDeviceToHost, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+      for (int r = 0; r < nrhs; ++r) if (ie[r] != 0) *ierr_any = ie[r];                     // :370
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+      ctx->stats.ms_solver += ms;
+    }
+    // dpsi *= wg/wk (= 1 for fully occupied bands, :373); average +-omega; incdrhoscf with weight 2 wk / omega
+    const double wgt = 2.0 * kp.wk / ctx->omega_cell;
+    const size_t per_pf = (size_t)nocc * ((size_t)ctx->nr3 * ks.sph.ncol + n) * sizeof(cplx);
+    size_t budget = (size_t)2 << 30;
+    int pfc = (int)std::max<size_t>(1, std::min<size_t>(npf, budget / per_pf));
+    pfc = std::min(pfc, std::max(1, 65535 / nocc));
+    cplx *davg = nullptr, *Td = nullptr;
+    SGW_CHECK(ws(ctx, "co_davg", (size_t)pfc * nocc * n, &davg));
+    SGW_CHECK(ws(ctx, "co_Td", (size_t)pfc * nocc * ctx->nr3 * ks.sph.ncol, &Td));
+    for (int pf0 = 0; pf0 < npf; pf0 += pfc) {
+      const int c = std::min(pfc, npf - pf0);
+      dim3 ga((n + 255) / 256, nocc, c);
+      k_average<<<ga, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, pf0, d_x, davg);
+      SGW_LAUNCH_CHECK();
+      SGW_CHECK(fft_zpass_g2r(ctx, ks.sph, c * nocc, davg, n, Td, nullptr));
+      SGW_CHECK(fft_plane_rho(ctx, ks.sph, rho, c, nocc, Td, psir, wgt, Trho + (size_t)pf0 * ctx->nr3 * rho.ncol, ik > 0));
+    }
+  }
+  // mp_sum over pools (:521) is the caller's (one pool per context); fwfft of drho on the density sphere
+  SGW_CUDA(cudaMemsetAsync(d_drhoG, 0, sizeof(cplx) * (size_t)npf * rho.npw, st));
+  ZEpilogue epi;
+  epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
+  for (int v0 = 0; v0 < npf; v0 += 32768) {
+    const int c = std::min(32768, npf - v0);
+    SGW_CHECK(fft_zpass_r2g(ctx, rho, c, Trho + (size_t)v0 * ctx->nr3 * rho.ncol, d_drhoG + (size_t)v0 * rho.npw, rho.npw, epi, nullptr));
+  }
+  return SGW_OK;
+}
+
+// how many perturbations fit next to each other on the device
+static int perturbation_chunk(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nshift, int nfs, const Sphere &rho, int want) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  size_t held = 0;
+  for (auto &kv : ctx->ws.bufs) held += kv.second.second;           // workspace is re-used, so it counts as available
+  const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  size_t per = 0, fixed = (size_t)3 << 30;
+  for (auto &kp : ctx->pairs) {
+    if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size()) continue;
+    const KSlot &ks = ctx->slots[kp.slot];
+    size_t p = (size_t)ks.nbnd * solver_bytes_per_rhs(ctx, ks, cfg->bicg_lmax, nshift);
+    p += (size_t)ks.nbnd * ctx->nr3 * ks.sph.ncol * sizeof(cplx);   // co_Tq
+    per = std::max(per, p);
+    fixed = std::max(fixed, ((size_t)3 << 30) + (size_t)ks.nbnd * (nnr + (size_t)ctx->nr3 * kp.sph_k.ncol) * sizeof(cplx));
+  }
+  per += (size_t)nnr * sizeof(cplx) + (size_t)nfs * ((size_t)ctx->nr3 * rho.ncol + rho.npw) * sizeof(cplx);
+  const double avail = 0.9 * (double)(free_b + held) - (double)fixed;
+  int c = avail > 0 ? (int)(avail / (double)per) : 1;
+  c = std::max(1, std::min(c, want));
+  // grid.y / grid.z limits of the batched kernels (vectors = perturbations x bands)
+  int maxb = 1;
+  for (auto &s : ctx->slots) if (s.set) maxb = std::max(maxb, s.nbnd);
+  c = std::min(c, std::max(1, 65535 / (maxb * std::max(1, nfs))));
+  return c;
+}
+
+static int check_pipeline_state(sgw_ctx *ctx) {
+  if (!ctx->grid_set || !ctx->vloc_set) { ctx->err = "grid / local potential not set"; return SGW_E_STATE; }
+  if (!ctx->system_set) { ctx->err = "sgw_set_system must be called first"; return SGW_E_STATE; }
+  if (ctx->pairs.empty()) { ctx->err = "no k-point pairs (sgw_set_nksq / sgw_set_kpair)"; return SGW_E_STATE; }
+  return SGW_OK;
+}
+
+}  // namespace sgw
+
+extern "C" {
+
+int sgw_set_system(sgw_ctx *ctx, double omega_cell, double tpiba2, int ngm, const double *g, const int32_t *nl) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->grid_set) { ctx->err = "sgw_set_grid must be called first"; return SGW_E_STATE; }
+  SGW_ARG(omega_cell > 0 && tpiba2 > 0 && ngm > 0 && g && nl, "bad cell / G-vector data");
+  ctx->omega_cell = omega_cell;
+  ctx->tpiba2 = tpiba2;
+  ctx->ngm = ngm;
+  ctx->g.assign(g, g + 3 * (size_t)ngm);
+  ctx->nl.assign(nl, nl + ngm);
+  for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
+  ctx->rho_spheres.clear();
+  ctx->system_set = true;
+  return SGW_OK;
+}
+
+int sgw_set_q(sgw_ctx *ctx, const double *xq) {
+  if (!ctx || !xq) return SGW_E_ARG;
+  for (int i = 0; i < 3; ++i) ctx->xq[i] = xq[i];
+  return SGW_OK;
+}
+
+int sgw_set_nksq(sgw_ctx *ctx, int nksq) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(nksq >= 0 && nksq < (1 << 20), "bad nksq");
+  for (auto &p : ctx->pairs) {
+    free_sphere(&p.sph_k);
+    if (p.d_evc) cudaFree(p.d_evc);
+  }
+  ctx->pairs.assign(nksq, KPair());
+  return SGW_OK;
+}
+
+int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *nl_igk_k, int nbnd, const sgw_cplx *evc,
+                  const double *et, double wk) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ik >= 0 && ik < (int)ctx->pairs.size(), "ik outside 0..nksq-1 (sgw_set_nksq)");
+  if (slot_kq < 0 || slot_kq >= (int)ctx->slots.size() || !ctx->slots[slot_kq].set || ctx->slots[slot_kq].dense) {
+    ctx->err = "slot_kq must be a plane-wave slot set with sgw_set_kpoint";
+    return SGW_E_STATE;
+  }
+  const KSlot &ks = ctx->slots[slot_kq];
+  SGW_ARG(npw_k > 0 && npw_k <= ks.npwx && nl_igk_k && nbnd > 0 && evc && et, "bad k-point data");
+  KPair &kp = ctx->pairs[ik];
+  free_sphere(&kp.sph_k);
+  if (kp.d_evc) { cudaFree(kp.d_evc); kp.d_evc = nullptr; }
+  SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
+  const int npwx = ks.npwx;
+  std::vector<cplx> e((size_t)npwx * nbnd, cmake(0.0, 0.0));
+  const cplx *src = (const cplx *)evc;
+  for (int b = 0; b < nbnd; ++b)
+    for (int p = 0; p < npw_k; ++p) e[(size_t)b * npwx + p] = src[(size_t)b * npwx + kp.sph_k.perm[p]];
+  SGW_CHECK(upload(ctx, &kp.d_evc, e.data(), e.size()));
+  kp.slot = slot_kq; kp.npw_k = npw_k; kp.nbnd = nbnd; kp.wk = wk;
+  kp.et.assign(et, et + nbnd);
+  kp.set = true;
+  return SGW_OK;
+}
+
+int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, const sgw_cplx *dvbarein, int nfreq,
+                     const sgw_cplx *freq, sgw_cplx *drhoscf, int32_t *ierr_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(cfg && dvbarein && freq && drhoscf && ierr_out && nfreq > 0, "null argument");
+  SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");
+  if (num_iter != 1) { ctx->err = "only the direct branch (num_iter = 1) is implemented"; return SGW_E_UNSUPPORTED; }
+  SGW_CHECK(check_pipeline_state(ctx));
+  begin_call(ctx);
+  const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  const FreqList fl = make_omega(nfreq, freq);
+  Sphere *rho = nullptr;
+  SGW_CHECK(get_rho_sphere(ctx, ctx->ngm, &rho));
+  cudaStream_t st = ctx->stream;
+  GridDev g = grid_dev(ctx);
+  cplx *d_nat = nullptr, *d_field = nullptr, *d_drhoG = nullptr, *Tr = nullptr;
+  SGW_CHECK(ws(ctx, "sl_nat", (size_t)nnr * nfreq, &d_nat));
+  SGW_CHECK(ws(ctx, "co_field", (size_t)nnr, &d_field));
+  SGW_CUDA(cudaMemcpyAsync(d_nat, dvbarein, sizeof(cplx) * nnr, cudaMemcpyHostToDevice, st));
+  {
+    dim3 gr((unsigned)((nnr + 255) / 256), 1);
+    k_nat2perm<<<gr, 256, 0, st>>>(g, 1, d_nat, d_field);
+    SGW_LAUNCH_CHECK();
+  }
+  double s2 = 0.0;                                                                         // solve_linter.f90:532
+  for (long i = 0; i < nnr; ++i) s2 += dvbarein[i].re * dvbarein[i].re + dvbarein[i].im * dvbarein[i].im;
+  const double meandvb = std::sqrt(s2) / (double)nnr;
+  SGW_CHECK(ws(ctx, "co_drhoG", (size_t)nfreq * rho->npw, &d_drhoG));
+  int ierr_any = 0;
+  SGW_CHECK(drho_block(ctx, cfg, 1, d_field, fl, *rho, d_drhoG, &ierr_any));
+  double *d_fac = nullptr;
+  SGW_CHECK(hartree_factor(ctx, *rho, rho->npw, "co_fac", &d_fac));
+  int zero_pos = -1;
+  if (meandvb < 1e-10)
+    for (int pos = 0; pos < rho->npw; ++pos) if (rho->perm[pos] == 0) zero_pos = pos;       // :544-550 (G = 0 is ig = 1)
+  {
+    dim3 gr((rho->npw + 255) / 256, nfreq);
+    k_hartree<<<gr, 256, 0, st>>>(rho->npw, nfreq, d_fac, d_drhoG, zero_pos);
+    SGW_LAUNCH_CHECK();
+  }
+  // back to real space (:556 dv_of_drho ends with invfft) and out = -dvscfout (:598, sign already applied)
+  SGW_CHECK(ws(ctx, "sl_Tr", (size_t)nfreq * ctx->nr3 * rho->ncol, &Tr));
+  SGW_CHECK(fft_zpass_g2r(ctx, *rho, nfreq, d_drhoG, rho->npw, Tr, nullptr));
+  cplx *d_R = nullptr;
+  SGW_CHECK(ws(ctx, "sl_R", (size_t)nnr * nfreq, &d_R));
+  SGW_CHECK(fft_plane(ctx, PLANE_TO_R, rho, nullptr, nfreq, Tr, nullptr, nullptr, 1, d_R, nullptr));
+  {
+    dim3 gr((unsigned)((nnr + 255) / 256), nfreq);
+    k_perm2nat<<<gr, 256, 0, st>>>(g, nfreq, d_R, d_nat, 1.0);
+    SGW_LAUNCH_CHECK();
+  }
+  SGW_CUDA(cudaMemcpyAsync(drhoscf, d_nat, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  *ierr_out = ierr_any;
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, int ntask, const int32_t *ig_unique,
+                int nfs, const sgw_cplx *fiu, sgw_cplx *scrcoul, int32_t *ierr_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(cfg && ig_unique && fiu && scrcoul && ierr_out, "null argument");
+  SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");
+  SGW_ARG(igstart >= 1 && ntask >= 0 && nfs > 0, "bad task range");
+  SGW_CHECK(check_pipeline_state(ctx));
+  SGW_ARG(ngc >= 1 && ngc <= ctx->ngm, "num_g_corr outside 1..ngm");
+  begin_call(ctx);
+  memset(scrcoul, 0, sizeof(sgw_cplx) * (size_t)ngc * nfs * ntask);                        // coulomb.f90:98
+  *ierr_out = 0;
+  const FreqList fl = make_omega(nfs, fiu);
+  Sphere *rho = nullptr;
+  SGW_CHECK(get_rho_sphere(ctx, ngc, &rho));
+  // tasks that are not skipped by the |q+G|^2 < 1e-8 rule (:126)
+  std::vector<int> task_indx, task_ig;
+  for (int indx = 0; indx < ntask; ++indx) {
+    const int ig = ig_unique[igstart - 1 + indx];
+    SGW_ARG(ig >= 1 && ig <= ctx->ngm, "ig_unique entry outside 1..ngm");
+    const double q0 = ctx->g[3 * (ig - 1)] + ctx->xq[0], q1 = ctx->g[3 * (ig - 1) + 1] + ctx->xq[1],
+                 q2 = ctx->g[3 * (ig - 1) + 2] + ctx->xq[2];
+    if (q0 * q0 + q1 * q1 + q2 * q2 < 1e-8) continue;
+    task_indx.push_back(indx);
+    task_ig.push_back(ig);
+  }
+  const int nt = (int)task_ig.size();
+  if (nt == 0) { end_call(ctx); return SGW_OK; }
+  double *d_fac = nullptr;
+  SGW_CHECK(hartree_factor(ctx, *rho, ngc, "co_fac", &d_fac));
+  const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  const int chunk = perturbation_chunk(ctx, cfg, fl.num_omega, nfs, *rho, nt);
+  cudaStream_t st = ctx->stream;
+  GridDev g = grid_dev(ctx);
+  std::vector<cplx> hscr((size_t)ngc * nfs * chunk);
+  int ierr_any = 0;
+  for (int t0 = 0; t0 < nt; t0 += chunk) {
+    const int np = std::min(chunk, nt - t0);
+    std::vector<int> mill(3 * np), ig0(np);
+    for (int p = 0; p < np; ++p) {
+      const long idx = (long)ctx->nl[task_ig[t0 + p] - 1] - 1;
+      mill[3 * p] = (int)(idx % ctx->nr1);
+      mill[3 * p + 1] = (int)((idx / ctx->nr1) % ctx->nr2);
+      mill[3 * p + 2] = (int)(idx / ((long)ctx->nr1 * ctx->nr2));
+      ig0[p] = task_ig[t0 + p] - 1;
+    }
+    int *d_mill = nullptr, *d_ig0 = nullptr;
+    cplx *d_field = nullptr, *d_drhoG = nullptr, *d_scr = nullptr;
+    SGW_CHECK(ws(ctx, "co_mill", (size_t)3 * np, &d_mill));
+    SGW_CHECK(ws(ctx, "co_ig0", (size_t)np, &d_ig0));
+    SGW_CHECK(ws(ctx, "co_field", (size_t)nnr * np, &d_field));
+    SGW_CHECK(ws(ctx, "co_drhoG", (size_t)np * nfs * ngc, &d_drhoG));
+    SGW_CHECK(ws(ctx, "co_scr", (size_t)np * nfs * ngc, &d_scr));
+    SGW_CUDA(cudaMemcpyAsync(d_mill, mill.data(), sizeof(int) * 3 * np, cudaMemcpyHostToDevice, st));
+    SGW_CUDA(cudaMemcpyAsync(d_ig0, ig0.data(), sizeof(int) * np, cudaMemcpyHostToDevice, st));
+    {
+      dim3 gr((unsigned)((nnr + 255) / 256), np);
+      k_delta_field<<<gr, 256, 0, st>>>(g, np, d_mill, d_field);                           // coulomb.f90:129-134
+      SGW_LAUNCH_CHECK();
+    }
+    SGW_CHECK(drho_block(ctx, cfg, np, d_field, fl, *rho, d_drhoG, &ierr_any));            // :137
+    {
+      dim3 gr((ngc + 127) / 128, nfs, np);
+      k_scr_extract<<<gr, 128, 0, st>>>(ngc, nfs, np, rho->d_perm, d_fac, d_ig0, d_drhoG, d_scr);   // :143-157
+      SGW_LAUNCH_CHECK();
+    }
+    SGW_CUDA(cudaMemcpyAsync(hscr.data(), d_scr, sizeof(cplx) * (size_t)ngc * nfs * np, cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < np; ++p)
+      memcpy(scrcoul + (size_t)ngc * nfs * task_indx[t0 + p], &hscr[(size_t)ngc * nfs * p], sizeof(cplx) * (size_t)ngc * nfs);
+  }
+  *ierr_out = ierr_any;
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw_cplx *fiu, sgw_cplx *eps_m,
+                     int32_t *ierr_out) {
+  // coulomb_q0G0.f90:31-158: the G = G' = 0 element at the (shifted) q currently installed
+  const int32_t one = 1;
+  return sgw_coulomb(ctx, cfg, 1, 1, 1, &one, nfs, fiu, eps_m, ierr_out);
+}
+
+int sgw_unfold_w(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *ig_unique, const sgw_cplx *scrcoul_in,
+                 sgw_cplx *scrcoul_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ngc > 0 && nfs > 0 && ngmunique > 0 && ig_unique && scrcoul_in && scrcoul_out, "bad argument");
+  for (int i = 0; i < ngmunique; ++i) SGW_ARG(ig_unique[i] >= 1 && ig_unique[i] <= ngc, "ig_unique outside 1..num_g_corr");
+  begin_call(ctx);
+  cudaStream_t st = ctx->stream;
+  cplx *d_in = nullptr, *d_out = nullptr;
+  int *d_iu = nullptr;
+  const size_t nin = (size_t)ngc * nfs * ngmunique, nout = (size_t)ngc * ngc * nfs;
+  SGW_CHECK(ws(ctx, "uf_in", nin, &d_in));
+  SGW_CHECK(ws(ctx, "uf_out", nout, &d_out));
+  SGW_CHECK(ws(ctx, "uf_iu", (size_t)ngmunique, &d_iu));
+  SGW_CUDA(cudaMemcpyAsync(d_in, scrcoul_in, sizeof(cplx) * nin, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_out, scrcoul_out, sizeof(cplx) * nout, cudaMemcpyHostToDevice, st));   // INTENT(INOUT)-like
+  SGW_CUDA(cudaMemcpyAsync(d_iu, ig_unique, sizeof(int) * ngmunique, cudaMemcpyHostToDevice, st));
+  dim3 gr((ngc + 127) / 128, nfs, ngmunique);
+  k_unfold<<<gr, 128, 0, st>>>(ngc, nfs, ngmunique, d_iu, d_in, d_out);
+  SGW_LAUNCH_CHECK();
+  SGW_CUDA(cudaMemcpyAsync(scrcoul_out, d_out, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrcoul_g, int lgamma) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ngc > 0 && nfs > 0 && scrcoul_g, "bad argument");
+  begin_call(ctx);
+  cudaStream_t st = ctx->stream;
+  cplx *d_a = nullptr, *d_colk = nullptr;
+  int *d_piv = nullptr, *d_info = nullptr;
+  const size_t tot = (size_t)ngc * ngc * nfs;
+  SGW_CHECK(ws(ctx, "ie_a", tot, &d_a));
+  SGW_CHECK(ws(ctx, "ie_colk", (size_t)ngc * nfs, &d_colk));
+  SGW_CHECK(ws(ctx, "ie_piv", (size_t)ngc * nfs + 1, &d_piv));
+  d_info = d_piv + (size_t)ngc * nfs;
+  SGW_CUDA(cudaMemcpyAsync(d_a, scrcoul_g, sizeof(cplx) * tot, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  const dim3 g1((ngc + 127) / 128, nfs);
+  if (lgamma) { k_eps_wings<<<g1, 128, 0, st>>>(ngc, d_a); SGW_LAUNCH_CHECK(); }            // :46-56
+  const int pt = ngc >= 1024 ? 1024 : (ngc >= 256 ? 256 : 64);
+  const dim3 ge((ngc + 63) / 64, (ngc + 31) / 32, nfs);
+  for (int k = 0; k < ngc; ++k) {                                                           // :59-66
+    k_gj_pivot<<<nfs, pt, 0, st>>>(ngc, k, d_a, d_piv, d_colk, d_info);
+    SGW_LAUNCH_CHECK();
+    k_gj_elim<<<ge, 256, 0, st>>>(ngc, k, d_a, d_colk);
+    SGW_LAUNCH_CHECK();
+  }
+  k_gj_colswap<<<g1, 128, 0, st>>>(ngc, d_a, d_piv);
+  SGW_LAUNCH_CHECK();
+  if (lgamma) { k_eps_wings<<<g1, 128, 0, st>>>(ngc, d_a); SGW_LAUNCH_CHECK(); }            // :72-81
+  k_eps_diag<<<g1, 128, 0, st>>>(ngc, d_a);                                                 // :84-88
+  SGW_LAUNCH_CHECK();
+  int info = 0;
+  SGW_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d_a, sizeof(cplx) * tot, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  end_call(ctx);
+  if (info != 0) {                                                                          // :61,:64 errore
+    ctx->err = "invert_epsilon: matrix is singular (zero pivot in column " + std::to_string(info) + ")";
+    return SGW_E_ARG;
+  }
+  return SGW_OK;
+}
+
+int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ngc, const int32_t *map, int ngp,
+                       const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green, int32_t *ierr_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(cfg && map && fft_map && omega && green && ierr_out, "null argument");
+  SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");
+  SGW_ARG(ngc > 0 && ngp > 0 && nfreq > 0, "bad sizes");
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
+  const KSlot &ks = ctx->slots[slot];
+  const int n = ks.npwx, num_g = ks.npw;
+  for (int k = 0; k < ngc; ++k) SGW_ARG(map[k] >= 0 && map[k] <= num_g, "map entry outside 0..num_g");
+  for (int i = 0; i < ngp; ++i) SGW_ARG(fft_map[i] >= 1 && fft_map[i] <= ngc, "fft_map entry outside 1..num_g_corr");
+  begin_call(ctx);
+  memset(green, 0, sizeof(sgw_cplx) * (size_t)ngc * ngp * nfreq);                           // green.f90:184
+  *ierr_out = 0;
+  cudaStream_t st = ctx->stream;
+  std::vector<int> invperm(num_g);
+  for (int p = 0; p < num_g; ++p) invperm[ks.sph.perm[p]] = p;
+  std::vector<int> pos, col;            // right-hand sides that exist: G' inside the k sphere (:199-200 CYCLE otherwise)
+  for (int i = 0; i < ngp; ++i) {
+    const int ig = map[fft_map[i] - 1];                                                     // :199
+    if (ig == 0) continue;
+    pos.push_back(invperm[ig - 1]);
+    col.push_back(i);
+  }
+  const int nlist = (int)pos.size();
+  if (nlist == 0) { end_call(ctx); return SGW_OK; }
+  std::vector<cplx> msig(nfreq);
+  for (int i = 0; i < nfreq; ++i) msig[i] = cmake(-omega[i].re, -omega[i].im);              // :207
+  // RHS chunk that fits on the device
+  size_t free_b = 0, total_b = 0, held = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  for (auto &kv : ctx->ws.bufs) held += kv.second.second;
+  const size_t per = solver_bytes_per_rhs(ctx, ks, cfg->bicg_lmax, nfreq) + (size_t)nfreq * sizeof(cplx);
+  const size_t gbytes = (size_t)ngc * ngp * nfreq * sizeof(cplx);
+  double avail = 0.85 * (double)(free_b + held) - (double)gbytes - (double)((size_t)1 << 30);
+  int chunk = avail > 0 ? (int)std::min<double>(avail / (double)per, 32768.0) : 1;
+  chunk = std::max(1, std::min(chunk, nlist));
+  cplx *d_green = nullptr, *d_b = nullptr, *d_sig = nullptr, *d_x = nullptr;
+  int *d_map = nullptr, *d_inv = nullptr, *d_pos = nullptr, *d_col = nullptr, *d_ierr = nullptr;
+  SGW_CHECK(ws(ctx, "gr_green", (size_t)ngc * ngp * nfreq, &d_green));
+  SGW_CHECK(ws(ctx, "gr_map", (size_t)ngc, &d_map));
+  SGW_CHECK(ws(ctx, "gr_inv", (size_t)num_g, &d_inv));
+  SGW_CHECK(ws(ctx, "gr_pos", (size_t)nlist, &d_pos));
+  SGW_CHECK(ws(ctx, "gr_col", (size_t)nlist, &d_col));
+  SGW_CUDA(cudaMemsetAsync(d_green, 0, gbytes, st));
+  SGW_CUDA(cudaMemcpyAsync(d_map, map, sizeof(int) * ngc, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_inv, invperm.data(), sizeof(int) * num_g, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_pos, pos.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_col, col.data(), sizeof(int) * nlist, cudaMemcpyHostToDevice, st));
+  SGW_CHECK(ws(ctx, "sv_b", (size_t)n * chunk, &d_b));
+  SGW_CHECK(ws(ctx, "sv_sig", (size_t)nfreq * chunk, &d_sig));
+  SGW_CHECK(ws(ctx, "sv_x", (size_t)n * nfreq * chunk, &d_x));
+  SGW_CHECK(ws(ctx, "sv_ierr", (size_t)chunk, &d_ierr));
+  std::vector<cplx> sig((size_t)nfreq * chunk);
+  for (int r = 0; r < chunk; ++r) memcpy(&sig[(size_t)r * nfreq], msig.data(), sizeof(cplx) * nfreq);
+  SGW_CUDA(cudaMemcpyAsync(d_sig, sig.data(), sizeof(cplx) * sig.size(), cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  int ierr_any = 0;
+  for (int r0 = 0; r0 < nlist; r0 += chunk) {                                               // :196
+    const int nr = std::min(chunk, nlist - r0);
+    dim3 gb((n + 255) / 256, nr);
+    k_green_rhs<<<gb, 256, 0, st>>>(n, nr, d_pos + r0, d_b);
+    SGW_LAUNCH_CHECK();
+    SolveBatch sb;
+    sb.slot = slot; sb.alpha_pv = 0.0;                                                      // green_operator :283
+    sb.nrhs = nr; sb.nshift = nfreq; sb.n = n;
+    sb.d_b = d_b; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
+    cudaEventRecord(ctx->ev2, st);
+    SGW_CHECK(select_solver_batched(ctx, sb, cfg));
+    cudaEventRecord(ctx->ev3, st);
+    std::vector<int> ie(nr);
+    SGW_CUDA(cudaMemcpyAsync(ie.data(), d_ierr, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < nr; ++r) if (ie[r] != 0) ierr_any = ie[r];                           // :208
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
+    ctx->stats.ms_solver += ms;
+    dim3 gs((ngc + 127) / 128, nfreq, nr);
+    k_green_scatter<<<gs, 128, 0, st>>>(ngc, ngp, nfreq, num_g, n, d_map, d_inv, d_col + r0, d_x, d_green);
+    SGW_LAUNCH_CHECK();
+  }
+  SGW_CUDA(cudaMemcpyAsync(green, d_green, gbytes, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  *ierr_out = ierr_any;
+  end_call(ctx);
+  return SGW_OK;
+}
+
+}  // extern "C"

@@ -103,8 +103,11 @@ template <int MODE>
 __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
                                                      cplx *__restrict__ Tout, const double *__restrict__ vperm,
                                                      const cplx *__restrict__ field, int vec_per_field, cplx *R,
-                                                     const int *__restrict__ active) {
+                                                     int in_mod, const int *__restrict__ active) {
+  // in_mod > 0: the INPUT (Tin or R) of vector `vec` is input vector vec % in_mod (one set of bands shared by
+  // every perturbation, dvqpsi_us.f90:99-130)
   const int vec = blockIdx.y, pz = blockIdx.x;
+  const int vin = in_mod > 0 ? vec % in_mod : vec;
   if (active && !active[vec]) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   extern __shared__ cplx sm[];
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, Sp
   if (MODE != PLANE_FROM_R) {
     for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
     __syncthreads();
-    const cplx *row = Tin + ((long)vec * g.nz + pz) * sin.ncol;
+    const cplx *row = Tin + ((long)vin * g.nz + pz) * sin.ncol;
     for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_y[c] * pitch + sin.col_x[c]] = row[c];
     __syncthreads();
     // inverse along y for the x columns that hold data (x still in natural order)
@@ -159,11 +162,19 @@ __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, Sp
       r[i] = plane[iy * pitch + ix];
     }
     return;
-  } else {  // PLANE_FROM_R
-    const cplx *r = R + ((long)vec * g.nz + pz) * nxy;
-    for (int i = tid; i < nx * ny; i += nt) {
-      const int ix = i % nx, iy = i / nx;
-      plane[iy * pitch + ix] = r[i];
+  } else {  // PLANE_FROM_R (optionally times a complex field: dV_bare(r) psi(r))
+    const cplx *r = R + ((long)vin * g.nz + pz) * nxy;
+    if (field) {
+      const cplx *f = field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy;
+      for (int i = tid; i < nx * ny; i += nt) {
+        const int ix = i % nx, iy = i / nx;
+        plane[iy * pitch + ix] = cmul(f[i], r[i]);
+      }
+    } else {
+      for (int i = tid; i < nx * ny; i += nt) {
+        const int ix = i % nx, iy = i / nx;
+        plane[iy * pitch + ix] = r[i];
+      }
     }
   }
   __syncthreads();
@@ -184,6 +195,74 @@ __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, Sp
   __syncthreads();
   cplx *orow = Tout + ((long)vec * g.nz + pz) * sout.ncol;
   for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_y[c] * pitch + sout.col_x[c]];
+}
+
+// incdrhoscf: one CTA per (pf = perturbation x frequency, z-plane); bands are summed on chip
+__global__ void __launch_bounds__(PTHREADS) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
+                                                         const cplx *__restrict__ Tin, const cplx *__restrict__ psir,
+                                                         double wgt, cplx *__restrict__ Tout, int accumulate) {
+  const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
+  const int tid = threadIdx.x, nt = blockDim.x;
+  extern __shared__ cplx sm[];
+  const int pitch = g.pitchx, nx = g.nx, ny = g.ny;
+  cplx *plane = sm;
+  cplx *acc = sm + ny * pitch;
+  cplx *twx = acc + ny * pitch;
+  cplx *twy = twx + nx;
+  for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
+  for (int i = tid; i < ny; i += nt) twy[i] = g.twy[i];
+  for (int i = tid; i < ny * pitch; i += nt) acc[i] = cmake(0.0, 0.0);
+  const long nxy = (long)nx * ny;
+  for (int ib = 0; ib < nocc; ++ib) {
+    for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
+    __syncthreads();
+    const cplx *row = Tin + (((long)pf * nocc + ib) * g.nz + pz) * sin.ncol;
+    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_y[c] * pitch + sin.col_x[c]] = row[c];
+    __syncthreads();
+    run_strided<+1>(g.ry1, plane, sin.nxs, sin.xs, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
+    __syncthreads();
+    if (g.ry2 > 1) {
+      run_contig<+1>(g.ry2, plane, sin.nxs, sin.xs, 1, pitch, g.ry1, twy, false, tid, nt);
+      __syncthreads();
+    }
+    run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
+    __syncthreads();
+    if (g.rx2 > 1) {
+      run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+      __syncthreads();
+    }
+    const cplx *pr = psir + ((long)ib * g.nz + pz) * nxy;
+    for (int i = tid; i < nx * ny; i += nt) {
+      const int ix = i % nx, iy = i / nx;
+      const int j = iy * pitch + ix;
+      acc[j] = cfma(cconj(pr[i]), plane[j], acc[j]);        // drho += conj(psi) dpsi
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < nx * ny; i += nt) {
+    const int ix = i % nx, iy = i / nx;
+    const int j = iy * pitch + ix;
+    plane[j] = cscale(wgt, acc[j]);
+  }
+  __syncthreads();
+  if (g.rx2 > 1) {
+    run_contig<-1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
+    __syncthreads();
+  }
+  run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
+  __syncthreads();
+  if (g.ry2 > 1) {
+    run_contig<-1>(g.ry2, plane, sout.nxs, sout.xs, 1, pitch, g.ry1, twy, true, tid, nt);
+    __syncthreads();
+  }
+  run_strided<-1>(g.ry1, plane, sout.nxs, sout.xs, 1, pitch, g.ry2, twy, false, tid, nt);
+  __syncthreads();
+  cplx *orow = Tout + ((long)pf * g.nz + pz) * sout.ncol;
+  if (accumulate) {
+    for (int c = tid; c < sout.ncol; c += nt) orow[c] = cadd(orow[c], plane[sout.col_y[c] * pitch + sout.col_x[c]]);
+  } else {
+    for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_y[c] * pitch + sout.col_x[c]];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -236,7 +315,7 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
 }
 
 int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
-              const cplx *field, int vec_per_field, cplx *R, const int *active) {
+              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod) {
   if (nvec <= 0) return SGW_OK;
   const size_t smem = plane_smem(ctx);
   dim3 grid(ctx->nr3, nvec);
@@ -246,21 +325,32 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   switch (mode) {
     case PLANE_VLOC:
       SGW_CHECK(set_smem(ctx, k_plane<PLANE_VLOC>, smem));
-      k_plane<PLANE_VLOC><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      k_plane<PLANE_VLOC><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
       break;
     case PLANE_FIELD:
       SGW_CHECK(set_smem(ctx, k_plane<PLANE_FIELD>, smem));
-      k_plane<PLANE_FIELD><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      k_plane<PLANE_FIELD><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
       break;
     case PLANE_TO_R:
       SGW_CHECK(set_smem(ctx, k_plane<PLANE_TO_R>, smem));
-      k_plane<PLANE_TO_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      k_plane<PLANE_TO_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
       break;
     case PLANE_FROM_R:
       SGW_CHECK(set_smem(ctx, k_plane<PLANE_FROM_R>, smem));
-      k_plane<PLANE_FROM_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, active);
+      k_plane<PLANE_FROM_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
       break;
   }
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
+                  double wgt, cplx *Tout, int accumulate) {
+  if (npf <= 0) return SGW_OK;
+  const size_t smem = (size_t)(2 * ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx);
+  SGW_CHECK(set_smem(ctx, k_plane_rho, smem));
+  dim3 grid(npf, ctx->nr3);
+  k_plane_rho<<<grid, PTHREADS, smem, ctx->stream>>>(grid_dev(ctx), sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }

@@ -185,7 +185,12 @@ enum PlaneMode { PLANE_VLOC = 0, PLANE_FIELD = 1, PLANE_TO_R = 2, PLANE_FROM_R =
 int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active);
 // plane stage: T_in (sphere sin) -> 2-D inverse -> (x v | x field | store R) ; (load R) -> 2-D forward -> T_out (sphere sout)
 int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
-              const cplx *field, int vec_per_field, cplx *R, const int *active);
+              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod = 0);
+// incdrhoscf ([QE], solve_linter.f90:489-497) for npf (perturbation, frequency) pairs: per z-plane, loop over the nocc
+// bands: 2-D inverse of dpsi, acc += conj(psi_v(r)) dpsi(r); then wgt*acc -> 2-D forward -> columns of the density
+// sphere `sout` (Tout[pf][pz][col], += if accumulate) or, when Rout != null, the real-space planes Rout[pf][pz][nxy]
+int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
+                  double wgt, cplx *Tout, int accumulate);
 // epilogue modes of the final z pass
 struct ZEpilogue {
   int mode;              // 0: out = val ; 1: out = out*keep + g2kin*psi + sigma*psi + val (H.psi) ; 2: out += val

@@ -1,0 +1,157 @@
+"""GPU parity of the screened-Coulomb / Green's-function pipelines (phys/coul, phys/green) against the oracle,
+through the C ABI: solve_linter, coulomb, coulomb_q0G0, unfold_w, invert_epsilon, green_function."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sternheimergw_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name,nk,ngc,fiu", [
+    ("tiny", 2, 9, [0.0, 1.2j]),
+    ("tiny", 2, 5, [0.4j, 1.2j, 3.0j]),          # no static frequency: num_omega = 2 nfreq (solve_linter.f90:238-242)
+    ("si", 1, 11, [0.0, 16j / 13.605698066]),     # gw_si: FREQUENCIES 0, 16i eV
+])
+def test_coulomb_matches_oracle(ctx, name, nk, ngc, fiu):
+    """eps_{G'G}(q,w) for a block of perturbations: converged (thr 1e-12) <= 1e-8 relative to the oracle."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset(name, nk=nk)
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    fiu = np.asarray(fiu, dtype=complex)
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-12)
+    scr = ctx.coulomb(cfg, 1, ngc, ngc, igu, fiu)
+    st = ctx.stats()
+    ref, ierr, so = ps.coulomb(1, ngc, ngc, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=4)
+    assert ierr == 0
+    assert _rel(scr, ref) < 1e-8, _rel(scr, ref)
+    assert st["n_kernel_launch"] > 0 and st["n_linear_op"] > 0
+    # a contiguous sub-block through igstart (do_stern.f90:199-209: every image gets one)
+    scr2 = ctx.coulomb(cfg, 3, ngc, 3, igu, fiu)
+    assert _rel(scr2, ref[:, :, 2:5]) < 1e-8
+    # head: coulomb_q0G0 == the (1,1) element of the first perturbation
+    eps_m = ctx.coulomb_q0G0(cfg, fiu)
+    assert _rel(eps_m, ref[0, :, 0]) < 1e-8
+
+
+def test_coulomb_production_threshold_and_sos(ctx):
+    """Production threshold (1e-4): eps within 10*thr of the converged one; converged one equals sum-over-states."""
+    import sos
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset("tiny")
+    ctx.install_system(syn)
+    fiu = np.array([0.0, 1.2j])
+    ngc = 9
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    tight = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-12), 1, ngc, ngc, igu, fiu)
+    loose = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-4), 1, ngc, ngc, igu, fiu)
+    assert np.abs(loose - tight).max() < 1e-3
+    for ig in (1, 2, 5, 9):
+        assert np.abs(tight[:, :, ig - 1] - sos.eps_sos(syn, ig, ngc, fiu)).max() < 1e-9
+    # the skipped perturbation rule |q+G|^2 < 1e-8 (coulomb.f90:126): at q = 0 the G = 0 column stays zero
+    syn0 = synth.preset("tiny", xq=[0.0, 0.0, 0.0])
+    ctx.install_system(syn0)
+    scr0 = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-10), 1, 5, 3, igu, fiu)
+    assert np.abs(scr0[:, :, 0]).max() == 0.0 and np.abs(scr0[:, :, 1]).max() > 0.0
+
+
+def test_solve_linter_matches_oracle(ctx):
+    """drhoscf(nnr, nfreq) = -dV_H(r) for a generic (non-delta) perturbation, incl. the subspace solver (priority 3)."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import SgwError, select_solver_type
+    syn = synth.preset("tiny")
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    rng = np.random.default_rng(4)
+    dv = np.zeros(syn.nnr, complex)
+    sel = syn.nl[:15] - 1
+    dv[sel] = rng.standard_normal(15) + 1j * rng.standard_normal(15)
+    dvr = oracle.fft3d(dv.reshape(syn.nr, order="F"), +1).reshape(-1, order="F")
+    freq = np.array([0.0, 0.7j, 2.0j])
+    for prio in ((1, 3), (3,)):
+        thr = 1e-12 if prio[0] == 1 else 1e-10
+        out = ctx.solve_linter(select_solver_type(priority=prio, threshold=thr), 1, dvr, freq)
+        ref, ierr, _ = ps.solve_linter(dvr, freq, oracle.make_cfg(priority=prio, threshold=thr), nthreads=4)
+        assert ierr == 0
+        assert out.shape == ref.shape
+        assert _rel(out, ref) < 1e-8, (prio, _rel(out, ref))
+    with pytest.raises(SgwError):
+        ctx.solve_linter(select_solver_type(), 3, dvr, freq)        # iterative branch: not implemented, loud
+
+
+@pytest.mark.parametrize("ngc,nfs", [(7, 3), (59, 2), (130, 2)])
+def test_unfold_and_invert_epsilon(ctx, ngc, nfs):
+    import oracle
+    rng = np.random.default_rng(2)
+    scr_in = rng.standard_normal((ngc, nfs, ngc)) + 1j * rng.standard_normal((ngc, nfs, ngc))
+    scr_in += 4 * np.sqrt(ngc) * np.eye(ngc)[:, None, :]
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    full = ctx.unfold_w(ngc, igu, scr_in)
+    assert np.array_equal(full, oracle.unfold_w(ngc, nfs, igu, scr_in))
+    for lgamma in (False, True):
+        inv = ctx.invert_epsilon(full, lgamma=lgamma)
+        ref, info = oracle.invert_epsilon(full, lgamma=lgamma)
+        assert info == 0
+        assert _rel(inv, ref) < 1e-11
+    # pivoting is needed: a matrix with a zero leading element
+    a = full.copy()
+    a[0, 0, :] = 0.0
+    inv = ctx.invert_epsilon(a)
+    for iw in range(nfs):
+        assert np.abs(inv[:, :, iw] + np.eye(ngc) - np.linalg.inv(a[:, :, iw])).max() < 1e-10
+
+
+def test_invert_epsilon_singular_is_loud(ctx):
+    from sternheimergw_b200 import SgwError
+    a = np.zeros((4, 4, 1), complex)
+    a[0, 0, 0] = 1.0
+    with pytest.raises(SgwError):
+        ctx.invert_epsilon(a)
+
+
+@pytest.mark.parametrize("name", ["tiny", "si"])
+def test_green_function_matches_oracle(ctx, name):
+    """green(ngc, ngp, nfreq): b = -e_{G'}, shifts -omega, strict '<' mask (green.f90:196-213)."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset(name, nk=1 if name == "si" else 2)
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    kq = syn.kpairs[0].kq
+    ngc = 9 if name == "tiny" else 15
+    pos = {int(g): i + 1 for i, g in enumerate(kq.igk)}
+    map_ = np.array([pos.get(ig, 0) for ig in range(1, ngc + 1)], dtype=np.int32)
+    map_[-1] = kq.npw                      # hits the strict '<' of green.f90:212
+    map_[3] = 0                            # a G' outside the k sphere: skipped right-hand side
+    fft_map = np.arange(1, ngc + 1, dtype=np.int32)[::-1].copy()
+    mu = 0.5 * (kq.et[3] + kq.et[4])
+    w = np.array([0.3j, 2.0j, 7.0j])
+    omega = np.concatenate([mu + w, mu - w])
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-12)
+    green = ctx.green_function(cfg, 0, map_, fft_map, omega)
+    ref, ierr, _ = ps.green_function(0, map_, fft_map, omega, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=4)
+    assert ierr == 0
+    assert _rel(green, ref) < 1e-8
+    assert np.abs(green[:, list(fft_map).index(4), :]).max() == 0.0
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
