@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- shifted Sternheimer solves/s on the Si64 synthetic (BASELINE.json configs[4]), one JSON line.
+
+A "step" = one pass of the hot path over one block of G-perturbations: ``sgw_coulomb`` (phys/coul/src/coulomb.f90:29)
+for P perturbations x 128 occupied bands x 63 shifts (32 imaginary frequencies -> +-omega) of the 64-atom Si
+supercell (72^3 FFT grid, npw ~ 24 k, nkb 256), production threshold 1e-4 (thres_coul default).  One solve = one
+(right-hand side, shift) pair converged to the reference's criterion.  Inputs are synthetic (synth/, seed 20261017):
+exact eigenvectors of the synthetic Hamiltonian the operator applies.
+
+  python bench.py [--gpus N --steps K --warmup W]         B200 path (under torchrun for N > 1: one rank per GPU)
+  python bench.py --impl reference [...]                   the CPU restatement of the reference (oracle/), all host cores
+
+value      : whole-job solves/s, operator tables resident in HBM, device time (CUDA events on the library's stream)
+e2e        : same metric through the C ABI with HOST buffers: every step re-installs all operator tables (H2D),
+             runs sgw_coulomb and reads scrcoul back (D2H), wall clock around the blocking calls
+roofline   : the kernel class with the largest share of the timed region, timed live with CUDA events
+cpu_baseline: the oracle (kind "port": the Fortran reference cannot be built here) on a bounded sample, host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "shifted Sternheimer solves/s"
+UNIT = "solves/s"
+NFS = 32               # imaginary frequencies -> 63 shifts (solve_linter.f90:238-252)
+NGC = 1900             # G-perturbations of the q-point (~59 x 32)
+THRESHOLD = 1e-4       # thres_coul default (main/src/gw_input.yml)
+
+
+def workload(name="si64"):
+    import synth
+    syn = synth.preset(name)
+    fiu = synth.imag_freqs(NFS)
+    ngc = min(NGC, syn.ngm)
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    return syn, fiu, ngc, igu
+
+
+def workload_config(syn, P, world):
+    kq = syn.kpairs[0].kq
+    return {"workload": "Si64 synthetic (BASELINE.json configs[4]): 64-atom Si supercell, FFT 72^3, 1 q / 1 k",
+            "fft_grid": list(syn.nr), "npw": int(kq.npw), "nbnd_occ": int(syn.nbnd_occ), "nkb": int(kq.vkb.shape[1]),
+            "nfreq": NFS, "nshift": 2 * NFS - 1, "perturbations_per_step_per_gpu": P, "threshold": THRESHOLD,
+            "bicg_lmax": 4, "solver": "multishift BiCGStab(l), priority (1,3)",
+            "parallelism": f"perturbation blocks over {world} GPU(s) (do_stern.f90:199), gather of eps columns per step",
+            "l2": "inputs larger than L2 (solver state of one step is > 10 GB)"}
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(syn, fiu, ngc, igu, steps, warmup, first_ig=2):
+    """The oracle in the reference's execution order (one band, one vector at a time, unfused BLAS-1), OpenMP over
+    bands on all host cores; each step = ONE perturbation x `cores` bands x 63 shifts (a bounded sample)."""
+    import oracle
+    oracle.build(native=True, force=True)          # -march=native for THIS host
+    cores = len(os.sched_getaffinity(0))
+    ps = oracle.PwSystem(syn, native=True)
+    nb = min(cores, syn.nbnd_occ)
+    ps.set_band_window(0, nb)
+    cfg = oracle.make_cfg(priority=(1, 3), threshold=THRESHOLD)
+    times = []
+    nop = 0
+    for s in range(warmup + steps):
+        t = time.perf_counter()
+        scr, ierr, st = ps.coulomb(first_ig + s, ngc, 1, igu, fiu, cfg, nthreads=cores)
+        dt = time.perf_counter() - t
+        if ierr != 0:
+            raise RuntimeError(f"oracle did not converge (ierr={ierr})")
+        if s >= warmup:
+            times.append(dt)
+            nop += st["n_op"]
+    ps.set_band_window()
+    solves = nb * (2 * NFS - 1)
+    total = sum(times)
+    return {"value": solves * steps / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of 1 perturbation x {nb} bands x {2 * NFS - 1} shifts each (of 128 bands), "
+                      f"OpenMP over bands, {nop} H.psi, {total:.1f} s",
+            "ms_per_step": 1e3 * total / steps, "solves_per_step": solves}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    syn, fiu, ngc, igu = workload()
+    cb = cpu_sample(syn, fiu, ngc, igu, args.steps, args.warmup)
+    cfg = workload_config(syn, 1, 1)
+    cfg["parallelism"] = f"OpenMP over bands, {cb['cores']} host threads (the reference's MPI axes are images/pools)"
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference algorithm (oracle/), not gw.x: no Fortran compiler / QE in this image"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- B200 arm
+def zgemm_peak_tflops():
+    """FP64 tensor denominator: MEASURED_PEAKS.json has no FP64 entry, so measure cuBLAS ZGEMM here (burst)."""
+    import torch
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+    b = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+    for _ in range(2):
+        (a @ b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); (a @ b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 8.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def h2d_bytes(syn, fiu, igu):
+    n = syn.vrs.nbytes + syn.g.nbytes + syn.nl.nbytes + fiu.nbytes + igu.nbytes
+    for kp in syn.kpairs:
+        kq = kp.kq
+        n += kq.nl_igk.nbytes + kq.g2kin.nbytes + kq.vkb.nbytes + kq.dion.nbytes + kq.evq.nbytes
+        n += kp.evc.nbytes + kp.et.nbytes + kp.nl_igk_k.nbytes
+    return int(n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pert", type=int, default=8, help="perturbations per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sternheimergw_b200 import Context, select_solver_type
+    from sternheimergw_b200.dist import gather_columns
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    syn, fiu, ngc, igu = workload()
+    P = args.pert
+    ctx = Context(local_rank)
+    ctx.install_system(syn)
+    ctx.set_profiling(True)
+    cfg = select_solver_type(priority=(1, 3), threshold=THRESHOLD)
+    nocc, nshift = syn.nbnd_occ, 2 * NFS - 1
+    solves_per_step = P * nocc * nshift
+    num_task = [P] * world
+
+    def igstart(s):
+        return 1 + ((s * world + rank) * P) % max(1, ngc - P)
+
+    def step(s, e2e=False):
+        if e2e:
+            ctx.install_system(syn)                       # H2D of every operator table, as a Fortran host would
+        scr = ctx.coulomb(cfg, igstart(s), ngc, P, igu, fiu)            # raises if a solve did not converge
+        st = ctx.stats()
+        prof = ctx.profile()
+        t_coll = 0.0
+        if world > 1:                                     # do_stern.f90:211 gather of the eps columns (NCCL)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gather_columns(scr, num_task)
+            e1.record(); torch.cuda.synchronize()
+            t_coll = e0.elapsed_time(e1)
+        return scr, st, prof, t_coll
+
+    for s in range(args.warmup):
+        step(s)
+    # ---- timed region: tables resident
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, launches, nop = 0.0, 0, 0
+    prof_tot = {}
+    for s in range(args.warmup, args.warmup + args.steps):
+        scr, st, prof, t_coll = step(s)
+        dev_ms += st["ms_total"] + t_coll
+        launches += st["n_kernel_launch"]
+        nop += st["n_linear_op"]
+        for k, v in prof.items():
+            a = prof_tot.setdefault(k, {"ms": 0.0, "regions": 0})
+            a["ms"] += v["ms"]; a["regions"] += v["regions"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    clocks = sampler.stop()
+    # ---- e2e: host buffers in, host buffers out, every step
+    barrier()
+    e0 = time.perf_counter()
+    for s in range(args.warmup, args.warmup + args.steps):
+        step(s, e2e=True)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - e0)
+
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_ms = [float(x) for x in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_solves = solves_per_step * args.steps * world
+    value = total_solves / (dev_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    f64_peak = zgemm_peak_tflops()
+    kq = syn.kpairs[0].kq
+    n, npw, m = kq.npwx, kq.npw, kq.vkb.shape[1] + nocc
+    nnr = syn.nnr
+    L, ns = 4, nshift - 1
+    ncol = int(len(set(((kq.nl_igk - 1) % (syn.nr[0] * syn.nr[1])).tolist())))
+    outer_rhs = nop / (2.0 * L)                      # sum over RHS of outer iterations they took part in
+    # algorithmic work per unit
+    alg = {
+        "fft_plane": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16 + 0.0), "GB/s"),
+        "fft_zpass": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16 + 4 * 16.0 * n), "GB/s"),
+        "gemm_project": ("tensor", nop * 8.0 * npw * m, "TFLOP/s"),
+        "gemm_expand": ("tensor", nop * 8.0 * n * m, "TFLOP/s"),
+        "shift_fused": ("hbm", outer_rhs * (4.0 * ns + (L * (L + 1) // 2 + 1) + L) * 16.0 * n, "GB/s"),
+    }
+    traffic = {}
+    try:
+        traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    except Exception:
+        pass
+    tot_prof = sum(v["ms"] for v in prof_tot.values()) or 1.0
+    kernels = {}
+    for k, v in prof_tot.items():
+        ent = {"ms_per_step": v["ms"] / args.steps, "share_of_profiled": v["ms"] / tot_prof, "regions": v["regions"]}
+        if k in alg and v["ms"] > 0:
+            bound, work, unit = alg[k]
+            ach = work / (v["ms"] * 1e-3) / (1e9 if unit == "GB/s" else 1e12)
+            peak = hbm_peak if bound == "hbm" else f64_peak
+            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "traffic": traffic.get(k)})
+        kernels[k] = ent
+    single = [k for k in alg if k in kernels and "frac" in kernels[k] and k != "fft_zpass"]
+    top = max(single, key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"kernel": top, **{k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
+                "peak_source": hbm_src if kernels[top]["bound"] == "hbm" else
+                "cuBLAS ZGEMM 4096^3 via torch.matmul(complex128), measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
+                "share_of_step": kernels[top]["ms_per_step"] / (dev_ms / args.steps)}
+    fft_ms = prof_tot.get("fft_plane", {"ms": 0})["ms"] + prof_tot.get("fft_zpass", {"ms": 0})["ms"]
+    hpsi_fft = None
+    if fft_ms > 0:
+        surv = nop * (192.0 * nnr + 32.0 * npw)       # six unfused 1-D passes
+        hpsi_fft = {"us_per_vector": 1e3 * fft_ms / nop, "GBps_survey_bytes": surv / (fft_ms * 1e-3) / 1e9,
+                    "frac_of_measured_hbm": surv / (fft_ms * 1e-3) / 1e9 / hbm_peak, "frac_of_8TBps": surv / (fft_ms * 1e-3) / 8e12,
+                    "note": "192*nnr+32*npw bytes/vector is the unfused six-pass count; the fused sphere-pruned pipeline "
+                            "keeps the 2-D transforms in shared memory, so real DRAM traffic is ~20x lower"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(syn, P, world),
+            "wall_ms_per_step": wall_ms / args.steps, "time_to_W_block_ms": dev_ms / args.steps,
+            "solves_per_step": solves_per_step * world, "linear_op_per_step": nop / args.steps,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": total_solves / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(syn, fiu, igu),
+                    "d2h_bytes_per_step": int(ngc * NFS * P * 16 + 4), "ms_per_step": e2e_ms / args.steps,
+                    "note": "host (pageable, caller-owned) arrays -> sgw_set_* + sgw_coulomb -> scrcoul on host, wall clock"},
+            "roofline": roofline, "kernels": kernels, "hpsi_fft": hpsi_fft, "fp64_zgemm_peak_tflops": f64_peak}
+    if world == 1 and not args.no_cpu_baseline:
+        del ctx
+        cb = cpu_sample(syn, fiu, ngc, igu, steps=1, warmup=0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,12 @@ const char *sgw_last_error(const sgw_ctx *ctx);
 int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out);        /* stats of the last solver-level call */
 int sgw_set_profiling(sgw_ctx *ctx, int on);                  /* time H.psi separately (adds syncs) */
 int sgw_device_synchronize(sgw_ctx *ctx);
+/* per-kernel-class device time of the last solver-level call (needs sgw_set_profiling(ctx, 1)): class i took ms[i]
+ * milliseconds in regions[i] timed regions (one region = one kernel launch for fft_plane, gemm_project, gemm_expand,
+ * shift_fused and rho_plane).  Labels via sgw_profile_class_name; the reference's clocks `linear operator` /
+ * `coul solver` (data/timing/src/timing.f90:64,104) are ms_linear_op / ms_solver of sgw_stats. */
+int sgw_get_profile(const sgw_ctx *ctx, int max_classes, double *ms, int64_t *regions, int *nclasses);
+const char *sgw_profile_class_name(int cls);
 
 /* ---- L0: FFT grid and local potential (result of set_vrs, gwq_setup.f90:92; QE dffts) ---- */
 int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, int nr3x);

@@ -277,6 +277,10 @@ class PwSystem:
                              c_int(fiu.size), _p(fiu), _p(scr), C.byref(st), c_int(nthreads))
         return scr, ierr, {"n_op": st.n_op, "n_outer": st.n_outer}
 
+    def set_band_window(self, lo=0, hi=2147483647):
+        """bench only: bounded CPU-baseline samples solve bands lo <= ibnd < hi (default: all, as the reference)."""
+        lib(self.native).orc_set_band_window(c_int(lo), c_int(hi))
+
     def coulomb_q0G0(self, fiu, cfg: SolverCfg):
         L = lib(self.native)
         fiu = _c16(fiu)

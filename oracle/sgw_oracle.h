@@ -138,6 +138,8 @@ typedef struct {
 /* solve_linter.f90:55-624, direct branch (num_iter = 1).  drhoscf: nnr x nfreq */
 int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
                      const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads);
+/* bench-only: restrict the band loops of orc_solve_linter to lo <= ibnd < hi (bounded CPU-baseline samples) */
+void orc_set_band_window(int lo, int hi);
 /* coulomb.f90:29-176.  scrcoul: ngc x nfs x ntask.  ig_unique (1-based G indices), igstart 1-based. */
 int orc_coulomb(const orc_system *sys, const orc_solver_cfg *cfg, int igstart, int ngc, int ntask,
                 const int32_t *ig_unique, int nfs, const zcplx *fiu, zcplx *scrcoul, orc_stats *st,

@@ -62,9 +62,42 @@ static void free_pair(KPair &p) {
   p = KPair();
 }
 
+static cudaEvent_t pool_event(sgw_ctx *ctx) {
+  if (!ctx->ev_pool.empty()) {
+    cudaEvent_t e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void prof_begin(sgw_ctx *ctx, int cls) {
+  ProfRec r;
+  r.cls = cls; r.a = pool_event(ctx); r.b = pool_event(ctx);
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->prof_recs.push_back(r);
+}
+
+void prof_end(sgw_ctx *ctx) { cudaEventRecord(ctx->prof_recs.back().b, ctx->stream); }
+
+static void prof_collect(sgw_ctx *ctx) {
+  for (auto &r : ctx->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ctx->prof_ms[r.cls] += ms; ctx->prof_n[r.cls] += 1; }
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof_recs.clear();
+  ctx->stats.ms_linear_op = ctx->prof_ms[PC_FFT_Z] + ctx->prof_ms[PC_FFT_PLANE] + ctx->prof_ms[PC_GEMM_PROJ] + ctx->prof_ms[PC_GEMM_OUT];
+}
+
 void begin_call(sgw_ctx *ctx) {
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->launches = 0;
+  memset(ctx->prof_ms, 0, sizeof(ctx->prof_ms));
+  memset(ctx->prof_n, 0, sizeof(ctx->prof_n));
   cudaEventRecord(ctx->ev0, ctx->stream);
 }
 
@@ -75,6 +108,7 @@ void end_call(sgw_ctx *ctx) {
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.ms_total = ms;
   ctx->stats.n_kernel_launch = ctx->launches;
+  if (ctx->profiling) prof_collect(ctx);
 }
 
 }  // namespace sgw
@@ -113,6 +147,8 @@ int sgw_destroy(sgw_ctx *ctx) {
   if (ctx->d_twz) cudaFree(ctx->d_twz);
   if (ctx->d_vperm) cudaFree(ctx->d_vperm);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+  for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SGW_OK;
@@ -130,6 +166,19 @@ int sgw_set_profiling(sgw_ctx *ctx, int on) {
   if (!ctx) return SGW_E_ARG;
   ctx->profiling = on != 0;
   return SGW_OK;
+}
+
+int sgw_get_profile(const sgw_ctx *ctx, int max_classes, double *ms, int64_t *regions, int *nclasses) {
+  if (!ctx || !ms || !regions || !nclasses) return SGW_E_ARG;
+  *nclasses = PC_N;
+  for (int i = 0; i < PC_N && i < max_classes; ++i) { ms[i] = ctx->prof_ms[i]; regions[i] = ctx->prof_n[i]; }
+  return SGW_OK;
+}
+
+const char *sgw_profile_class_name(int cls) {
+  static const char *names[PC_N] = {"fft_zpass", "fft_plane", "gemm_project", "gemm_expand", "shift_fused", "seed_blas1",
+                                    "rho_plane", "other"};
+  return cls >= 0 && cls < PC_N ? names[cls] : "";
 }
 
 int sgw_device_synchronize(sgw_ctx *ctx) {

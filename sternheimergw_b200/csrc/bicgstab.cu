@@ -3,8 +3,12 @@
 // for nrhs right-hand sides x nshift shifts at once, entirely on the device:
 //   * per-RHS / per-(RHS,shift) recurrence scalars live in device memory and are advanced by tiny scalar
 //     kernels (one thread per RHS) -- no host round trip inside an outer iteration;
-//   * the BLAS-1 work is fused: every seed vector is read once per step and applied to ALL shifts
-//     (k_bicg_update), the u^sigma_{j+1} recurrence of L19/L26 is formed without its intermediate store;
+//   * the shifted systems never feed back into the seed recurrence, so their BLAS-1 work is DEFERRED: the seed
+//     part keeps snapshots of the residuals r_i it had at every step, and one fused kernel per outer iteration
+//     (k_shift_fused) replays all L BiCG steps and the MR update of every shift with u^sigma_0..u^sigma_L held in
+//     registers.  Per shift and outer iteration that is 4 vector passes (read/write u^sigma_0 and x^sigma)
+//     instead of the reference's 136 -- u^sigma_1..L never touch memory; arithmetic order per
+//     element is the reference's;
 //   * dot products / norms: warp-shuffle + shared-memory block reduction into per-chunk partials that the
 //     scalar kernels sum in a fixed order (deterministic, unconjugated ZDOTU semantics);
 //   * the MR part keeps the reference's modified Gram-Schmidt order (one CTA per RHS, k_mr_mgs);
@@ -13,6 +17,8 @@
 // The inverse storage of phi/theta, the position of the alpha_old update (:666-670) and the corrected L28
 // (:890-894) follow the reference, not Frommer's paper.
 #include "internal.cuh"
+
+#include <algorithm>
 
 namespace sgw {
 
@@ -37,12 +43,21 @@ struct ShiftScal {
   cplx mu[MUCAP], gamma[LCAP], gamma_p[LCAP], gamma_pp[LCAP];
 };
 
+struct StepScal {          // per (rhs, shift, step jj): what the deferred shifted update of that step needs
+  cplx beta, f_old, alpha, f_new, inv_alpha;
+};
+
 struct BicgState {
   int n, nrhs, ns, L;      // ns = number of shifted systems (nshift - 1)
-  cplx *U, *R, *X, *RT;    // seed: U,R [nrhs][L+1][n] ; X, RT [nrhs][n]
-  cplx *US, *XS;           // shifts: US [nrhs][ns][L+1][n] ; XS [nrhs][ns][n]
+  int nsnap;               // L(L+1)/2 + 1 residual snapshots per RHS
+  cplx *U, *R, *RT;        // seed: U,R [nrhs][L+1][n] ; RT [nrhs][n]
+  cplx *XO;                // solutions, in the caller's buffer: [(rhs*(ns+1) + is)*n], is = 0 is the seed system
+  cplx *US0;               // shifts: u^sigma_0 [nrhs][ns][n]
+  cplx *SNAP;              // [nrhs][nsnap][n]: r_i before the update of step jj at jj(jj+1)/2+i, last = r_{L-1} after step L-1
   SeedScal *seed;          // [nrhs]
   ShiftScal *shift;        // [nrhs][ns]
+  StepScal *step;          // [nrhs][ns][L]
+  int *stage;              // [nrhs] this outer iteration: 0 idle, 1 BiCG part only (converged at :237), 2 BiCG + MR
   cplx *part;              // [3][nrhs][nchunk] dot partials
   int nchunk;
   int *active;             // [nrhs]
@@ -52,10 +67,10 @@ struct BicgState {
 
 __device__ __forceinline__ cplx *seedU(const BicgState &s, int b, int i) { return s.U + ((long)b * (s.L + 1) + i) * s.n; }
 __device__ __forceinline__ cplx *seedR(const BicgState &s, int b, int i) { return s.R + ((long)b * (s.L + 1) + i) * s.n; }
-__device__ __forceinline__ cplx *shiftU(const BicgState &s, int b, int is, int i) {
-  return s.US + (((long)b * s.ns + is) * (s.L + 1) + i) * s.n;
-}
-__device__ __forceinline__ cplx *shiftX(const BicgState &s, int b, int is) { return s.XS + ((long)b * s.ns + is) * s.n; }
+__device__ __forceinline__ cplx *seedX(const BicgState &s, int b) { return s.XO + ((long)b * (s.ns + 1)) * s.n; }
+__device__ __forceinline__ cplx *shiftU0(const BicgState &s, int b, int is) { return s.US0 + ((long)b * s.ns + is) * s.n; }
+__device__ __forceinline__ cplx *shiftX(const BicgState &s, int b, int is) { return s.XO + ((long)b * (s.ns + 1) + is + 1) * s.n; }
+__device__ __forceinline__ cplx *snap(const BicgState &s, int b, int k) { return s.SNAP + ((long)b * s.nsnap + k) * s.n; }
 
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ cplx block_reduce(cplx v, cplx *sm /* >= 32 */) {
@@ -159,9 +174,9 @@ __global__ void __launch_bounds__(BT) k_init_vec(BicgState s, const cplx *__rest
   seedR(s, b, 0)[e] = v;
   s.RT[(long)b * s.n + e] = v;
   seedU(s, b, 0)[e] = z;
-  s.X[(long)b * s.n + e] = z;
+  seedX(s, b)[e] = z;
   for (int is = 0; is < s.ns; ++is) {
-    shiftU(s, b, is, 0)[e] = z;
+    shiftU0(s, b, is)[e] = z;
     shiftX(s, b, is)[e] = z;
   }
 }
@@ -178,29 +193,39 @@ __global__ void k_scal_beta(BicgState s, int jj) {
   sd.rho_old = sd.rho;                                               // :599
 }
 
-// L11: alpha = rho / (u_{j+1}, rt0); L13 scalars of every shift; L18 alpha_old = alpha (after the shift loop)
-__global__ void k_scal_alpha(BicgState s) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.nrhs || !s.active[b]) return;
+// L11: alpha = rho / (u_{j+1}, rt0); L13 scalars of every shift (kept per step for the deferred shifted update);
+// L18 alpha_old = alpha (after the shift loop).  One CTA per RHS, threads over shifts.
+__global__ void __launch_bounds__(128) k_scal_alpha(BicgState s, int jj) {
+  const int b = blockIdx.x;
+  if (!s.active[b]) return;
   SeedScal &sd = s.seed[b];
-  sd.alpha = cdiv(sd.rho, sum_part(s, 0, b));                        // :614
+  __shared__ cplx sh_alpha;
+  if (threadIdx.x == 0) sh_alpha = cdiv(sd.rho, sum_part(s, 0, b));   // :614
+  __syncthreads();
+  const cplx alpha = sh_alpha, beta = sd.beta, alpha_old = sd.alpha_old;
   const cplx one = cmake(1.0, 0.0);
-  for (int is = 0; is < s.ns; ++is) {
+  for (int is = threadIdx.x; is < s.ns; is += blockDim.x) {
     ShiftScal &a = s.shift[(long)b * s.ns + is];
+    StepScal &t = s.step[((long)b * s.ns + is) * s.L + jj];
     // :629-631
     const cplx ratio = cdiv(a.inv_phi, a.inv_phi_old);
-    cplx den = cadd(one, cmul(sd.alpha, a.sigma));
-    den = cadd(den, cmul(cdiv(cmul(sd.alpha, sd.beta), sd.alpha_old), csub(ratio, one)));
+    cplx den = cadd(one, cmul(alpha, a.sigma));
+    den = cadd(den, cmul(cdiv(cmul(alpha, beta), alpha_old), csub(ratio, one)));
     a.inv_phi_new = cdiv(a.inv_phi, den);
-    a.beta = cmul(cmul(ratio, ratio), sd.beta);                      // :633
-    a.alpha = cmul(cdiv(a.inv_phi_new, a.inv_phi), sd.alpha);        // :635
+    a.beta = cmul(cmul(ratio, ratio), beta);                         // :633
+    a.alpha = cmul(cdiv(a.inv_phi_new, a.inv_phi), alpha);           // :635
     a.f_old = cmul(a.inv_theta, a.inv_phi);                          // :638
     a.inv_phi_old = a.inv_phi;                                       // :655
     a.inv_phi = a.inv_phi_new;                                       // :657
     a.f_new = cmul(a.inv_theta, a.inv_phi);                          // :693 (sign applied in the update)
     a.inv_alpha = cdiv(one, a.alpha);                                // :695
+    t.beta = a.beta; t.f_old = a.f_old; t.alpha = a.alpha; t.f_new = a.f_new; t.inv_alpha = a.inv_alpha;
   }
-  sd.alpha_old = sd.alpha;                                           // :670
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sd.alpha = alpha;
+    sd.alpha_old = alpha;                                            // :670
+  }
 }
 
 // ---------------------------------------------------------------- bicg_part vector updates
@@ -216,48 +241,27 @@ __global__ void __launch_bounds__(BT) k_seed_u(BicgState s, int jj) {
   }
 }
 
-// Everything between the two operator applications of step jj plus the post-operator shifted update:
-//   shifts: L15 u^_i = f r_i - beta^ u^_i (i<=jj); L17 x^ += alpha^ u^_0; L19+L26 u^_{j+1} without the store
-//   seed  : L22 r_i -= alpha u_{i+1} (i<=jj); L25 x += alpha u_0
-// (L26 only needs r_j before/after L22 and the updated u^_j, all local to one vector element.)
+// Seed part of step jj between the two operator applications: L22 r_i -= alpha u_{i+1} (i<=jj); L25 x += alpha u_0.
+// The residuals the shifted systems will need for THIS step (r_i before the update, and r_{L-1} after the last
+// one) are kept as snapshots; the shifted updates themselves are deferred to k_shift_fused.
 __global__ void __launch_bounds__(BT) k_bicg_update(BicgState s, int jj) {
   const int b = blockIdx.y;
   if (!s.active[b]) return;
-  extern __shared__ cplx ssc[];   // per shift: beta, f_old, alpha, f_new, inv_alpha, sigma
-  for (int i = threadIdx.x; i < s.ns; i += BT) {
-    const ShiftScal &a = s.shift[(long)b * s.ns + i];
-    ssc[6 * i + 0] = a.beta; ssc[6 * i + 1] = a.f_old; ssc[6 * i + 2] = a.alpha;
-    ssc[6 * i + 3] = a.f_new; ssc[6 * i + 4] = a.inv_alpha; ssc[6 * i + 5] = a.sigma;
-  }
-  __syncthreads();
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n) return;
   const cplx alpha = s.seed[b].alpha, malpha = cneg(alpha);
+  const bool keep = s.ns > 0;
   for (int i = 0; i <= jj; ++i) {
     cplx *r = seedR(s, b, i);
     const cplx r_old = r[e];
     const cplx r_new = cfma(malpha, seedU(s, b, i + 1)[e], r_old);          // :676
     r[e] = r_new;
-    for (int is = 0; is < s.ns; ++is) {
-      const cplx beta_s = ssc[6 * is + 0], f_old = ssc[6 * is + 1];
-      cplx *us = shiftU(s, b, is, i);
-      cplx u = cmul(cneg(beta_s), us[e]);                                    // :644
-      u = cfma(f_old, r_old, u);                                             // :645
-      us[e] = u;
-      if (i == 0) {
-        cplx *xs = shiftX(s, b, is);
-        xs[e] = cfma(ssc[6 * is + 2], u, xs[e]);                             // :650
-      }
-      if (i == jj) {
-        cplx t = cmul(f_old, r_old);                                         // :661-662
-        t = cfma(cneg(ssc[6 * is + 3]), r_new, t);                           // :693-694
-        t = cmul(ssc[6 * is + 4], t);                                        // :695
-        t = cfma(cneg(ssc[6 * is + 5]), u, t);                               // :696
-        shiftU(s, b, is, jj + 1)[e] = t;
-      }
+    if (keep) {
+      snap(s, b, jj * (jj + 1) / 2 + i)[e] = r_old;
+      if (jj == s.L - 1 && i == jj) snap(s, b, s.nsnap - 1)[e] = r_new;
     }
   }
-  cplx *x = s.X + (long)b * s.n;
+  cplx *x = seedX(s, b);
   x[e] = cfma(alpha, seedU(s, b, 0)[e], x[e]);                               // :685
 }
 
@@ -278,13 +282,20 @@ __global__ void __launch_bounds__(BT) k_norm_r0(BicgState s) {
   if (threadIdx.x == 0) s.part[((long)2 * s.nrhs + b) * s.nchunk + blockIdx.x] = acc;
 }
 
-__global__ void k_check(BicgState s, double threshold, int outer_iter) {
+// phase 1 = after bicg_part (:237), phase 2 = after mr_part (:245)
+__global__ void k_check(BicgState s, double threshold, int outer_iter, int phase) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.nrhs || !s.active[b]) return;
+  if (b >= s.nrhs) return;
+  if (!s.active[b]) {
+    if (phase == 1) s.stage[b] = 0;
+    return;
+  }
   const cplx p = sum_part(s, 2, b);
   const double nrm = sqrt(p.x + p.y);
   s.iters[b] = outer_iter;
-  if (nrm < threshold) s.active[b] = 0;     // :299 strict '<'
+  const bool conv = nrm < threshold;        // :299 strict '<'
+  if (phase == 1) s.stage[b] = conv ? 1 : 2;
+  if (conv) s.active[b] = 0;
   else atomicAdd(s.nactive, 1);
 }
 
@@ -372,67 +383,139 @@ __global__ void __launch_bounds__(1024) k_mr_mgs(BicgState s) {
   }
 }
 
-// L14-L17 seed, L28-L34 shifts, delayed L32 residual update (:833-925) in one pass over the vectors
-__global__ void __launch_bounds__(BT) k_mr_update(BicgState s) {
+// Deferred update of the shifted systems for one whole outer iteration (bicg_part :621-664,:688-698 for every
+// step jj, then mr_part :850-911), one thread per vector element, u^sigma_0..u^sigma_L in registers.
+// Must run after k_mr_mgs (needs r_1..r_{L-1} after the Gram-Schmidt) and BEFORE k_mr_seed (needs r_0 before :919-925).
+// LT > 0: compile-time L with the residual snapshots preloaded into registers; LT == 0: any L <= LCAP-1.
+constexpr int SHIFT_CHUNK = 32;
+template <int LT>
+__global__ void __launch_bounds__(BT) k_shift_fused(BicgState s, int chunk) {
   const int b = blockIdx.y;
-  if (!s.active[b]) return;
-  const int L = s.L;
-  extern __shared__ cplx ssc[];   // seed: gamma[L], gamma_p[L], gamma_pp[L]; per shift: inv_psi, inv_xi*gamma_p1, inv_xi*gamma_pp[L-1]
-  const SeedScal &sd = s.seed[b];
-  cplx *sg = ssc, *sgp = ssc + L, *sgpp = ssc + 2 * L, *sh = ssc + 3 * L;
-  const int per = L + 1;
-  for (int i = threadIdx.x; i < L; i += BT) { sg[i] = sd.gamma[i]; sgp[i] = sd.gamma_p[i]; sgpp[i] = i < L - 1 ? sd.gamma_pp[i] : cmake(0, 0); }
-  for (int i = threadIdx.x; i < s.ns; i += BT) {
-    const ShiftScal &a = s.shift[(long)b * s.ns + i];
-    sh[per * i + 0] = cdiv(cmake(1.0, 0.0), a.psi);                               // :910
-    sh[per * i + 1] = cmul(a.gamma_p[0], a.inv_xi);                               // :888
-    for (int jj = 1; jj <= L - 1; ++jj) sh[per * i + 1 + jj] = cmul(a.gamma_pp[jj - 1], a.inv_xi);   // :904
+  const int stage = s.stage[b];
+  if (stage == 0) return;
+  const int L = LT > 0 ? LT : s.L;
+  const int is0 = blockIdx.z * chunk, nsl = min(chunk, s.ns - is0);
+  extern __shared__ cplx ssc[];   // per local shift: [5*L step scalars][sigma][1/psi][inv_xi*gamma_p1][inv_xi*gamma_pp 1..L-1]
+  const int per = 5 * L + 2 + L;
+  for (int t = threadIdx.x; t < nsl * L; t += BT) {
+    const int il = t / L, jj = t % L;
+    const StepScal &q = s.step[((long)b * s.ns + is0 + il) * L + jj];
+    cplx *d = ssc + il * per + 5 * jj;
+    d[0] = q.beta; d[1] = q.f_old; d[2] = q.alpha; d[3] = q.f_new; d[4] = q.inv_alpha;
   }
+  for (int il = threadIdx.x; il < nsl; il += BT) {
+    const ShiftScal &a = s.shift[(long)b * s.ns + is0 + il];
+    cplx *d = ssc + il * per + 5 * L;
+    d[0] = a.sigma;
+    if (stage == 2) {
+      d[1] = cdiv(cmake(1.0, 0.0), a.psi);                                        // :910
+      d[2] = cmul(a.gamma_p[0], a.inv_xi);                                        // :888
+      for (int jj = 1; jj <= L - 1; ++jj) d[2 + jj] = cmul(a.gamma_pp[jj - 1], a.inv_xi);   // :904
+    }
+  }
+  __shared__ cplx sgam[LCAP];
+  for (int i = threadIdx.x; i < L; i += BT) sgam[i] = s.seed[b].gamma[i];
   __syncthreads();
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n) return;
-  // seed x and u0
+  constexpr int NSN = LT > 0 ? LT * (LT + 1) / 2 + 1 : 1;
+  constexpr int NRR = LT > 0 ? LT : 1;
+  constexpr int NUS = LT > 0 ? LT + 1 : LCAP;
+  cplx sn[NSN], rr[NRR];
+  const cplx *snapg = snap(s, b, 0) + e;
+  const long n = s.n;
+  if (LT > 0) {
+#pragma unroll
+    for (int k = 0; k < NSN; ++k) sn[k] = snapg[(long)k * n];
+    if (stage == 2) {
+#pragma unroll
+      for (int j = 0; j < NRR; ++j) rr[j] = seedR(s, b, j)[e];
+    }
+  }
+  const int last = LT > 0 ? NSN - 1 : s.nsnap - 1;
+  for (int il = 0; il < nsl; ++il) {
+    const cplx *sc = ssc + il * per;
+    const cplx sigma = sc[5 * L];
+    cplx *pu0 = shiftU0(s, b, is0 + il) + e, *px = shiftX(s, b, is0 + il) + e;
+    cplx us[NUS];
+    us[0] = *pu0;
+    cplx xs = *px;
+#pragma unroll
+    for (int jj = 0; jj < (LT > 0 ? LT : L); ++jj) {
+      const cplx beta_s = sc[5 * jj], f_old = sc[5 * jj + 1], alpha_s = sc[5 * jj + 2], f_new = sc[5 * jj + 3],
+                 inv_alpha = sc[5 * jj + 4];
+#pragma unroll
+      for (int i = 0; i <= jj; ++i) {
+        const int k = jj * (jj + 1) / 2 + i;
+        const cplx r_old = LT > 0 ? sn[LT > 0 ? k : 0] : snapg[(long)k * n];
+        cplx u = cmul(cneg(beta_s), us[i]);                                      // :644
+        u = cfma(f_old, r_old, u);                                               // :645
+        us[i] = u;
+        if (i == 0) xs = cfma(alpha_s, u, xs);                                   // :650
+        if (i == jj) {
+          const int kn = (jj < L - 1) ? (jj + 1) * (jj + 2) / 2 + jj : last;
+          const cplx r_new = LT > 0 ? sn[LT > 0 ? kn : 0] : snapg[(long)kn * n];
+          cplx t = cmul(f_old, r_old);                                           // :661-662
+          t = cfma(cneg(f_new), r_new, t);                                       // :693-694
+          t = cmul(inv_alpha, t);                                                // :695
+          t = cfma(cneg(sigma), u, t);                                           // :696
+          us[jj + 1] = t;
+        }
+      }
+    }
+    if (stage == 2) {
+      const cplx *c = sc + 5 * L + 1;    // c[0] = 1/psi, c[1] = inv_xi gamma_p1, c[1+jj] = inv_xi gamma_pp_jj
+      const cplx r0 = LT > 0 ? rr[0] : seedR(s, b, 0)[e];
+      xs = cfma(c[1], r0, xs);                                                   // :889
+      cplx u0 = cfma(cneg(sgam[L - 1]), us[L], us[0]);                           // :893
+#pragma unroll
+      for (int jj = 1; jj <= (LT > 0 ? LT : L) - 1; ++jj) {
+        u0 = cfma(cneg(sgam[jj - 1]), us[jj], u0);                               // :900
+        const cplx rj = LT > 0 ? rr[LT > 0 ? jj : 0] : seedR(s, b, jj)[e];
+        xs = cfma(c[1 + jj], rj, xs);                                            // :905
+      }
+      *pu0 = cmul(c[0], u0);                                                     // :911
+    }
+    *px = xs;
+  }
+}
+
+// L14-L17 of the seed system and the delayed L32 residual update (:833-844, :919-925)
+__global__ void __launch_bounds__(BT) k_mr_seed(BicgState s) {
+  const int b = blockIdx.y;
+  if (!s.active[b]) return;
+  const int L = s.L;
+  __shared__ cplx sg[LCAP], sgp[LCAP], sgpp[LCAP];
+  const SeedScal &sd = s.seed[b];
+  for (int i = threadIdx.x; i < L; i += BT) { sg[i] = sd.gamma[i]; sgp[i] = sd.gamma_p[i]; sgpp[i] = i < L - 1 ? sd.gamma_pp[i] : cmake(0, 0); }
+  __syncthreads();
+  const int e = blockIdx.x * BT + threadIdx.x;
+  if (e >= s.n) return;
   cplx r0 = seedR(s, b, 0)[e];
-  cplx x = cfma(sg[0], r0, s.X[(long)b * s.n + e]);                               // :833
+  cplx *px = seedX(s, b) + e;
+  cplx x = cfma(sg[0], r0, *px);                                                  // :833
   cplx u0 = cfma(cneg(sg[L - 1]), seedU(s, b, L)[e], seedU(s, b, 0)[e]);          // :835
   for (int jj = 1; jj <= L - 1; ++jj) {
     u0 = cfma(cneg(sg[jj - 1]), seedU(s, b, jj)[e], u0);                          // :841
     x = cfma(sgpp[jj - 1], seedR(s, b, jj)[e], x);                                // :844
   }
-  s.X[(long)b * s.n + e] = x;
+  *px = x;
   seedU(s, b, 0)[e] = u0;
-  // shifted systems
-  for (int is = 0; is < s.ns; ++is) {
-    const cplx *c = sh + per * is;
-    cplx xs = cfma(c[1], r0, shiftX(s, b, is)[e]);                                // :889
-    cplx us = cfma(cneg(sg[L - 1]), shiftU(s, b, is, L)[e], shiftU(s, b, is, 0)[e]);   // :893
-    for (int jj = 1; jj <= L - 1; ++jj) {
-      us = cfma(cneg(sg[jj - 1]), shiftU(s, b, is, jj)[e], us);                   // :900
-      xs = cfma(c[1 + jj], seedR(s, b, jj)[e], xs);                               // :905
-    }
-    shiftU(s, b, is, 0)[e] = cmul(c[0], us);                                      // :911
-    shiftX(s, b, is)[e] = xs;
-  }
-  // delayed residual update :919-925
-  for (int jj = 1; jj <= L; ++jj) r0 = cfma(cneg(sgp[jj - 1]), seedR(s, b, jj)[e], r0);
+  for (int jj = 1; jj <= L; ++jj) r0 = cfma(cneg(sgp[jj - 1]), seedR(s, b, jj)[e], r0);   // :919-925
   seedR(s, b, 0)[e] = r0;
 }
 
 // ---------------------------------------------------------------- finish: copy out (:258-261), NaN scan (:264-267)
-__global__ void __launch_bounds__(BT) k_copy_out(BicgState s, cplx *__restrict__ xout, int *__restrict__ ierr, int max_iter,
-                                                  const int *__restrict__ todo) {
+// the solutions already live in the caller's buffer (:258-261); NaN scan (:264-267)
+__global__ void __launch_bounds__(BT) k_nan_scan(BicgState s, int *__restrict__ ierr, const int *__restrict__ todo) {
   const int b = blockIdx.y;
   if (todo && !todo[b]) return;
   const int e = blockIdx.x * BT + threadIdx.x;
   const int nshift = s.ns + 1;
   bool bad = false;
   if (e < s.n) {
-    cplx v = s.X[(long)b * s.n + e];
-    xout[((long)b * nshift) * s.n + e] = v;
-    bad |= (v.x != v.x) || (v.y != v.y);
-    for (int is = 0; is < s.ns; ++is) {
-      v = shiftX(s, b, is)[e];
-      xout[((long)b * nshift + is + 1) * s.n + e] = v;
+    for (int is = 0; is < nshift; ++is) {
+      const cplx v = s.XO[((long)b * nshift + is) * s.n + e];
       bad |= (v.x != v.x) || (v.y != v.y);
     }
   }
@@ -447,6 +530,16 @@ __global__ void k_set_ierr(BicgState s, int *__restrict__ ierr, const int *__res
 }
 
 // ---------------------------------------------------------------- driver
+template <int LT>
+static int launch_shift_fused(sgw_ctx *ctx, const BicgState &s, int chunk, size_t smem) {
+  if (smem > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_shift_fused<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((s.n + BT - 1) / BT), (unsigned)s.nrhs, (unsigned)((s.ns + chunk - 1) / chunk));
+  ProfScope prof(ctx, PC_SHIFT);
+  k_shift_fused<LT><<<grid, BT, smem, ctx->stream>>>(s, chunk);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
 int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo) {
   if (lmax < 1 || lmax > LCAP - 1) {
     ctx->err = "bicg_lmax must be in 1..15";
@@ -455,18 +548,21 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   if (sb.nrhs <= 0) return SGW_OK;
   BicgState s;
   s.n = sb.n; s.nrhs = sb.nrhs; s.ns = sb.nshift - 1; s.L = lmax;
+  s.nsnap = lmax * (lmax + 1) / 2 + 1;
+  s.XO = sb.d_x;
   const long n = s.n, nr = s.nrhs, L1 = lmax + 1;
   SGW_CHECK(ws(ctx, "bi_U", (size_t)(nr * L1 * n), &s.U));
   SGW_CHECK(ws(ctx, "bi_R", (size_t)(nr * L1 * n), &s.R));
-  SGW_CHECK(ws(ctx, "bi_X", (size_t)(nr * n), &s.X));
   SGW_CHECK(ws(ctx, "bi_RT", (size_t)(nr * n), &s.RT));
-  SGW_CHECK(ws(ctx, "bi_US", (size_t)(nr * s.ns * L1 * n) + 1, &s.US));
-  SGW_CHECK(ws(ctx, "bi_XS", (size_t)(nr * s.ns * n) + 1, &s.XS));
+  SGW_CHECK(ws(ctx, "bi_US0", (size_t)(nr * s.ns * n) + 1, &s.US0));
+  SGW_CHECK(ws(ctx, "bi_SNAP", s.ns > 0 ? (size_t)(nr * s.nsnap * n) : 1, &s.SNAP));
   SGW_CHECK(ws(ctx, "bi_seed", (size_t)nr, &s.seed));
   SGW_CHECK(ws(ctx, "bi_shift", (size_t)(nr * s.ns) + 1, &s.shift));
+  SGW_CHECK(ws(ctx, "bi_step", (size_t)(nr * s.ns * lmax) + 1, &s.step));
   s.nchunk = (int)((n + BT * DOT_EPT - 1) / (BT * DOT_EPT));
   SGW_CHECK(ws(ctx, "bi_part", (size_t)(3 * nr * s.nchunk), &s.part));
   SGW_CHECK(ws(ctx, "bi_active", (size_t)nr, &s.active));
+  SGW_CHECK(ws(ctx, "bi_stage", (size_t)nr, &s.stage));
   SGW_CHECK(ws(ctx, "bi_iters", (size_t)nr, &s.iters));
   SGW_CHECK(ws(ctx, "bi_nactive", (size_t)1, &s.nactive));
   int *h_nactive = nullptr;
@@ -476,10 +572,11 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   const int gb = (int)((nr + 127) / 128);
   const dim3 gvec((unsigned)((n + BT - 1) / BT), (unsigned)nr);
   const dim3 gdot((unsigned)s.nchunk, (unsigned)nr);
-  const size_t sm_bicg = (size_t)(6 * s.ns + 1) * sizeof(cplx);
-  const size_t sm_mr = (size_t)(3 * lmax + (lmax + 1) * s.ns + 1) * sizeof(cplx);
-  if (sm_bicg > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_bicg_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bicg));
-  if (sm_mr > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_mr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mr));
+  // shifts per CTA of the fused update: scalars of one chunk must fit in 48 KB of shared memory
+  const int per_shift = 5 * lmax + 2 + lmax;
+  int chunk = std::min(SHIFT_CHUNK, (int)(48 * 1024 / (per_shift * sizeof(cplx))));
+  chunk = std::max(1, std::min(chunk, std::max(1, s.ns)));
+  const size_t sm_fused = (size_t)chunk * per_shift * sizeof(cplx);
 
   k_init_scal<<<gb, 128, 0, st>>>(s, sb.d_sigma, d_todo);
   SGW_LAUNCH_CHECK();
@@ -487,60 +584,78 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   SGW_LAUNCH_CHECK();
 
   const long ldv = n;   // vectors inside U/R are contiguous with stride (L+1)*n between RHS
-  int outer_done = 0;
   int rc = SGW_OK;
   for (int iter = 1; iter <= max_iter && rc == SGW_OK; ++iter) {
-    // ---- bicg_part
+    // ---- bicg_part (seed system; the shifted systems only record their step scalars)
     for (int jj = 0; jj < lmax && rc == SGW_OK; ++jj) {
       DotSpec d; d.nd = 1; d.ka[0] = 0; d.ia[0] = jj; d.kb[0] = 2; d.ib[0] = 0;     // (r_j, rt0)
-      k_dots<<<gdot, BT, 0, st>>>(s, d);
-      SGW_LAUNCH_CHECK();
-      k_scal_beta<<<gb, 128, 0, st>>>(s, jj);
-      SGW_LAUNCH_CHECK();
-      k_seed_u<<<gvec, BT, 0, st>>>(s, jj);
-      SGW_LAUNCH_CHECK();
+      {
+        ProfScope prof(ctx, PC_SEED);
+        k_dots<<<gdot, BT, 0, st>>>(s, d);
+        SGW_LAUNCH_CHECK();
+        k_scal_beta<<<gb, 128, 0, st>>>(s, jj);
+        SGW_LAUNCH_CHECK();
+        k_seed_u<<<gvec, BT, 0, st>>>(s, jj);
+        SGW_LAUNCH_CHECK();
+      }
       // u_{j+1} = A u_j   (bicgstab.f90:611)
       rc = apply_operator(ctx, sb.slot, sb.alpha_pv, s.nrhs, s.U + (long)jj * n, L1 * ldv, &s.seed[0].sigma,
                           sizeof(SeedScal) / sizeof(cplx), s.U + (long)(jj + 1) * n, L1 * ldv, s.active);
       if (rc != SGW_OK) break;
       d.ka[0] = 1; d.ia[0] = jj + 1;                                                // (u_{j+1}, rt0)
-      k_dots<<<gdot, BT, 0, st>>>(s, d);
-      SGW_LAUNCH_CHECK();
-      k_scal_alpha<<<gb, 128, 0, st>>>(s);
-      SGW_LAUNCH_CHECK();
-      k_bicg_update<<<gvec, BT, sm_bicg, st>>>(s, jj);
-      SGW_LAUNCH_CHECK();
+      {
+        ProfScope prof(ctx, PC_SEED);
+        k_dots<<<gdot, BT, 0, st>>>(s, d);
+        SGW_LAUNCH_CHECK();
+        k_scal_alpha<<<(unsigned)nr, 128, 0, st>>>(s, jj);
+        SGW_LAUNCH_CHECK();
+        k_bicg_update<<<gvec, BT, 0, st>>>(s, jj);
+        SGW_LAUNCH_CHECK();
+      }
       // r_{j+1} = A r_j   (bicgstab.f90:682)
       rc = apply_operator(ctx, sb.slot, sb.alpha_pv, s.nrhs, s.R + (long)jj * n, L1 * ldv, &s.seed[0].sigma,
                           sizeof(SeedScal) / sizeof(cplx), s.R + (long)(jj + 1) * n, L1 * ldv, s.active);
     }
     if (rc != SGW_OK) break;
-    ctx->stats.n_linear_op += 0;   // counted from iteration totals after the loop
-    SGW_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), st));
-    k_norm_r0<<<gdot, BT, 0, st>>>(s);
-    SGW_LAUNCH_CHECK();
-    k_check<<<gb, 128, 0, st>>>(s, threshold, iter);                                // :237
-    SGW_LAUNCH_CHECK();
-    // ---- mr_part (RHS that converged above are masked out)
-    k_mr_mgs<<<(unsigned)nr, 1024, 0, st>>>(s);
-    SGW_LAUNCH_CHECK();
-    k_mr_update<<<gvec, BT, sm_mr, st>>>(s);
-    SGW_LAUNCH_CHECK();
-    SGW_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), st));
-    k_norm_r0<<<gdot, BT, 0, st>>>(s);
-    SGW_LAUNCH_CHECK();
-    k_check<<<gb, 128, 0, st>>>(s, threshold, iter);                                // :245
-    SGW_LAUNCH_CHECK();
+    {
+      ProfScope prof(ctx, PC_SEED);
+      SGW_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), st));
+      k_norm_r0<<<gdot, BT, 0, st>>>(s);
+      SGW_LAUNCH_CHECK();
+      k_check<<<gb, 128, 0, st>>>(s, threshold, iter, 1);                           // :237
+      SGW_LAUNCH_CHECK();
+      // ---- mr_part (RHS that converged above are masked out)
+      k_mr_mgs<<<(unsigned)nr, 1024, 0, st>>>(s);
+      SGW_LAUNCH_CHECK();
+    }
+    if (s.ns > 0) {
+      switch (lmax) {
+        case 1: rc = launch_shift_fused<1>(ctx, s, chunk, sm_fused); break;
+        case 2: rc = launch_shift_fused<2>(ctx, s, chunk, sm_fused); break;
+        case 4: rc = launch_shift_fused<4>(ctx, s, chunk, sm_fused); break;
+        default: rc = launch_shift_fused<0>(ctx, s, chunk, sm_fused); break;
+      }
+      if (rc != SGW_OK) break;
+    }
+    {
+      ProfScope prof(ctx, PC_SEED);
+      k_mr_seed<<<gvec, BT, 0, st>>>(s);
+      SGW_LAUNCH_CHECK();
+      SGW_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), st));
+      k_norm_r0<<<gdot, BT, 0, st>>>(s);
+      SGW_LAUNCH_CHECK();
+      k_check<<<gb, 128, 0, st>>>(s, threshold, iter, 2);                           // :245
+      SGW_LAUNCH_CHECK();
+    }
     SGW_CUDA(cudaMemcpyAsync(h_nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGW_CUDA(cudaStreamSynchronize(st));
-    outer_done = iter;
     if (*h_nactive == 0) break;
   }
   cudaFreeHost(h_nactive);
   if (rc != SGW_OK) return rc;
   k_set_ierr<<<gb, 128, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();
-  k_copy_out<<<gvec, BT, 0, st>>>(s, sb.d_x, sb.d_ierr, max_iter, d_todo);
+  k_nan_scan<<<gvec, BT, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();
   // statistics: every RHS did 2*L operator applications per outer iteration it took part in
   {
@@ -552,7 +667,6 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
       if (it[b] > ctx->stats.n_outer_max) ctx->stats.n_outer_max = it[b];
     }
   }
-  (void)outer_done;
   return SGW_OK;
 }
 

@@ -297,6 +297,7 @@ int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long 
   const size_t smem = zpass_smem(ctx);
   SGW_CHECK(set_smem(ctx, k_zpass_g2r, smem));
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
+  ProfScope prof(ctx, PC_FFT_Z);
   k_zpass_g2r<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), in, ld, T, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
@@ -309,6 +310,7 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
   SGW_CHECK(set_smem(ctx, k_zpass_r2g, smem));
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
   const double scale = 1.0 / ((double)ctx->nr1 * ctx->nr2 * ctx->nr3);
+  ProfScope prof(ctx, PC_FFT_Z);
   k_zpass_r2g<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), T, out, ld, epi, scale, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
@@ -322,6 +324,7 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   GridDev g = grid_dev(ctx);
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
+  ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
   switch (mode) {
     case PLANE_VLOC:
       SGW_CHECK(set_smem(ctx, k_plane<PLANE_VLOC>, smem));
@@ -350,6 +353,7 @@ int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, 
   const size_t smem = (size_t)(2 * ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx);
   SGW_CHECK(set_smem(ctx, k_plane_rho, smem));
   dim3 grid(npf, ctx->nr3);
+  ProfScope prof(ctx, PC_RHO_PLANE);
   k_plane_rho<<<grid, PTHREADS, smem, ctx->stream>>>(grid_dev(ctx), sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
   SGW_LAUNCH_CHECK();
   return SGW_OK;

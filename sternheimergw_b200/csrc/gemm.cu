@@ -198,15 +198,20 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
   SGW_CHECK(ws(ctx, "nl_coef", (size_t)split_stride, &coef));
   {
     dim3 grid((m + BM - 1) / BM, (nvec + BN - 1) / BN, nsplit);
+    ProfScope prof(ctx, PC_GEMM_PROJ);
     k_zgemm<true, true><<<grid, GT, 0, ctx->stream>>>(m, nvec, ks.npw, ks.d_P, ks.npwx, psi, ldpsi, part, m, cmake(1, 0),
                                                      cmake(0, 0), kchunk, split_stride, active);
     SGW_LAUNCH_CHECK();
   }
-  k_coef_finish<<<nvec, 128, (size_t)m * sizeof(cplx), ctx->stream>>>(m, ks.nkb, nvec, nsplit, part, split_stride, ks.d_dion,
+  {
+    ProfScope prof(ctx, PC_OTHER);
+    k_coef_finish<<<nvec, 128, (size_t)m * sizeof(cplx), ctx->stream>>>(m, ks.nkb, nvec, nsplit, part, split_stride, ks.d_dion,
                                                                       alpha_pv, coef, active);
-  SGW_LAUNCH_CHECK();
+    SGW_LAUNCH_CHECK();
+  }
   {
     dim3 grid((ks.npwx + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
+    ProfScope prof(ctx, PC_GEMM_OUT);
     k_zgemm<false, false><<<grid, GT, 0, ctx->stream>>>(ks.npwx, nvec, m, ks.d_P, ks.npwx, coef, m, out, ldout, cmake(1, 0),
                                                        cmake(0, 0), m, 0, active);
     SGW_LAUNCH_CHECK();

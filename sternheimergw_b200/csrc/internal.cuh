@@ -85,6 +85,10 @@ struct KPair {
   std::vector<double> et;
 };
 
+// kernel classes timed separately (CUDA events on the library's stream) when profiling is on
+enum ProfClass { PC_FFT_Z = 0, PC_FFT_PLANE, PC_GEMM_PROJ, PC_GEMM_OUT, PC_SHIFT, PC_SEED, PC_RHO_PLANE, PC_OTHER, PC_N };
+struct ProfRec { int cls; cudaEvent_t a, b; };
+
 struct Workspace {
   std::map<std::string, std::pair<void *, size_t>> bufs;
 };
@@ -114,6 +118,10 @@ struct sgw_ctx {
   sgw_stats stats;
   bool profiling = false;
   int64_t launches = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<sgw::ProfRec> prof_recs;
+  double prof_ms[sgw::PC_N] = {0};
+  int64_t prof_n[sgw::PC_N] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   int sm_count = 148;
   size_t smem_optin = 0;
@@ -173,6 +181,13 @@ inline int upload(sgw_ctx *ctx, T **dptr, const T *h, size_t count) {
   return SGW_OK;
 }
 
+void prof_begin(sgw_ctx *ctx, int cls);
+void prof_end(sgw_ctx *ctx);
+struct ProfScope {
+  sgw_ctx *c;
+  ProfScope(sgw_ctx *ctx, int cls) : c(ctx) { if (c->profiling) prof_begin(c, cls); }
+  ~ProfScope() { if (c->profiling) prof_end(c); }
+};
 void begin_call(sgw_ctx *ctx);
 void end_call(sgw_ctx *ctx);
 GridDev grid_dev(const sgw_ctx *ctx);

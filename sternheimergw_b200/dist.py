@@ -1,0 +1,86 @@
+"""q-point level driver: the part of do_stern (phys/coul/src/do_stern.f90:189-236) that distributes the
+G-perturbations over ranks and gathers the dielectric-matrix columns.
+
+The reference splits ``ngmunique`` perturbations over MPI images with ``parallel_task`` (do_stern.f90:199), every image
+runs ``coulomb`` on its contiguous block (:209) and ``mp_gatherv`` collects ``scrcoul_loc(ngc, nfs, ntask)`` on the
+root image (:211), which unfolds, patches the head, inverts and writes (:220-236).  Here one rank = one GPU; the
+blocks are independent, so there is NO data-path collective during the solves; the gather is a single
+``torch.distributed`` call per q (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .host import parallel_task
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None):
+    """mp_gatherv(inter_image_comm, root, num_task, scrcoul_loc, scrcoul_root) (do_stern.f90:211, parallel.f90:1130).
+
+    scr_loc: (ngc, nfs, ntask_loc) complex128 of this rank; num_task: tasks of every rank.  Returns the
+    (ngc, nfs, sum(num_task)) array on ``root`` and None elsewhere.  Without an initialised process group
+    (single rank) the input is returned unchanged.
+    """
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return scr_loc
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ngc, nfs = scr_loc.shape[0], scr_loc.shape[1]
+    nmax = max(num_task)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+    # pad every block to the largest one: all_gather needs equal shapes (the remainder rule gives blocks that
+    # differ by at most one column)
+    buf = np.zeros((nmax, nfs, ngc, 2), dtype=np.float64)
+    if scr_loc.shape[2]:
+        t = np.ascontiguousarray(np.transpose(scr_loc, (2, 1, 0)))
+        buf[:scr_loc.shape[2]] = t.view(np.float64).reshape(scr_loc.shape[2], nfs, ngc, 2)
+    mine = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    if rank != root:
+        return None
+    out = np.zeros((ngc, nfs, int(sum(num_task))), dtype=np.complex128, order="F")
+    off = 0
+    for r in range(world):
+        n = num_task[r]
+        if n:
+            blk = parts[r][:n].cpu().numpy().reshape(n, nfs, ngc, 2)
+            out[:, :, off:off + n] = np.transpose(blk[..., 0] + 1j * blk[..., 1], (2, 1, 0))
+        off += n
+    return out
+
+
+def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, invert_fn=None, eps_head=None,
+               lgamma=False, root: int = 0):
+    """One q-point of do_stern: split -> coulomb on the local block -> gather -> (root) unfold, head, invert.
+
+    coulomb_fn(config, igstart, num_g_corr, num_task, ig_unique, fiu) -> (ngc, nfs, num_task) is normally
+    ``Context.coulomb``; unfold_fn / invert_fn are ``Context.unfold_w`` / ``Context.invert_epsilon``.
+    Returns (scrcoul_g on root | None, (first_task, last_task, num_task)).
+    """
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    ngmunique = len(ig_unique)
+    first, last, num_task = parallel_task(world, rank, ngmunique)                 # do_stern.f90:199
+    ntask_loc = num_task[rank]
+    if ntask_loc > 0:
+        scr_loc = coulomb_fn(config, first, num_g_corr, ntask_loc, ig_unique, fiu)   # :209
+    else:
+        scr_loc = np.zeros((num_g_corr, len(fiu), 0), dtype=np.complex128, order="F")
+    scr_root = gather_columns(scr_loc, num_task, root=root)                        # :211
+    if rank != root or unfold_fn is None:
+        return (scr_root if rank == root else None), (first, last, num_task)
+    scr_g = unfold_fn(num_g_corr, ig_unique, scr_root)                             # :220 (identity symmetry)
+    if eps_head is not None:
+        scr_g[0, 0, :] = eps_head                                                  # :224
+    if invert_fn is not None:
+        scr_g = invert_fn(scr_g, lgamma=lgamma)                                    # :232
+    return scr_g, (first, last, num_task)

@@ -85,6 +85,17 @@ class Context:
         self._L.sgw_get_stats(self._h, C.byref(st))
         return {k: getattr(st, k) for k, _ in st._fields_}
 
+    def set_profiling(self, on: bool):
+        self._chk(self._L.sgw_set_profiling(self._h, 1 if on else 0), "set_profiling")
+
+    def profile(self) -> dict:
+        """Per-kernel-class device milliseconds and region counts of the last solver-level call."""
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
+        n = C.c_int(0)
+        self._chk(self._L.sgw_get_profile(self._h, 16, ms, cnt, C.byref(n)), "get_profile")
+        return {self._L.sgw_profile_class_name(i).decode(): {"ms": ms[i], "regions": int(cnt[i])} for i in range(n.value)}
+
     def synchronize(self):
         self._chk(self._L.sgw_device_synchronize(self._h), "synchronize")
 

@@ -243,6 +243,98 @@ def make_kq(sys: SynthSystem, xk, nbnd, npwx=None) -> KQ:
               evq=ev[:, :nbnd].copy(), et=et[:max(nbnd, min(len(et), nbnd + 4))].copy())
 
 
+def make_kq_blocks(sys: SynthSystem, xk, nbnd_blk, key_fn, nextra=1) -> KQ:
+    """Like make_kq for a supercell whose potential has the periodicity of a smaller primitive cell.
+
+    H couples two plane waves only if their Miller indices differ by a primitive reciprocal-lattice vector,
+    so H is block diagonal over the cosets ``key_fn(mill)`` (one block per folded k-point of the primitive
+    cell).  Each block is diagonalised densely; the ``nbnd_blk`` lowest states of every block together are the
+    occupied manifold (checked: the highest of them lies below the lowest unoccupied state of every block).
+    """
+    igk, g2kin = kpoint_sphere(sys, xk)
+    mill = sys.mill[igk]
+    vkb, dion = build_vkb(sys, xk, igk)
+    keys = key_fn(mill)
+    npw = len(igk)
+    cols, ets, e_unocc = [], [], []
+    for key in np.unique(keys):
+        idx = np.flatnonzero(keys == key)
+        H = dense_h(sys, mill[idx], g2kin[idx], vkb[idx], dion)
+        e, v = np.linalg.eigh(H)
+        for b in range(nbnd_blk):
+            j = np.argmax(np.abs(v[:, b]))
+            col = np.zeros(npw, dtype=complex)
+            col[idx] = v[:, b] * np.exp(-1j * np.angle(v[j, b]))
+            cols.append(col)
+            ets.append(e[b])
+        e_unocc.append(e[nbnd_blk:nbnd_blk + nextra])
+    ets = np.asarray(ets)
+    order = np.argsort(ets, kind="stable")
+    evq = np.stack([cols[i] for i in order], axis=1)
+    e_un = np.sort(np.concatenate(e_unocc))
+    assert ets.max() < e_un[0], ("occupied manifold is not the union of the block manifolds", ets.max(), e_un[0])
+    et = np.concatenate([ets[order], e_un[:4]])
+    return KQ(xk=np.asarray(xk, float), npw=npw, npwx=npw, igk=(igk + 1).astype(np.int32), mill=mill,
+              nl_igk=sys.nl[igk].astype(np.int32), g2kin=g2kin, vkb=vkb, dion=dion, evq=evq, et=et)
+
+
+def attach_kpoints_blocks(sys: SynthSystem, klist, xq, nbnd_blk, key_fn, weights=None):
+    """attach_kpoints for block-diagonal supercells (see make_kq_blocks)."""
+    xq = np.asarray(xq, dtype=float)
+    klist = [np.asarray(k, dtype=float) for k in klist]
+    nk = len(klist)
+    weights = weights if weights is not None else [2.0 / nk] * nk
+    ks = [make_kq_blocks(sys, k, nbnd_blk, key_fn) for k in klist]
+    kqs = [make_kq_blocks(sys, k + xq, nbnd_blk, key_fn) for k in klist]
+    nbnd = ks[0].evq.shape[1]
+    npwx = max(max(k.npw for k in ks), max(k.npw for k in kqs))
+    emax_occ = max(k.et[nbnd - 1] for k in ks + kqs)
+    emin = min(k.et[0] for k in ks + kqs)
+    alpha_pv = max(2.0 * (emax_occ - emin), 1e-2)
+    sys.kpairs = []
+    for k, kq, w in zip(ks, kqs, weights):
+        for o in (k, kq):
+            o.npwx = npwx
+            o.vkb = _pad(o.vkb, npwx)
+            o.evq = _pad(o.evq, npwx)
+            o.alpha_pv = alpha_pv
+        sys.kpairs.append(KPairS(kq=kq, npw_k=k.npw, nl_igk_k=k.nl_igk, evc=k.evq, et=k.et[:nbnd].copy(), wk=w, k=k))
+    sys.npwx, sys.alpha_pv, sys.xq, sys.nbnd_occ = npwx, alpha_pv, xq, nbnd
+    sys.gap = min(k.et[nbnd] for k in ks + kqs) - emax_occ
+    return sys
+
+
+def si_supercell(ncell=2, ecutwfc=None, nr=None, xq=None, name=None):
+    """Diamond Si in a simple-cubic supercell of ncell^3 conventional cells (8 ncell^3 atoms); ncell = 2 is the
+    64-atom cell of BASELINE.json's scaling config (72^3 grid, ~24 k plane waves, 128 occupied bands, nkb 256)."""
+    a0 = 10.26
+    alat = a0 * ncell
+    fcc = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+    tau = []
+    for i in range(ncell):
+        for j in range(ncell):
+            for k in range(ncell):
+                for f in fcc:
+                    for sgn in (+1, -1):
+                        tau.append((np.array([i, j, k]) + f + sgn * 0.125) / ncell)
+    tau = np.array(tau)
+    if ecutwfc is None:
+        # radius-(9 ncell - 0.1) sphere in units of 2pi/alat: fills the (36 ncell)^3 box the way 16 Ry fills 20^3
+        ecutwfc = (9.0 * ncell - 0.1) ** 2 * (2.0 * np.pi / alat) ** 2
+    s = build_lattice(name or f"si{8 * ncell ** 3}", alat, np.eye(3), tau, ["Si"] * len(tau), ecutwfc, nr=nr,
+                      nbnd_occ=4 * 4 * ncell ** 3)
+    m = 2 * ncell    # primitive (fcc) reciprocal lattice in supercell Miller units: all = 0 or all = ncell (mod 2 ncell)
+
+    def key_fn(mill):
+        r = np.mod(mill, m)
+        flip = r[:, 0] >= ncell
+        r[flip] = np.mod(r[flip] + ncell, m)
+        return (r[:, 0] * m + r[:, 1]) * m + r[:, 2]
+
+    q = [0.25, 0.25, 0.25] if xq is None else xq
+    return attach_kpoints_blocks(s, [np.zeros(3)], q, 4, key_fn)
+
+
 def _pad(a, npwx):
     out = np.zeros((npwx,) + a.shape[1:], dtype=a.dtype, order="F")
     out[:a.shape[0]] = a
@@ -318,6 +410,10 @@ def preset(name: str, xq=None, nk=2):
         ks = [(i / 5) * s.bg[0] + (j / 5) * s.bg[1] for i in range(5) for j in range(5)] if nk >= 5 \
             else [(i / nk) * s.bg[0] + (j / nk) * s.bg[1] for i in range(nk) for j in range(nk)]
         return attach_kpoints(s, ks, q)
+    if name == "si64":          # BASELINE.json configs[4]: 64-atom Si supercell, 72^3 grid, 1 q / 1 k
+        return si_supercell(2, xq=xq)
+    if name == "si8":           # same construction, one conventional cell (36^3 grid): CPU-sized parity case
+        return si_supercell(1, xq=xq)
     raise KeyError(name)
 
 
