@@ -1,0 +1,88 @@
+"""N > 1 path on CPU: the do_stern split/gather logic (sternheimergw_b200/dist.py) with world_size 2 and 3 over gloo.
+
+The data path has no collective (perturbation blocks are independent, do_stern.f90:199-209); what is tested here is
+the host-side logic around it: parallel_task's block rule (parallel.f90:80-138, remainder to the LAST ranks), the
+gather of scrcoul_loc(ngc, nfs, ntask_loc) in task order (do_stern.f90:211 / parallel.f90:1130) including ranks with
+zero tasks and unequal blocks, and the root-only unfold (unfold_w.f90:84: conjugate transpose).
+coulomb_fn is a deterministic stand-in (no GPU here); the GPU tests cover Context.coulomb itself.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _fake_coulomb(config, igstart, ngc, ntask, ig_unique, fiu):
+    out = np.zeros((ngc, len(fiu), ntask), dtype=np.complex128, order="F")
+    for t in range(ntask):
+        ig = int(ig_unique[igstart - 1 + t])
+        for iw in range(len(fiu)):
+            out[:, iw, t] = (np.arange(ngc) + 1) * (1.0 + 0.5j * iw) + 1000.0 * ig
+    return out
+
+
+def _unfold_identity(ngc, ig_unique, scr):
+    out = np.zeros((ngc, ngc, scr.shape[1]), dtype=np.complex128, order="F")
+    for i, ig in enumerate(ig_unique):
+        out[ig - 1, :, :] = np.conj(scr[:, :, i])           # unfold_w.f90:84
+    return out
+
+
+def _worker(rank, world, port, ngmunique, ngc, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sternheimergw_b200.dist import do_stern_q
+        ig_unique = np.arange(1, ngmunique + 1, dtype=np.int32)
+        fiu = np.array([0.0, 0.5j, 1.0j])
+        scr_g, (first, last, num_task) = do_stern_q(_fake_coulomb, None, ngc, ig_unique, fiu, unfold_fn=_unfold_identity)
+        q.put((rank, first, last, num_task, None if scr_g is None else scr_g.copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,ngmunique,expect", [(2, 7, [3, 4]), (3, 7, [2, 2, 3]), (3, 2, [0, 1, 1]), (2, 8, [4, 4])])
+def test_do_stern_split_and_gather(world, ngmunique, expect):
+    ngc = max(ngmunique, 5)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ngmunique, ngc, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # serial answer
+    ig_unique = np.arange(1, ngmunique + 1, dtype=np.int32)
+    fiu = np.array([0.0, 0.5j, 1.0j])
+    serial = _unfold_identity(ngc, ig_unique, _fake_coulomb(None, 1, ngc, ngmunique, ig_unique, fiu))
+    off = 1
+    for r in range(world):
+        _, first, last, num_task, scr = res[r]
+        assert list(num_task) == expect
+        if expect[r]:
+            assert (first, last) == (off, off + expect[r] - 1)
+        off += expect[r]
+        if r == 0:
+            assert scr is not None and np.array_equal(scr, serial)          # bit-exact: a gather moves bytes only
+        else:
+            assert scr is None
