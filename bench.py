@@ -60,43 +60,82 @@ def workload_config(syn, P, world):
 
 # ----------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    """SM clock / throttle-reason samples DURING the timed region.  NVML is polled from a thread every 250 ms
+    (a fast `nvidia-smi -lms` loop takes driver locks often enough to stall kernel launches of the process it
+    watches: measured +60% on this launch-bound-free but sync-per-iteration workload); falls back to
+    `nvidia-smi -lms 500` when pynvml is missing."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.25):
+        self.index, self.period = index, period
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = self.proc = self.nv = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                                          "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.proc.stdout:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                self.sm.append(float(f[0])); self.mx.append(float(f[1])); self.pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    self.reasons.add(nm)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            time.sleep(0.1)
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (nvml / nvidia-smi unavailable)"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": max(self.mx),
+                "power_w_median": float(np.median(self.pw)) if self.pw else None, "samples": len(self.sm),
+                "source": "nvml" if self.nv else "nvidia-smi", "reasons": sorted(self.reasons)}
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
@@ -238,12 +277,13 @@ def main():
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    dev_ms, launches, nop = 0.0, 0, 0
+    dev_ms, launches, nop, solver_ms = 0.0, 0, 0, 0.0
     prof_tot = {}
     for s in range(args.warmup, args.warmup + args.steps):
         scr, st, prof, t_coll = step(s)
         dev_ms += st["ms_total"] + t_coll
         launches += st["n_kernel_launch"]
+        solver_ms += st["ms_solver"]
         nop += st["n_linear_op"]
         for k, v in prof.items():
             a = prof_tot.setdefault(k, {"ms": 0.0, "regions": 0})
@@ -327,6 +367,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(syn, P, world),
             "wall_ms_per_step": wall_ms / args.steps, "time_to_W_block_ms": dev_ms / args.steps,
             "solves_per_step": solves_per_step * world, "linear_op_per_step": nop / args.steps,
+            "coul_solver_ms_per_step": solver_ms / args.steps,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": total_solves / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(syn, fiu, igu),
                     "d2h_bytes_per_step": int(ngc * NFS * P * 16 + 4), "ms_per_step": e2e_ms / args.steps,

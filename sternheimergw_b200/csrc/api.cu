@@ -149,6 +149,8 @@ int sgw_destroy(sgw_ctx *ctx) {
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
   for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) if (ctx->ev_iter[i]) cudaEventDestroy(ctx->ev_iter[i]);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SGW_OK;

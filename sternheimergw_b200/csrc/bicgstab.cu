@@ -565,8 +565,14 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   SGW_CHECK(ws(ctx, "bi_stage", (size_t)nr, &s.stage));
   SGW_CHECK(ws(ctx, "bi_iters", (size_t)nr, &s.iters));
   SGW_CHECK(ws(ctx, "bi_nactive", (size_t)1, &s.nactive));
-  int *h_nactive = nullptr;
-  SGW_CUDA(cudaMallocHost((void **)&h_nactive, sizeof(int)));
+  // The host runs ONE outer iteration ahead of the device: iteration i+1 is enqueued before the active count of
+  // iteration i is read back, so the stream never drains while the host waits (a drained stream costs a full
+  // launch latency per kernel and makes the solve sensitive to host jitter).  If iteration i turns out to have
+  // converged everything, the already enqueued iteration i+1 is a no-op: every kernel returns on the active mask.
+  if (!ctx->h_flags) SGW_CUDA(cudaMallocHost((void **)&ctx->h_flags, 4 * sizeof(int)));
+  volatile int *h_nactive = ctx->h_flags;
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->ev_iter[i]) SGW_CUDA(cudaEventCreateWithFlags(&ctx->ev_iter[i], cudaEventDisableTiming));
 
   cudaStream_t st = ctx->stream;
   const int gb = (int)((nr + 127) / 128);
@@ -647,11 +653,13 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
       k_check<<<gb, 128, 0, st>>>(s, threshold, iter, 2);                           // :245
       SGW_LAUNCH_CHECK();
     }
-    SGW_CUDA(cudaMemcpyAsync(h_nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SGW_CUDA(cudaStreamSynchronize(st));
-    if (*h_nactive == 0) break;
+    SGW_CUDA(cudaMemcpyAsync((void *)&h_nactive[iter & 1], s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaEventRecord(ctx->ev_iter[iter & 1], st));
+    if (iter >= 2) {
+      SGW_CUDA(cudaEventSynchronize(ctx->ev_iter[(iter - 1) & 1]));
+      if (h_nactive[(iter - 1) & 1] == 0) break;
+    }
   }
-  cudaFreeHost(h_nactive);
   if (rc != SGW_OK) return rc;
   k_set_ierr<<<gb, 128, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();

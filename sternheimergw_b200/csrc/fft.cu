@@ -14,15 +14,19 @@
 // box sweeps of an unfused 3-D FFT (SURVEY.md section 8d counts 192*nnr + 32*N algorithmic bytes).
 #include "internal.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace sgw {
 
 constexpr int ZCB = 16;        // columns per CTA in the z passes
-constexpr int ZTHREADS = 128;
+constexpr int ZTHREADS = 160;   // launch bound; the launch uses zpass_threads()
+constexpr int ZMINB = 4;        // resident CTAs per SM the register allocation must allow
+static_assert((ZCB & (ZCB - 1)) == 0, "ZCB must be a power of two");
 constexpr int PTHREADS = 256;
 
-__global__ void __launch_bounds__(ZTHREADS) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
+__global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
                                                          cplx *__restrict__ T, const int *__restrict__ active) {
   const int vec = blockIdx.y;
   if (active && !active[vec]) return;
@@ -47,13 +51,13 @@ __global__ void __launch_bounds__(ZTHREADS) k_zpass_g2r(GridDev g, SphereDev s, 
     __syncthreads();
   }
   cplx *dst = T + (long)vec * g.nz * s.ncol + c0;
-  for (int i = tid; i < nc * g.nz; i += nt) {
-    const int c = i % nc, pz = i / nc;
-    dst[(long)pz * s.ncol + c] = lines[c * pitch + pz];
+  for (int i = tid; i < ZCB * g.nz; i += nt) {
+    const int c = i & (ZCB - 1), pz = i / ZCB;
+    if (c < nc) dst[pz * s.ncol + c] = lines[c * pitch + pz];
   }
 }
 
-__global__ void __launch_bounds__(ZTHREADS) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
+__global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
                                                          cplx *__restrict__ out, long ld, ZEpilogue epi, double scale,
                                                          const int *__restrict__ active) {
   const int vec = blockIdx.y;
@@ -67,9 +71,9 @@ __global__ void __launch_bounds__(ZTHREADS) k_zpass_r2g(GridDev g, SphereDev s, 
   cplx *tw = sm + ZCB * pitch;
   for (int i = tid; i < g.nz; i += nt) tw[i] = g.twz[i];
   const cplx *src = T + (long)vec * g.nz * s.ncol + c0;
-  for (int i = tid; i < nc * g.nz; i += nt) {
-    const int c = i % nc, pz = i / nc;
-    lines[c * pitch + pz] = src[(long)pz * s.ncol + c];
+  for (int i = tid; i < ZCB * g.nz; i += nt) {
+    const int c = i & (ZCB - 1), pz = i / ZCB;
+    if (c < nc) lines[c * pitch + pz] = src[pz * s.ncol + c];
   }
   __syncthreads();
   if (g.rz2 > 1) {
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(ZTHREADS) k_zpass_r2g(GridDev g, SphereDev s, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
+__global__ void __launch_bounds__(PTHREADS, 2) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
                                                      cplx *__restrict__ Tout, const double *__restrict__ vperm,
                                                      const cplx *__restrict__ field, int vec_per_field, cplx *R,
                                                      int in_mod, const int *__restrict__ active) {
@@ -115,46 +119,56 @@ __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, Sp
   cplx *plane = sm;
   cplx *twx = sm + ny * pitch;
   cplx *twy = twx + nx;
+  int *xs_in = (int *)(twy + ny), *xs_out = xs_in + nx;     // x columns that hold data, staged on chip
   for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
   for (int i = tid; i < ny; i += nt) twy[i] = g.twy[i];
+  if (MODE != PLANE_FROM_R) for (int i = tid; i < sin.nxs; i += nt) xs_in[i] = sin.xs[i];
+  if (MODE != PLANE_TO_R) for (int i = tid; i < sout.nxs; i += nt) xs_out[i] = sout.xs[i];
   const long nxy = (long)nx * ny;
 
   if (MODE != PLANE_FROM_R) {
     for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
     __syncthreads();
     const cplx *row = Tin + ((long)vin * g.nz + pz) * sin.ncol;
-    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_y[c] * pitch + sin.col_x[c]] = row[c];
+    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_off[c]] = row[c];
     __syncthreads();
     // inverse along y for the x columns that hold data (x still in natural order)
-    run_strided<+1>(g.ry1, plane, sin.nxs, sin.xs, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
+    run_strided<+1>(g.ry1, plane, sin.nxs, xs_in, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
     __syncthreads();
     if (g.ry2 > 1) {
-      run_contig<+1>(g.ry2, plane, sin.nxs, sin.xs, 1, pitch, g.ry1, twy, false, tid, nt);
+      run_contig<+1>(g.ry2, plane, sin.nxs, xs_in, 1, pitch, g.ry1, twy, false, tid, nt);
       __syncthreads();
     }
-    // inverse along x for all rows
-    run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
-    __syncthreads();
-    if (g.rx2 > 1) {
-      run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+    if (MODE == PLANE_VLOC || MODE == PLANE_FIELD) {
+      // inverse along x, x v(r), forward along x: the last inverse stage, the product and the first forward stage
+      // touch the same contiguous radix group of a row -> one register round trip (fft_core.h stage_mid)
+      const double *v = MODE == PLANE_VLOC ? vperm + (long)pz * nxy : nullptr;
+      const cplx *f = MODE == PLANE_FIELD ? field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy : nullptr;
+      if (g.rx2 > 1) {
+        run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, true, tid, nt);
+        __syncthreads();
+        run_mid<MODE == PLANE_FIELD>(g.rx2, plane, ny, pitch, g.rx1, twx, true, v, f, nx, tid, nt);
+        __syncthreads();
+        run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
+      } else {
+        run_mid<MODE == PLANE_FIELD>(g.rx1, plane, ny, pitch, 1, twx, false, v, f, nx, tid, nt);
+      }
       __syncthreads();
+    } else {
+      // inverse along x for all rows
+      run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
+      __syncthreads();
+      if (g.rx2 > 1) {
+        run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+        __syncthreads();
+      }
     }
   } else {
     __syncthreads();
   }
 
-  if (MODE == PLANE_VLOC) {
-    const double *v = vperm + (long)pz * nxy;
-    for (int i = tid; i < nx * ny; i += nt) {
-      const int ix = i % nx, iy = i / nx;
-      plane[iy * pitch + ix] = cscale(v[i], plane[iy * pitch + ix]);
-    }
-  } else if (MODE == PLANE_FIELD) {
-    const cplx *f = field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy;
-    for (int i = tid; i < nx * ny; i += nt) {
-      const int ix = i % nx, iy = i / nx;
-      plane[iy * pitch + ix] = cmul(f[i], plane[iy * pitch + ix]);
-    }
+  if (MODE == PLANE_VLOC || MODE == PLANE_FIELD) {
+    // x transforms and the product are done (fused above)
   } else if (MODE == PLANE_TO_R) {
     cplx *r = R + ((long)vec * g.nz + pz) * nxy;
     for (int i = tid; i < nx * ny; i += nt) {
@@ -177,28 +191,60 @@ __global__ void __launch_bounds__(PTHREADS) k_plane(GridDev g, SphereDev sin, Sp
       }
     }
   }
-  __syncthreads();
-
-  // forward along x (permuted in -> natural out), all rows
-  if (g.rx2 > 1) {
-    run_contig<-1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
+  if (MODE == PLANE_FROM_R) {
+    __syncthreads();
+    // forward along x (permuted in -> natural out), all rows
+    if (g.rx2 > 1) {
+      run_contig<-1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
+      __syncthreads();
+    }
+    run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
     __syncthreads();
   }
-  run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
-  __syncthreads();
   // forward along y only for the x columns of the output sphere
   if (g.ry2 > 1) {
-    run_contig<-1>(g.ry2, plane, sout.nxs, sout.xs, 1, pitch, g.ry1, twy, true, tid, nt);
+    run_contig<-1>(g.ry2, plane, sout.nxs, xs_out, 1, pitch, g.ry1, twy, true, tid, nt);
     __syncthreads();
   }
-  run_strided<-1>(g.ry1, plane, sout.nxs, sout.xs, 1, pitch, g.ry2, twy, false, tid, nt);
+  run_strided<-1>(g.ry1, plane, sout.nxs, xs_out, 1, pitch, g.ry2, twy, false, tid, nt);
   __syncthreads();
   cplx *orow = Tout + ((long)vec * g.nz + pz) * sout.ncol;
-  for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_y[c] * pitch + sout.col_x[c]];
+  for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_off[c]];
+}
+
+// Last inverse stage along x fused with the accumulation  acc(r) += conj(psi_v(r)) dpsi(r)  ([QE] incdrhoscf):
+// the R outputs of a contiguous radix group stay in registers; dpsi(r) itself is never stored.
+template <int R>
+__device__ __forceinline__ void stage_acc(const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
+                                          int tid, int nthreads) {
+  const int ntasks = nlines * r_other;
+  TaskIter it(tid, nthreads, nlines);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    const int l = it.l, a = it.j;
+    const cplx *base = x + (l * ls + a * R);
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const cplx w = base[j]; re[j] = w.x; im[j] = w.y; }
+    dft_fwd<R>(im, re);
+    cplx *ab = acc + (l * ls + a * R);
+    const cplx *pb = pr + (l * vls + a * R);
+#pragma unroll
+    for (int j = 0; j < R; ++j) ab[j] = cfma(cconj(pb[j]), cmake(re[j], im[j]), ab[j]);   // drho += conj(psi) dpsi
+  }
+}
+__device__ __noinline__ void run_acc(int R, const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
+                                     int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_acc<r>(x, acc, nlines, ls, r_other, pr, vls, tid, nthreads); break;
+    SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
 }
 
 // incdrhoscf: one CTA per (pf = perturbation x frequency, z-plane); bands are summed on chip
-__global__ void __launch_bounds__(PTHREADS) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
+constexpr int RTHREADS = 512;
+__global__ void __launch_bounds__(RTHREADS) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
                                                          const cplx *__restrict__ Tin, const cplx *__restrict__ psir,
                                                          double wgt, cplx *__restrict__ Tout, int accumulate) {
   const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
@@ -209,33 +255,32 @@ __global__ void __launch_bounds__(PTHREADS) k_plane_rho(GridDev g, SphereDev sin
   cplx *acc = sm + ny * pitch;
   cplx *twx = acc + ny * pitch;
   cplx *twy = twx + nx;
+  int *xs_in = (int *)(twy + ny), *xs_out = xs_in + nx;
   for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
   for (int i = tid; i < ny; i += nt) twy[i] = g.twy[i];
+  for (int i = tid; i < sin.nxs; i += nt) xs_in[i] = sin.xs[i];
+  for (int i = tid; i < sout.nxs; i += nt) xs_out[i] = sout.xs[i];
   for (int i = tid; i < ny * pitch; i += nt) acc[i] = cmake(0.0, 0.0);
   const long nxy = (long)nx * ny;
   for (int ib = 0; ib < nocc; ++ib) {
     for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
     __syncthreads();
     const cplx *row = Tin + (((long)pf * nocc + ib) * g.nz + pz) * sin.ncol;
-    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_y[c] * pitch + sin.col_x[c]] = row[c];
+    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_off[c]] = row[c];
     __syncthreads();
-    run_strided<+1>(g.ry1, plane, sin.nxs, sin.xs, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
+    run_strided<+1>(g.ry1, plane, sin.nxs, xs_in, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
     __syncthreads();
     if (g.ry2 > 1) {
-      run_contig<+1>(g.ry2, plane, sin.nxs, sin.xs, 1, pitch, g.ry1, twy, false, tid, nt);
-      __syncthreads();
-    }
-    run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
-    __syncthreads();
-    if (g.rx2 > 1) {
-      run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+      run_contig<+1>(g.ry2, plane, sin.nxs, xs_in, 1, pitch, g.ry1, twy, false, tid, nt);
       __syncthreads();
     }
     const cplx *pr = psir + ((long)ib * g.nz + pz) * nxy;
-    for (int i = tid; i < nx * ny; i += nt) {
-      const int ix = i % nx, iy = i / nx;
-      const int j = iy * pitch + ix;
-      acc[j] = cfma(cconj(pr[i]), plane[j], acc[j]);        // drho += conj(psi) dpsi
+    if (g.rx2 > 1) {
+      run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, true, tid, nt);
+      __syncthreads();
+      run_acc(g.rx2, plane, acc, ny, pitch, g.rx1, pr, nx, tid, nt);
+    } else {
+      run_acc(g.rx1, plane, acc, ny, pitch, 1, pr, nx, tid, nt);
     }
     __syncthreads();
   }
@@ -252,16 +297,16 @@ __global__ void __launch_bounds__(PTHREADS) k_plane_rho(GridDev g, SphereDev sin
   run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
   __syncthreads();
   if (g.ry2 > 1) {
-    run_contig<-1>(g.ry2, plane, sout.nxs, sout.xs, 1, pitch, g.ry1, twy, true, tid, nt);
+    run_contig<-1>(g.ry2, plane, sout.nxs, xs_out, 1, pitch, g.ry1, twy, true, tid, nt);
     __syncthreads();
   }
-  run_strided<-1>(g.ry1, plane, sout.nxs, sout.xs, 1, pitch, g.ry2, twy, false, tid, nt);
+  run_strided<-1>(g.ry1, plane, sout.nxs, xs_out, 1, pitch, g.ry2, twy, false, tid, nt);
   __syncthreads();
   cplx *orow = Tout + ((long)pf * g.nz + pz) * sout.ncol;
   if (accumulate) {
-    for (int c = tid; c < sout.ncol; c += nt) orow[c] = cadd(orow[c], plane[sout.col_y[c] * pitch + sout.col_x[c]]);
+    for (int c = tid; c < sout.ncol; c += nt) orow[c] = cadd(orow[c], plane[sout.col_off[c]]);
   } else {
-    for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_y[c] * pitch + sout.col_x[c]];
+    for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_off[c]];
   }
 }
 
@@ -277,9 +322,16 @@ GridDev grid_dev(const sgw_ctx *ctx) {
   return g;
 }
 
+static int zpass_threads(const sgw_ctx *ctx) {
+  static int forced = -1;                                       // SGW_ZTHREADS: tuning knob (multiple of 32, <= ZTHREADS)
+  if (forced < 0) { const char *e = getenv("SGW_ZTHREADS"); forced = e ? atoi(e) : 0; }
+  if (forced >= 32 && forced <= ZTHREADS) return forced;
+  (void)ctx;
+  return 128;
+}
 static size_t zpass_smem(const sgw_ctx *ctx) { return (size_t)(ZCB * (ctx->nr3 | 1) + ctx->nr3) * sizeof(cplx); }
 static size_t plane_smem(const sgw_ctx *ctx) {
-  return (size_t)(ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx);
+  return (size_t)(ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx) + 2 * (size_t)ctx->nr1 * sizeof(int);
 }
 
 template <typename K>
@@ -298,7 +350,7 @@ int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long 
   SGW_CHECK(set_smem(ctx, k_zpass_g2r, smem));
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_g2r<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), in, ld, T, active);
+  k_zpass_g2r<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(grid_dev(ctx), s.dev(), in, ld, T, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -311,7 +363,7 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
   const double scale = 1.0 / ((double)ctx->nr1 * ctx->nr2 * ctx->nr3);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_r2g<<<grid, ZTHREADS, smem, ctx->stream>>>(grid_dev(ctx), s.dev(), T, out, ld, epi, scale, active);
+  k_zpass_r2g<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(grid_dev(ctx), s.dev(), T, out, ld, epi, scale, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -350,11 +402,11 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
 int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
                   double wgt, cplx *Tout, int accumulate) {
   if (npf <= 0) return SGW_OK;
-  const size_t smem = (size_t)(2 * ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx);
+  const size_t smem = (size_t)(2 * ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx) + 2 * (size_t)ctx->nr1 * sizeof(int);
   SGW_CHECK(set_smem(ctx, k_plane_rho, smem));
   dim3 grid(npf, ctx->nr3);
   ProfScope prof(ctx, PC_RHO_PLANE);
-  k_plane_rho<<<grid, PTHREADS, smem, ctx->stream>>>(grid_dev(ctx), sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  k_plane_rho<<<grid, RTHREADS, smem, ctx->stream>>>(grid_dev(ctx), sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -407,6 +459,11 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   sph->perm = order;
   SGW_CHECK(upload(ctx, &sph->d_col_x, col_x.data(), col_x.size()));
   SGW_CHECK(upload(ctx, &sph->d_col_y, col_y.data(), col_y.size()));
+  {
+    std::vector<int> col_off(col_x.size());
+    for (size_t c = 0; c < col_x.size(); ++c) col_off[c] = col_y[c] * (nx | 1) + col_x[c];
+    SGW_CHECK(upload(ctx, &sph->d_col_off, col_off.data(), col_off.size()));
+  }
   SGW_CHECK(upload(ctx, &sph->d_col_ptr, col_ptr.data(), col_ptr.size()));
   SGW_CHECK(upload(ctx, &sph->d_colof, colof.data(), colof.size()));
   SGW_CHECK(upload(ctx, &sph->d_zof, zof.data(), zof.size()));
@@ -416,7 +473,7 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
 }
 
 void free_sphere(Sphere *s) {
-  int **ptrs[] = {&s->d_col_x, &s->d_col_y, &s->d_col_ptr, &s->d_colof, &s->d_zof, &s->d_xs, &s->d_perm};
+  int **ptrs[] = {&s->d_col_x, &s->d_col_y, &s->d_col_ptr, &s->d_colof, &s->d_zof, &s->d_xs, &s->d_perm, &s->d_col_off};
   for (auto p : ptrs) {
     if (*p) cudaFree(*p);
     *p = nullptr;

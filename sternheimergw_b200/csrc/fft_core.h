@@ -53,17 +53,30 @@ SGW_HD int perm_index(int r1, int r2, int pos) { return pos / r2 + r1 * (pos % r
 
 // ---- one stage over a set of lines; thread `tid` of `nthreads` takes tasks tid, tid+nthreads, ...
 // line l starts at x + (line_ids ? line_ids[l] : l) * ls ; element e of a line at + e * es.
+// Task t = (line l = t % nlines, sub-index t / nlines); the pair is advanced incrementally (one division per
+// stage call instead of two per task) and all offsets are 32-bit: the integer pipe, not FP64, was the top
+// issuer in the first profile of the plane kernel.
+struct TaskIter {
+  int l, j, dl, dj, nlines;
+  SGW_HD TaskIter(int tid, int nthreads, int nl) : l(tid % nl), j(tid / nl), dl(nthreads % nl), dj(nthreads / nl), nlines(nl) {}
+  SGW_HD void next() {
+    l += dl; j += dj;
+    if (l >= nlines) { l -= nlines; ++j; }
+  }
+};
+
 template <int R, int DIR>
 SGW_HD void stage_strided(double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
                           const double2* tw, bool do_tw, int tid, int nthreads) {
   const int ntasks = nlines * r_other;
   const int st = r_other * es;
-  for (int t = tid; t < ntasks; t += nthreads) {
-    const int l = t % nlines, j2 = t / nlines;
-    double2* base = x + (long)(line_ids ? line_ids[l] : l) * ls + (long)j2 * es;
+  TaskIter it(tid, nthreads, nlines);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    const int j2 = it.j;
+    double2* base = x + ((line_ids ? line_ids[it.l] : it.l) * ls + j2 * es);
     double re[R], im[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) { const double2 v = base[(long)j * st]; re[j] = v.x; im[j] = v.y; }
+    for (int j = 0; j < R; ++j) { const double2 v = base[j * st]; re[j] = v.x; im[j] = v.y; }
     if (DIR < 0) dft_fwd<R>(re, im); else dft_fwd<R>(im, re);
     if (do_tw) {
 #pragma unroll
@@ -76,7 +89,7 @@ SGW_HD void stage_strided(double2* x, int nlines, const int* line_ids, int ls, i
       }
     }
 #pragma unroll
-    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[(long)k * st] = v; }
+    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[k * st] = v; }
   }
 }
 
@@ -84,12 +97,13 @@ template <int R, int DIR>
 SGW_HD void stage_contig(double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
                          const double2* tw, bool do_tw, int tid, int nthreads) {
   const int ntasks = nlines * r_other;
-  for (int t = tid; t < ntasks; t += nthreads) {
-    const int l = t % nlines, a = t / nlines;
-    double2* base = x + (long)(line_ids ? line_ids[l] : l) * ls + (long)a * R * es;
+  TaskIter it(tid, nthreads, nlines);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    const int a = it.j;
+    double2* base = x + ((line_ids ? line_ids[it.l] : it.l) * ls + a * R * es);
     double re[R], im[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) { const double2 v = base[(long)j * es]; re[j] = v.x; im[j] = v.y; }
+    for (int j = 0; j < R; ++j) { const double2 v = base[j * es]; re[j] = v.x; im[j] = v.y; }
     if (DIR < 0) dft_fwd<R>(re, im); else dft_fwd<R>(im, re);
     if (do_tw) {
 #pragma unroll
@@ -102,7 +116,54 @@ SGW_HD void stage_contig(double2* x, int nlines, const int* line_ids, int ls, in
       }
     }
 #pragma unroll
-    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[(long)k * es] = v; }
+    for (int k = 0; k < R; ++k) { double2 v; v.x = re[k]; v.y = im[k]; base[k * es] = v; }
+  }
+}
+
+// Fused middle of the local-potential product along the contiguous axis: the LAST inverse stage (contiguous DFT_R,
+// no twiddle), the point-wise multiplication by the potential, and the FIRST forward stage (contiguous DFT_R +
+// twiddle) act on the same R elements of a row, so they are done in one register round trip.  Arithmetic per
+// element is exactly that of stage_contig<R,+1> -> multiply -> stage_contig<R,-1>.
+// v (real) or f (complex) are indexed like the plane without padding: row l at + l * vls.
+template <int R, bool CPLX>
+SGW_HD void stage_mid(double2* x, int nlines, int ls, int r_other, const double2* tw, bool do_tw, const double* v,
+                      const double2* f, int vls, int tid, int nthreads) {
+  const int ntasks = nlines * r_other;
+  TaskIter it(tid, nthreads, nlines);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    const int l = it.l, a = it.j;
+    double2* base = x + (l * ls + a * R);
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const double2 w = base[j]; re[j] = w.x; im[j] = w.y; }
+    dft_fwd<R>(im, re);
+    if (CPLX) {
+      const double2* fr = f + (l * vls + a * R);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double2 q = fr[j];
+        const double p = re[j], s = im[j];
+        re[j] = q.x * p - q.y * s;
+        im[j] = q.x * s + q.y * p;
+      }
+    } else {
+      const double* vr = v + (l * vls + a * R);
+#pragma unroll
+      for (int j = 0; j < R; ++j) { const double q = vr[j]; re[j] *= q; im[j] *= q; }
+    }
+    dft_fwd<R>(re, im);
+    if (do_tw) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) {
+        const double2 w = tw[a * k];
+        const double c = w.x, s = w.y;
+        const double p = re[k], q = im[k];
+        re[k] = p * c - q * s;
+        im[k] = p * s + q * c;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) { double2 w; w.x = re[k]; w.y = im[k]; base[k] = w; }
   }
 }
 
@@ -133,6 +194,22 @@ void run_contig(int R, double2* x, int nlines, const int* line_ids, int ls, int 
                 const double2* tw, bool do_tw, int tid, int nthreads) {
   switch (R) {
 #define SGW_CASE(r) case r: stage_contig<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+    SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
+}
+
+template <bool CPLX>
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void run_mid(int R, double2* x, int nlines, int ls, int r_other, const double2* tw, bool do_tw, const double* v,
+             const double2* f, int vls, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_mid<r, CPLX>(x, nlines, ls, r_other, tw, do_tw, v, f, vls, tid, nthreads); break;
     SGW_FOR_EACH_RADIX(SGW_CASE)
 #undef SGW_CASE
     default: break;

@@ -10,17 +10,35 @@
 namespace sgw {
 
 constexpr int BM = 64, BN = 32, BK = 16, GT = 256;
-constexpr int PK = BK + 4;   // k-contiguous smem pitch (doubles): 8 rows x 4 k hit 32 distinct bank pairs
-constexpr int PM = BM + 8;   // m-contiguous smem pitch
+// Shared-memory tiles hold interleaved complex (16 B) elements so that one LDS.128 fetches (re, im) of a fragment
+// element and cp.async (LDGSTS) can stage them straight from global memory.  Pitches are chosen so that the 8 lanes
+// of a quarter-warp (g = 0..1, t = 0..3) of a 16-byte access hit 8 distinct 16-byte bank groups:
+constexpr int PK = BK + 4;   // k-contiguous tiles: (g*PK + t) mod 8 distinct  <=  PK = 4 mod 8
+constexpr int PM = BM + 2;   // m-contiguous A tile: (t*PM + g) mod 8 distinct  <=  PM = 2 mod 8
+constexpr int NSTAGE = 2;
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
+// 16-byte asynchronous global -> shared copy; bytes = 0 zero-fills the destination (tile edges)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool A_KCONTIG>
+constexpr int a_tile_elems() { return A_KCONTIG ? BM * PK : BK * PM; }
+template <bool A_KCONTIG>
+constexpr size_t zgemm_smem() { return (size_t)NSTAGE * (a_tile_elems<A_KCONTIG>() + BN * PK) * sizeof(cplx); }
 
 // C(M x N) = alpha * op(A) * B + beta * C ; op(A) = A^H (A_KCONTIG: A is K x M, column-major) or A (M x K).
 // B is K x N column-major.  blockIdx.z selects a K range (split-K): partial results go to C + z * split_stride.
+// Global -> shared staging is double buffered with cp.async so that the DMMA pipe does not wait on HBM/L2.
 template <bool A_KCONTIG, bool CONJA>
 __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
                                                const cplx *__restrict__ B, long ldb, cplx *__restrict__ C, long ldc,
@@ -34,8 +52,10 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
     for (int n = n0; n < min(N, n0 + BN); ++n) any |= (active[n] != 0);
     if (!any) return;
   }
-  constexpr int ASZ = A_KCONTIG ? BM * PK : BK * PM;
-  __shared__ double As_re[ASZ], As_im[ASZ], Bs_re[BN * PK], Bs_im[BN * PK];
+  constexpr int ASZ = a_tile_elems<A_KCONTIG>();
+  extern __shared__ cplx gsm[];
+  cplx *As = gsm;                      // [NSTAGE][ASZ]
+  cplx *Bs = gsm + NSTAGE * ASZ;       // [NSTAGE][BN * PK]
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
   const int g = lane >> 2, t = lane & 3;
   double cre[2][2][2], cim[2][2][2];
@@ -44,59 +64,67 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
 #pragma unroll
     for (int j = 0; j < 2; ++j) cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0;
 
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    // ---- stage tiles
-    if (A_KCONTIG) {
-      for (int i = tid; i < BM * BK; i += GT) {
+  auto stage_load = [&](int st, int k0) {
+    cplx *as = As + st * ASZ, *bs = Bs + st * (BN * PK);
+#pragma unroll
+    for (int r = 0; r < BM * BK / GT; ++r) {
+      const int i = tid + r * GT;
+      if (A_KCONTIG) {
         const int k = i % BK, m = i / BK;
-        cplx v = cmake(0.0, 0.0);
-        if (k0 + k < kend && m0 + m < M) v = A[(long)(k0 + k) + (long)(m0 + m) * lda];
-        As_re[m * PK + k] = v.x;
-        As_im[m * PK + k] = v.y;
-      }
-    } else {
-      for (int i = tid; i < BM * BK; i += GT) {
+        const bool ok = (k0 + k < kend) && (m0 + m < M);
+        cp_async16(as + m * PK + k, ok ? A + (long)(k0 + k) + (long)(m0 + m) * lda : A, ok ? 16 : 0);
+      } else {
         const int m = i % BM, k = i / BM;
-        cplx v = cmake(0.0, 0.0);
-        if (k0 + k < kend && m0 + m < M) v = A[(long)(m0 + m) + (long)(k0 + k) * lda];
-        As_re[k * PM + m] = v.x;
-        As_im[k * PM + m] = v.y;
+        const bool ok = (k0 + k < kend) && (m0 + m < M);
+        cp_async16(as + k * PM + m, ok ? A + (long)(m0 + m) + (long)(k0 + k) * lda : A, ok ? 16 : 0);
       }
     }
-    for (int i = tid; i < BN * BK; i += GT) {
+#pragma unroll
+    for (int r = 0; r < BN * BK / GT; ++r) {
+      const int i = tid + r * GT;
       const int k = i % BK, n = i / BK;
-      cplx v = cmake(0.0, 0.0);
-      if (k0 + k < kend && n0 + n < N) v = B[(long)(k0 + k) + (long)(n0 + n) * ldb];
-      Bs_re[n * PK + k] = v.x;
-      Bs_im[n * PK + k] = v.y;
+      const bool ok = (k0 + k < kend) && (n0 + n < N);
+      cp_async16(bs + n * PK + k, ok ? B + (long)(k0 + k) + (long)(n0 + n) * ldb : B, ok ? 16 : 0);
     }
+  };
+
+  if (kbeg < kend) stage_load(0, kbeg);
+  cp_async_commit();
+  int it = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += BK, ++it) {
+    if (k0 + BK < kend) stage_load((it + 1) & 1, k0 + BK);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const cplx *as = As + (it & 1) * ASZ, *bs = Bs + (it & 1) * (BN * PK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double are[2], aim[2], bre[2], bim[2];
+      cplx a[2], b[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int m = wm + i * 8 + g;
-        const int idx = A_KCONTIG ? m * PK + kk + t : (kk + t) * PM + m;
-        are[i] = As_re[idx];
-        aim[i] = As_im[idx];
+        a[i] = as[A_KCONTIG ? m * PK + kk + t : (kk + t) * PM + m];
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int n = wn + j * 8 + g;
-        bre[j] = Bs_re[n * PK + kk + t];
-        bim[j] = Bs_im[n * PK + kk + t];
-      }
+      for (int j = 0; j < 2; ++j) b[j] = bs[(wn + j * 8 + g) * PK + kk + t];
+      // op(A) = conj(A)^T: re += ar*br + ai*bi ; im += ar*bi - ai*br.  op(A) = A: re += ar*br - ai*bi ; im += ar*bi + ai*br
+      // The two updates of one accumulator are issued 8 DMMAs apart so that they do not serialise on its latency.
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          // op(A) = conj(A)^T: re += ar*br + ai*bi ; im += ar*bi - ai*br.  op(A) = A: re += ar*br - ai*bi ; im += ar*bi + ai*br
-          dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
-          dmma(cre[i][j][0], cre[i][j][1], CONJA ? aim[i] : -aim[i], bim[j]);
-          dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
-          dmma(cim[i][j][0], cim[i][j][1], CONJA ? -aim[i] : aim[i], bre[j]);
+          dmma(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
+          dmma(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
         }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double ai_re = CONJA ? a[i].y : -a[i].y, ai_im = CONJA ? -a[i].y : a[i].y;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(cre[i][j][0], cre[i][j][1], ai_re, b[j].y);
+          dmma(cim[i][j][0], cim[i][j][1], ai_im, b[j].x);
+        }
+      }
     }
     __syncthreads();
   }
@@ -117,6 +145,29 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
           Cz[(long)row + (long)col * ldc] = r;
         }
       }
+}
+
+// opt in to > 48 KB of dynamic shared memory (per device) and record how many CTAs fit on an SM
+static int zgemm_init(sgw_ctx *ctx);
+
+template <bool A_KCONTIG, bool CONJA>
+static int launch_zgemm(sgw_ctx *ctx, dim3 grid, int M, int N, int K, const cplx *A, long lda, const cplx *B, long ldb, cplx *C,
+                        long ldc, cplx alpha, cplx beta, int kchunk, long split_stride, const int *active) {
+  constexpr size_t smem = zgemm_smem<A_KCONTIG>();
+  SGW_CHECK(zgemm_init(ctx));
+  k_zgemm<A_KCONTIG, CONJA><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, active);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+static int zgemm_init(sgw_ctx *ctx) {
+  if (ctx->gemm_cta_per_sm > 0) return SGW_OK;
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zgemm<true, true>, GT, zgemm_smem<true>()) != cudaSuccess || n < 1) n = 1;
+  ctx->gemm_cta_per_sm = n;
+  return SGW_OK;
 }
 
 // coef'(:, v) = blockdiag(D, alpha I) * sum_z partial_z(:, v)
@@ -161,18 +212,14 @@ __global__ void k_add_sigma(int n, int nvec, const cplx *__restrict__ psi, long 
 int gemm_ch_n(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, const cplx *B, long ldb, cplx *C, long ldc) {
   if (m <= 0 || n <= 0) return SGW_OK;
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, 1);
-  k_zgemm<true, true><<<grid, GT, 0, ctx->stream>>>(m, n, k, A, lda, B, ldb, C, ldc, cmake(1, 0), cmake(0, 0), k > 0 ? k : 1, 0, nullptr);
-  SGW_LAUNCH_CHECK();
-  return SGW_OK;
+  return launch_zgemm<true, true>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, cmake(1, 0), cmake(0, 0), k > 0 ? k : 1, 0, nullptr);
 }
 
 int gemm_n_n(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, const cplx *B, long ldb, cplx beta,
              cplx *C, long ldc) {
   if (m <= 0 || n <= 0) return SGW_OK;
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, 1);
-  k_zgemm<false, false><<<grid, GT, 0, ctx->stream>>>(m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k > 0 ? k : 1, 0, nullptr);
-  SGW_LAUNCH_CHECK();
-  return SGW_OK;
+  return launch_zgemm<false, false>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k > 0 ? k : 1, 0, nullptr);
 }
 
 int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, const cplx *psi, long ldpsi, cplx *out,
@@ -184,14 +231,23 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
     SGW_CUDA(cudaMemset2DAsync(out, (size_t)ldout * sizeof(cplx), 0, (size_t)ks.npwx * sizeof(cplx), nvec, ctx->stream));
     return SGW_OK;
   }
-  // split-K so that the projection fills the machine
+  // split-K so that the projection fills the machine in whole waves: pick the split whose CTA count wastes the
+  // least of the last wave (slots = SMs x resident CTAs per SM), preferring fewer splits on ties
   const int tiles = ((m + BM - 1) / BM) * ((nvec + BN - 1) / BN);
-  int nsplit = (2 * ctx->sm_count + tiles - 1) / tiles;
   const int kblocks = (ks.npw + BK - 1) / BK;
-  if (nsplit > kblocks) nsplit = kblocks;
-  if (nsplit < 1) nsplit = 1;
-  int kchunk = ((kblocks + nsplit - 1) / nsplit) * BK;
-  nsplit = (ks.npw + kchunk - 1) / kchunk;
+  SGW_CHECK(zgemm_init(ctx));
+  const long slots = (long)ctx->sm_count * ctx->gemm_cta_per_sm;
+  int nsplit = 1, kchunk = kblocks * BK;
+  double best = -1.0;
+  for (int cand = 1; cand <= 64 && cand <= kblocks; ++cand) {
+    const int kc = ((kblocks + cand - 1) / cand) * BK;
+    const int ns = (ks.npw + kc - 1) / kc;
+    const long ctas = (long)tiles * ns;
+    const long waves = (ctas + slots - 1) / slots;
+    // time ~ waves x (work of one CTA) = waves x kc ; lower is better
+    const double cost = (double)waves * kc;
+    if (best < 0 || cost < best * 0.98) { best = cost; nsplit = ns; kchunk = kc; }
+  }
   cplx *part = nullptr, *coef = nullptr;
   const long split_stride = (long)m * nvec;
   SGW_CHECK(ws(ctx, "nl_part", (size_t)split_stride * nsplit, &part));
@@ -199,9 +255,8 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
   {
     dim3 grid((m + BM - 1) / BM, (nvec + BN - 1) / BN, nsplit);
     ProfScope prof(ctx, PC_GEMM_PROJ);
-    k_zgemm<true, true><<<grid, GT, 0, ctx->stream>>>(m, nvec, ks.npw, ks.d_P, ks.npwx, psi, ldpsi, part, m, cmake(1, 0),
-                                                     cmake(0, 0), kchunk, split_stride, active);
-    SGW_LAUNCH_CHECK();
+    SGW_CHECK((launch_zgemm<true, true>(ctx, grid, m, nvec, ks.npw, ks.d_P, ks.npwx, psi, ldpsi, part, m, cmake(1, 0),
+                                         cmake(0, 0), kchunk, split_stride, active)));
   }
   {
     ProfScope prof(ctx, PC_OTHER);
@@ -212,9 +267,8 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
   {
     dim3 grid((ks.npwx + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
     ProfScope prof(ctx, PC_GEMM_OUT);
-    k_zgemm<false, false><<<grid, GT, 0, ctx->stream>>>(ks.npwx, nvec, m, ks.d_P, ks.npwx, coef, m, out, ldout, cmake(1, 0),
-                                                       cmake(0, 0), m, 0, active);
-    SGW_LAUNCH_CHECK();
+    SGW_CHECK((launch_zgemm<false, false>(ctx, grid, ks.npwx, nvec, m, ks.d_P, ks.npwx, coef, m, out, ldout, cmake(1, 0),
+                                           cmake(0, 0), m, 0, active)));
   }
   return SGW_OK;
 }
@@ -224,9 +278,8 @@ int dense_apply(sgw_ctx *ctx, const KSlot &ks, int nvec, const cplx *psi, long l
   if (nvec <= 0) return SGW_OK;
   const int n = ks.npw;
   dim3 grid((n + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
-  k_zgemm<false, false><<<grid, GT, 0, ctx->stream>>>(n, nvec, n, ks.d_A, n, psi, ldpsi, out, ldout, cmake(1, 0), cmake(0, 0), n, 0,
-                                                     active);
-  SGW_LAUNCH_CHECK();
+  SGW_CHECK((launch_zgemm<false, false>(ctx, grid, n, nvec, n, ks.d_A, n, psi, ldpsi, out, ldout, cmake(1, 0), cmake(0, 0), n, 0,
+                                         active)));
   dim3 g2((n + 255) / 256, nvec);
   k_add_sigma<<<g2, 256, 0, ctx->stream>>>(n, nvec, psi, ldpsi, sigma, sigma_stride, out, ldout, active);
   SGW_LAUNCH_CHECK();

@@ -52,16 +52,17 @@ struct GridDev {
 struct SphereDev {
   int npw, ncol, nxs;
   const int *col_x, *col_y, *col_ptr, *colof, *zof, *xs;
+  const int *col_off;      // col_y * (nx | 1) + col_x: offset of the column inside a shared-memory plane
 };
 
 struct Sphere {
   int npw = 0, ncol = 0, nxs = 0;
   std::vector<int> perm;   // perm[p] = caller's 0-based index of internal entry p
   int *d_col_x = nullptr, *d_col_y = nullptr, *d_col_ptr = nullptr, *d_colof = nullptr, *d_zof = nullptr,
-      *d_xs = nullptr, *d_perm = nullptr;
+      *d_xs = nullptr, *d_perm = nullptr, *d_col_off = nullptr;
   SphereDev dev() const {
     SphereDev s; s.npw = npw; s.ncol = ncol; s.nxs = nxs; s.col_x = d_col_x; s.col_y = d_col_y;
-    s.col_ptr = d_col_ptr; s.colof = d_colof; s.zof = d_zof; s.xs = d_xs; return s;
+    s.col_ptr = d_col_ptr; s.colof = d_colof; s.zof = d_zof; s.xs = d_xs; s.col_off = d_col_off; return s;
   }
 };
 
@@ -123,6 +124,9 @@ struct sgw_ctx {
   double prof_ms[sgw::PC_N] = {0};
   int64_t prof_n[sgw::PC_N] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // solver look-ahead (bicgstab.cu)
+  int *h_flags = nullptr;                        // pinned host flags read back by the solvers
+  int gemm_cta_per_sm = 0;                       // resident k_zgemm CTAs per SM (0 = attributes not set yet)
   int sm_count = 148;
   size_t smem_optin = 0;
 };

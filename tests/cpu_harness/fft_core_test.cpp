@@ -17,7 +17,17 @@ int main() {
   std::vector<double2> x((size_t)(n + 1) * (nlines + 1));
   for (int l = 0; l < nlines; ++l)
     for (int e = 0; e < n; ++e) { double a, b; if (scanf("%lf %lf", &a, &b) != 2) return 2; x[(size_t)l * ls + (size_t)e * es] = {a, b}; }
-  if (dir > 0) {   // nat2perm, inverse codelets
+  if (dir == 0) {  // fused local-potential product along a contiguous axis: inverse, x v (permuted order), forward
+    std::vector<double> v((size_t)n * nlines);
+    for (auto &q : v) if (scanf("%lf", &q) != 1) return 3;
+    if (p.r2 > 1) {
+      for (int t = 0; t < nthreads; ++t) run_strided<+1>(p.r1, x.data(), nlines, nullptr, ls, es, p.r2, tw.data(), true, t, nthreads);
+      for (int t = 0; t < nthreads; ++t) run_mid<false>(p.r2, x.data(), nlines, ls, p.r1, tw.data(), true, v.data(), nullptr, n, t, nthreads);
+      for (int t = 0; t < nthreads; ++t) run_strided<-1>(p.r1, x.data(), nlines, nullptr, ls, es, p.r2, tw.data(), false, t, nthreads);
+    } else {
+      for (int t = 0; t < nthreads; ++t) run_mid<false>(p.r1, x.data(), nlines, ls, 1, tw.data(), false, v.data(), nullptr, n, t, nthreads);
+    }
+  } else if (dir > 0) {   // nat2perm, inverse codelets
     for (int t = 0; t < nthreads; ++t) run_strided<+1>(p.r1, x.data(), nlines, nullptr, ls, es, p.r2, tw.data(), p.r2 > 1, t, nthreads);
     if (p.r2 > 1) for (int t = 0; t < nthreads; ++t) run_contig<+1>(p.r2, x.data(), nlines, nullptr, ls, es, p.r1, tw.data(), false, t, nthreads);
   } else {         // perm2nat, forward codelets
