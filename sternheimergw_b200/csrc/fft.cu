@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_r2g(GridDev g, Sphere
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(PTHREADS, 2) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
+template <int MODE, int NT>
+__global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
                                                      cplx *__restrict__ Tout, const double *__restrict__ vperm,
                                                      const cplx *__restrict__ field, int vec_per_field, cplx *R,
                                                      int in_mod, const int *__restrict__ active) {
@@ -327,7 +327,12 @@ static int zpass_threads(const sgw_ctx *ctx) {
   if (forced < 0) { const char *e = getenv("SGW_ZTHREADS"); forced = e ? atoi(e) : 0; }
   if (forced >= 32 && forced <= ZTHREADS) return forced;
   (void)ctx;
-  return 128;
+  return 96;   // measured on B200 (Si64): 96 -> 58 ms, 128 -> 63 ms, 160 -> 73 ms per step; small CTAs keep more loads in flight
+}
+static int plane_threads() {
+  static int forced = -1;                                       // SGW_PTHREADS: tuning knob (256 | 384 | 512)
+  if (forced < 0) { const char *e = getenv("SGW_PTHREADS"); forced = e ? atoi(e) : 0; }
+  return (forced == 384 || forced == 512) ? forced : 256;
 }
 static size_t zpass_smem(const sgw_ctx *ctx) { return (size_t)(ZCB * (ctx->nr3 | 1) + ctx->nr3) * sizeof(cplx); }
 static size_t plane_smem(const sgw_ctx *ctx) {
@@ -377,24 +382,23 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
   ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
+#define SGW_PLANE_LAUNCH(M, NT)                                                                                          \
+  do {                                                                                                                  \
+    SGW_CHECK(set_smem(ctx, k_plane<M, NT>, smem));                                                                     \
+    k_plane<M, NT><<<grid, NT, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active); \
+  } while (0)
+  const int nt = plane_threads();
   switch (mode) {
     case PLANE_VLOC:
-      SGW_CHECK(set_smem(ctx, k_plane<PLANE_VLOC>, smem));
-      k_plane<PLANE_VLOC><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
+      if (nt == 512) SGW_PLANE_LAUNCH(PLANE_VLOC, 512);
+      else if (nt == 384) SGW_PLANE_LAUNCH(PLANE_VLOC, 384);
+      else SGW_PLANE_LAUNCH(PLANE_VLOC, 256);
       break;
-    case PLANE_FIELD:
-      SGW_CHECK(set_smem(ctx, k_plane<PLANE_FIELD>, smem));
-      k_plane<PLANE_FIELD><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
-      break;
-    case PLANE_TO_R:
-      SGW_CHECK(set_smem(ctx, k_plane<PLANE_TO_R>, smem));
-      k_plane<PLANE_TO_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
-      break;
-    case PLANE_FROM_R:
-      SGW_CHECK(set_smem(ctx, k_plane<PLANE_FROM_R>, smem));
-      k_plane<PLANE_FROM_R><<<grid, PTHREADS, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active);
-      break;
+    case PLANE_FIELD: SGW_PLANE_LAUNCH(PLANE_FIELD, 256); break;
+    case PLANE_TO_R: SGW_PLANE_LAUNCH(PLANE_TO_R, 256); break;
+    case PLANE_FROM_R: SGW_PLANE_LAUNCH(PLANE_FROM_R, 256); break;
   }
+#undef SGW_PLANE_LAUNCH
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }

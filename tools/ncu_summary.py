@@ -1,0 +1,69 @@
+"""Summarise an `ncu --set full` report (.ncu-rep) into a small tracked text table for profiles/.
+
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/r01_hpsi_full.md
+
+Per captured launch: duration, DRAM bytes (read + write = `traffic`), DRAM / SM / L1 throughput %, pipe utilisation
+(FP64 vector pipe and the tensor pipe, which executes DMMA), registers, occupancy, shared-memory
+wavefronts and bank conflicts, and the top warp-stall reasons.
+"""
+import csv
+import io
+import subprocess
+import sys
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+
+def f(x):
+    try:
+        return float(x.replace(",", ""))
+    except Exception:
+        return float("nan")
+
+
+def main():
+    rep = sys.argv[1]
+    hdr, units, data = raw(rep)
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def g(d, name):
+        return f(d[ix[name]]) if name in ix else float("nan")
+
+    def unit(name):
+        return units[ix[name]] if name in ix else ""
+
+    print(f"# ncu --set full summary of `{rep}`\n")
+    print("| # | kernel | grid x block | time [us] | DRAM rd+wr [MB] | DRAM % | SM % | L1/smem % | FP64 pipe % | tensor (DMMA) pipe % | regs | "
+          "occ % (theor.) | smem wavefronts | bank conflicts | top stalls |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for n, d in enumerate(data):
+        name = d[ix["Kernel Name"]].split("(")[0].replace("void ", "")
+        t = g(d, "gpu__time_duration.sum")
+        tu = unit("gpu__time_duration.sum")
+        t_us = t * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(tu, 1e-3)
+        def bytes_of(m):
+            v, u = g(d, m), unit(m)
+            return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
+        dram = bytes_of("dram__bytes_read.sum") + bytes_of("dram__bytes_write.sum")
+        stalls = [(f(d[i]), h.replace("smsp__pcsamp_warps_issue_stalled_", "")) for i, h in enumerate(hdr)
+                  if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h and d[i] not in ("", "n/a")]
+        tot = sum(v for v, _ in stalls) or 1.0
+        top = ", ".join(f"{h} {100 * v / tot:.0f}%" for v, h in sorted(stalls, reverse=True)[:3])
+        print(f"| {n} | {name} | {int(g(d, 'launch__grid_size'))} x {int(g(d, 'launch__block_size'))} | {t_us:.1f} | {dram:.1f} | "
+              f"{g(d, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+              f"{g(d, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+              f"{g(d, 'l1tex__throughput.avg.pct_of_peak_sustained_active'):.1f} | "
+              f"{g(d, 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+              f"{g(d, 'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+              f"{int(g(d, 'launch__registers_per_thread'))} | "
+              f"{g(d, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} ({g(d, 'sm__maximum_warps_per_active_cycle_pct'):.0f}) | "
+              f"{g(d, 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'):.3g} | "
+              f"{g(d, 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'):.3g} | {top} |")
+
+
+if __name__ == "__main__":
+    main()
