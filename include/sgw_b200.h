@@ -116,6 +116,11 @@ int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, cons
  * perturbations x k x bands.  scrcoul(ngc, nfs, ntask). */
 int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, int ntask,
                 const int32_t *ig_unique, int nfs, const sgw_cplx *fiu, sgw_cplx *scrcoul, int32_t *ierr_out);
+/* Grid on which the last sgw_coulomb accumulated Delta-rho ([QE] incdrhoscf, solve_linter.f90:489-497).  coulomb.f90:143-157
+ * keeps only the first ngc G vectors of Delta-rho, so the library uses the smallest FFT box that yields those components
+ * without aliasing (n >= M_k + M_k+q + M_out + 1 per axis; identical to the full-box result up to rounding).
+ * Returns 1 and the box in dims when a reduced box was used, 0 when the full dffts box was used. */
+int sgw_get_rho_grid(const sgw_ctx *ctx, int *dims /* 3 */);
 /* coulomb_q0G0 (phys/coul/src/coulomb_q0G0.f90:31): head element at the (shifted) q currently set */
 int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw_cplx *fiu, sgw_cplx *eps_m,
                      int32_t *ierr_out);

@@ -15,7 +15,7 @@ SYMBOLS = [
     "sgw_get_profile", "sgw_profile_class_name",
     "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
     "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_solve_linter",
-    "sgw_coulomb", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
+    "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
     "sgw_parallel_task", "sgw_bench_linear_op",
 ]
 
@@ -68,6 +68,7 @@ def load():
                                        c_void_p]
         L.sgw_coulomb.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p]
+        L.sgw_get_rho_grid.argtypes = [c_void_p, c_void_p]
         L.sgw_coulomb_q0G0.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_void_p, c_void_p, c_void_p]
         L.sgw_unfold_w.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.sgw_invert_epsilon.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int]

@@ -141,6 +141,10 @@ int sgw_destroy(sgw_ctx *ctx) {
   for (auto &k : ctx->slots) free_slot(k);
   for (auto &p : ctx->pairs) free_pair(p);
   for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
+  free_sphere(&ctx->rho_sph_c);
+  for (auto &sp : ctx->pair_k_c) free_sphere(&sp);
+  for (auto &sp : ctx->pair_kq_c) free_sphere(&sp);
+  free_fft_grid(&ctx->rho_grid);
   ws_free_all(ctx);
   if (ctx->d_twx) cudaFree(ctx->d_twx);
   if (ctx->d_twy) cudaFree(ctx->d_twy);
@@ -200,9 +204,35 @@ static int upload_twiddle(sgw_ctx *ctx, int n, cplx **d) {
   return upload(ctx, d, tw.data(), tw.size());
 }
 
+}  // extern "C"
+
+namespace sgw {
+int make_fft_grid(sgw_ctx *ctx, int n1, int n2, int n3, FftGrid *gr) {
+  free_fft_grid(gr);
+  if (!make_plan(n1, &gr->px) || !make_plan(n2, &gr->py) || !make_plan(n3, &gr->pz)) {
+    ctx->err = "FFT dimension not of the form r1*r2 with radices in {1,2,3,4,5,6,8,9,10,12,15,16}";
+    return SGW_E_UNSUPPORTED;
+  }
+  gr->n1 = n1; gr->n2 = n2; gr->n3 = n3;
+  SGW_CHECK(upload_twiddle(ctx, n1, &gr->d_twx));
+  SGW_CHECK(upload_twiddle(ctx, n2, &gr->d_twy));
+  SGW_CHECK(upload_twiddle(ctx, n3, &gr->d_twz));
+  return SGW_OK;
+}
+void free_fft_grid(FftGrid *gr) {
+  if (gr->d_twx) cudaFree(gr->d_twx);
+  if (gr->d_twy) cudaFree(gr->d_twy);
+  if (gr->d_twz) cudaFree(gr->d_twz);
+  *gr = FftGrid();
+}
+}  // namespace sgw
+
+extern "C" {
+
 int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, int nr3x) {
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
+  ctx->tables_version++;
   SGW_ARG(nr1 > 0 && nr2 > 0 && nr3 > 0, "grid dimensions must be positive");
   if (nr1x != nr1 || nr2x != nr2 || nr3x != nr3) {
     ctx->err = "padded FFT boxes (nr1x != nr1) are not supported";
@@ -265,6 +295,7 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
   KSlot *k = get_slot(ctx, slot);
   SGW_ARG(k != nullptr, "bad slot");
   free_slot(*k);
+  ctx->tables_version++;
   SGW_CHECK(build_sphere(ctx, npw, nl_igk, &k->sph));
   k->npw = npw; k->npwx = npwx; k->nkb = nkb; k->nbnd = nbnd_occ; k->alpha_pv = alpha_pv;
   const std::vector<int> &perm = k->sph.perm;

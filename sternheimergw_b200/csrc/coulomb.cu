@@ -11,6 +11,7 @@
 // device; only wavefunction tables go in and scrcoul comes out.
 #include "internal.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -281,15 +282,94 @@ static size_t solver_bytes_per_rhs(const sgw_ctx *ctx, const KSlot &ks, int lmax
   return v * sizeof(cplx);
 }
 
+// ---- alias-free coarse grid for the Delta-rho accumulation of sgw_coulomb ------------------------------------
+// coulomb.f90:143-157 keeps only the first ngc G vectors of Delta-rho.  Delta-rho(G) = sum_G' conj(psi(G'-G)) dpsi(G') is a
+// finite convolution: with M_k, M_kq the largest |Miller index| of the k and k+q spheres along an axis and M_out that of
+// the ngc retained G vectors, an n-point axis gives those components EXACTLY (no aliasing) as soon as
+// n >= M_k + M_kq + M_out + 1.  [QE] incdrhoscf uses the full dffts box (72 at Si64) where 45 suffices, i.e. 4.1x more
+// points than the retained components need; the result differs from the full-box one by rounding only.
+// SGW_RHO_GRID=fine switches this off (A/B testing); sgw_solve_linter, which returns drho(r) on the full box, never uses it.
+static void rho_grid_release(sgw_ctx *ctx) {
+  free_sphere(&ctx->rho_sph_c);
+  for (auto &s : ctx->pair_k_c) free_sphere(&s);
+  for (auto &s : ctx->pair_kq_c) free_sphere(&s);
+  ctx->pair_k_c.clear();
+  ctx->pair_kq_c.clear();
+  free_fft_grid(&ctx->rho_grid);
+  ctx->rho_grid_on = false;
+}
+
+static void miller_extent(const sgw_ctx *ctx, const Sphere &s, int ext[3]) {
+  const int nf[3] = {ctx->nr1, ctx->nr2, ctx->nr3};
+  auto mil = [&](int c, int d) { return std::abs(c <= (nf[d] - 1) / 2 ? c : c - nf[d]); };
+  ext[0] = ext[1] = ext[2] = 0;
+  for (int c = 0; c < s.ncol; ++c) {
+    ext[0] = std::max(ext[0], mil(s.h_col_x[c], 0));
+    ext[1] = std::max(ext[1], mil(s.h_col_y[c], 1));
+  }
+  for (int p = 0; p < s.npw; ++p) ext[2] = std::max(ext[2], mil(s.h_zof[p], 2));
+}
+
+static int rho_grid_prepare(sgw_ctx *ctx, int ngc, const Sphere &rho_fine, bool *use) {
+  *use = false;
+  const char *e = getenv("SGW_RHO_GRID");
+  if (e && strcmp(e, "fine") == 0) return SGW_OK;
+  if (ctx->rho_grid_version == ctx->tables_version && ctx->rho_grid_ngc == ngc) {
+    *use = ctx->rho_grid_on;
+    return SGW_OK;
+  }
+  rho_grid_release(ctx);
+  ctx->rho_grid_version = ctx->tables_version;
+  ctx->rho_grid_ngc = ngc;
+  int mo[3], need[3] = {0, 0, 0};
+  miller_extent(ctx, rho_fine, mo);
+  for (auto &kp : ctx->pairs) {
+    if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size() || !ctx->slots[kp.slot].set) return SGW_OK;
+    int mk[3], mq[3];
+    miller_extent(ctx, kp.sph_k, mk);
+    miller_extent(ctx, ctx->slots[kp.slot].sph, mq);
+    // alias-free product, and every sphere must itself fit the box without wrap-around collisions (the scatter
+    // into the box overwrites, it does not sum)
+    for (int d = 0; d < 3; ++d)
+      need[d] = std::max(need[d], std::max(mk[d] + mq[d] + mo[d] + 1, 2 * std::max(mk[d], std::max(mq[d], mo[d])) + 1));
+  }
+  const int nf[3] = {ctx->nr1, ctx->nr2, ctx->nr3};
+  int nc[3];
+  for (int d = 0; d < 3; ++d) {
+    nc[d] = nf[d];
+    for (int n = need[d]; n < nf[d]; ++n) {
+      Plan1D p;
+      if (make_plan(n, &p)) { nc[d] = n; break; }
+    }
+  }
+  if ((double)nc[0] * nc[1] * nc[2] > 0.7 * (double)nf[0] * nf[1] * nf[2]) return SGW_OK;   // not worth a second grid
+  SGW_CHECK(make_fft_grid(ctx, nc[0], nc[1], nc[2], &ctx->rho_grid));
+  SGW_CHECK(remap_sphere(ctx, rho_fine, ctx->rho_grid, &ctx->rho_sph_c));
+  ctx->pair_k_c.resize(ctx->pairs.size());
+  ctx->pair_kq_c.resize(ctx->pairs.size());
+  for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {
+    SGW_CHECK(remap_sphere(ctx, ctx->pairs[ik].sph_k, ctx->rho_grid, &ctx->pair_k_c[ik]));
+    SGW_CHECK(remap_sphere(ctx, ctx->slots[ctx->pairs[ik].slot].sph, ctx->rho_grid, &ctx->pair_kq_c[ik]));
+  }
+  ctx->rho_grid_on = true;
+  *use = true;
+  return SGW_OK;
+}
+
 // Delta-rho of `np` perturbations whose dvbare(r) sit in d_field (permuted order): d_drhoG[(p*nfreq+ifreq)*rho.npw + pos]
 // = fwfft(drho)(G) in the column order of `rho`, summed over the k-points of this pool.
 static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cplx *d_field, const FreqList &fl,
-                      const Sphere &rho, cplx *d_drhoG, int *ierr_any) {
+                      const Sphere &rho_fine, cplx *d_drhoG, int *ierr_any, bool coarse = false) {
   const int nfreq = fl.nfreq, nshift = fl.num_omega;
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
   const int npf = np * nfreq;
+  // grid of the Delta-rho accumulation: the context's box, or the alias-free coarse one (rho_grid_prepare)
+  const FftGrid *rg = coarse ? &ctx->rho_grid : nullptr;
+  const Sphere &rho = coarse ? ctx->rho_sph_c : rho_fine;
+  const int rnz = coarse ? ctx->rho_grid.n3 : ctx->nr3;
+  const long rnnr = coarse ? (long)ctx->rho_grid.n1 * ctx->rho_grid.n2 * ctx->rho_grid.n3 : nnr;
   cplx *Trho = nullptr;
-  SGW_CHECK(ws(ctx, "co_Trho", (size_t)npf * ctx->nr3 * rho.ncol, &Trho));
+  SGW_CHECK(ws(ctx, "co_Trho", (size_t)npf * rnz * rho.ncol, &Trho));
   cudaStream_t st = ctx->stream;
   for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {                                     // solve_linter.f90:288
     const KPair &kp = ctx->pairs[ik];
@@ -308,6 +388,15 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));
     SGW_CHECK(fft_zpass_g2r(ctx, kp.sph_k, nocc, kp.d_evc, n, Tk, nullptr));
     SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &kp.sph_k, nullptr, nocc, Tk, nullptr, nullptr, 1, psir, nullptr));
+    // psi_v(r) once more on the Delta-rho grid when that is a different box
+    const Sphere &sq = coarse ? ctx->pair_kq_c[ik] : ks.sph;
+    cplx *psir_rho = psir;
+    if (coarse) {
+      const Sphere &sk = ctx->pair_k_c[ik];
+      SGW_CHECK(ws(ctx, "co_psir_c", (size_t)nocc * rnnr, &psir_rho));
+      SGW_CHECK(fft_zpass_g2r(ctx, sk, nocc, kp.d_evc, n, Tk, nullptr, rg));
+      SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &sk, nullptr, nocc, Tk, nullptr, nullptr, 1, psir_rho, nullptr, 0, rg));
+    }
     // dvqpsi_us.f90:99-130: dvpsi = fwfft(dvbare(r) psi(r)) on the k+q sphere (only the bands the solver uses)
     SGW_CHECK(ws(ctx, "co_Tq", (size_t)nrhs * ctx->nr3 * ks.sph.ncol, &Tq));
     SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nrhs * n, &dvpsi));
@@ -351,20 +440,20 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     }
     // dpsi *= wg/wk (= 1 for fully occupied bands, :373); average +-omega; incdrhoscf with weight 2 wk / omega
     const double wgt = 2.0 * kp.wk / ctx->omega_cell;
-    const size_t per_pf = (size_t)nocc * ((size_t)ctx->nr3 * ks.sph.ncol + n) * sizeof(cplx);
+    const size_t per_pf = (size_t)nocc * ((size_t)rnz * sq.ncol + n) * sizeof(cplx);
     size_t budget = (size_t)2 << 30;
     int pfc = (int)std::max<size_t>(1, std::min<size_t>(npf, budget / per_pf));
     pfc = std::min(pfc, std::max(1, 65535 / nocc));
     cplx *davg = nullptr, *Td = nullptr;
     SGW_CHECK(ws(ctx, "co_davg", (size_t)pfc * nocc * n, &davg));
-    SGW_CHECK(ws(ctx, "co_Td", (size_t)pfc * nocc * ctx->nr3 * ks.sph.ncol, &Td));
+    SGW_CHECK(ws(ctx, "co_Td", (size_t)pfc * nocc * rnz * sq.ncol, &Td));
     for (int pf0 = 0; pf0 < npf; pf0 += pfc) {
       const int c = std::min(pfc, npf - pf0);
       dim3 ga((n + 255) / 256, nocc, c);
       k_average<<<ga, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, pf0, d_x, davg);
       SGW_LAUNCH_CHECK();
-      SGW_CHECK(fft_zpass_g2r(ctx, ks.sph, c * nocc, davg, n, Td, nullptr));
-      SGW_CHECK(fft_plane_rho(ctx, ks.sph, rho, c, nocc, Td, psir, wgt, Trho + (size_t)pf0 * ctx->nr3 * rho.ncol, ik > 0));
+      SGW_CHECK(fft_zpass_g2r(ctx, sq, c * nocc, davg, n, Td, nullptr, rg));
+      SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Trho + (size_t)pf0 * rnz * rho.ncol, ik > 0, rg));
     }
   }
   // mp_sum over pools (:521) is the caller's (one pool per context); fwfft of drho on the density sphere
@@ -373,7 +462,7 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
   epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
   for (int v0 = 0; v0 < npf; v0 += 32768) {
     const int c = std::min(32768, npf - v0);
-    SGW_CHECK(fft_zpass_r2g(ctx, rho, c, Trho + (size_t)v0 * ctx->nr3 * rho.ncol, d_drhoG + (size_t)v0 * rho.npw, rho.npw, epi, nullptr));
+    SGW_CHECK(fft_zpass_r2g(ctx, rho, c, Trho + (size_t)v0 * rnz * rho.ncol, d_drhoG + (size_t)v0 * rho.npw, rho.npw, epi, nullptr, rg));
   }
   return SGW_OK;
 }
@@ -421,6 +510,7 @@ int sgw_set_system(sgw_ctx *ctx, double omega_cell, double tpiba2, int ngm, cons
   cudaSetDevice(ctx->device);
   if (!ctx->grid_set) { ctx->err = "sgw_set_grid must be called first"; return SGW_E_STATE; }
   SGW_ARG(omega_cell > 0 && tpiba2 > 0 && ngm > 0 && g && nl, "bad cell / G-vector data");
+  ctx->tables_version++;
   ctx->omega_cell = omega_cell;
   ctx->tpiba2 = tpiba2;
   ctx->ngm = ngm;
@@ -442,6 +532,7 @@ int sgw_set_nksq(sgw_ctx *ctx, int nksq) {
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
   SGW_ARG(nksq >= 0 && nksq < (1 << 20), "bad nksq");
+  ctx->tables_version++;
   for (auto &p : ctx->pairs) {
     free_sphere(&p.sph_k);
     if (p.d_evc) cudaFree(p.d_evc);
@@ -462,6 +553,7 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   const KSlot &ks = ctx->slots[slot_kq];
   SGW_ARG(npw_k > 0 && npw_k <= ks.npwx && nl_igk_k && nbnd > 0 && evc && et, "bad k-point data");
   KPair &kp = ctx->pairs[ik];
+  ctx->tables_version++;
   free_sphere(&kp.sph_k);
   if (kp.d_evc) { cudaFree(kp.d_evc); kp.d_evc = nullptr; }
   SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
@@ -567,6 +659,9 @@ int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, i
   SGW_CHECK(hartree_factor(ctx, *rho, ngc, "co_fac", &d_fac));
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
   const int chunk = perturbation_chunk(ctx, cfg, fl.num_omega, nfs, *rho, nt);
+  bool coarse = false;
+  SGW_CHECK(rho_grid_prepare(ctx, ngc, *rho, &coarse));
+  ctx->rho_last_coarse = coarse;
   cudaStream_t st = ctx->stream;
   GridDev g = grid_dev(ctx);
   std::vector<cplx> hscr((size_t)ngc * nfs * chunk);
@@ -595,7 +690,7 @@ int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, i
       k_delta_field<<<gr, 256, 0, st>>>(g, np, d_mill, d_field);                           // coulomb.f90:129-134
       SGW_LAUNCH_CHECK();
     }
-    SGW_CHECK(drho_block(ctx, cfg, np, d_field, fl, *rho, d_drhoG, &ierr_any));            // :137
+    SGW_CHECK(drho_block(ctx, cfg, np, d_field, fl, *rho, d_drhoG, &ierr_any, coarse));    // :137
     {
       dim3 gr((ngc + 127) / 128, nfs, np);
       k_scr_extract<<<gr, 128, 0, st>>>(ngc, nfs, np, rho->d_perm, d_fac, d_ig0, d_drhoG, d_scr);   // :143-157
@@ -609,6 +704,15 @@ int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, i
   *ierr_out = ierr_any;
   end_call(ctx);
   return SGW_OK;
+}
+
+int sgw_get_rho_grid(const sgw_ctx *ctx, int *dims) {
+  if (!ctx || !dims) return SGW_E_ARG;
+  const bool on = ctx->rho_last_coarse && ctx->rho_grid_on && ctx->rho_grid_version == ctx->tables_version;
+  dims[0] = on ? ctx->rho_grid.n1 : ctx->nr1;
+  dims[1] = on ? ctx->rho_grid.n2 : ctx->nr2;
+  dims[2] = on ? ctx->rho_grid.n3 : ctx->nr3;
+  return on ? 1 : 0;
 }
 
 int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw_cplx *fiu, sgw_cplx *eps_m,

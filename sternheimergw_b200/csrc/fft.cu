@@ -311,14 +311,22 @@ __global__ void __launch_bounds__(RTHREADS) k_plane_rho(GridDev g, SphereDev sin
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-GridDev grid_dev(const sgw_ctx *ctx) {
+GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr) {
   GridDev g;
-  g.nx = ctx->nr1; g.ny = ctx->nr2; g.nz = ctx->nr3;
-  g.rx1 = ctx->px.r1; g.rx2 = ctx->px.r2;
-  g.ry1 = ctx->py.r1; g.ry2 = ctx->py.r2;
-  g.rz1 = ctx->pz.r1; g.rz2 = ctx->pz.r2;
-  g.pitchx = ctx->nr1 | 1;
-  g.twx = ctx->d_twx; g.twy = ctx->d_twy; g.twz = ctx->d_twz;
+  if (gr) {
+    g.nx = gr->n1; g.ny = gr->n2; g.nz = gr->n3;
+    g.rx1 = gr->px.r1; g.rx2 = gr->px.r2;
+    g.ry1 = gr->py.r1; g.ry2 = gr->py.r2;
+    g.rz1 = gr->pz.r1; g.rz2 = gr->pz.r2;
+    g.twx = gr->d_twx; g.twy = gr->d_twy; g.twz = gr->d_twz;
+  } else {
+    g.nx = ctx->nr1; g.ny = ctx->nr2; g.nz = ctx->nr3;
+    g.rx1 = ctx->px.r1; g.rx2 = ctx->px.r2;
+    g.ry1 = ctx->py.r1; g.ry2 = ctx->py.r2;
+    g.rz1 = ctx->pz.r1; g.rz2 = ctx->pz.r2;
+    g.twx = ctx->d_twx; g.twy = ctx->d_twy; g.twz = ctx->d_twz;
+  }
+  g.pitchx = g.nx | 1;
   return g;
 }
 
@@ -334,9 +342,9 @@ static int plane_threads() {
   if (forced < 0) { const char *e = getenv("SGW_PTHREADS"); forced = e ? atoi(e) : 0; }
   return (forced == 384 || forced == 512) ? forced : 256;
 }
-static size_t zpass_smem(const sgw_ctx *ctx) { return (size_t)(ZCB * (ctx->nr3 | 1) + ctx->nr3) * sizeof(cplx); }
-static size_t plane_smem(const sgw_ctx *ctx) {
-  return (size_t)(ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx) + 2 * (size_t)ctx->nr1 * sizeof(int);
+static size_t zpass_smem(const GridDev &g) { return (size_t)(ZCB * (g.nz | 1) + g.nz) * sizeof(cplx); }
+static size_t plane_smem(const GridDev &g, int nplanes) {
+  return (size_t)(nplanes * g.ny * g.pitchx + g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)g.nx * sizeof(int);
 }
 
 template <typename K>
@@ -349,36 +357,39 @@ static int set_smem(sgw_ctx *ctx, K kernel, size_t bytes) {
   return SGW_OK;
 }
 
-int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active) {
+int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active,
+                  const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
-  const size_t smem = zpass_smem(ctx);
+  const GridDev g = grid_dev(ctx, gr);
+  const size_t smem = zpass_smem(g);
   SGW_CHECK(set_smem(ctx, k_zpass_g2r, smem));
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_g2r<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(grid_dev(ctx), s.dev(), in, ld, T, active);
+  k_zpass_g2r<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), in, ld, T, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
 
 int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *out, long ld, const ZEpilogue &epi,
-                  const int *active) {
+                  const int *active, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
-  const size_t smem = zpass_smem(ctx);
+  const GridDev g = grid_dev(ctx, gr);
+  const size_t smem = zpass_smem(g);
   SGW_CHECK(set_smem(ctx, k_zpass_r2g, smem));
   dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
-  const double scale = 1.0 / ((double)ctx->nr1 * ctx->nr2 * ctx->nr3);
+  const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_r2g<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(grid_dev(ctx), s.dev(), T, out, ld, epi, scale, active);
+  k_zpass_r2g<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), T, out, ld, epi, scale, active);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
 
 int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
-              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod) {
+              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
-  const size_t smem = plane_smem(ctx);
-  dim3 grid(ctx->nr3, nvec);
-  GridDev g = grid_dev(ctx);
+  GridDev g = grid_dev(ctx, gr);
+  const size_t smem = plane_smem(g, 1);
+  dim3 grid(g.nz, nvec);
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
   ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
@@ -404,13 +415,14 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
 }
 
 int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
-                  double wgt, cplx *Tout, int accumulate) {
+                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr) {
   if (npf <= 0) return SGW_OK;
-  const size_t smem = (size_t)(2 * ctx->nr2 * (ctx->nr1 | 1) + ctx->nr1 + ctx->nr2) * sizeof(cplx) + 2 * (size_t)ctx->nr1 * sizeof(int);
+  const GridDev g = grid_dev(ctx, gr);
+  const size_t smem = plane_smem(g, 2);
   SGW_CHECK(set_smem(ctx, k_plane_rho, smem));
-  dim3 grid(npf, ctx->nr3);
+  dim3 grid(npf, g.nz);
   ProfScope prof(ctx, PC_RHO_PLANE);
-  k_plane_rho<<<grid, RTHREADS, smem, ctx->stream>>>(grid_dev(ctx), sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  k_plane_rho<<<grid, RTHREADS, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -461,6 +473,7 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   sph->ncol = (int)col_x.size();
   sph->nxs = (int)xs.size();
   sph->perm = order;
+  sph->h_col_x = col_x; sph->h_col_y = col_y; sph->h_col_ptr = col_ptr; sph->h_zof = zof;
   SGW_CHECK(upload(ctx, &sph->d_col_x, col_x.data(), col_x.size()));
   SGW_CHECK(upload(ctx, &sph->d_col_y, col_y.data(), col_y.size()));
   {
@@ -476,6 +489,51 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   return SGW_OK;
 }
 
+// Re-express a sphere in another box: every entry keeps its Miller indices (box coordinate c of an n-point axis
+// means m = c for c <= (n-1)/2, else c - n), its position in the vector and its column; only the box coordinates
+// change, so coefficient vectors are shared between the two grids.  Fails if the box is too small for the sphere.
+int remap_sphere(sgw_ctx *ctx, const Sphere &fine, const FftGrid &gr, Sphere *out) {
+  free_sphere(out);
+  const int nf[3] = {ctx->nr1, ctx->nr2, ctx->nr3}, nc[3] = {gr.n1, gr.n2, gr.n3};
+  auto conv = [&](int c, int d, int *res) {
+    const int m = c <= (nf[d] - 1) / 2 ? c : c - nf[d];
+    if (2 * std::abs(m) >= nc[d]) return false;
+    *res = ((m % nc[d]) + nc[d]) % nc[d];
+    return true;
+  };
+  const int ncol = fine.ncol, npw = fine.npw;
+  std::vector<int> col_x(ncol), col_y(ncol), col_off(ncol), zof(npw), colof(npw);
+  std::vector<char> xused(nc[0], 0);
+  bool ok = true;
+  for (int c = 0; c < ncol; ++c) {
+    ok = ok && conv(fine.h_col_x[c], 0, &col_x[c]) && conv(fine.h_col_y[c], 1, &col_y[c]);
+    if (!ok) break;
+    col_off[c] = col_y[c] * (nc[0] | 1) + col_x[c];
+    xused[col_x[c]] = 1;
+    for (int p = fine.h_col_ptr[c]; p < fine.h_col_ptr[c + 1]; ++p) colof[p] = c;
+  }
+  for (int p = 0; ok && p < npw; ++p) ok = conv(fine.h_zof[p], 2, &zof[p]);
+  if (!ok) {
+    ctx->err = "remap_sphere: target FFT box too small for the sphere";
+    return SGW_E_ARG;
+  }
+  std::vector<int> xs;
+  for (int x = 0; x < nc[0]; ++x)
+    if (xused[x]) xs.push_back(x);
+  out->npw = npw; out->ncol = ncol; out->nxs = (int)xs.size();
+  out->perm = fine.perm;
+  out->h_col_x = col_x; out->h_col_y = col_y; out->h_col_ptr = fine.h_col_ptr; out->h_zof = zof;
+  SGW_CHECK(upload(ctx, &out->d_col_x, col_x.data(), col_x.size()));
+  SGW_CHECK(upload(ctx, &out->d_col_y, col_y.data(), col_y.size()));
+  SGW_CHECK(upload(ctx, &out->d_col_off, col_off.data(), col_off.size()));
+  SGW_CHECK(upload(ctx, &out->d_col_ptr, fine.h_col_ptr.data(), fine.h_col_ptr.size()));
+  SGW_CHECK(upload(ctx, &out->d_colof, colof.data(), colof.size()));
+  SGW_CHECK(upload(ctx, &out->d_zof, zof.data(), zof.size()));
+  SGW_CHECK(upload(ctx, &out->d_xs, xs.data(), xs.size()));
+  SGW_CHECK(upload(ctx, &out->d_perm, fine.perm.data(), fine.perm.size()));
+  return SGW_OK;
+}
+
 void free_sphere(Sphere *s) {
   int **ptrs[] = {&s->d_col_x, &s->d_col_y, &s->d_col_ptr, &s->d_colof, &s->d_zof, &s->d_xs, &s->d_perm, &s->d_col_off};
   for (auto p : ptrs) {
@@ -484,6 +542,7 @@ void free_sphere(Sphere *s) {
   }
   s->npw = s->ncol = s->nxs = 0;
   s->perm.clear();
+  s->h_col_x.clear(); s->h_col_y.clear(); s->h_col_ptr.clear(); s->h_zof.clear();
 }
 
 }  // namespace sgw

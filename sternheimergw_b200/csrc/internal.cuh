@@ -55,9 +55,17 @@ struct SphereDev {
   const int *col_off;      // col_y * (nx | 1) + col_x: offset of the column inside a shared-memory plane
 };
 
+// An FFT box other than the context's main one (used for the alias-free coarse grid of the Delta-rho accumulation)
+struct FftGrid {
+  int n1 = 0, n2 = 0, n3 = 0;
+  Plan1D px, py, pz;
+  cplx *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
+};
+
 struct Sphere {
   int npw = 0, ncol = 0, nxs = 0;
   std::vector<int> perm;   // perm[p] = caller's 0-based index of internal entry p
+  std::vector<int> h_col_x, h_col_y, h_col_ptr, h_zof;   // host copies (box coordinates of the grid it was built on)
   int *d_col_x = nullptr, *d_col_y = nullptr, *d_col_ptr = nullptr, *d_colof = nullptr, *d_zof = nullptr,
       *d_xs = nullptr, *d_perm = nullptr, *d_col_off = nullptr;
   SphereDev dev() const {
@@ -124,6 +132,13 @@ struct sgw_ctx {
   double prof_ms[sgw::PC_N] = {0};
   int64_t prof_n[sgw::PC_N] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // alias-free coarse grid for the Delta-rho accumulation of sgw_coulomb (coulomb.cu: rho_grid_prepare)
+  sgw::FftGrid rho_grid;
+  bool rho_grid_on = false, rho_last_coarse = false;
+  long tables_version = 0, rho_grid_version = -1;
+  int rho_grid_ngc = -1;
+  sgw::Sphere rho_sph_c;
+  std::vector<sgw::Sphere> pair_k_c, pair_kq_c;
   cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // solver look-ahead (bicgstab.cu)
   int *h_flags = nullptr;                        // pinned host flags read back by the solvers
   int gemm_cta_per_sm = 0;                       // resident k_zgemm CTAs per SM (0 = attributes not set yet)
@@ -194,22 +209,27 @@ struct ProfScope {
 };
 void begin_call(sgw_ctx *ctx);
 void end_call(sgw_ctx *ctx);
-GridDev grid_dev(const sgw_ctx *ctx);
+GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr = nullptr);
 int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl_1based, Sphere *sph);
+// same entries, same order and same column partition as `fine` (built on the context's grid), re-expressed in the box `gr`
+int remap_sphere(sgw_ctx *ctx, const Sphere &fine, const FftGrid &gr, Sphere *out);
+int make_fft_grid(sgw_ctx *ctx, int n1, int n2, int n3, FftGrid *gr);
+void free_fft_grid(FftGrid *gr);
 void free_sphere(Sphere *s);
 
 // ---- fft.cu : batched local-potential pipeline ----
 enum PlaneMode { PLANE_VLOC = 0, PLANE_FIELD = 1, PLANE_TO_R = 2, PLANE_FROM_R = 3 };
 // G (column order, nvec vectors with leading dim ld) -> T1[vec][pz][col]
-int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active);
+int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active,
+                  const FftGrid *gr = nullptr);
 // plane stage: T_in (sphere sin) -> 2-D inverse -> (x v | x field | store R) ; (load R) -> 2-D forward -> T_out (sphere sout)
 int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
-              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod = 0);
+              const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod = 0, const FftGrid *gr = nullptr);
 // incdrhoscf ([QE], solve_linter.f90:489-497) for npf (perturbation, frequency) pairs: per z-plane, loop over the nocc
 // bands: 2-D inverse of dpsi, acc += conj(psi_v(r)) dpsi(r); then wgt*acc -> 2-D forward -> columns of the density
 // sphere `sout` (Tout[pf][pz][col], += if accumulate) or, when Rout != null, the real-space planes Rout[pf][pz][nxy]
 int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
-                  double wgt, cplx *Tout, int accumulate);
+                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr = nullptr);
 // epilogue modes of the final z pass
 struct ZEpilogue {
   int mode;              // 0: out = val ; 1: out = out*keep + g2kin*psi + sigma*psi + val (H.psi) ; 2: out += val
@@ -220,7 +240,7 @@ struct ZEpilogue {
   int keep_out;          // 1: add to existing out (non-local part already there)
 };
 int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *out, long ld, const ZEpilogue &epi,
-                  const int *active);
+                  const int *active, const FftGrid *gr = nullptr);
 
 // ---- gemm.cu : non-local projectors and valence projector (complex FP64, DMMA) ----
 // out[:, v] = P * (W .* (P^H psi[:, v]))  with W = blockdiag(dion, alpha_pv * I_nbnd); out overwritten (npwx rows)

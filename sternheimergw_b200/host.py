@@ -209,6 +209,12 @@ class Context:
             raise SgwError(f"solver did not converge (ierr={ierr.value})")
         return scr
 
+    def rho_grid(self):
+        """(reduced, (n1, n2, n3)): the box the last `coulomb` accumulated Delta-rho on (see sgw_get_rho_grid)."""
+        dims = (C.c_int * 3)()
+        rc = self._chk(self._L.sgw_get_rho_grid(self._h, dims), "get_rho_grid")
+        return bool(rc), tuple(dims)
+
     def coulomb_q0G0(self, config: select_solver_type, fiu):
         fiu = _c16(fiu)
         eps = np.zeros(fiu.size, dtype=np.complex128)

@@ -48,6 +48,32 @@ def test_coulomb_matches_oracle(ctx, name, nk, ngc, fiu):
     assert _rel(eps_m, ref[0, :, 0]) < 1e-8
 
 
+def test_coulomb_reduced_rho_grid_matches_oracle_and_full_box(ctx, monkeypatch):
+    """Si8 supercell (36^3 box): Delta-rho is accumulated on the alias-free reduced box; eps must equal the oracle's
+    (full box, [QE] incdrhoscf order) to 1e-8 and the library's own full-box result to rounding."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset("si8")
+    ctx.install_system(syn)
+    fiu = np.array([0.0, 0.9j])
+    ngc = 7
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-11)
+    scr = ctx.coulomb(cfg, 2, ngc, 2, igu, fiu)
+    reduced, dims = ctx.rho_grid()
+    assert reduced and np.prod(dims) < 0.7 * np.prod(syn.nr), (reduced, dims)
+    monkeypatch.setenv("SGW_RHO_GRID", "fine")
+    scr_full = ctx.coulomb(cfg, 2, ngc, 2, igu, fiu)
+    assert ctx.rho_grid() == (False, tuple(syn.nr))
+    monkeypatch.delenv("SGW_RHO_GRID")
+    assert _rel(scr, scr_full) < 1e-11, _rel(scr, scr_full)
+    ps = oracle.PwSystem(syn)
+    ref, ierr, _ = ps.coulomb(2, ngc, 2, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-11), nthreads=8)
+    assert ierr == 0
+    assert _rel(scr, ref) < 1e-8, _rel(scr, ref)
+
+
 def test_coulomb_production_threshold_and_sos(ctx):
     """Production threshold (1e-4): eps within 10*thr of the converged one; converged one equals sum-over-states."""
     import sos
