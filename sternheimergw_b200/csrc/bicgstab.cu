@@ -18,6 +18,9 @@
 // (:890-894) follow the reference, not Frommer's paper.
 #include "internal.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 namespace sgw {
@@ -480,6 +483,143 @@ __global__ void __launch_bounds__(BT) k_shift_fused(BicgState s, int chunk) {
   }
 }
 
+// ---------------------------------------------------------------- collapsed shifted update (L <= 4)
+// The deferred shifted update is LINEAR in (u^sigma_0, the L(L+1)/2+1 residual snapshots, r_0..r_{L-1}): replaying
+// the recurrences of k_shift_fused on coefficient vectors instead of on vector elements (k_shift_coef, one thread per
+// (rhs, shift)) gives   x^sigma += sum_k X_k basis_k ,  u^sigma_0 <- sum_k C_k basis_k .  Per element and shift that is
+// 1 + 2L terms for x and 2 + L(L+1)/2 terms for u_0 (84 FP64 FMAs at L = 4 instead of 196), which turns the update from
+// FP64-pipe-bound (ncu: 62 % FP64, 42 % DRAM) into an HBM-bound stream.  Algebraically identical to the reference's
+// recurrences (bicgstab.f90:621-664,:688-698,:850-911), re-associated; SGW_SHIFT=faithful keeps the step-by-step kernel.
+template <int LT>
+struct ShiftCoef {
+  static constexpr int NSN = LT * (LT + 1) / 2 + 1;
+  cplx xu0;            // x  += xu0 * u0_old
+  cplx xs[LT];         //     + xs[jj] * snap[jj(jj+1)/2]        (the i = 0 snapshots)
+  cplx xr[LT];         //     + xr[j] * r_j                      (stage 2 only)
+  cplx uu0;            // u0 <- uu0 * u0_old + sum_k us[k] * snap[k]   (stage 2 only)
+  cplx us[NSN];
+};
+
+template <int LT>
+__global__ void __launch_bounds__(128) k_shift_coef(BicgState s, ShiftCoef<LT> *__restrict__ out) {
+  constexpr int NSN = LT * (LT + 1) / 2 + 1, NB = 1 + NSN;   // basis: u0_old, snap[0..NSN-1]
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)s.nrhs * s.ns) return;
+  const int b = (int)(idx / s.ns), is = (int)(idx % s.ns);
+  const int stage = s.stage[b];
+  if (stage == 0) return;
+  const ShiftScal &a = s.shift[(long)b * s.ns + is];
+  const StepScal *q = s.step + ((long)b * s.ns + is) * LT;
+  const cplx zero = cmake(0.0, 0.0), sigma = a.sigma;
+  cplx US[LT + 1][NB], X[NB];
+#pragma unroll
+  for (int i = 0; i <= LT; ++i)
+#pragma unroll
+    for (int k = 0; k < NB; ++k) US[i][k] = zero;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) X[k] = zero;
+  US[0][0] = cmake(1.0, 0.0);
+#pragma unroll
+  for (int jj = 0; jj < LT; ++jj) {
+    const cplx beta_s = q[jj].beta, f_old = q[jj].f_old, alpha_s = q[jj].alpha, f_new = q[jj].f_new, inv_alpha = q[jj].inv_alpha;
+#pragma unroll
+    for (int i = 0; i <= jj; ++i) {
+      const int k = jj * (jj + 1) / 2 + i;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) US[i][c] = cmul(cneg(beta_s), US[i][c]);              // :644
+      US[i][1 + k] = cadd(US[i][1 + k], f_old);                                        // :645
+      if (i == 0) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) X[c] = cfma(alpha_s, US[0][c], X[c]);              // :650
+      }
+      if (i == jj) {
+        const int kn = (jj < LT - 1) ? (jj + 1) * (jj + 2) / 2 + jj : NSN - 1;
+        cplx T[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) T[c] = zero;
+        T[1 + k] = f_old;                                                              // :661-662
+        T[1 + kn] = csub(T[1 + kn], f_new);                                            // :693-694
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          T[c] = cmul(inv_alpha, T[c]);                                                // :695
+          US[jj + 1][c] = cfma(cneg(sigma), US[i][c], T[c]);                           // :696
+        }
+      }
+    }
+  }
+  ShiftCoef<LT> &o = out[idx];
+  o.xu0 = X[0];
+#pragma unroll
+  for (int jj = 0; jj < LT; ++jj) o.xs[jj] = X[1 + jj * (jj + 1) / 2];
+  if (stage == 2) {
+    const SeedScal &sd = s.seed[b];
+    const cplx inv_psi = cdiv(cmake(1.0, 0.0), a.psi);                                  // :910
+    o.xr[0] = cmul(a.gamma_p[0], a.inv_xi);                                            // :888
+#pragma unroll
+    for (int jj = 1; jj <= LT - 1; ++jj) o.xr[jj] = cmul(a.gamma_pp[jj - 1], a.inv_xi); // :904
+    cplx U0[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      cplx u0 = cfma(cneg(sd.gamma[LT - 1]), US[LT][c], US[0][c]);                     // :893
+#pragma unroll
+      for (int jj = 1; jj <= LT - 1; ++jj) u0 = cfma(cneg(sd.gamma[jj - 1]), US[jj][c], u0);   // :900
+      U0[c] = cmul(inv_psi, u0);                                                       // :911
+    }
+    o.uu0 = U0[0];
+#pragma unroll
+    for (int k = 0; k < NSN; ++k) o.us[k] = U0[1 + k];
+  }
+}
+
+constexpr int CSHIFT_CHUNK = 32;
+template <int LT>
+__global__ void __launch_bounds__(BT) k_shift_apply(BicgState s, const ShiftCoef<LT> *__restrict__ coef, int chunk) {
+  constexpr int NSN = LT * (LT + 1) / 2 + 1;
+  const int b = blockIdx.y;
+  const int stage = s.stage[b];
+  if (stage == 0) return;
+  const int is0 = blockIdx.z * chunk, nsl = min(chunk, s.ns - is0);
+  __shared__ ShiftCoef<LT> sc[CSHIFT_CHUNK];
+  {
+    const cplx *src = (const cplx *)(coef + (long)b * s.ns + is0);
+    cplx *dst = (cplx *)sc;
+    const int nc = nsl * (int)(sizeof(ShiftCoef<LT>) / sizeof(cplx));
+    for (int t = threadIdx.x; t < nc; t += BT) dst[t] = src[t];
+  }
+  __syncthreads();
+  const int e = blockIdx.x * BT + threadIdx.x;
+  if (e >= s.n) return;
+  const long n = s.n;
+  cplx sn[NSN], rr[LT];
+  const cplx *snapg = snap(s, b, 0) + e;
+#pragma unroll
+  for (int k = 0; k < NSN; ++k) sn[k] = snapg[(long)k * n];
+  if (stage == 2) {
+#pragma unroll
+    for (int j = 0; j < LT; ++j) rr[j] = seedR(s, b, j)[e];
+  }
+  cplx *pu0 = shiftU0(s, b, is0) + e, *px = shiftX(s, b, is0) + e;
+  // software pipeline: the loads of shift il+1 are issued before the arithmetic of shift il
+  cplx u0n = pu0[0], xn = px[0];
+  for (int il = 0; il < nsl; ++il) {
+    const cplx u0 = u0n, x0 = xn;
+    if (il + 1 < nsl) { u0n = pu0[(long)(il + 1) * n]; xn = px[(long)(il + 1) * n]; }
+    const ShiftCoef<LT> &c = sc[il];
+    cplx x = cfma(c.xu0, u0, x0);
+#pragma unroll
+    for (int jj = 0; jj < LT; ++jj) x = cfma(c.xs[jj], sn[jj * (jj + 1) / 2], x);
+    if (stage == 2) {
+#pragma unroll
+      for (int j = 0; j < LT; ++j) x = cfma(c.xr[j], rr[j], x);
+      cplx u = cmul(c.uu0, u0);
+#pragma unroll
+      for (int k = 0; k < NSN; ++k) u = cfma(c.us[k], sn[k], u);
+      pu0[(long)il * n] = u;
+    }
+    px[(long)il * n] = x;
+  }
+}
+
 // L14-L17 of the seed system and the delayed L32 residual update (:833-844, :919-925)
 __global__ void __launch_bounds__(BT) k_mr_seed(BicgState s) {
   const int b = blockIdx.y;
@@ -540,6 +680,27 @@ static int launch_shift_fused(sgw_ctx *ctx, const BicgState &s, int chunk, size_
   return SGW_OK;
 }
 
+template <int LT>
+static int launch_shift_collapsed(sgw_ctx *ctx, const BicgState &s) {
+  ShiftCoef<LT> *coef = nullptr;
+  SGW_CHECK(ws(ctx, "bi_scoef", (size_t)s.nrhs * s.ns, &coef));
+  ProfScope prof(ctx, PC_SHIFT);
+  const long tot = (long)s.nrhs * s.ns;
+  k_shift_coef<LT><<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(s, coef);
+  SGW_LAUNCH_CHECK();
+  const int nchunks = (s.ns + CSHIFT_CHUNK - 1) / CSHIFT_CHUNK;     // equal-sized chunks of <= 32 shifts per CTA
+  const int chunk = (s.ns + nchunks - 1) / nchunks;
+  dim3 grid((unsigned)((s.n + BT - 1) / BT), (unsigned)s.nrhs, (unsigned)((s.ns + chunk - 1) / chunk));
+  k_shift_apply<LT><<<grid, BT, 0, ctx->stream>>>(s, coef, chunk);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+static bool shift_faithful() {
+  const char *e = getenv("SGW_SHIFT");
+  return e && strcmp(e, "faithful") == 0;
+}
+
 int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo) {
   if (lmax < 1 || lmax > LCAP - 1) {
     ctx->err = "bicg_lmax must be in 1..15";
@@ -589,6 +750,7 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   k_init_vec<<<gvec, BT, 0, st>>>(s, sb.d_b, sb.ldb);
   SGW_LAUNCH_CHECK();
 
+  const bool faithful = shift_faithful();
   const long ldv = n;   // vectors inside U/R are contiguous with stride (L+1)*n between RHS
   int rc = SGW_OK;
   for (int iter = 1; iter <= max_iter && rc == SGW_OK; ++iter) {
@@ -634,7 +796,10 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
       k_mr_mgs<<<(unsigned)nr, 1024, 0, st>>>(s);
       SGW_LAUNCH_CHECK();
     }
-    if (s.ns > 0) {
+    if (s.ns > 0 && !faithful && (lmax == 2 || lmax == 4)) {
+      rc = lmax == 4 ? launch_shift_collapsed<4>(ctx, s) : launch_shift_collapsed<2>(ctx, s);
+      if (rc != SGW_OK) break;
+    } else if (s.ns > 0) {
       switch (lmax) {
         case 1: rc = launch_shift_fused<1>(ctx, s, chunk, sm_fused); break;
         case 2: rc = launch_shift_fused<2>(ctx, s, chunk, sm_fused); break;

@@ -40,7 +40,7 @@ constexpr size_t zgemm_smem() { return (size_t)NSTAGE * (a_tile_elems<A_KCONTIG>
 // B is K x N column-major.  blockIdx.z selects a K range (split-K): partial results go to C + z * split_stride.
 // Global -> shared staging is double buffered with cp.async so that the DMMA pipe does not wait on HBM/L2.
 template <bool A_KCONTIG, bool CONJA>
-__global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
+__global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
                                                const cplx *__restrict__ B, long ldb, cplx *__restrict__ C, long ldc,
                                                cplx alpha, cplx beta, int kchunk, long split_stride,
                                                const int *__restrict__ active) {
@@ -58,11 +58,17 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
   cplx *Bs = gsm + NSTAGE * ASZ;       // [NSTAGE][BN * PK]
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
   const int g = lane >> 2, t = lane & 3;
-  double cre[2][2][2], cim[2][2][2];
+  // 3M complex product (Karatsuba): with a = op(A) element, p1 += ar*br, p2 += ai*bi, p3 += (ar+ai)*(br+bi);
+  // re = p1 - p2, im = p3 - p1 - p2.  Three DMMAs per complex tile product instead of four: the kernel is bound by
+  // the DMMA pipe (ncu: math_pipe_throttle), so this is a 25 % cut of its critical resource.  The imaginary part
+  // carries one extra rounding of size eps*(|p1|+|p2|), i.e. the same norm-wise bound as a 4M product.
+  double p1[2][2][2], p2[2][2][2], p3[2][2][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) p1[i][j][c] = p2[i][j][c] = p3[i][j][c] = 0.0;
 
   auto stage_load = [&](int st, int k0) {
     cplx *as = As + st * ASZ, *bs = Bs + st * (BN * PK);
@@ -107,24 +113,20 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) b[j] = bs[(wn + j * 8 + g) * PK + kk + t];
-      // op(A) = conj(A)^T: re += ar*br + ai*bi ; im += ar*bi - ai*br.  op(A) = A: re += ar*br - ai*bi ; im += ar*bi + ai*br
-      // The two updates of one accumulator are issued 8 DMMAs apart so that they do not serialise on its latency.
+      // op(A) = conj(A)^T uses ai -> -ai
+      double ai[2], asum[2], bsum[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { ai[i] = CONJA ? -a[i].y : a[i].y; asum[i] = a[i].x + ai[i]; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bsum[j] = b[j].x + b[j].y;
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          dmma(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
-          dmma(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
+          dmma(p1[i][j][0], p1[i][j][1], a[i].x, b[j].x);
+          dmma(p2[i][j][0], p2[i][j][1], ai[i], b[j].y);
+          dmma(p3[i][j][0], p3[i][j][1], asum[i], bsum[j]);
         }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double ai_re = CONJA ? a[i].y : -a[i].y, ai_im = CONJA ? -a[i].y : a[i].y;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          dmma(cre[i][j][0], cre[i][j][1], ai_re, b[j].y);
-          dmma(cim[i][j][0], cim[i][j][1], ai_im, b[j].x);
-        }
-      }
     }
     __syncthreads();
   }
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(GT) k_zgemm(int M, int N, int K, const cplx *_
         const int row = m0 + wm + i * 8 + g;
         const int col = n0 + wn + j * 8 + 2 * t + c;
         if (row < M && col < N) {
-          cplx acc = cmake(cre[i][j][c], cim[i][j][c]);
+          cplx acc = cmake(p1[i][j][c] - p2[i][j][c], (p3[i][j][c] - p1[i][j][c]) - p2[i][j][c]);
           cplx r = cmul(alpha, acc);
           if (has_beta) r = cfma(beta, Cz[(long)row + (long)col * ldc], r);
           Cz[(long)row + (long)col * ldc] = r;
