@@ -304,13 +304,21 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
   SGW_CHECK(upload(ctx, &k->d_g2kin, g2.data(), g2.size()));
   const int m = nkb + nbnd_occ;
   if (m > 0) {
-    std::vector<cplx> P((size_t)npwx * m, cmake(0.0, 0.0));
-    const cplx *v = (const cplx *)vkb, *e = (const cplx *)evq;
-    for (int j = 0; j < nkb; ++j)
-      for (int p = 0; p < npw; ++p) P[(size_t)j * npwx + p] = v[(size_t)j * npwx + perm[p]];
-    for (int j = 0; j < nbnd_occ; ++j)
-      for (int p = 0; p < npw; ++p) P[(size_t)(nkb + j) * npwx + p] = e[(size_t)j * npwx + perm[p]];
-    SGW_CHECK(upload(ctx, &k->d_P, P.data(), P.size()));
+    // P = [vkb | evq] with rows in column order: the caller's arrays go up as they are and are permuted on the device
+    cplx *stage = nullptr;
+    const int mmax = std::max(nkb, nbnd_occ);
+    SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * mmax, &stage));
+    if (k->d_P) { cudaFree(k->d_P); k->d_P = nullptr; }
+    SGW_CUDA(cudaMalloc((void **)&k->d_P, sizeof(cplx) * (size_t)npwx * m));
+    if (nkb > 0) {
+      SGW_CUDA(cudaMemcpyAsync(stage, vkb, sizeof(cplx) * (size_t)npwx * nkb, cudaMemcpyHostToDevice, ctx->stream));
+      SGW_CHECK(permute_in(ctx, k->sph, nkb, stage, npwx, k->d_P, npwx, npwx));
+    }
+    if (nbnd_occ > 0) {
+      SGW_CUDA(cudaMemcpyAsync(stage, evq, sizeof(cplx) * (size_t)npwx * nbnd_occ, cudaMemcpyHostToDevice, ctx->stream));
+      SGW_CHECK(permute_in(ctx, k->sph, nbnd_occ, stage, npwx, k->d_P + (size_t)nkb * npwx, npwx, npwx));
+    }
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   if (nkb > 0) SGW_CHECK(upload(ctx, &k->d_dion, dion, (size_t)nkb * nkb));
   k->set = true;

@@ -558,11 +558,14 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   if (kp.d_evc) { cudaFree(kp.d_evc); kp.d_evc = nullptr; }
   SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
   const int npwx = ks.npwx;
-  std::vector<cplx> e((size_t)npwx * nbnd, cmake(0.0, 0.0));
-  const cplx *src = (const cplx *)evc;
-  for (int b = 0; b < nbnd; ++b)
-    for (int p = 0; p < npw_k; ++p) e[(size_t)b * npwx + p] = src[(size_t)b * npwx + kp.sph_k.perm[p]];
-  SGW_CHECK(upload(ctx, &kp.d_evc, e.data(), e.size()));
+  {
+    cplx *stage = nullptr;
+    SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * nbnd, &stage));
+    SGW_CUDA(cudaMalloc((void **)&kp.d_evc, sizeof(cplx) * (size_t)npwx * nbnd));
+    SGW_CUDA(cudaMemcpyAsync(stage, evc, sizeof(cplx) * (size_t)npwx * nbnd, cudaMemcpyHostToDevice, ctx->stream));
+    SGW_CHECK(permute_in(ctx, kp.sph_k, nbnd, stage, npwx, kp.d_evc, npwx, npwx));     // rows >= npw_k are zeroed
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   kp.slot = slot_kq; kp.npw_k = npw_k; kp.nbnd = nbnd; kp.wk = wk;
   kp.et.assign(et, et + nbnd);
   kp.set = true;

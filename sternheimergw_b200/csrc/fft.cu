@@ -20,13 +20,14 @@
 
 namespace sgw {
 
-constexpr int ZCB = 16;        // columns per CTA in the z passes
-constexpr int ZTHREADS = 160;   // launch bound; the launch uses zpass_threads()
-constexpr int ZMINB = 4;        // resident CTAs per SM the register allocation must allow
-static_assert((ZCB & (ZCB - 1)) == 0, "ZCB must be a power of two");
+constexpr int ZCB_DEFAULT = 16; // columns per CTA in the z passes (template parameter ZCB of the kernels)
+constexpr int ZTHREADS = 256;   // launch bound; the launch uses zpass_threads()
+constexpr int ZMINB = 2;        // resident CTAs per SM the register allocation must allow
+
 constexpr int PTHREADS = 256;
 
-__global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
+template <int ZCB>
+__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
                                                          cplx *__restrict__ T, const int *__restrict__ active) {
   const int vec = blockIdx.y;
   if (active && !active[vec]) return;
@@ -57,7 +58,8 @@ __global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_g2r(GridDev g, Sphere
   }
 }
 
-__global__ void __launch_bounds__(ZTHREADS, ZMINB) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
+template <int ZCB>
+__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
                                                          cplx *__restrict__ out, long ld, ZEpilogue epi, double scale,
                                                          const int *__restrict__ active) {
   const int vec = blockIdx.y;
@@ -330,10 +332,15 @@ GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr) {
   return g;
 }
 
+static int zpass_zcb() {
+  static int forced = -1;                                       // SGW_ZCB: tuning knob (8 | 16 | 32)
+  if (forced < 0) { const char *e = getenv("SGW_ZCB"); forced = e ? atoi(e) : 0; }
+  return (forced == 8 || forced == 32) ? forced : ZCB_DEFAULT;
+}
 static int zpass_threads(const sgw_ctx *ctx) {
   static int forced = -1;                                       // SGW_ZTHREADS: tuning knob (multiple of 32, <= ZTHREADS)
   if (forced < 0) { const char *e = getenv("SGW_ZTHREADS"); forced = e ? atoi(e) : 0; }
-  if (forced >= 32 && forced <= ZTHREADS) return forced;
+  if (forced >= 32 && forced <= (zpass_zcb() >= 32 ? 256 : 160)) return forced;
   (void)ctx;
   return 96;   // measured on B200 (Si64): 96 -> 58 ms, 128 -> 63 ms, 160 -> 73 ms per step; small CTAs keep more loads in flight
 }
@@ -342,7 +349,7 @@ static int plane_threads() {
   if (forced < 0) { const char *e = getenv("SGW_PTHREADS"); forced = e ? atoi(e) : 0; }
   return (forced == 384 || forced == 512) ? forced : 256;
 }
-static size_t zpass_smem(const GridDev &g) { return (size_t)(ZCB * (g.nz | 1) + g.nz) * sizeof(cplx); }
+static size_t zpass_smem(const GridDev &g, int zcb) { return (size_t)(zcb * (g.nz | 1) + g.nz) * sizeof(cplx); }
 static size_t plane_smem(const GridDev &g, int nplanes) {
   return (size_t)(nplanes * g.ny * g.pitchx + g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)g.nx * sizeof(int);
 }
@@ -361,11 +368,17 @@ int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long 
                   const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
-  const size_t smem = zpass_smem(g);
-  SGW_CHECK(set_smem(ctx, k_zpass_g2r, smem));
-  dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
+  const int zcb = zpass_zcb();
+  const size_t smem = zpass_smem(g, zcb);
+  dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_g2r<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), in, ld, T, active);
+#define SGW_Z(Z)                                                                                       \
+  do {                                                                                                 \
+    SGW_CHECK(set_smem(ctx, k_zpass_g2r<Z>, smem));                                                    \
+    k_zpass_g2r<Z><<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), in, ld, T, active);    \
+  } while (0)
+  if (zcb == 8) SGW_Z(8); else if (zcb == 32) SGW_Z(32); else SGW_Z(16);
+#undef SGW_Z
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -374,12 +387,18 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
                   const int *active, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
-  const size_t smem = zpass_smem(g);
-  SGW_CHECK(set_smem(ctx, k_zpass_r2g, smem));
-  dim3 grid((s.ncol + ZCB - 1) / ZCB, nvec);
+  const int zcb = zpass_zcb();
+  const size_t smem = zpass_smem(g, zcb);
+  dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
   const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
   ProfScope prof(ctx, PC_FFT_Z);
-  k_zpass_r2g<<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), T, out, ld, epi, scale, active);
+#define SGW_Z(Z)                                                                                                  \
+  do {                                                                                                            \
+    SGW_CHECK(set_smem(ctx, k_zpass_r2g<Z>, smem));                                                               \
+    k_zpass_r2g<Z><<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), T, out, ld, epi, scale, active);  \
+  } while (0)
+  if (zcb == 8) SGW_Z(8); else if (zcb == 32) SGW_Z(32); else SGW_Z(16);
+#undef SGW_Z
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }

@@ -25,7 +25,41 @@ def f(x):
         return float("nan")
 
 
+CLASS_OF = {"k_plane<0": "fft_plane", "k_zpass_g2r": "fft_zpass", "k_zpass_r2g": "fft_zpass", "k_zgemm<1, 1>": "gemm_project",
+            "k_zgemm<0, 0>": "gemm_expand", "k_shift_fused": "shift_fused", "k_shift_apply": "shift_fused"}
+
+
+def traffic(rep, units_per_launch):
+    """bench.py's profiles/traffic.json: measured DRAM bytes per unit (vector; RHS x outer iteration for the shifted
+    update) and pipe utilisation of every kernel class, averaged over the captured launches."""
+    import json
+    hdr, units, data = raw(rep)
+    ix = {h: i for i, h in enumerate(hdr)}
+    acc = {}
+    for d in data:
+        name = d[ix["Kernel Name"]].replace("void ", "")
+        cls = next((c for k, c in CLASS_OF.items() if name.startswith(k)), None)
+        if cls is None:
+            continue
+        def byt(m):
+            return f(d[ix[m]]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[ix[m]], 1.0)
+        a = acc.setdefault(cls, {"n": 0, "bytes": 0.0, "fp64": 0.0, "tensor": 0.0, "dram": 0.0})
+        a["n"] += 1
+        a["bytes"] += byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum")
+        a["fp64"] += f(d[ix["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]])
+        a["tensor"] += f(d[ix["TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"]])
+        a["dram"] += f(d[ix["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])
+    out = {}
+    for cls, a in acc.items():
+        out[cls] = {"dram_bytes_per_unit": a["bytes"] / a["n"] / units_per_launch, "fp64_pipe_pct": a["fp64"] / a["n"],
+                    "tensor_pipe_pct": a["tensor"] / a["n"], "dram_pct": a["dram"] / a["n"], "launches_captured": a["n"],
+                    "source": rep.split("/")[-1], "units_per_launch": units_per_launch}
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[3], float(sys.argv[2]))
     rep = sys.argv[1]
     hdr, units, data = raw(rep)
     ix = {h: i for i, h in enumerate(hdr)}
