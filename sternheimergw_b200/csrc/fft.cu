@@ -245,8 +245,8 @@ __device__ __noinline__ void run_acc(int R, const cplx *x, cplx *acc, int nlines
 }
 
 // incdrhoscf: one CTA per (pf = perturbation x frequency, z-plane); bands are summed on chip
-constexpr int RTHREADS = 512;
-__global__ void __launch_bounds__(RTHREADS) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 2) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
                                                          const cplx *__restrict__ Tin, const cplx *__restrict__ psir,
                                                          double wgt, cplx *__restrict__ Tout, int accumulate) {
   const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
@@ -345,9 +345,9 @@ static int zpass_threads(const sgw_ctx *ctx) {
   return 96;   // measured on B200 (Si64): 96 -> 58 ms, 128 -> 63 ms, 160 -> 73 ms per step; small CTAs keep more loads in flight
 }
 static int plane_threads() {
-  static int forced = -1;                                       // SGW_PTHREADS: tuning knob (256 | 384 | 512)
+  static int forced = -1;                                       // SGW_PTHREADS: tuning knob (256 | 384 | 512), default 384
   if (forced < 0) { const char *e = getenv("SGW_PTHREADS"); forced = e ? atoi(e) : 0; }
-  return (forced == 384 || forced == 512) ? forced : 256;
+  return (forced == 256 || forced == 512) ? forced : 384;   // B200, Si64: 384 -> 155 ms, 256 -> 161 ms, 512 -> 162 ms per step
 }
 static size_t zpass_smem(const GridDev &g, int zcb) { return (size_t)(zcb * (g.nz | 1) + g.nz) * sizeof(cplx); }
 static size_t plane_smem(const GridDev &g, int nplanes) {
@@ -438,10 +438,16 @@ int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, 
   if (npf <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
   const size_t smem = plane_smem(g, 2);
-  SGW_CHECK(set_smem(ctx, k_plane_rho, smem));
   dim3 grid(npf, g.nz);
   ProfScope prof(ctx, PC_RHO_PLANE);
-  k_plane_rho<<<grid, RTHREADS, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  // small planes (the reduced Delta-rho box): 256 threads fill the butterfly stages better and two CTAs fit on an SM
+  if (g.nx * g.ny <= 3072) {
+    SGW_CHECK(set_smem(ctx, k_plane_rho<256>, smem));
+    k_plane_rho<256><<<grid, 256, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  } else {
+    SGW_CHECK(set_smem(ctx, k_plane_rho<512>, smem));
+    k_plane_rho<512><<<grid, 512, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  }
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
