@@ -108,8 +108,16 @@ int sgw_set_nksq(sgw_ctx *ctx, int nksq);
 int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *nl_igk_k, int nbnd,
                   const sgw_cplx *evc, const double *et, double wk);
 
-/* solve_linter (phys/coul/src/solve_linter.f90:55), direct branch (num_iter = 1):
- * dvbarein(nnr) real-space perturbation, freq(nfreq) -> drhoscf(nnr, nfreq) = -dV_H.  ierr_out: solver code. */
+/* control_gw globals of the self-consistent branch (main/src/gw_input.yml: num_iter_coul -> niter_gw, alpha_mix,
+ * tr2_gw, num_mix_coul -> nmix_gw <= 8 = maxter of mix_pot_c.f90:76): alpha_mix has niter_gw entries. */
+int sgw_set_mixing(sgw_ctx *ctx, int niter_gw, const double *alpha_mix, double tr2_gw, int nmix_gw);
+/* iterations the last self-consistent sgw_solve_linter took ("iter #" line, solve_linter.f90:604) */
+int sgw_get_scf_iterations(const sgw_ctx *ctx);
+/* solve_linter (phys/coul/src/solve_linter.f90:55): dvbarein(nnr) real-space perturbation, freq(nfreq).
+ *  num_iter = 1: direct branch, drhoscf(nnr, nfreq) = -dV_H (:598);
+ *  num_iter > 1: self-consistent branch (:376-460 per-frequency solves with dV_scf psi added, :564-582 complex Broyden
+ *  mixing mix_potential_c, needs sgw_set_mixing), drhoscf = dvscfin (:610).
+ * ierr_out: solver code (0/1/2/3), or 10 when self-consistency was not reached within num_iter (:588-591). */
 int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, const sgw_cplx *dvbarein, int nfreq,
                      const sgw_cplx *freq, sgw_cplx *drhoscf, int32_t *ierr_out);
 /* coulomb (phys/coul/src/coulomb.f90:29): perturbations igstart..igstart+ntask-1 of ig_unique, batched over

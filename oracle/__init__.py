@@ -267,6 +267,20 @@ class PwSystem:
                                   C.byref(st), c_int(nthreads))
         return drho, ierr, {"n_op": st.n_op, "n_outer": st.n_outer}
 
+    def solve_linter_iter(self, num_iter, alpha_mix, tr2_gw, nmix_gw, dvbare, freq, cfg: SolverCfg, nthreads=1):
+        """solve_linter.f90 with num_iter > 1 (self-consistent branch + mix_potential_c): returns dvscfin(nnr, nfreq)."""
+        L = lib(self.native)
+        nnr = int(np.prod(self.syn.nr))
+        dvbare, freq = _c16(np.ravel(dvbare, order="F")), _c16(freq)
+        am = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha_mix, dtype=np.float64), (num_iter,)))
+        out = np.zeros((nnr, freq.size), dtype=np.complex128, order="F")
+        st = Stats()
+        it = c_int(0)
+        ierr = L.orc_solve_linter_iter(C.byref(self.sys), C.byref(cfg), c_int(num_iter), _p(am), c_double(tr2_gw),
+                                       c_int(nmix_gw), _p(dvbare), c_int(freq.size), _p(freq), _p(out), C.byref(st),
+                                       c_int(nthreads), C.byref(it))
+        return out, ierr, {"n_op": st.n_op, "n_outer": st.n_outer, "iter": it.value}
+
     def coulomb(self, igstart, ngc, ntask, ig_unique, fiu, cfg: SolverCfg, nthreads=1):
         L = lib(self.native)
         fiu = _c16(fiu)

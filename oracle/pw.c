@@ -293,11 +293,112 @@ void orc_pw_apply(void *ctx, zcplx sigma, const zcplx *x, zcplx *ax, int n) {
 static int g_band_lo = 0, g_band_hi = 2147483647;
 void orc_set_band_window(int lo, int hi) { g_band_lo = lo; g_band_hi = hi; }
 
-int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
-                     const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads) {
+/* ---------------------------------------------------------------- mix_pot_c.f90:25-198 (complex modified Broyden) */
+static int zinverse(int n, zcplx *a);
+#define MIX_MAXTER 8
+typedef struct {
+  zcplx *df, *dv;          /* ndim x n_iter, SAVEd between calls (mix_pot_c.f90:83) */
+  size_t ndim;
+  int n_iter;
+} orc_mix_state;
+
+static void mix_free(orc_mix_state *m) { free(m->df); free(m->dv); m->df = m->dv = NULL; }
+
+/* returns 0, or > 0 if the Broyden matrix is singular (errore 'broyden') */
+static int mix_potential_c(orc_mix_state *m, size_t ndim, zcplx *vout, zcplx *vin, double alphamix, double *dr2,
+                           double tr2, int iter, int n_iter, int *conv) {
+  const double w0 = 0.01;                                               /* :95 (w(:) = 1) */
+  for (size_t n = 0; n < ndim; ++n) vout[n] -= vin[n];                  /* :97-99 */
+  double nrm2 = 0.0;
+  for (size_t n = 0; n < ndim; ++n) nrm2 += creal(vout[n]) * creal(vout[n]) + cimag(vout[n]) * cimag(vout[n]);
+  *dr2 = (sqrt(nrm2) / (double)ndim) * (sqrt(nrm2) / (double)ndim);     /* :100-106 */
+  *conv = *dr2 < tr2;                                                   /* :108 */
+  if (iter == 1 && !m->df) {                                            /* :110-113 */
+    m->df = calloc(ndim * n_iter, sizeof(zcplx));
+    m->dv = calloc(ndim * n_iter, sizeof(zcplx));
+    m->ndim = ndim; m->n_iter = n_iter;
+  }
+  if (*conv) { mix_free(m); return 0; }                                 /* :114-118 */
+  zcplx *vinsave = malloc(sizeof(zcplx) * ndim);
+  const int iter_used = iter - 1 < n_iter ? iter - 1 : n_iter;          /* :124 */
+  const int ipos = iter - 1 - ((iter - 2) / n_iter) * n_iter;           /* :129 (1-based) */
+  if (iter > 1) {                                                       /* :131-140 */
+    zcplx *dfp = m->df + ndim * (ipos - 1), *dvp = m->dv + ndim * (ipos - 1);
+    double nn = 0.0;
+    for (size_t n = 0; n < ndim; ++n) {
+      dfp[n] = vout[n] - dfp[n];
+      dvp[n] = vin[n] - dvp[n];
+    }
+    for (size_t n = 0; n < ndim; ++n) nn += creal(dfp[n]) * creal(dfp[n]) + cimag(dfp[n]) * cimag(dfp[n]);
+    const double inv = 1.0 / sqrt(nn);
+    for (size_t n = 0; n < ndim; ++n) { dfp[n] *= inv; dvp[n] *= inv; }
+  }
+  memcpy(vinsave, vin, sizeof(zcplx) * ndim);                           /* :142 */
+  zcplx beta[MIX_MAXTER * MIX_MAXTER], work[MIX_MAXTER];
+  memset(beta, 0, sizeof beta);
+  for (int i = 0; i < iter_used; ++i) {                                 /* :144-149 */
+    for (int j = i + 1; j < iter_used; ++j) {
+      zcplx d = 0.0;                                                    /* ZDOTC(df_j, df_i) = sum conj(df_j) df_i */
+      const zcplx *dfi = m->df + ndim * i, *dfj = m->df + ndim * j;
+      for (size_t n = 0; n < ndim; ++n) d += conj(dfj[n]) * dfi[n];
+      beta[i + iter_used * j] = d;
+      beta[j + iter_used * i] = conj(d);                                /* Hermitian: ZHETRF('U') reads the upper part */
+    }
+    beta[i + iter_used * i] = w0 * w0 + 1.0;
+  }
+  if (iter_used > 0 && zinverse(iter_used, beta)) { free(vinsave); return 1; }   /* :153-157 ZHETRF + ZHETRI */
+  for (int i = 0; i < iter_used; ++i)                                   /* :159-163 re-symmetrise from the upper part */
+    for (int j = i + 1; j < iter_used; ++j) beta[j + iter_used * i] = conj(beta[i + iter_used * j]);
+  for (int i = 0; i < iter_used; ++i) {                                 /* :165-167 */
+    zcplx d = 0.0;
+    const zcplx *dfi = m->df + ndim * i;
+    for (size_t n = 0; n < ndim; ++n) d += conj(dfi[n]) * vout[n];
+    work[i] = d;
+  }
+  for (size_t n = 0; n < ndim; ++n) vin[n] += alphamix * vout[n];       /* :169-171 */
+  for (int i = 0; i < iter_used; ++i) {                                 /* :173-182 */
+    zcplx gamma = 0.0;
+    for (int j = 0; j < iter_used; ++j) gamma += beta[j + iter_used * i] * work[j];
+    const zcplx *dfi = m->df + ndim * i, *dvi = m->dv + ndim * i;
+    for (size_t n = 0; n < ndim; ++n) vin[n] -= gamma * (alphamix * dfi[n] + dvi[n]);
+  }
+  const int inext = iter - ((iter - 1) / n_iter) * n_iter;              /* :184 (1-based) */
+  memcpy(m->df + ndim * (inext - 1), vout, sizeof(zcplx) * ndim);       /* :185 */
+  memcpy(m->dv + ndim * (inext - 1), vinsave, sizeof(zcplx) * ndim);    /* :186 */
+  free(vinsave);
+  return 0;
+}
+
+/* [QE] orthogonalize, insulator (solve_linter.f90:337,409): dvpsi <- evq (evq^H dvpsi) - dvpsi = -P_c^+ dvpsi */
+static void orthogonalize(const orc_kpoint *kq, zcplx *dvpsi) {
+  const int npwx = kq->npwx, npwq = kq->npw, nocc = kq->nbnd_occ;
+  zcplx *ps = calloc((size_t)nocc * nocc, sizeof(zcplx));
+  for (int jb = 0; jb < nocc; ++jb)
+    for (int ib = 0; ib < nocc; ++ib) {
+      zcplx s = 0.0;
+      for (int ig = 0; ig < npwq; ++ig) s += conj(kq->evq[ig + (size_t)npwx * ib]) * dvpsi[ig + (size_t)npwx * jb];
+      ps[ib + (size_t)nocc * jb] = s;
+    }
+  for (int jb = 0; jb < nocc; ++jb)
+    for (int ig = 0; ig < npwq; ++ig) {
+      zcplx s = 0.0;
+      for (int ib = 0; ib < nocc; ++ib) s += kq->evq[ig + (size_t)npwx * ib] * ps[ib + (size_t)nocc * jb];
+      dvpsi[ig + (size_t)npwx * jb] = s - dvpsi[ig + (size_t)npwx * jb];
+    }
+  free(ps);
+}
+
+/* solve_linter.f90:55-624.  num_iter = 1: direct branch (drhoscf = -dV_H);  num_iter > 1: self-consistent branch
+ * (:376-460 per-frequency non-multishift solves with dV_scf psi added to the right-hand side, :564-582 complex Broyden
+ * mixing) -> drhoscf = dvscfin.  alpha_mix[iter-1], tr2_gw, nmix_gw are the control_gw globals of the reference.
+ * Returns the solver's ierr, or 10 if the self-consistency loop did not converge within num_iter (:588-591 errore). */
+int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_global, int num_iter, const double *alpha_mix,
+                          double tr2_gw, int nmix_gw, const zcplx *dvbarein, int nfreq, const zcplx *freq,
+                          zcplx *drhoscf, orc_stats *st, int nthreads, int *iter_done) {
   const orc_grid *g = &sys->grid;
   const size_t nnr = (size_t)g->nr1 * g->nr2 * g->nr3;
   const int zero_freq = cabs(freq[0]) < 1e-14;                          /* :217 */
+  const int direct_solver = num_iter == 1;                              /* :220 */
   const int num_omega = zero_freq ? 2 * nfreq - 1 : 2 * nfreq;          /* :238-242 */
   zcplx *omega = malloc(sizeof(zcplx) * num_omega);
   for (int i = 0; i < nfreq; ++i) omega[i] = freq[i];                   /* :247 */
@@ -307,150 +408,220 @@ int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcp
   long nop_all = 0;
   int nouter_max = 0;
   if (nthreads < 1) nthreads = 1;
+  orc_solver_cfg config = *cfg_global;                                  /* :223 local copy */
+  zcplx *dvscfin = calloc(nnr * nfreq, sizeof(zcplx));
+  zcplx *dvscfout = calloc(nnr * nfreq, sizeof(zcplx));
+  zcplx **dvpsi_bare = calloc(sys->nks, sizeof(zcplx *));               /* buffer iubar (:332) */
+  orc_mix_state mix = {NULL, NULL, 0, 0};
+  double dr2 = 0.0;
+  int convt = 0, iter;
+  const double e2 = 2.0, fpi = 4.0 * M_PI;
 
-  memset(drhoscf, 0, sizeof(zcplx) * nnr * nfreq);                      /* :283 */
+  for (iter = 1; iter <= num_iter; ++iter) {                            /* :279 */
+    const int first_iteration = iter == 1;
+    memset(drhoscf, 0, sizeof(zcplx) * nnr * nfreq);                    /* :283 */
+    for (int ik = 0; ik < sys->nks; ++ik) {                             /* :288 */
+      const orc_kpair *kp = &sys->kp[ik];
+      const orc_kpoint *kq = &kp->kq;
+      const int npwx = kq->npwx, npwq = kq->npw, nbnd = kp->nbnd, nocc = kq->nbnd_occ;
+      zcplx *dpsi = calloc((size_t)npwx * nbnd * num_omega, sizeof(zcplx));
 
-  for (int ik = 0; ik < sys->nks; ++ik) {                               /* :288 */
-    const orc_kpair *kp = &sys->kp[ik];
-    const orc_kpoint *kq = &kp->kq;
-    const int npwx = kq->npwx, npwq = kq->npw, nbnd = kp->nbnd, nocc = kq->nbnd_occ;
-    zcplx *dvpsi = calloc((size_t)npwx * nbnd, sizeof(zcplx));
-    zcplx *dpsi = calloc((size_t)npwx * nbnd * num_omega, sizeof(zcplx)); /* :256,341 */
-
-    /* dvqpsi_us.f90:99-130 : all nbnd bands, full 'Rho' FFTs */
+      if (first_iteration) {
+        zcplx *dvpsi = calloc((size_t)npwx * nbnd, sizeof(zcplx));
+        /* dvqpsi_us.f90:99-130 : all nbnd bands, full 'Rho' FFTs */
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic)
-    for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
-      if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
-      zcplx *aux2 = calloc(nnr, sizeof(zcplx));
-      for (int ig = 0; ig < kp->npw_k; ++ig) aux2[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
-      orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, +1);
-      for (size_t ir = 0; ir < nnr; ++ir) aux2[ir] *= dvbarein[ir];
-      orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, -1);
-      for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ibnd] = aux2[kq->nl_igk[ig] - 1];
-      free(aux2);
-    }
-    /* orthogonalize [QE], insulator: ps = evq^H dvpsi ; dvpsi <- evq ps - dvpsi  (= -P_c^+ dV psi) :337 */
-    {
-      zcplx *ps = calloc((size_t)nocc * nocc, sizeof(zcplx));
-      for (int jb = 0; jb < nocc; ++jb)
-        for (int ib = 0; ib < nocc; ++ib) {
-          zcplx s = 0.0;
-          for (int ig = 0; ig < npwq; ++ig) s += conj(kq->evq[ig + (size_t)npwx * ib]) * dvpsi[ig + (size_t)npwx * jb];
-          ps[ib + (size_t)nocc * jb] = s;
+        for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
+          if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
+          zcplx *aux2 = calloc(nnr, sizeof(zcplx));
+          for (int ig = 0; ig < kp->npw_k; ++ig) aux2[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
+          orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, +1);
+          for (size_t ir = 0; ir < nnr; ++ir) aux2[ir] *= dvbarein[ir];
+          orc_fft3d(aux2, g->nr1, g->nr2, g->nr3, -1);
+          for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ibnd] = aux2[kq->nl_igk[ig] - 1];
+          free(aux2);
         }
-      for (int jb = 0; jb < nocc; ++jb)
-        for (int ig = 0; ig < npwq; ++ig) {
-          zcplx s = 0.0;
-          for (int ib = 0; ib < nocc; ++ib) s += kq->evq[ig + (size_t)npwx * ib] * ps[ib + (size_t)nocc * jb];
-          dvpsi[ig + (size_t)npwx * jb] = s - dvpsi[ig + (size_t)npwx * jb];
+        if (!direct_solver) {                                           /* save_buffer(dvpsi, lrbar, iubar, nrec) :332 */
+          dvpsi_bare[ik] = malloc(sizeof(zcplx) * (size_t)npwx * nbnd);
+          memcpy(dvpsi_bare[ik], dvpsi, sizeof(zcplx) * (size_t)npwx * nbnd);
         }
-      free(ps);
-    }
-    /* band loop :367-374 */
+        orthogonalize(kq, dvpsi);                                       /* :337 */
+        config.threshold = direct_solver ? cfg_global->threshold : 1.0e-2;   /* :348-362 */
+        /* band loop :367-374 */
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop_all) reduction(max : nouter_max)
-    for (int ibnd = 0; ibnd < nocc; ++ibnd) {
-      if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
-      orc_pw_op op;
-      op.grid = g;
-      op.kp = kq;
-      op.alpha_pv = kq->alpha_pv;
-      op.work = malloc(sizeof(zcplx) * nnr);
-      op.becp = malloc(sizeof(zcplx) * 2 * (kq->nkb + kq->nbnd_occ + 1));
-      zcplx *sig = malloc(sizeof(zcplx) * num_omega);
-      for (int io = 0; io < num_omega; ++io) sig[io] = -(kp->et[ibnd] + omega[io]);    /* :369 */
-      zcplx *xx = calloc((size_t)npwq * num_omega, sizeof(zcplx));
-      orc_stats s1 = {0, 0, 0};
-      int ierr = orc_select_solver(cfg, orc_pw_apply, &op, npwq, dvpsi + (size_t)npwx * ibnd, num_omega, sig, xx, &s1);
-      if (ierr != 0) {
-#pragma omp critical(orc_ierr)
-        ierr_all = ierr;                                                /* :370 errore */
-      }
-      /* dpsi *= wg/wk (=1: fully occupied insulator bands)  :373 */
-      for (int io = 0; io < num_omega; ++io)
-        memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx + (size_t)npwq * io, sizeof(zcplx) * npwq);
-      nop_all += s1.n_op;
-      if (s1.n_outer > nouter_max) nouter_max = s1.n_outer;
-      free(xx); free(sig); free(op.work); free(op.becp);
-    }
-    /* average +-omega :464-480 */
-    {
-      const size_t blk = (size_t)npwx * nbnd;
-      const int first = zero_freq ? 1 : 0;
-      const size_t cnt = blk * (nfreq - first);
-      zcplx *a = dpsi + blk * first, *b = dpsi + blk * nfreq;
-      for (size_t i = 0; i < cnt; ++i) a[i] = 0.5 * a[i];
-      for (size_t i = 0; i < cnt; ++i) a[i] += 0.5 * b[i];
-    }
-    /* incdrhoscf [QE] :489-497 */
-    {
-      const double wgt = 2.0 * kp->wk / sys->omega_cell;
-      unsigned char *mk = malloc(2 * ((size_t)g->nr1 * g->nr2 + g->nr1));
-      unsigned char *mkx = mk + (size_t)g->nr1 * g->nr2;
-      unsigned char *mq = mkx + g->nr1, *mqx = mq + (size_t)g->nr1 * g->nr2;
-      sphere_masks(g->nr1, g->nr2, kp->npw_k, kp->nl_igk_k, mk, mkx);
-      sphere_masks(g->nr1, g->nr2, npwq, kq->nl_igk, mq, mqx);
-      zcplx *psir = malloc(sizeof(zcplx) * nnr * nocc);
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
-      for (int ibnd = 0; ibnd < nocc; ++ibnd) {
-        if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
-        zcplx *p = psir + nnr * ibnd;
-        memset(p, 0, sizeof(zcplx) * nnr);
-        for (int ig = 0; ig < kp->npw_k; ++ig) p[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
-        fft3d_pruned(p, g->nr1, g->nr2, g->nr3, +1, mk, mkx);
-      }
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
-      for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
-        zcplx *dpsic = malloc(sizeof(zcplx) * nnr);
-        zcplx *drho = drhoscf + nnr * ifreq;
         for (int ibnd = 0; ibnd < nocc; ++ibnd) {
           if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
-          const zcplx *dp = dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * ifreq);
-          const zcplx *p = psir + nnr * ibnd;
-          memset(dpsic, 0, sizeof(zcplx) * nnr);
-          for (int ig = 0; ig < npwq; ++ig) dpsic[kq->nl_igk[ig] - 1] = dp[ig];
-          fft3d_pruned(dpsic, g->nr1, g->nr2, g->nr3, +1, mq, mqx);
-          for (size_t ir = 0; ir < nnr; ++ir) drho[ir] += wgt * conj(p[ir]) * dpsic[ir];
+          orc_pw_op op;
+          op.grid = g;
+          op.kp = kq;
+          op.alpha_pv = kq->alpha_pv;
+          op.work = malloc(sizeof(zcplx) * nnr);
+          op.becp = malloc(sizeof(zcplx) * 2 * (kq->nkb + kq->nbnd_occ + 1));
+          zcplx *sig = malloc(sizeof(zcplx) * num_omega);
+          for (int io = 0; io < num_omega; ++io) sig[io] = -(kp->et[ibnd] + omega[io]);    /* :369 */
+          zcplx *xx = calloc((size_t)npwq * num_omega, sizeof(zcplx));
+          orc_stats s1 = {0, 0, 0};
+          int ierr = orc_select_solver(&config, orc_pw_apply, &op, npwq, dvpsi + (size_t)npwx * ibnd, num_omega, sig, xx, &s1);
+          if (ierr != 0) {
+#pragma omp critical(orc_ierr)
+            ierr_all = ierr;                                            /* :370 errore */
+          }
+          /* dpsi *= wg/wk (=1: fully occupied insulator bands)  :373 */
+          for (int io = 0; io < num_omega; ++io)
+            memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx + (size_t)npwq * io, sizeof(zcplx) * npwq);
+          nop_all += s1.n_op;
+          if (s1.n_outer > nouter_max) nouter_max = s1.n_outer;
+          free(xx); free(sig); free(op.work); free(op.becp);
         }
-        free(dpsic);
+        free(dvpsi);
+      } else {                                                          /* general case iter > 1 :376-458 */
+        config.threshold = fmin(1.0e-1 * sqrt(dr2), 1.0e-2);            /* :417 */
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop_all) reduction(max : nouter_max)
+        for (int ifreq = 0; ifreq < nfreq; ++ifreq) {                   /* :384 */
+          zcplx *dvpsi = malloc(sizeof(zcplx) * (size_t)npwx * nbnd);
+          memcpy(dvpsi, dvpsi_bare[ik], sizeof(zcplx) * (size_t)npwx * nbnd);   /* get_buffer :389 */
+          zcplx *aux = malloc(sizeof(zcplx) * nnr);
+          for (int ibnd = 0; ibnd < nocc; ++ibnd) {                     /* :395-399 cft_wave, apply_dpot, cft_wave */
+            memset(aux, 0, sizeof(zcplx) * nnr);
+            for (int ig = 0; ig < kp->npw_k; ++ig) aux[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
+            orc_fft3d(aux, g->nr1, g->nr2, g->nr3, +1);
+            for (size_t ir = 0; ir < nnr; ++ir) aux[ir] *= dvscfin[ir + nnr * ifreq];
+            orc_fft3d(aux, g->nr1, g->nr2, g->nr3, -1);
+            for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ibnd] += aux[kq->nl_igk[ig] - 1];   /* cft_wave(-1) adds */
+          }
+          free(aux);
+          orthogonalize(kq, dvpsi);                                     /* :409 */
+          const int iomega = zero_freq ? ifreq + nfreq - 1 : ifreq + nfreq;   /* :426-430 */
+          orc_pw_op op;
+          op.grid = g;
+          op.kp = kq;
+          op.alpha_pv = kq->alpha_pv;
+          op.work = malloc(sizeof(zcplx) * nnr);
+          op.becp = malloc(sizeof(zcplx) * 2 * (kq->nkb + kq->nbnd_occ + 1));
+          for (int ibnd = 0; ibnd < nocc; ++ibnd) {                     /* :434-456 */
+            for (int pm = 0; pm < 2; ++pm) {
+              if (pm == 1 && zero_freq && ifreq == 0) continue;         /* :446 */
+              const int io = pm == 0 ? ifreq : iomega;
+              zcplx sig = -(kp->et[ibnd] + omega[io]);
+              zcplx *xx = calloc((size_t)npwq, sizeof(zcplx));
+              orc_stats s1 = {0, 0, 0};
+              int ierr = orc_select_solver(&config, orc_pw_apply, &op, npwq, dvpsi + (size_t)npwx * ibnd, 1, &sig, xx, &s1);
+              if (ierr != 0) {
+#pragma omp critical(orc_ierr)
+                ierr_all = ierr;
+              }
+              memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx, sizeof(zcplx) * npwq);
+              nop_all += s1.n_op;
+              if (s1.n_outer > nouter_max) nouter_max = s1.n_outer;
+              free(xx);
+            }
+          }
+          free(op.work); free(op.becp);
+          free(dvpsi);
+        }
       }
-      free(psir);
-      free(mk);
+      /* average +-omega :464-480 */
+      {
+        const size_t blk = (size_t)npwx * nbnd;
+        const int first = zero_freq ? 1 : 0;
+        const size_t cnt = blk * (nfreq - first);
+        zcplx *a = dpsi + blk * first, *b = dpsi + blk * nfreq;
+        for (size_t i = 0; i < cnt; ++i) a[i] = 0.5 * a[i];
+        for (size_t i = 0; i < cnt; ++i) a[i] += 0.5 * b[i];
+      }
+      /* incdrhoscf [QE] :489-497 */
+      {
+        const double wgt = 2.0 * kp->wk / sys->omega_cell;
+        unsigned char *mk = malloc(2 * ((size_t)g->nr1 * g->nr2 + g->nr1));
+        unsigned char *mkx = mk + (size_t)g->nr1 * g->nr2;
+        unsigned char *mq = mkx + g->nr1, *mqx = mq + (size_t)g->nr1 * g->nr2;
+        sphere_masks(g->nr1, g->nr2, kp->npw_k, kp->nl_igk_k, mk, mkx);
+        sphere_masks(g->nr1, g->nr2, npwq, kq->nl_igk, mq, mqx);
+        zcplx *psir = malloc(sizeof(zcplx) * nnr * nocc);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
+        for (int ibnd = 0; ibnd < nocc; ++ibnd) {
+          if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
+          zcplx *p = psir + nnr * ibnd;
+          memset(p, 0, sizeof(zcplx) * nnr);
+          for (int ig = 0; ig < kp->npw_k; ++ig) p[kp->nl_igk_k[ig] - 1] = kp->evc[ig + (size_t)npwx * ibnd];
+          fft3d_pruned(p, g->nr1, g->nr2, g->nr3, +1, mk, mkx);
+        }
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic)
+        for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
+          zcplx *dpsic = malloc(sizeof(zcplx) * nnr);
+          zcplx *drho = drhoscf + nnr * ifreq;
+          for (int ibnd = 0; ibnd < nocc; ++ibnd) {
+            if (ibnd < g_band_lo || ibnd >= g_band_hi) continue;
+            const zcplx *dp = dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * ifreq);
+            const zcplx *p = psir + nnr * ibnd;
+            memset(dpsic, 0, sizeof(zcplx) * nnr);
+            for (int ig = 0; ig < npwq; ++ig) dpsic[kq->nl_igk[ig] - 1] = dp[ig];
+            fft3d_pruned(dpsic, g->nr1, g->nr2, g->nr3, +1, mq, mqx);
+            for (size_t ir = 0; ir < nnr; ++ir) drho[ir] += wgt * conj(p[ir]) * dpsic[ir];
+          }
+          free(dpsic);
+        }
+        free(psir);
+        free(mk);
+      }
+      free(dpsi);
     }
-    free(dvpsi);
-    free(dpsi);
-  }
-  /* mp_sum over pools :521 -- single pool here */
+    /* mp_sum over pools :521 -- single pool here */
 
-  /* meandvb :532 ; zero-mean fix :544-550 ; dv_of_drho (lrpa) :556 ; drhoscf = -dvscfout :598 */
-  double s2 = 0.0;
-  for (size_t ir = 0; ir < nnr; ++ir) s2 += creal(dvbarein[ir]) * creal(dvbarein[ir]) + cimag(dvbarein[ir]) * cimag(dvbarein[ir]);
-  const double meandvb = sqrt(s2) / (double)nnr;
-  const double e2 = 2.0, fpi = 4.0 * M_PI;
-  zcplx *dvhart = malloc(sizeof(zcplx) * nnr);
-  for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
-    zcplx *dv = drhoscf + nnr * ifreq;
-    if (meandvb < 1e-10) {
+    /* meandvb :532 ; zero-mean fix :544-550 ; dv_of_drho (lrpa) :556 */
+    double s2 = 0.0;
+    for (size_t ir = 0; ir < nnr; ++ir) s2 += creal(dvbarein[ir]) * creal(dvbarein[ir]) + cimag(dvbarein[ir]) * cimag(dvbarein[ir]);
+    const double meandvb = sqrt(s2) / (double)nnr;
+    for (int ifreq = 0; ifreq < nfreq; ++ifreq) {
+      zcplx *dv = dvscfout + nnr * ifreq;
+      memcpy(dv, drhoscf + nnr * ifreq, sizeof(zcplx) * nnr);           /* :536 */
+      if (meandvb < 1e-10) {
+        orc_fft3d(dv, g->nr1, g->nr2, g->nr3, -1);
+        dv[sys->nl[0] - 1] = 0.0;
+        orc_fft3d(dv, g->nr1, g->nr2, g->nr3, +1);
+      }
       orc_fft3d(dv, g->nr1, g->nr2, g->nr3, -1);
-      dv[sys->nl[0] - 1] = 0.0;
-      orc_fft3d(dv, g->nr1, g->nr2, g->nr3, +1);
+      zcplx *dvhart = calloc(nnr, sizeof(zcplx));
+      for (int ig = 0; ig < sys->ngm; ++ig) {
+        double q0 = sys->g[3 * ig] + sys->xq[0], q1 = sys->g[3 * ig + 1] + sys->xq[1], q2 = sys->g[3 * ig + 2] + sys->xq[2];
+        double qg2 = q0 * q0 + q1 * q1 + q2 * q2;
+        if (qg2 > 1e-8) dvhart[sys->nl[ig] - 1] = e2 * fpi * dv[sys->nl[ig] - 1] / (sys->tpiba2 * qg2);
+      }
+      orc_fft3d(dvhart, g->nr1, g->nr2, g->nr3, +1);
+      memcpy(dv, dvhart, sizeof(zcplx) * nnr);
+      free(dvhart);
     }
-    orc_fft3d(dv, g->nr1, g->nr2, g->nr3, -1);
-    memset(dvhart, 0, sizeof(zcplx) * nnr);
-    for (int ig = 0; ig < sys->ngm; ++ig) {
-      double q0 = sys->g[3 * ig] + sys->xq[0], q1 = sys->g[3 * ig + 1] + sys->xq[1], q2 = sys->g[3 * ig + 2] + sys->xq[2];
-      double qg2 = q0 * q0 + q1 * q1 + q2 * q2;
-      if (qg2 > 1e-8) dvhart[sys->nl[ig] - 1] = e2 * fpi * dv[sys->nl[ig] - 1] / (sys->tpiba2 * qg2);
+    if (direct_solver) break;                                           /* :562 */
+    if (ierr_all) break;                                                /* errore aborts the reference */
+    /* mix with the old potential :566-568 */
+    if (mix_potential_c(&mix, nnr * nfreq, dvscfout, dvscfin, alpha_mix[iter - 1], &dr2, tr2_gw * nfreq, iter, nmix_gw, &convt)) {
+      ierr_all = 11;
+      break;
     }
-    orc_fft3d(dvhart, g->nr1, g->nr2, g->nr3, +1);
-    for (size_t ir = 0; ir < nnr; ++ir) dv[ir] = -dvhart[ir];
+    if (convt) break;                                                   /* :582 */
   }
-  free(dvhart);
+  if (iter_done) *iter_done = iter > num_iter ? num_iter : iter;
+  if (!direct_solver && !ierr_all && !convt) ierr_all = 10;             /* :588-591 */
+  if (direct_solver) {
+    for (size_t i = 0; i < nnr * nfreq; ++i) drhoscf[i] = -dvscfout[i]; /* :598 */
+  } else {
+    memcpy(drhoscf, dvscfin, sizeof(zcplx) * nnr * nfreq);              /* :610 */
+  }
+  mix_free(&mix);
+  for (int ik = 0; ik < sys->nks; ++ik) free(dvpsi_bare[ik]);
+  free(dvpsi_bare);
+  free(dvscfin);
+  free(dvscfout);
   free(omega);
   if (st) {
     st->n_op += nop_all;
     if (nouter_max > st->n_outer) st->n_outer = nouter_max;
   }
   return ierr_all;
+}
+
+int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
+                     const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads) {
+  return orc_solve_linter_iter(sys, cfg, 1, NULL, 0.0, 0, dvbarein, nfreq, freq, drhoscf, st, nthreads, NULL);
 }
 
 /* ================================================================ coulomb.f90:29-176 */

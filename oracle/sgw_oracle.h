@@ -138,6 +138,12 @@ typedef struct {
 /* solve_linter.f90:55-624, direct branch (num_iter = 1).  drhoscf: nnr x nfreq */
 int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
                      const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads);
+/* solve_linter.f90:55-624 with num_iter > 1: the self-consistent branch (:376-460) + mix_potential_c (mix_pot_c.f90:25).
+ * alpha_mix: num_iter entries (control_gw alpha_mix), tr2_gw, nmix_gw as in the reference; drhoscf = dvscfin on exit.
+ * Returns 0, a solver ierr, 10 (not converged within num_iter, solve_linter.f90:588-591) or 11 (Broyden matrix singular). */
+int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg, int num_iter, const double *alpha_mix,
+                          double tr2_gw, int nmix_gw, const zcplx *dvbarein, int nfreq, const zcplx *freq,
+                          zcplx *drhoscf, orc_stats *st, int nthreads, int *iter_done);
 /* bench-only: restrict the band loops of orc_solve_linter to lo <= ibnd < hi (bounded CPU-baseline samples) */
 void orc_set_band_window(int lo, int hi);
 /* coulomb.f90:29-176.  scrcoul: ngc x nfs x ntask.  ig_unique (1-based G indices), igstart 1-based. */

@@ -80,13 +80,13 @@ __global__ void k_average(int n, int nocc, int nfreq, int nshift, int zero_freq,
 
 // [QE] dv_of_drho with lrpa: dv(G) = e2 fpi drho(G) / (tpiba2 |q+G|^2); out = -dv (solve_linter.f90:598)
 __global__ void k_hartree(int npw, int nvec, const double *__restrict__ fac /* column order */, cplx *__restrict__ drho,
-                          int zero_pos) {
+                          int zero_pos, double sign = -1.0) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = blockIdx.y;
   if (e >= npw) return;
   cplx d = drho[(long)v * npw + e];
   if (e == zero_pos) d = cmake(0.0, 0.0);       // zero-mean fix (:544-550)
-  drho[(long)v * npw + e] = cscale(-fac[e], d);
+  drho[(long)v * npw + e] = cscale(sign * fac[e], d);
 }
 
 // coulomb.f90:143-157: scrcoul(igp, iw, indx) = -dV_H(G_igp) + delta(igp, ig)
@@ -494,6 +494,317 @@ static int perturbation_chunk(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nshif
   return c;
 }
 
+// ================================================================ self-consistent branch of solve_linter
+// (solve_linter.f90:376-460, :564-582) and mix_potential_c (mix_pot_c.f90:25-198) -- SURVEY section 8 row f1.
+// Small BLAS-1 style kernels for the mixing (ndim = nnr * nfreq, a handful of calls per iteration):
+__global__ void k_vsub(long n, cplx *__restrict__ a, const cplx *__restrict__ b) {            // a -= b
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = csub(a[i], b[i]);
+}
+__global__ void k_vrdiff(long n, cplx *__restrict__ d, const cplx *__restrict__ a) {          // d = a - d
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = csub(a[i], d[i]);
+}
+__global__ void k_vscale2(long n, double sc, cplx *__restrict__ a, cplx *__restrict__ b) {    // a *= sc ; b *= sc
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = cscale(sc, a[i]); b[i] = cscale(sc, b[i]); }
+}
+__global__ void k_vaxpy_r(long n, double al, const cplx *__restrict__ x, cplx *__restrict__ y) {   // y += al x
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = cmake(y[i].x + al * x[i].x, y[i].y + al * x[i].y);
+}
+// vin -= gamma * (alphamix * df + dv)      (mix_pot_c.f90:179-181, w(i) = 1)
+__global__ void k_vbroyden(long n, cplx gamma, double al, const cplx *__restrict__ df, const cplx *__restrict__ dv,
+                           cplx *__restrict__ vin) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cplx t = cmake(al * df[i].x + dv[i].x, al * df[i].y + dv[i].y);
+  vin[i] = csub(vin[i], cmul(gamma, t));
+}
+// ZDOTC partials: part[block] = sum conj(x) y over the block's slice (summed on the host in block order: deterministic)
+__global__ void __launch_bounds__(256) k_zdotc_part(long n, const cplx *__restrict__ x, const cplx *__restrict__ y,
+                                                     cplx *__restrict__ part) {
+  __shared__ cplx sm[256];
+  cplx acc = cmake(0.0, 0.0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    acc = cfma(cconj(x[i]), y[i], acc);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] = cadd(sm[threadIdx.x], sm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
+}
+// right-hand sides of the per-frequency solves: b2[(ib * num_omega + io)] = rhs[(ifreq(io) * nocc + ib)]   (:434-456)
+__global__ void k_iter_rhs(int n, int nocc, int nfreq, int num_omega, int zero_freq, const cplx *__restrict__ rhs,
+                           cplx *__restrict__ b2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int ib = blockIdx.y, io = blockIdx.z;
+  const int ifreq = io < nfreq ? io : (zero_freq ? io - nfreq + 1 : io - nfreq);
+  b2[((long)ib * num_omega + io) * n + e] = rhs[((long)ifreq * nocc + ib) * n + e];
+}
+
+static int zdotc_dev(sgw_ctx *ctx, long n, const cplx *x, const cplx *y, cplx *out) {
+  const int nb = (int)std::min<long>(512, (n + 255) / 256);
+  cplx *part = nullptr;
+  SGW_CHECK(ws(ctx, "it_part", (size_t)512, &part));
+  k_zdotc_part<<<nb, 256, 0, ctx->stream>>>(n, x, y, part);
+  SGW_LAUNCH_CHECK();
+  cplx h[512];
+  SGW_CUDA(cudaMemcpyAsync(h, part, sizeof(cplx) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  cplx s = cmake(0.0, 0.0);
+  for (int i = 0; i < nb; ++i) s = cadd(s, h[i]);
+  *out = s;
+  return SGW_OK;
+}
+
+// inverse of a small complex matrix (<= 8 x 8), Gauss-Jordan with partial pivoting; column-major, ld = n
+static bool small_inverse(int n, cplx *a) {
+  cplx inv[64];
+  for (int i = 0; i < n * n; ++i) inv[i] = cmake(0.0, 0.0);
+  for (int i = 0; i < n; ++i) inv[i + n * i] = cmake(1.0, 0.0);
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    double best = std::fabs(a[c + n * c].x) + std::fabs(a[c + n * c].y);
+    for (int r = c + 1; r < n; ++r) {
+      const double v = std::fabs(a[r + n * c].x) + std::fabs(a[r + n * c].y);
+      if (v > best) { best = v; p = r; }
+    }
+    if (best == 0.0) return false;
+    if (p != c)
+      for (int k = 0; k < n; ++k) { std::swap(a[c + n * k], a[p + n * k]); std::swap(inv[c + n * k], inv[p + n * k]); }
+    const cplx d = cdiv(cmake(1.0, 0.0), a[c + n * c]);
+    for (int k = 0; k < n; ++k) { a[c + n * k] = cmul(d, a[c + n * k]); inv[c + n * k] = cmul(d, inv[c + n * k]); }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const cplx f = a[r + n * c];
+      for (int k = 0; k < n; ++k) {
+        a[r + n * k] = csub(a[r + n * k], cmul(f, a[c + n * k]));
+        inv[r + n * k] = csub(inv[r + n * k], cmul(f, inv[c + n * k]));
+      }
+    }
+  }
+  for (int i = 0; i < n * n; ++i) a[i] = inv[i];
+  return true;
+}
+
+struct MixState {          // df, dv of mix_pot_c.f90:83 (device), allocated at iter == 1
+  cplx *df = nullptr, *dv = nullptr, *vinsave = nullptr;
+};
+
+// mix_potential_c(ndim, vout, vin, alphamix, dr2, tr2, iter, n_iter, conv) on device vectors
+static int mix_potential_c_dev(sgw_ctx *ctx, MixState &m, long ndim, cplx *vout, cplx *vin, double alphamix, double *dr2,
+                               double tr2, int iter, int n_iter, bool *conv) {
+  cudaStream_t st = ctx->stream;
+  const unsigned gb = (unsigned)((ndim + 255) / 256);
+  k_vsub<<<gb, 256, 0, st>>>(ndim, vout, vin);                                              // :97-99
+  SGW_LAUNCH_CHECK();
+  cplx d;
+  SGW_CHECK(zdotc_dev(ctx, ndim, vout, vout, &d));
+  *dr2 = (std::sqrt(d.x) / (double)ndim) * (std::sqrt(d.x) / (double)ndim);                 // :100-106
+  *conv = *dr2 < tr2;                                                                      // :108
+  if (*conv) return SGW_OK;                                                                // :114-118
+  const int iter_used = std::min(iter - 1, n_iter);                                        // :124
+  const int ipos = iter - 1 - ((iter - 2) / n_iter) * n_iter;                              // :129
+  if (iter > 1) {                                                                          // :131-140
+    cplx *dfp = m.df + (size_t)ndim * (ipos - 1), *dvp = m.dv + (size_t)ndim * (ipos - 1);
+    k_vrdiff<<<gb, 256, 0, st>>>(ndim, dfp, vout);
+    SGW_LAUNCH_CHECK();
+    k_vrdiff<<<gb, 256, 0, st>>>(ndim, dvp, vin);
+    SGW_LAUNCH_CHECK();
+    SGW_CHECK(zdotc_dev(ctx, ndim, dfp, dfp, &d));
+    k_vscale2<<<gb, 256, 0, st>>>(ndim, 1.0 / std::sqrt(d.x), dfp, dvp);
+    SGW_LAUNCH_CHECK();
+  }
+  SGW_CUDA(cudaMemcpyAsync(m.vinsave, vin, sizeof(cplx) * ndim, cudaMemcpyDeviceToDevice, st));   // :142
+  cplx beta[64], work[8];
+  const double w0 = 0.01;
+  for (int i = 0; i < iter_used; ++i) {                                                    // :144-149
+    for (int j = i + 1; j < iter_used; ++j) {
+      SGW_CHECK(zdotc_dev(ctx, ndim, m.df + (size_t)ndim * j, m.df + (size_t)ndim * i, &d));
+      beta[i + iter_used * j] = d;
+      beta[j + iter_used * i] = cconj(d);
+    }
+    beta[i + iter_used * i] = cmake(w0 * w0 + 1.0, 0.0);
+  }
+  if (iter_used > 0 && !small_inverse(iter_used, beta)) {                                  // :153-157
+    ctx->err = "broyden: factorization of the mixing matrix failed";
+    return SGW_E_ARG;
+  }
+  for (int i = 0; i < iter_used; ++i)                                                      // :159-163
+    for (int j = i + 1; j < iter_used; ++j) beta[j + iter_used * i] = cconj(beta[i + iter_used * j]);
+  for (int i = 0; i < iter_used; ++i) SGW_CHECK(zdotc_dev(ctx, ndim, m.df + (size_t)ndim * i, vout, &work[i]));   // :165-167
+  k_vaxpy_r<<<gb, 256, 0, st>>>(ndim, alphamix, vout, vin);                                // :169-171
+  SGW_LAUNCH_CHECK();
+  for (int i = 0; i < iter_used; ++i) {                                                    // :173-182
+    cplx gamma = cmake(0.0, 0.0);
+    for (int j = 0; j < iter_used; ++j) gamma = cfma(beta[j + iter_used * i], work[j], gamma);
+    k_vbroyden<<<gb, 256, 0, st>>>(ndim, gamma, alphamix, m.df + (size_t)ndim * i, m.dv + (size_t)ndim * i, vin);
+    SGW_LAUNCH_CHECK();
+  }
+  const int inext = iter - ((iter - 1) / n_iter) * n_iter;                                 // :184
+  SGW_CUDA(cudaMemcpyAsync(m.df + (size_t)ndim * (inext - 1), vout, sizeof(cplx) * ndim, cudaMemcpyDeviceToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(m.dv + (size_t)ndim * (inext - 1), m.vinsave, sizeof(cplx) * ndim, cudaMemcpyDeviceToDevice, st));
+  return SGW_OK;
+}
+
+// One perturbation, num_iter > 1.  d_field: dvbare(r) in permuted order; on success d_dvscfin (nfreq x nnr, permuted
+// order) holds the self-consistent dV_scf(r, omega).  ierr: solver code, or 10 if not converged within num_iter.
+static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global, int num_iter, const cplx *d_field,
+                                  double meandvb, const FreqList &fl, const Sphere &rho, cplx *d_dvscfin, int *ierr_out,
+                                  int *iter_done) {
+  const int nfreq = fl.nfreq, nshift = fl.num_omega;
+  const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  const long ndim = nnr * nfreq;
+  cudaStream_t st = ctx->stream;
+  SGW_ARG(ctx->mix_niter >= num_iter && ctx->mix_nmix >= 1 && ctx->mix_nmix <= 8,
+          "sgw_set_mixing must provide alpha_mix for every iteration and 1 <= nmix_gw <= 8");
+  sgw_solver_cfg config = *cfg_global;                                                     // :223
+  cplx *dvout = nullptr, *Trho = nullptr, *d_drhoG = nullptr, *Tr = nullptr;
+  MixState mix;
+  SGW_CHECK(ws(ctx, "it_dvout", (size_t)ndim, &dvout));
+  SGW_CHECK(ws(ctx, "it_df", (size_t)ndim * ctx->mix_nmix, &mix.df));
+  SGW_CHECK(ws(ctx, "it_dv", (size_t)ndim * ctx->mix_nmix, &mix.dv));
+  SGW_CHECK(ws(ctx, "it_vinsave", (size_t)ndim, &mix.vinsave));
+  SGW_CHECK(ws(ctx, "co_Trho", (size_t)nfreq * ctx->nr3 * rho.ncol, &Trho));
+  SGW_CHECK(ws(ctx, "co_drhoG", (size_t)nfreq * rho.npw, &d_drhoG));
+  SGW_CHECK(ws(ctx, "sl_Tr", (size_t)nfreq * ctx->nr3 * rho.ncol, &Tr));
+  SGW_CUDA(cudaMemsetAsync(d_dvscfin, 0, sizeof(cplx) * ndim, st));                        // :343
+  SGW_CUDA(cudaMemsetAsync(mix.df, 0, sizeof(cplx) * ndim * ctx->mix_nmix, st));
+  SGW_CUDA(cudaMemsetAsync(mix.dv, 0, sizeof(cplx) * ndim * ctx->mix_nmix, st));
+  double *d_fac = nullptr;
+  SGW_CHECK(hartree_factor(ctx, rho, rho.npw, "co_fac", &d_fac));
+  int zero_pos = -1;
+  if (meandvb < 1e-10)
+    for (int pos = 0; pos < rho.npw; ++pos) if (rho.perm[pos] == 0) zero_pos = pos;         // :544-550
+  // storage for dvbare psi of every k-point (buffer iubar, :332)
+  size_t bare_tot = 0;
+  std::vector<size_t> bare_off(ctx->pairs.size());
+  for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {
+    const KPair &kp = ctx->pairs[ik];
+    if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size() || !ctx->slots[kp.slot].set) {
+      ctx->err = "k-point pair not set (sgw_set_kpair / sgw_set_kpoint)";
+      return SGW_E_STATE;
+    }
+    bare_off[ik] = bare_tot;
+    bare_tot += (size_t)ctx->slots[kp.slot].nbnd * ctx->slots[kp.slot].npwx;
+  }
+  cplx *bare = nullptr;
+  SGW_CHECK(ws(ctx, "it_bare", bare_tot, &bare));
+  double dr2 = 0.0;
+  bool convt = false;
+  int ierr_any = 0, iter;
+  ZEpilogue epi0;
+  epi0.mode = 0; epi0.g2kin = nullptr; epi0.psi = nullptr; epi0.sigma = nullptr; epi0.sigma_stride = 0; epi0.keep_out = 0;
+  for (iter = 1; iter <= num_iter; ++iter) {                                               // :279
+    const bool first = iter == 1;
+    for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {                                    // :288
+      const KPair &kp = ctx->pairs[ik];
+      const KSlot &ks = ctx->slots[kp.slot];
+      const int n = ks.npwx, nocc = ks.nbnd;
+      if (nocc > kp.nbnd) { ctx->err = "evc holds fewer bands than nbnd_occ"; return SGW_E_ARG; }
+      cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *rhs = nullptr, *ps = nullptr, *d_sig = nullptr, *d_x = nullptr,
+           *b2 = nullptr, *davg = nullptr, *Td = nullptr;
+      int *d_ierr = nullptr;
+      SGW_CHECK(ws(ctx, "co_Tk", (size_t)nocc * ctx->nr3 * kp.sph_k.ncol, &Tk));
+      SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));
+      SGW_CHECK(fft_zpass_g2r(ctx, kp.sph_k, nocc, kp.d_evc, n, Tk, nullptr));
+      SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &kp.sph_k, nullptr, nocc, Tk, nullptr, nullptr, 1, psir, nullptr));
+      const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
+      cplx *bare_k = bare + bare_off[ik];
+      const int nrhs = first ? nocc : nocc * nshift;
+      SGW_CHECK(ws(ctx, "sv_sig", (size_t)nocc * nshift, &d_sig));
+      SGW_CHECK(ws(ctx, "sv_x", (size_t)n * nshift * nocc, &d_x));
+      SGW_CHECK(ws(ctx, "sv_ierr", (size_t)nocc * nshift, &d_ierr));
+      {
+        std::vector<cplx> sig((size_t)nshift * nocc);                                      // sigma = -(et + omega) :369
+        for (int ib = 0; ib < nocc; ++ib)
+          for (int is = 0; is < nshift; ++is) sig[(size_t)ib * nshift + is] = cmake(-(kp.et[ib] + fl.omega[is].x), -fl.omega[is].y);
+        SGW_CUDA(cudaMemcpyAsync(d_sig, sig.data(), sizeof(cplx) * sig.size(), cudaMemcpyHostToDevice, st));
+        SGW_CUDA(cudaStreamSynchronize(st));
+      }
+      SolveBatch sb;
+      sb.slot = kp.slot; sb.alpha_pv = ks.alpha_pv; sb.n = n; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
+      if (first) {
+        // dvqpsi_us (:331) -> buffer iubar (:332) -> orthogonalize (:337) -> multishift solves at thresh 1e-2 (:362)
+        SGW_CHECK(ws(ctx, "co_Tq", (size_t)nocc * ctx->nr3 * ks.sph.ncol, &Tq));
+        SGW_CHECK(fft_plane(ctx, PLANE_FROM_R, nullptr, &ks.sph, nocc, nullptr, Tq, d_field, nocc, psir, nullptr, nocc));
+        SGW_CUDA(cudaMemsetAsync(bare_k, 0, sizeof(cplx) * (size_t)nocc * n, st));
+        SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nocc, Tq, bare_k, n, epi0, nullptr));
+        SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nocc * n, &rhs));
+        SGW_CUDA(cudaMemcpyAsync(rhs, bare_k, sizeof(cplx) * (size_t)nocc * n, cudaMemcpyDeviceToDevice, st));
+        SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nocc, &ps));
+        SGW_CHECK(gemm_ch_n(ctx, nocc, nocc, ks.npw, evq, n, rhs, n, ps, nocc));
+        SGW_CHECK(gemm_n_n(ctx, n, nocc, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), rhs, n));
+        config.threshold = 1.0e-2;
+        sb.nrhs = nocc; sb.nshift = nshift; sb.d_b = rhs;
+        SGW_CHECK(select_solver_batched(ctx, sb, &config));
+      } else {
+        // dvpsi(ifreq) = dvbare psi + fwfft(dvscfin(r, ifreq) psi(r))  (:389-399), orthogonalize (:409), then one
+        // single-shift solve per (band, +-omega) (:434-456) -- the bands x frequencies batch
+        const int nv = nocc * nfreq;
+        SGW_CHECK(ws(ctx, "co_Tq", (size_t)nv * ctx->nr3 * ks.sph.ncol, &Tq));
+        SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nv * n, &rhs));
+        for (int f = 0; f < nfreq; ++f)
+          SGW_CUDA(cudaMemcpyAsync(rhs + (size_t)f * nocc * n, bare_k, sizeof(cplx) * (size_t)nocc * n, cudaMemcpyDeviceToDevice, st));
+        SGW_CHECK(fft_plane(ctx, PLANE_FROM_R, nullptr, &ks.sph, nv, nullptr, Tq, d_dvscfin, nocc, psir, nullptr, nocc));
+        ZEpilogue epi2 = epi0;
+        epi2.mode = 2;                                                                     // cft_wave(-1) ADDS to dvpsi
+        SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nv, Tq, rhs, n, epi2, nullptr));
+        SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nv, &ps));
+        SGW_CHECK(gemm_ch_n(ctx, nocc, nv, ks.npw, evq, n, rhs, n, ps, nocc));
+        SGW_CHECK(gemm_n_n(ctx, n, nv, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), rhs, n));
+        SGW_CHECK(ws(ctx, "it_b2", (size_t)nocc * nshift * n, &b2));
+        {
+          dim3 gr((n + 255) / 256, nocc, nshift);
+          k_iter_rhs<<<gr, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, rhs, b2);
+          SGW_LAUNCH_CHECK();
+        }
+        config.threshold = std::min(1.0e-1 * std::sqrt(dr2), 1.0e-2);                      // :417
+        sb.nrhs = nrhs; sb.nshift = 1; sb.d_b = b2;
+        SGW_CHECK(select_solver_batched(ctx, sb, &config));
+      }
+      {
+        std::vector<int> ie(nrhs);
+        SGW_CUDA(cudaMemcpyAsync(ie.data(), d_ierr, sizeof(int) * nrhs, cudaMemcpyDeviceToHost, st));
+        SGW_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < nrhs; ++r) if (ie[r] != 0) ierr_any = ie[r];                     // :370
+      }
+      // +-omega average (:464-480) and incdrhoscf (:489-497); x is laid out [(ib * nshift + is) * n] in both branches
+      const double wgt = 2.0 * kp.wk / ctx->omega_cell;
+      SGW_CHECK(ws(ctx, "co_davg", (size_t)nfreq * nocc * n, &davg));
+      SGW_CHECK(ws(ctx, "co_Td", (size_t)nfreq * nocc * ctx->nr3 * ks.sph.ncol, &Td));
+      dim3 ga((n + 255) / 256, nocc, nfreq);
+      k_average<<<ga, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, 0, d_x, davg);
+      SGW_LAUNCH_CHECK();
+      SGW_CHECK(fft_zpass_g2r(ctx, ks.sph, nfreq * nocc, davg, n, Td, nullptr));
+      SGW_CHECK(fft_plane_rho(ctx, ks.sph, rho, nfreq, nocc, Td, psir, wgt, Trho, ik > 0));
+    }
+    if (ierr_any) break;                                                                   // errore aborts the reference
+    // dvscfout = dv_of_drho(drho) (:534-558), real space, permuted order
+    SGW_CUDA(cudaMemsetAsync(d_drhoG, 0, sizeof(cplx) * (size_t)nfreq * rho.npw, st));
+    SGW_CHECK(fft_zpass_r2g(ctx, rho, nfreq, Trho, d_drhoG, rho.npw, epi0, nullptr));
+    {
+      dim3 gr((rho.npw + 255) / 256, nfreq);
+      k_hartree<<<gr, 256, 0, st>>>(rho.npw, nfreq, d_fac, d_drhoG, zero_pos, +1.0);
+      SGW_LAUNCH_CHECK();
+    }
+    SGW_CHECK(fft_zpass_g2r(ctx, rho, nfreq, d_drhoG, rho.npw, Tr, nullptr));
+    SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &rho, nullptr, nfreq, Tr, nullptr, nullptr, 1, dvout, nullptr));
+    // mix with the old potential (:566-568)
+    SGW_CHECK(mix_potential_c_dev(ctx, mix, ndim, dvout, d_dvscfin, ctx->mix_alpha[iter - 1], &dr2, ctx->mix_tr2 * nfreq, iter,
+                                  ctx->mix_nmix, &convt));
+    if (convt) break;                                                                      // :582
+  }
+  *iter_done = std::min(iter, num_iter);
+  if (!ierr_any && !convt) ierr_any = 10;                                                  // :588-591
+  *ierr_out = ierr_any;
+  return SGW_OK;
+}
+
 static int check_pipeline_state(sgw_ctx *ctx) {
   if (!ctx->grid_set || !ctx->vloc_set) { ctx->err = "grid / local potential not set"; return SGW_E_STATE; }
   if (!ctx->system_set) { ctx->err = "sgw_set_system must be called first"; return SGW_E_STATE; }
@@ -572,13 +883,25 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   return SGW_OK;
 }
 
+int sgw_set_mixing(sgw_ctx *ctx, int niter_gw, const double *alpha_mix, double tr2_gw, int nmix_gw) {
+  if (!ctx) return SGW_E_ARG;
+  SGW_ARG(niter_gw >= 1 && alpha_mix && tr2_gw > 0.0 && nmix_gw >= 1 && nmix_gw <= 8, "bad mixing parameters (1 <= nmix_gw <= 8)");
+  ctx->mix_niter = niter_gw;
+  ctx->mix_alpha.assign(alpha_mix, alpha_mix + niter_gw);
+  ctx->mix_tr2 = tr2_gw;
+  ctx->mix_nmix = nmix_gw;
+  return SGW_OK;
+}
+
+int sgw_get_scf_iterations(const sgw_ctx *ctx) { return ctx ? ctx->last_scf_iter : SGW_E_ARG; }
+
 int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, const sgw_cplx *dvbarein, int nfreq,
                      const sgw_cplx *freq, sgw_cplx *drhoscf, int32_t *ierr_out) {
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
   SGW_ARG(cfg && dvbarein && freq && drhoscf && ierr_out && nfreq > 0, "null argument");
   SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");
-  if (num_iter != 1) { ctx->err = "only the direct branch (num_iter = 1) is implemented"; return SGW_E_UNSUPPORTED; }
+  SGW_ARG(num_iter >= 1, "num_iter must be >= 1");
   SGW_CHECK(check_pipeline_state(ctx));
   begin_call(ctx);
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
@@ -599,6 +922,22 @@ int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, cons
   double s2 = 0.0;                                                                         // solve_linter.f90:532
   for (long i = 0; i < nnr; ++i) s2 += dvbarein[i].re * dvbarein[i].re + dvbarein[i].im * dvbarein[i].im;
   const double meandvb = std::sqrt(s2) / (double)nnr;
+  if (num_iter > 1) {
+    // self-consistent branch: drhoscf = dvscfin (solve_linter.f90:610)
+    cplx *d_dvin = nullptr;
+    SGW_CHECK(ws(ctx, "it_dvin", (size_t)nnr * nfreq, &d_dvin));
+    int ierr_it = 0, iters = 0;
+    SGW_CHECK(solve_linter_iter_core(ctx, cfg, num_iter, d_field, meandvb, fl, *rho, d_dvin, &ierr_it, &iters));
+    ctx->last_scf_iter = iters;
+    dim3 gr((unsigned)((nnr + 255) / 256), nfreq);
+    k_perm2nat<<<gr, 256, 0, st>>>(g, nfreq, d_dvin, d_nat, 1.0);
+    SGW_LAUNCH_CHECK();
+    SGW_CUDA(cudaMemcpyAsync(drhoscf, d_nat, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+    *ierr_out = ierr_it;
+    end_call(ctx);
+    return SGW_OK;
+  }
   SGW_CHECK(ws(ctx, "co_drhoG", (size_t)nfreq * rho->npw, &d_drhoG));
   int ierr_any = 0;
   SGW_CHECK(drho_block(ctx, cfg, 1, d_field, fl, *rho, d_drhoG, &ierr_any));

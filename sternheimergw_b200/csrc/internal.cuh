@@ -139,6 +139,10 @@ struct sgw_ctx {
   int rho_grid_ngc = -1;
   sgw::Sphere rho_sph_c;
   std::vector<sgw::Sphere> pair_k_c, pair_kq_c;
+  // control_gw globals of the self-consistent branch (sgw_set_mixing): niter_gw, alpha_mix(:), tr2_gw, nmix_gw
+  int mix_niter = 0, mix_nmix = 0, last_scf_iter = 0;
+  std::vector<double> mix_alpha;
+  double mix_tr2 = 0.0;
   cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // solver look-ahead (bicgstab.cu)
   int *h_flags = nullptr;                        // pinned host flags read back by the solvers
   int gemm_cta_per_sm = 0;                       // resident k_zgemm CTAs per SM (0 = attributes not set yet)

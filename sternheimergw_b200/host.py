@@ -186,6 +186,14 @@ class Context:
         return xx, ierr
 
     # ---- phys/coul -------------------------------------------------------------------------------------
+    def set_mixing(self, niter_gw, alpha_mix, tr2_gw, nmix_gw):
+        """control_gw globals of the self-consistent W branch (num_iter_coul, alpha_mix, tr2_gw, num_mix_coul)."""
+        am = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha_mix, dtype=np.float64), (niter_gw,)))
+        self._chk(self._L.sgw_set_mixing(self._h, int(niter_gw), _p(am), float(tr2_gw), int(nmix_gw)), "set_mixing")
+
+    def scf_iterations(self):
+        return int(self._L.sgw_get_scf_iterations(self._h))
+
     def solve_linter(self, config: select_solver_type, num_iter, dvbarein, freq):
         dvbarein, freq = _c16(np.ravel(dvbarein, order="F")), _c16(freq)
         drho = np.zeros((dvbarein.size, freq.size), dtype=np.complex128, order="F")
@@ -193,6 +201,8 @@ class Context:
         cfg = config.c()
         self._chk(self._L.sgw_solve_linter(self._h, C.byref(cfg), num_iter, _p(dvbarein), freq.size, _p(freq), _p(drho),
                                            C.byref(ierr)), "solve_linter")
+        if ierr.value == 10:
+            raise SgwError("Iterative solver did not converge within given number of iterations")   # solve_linter.f90:588-591
         if ierr.value != 0:
             raise SgwError(f"solver did not converge (ierr={ierr.value})")          # solve_linter.f90:370
         return drho

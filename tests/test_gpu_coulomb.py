@@ -74,6 +74,39 @@ def test_coulomb_reduced_rho_grid_matches_oracle_and_full_box(ctx, monkeypatch):
     assert _rel(scr, ref) < 1e-8, _rel(scr, ref)
 
 
+@pytest.mark.parametrize("name,fiu,nmix", [("tiny", [0.0, 1.2j], 4), ("tiny", [0.5j, 2.0j], 2)])
+def test_solve_linter_selfconsistent_matches_oracle(ctx, name, fiu, nmix):
+    """self-consistent W branch (solve_linter.f90:376-460, :564-582) + complex Broyden mixing
+    (mix_pot_c.f90:25): same number of self-consistency iterations as the oracle and dV_scf(r, w) equal to 1e-7
+    (both sides stop at the same tr2; the per-iteration solver threshold min(0.1 sqrt(dr2), 1e-2) follows dr2)."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import SgwError, select_solver_type
+    syn = synth.preset(name)
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    fiu = np.asarray(fiu, dtype=complex)
+    nnr = int(np.prod(syn.nr))
+    ig = 4
+    dv = np.zeros(nnr, dtype=complex)
+    dv[syn.nl[ig - 1] - 1] = 1.0
+    dvr = (np.fft.ifftn(dv.reshape(syn.nr, order="F")) * nnr).reshape(-1, order="F")
+    niter, alpha, tr2 = 40, 0.7, 1e-22
+    ref, ierr, st = ps.solve_linter_iter(niter, alpha, tr2, nmix, dvr, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-4), nthreads=8)
+    assert ierr == 0
+    ctx.set_mixing(niter, alpha, tr2, nmix)
+    out = ctx.solve_linter(select_solver_type(priority=(1, 3), threshold=1e-4), niter, dvr, fiu)
+    assert abs(ctx.scf_iterations() - st["iter"]) <= 1, (ctx.scf_iterations(), st["iter"])
+    assert _rel(out, ref) < 1e-7, _rel(out, ref)
+    # not enough iterations -> the reference's errore (solve_linter.f90:588-591)
+    ctx.set_mixing(3, alpha, tr2, nmix)
+    with pytest.raises(SgwError, match="Iterative solver did not converge"):
+        ctx.solve_linter(select_solver_type(priority=(1, 3), threshold=1e-4), 3, dvr, fiu)
+    # without sgw_set_mixing for enough iterations the call is refused, not silently defaulted
+    with pytest.raises(SgwError):
+        ctx.solve_linter(select_solver_type(priority=(1, 3), threshold=1e-4), 12, dvr, fiu)
+
+
 def test_coulomb_production_threshold_and_sos(ctx):
     """Production threshold (1e-4): eps within 10*thr of the converged one; converged one equals sum-over-states."""
     import sos

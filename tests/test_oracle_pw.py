@@ -116,3 +116,32 @@ def test_green_function(tiny_sys):
             for ig in range(ngc):
                 want = Gd[map_[ig] - 1, map_[igp] - 1] if 0 < map_[ig] < kq.npw else 0.0
                 assert abs(green[ig, igp, ifr] - want) < 1e-10
+
+
+def test_solve_linter_selfconsistent_vs_dense_inverse(tiny_sys):
+    """the self-consistent branch (solve_linter.f90:376-460,:564-582 + mix_potential_c) must converge to
+    dV_scf = (eps^-1 - 1) dV_bare, where eps is the FULL direct dielectric matrix over the density sphere -- an
+    independent formula (dense inverse of the direct branch's output) for the same quantity."""
+    syn = tiny_sys
+    ps = oracle.PwSystem(syn)
+    fiu = np.array([0.0, 1.2j])
+    ngm = syn.ngm
+    igu = np.arange(1, ngm + 1, dtype=np.int32)
+    E, ierr, _ = ps.coulomb(1, ngm, ngm, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=8)
+    assert ierr == 0
+    nnr = int(np.prod(syn.nr))
+    for ig in (3, 10):
+        dv = np.zeros(nnr, dtype=complex)
+        dv[syn.nl[ig - 1] - 1] = 1.0
+        dvr = (np.fft.ifftn(dv.reshape(syn.nr, order="F")) * nnr).reshape(-1, order="F")      # invfft (coulomb.f90:134)
+        out, ierr, st = ps.solve_linter_iter(40, 0.7, 1e-22, 4, dvr, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-4),
+                                             nthreads=8)
+        assert ierr == 0 and 3 < st["iter"] < 40
+        for iw in range(fiu.size):
+            W = (np.fft.fftn(out[:, iw].reshape(syn.nr, order="F")) / nnr).reshape(-1, order="F")[syn.nl - 1]
+            ref = np.linalg.inv(E[:, iw, :])[:, ig - 1].copy()
+            ref[ig - 1] -= 1.0
+            assert np.abs(W - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
+    # too few iterations: the reference aborts (solve_linter.f90:588-591) -> code 10
+    _, ierr, st = ps.solve_linter_iter(3, 0.7, 1e-22, 4, dvr, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-4), nthreads=8)
+    assert ierr == 10 and st["iter"] == 3
