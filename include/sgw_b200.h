@@ -111,7 +111,11 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
 /* control_gw globals of the self-consistent branch (main/src/gw_input.yml: num_iter_coul -> niter_gw, alpha_mix,
  * tr2_gw, num_mix_coul -> nmix_gw <= 8 = maxter of mix_pot_c.f90:76): alpha_mix has niter_gw entries. */
 int sgw_set_mixing(sgw_ctx *ctx, int niter_gw, const double *alpha_mix, double tr2_gw, int nmix_gw);
-/* iterations the last self-consistent sgw_solve_linter took ("iter #" line, solve_linter.f90:604) */
+/* control_gw solve_direct (input solve_coul = 'direct' | 'iter', gwq_readin.f90): 1 (default) -> sgw_coulomb returns
+ * eps = delta - v chi0 columns (coulomb.f90:153-157); 0 -> every perturbation runs the self-consistent solve_linter with
+ * num_iter = niter_gw (needs sgw_set_mixing, niter_gw > 1, coulomb.f90:106-110) and scrcoul holds dV_scf = (eps^-1 - 1) columns */
+int sgw_set_solve_direct(sgw_ctx *ctx, int solve_direct);
+/* iterations the last self-consistent sgw_solve_linter / sgw_coulomb took ("iter #" line, solve_linter.f90:604) */
 int sgw_get_scf_iterations(const sgw_ctx *ctx);
 /* solve_linter (phys/coul/src/solve_linter.f90:55): dvbarein(nnr) real-space perturbation, freq(nfreq).
  *  num_iter = 1: direct branch, drhoscf(nnr, nfreq) = -dV_H (:598);

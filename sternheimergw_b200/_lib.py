@@ -14,7 +14,7 @@ SYMBOLS = [
     "sgw_create", "sgw_destroy", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_device_synchronize",
     "sgw_get_profile", "sgw_profile_class_name",
     "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
-    "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_get_scf_iterations", "sgw_solve_linter",
+    "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
     "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
     "sgw_parallel_task", "sgw_bench_linear_op",
 ]
@@ -65,6 +65,7 @@ def load():
         L.sgw_set_nksq.argtypes = [c_void_p, c_int]
         L.sgw_set_kpair.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_double]
         L.sgw_set_mixing.argtypes = [c_void_p, c_int, c_void_p, c_double, c_int]
+        L.sgw_set_solve_direct.argtypes = [c_void_p, c_int]
         L.sgw_get_scf_iterations.argtypes = [c_void_p]
         L.sgw_solve_linter.argtypes = [c_void_p, C.POINTER(SolverCfg), c_int, c_void_p, c_int, c_void_p, c_void_p,
                                        c_void_p]

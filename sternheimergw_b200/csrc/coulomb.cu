@@ -92,13 +92,15 @@ __global__ void k_hartree(int npw, int nvec, const double *__restrict__ fac /* c
 // coulomb.f90:143-157: scrcoul(igp, iw, indx) = -dV_H(G_igp) + delta(igp, ig)
 __global__ void k_scr_extract(int ngc, int nfs, int np, const int *__restrict__ perm, const double *__restrict__ fac,
                               const int *__restrict__ ig0 /* 0-based perturbation G per task */,
-                              const cplx *__restrict__ drho /* [p][iw][pos] */, cplx *__restrict__ scr /* ngc x nfs x np */) {
+                              const cplx *__restrict__ drho /* [p][iw][pos] */, cplx *__restrict__ scr /* ngc x nfs x np */,
+                              int direct = 1) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const int iw = blockIdx.y, p = blockIdx.z;
   if (pos >= ngc) return;
   const int igp = perm[pos];
-  cplx v = cscale(-fac[pos], drho[((long)p * nfs + iw) * ngc + pos]);
-  if (igp == ig0[p]) v.x += 1.0;
+  // direct: eps = delta - v drho (:149-157); self-consistent: the input already is dV_scf(G) and is copied (:149-151)
+  cplx v = direct ? cscale(-fac[pos], drho[((long)p * nfs + iw) * ngc + pos]) : drho[((long)p * nfs + iw) * ngc + pos];
+  if (direct && igp == ig0[p]) v.x += 1.0;
   scr[(long)igp + (long)ngc * (iw + (long)nfs * p)] = v;
 }
 
@@ -893,6 +895,12 @@ int sgw_set_mixing(sgw_ctx *ctx, int niter_gw, const double *alpha_mix, double t
   return SGW_OK;
 }
 
+int sgw_set_solve_direct(sgw_ctx *ctx, int solve_direct) {
+  if (!ctx) return SGW_E_ARG;
+  ctx->solve_direct = solve_direct != 0;
+  return SGW_OK;
+}
+
 int sgw_get_scf_iterations(const sgw_ctx *ctx) { return ctx ? ctx->last_scf_iter : SGW_E_ARG; }
 
 int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, const sgw_cplx *dvbarein, int nfreq,
@@ -1000,6 +1008,64 @@ int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, i
   double *d_fac = nullptr;
   SGW_CHECK(hartree_factor(ctx, *rho, ngc, "co_fac", &d_fac));
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  if (!ctx->solve_direct) {
+    // coulomb.f90:104-110 with solve_direct = .FALSE.: every perturbation runs the self-consistent solve_linter with
+    // num_iter = niter_gw and scrcoul(igp, iw, indx) = fwfft(dV_scf)(G_igp) -- no delta on the diagonal (:153)
+    SGW_ARG(ctx->mix_niter > 1, "self-consistent coulomb needs sgw_set_mixing with niter_gw > 1 (coulomb.f90:108)");
+    Sphere *rho_full = nullptr;
+    SGW_CHECK(get_rho_sphere(ctx, ctx->ngm, &rho_full));
+    cudaStream_t st = ctx->stream;
+    GridDev g = grid_dev(ctx);
+    int *d_mill = nullptr, *d_ig0 = nullptr;
+    cplx *d_field = nullptr, *d_dvin = nullptr, *Tg = nullptr, *d_dvG = nullptr, *d_scr = nullptr;
+    SGW_CHECK(ws(ctx, "co_mill", (size_t)3, &d_mill));
+    SGW_CHECK(ws(ctx, "co_ig0", (size_t)1, &d_ig0));
+    SGW_CHECK(ws(ctx, "co_field", (size_t)nnr, &d_field));
+    SGW_CHECK(ws(ctx, "it_dvin", (size_t)nnr * nfs, &d_dvin));
+    SGW_CHECK(ws(ctx, "it_Tg", (size_t)nfs * ctx->nr3 * rho->ncol, &Tg));
+    SGW_CHECK(ws(ctx, "it_dvG", (size_t)nfs * ngc, &d_dvG));
+    SGW_CHECK(ws(ctx, "co_scr", (size_t)nfs * ngc, &d_scr));
+    ctx->rho_last_coarse = false;
+    int ierr_any = 0, iters_max = 0;
+    std::vector<cplx> hscr((size_t)ngc * nfs);
+    ZEpilogue epi;
+    epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
+    for (int t = 0; t < nt && !ierr_any; ++t) {
+      const long idx = (long)ctx->nl[task_ig[t] - 1] - 1;
+      const int mill[3] = {(int)(idx % ctx->nr1), (int)((idx / ctx->nr1) % ctx->nr2), (int)(idx / ((long)ctx->nr1 * ctx->nr2))};
+      const int ig0 = task_ig[t] - 1;
+      SGW_CUDA(cudaMemcpyAsync(d_mill, mill, sizeof(mill), cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaMemcpyAsync(d_ig0, &ig0, sizeof(int), cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+      {
+        dim3 gr((unsigned)((nnr + 255) / 256), 1);
+        k_delta_field<<<gr, 256, 0, st>>>(g, 1, d_mill, d_field);                          // coulomb.f90:129-134
+        SGW_LAUNCH_CHECK();
+      }
+      int ierr_it = 0, iters = 0;
+      // |dvbare(r)| = 1 everywhere for a delta perturbation: meandvb = 1/sqrt(nnr) (solve_linter.f90:532)
+      SGW_CHECK(solve_linter_iter_core(ctx, cfg, ctx->mix_niter, d_field, 1.0 / std::sqrt((double)nnr), fl, *rho_full, d_dvin,
+                                       &ierr_it, &iters));
+      iters_max = std::max(iters_max, iters);
+      if (ierr_it) { ierr_any = ierr_it; break; }
+      // fwfft('Rho') of dV_scf and the first ngc components (:146-151)
+      SGW_CHECK(fft_plane(ctx, PLANE_FROM_R, nullptr, rho, nfs, nullptr, Tg, nullptr, 1, d_dvin, nullptr));
+      SGW_CUDA(cudaMemsetAsync(d_dvG, 0, sizeof(cplx) * (size_t)nfs * ngc, st));
+      SGW_CHECK(fft_zpass_r2g(ctx, *rho, nfs, Tg, d_dvG, ngc, epi, nullptr));
+      {
+        dim3 gr((ngc + 127) / 128, nfs, 1);
+        k_scr_extract<<<gr, 128, 0, st>>>(ngc, nfs, 1, rho->d_perm, d_fac, d_ig0, d_dvG, d_scr, 0);
+        SGW_LAUNCH_CHECK();
+      }
+      SGW_CUDA(cudaMemcpyAsync(hscr.data(), d_scr, sizeof(cplx) * (size_t)ngc * nfs, cudaMemcpyDeviceToHost, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+      memcpy(scrcoul + (size_t)ngc * nfs * task_indx[t], hscr.data(), sizeof(cplx) * (size_t)ngc * nfs);
+    }
+    ctx->last_scf_iter = iters_max;
+    *ierr_out = ierr_any;
+    end_call(ctx);
+    return SGW_OK;
+  }
   const int chunk = perturbation_chunk(ctx, cfg, fl.num_omega, nfs, *rho, nt);
   bool coarse = false;
   SGW_CHECK(rho_grid_prepare(ctx, ngc, *rho, &coarse));

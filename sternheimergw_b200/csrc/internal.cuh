@@ -141,6 +141,7 @@ struct sgw_ctx {
   std::vector<sgw::Sphere> pair_k_c, pair_kq_c;
   // control_gw globals of the self-consistent branch (sgw_set_mixing): niter_gw, alpha_mix(:), tr2_gw, nmix_gw
   int mix_niter = 0, mix_nmix = 0, last_scf_iter = 0;
+  bool solve_direct = true;                      // control_gw solve_direct (coulomb.f90:104)
   std::vector<double> mix_alpha;
   double mix_tr2 = 0.0;
   cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // solver look-ahead (bicgstab.cu)

@@ -191,6 +191,10 @@ class Context:
         am = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha_mix, dtype=np.float64), (niter_gw,)))
         self._chk(self._L.sgw_set_mixing(self._h, int(niter_gw), _p(am), float(tr2_gw), int(nmix_gw)), "set_mixing")
 
+    def set_solve_direct(self, solve_direct: bool):
+        """control_gw solve_direct: False makes `coulomb` run the self-consistent branch (needs set_mixing)."""
+        self._chk(self._L.sgw_set_solve_direct(self._h, 1 if solve_direct else 0), "set_solve_direct")
+
     def scf_iterations(self):
         return int(self._L.sgw_get_scf_iterations(self._h))
 
@@ -215,6 +219,8 @@ class Context:
         cfg = config.c()
         self._chk(self._L.sgw_coulomb(self._h, C.byref(cfg), igstart, num_g_corr, num_task, _p(ig_unique), fiu.size,
                                       _p(fiu), _p(scr), C.byref(ierr)), "coulomb")
+        if check and ierr.value == 10:
+            raise SgwError("Iterative solver did not converge within given number of iterations")
         if check and ierr.value != 0:
             raise SgwError(f"solver did not converge (ierr={ierr.value})")
         return scr

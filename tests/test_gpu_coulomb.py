@@ -107,6 +107,32 @@ def test_solve_linter_selfconsistent_matches_oracle(ctx, name, fiu, nmix):
         ctx.solve_linter(select_solver_type(priority=(1, 3), threshold=1e-4), 12, dvr, fiu)
 
 
+def test_coulomb_selfconsistent_equals_inverse_of_direct(ctx):
+    """solve_coul = 'iter' (coulomb.f90:104-110,:149-151): the columns returned by the self-consistent branch are
+    (eps^-1 - 1) of the FULL direct dielectric matrix -- both computed on the GPU, related by a dense numpy inverse."""
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset("tiny")
+    ctx.install_system(syn)
+    fiu = np.array([0.0, 1.2j])
+    ngm = syn.ngm
+    igu = np.arange(1, ngm + 1, dtype=np.int32)
+    eps = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-12), 1, ngm, ngm, igu, fiu)
+    ctx.set_mixing(40, 0.7, 1e-22, 4)
+    ctx.set_solve_direct(False)
+    try:
+        w = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-4), 2, ngm, 3, igu, fiu)
+    finally:
+        ctx.set_solve_direct(True)
+    assert 3 < ctx.scf_iterations() < 40
+    for iw in range(fiu.size):
+        inv = np.linalg.inv(eps[:, iw, :])
+        for t in range(3):
+            ref = inv[:, 1 + t].copy()
+            ref[1 + t] -= 1.0
+            assert np.abs(w[:, iw, t] - ref).max() < 1e-8, (iw, t, np.abs(w[:, iw, t] - ref).max())
+
+
 def test_coulomb_production_threshold_and_sos(ctx):
     """Production threshold (1e-4): eps within 10*thr of the converged one; converged one equals sum-over-states."""
     import sos
