@@ -54,7 +54,6 @@ def workload_config(syn, P, world):
             "fft_grid": list(syn.nr), "npw": int(kq.npw), "nbnd_occ": int(syn.nbnd_occ), "nkb": int(kq.vkb.shape[1]),
             "nfreq": NFS, "nshift": 2 * NFS - 1, "perturbations_per_step_per_gpu": P, "threshold": THRESHOLD,
             "bicg_lmax": 4, "solver": "multishift BiCGStab(l), priority (1,3)",
-            "rho_grid": "Delta-rho accumulated on the alias-free reduced box (sgw_get_rho_grid)",
             "parallelism": f"perturbation blocks over {world} GPU(s) (do_stern.f90:199), gather of eps columns per step",
             "l2": "inputs larger than L2 (solver state of one step is > 10 GB)"}
 
@@ -399,7 +398,9 @@ def main():
             "e2e": {"value": total_solves / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(syn, fiu, igu),
                     "d2h_bytes_per_step": int(ngc * NFS * P * 16 + 4), "ms_per_step": e2e_ms / args.steps,
                     "note": "host (pageable, caller-owned) arrays -> sgw_set_* + sgw_coulomb -> scrcoul on host, wall clock"},
-            "roofline": roofline, "kernels": kernels, "hpsi_fft": hpsi_fft, "fp64_zgemm_peak_tflops": f64_peak}
+            "roofline": roofline, "kernels": kernels, "hpsi_fft": hpsi_fft, "fp64_zgemm_peak_tflops": f64_peak,
+            "rho_grid": {"reduced": bool(ctx.rho_grid()[0]), "dims": list(ctx.rho_grid()[1]),
+                         "note": "Delta-rho accumulated on the alias-free reduced box (sgw_get_rho_grid, DESIGN.md section 4)"}}
     if world == 1 and not args.no_cpu_baseline:
         del ctx
         cb = cpu_sample(syn, fiu, ngc, igu, steps=1, warmup=0)
