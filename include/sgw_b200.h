@@ -149,6 +149,58 @@ int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ng
                        int ngp, const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green,
                        int32_t *ierr_out);
 
+/* ---- analytic continuation of W (algo/analytic/src/analytic.f90) ----
+ * freqbins_type (algo/grid/src/freqbins.f90:42-105): the members the continuation and the G W convolution read. */
+typedef struct {
+  int32_t imag_sigma;       /* convolution along the imaginary (1) or real (0) axis */
+  int32_t freq_symm_coul;   /* 0 no_symmetry, 1 even_symmetry, 2 square_symmetry (freqbins.f90:31-35) */
+  int32_t num_solver;       /* SIZE(freq%solver): FREQUENCIES card */
+  const sgw_cplx *solver;
+  int32_t num_coul;         /* integration mesh of the convolution and its weights */
+  const sgw_cplx *coul;
+  const double *weight;
+  int32_t num_sigma;        /* frequencies of the self-energy */
+  const sgw_cplx *sigma;
+} sgw_freqbins;
+#define SGW_GODBY_NEEDS 1   /* analytic.f90:39-60 model_coul values */
+#define SGW_PADE_APPROX 2
+#define SGW_PADE_ROBUST 3   /* not built: SGW_E_UNSUPPORTED */
+#define SGW_AAA_APPROX 4    /* not built: SGW_E_UNSUPPORTED */
+#define SGW_AAA_POLE 5      /* not built: SGW_E_UNSUPPORTED */
+/* freq%num_freq() = size of the symmetrised mesh (freqbins_symm, freqbins.f90:243-305); < 0 on error
+ * (more than one frequency below 1e-14 with even symmetry, as the reference's errore). */
+int sgw_freqbins_num_freq(const sgw_freqbins *freq);
+/* coulpade (phys/coul/src/coulpade.f90:36): scrcoul_g(ig, :, :) *= factor(ig); factor = truncate(q + G_ig) is host code */
+int sgw_coulpade(sgw_ctx *ctx, int ngc, int nfreq, const double *factor /* ngc */, sgw_cplx *scrcoul_g);
+/* analytic_coeff (analytic.f90:50): scrcoul_g(ngc, ngc, num_freq()) in place -> coefficients of the model
+ * (Godby-Needs godby_needs.f90:34, Pade pade.f90 pade_coeff incl. the mirrored frequencies of freqbins_symm) */
+int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_freqbins *freq, int ngc, sgw_cplx *scrcoul_g);
+/* analytic_eval (analytic.f90:211) at nout frequencies at once: scrcoul(ig, igp, iout) =
+ * model(coeff(gmapsym(ig), gmapsym(igp), :), freq%symmetrize(freq_out(iout))) -- the G-space block the reference
+ * stores in the corner of scrcoul(nnr_c, nnr_c'). */
+int sgw_analytic_eval(sgw_ctx *ctx, int model_coul, const sgw_freqbins *freq, int ngc, const int32_t *gmapsym /* ngc, 1-based */,
+                      const sgw_cplx *scrcoul_coeff /* ngc x ngc x num_freq() */, int nout, const sgw_cplx *freq_out,
+                      sgw_cplx *scrcoul /* ngc x ngc x nout */);
+
+/* ---- Sigma_c = G W (phys/corr/src/sigma.f90, data/fft/src/fft6.f90) ----
+ * grid%corr_fft (algo/grid/src/sigma_grid.f90): box of the correlation cutoff and nl of its ngm_c G vectors (1-based).
+ * One image: corr_par_fft = corr_fft (the reference's image distribution of G'/r' is replaced by sharding the
+ * (k, q) configurations over GPUs). */
+int sgw_set_corr_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int ngm_c, const int32_t *nl_c);
+/* invfft6 / fwfft6 (fft6.f90:231 / :84) in place on f(nnr_c, nnr_c): invfft6 reads f(:ngm_c, :ngm_c) and fills all of
+ * f; fwfft6 reads all of f and writes f(:ngm_c, :ngm_c) (the rest is left unchanged; the reference leaves scratch). */
+int sgw_invfft6(sgw_ctx *ctx, double omega, sgw_cplx *f);
+int sgw_fwfft6(sgw_ctx *ctx, double omega, sgw_cplx *f);
+/* sigma_correlation (sigma.f90:528): Green's function at freq%green(mu) for the operator in `slot` (green_prepare data:
+ * map), its 6-D transform, and for every (omega_sigma, omega_green) pair W(omega_sigma - omega_green) by analytic_eval,
+ * the real-space product (sigma_prod, :417) and the transform back; sigma(ngm_c, ngm_c, num_sigma) += result.
+ * The sum over omega_green is taken in real space before ONE forward transform per omega_sigma (linear, same result).
+ * ierr_out: solver code of the Green's function (0/1/2/3). */
+int sgw_sigma_correlation(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg_green, double omega_cell, double mu,
+                          sgw_cplx alpha, int model_coul, const sgw_freqbins *freq, int ngm_c, const int32_t *map /* ngm_c */,
+                          const int32_t *gmapsym /* ngm_c, 1-based */, const sgw_cplx *coulomb /* ngm_c x ngm_c x num_freq() */,
+                          sgw_cplx *sigma /* ngm_c x ngm_c x num_sigma */, int32_t *ierr_out);
+
 /* ---- data/parallel/src/parallel.f90:80 parallel_task: contiguous blocks, remainder to the LAST ranks.
  * rank 0-based; first/last 1-based; num_task[nproc]. ---- */
 int sgw_parallel_task(int nproc, int rank, int num_task_total, int32_t *first_task, int32_t *last_task,

@@ -1,0 +1,358 @@
+"""oracle/sigma.py -- TEST INFRASTRUCTURE (checker only; never imported by the product path).
+
+numpy restatement, in the reference's execution order, of SURVEY.md section 8 rows f2 and f3:
+
+  f3  analytic continuation of W   algo/analytic/src/analytic.f90:50 (analytic_coeff), :211 (analytic_eval),
+                                   algo/analytic/src/pade.f90 (pade_coeff, pade_eval),
+                                   algo/analytic/src/godby_needs.f90 (godby_needs_coeffs, godby_needs_model),
+                                   algo/grid/src/freqbins.f90 (freqbins_type, freqbins_symm), gauleg_grid.f90,
+                                   phys/coul/src/coulpade.f90
+  f2  Sigma_c = G W                phys/corr/src/sigma.f90:417 (sigma_prod), :528 (sigma_correlation),
+                                   data/fft/src/fft6.f90:84 (fwfft6), :231 (invfft6)
+
+The reference cannot be compiled here (Fortran 2003 + QE 6.3).  Its only unit test in this area (algo/analytic/test/pade.pf)
+covers `pade_robust`, which is not restated (no BASELINE config uses it), so for these routines **parity is unpinned** by
+reference tests; tests/test_oracle_sigma.py anchors them by independent properties instead: the Pade approximant
+interpolates its input, the Godby-Needs model reproduces its two input frequencies, fft6 equals numpy's 6-D fftn, and
+sigma_prod equals the explicit G-space convolution.
+
+numpy divides complex numbers with Smith's algorithm, which is also what gfortran emits and what the CUDA kernels use.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# analytic.f90:39-60
+GODBY_NEEDS, PADE_APPROX, PADE_ROBUST, AAA_APPROX, AAA_POLE = 1, 2, 3, 4, 5
+# freqbins.f90:31-35
+NO_SYMMETRY, EVEN_SYMMETRY, SQUARE_SYMMETRY = 0, 1, 2
+EPS8, EPS14, EPS24 = 1e-8, 1e-14, 1e-24
+
+
+# ----------------------------------------------------------------------------- algo/grid
+def gauleg_grid(x1, x2, n):
+    """gauleg_grid.f90:23-74: Gauss-Legendre abscissas and weights on [x1, x2] (Newton iteration, eps = 3e-14)."""
+    x = np.zeros(n)
+    w = np.zeros(n)
+    m = (n + 1) // 2
+    xm, xl = 0.5 * (x2 + x1), 0.5 * (x2 - x1)
+    for i in range(1, m + 1):
+        z = np.cos(np.pi * (i - 0.25) / (n + 0.5))
+        while True:
+            p1, p2 = 1.0, 0.0
+            for j in range(1, n + 1):
+                p3, p2 = p2, p1
+                p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j
+            pp = n * (z * p1 - p2) / (z * z - 1.0)
+            z1 = z
+            z = z1 - p1 / pp
+            if not abs(z - z1) > 3e-14:
+                break
+        x[i - 1], x[n - i] = xm - xl * z, xm + xl * z
+        w[i - 1] = 2.0 * xl / ((1.0 - z * z) * pp * pp)
+        w[n - i] = w[i - 1]
+    return x, w
+
+
+def freqbins_symm(solver, freq_symm_coul, array=None):
+    """freqbins.f90:243-305: frequencies used for the continuation; with even symmetry the mesh is extended by
+    -solver (a single zero frequency is not doubled) and `array(:,:,ifreq_sym)` is filled with the mirrored values."""
+    solver = np.asarray(solver, dtype=complex)
+    nf = solver.size
+    if freq_symm_coul == NO_SYMMETRY:
+        return solver.copy()
+    if freq_symm_coul == SQUARE_SYMMETRY:
+        return solver ** 2
+    num_zero = int(np.count_nonzero(np.abs(solver) < EPS14))
+    if num_zero > 1:
+        raise ValueError("only a single frequency may be smaller than 1e-14")
+    nsym = 2 * nf - num_zero
+    out = np.zeros(nsym, dtype=complex)
+    if array is not None and array.shape[2] != nsym:
+        raise ValueError("array and frequency mesh inconsistent")
+    ifs = nf
+    for i in range(nf):
+        out[i] = solver[i]
+        if abs(out[i]) >= EPS14:
+            out[ifs] = -solver[i]
+            if array is not None:
+                array[:, :, ifs] = array[:, :, i]
+            ifs += 1
+    return out
+
+
+@dataclass
+class freqbins_type:
+    """freqbins.f90:42-105 (only the members the G W convolution reads)."""
+    solver: np.ndarray                     # frequencies of the linear solver (FREQUENCIES card, Ry)
+    coul: np.ndarray                       # integration mesh of the convolution
+    weight: np.ndarray                     # its weights
+    sigma: np.ndarray                      # frequencies of the self-energy
+    freq_symm_coul: int = EVEN_SYMMETRY
+    imag_sigma: bool = True
+    window: np.ndarray = field(default_factory=lambda: np.zeros(0))
+
+    def num_freq(self):
+        return freqbins_symm(self.solver, self.freq_symm_coul).size       # freqbins_init :307-320
+
+    def num_coul(self):
+        return self.coul.size
+
+    def num_sigma(self):
+        return self.sigma.size
+
+    def green(self, freq_sigma):
+        """freqbins_green :222-240: mu + coul, then mu - coul."""
+        return np.concatenate([freq_sigma + self.coul, freq_sigma - self.coul])
+
+    def symmetrize(self, freq):
+        """freqbins_symmetrize :322-337."""
+        return freq ** 2 if self.freq_symm_coul == SQUARE_SYMMETRY else freq
+
+
+def freqbins(imag_sigma, min_sigma, max_sigma, num_sigma, max_coul, num_coul, solver, freq_symm_coul=EVEN_SYMMETRY, eta=0.0,
+             window=(0.0, 0.0, 2)):
+    """freqbins.f90:109-180: equidistant self-energy mesh; Gauss-Legendre (imaginary axis) or equidistant + i eta
+    (real axis) integration mesh for the convolution."""
+    grid = min_sigma + (max_sigma - min_sigma) / (num_sigma - 1) * np.arange(num_sigma)
+    sigma = 1j * grid if imag_sigma else grid.astype(complex)
+    if not imag_sigma:
+        g = max_coul / (num_coul - 1) * np.arange(num_coul)
+        coul = g + 1j * eta
+        weight = np.full(num_coul, 2.0 * max_coul / float(2 * num_coul - 1))
+        weight[0] *= 0.5
+    else:
+        g, weight = gauleg_grid(0.0, max_coul, num_coul)
+        coul = 1j * g
+    win = window[0] + (window[1] - window[0]) / (window[2] - 1) * np.arange(window[2])
+    return freqbins_type(np.asarray(solver, dtype=complex), coul, weight, sigma, freq_symm_coul, imag_sigma, win)
+
+
+# ----------------------------------------------------------------------------- algo/analytic
+def _protect(x):
+    """pade.f90 `protect`: values with |x| <= eps24 are replaced by eps24."""
+    return np.where(np.abs(x) > EPS24, x, EPS24 + 0j)
+
+
+def pade_coeff(z, u):
+    """pade.f90 pade_coeff (Vidberg-Serene continued fraction).  u: (..., N) -> a: (..., N); vectorised over the
+    leading axes (the reference loops ig, igp around the scalar routine, analytic.f90:119-131)."""
+    z = np.asarray(z, dtype=complex)
+    N = z.size
+    g = _protect(np.array(u, dtype=complex))
+    a = np.zeros_like(g)
+    a[..., 0] = g[..., 0]
+    for p in range(1, N):
+        prev = g[..., p - 1:p]                       # g(p-1, p-1)
+        gi = g[..., p:]
+        tmp1 = prev / gi
+        tmp2 = gi / gi
+        g[..., p:] = _protect((tmp1 - tmp2) / (z[p:] - z[p - 1]))
+        a[..., p] = g[..., p]
+    return a
+
+
+def _cmul(a, b):
+    """Complex product from real operations, each rounded once (numpy's vectorised complex multiply fuses
+    multiply-adds on AVX2/AVX-512 hosts; the CUDA kernels use unfused *_rn operations, so this keeps the two bit-equal)."""
+    a, b = np.asarray(a, dtype=complex), np.asarray(b, dtype=complex)
+    out = np.empty(np.broadcast(a, b).shape, dtype=complex)
+    out.real = a.real * b.real - a.imag * b.imag
+    out.imag = a.real * b.imag + a.imag * b.real
+    return out
+
+
+def pade_eval(z, a, w):
+    """pade.f90 pade_eval: three-term recurrence of the continued fraction at the point w.  a: (..., N)."""
+    z = np.asarray(z, dtype=complex)
+    N = z.size
+    a = np.asarray(a, dtype=complex)
+    acap_m2 = np.zeros(a.shape[:-1], dtype=complex)
+    acap_m1 = a[..., 0].copy()
+    bcap_m2 = np.ones(a.shape[:-1], dtype=complex)
+    bcap_m1 = np.ones(a.shape[:-1], dtype=complex)
+    for i in range(1, N):
+        f = _cmul(w - z[i - 1], a[..., i])
+        acap = acap_m1 + _cmul(f, acap_m2)
+        bcap = bcap_m1 + _cmul(f, bcap_m2)
+        acap_m2, acap_m1 = acap_m1, acap
+        bcap_m2, bcap_m1 = bcap_m1, bcap
+    return acap_m1 / bcap_m1
+
+
+def godby_needs_coeffs(omega_p, coulomb):
+    """godby_needs.f90:34-90, in place on coulomb(ngc, ngc, 2)."""
+    if omega_p < 0:
+        raise ValueError("plasmon frequency must be positive")
+    if coulomb.shape[2] != 2:
+        raise ValueError("must provide exactly 2 frequencies")
+    c1, c2 = coulomb[:, :, 0].copy(), coulomb[:, :, 1].copy()
+    work = c1 - c2
+    set_zero = np.abs(work.real) < EPS8
+    safe = np.where(set_zero, 1.0 + 0j, work)
+    work2 = c2 / safe
+    set_zero = set_zero | (work2.real < EPS8)
+    b = np.sqrt(np.where(set_zero, 1.0 + 0j, work2)) * omega_p
+    a = 0.5 * c1 * b
+    coulomb[:, :, 1] = np.where(set_zero, 0.0, b)
+    coulomb[:, :, 0] = np.where(set_zero, 0.0, a)
+
+
+def godby_needs_model(freq, coeff):
+    """godby_needs.f90:108-135; coeff: (..., 2)."""
+    c1, c2 = coeff[..., 0], coeff[..., 1]
+    ok = np.abs(c1) > EPS8
+    d1 = np.where(ok, c2 + freq, 1.0)
+    d2 = np.where(ok, c2 - freq, 1.0)
+    return np.where(ok, c1 * (1.0 / d1 + 1.0 / d2), 0.0)
+
+
+def coulpade(factor, scrcoul_g):
+    """coulpade.f90:36-90: row ig of every frequency slice times the (truncated) Coulomb factor of q + G_ig
+    (the truncation module is host code; `factor` is its result)."""
+    scrcoul_g *= np.asarray(factor)[:, None, None]
+
+
+def analytic_coeff(model_coul, thres, freq: freqbins_type, scrcoul_g):
+    """analytic.f90:50-190, in place on scrcoul_g(ngc, ngc, freq.num_freq())."""
+    ngc = scrcoul_g.shape[0]
+    if scrcoul_g.shape[1] != ngc:
+        raise ValueError("input array should have same dimension for G and G'")
+    if scrcoul_g.shape[2] != freq.num_freq():
+        raise ValueError("frequency dimension of Coulomb inconsistent with frequency mesh")
+    if model_coul == GODBY_NEEDS:
+        godby_needs_coeffs(freq.solver[1].imag, scrcoul_g)
+    elif model_coul == PADE_APPROX:
+        z = freqbins_symm(freq.solver, freq.freq_symm_coul, scrcoul_g)
+        scrcoul_g[:, :, :] = pade_coeff(z, scrcoul_g)
+    else:
+        raise NotImplementedError("only 'godby-needs' and 'pade' are restated (the BASELINE configs use these two)")
+
+
+def analytic_eval(model_coul, gmapsym, freq_in: freqbins_type, scrcoul_coeff, freq_out, fft_map=None):
+    """analytic.f90:211-310: W(G, G') at one frequency -- the G-space block the reference stores in the upper-left
+    corner of scrcoul(nnr_c, nnr_c').  gmapsym, fft_map 1-based."""
+    gmapsym = np.asarray(gmapsym) - 1
+    ngc = gmapsym.size
+    fmap = np.arange(ngc) if fft_map is None else np.asarray(fft_map) - 1
+    freq_sym = freq_in.symmetrize(freq_out)
+    coeff = scrcoul_coeff[np.ix_(gmapsym, gmapsym[fmap])]          # (ngc, ngp, nfreq)
+    if model_coul == PADE_APPROX:
+        z = freqbins_symm(freq_in.solver, freq_in.freq_symm_coul)
+        return pade_eval(z, coeff, freq_sym)
+    if model_coul == GODBY_NEEDS:
+        return godby_needs_model(freq_sym, coeff)
+    raise NotImplementedError
+
+
+# ----------------------------------------------------------------------------- data/fft/src/fft6.f90
+@dataclass
+class corr_fft_type:
+    """The two members of grid%corr_fft the 6-D transforms read: box dimensions and nl (1-based)."""
+    nr: tuple
+    nl: np.ndarray
+
+    @property
+    def nnr(self):
+        return int(np.prod(self.nr))
+
+    @property
+    def ngm(self):
+        return int(self.nl.size)
+
+
+def _invfft(work, nr):
+    """[QE] invfft: unscaled sum_G f(G) exp(+i G r) on the column-major box."""
+    return (np.fft.ifftn(work.reshape(nr, order="F")) * np.prod(nr)).reshape(-1, order="F")
+
+
+def _fwfft(work, nr):
+    """[QE] fwfft: (1/nnr) sum_r f(r) exp(-i G r)."""
+    return (np.fft.fftn(work.reshape(nr, order="F")) / np.prod(nr)).reshape(-1, order="F")
+
+
+def invfft6(f, dfft: corr_fft_type, dfft_p: corr_fft_type, omega):
+    """fft6.f90:231-320, in place on f(nnr, nnr'): G' -> r' for every G, then conj/invfft/conj G -> r for every r'."""
+    ng, ngp = dfft.ngm, dfft_p.ngm
+    nl, nlp = dfft.nl - 1, dfft_p.nl - 1
+    for ig in range(ng):
+        work = np.zeros(dfft_p.nnr, dtype=complex)
+        work[nlp] = f[ig, :ngp] / omega
+        f[ig, :] = _invfft(work, dfft_p.nr)
+    for ir in range(dfft_p.nnr):
+        work = np.zeros(dfft.nnr, dtype=complex)
+        work[nl] = np.conj(f[:ng, ir])
+        f[:, ir] = np.conj(_invfft(work, dfft.nr))
+
+
+def fwfft6(f, dfft: corr_fft_type, dfft_p: corr_fft_type, omega):
+    """fft6.f90:84-170, in place on f(nnr, nnr'); the result occupies f(:ngm, :ngm')."""
+    ng, ngp = dfft.ngm, dfft_p.ngm
+    nl, nlp = dfft.nl - 1, dfft_p.nl - 1
+    for ir in range(dfft_p.nnr):
+        work = _fwfft(np.conj(f[:, ir]), dfft.nr)
+        f[:ng, ir] = np.conj(work[nl])
+    for ig in range(ng):
+        work = _fwfft(f[ig, :].copy(), dfft_p.nr)
+        f[ig, :ngp] = work[nlp] * omega
+
+
+# ----------------------------------------------------------------------------- phys/corr/src/sigma.f90
+def sigma_prod(omega, dfft, dfft_p, alpha, green, array):
+    """sigma.f90:417-500: array(:ngm, :ngm') = alpha * fwfft6( green(r,r') * invfft6(array) )."""
+    if np.isnan(alpha):
+        raise ValueError("prefactor of the convolution is NaN")
+    invfft6(array, dfft, dfft_p, omega)
+    array *= green
+    fwfft6(array, dfft, dfft_p, omega)
+    array[:dfft.ngm, :dfft_p.ngm] *= alpha
+
+
+def sigma_correlation(omega, dfft: corr_fft_type, model_coul, mu, alpha, freq: freqbins_type, gmapsym, coulomb, green_g,
+                      sigma):
+    """sigma.f90:528-750.  green_g(ngc, ngc, 2 num_coul) is the result of green_function (phys/green/src/green.f90:105)
+    at the frequencies freq.green(mu); sigma(ngc, ngc, num_sigma) is accumulated in place."""
+    ngc = dfft.ngm
+    nnr = dfft.nnr
+    if coulomb.shape[0] != ngc or coulomb.shape[1] != ngc:
+        raise ValueError("screened Coulomb and G-vector FFT type inconsistent")
+    if sigma.shape[2] != freq.num_sigma():
+        raise ValueError("frequency dimension of self energy not correct size")
+    num_green = 2 * freq.num_coul()
+    freq_green = freq.green(complex(mu))
+    freq_sigma = complex(mu) + freq.sigma
+    green = np.zeros((nnr, nnr, num_green), dtype=complex)
+    green[:ngc, :ngc, :] = green_g
+    for igreen in range(num_green):                                        # :664-666
+        invfft6(green[:, :, igreen], dfft, dfft, omega)
+    for isigma in range(freq.num_sigma()):                                 # :680
+        for igreen in range(num_green):
+            freq_coul = freq_sigma[isigma] - freq_green[igreen]            # :685
+            if freq_coul.real * freq_coul.imag < 0.0:                      # :688
+                freq_coul = np.conj(freq_coul)
+            work = np.zeros((nnr, nnr), dtype=complex)
+            work[:ngc, :ngc] = analytic_eval(model_coul, gmapsym, freq, coulomb, freq_coul)
+            icoul = igreen % freq.num_coul()
+            alpha_weight = alpha * freq.weight[icoul]                      # :703-704
+            sigma_prod(omega, dfft, dfft, alpha_weight, green[:, :, igreen], work)
+            sigma[:, :, isigma] += work[:ngc, :ngc]                        # :717
+
+
+# ----------------------------------------------------------------------------- post-processing used by the QP-energy test
+def qp_eigval(w, sig, et):
+    """print_matel.f90:278-320: linearised quasiparticle equation on the real-frequency window."""
+    dw = w[1] - w[0]
+    if et < w[0] + dw or et > w[-1] - dw:
+        return et, 1.0
+    iw = 0
+    iw1 = iw2 = 0
+    while iw < len(w) - 1 and w[iw] < et:
+        iw += 1
+        iw1, iw2 = iw - 1, iw
+    w1, w2, s1, s2 = w[iw1], w[iw2], sig[iw1], sig[iw2]
+    sig_et = s1 + (s2 - s1) * (et - w1) / (w2 - w1)
+    sig_der = (s2 - s1) / (w2 - w1)
+    zfac = 1.0 / (1.0 - sig_der)
+    return et + zfac * sig_et, zfac

@@ -17,6 +17,8 @@ SYMBOLS = [
     "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
     "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
     "sgw_parallel_task", "sgw_bench_linear_op",
+    "sgw_freqbins_num_freq", "sgw_coulpade", "sgw_analytic_coeff", "sgw_analytic_eval", "sgw_set_corr_grid", "sgw_invfft6",
+    "sgw_fwfft6", "sgw_sigma_correlation",
 ]
 
 
@@ -29,6 +31,17 @@ class SolverCfg(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_linear_op", c_int64), ("n_kernel_launch", c_int64), ("n_outer_max", C.c_int32),
                 ("n_fallback", C.c_int32), ("ms_solver", c_double), ("ms_linear_op", c_double), ("ms_total", c_double)]
+
+
+class Cplx(C.Structure):
+    _fields_ = [("re", c_double), ("im", c_double)]
+
+
+class Freqbins(C.Structure):
+    """sgw_freqbins == the members of freqbins_type (freqbins.f90:42-105) read by analytic.f90 / sigma.f90."""
+    _fields_ = [("imag_sigma", C.c_int32), ("freq_symm_coul", C.c_int32), ("num_solver", C.c_int32), ("solver", c_void_p),
+                ("num_coul", C.c_int32), ("coul", c_void_p), ("weight", c_void_p), ("num_sigma", C.c_int32),
+                ("sigma", c_void_p)]
 
 
 _lib = None
@@ -80,5 +93,15 @@ def load():
         L.sgw_parallel_task.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.sgw_bench_linear_op.argtypes = [c_void_p, c_int, c_int, c_int, C.POINTER(c_double), C.POINTER(c_double),
                                           C.POINTER(c_double)]
+        L.sgw_freqbins_num_freq.argtypes = [C.POINTER(Freqbins)]
+        L.sgw_coulpade.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
+        L.sgw_analytic_coeff.argtypes = [c_void_p, c_int, c_double, C.POINTER(Freqbins), c_int, c_void_p]
+        L.sgw_analytic_eval.argtypes = [c_void_p, c_int, C.POINTER(Freqbins), c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_void_p]
+        L.sgw_set_corr_grid.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+        L.sgw_invfft6.argtypes = [c_void_p, c_double, c_void_p]
+        L.sgw_fwfft6.argtypes = [c_void_p, c_double, c_void_p]
+        L.sgw_sigma_correlation.argtypes = [c_void_p, c_int, C.POINTER(SolverCfg), c_double, c_double, Cplx, c_int,
+                                            C.POINTER(Freqbins), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         _lib = L
     return _lib

@@ -1201,8 +1201,20 @@ int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrcoul_g, int 
 int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ngc, const int32_t *map, int ngp,
                        const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green, int32_t *ierr_out) {
   if (!ctx) return SGW_E_ARG;
+  SGW_ARG(green != nullptr, "null argument");
+  return sgw::green_function_core(ctx, slot, cfg, ngc, map, ngp, fft_map, nfreq, omega, green, ierr_out, nullptr);
+}
+
+}  // extern "C"
+
+// green_function with the result left on the device (workspace "gr_green", layout green(ngc, ngp, nfreq)) for
+// sgw_sigma_correlation; `green` may be null (no download).
+int sgw::green_function_core(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ngc, const int32_t *map, int ngp,
+                             const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green, int32_t *ierr_out,
+                             cplx **d_green_out) {
+  if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
-  SGW_ARG(cfg && map && fft_map && omega && green && ierr_out, "null argument");
+  SGW_ARG(cfg && map && fft_map && omega && ierr_out, "null argument");
   SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");
   SGW_ARG(ngc > 0 && ngp > 0 && nfreq > 0, "bad sizes");
   if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
@@ -1211,7 +1223,7 @@ int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ng
   for (int k = 0; k < ngc; ++k) SGW_ARG(map[k] >= 0 && map[k] <= num_g, "map entry outside 0..num_g");
   for (int i = 0; i < ngp; ++i) SGW_ARG(fft_map[i] >= 1 && fft_map[i] <= ngc, "fft_map entry outside 1..num_g_corr");
   begin_call(ctx);
-  memset(green, 0, sizeof(sgw_cplx) * (size_t)ngc * ngp * nfreq);                           // green.f90:184
+  if (green) memset(green, 0, sizeof(sgw_cplx) * (size_t)ngc * ngp * nfreq);                // green.f90:184
   *ierr_out = 0;
   cudaStream_t st = ctx->stream;
   std::vector<int> invperm(num_g);
@@ -1224,7 +1236,6 @@ int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ng
     col.push_back(i);
   }
   const int nlist = (int)pos.size();
-  if (nlist == 0) { end_call(ctx); return SGW_OK; }
   std::vector<cplx> msig(nfreq);
   for (int i = 0; i < nfreq; ++i) msig[i] = cmake(-omega[i].re, -omega[i].im);              // :207
   // RHS chunk that fits on the device
@@ -1280,11 +1291,10 @@ int sgw_green_function(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ng
     k_green_scatter<<<gs, 128, 0, st>>>(ngc, ngp, nfreq, num_g, n, d_map, d_inv, d_col + r0, d_x, d_green);
     SGW_LAUNCH_CHECK();
   }
-  SGW_CUDA(cudaMemcpyAsync(green, d_green, gbytes, cudaMemcpyDeviceToHost, st));
+  if (green) SGW_CUDA(cudaMemcpyAsync(green, d_green, gbytes, cudaMemcpyDeviceToHost, st));
   SGW_CUDA(cudaStreamSynchronize(st));
+  if (d_green_out) *d_green_out = d_green;
   *ierr_out = ierr_any;
   end_call(ctx);
   return SGW_OK;
 }
-
-}  // extern "C"

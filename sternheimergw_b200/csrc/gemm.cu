@@ -17,20 +17,6 @@ constexpr int PK = BK + 4;   // k-contiguous tiles: (g*PK + t) mod 8 distinct  <
 constexpr int PM = BM + 2;   // m-contiguous A tile: (t*PM + g) mod 8 distinct  <=  PM = 2 mod 8
 constexpr int NSTAGE = 2;
 
-__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
-}
-// 16-byte asynchronous global -> shared copy; bytes = 0 zero-fills the destination (tile edges)
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 template <bool A_KCONTIG>
 constexpr int a_tile_elems() { return A_KCONTIG ? BM * PK : BK * PM; }
 template <bool A_KCONTIG>

@@ -38,6 +38,24 @@ __host__ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
   return cmake((a.x * r + a.y) / d, (a.y * r - a.x) / d);
 }
 
+#ifdef __CUDACC__
+// FP64 tensor-core MMA and asynchronous global -> shared staging shared by gemm.cu and sigma.cu
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+// 16-byte asynchronous global -> shared copy; bytes = 0 zero-fills the destination (tile edges)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+#endif
+
 // ---------------------------------------------------------------- device descriptors
 struct GridDev {
   int nx, ny, nz;
@@ -95,8 +113,17 @@ struct KPair {
 };
 
 // kernel classes timed separately (CUDA events on the library's stream) when profiling is on
-enum ProfClass { PC_FFT_Z = 0, PC_FFT_PLANE, PC_GEMM_PROJ, PC_GEMM_OUT, PC_SHIFT, PC_SEED, PC_RHO_PLANE, PC_OTHER, PC_N };
+enum ProfClass { PC_FFT_Z = 0, PC_FFT_PLANE, PC_GEMM_PROJ, PC_GEMM_OUT, PC_SHIFT, PC_SEED, PC_RHO_PLANE, PC_OTHER, PC_GW_PROD, PC_N };
 struct ProfRec { int cls; cudaEvent_t a, b; };
+
+// grid%corr_fft of the correlation cutoff (sgw_set_corr_grid): the 6-D transforms of fft6.f90 act on ngm_c <= ~100 G vectors
+// of a box of a few hundred points, so they are applied as sphere-pruned DFT matrices on the FP64 tensor path:
+//   Ec(r, G) = exp(-i G r)  (nnr x ngm),   ET(G, r) = exp(+i G r)  (ngm x nnr)
+struct CorrGrid {
+  bool set = false;
+  int n1 = 0, n2 = 0, n3 = 0, nnr = 0, ngm = 0;
+  cplx *d_Ec = nullptr, *d_ET = nullptr;
+};
 
 struct Workspace {
   std::map<std::string, std::pair<void *, size_t>> bufs;
@@ -149,6 +176,8 @@ struct sgw_ctx {
   int gemm_cta_per_sm = 0;                       // resident k_zgemm CTAs per SM (0 = attributes not set yet)
   int sm_count = 148;
   size_t smem_optin = 0;
+  sgw::CorrGrid corr;                            // sigma.cu
+  bool gw_attr_set = false;
 };
 
 namespace sgw {
@@ -278,5 +307,10 @@ struct SolveBatch {
 int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo);
 int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo);
 int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_cfg *cfg);
+
+// ---- coulomb.cu ----
+int green_function_core(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int ngc, const int32_t *map, int ngp,
+                        const int32_t *fft_map, int nfreq, const sgw_cplx *omega, sgw_cplx *green, int32_t *ierr_out,
+                        cplx **d_green_out);
 
 }  // namespace sgw

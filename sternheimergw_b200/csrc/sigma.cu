@@ -1,0 +1,684 @@
+// sigma.cu -- SURVEY.md section 8 rows f2 and f3 on the device:
+//   f3  analytic continuation of W    algo/analytic/src/analytic.f90:50 (analytic_coeff), :211 (analytic_eval),
+//                                     pade.f90 (pade_coeff / pade_eval), godby_needs.f90, freqbins.f90:243 (freqbins_symm),
+//                                     phys/coul/src/coulpade.f90
+//   f2  Sigma_c = G W                 phys/corr/src/sigma.f90:417 (sigma_prod), :528 (sigma_correlation),
+//                                     data/fft/src/fft6.f90:84 (fwfft6), :231 (invfft6)
+//
+// Design.  The correlation box holds a few hundred points and <= ~100 G vectors (5^3..9^3 boxes, 15..59 G at the
+// BASELINE configs), so the reference's 2 x nnr tiny 3-D FFTs per 6-D transform are replaced by sphere-pruned DFT matrices
+// applied on the FP64 tensor path (DMMA):   f(r,r') = 1/Omega  Ec f(G,G') ET ,  f(G,G') = Omega/nnr^2  ET f(r,r') Ec
+// with Ec(r,G) = exp(-iGr), ET(G,r) = exp(+iGr).  The reference evaluates, for every (omega_sigma, omega_green) pair,
+// analytic_eval -> invfft6 -> product with G(r,r') -> fwfft6 -> accumulate.  Here one omega_sigma is ONE pass:
+//   k_analytic_eval   W(G,G') for all omega_green at once
+//   k_zgemm           X_b = Ec W_b / Omega                              (one GEMM over all omega_green)
+//   k_gw_product      acc(r,r') = sum_b alpha w_b G_b(r,r') (X_b ET)(r,r')   -- W(r,r') is never written to memory: the
+//                     second half of invfft6 is the main loop of the kernel and the product with G its epilogue
+//   k_zgemm x 2       sigma(G,G') += Omega/nnr^2 ET acc Ec               (one fwfft6 per omega_sigma instead of one per pair)
+// Algebraically identical to the reference (all steps are linear), re-associated.
+#include "internal.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+using namespace sgw;
+
+namespace sgw {
+
+// ---------------------------------------------------------------- arithmetic of the continuation kernels
+// The Pade recurrences amplify rounding differences, so these kernels use exactly the operation order of the oracle
+// (numpy: Smith division with a reciprocal, products without FMA contraction); *_rn intrinsics are never fused by nvcc.
+__device__ __forceinline__ cplx cmul_nf(cplx a, cplx b) {
+  return cmake(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ cplx cdiv_nf(cplx a, cplx b) {
+  if (fabs(b.x) >= fabs(b.y)) {
+    if (b.x == 0.0 && b.y == 0.0) return cmake(a.x / fabs(b.x), a.y / fabs(b.y));
+    const double rat = __ddiv_rn(b.y, b.x);
+    const double scl = __ddiv_rn(1.0, __dadd_rn(b.x, __dmul_rn(b.y, rat)));
+    return cmake(__dmul_rn(__dadd_rn(a.x, __dmul_rn(a.y, rat)), scl), __dmul_rn(__dsub_rn(a.y, __dmul_rn(a.x, rat)), scl));
+  }
+  const double rat = __ddiv_rn(b.x, b.y);
+  const double scl = __ddiv_rn(1.0, __dadd_rn(b.y, __dmul_rn(b.x, rat)));
+  return cmake(__dmul_rn(__dadd_rn(__dmul_rn(a.x, rat), a.y), scl), __dmul_rn(__dsub_rn(__dmul_rn(a.y, rat), a.x), scl));
+}
+__device__ __forceinline__ cplx protect(cplx x) {      // pade.f90: |x| <= eps24 -> eps24
+  return hypot(x.x, x.y) > 1e-24 ? x : cmake(1e-24, 0.0);
+}
+__device__ __forceinline__ cplx csqrt_dev(cplx z) {    // principal branch, Re >= 0
+  const double m = hypot(z.x, z.y);
+  if (m == 0.0) return cmake(0.0, 0.0);
+  if (z.x >= 0.0) {
+    const double t = sqrt(0.5 * (m + z.x));
+    return cmake(t, 0.5 * z.y / t);
+  }
+  const double t = sqrt(0.5 * (m - z.x));
+  return cmake(0.5 * fabs(z.y) / t, z.y >= 0.0 ? t : -t);
+}
+
+// coulpade.f90:72-85: scrcoul_g(ig, igp, ifreq) *= factor(ig)
+__global__ void k_coulpade(int ngc, long total, const double *__restrict__ factor, cplx *__restrict__ scr) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  scr[i] = cscale(factor[(int)(i % ngc)], scr[i]);
+}
+
+// freqbins_symm, array part (freqbins.f90:296-302): array(:,:,dst) = array(:,:,src) for the mirrored frequencies
+__global__ void k_mirror(long npair, int nmirror, const int *__restrict__ src, const int *__restrict__ dst, cplx *__restrict__ scr) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (i >= npair || m >= nmirror) return;
+  scr[i + npair * dst[m]] = scr[i + npair * src[m]];
+}
+
+// pade_coeff (pade.f90): one thread per (ig, igp); the g(p, :) row overwrites g(p-1, :) in place inside scrcoul_g itself,
+// whose frequency stride is ngc^2 -> coalesced across the pairs.  a(p) = g(p, p) is final once row p is done.
+__global__ void k_pade_coeff(long npair, int N, const cplx *__restrict__ z, cplx *__restrict__ scr) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npair) return;
+  cplx *g = scr + i;
+  for (int f = 0; f < N; ++f) g[npair * f] = protect(g[npair * f]);
+  for (int p = 1; p < N; ++p) {
+    const cplx prev = g[npair * (p - 1)];
+    const cplx zp = z[p - 1];
+    for (int f = p; f < N; ++f) {
+      const cplx gi = g[npair * f];
+      const cplx tmp1 = cdiv_nf(prev, gi);
+      const cplx tmp2 = cdiv_nf(gi, gi);
+      g[npair * f] = protect(cdiv_nf(csub(tmp1, tmp2), csub(z[f], zp)));
+    }
+  }
+}
+
+// godby_needs_coeffs (godby_needs.f90:34-90)
+__global__ void k_gn_coeff(long npair, double omega_p, cplx *__restrict__ scr) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npair) return;
+  const cplx c1 = scr[i], c2 = scr[i + npair];
+  cplx work = csub(c1, c2);
+  bool set_zero = fabs(work.x) < 1e-8;
+  if (!set_zero) {
+    work = cdiv_nf(c2, work);
+    set_zero = work.x < 1e-8;
+  }
+  if (!set_zero) {
+    const cplx b = cscale(omega_p, csqrt_dev(work));
+    scr[i + npair] = b;
+    scr[i] = cmul(cscale(0.5, c1), b);
+  } else {
+    scr[i] = cmake(0.0, 0.0);
+    scr[i + npair] = cmake(0.0, 0.0);
+  }
+}
+
+// analytic_eval (analytic.f90:266-300) for nout frequencies: out(ig, igp, io) = model(coeff(gmapsym(ig), gmapsym(igp), :), w_io)
+__global__ void k_analytic_eval(int model, int ngc, int N, const int *__restrict__ gmapsym, const cplx *__restrict__ z,
+                                const cplx *__restrict__ coeff, const cplx *__restrict__ wout, cplx *__restrict__ out) {
+  const int ig = blockIdx.x * blockDim.x + threadIdx.x;
+  const int igp = blockIdx.y, io = blockIdx.z;
+  if (ig >= ngc) return;
+  const long npair = (long)ngc * ngc;
+  const cplx *c = coeff + (gmapsym[ig] - 1) + (long)ngc * (gmapsym[igp] - 1);
+  const cplx w = wout[io];
+  cplx res;
+  if (model == SGW_PADE_APPROX) {                      // pade_eval (pade.f90)
+    cplx am2 = cmake(0.0, 0.0), am1 = c[0], bm2 = cmake(1.0, 0.0), bm1 = cmake(1.0, 0.0);
+    for (int f = 1; f < N; ++f) {
+      const cplx fac = cmul_nf(csub(w, z[f - 1]), c[npair * f]);
+      const cplx pa = cmul_nf(fac, am2), pb = cmul_nf(fac, bm2);
+      const cplx a = cmake(__dadd_rn(am1.x, pa.x), __dadd_rn(am1.y, pa.y));
+      const cplx b = cmake(__dadd_rn(bm1.x, pb.x), __dadd_rn(bm1.y, pb.y));
+      am2 = am1; am1 = a; bm2 = bm1; bm1 = b;
+    }
+    res = cdiv_nf(am1, bm1);
+  } else {                                             // godby_needs_model (godby_needs.f90:108-135)
+    const cplx c1 = c[0], c2 = c[npair];
+    if (hypot(c1.x, c1.y) > 1e-8) {
+      const cplx one = cmake(1.0, 0.0);
+      res = cmul(c1, cadd(cdiv_nf(one, cadd(c2, w)), cdiv_nf(one, csub(c2, w))));
+    } else {
+      res = cmake(0.0, 0.0);
+    }
+  }
+  out[ig + (long)ngc * (igp + (long)ngc * io)] = res;
+}
+
+// Ec(r, G) = exp(-i G r) (nnr x ngm) and ET(G, r) = exp(+i G r) (ngm x nnr); r = i1 + n1 (i2 + n2 i3) (QE column-major box),
+// G at box position p: G r = 2 pi (p1 i1 / n1 + p2 i2 / n2 + p3 i3 / n3), each term reduced exactly in integers.
+__global__ void k_corr_tables(int n1, int n2, int n3, int ngm, const int *__restrict__ nl, cplx *__restrict__ Ec,
+                              cplx *__restrict__ ET) {
+  const int nnr = n1 * n2 * n3;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ig = blockIdx.y;
+  if (r >= nnr || ig >= ngm) return;
+  const int p = nl[ig] - 1;
+  const int p1 = p % n1, p2 = (p / n1) % n2, p3 = p / (n1 * n2);
+  const int i1 = r % n1, i2 = (r / n1) % n2, i3 = r / (n1 * n2);
+  const double ph = 2.0 * ((double)((p1 * i1) % n1) / n1 + (double)((p2 * i2) % n2) / n2 + (double)((p3 * i3) % n3) / n3);
+  double s, c;
+  sincospi(ph, &s, &c);
+  Ec[(long)r + (long)nnr * ig] = cmake(c, -s);
+  ET[(long)ig + (long)ngm * r] = cmake(c, s);
+}
+
+// strided copy of the G block f(:ngm, :ngm) of a host-layout f(nnr, nnr)
+__global__ void k_block_copy(int ngm, long ld_src, long ld_dst, const cplx *__restrict__ src, cplx *__restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i < ngm) dst[(long)i + ld_dst * j] = src[(long)i + ld_src * j];
+}
+
+// ---------------------------------------------------------------- the G W product
+// part_z(r, r') = sum_{b in chunk z} coef_b * Gr_b(r, r') * (X_b ET)(r, r'),  X_b: M x K (column-major, batch stride M*K),
+// ET: K x N, Gr_b: M x N (batch stride M*N).  Tiling, staging and the 3M complex DMMA product are those of k_zgemm
+// (gemm.cu); the batch loop sits outside the K loop and the product with G is the epilogue of every batch entry, so the
+// real-space W never exists in memory.  The G tile of entry b is prefetched into registers before the K loop of b.
+constexpr int GW_BM = 64, GW_BN = 32, GW_BK = 16, GW_T = 256;
+constexpr int GW_PK = GW_BK + 4, GW_PM = GW_BM + 2;
+constexpr size_t GW_SMEM = (size_t)2 * (GW_BK * GW_PM + GW_BN * GW_PK) * sizeof(cplx);
+
+__global__ void __launch_bounds__(GW_T, 1) k_gw_product(int M, int N, int K, int nb, int bchunk, const cplx *__restrict__ X,
+                                                      const cplx *__restrict__ ET, const cplx *__restrict__ Gr,
+                                                      const cplx *__restrict__ coef, cplx *__restrict__ part) {
+  const int m0 = blockIdx.x * GW_BM, n0 = blockIdx.y * GW_BN;
+  const int b0 = blockIdx.z * bchunk, b1 = min(nb, b0 + bchunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int ASZ = GW_BK * GW_PM, BSZ = GW_BN * GW_PK;
+  extern __shared__ cplx gwsm[];
+  cplx *As = gwsm, *Bs = gwsm + 2 * ASZ;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
+  const int g = lane >> 2, t = lane & 3;
+  const long MK = (long)M * K, MN = (long)M * N;
+
+  cplx sacc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) sacc[i][j][c] = cmake(0.0, 0.0);
+
+  auto stage_load = [&](int st, const cplx *A, int k0) {
+    cplx *as = As + st * ASZ, *bs = Bs + st * BSZ;
+#pragma unroll
+    for (int r = 0; r < GW_BM * GW_BK / GW_T; ++r) {
+      const int i = tid + r * GW_T;
+      const int m = i % GW_BM, k = i / GW_BM;
+      const bool ok = (k0 + k < K) && (m0 + m < M);
+      cp_async16(as + k * GW_PM + m, ok ? A + (long)(m0 + m) + (long)(k0 + k) * M : A, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int r = 0; r < GW_BN * GW_BK / GW_T; ++r) {
+      const int i = tid + r * GW_T;
+      const int k = i % GW_BK, n = i / GW_BK;
+      const bool ok = (k0 + k < K) && (n0 + n < N);
+      cp_async16(bs + n * GW_PK + k, ok ? ET + (long)(k0 + k) + (long)(n0 + n) * K : ET, ok ? 16 : 0);
+    }
+  };
+
+  for (int b = b0; b < b1; ++b) {
+    const cplx *A = X + MK * b;
+    const cplx *Gb = Gr + MN * b;
+    stage_load(0, A, 0);
+    cp_async_commit();
+    // G tile of this entry -> registers (latency hidden behind the K loop)
+    cplx gv[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int row = m0 + wm + i * 8 + g, col = n0 + wn + j * 8 + 2 * t + c;
+          gv[i][j][c] = (row < M && col < N) ? __ldg(Gb + (long)row + (long)col * M) : cmake(0.0, 0.0);
+        }
+    double p1[2][2][2], p2[2][2][2], p3[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) p1[i][j][c] = p2[i][j][c] = p3[i][j][c] = 0.0;
+    int it = 0;
+    for (int k0 = 0; k0 < K; k0 += GW_BK, ++it) {
+      if (k0 + GW_BK < K) stage_load((it + 1) & 1, A, k0 + GW_BK);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const cplx *as = As + (it & 1) * ASZ, *bs = Bs + (it & 1) * BSZ;
+#pragma unroll
+      for (int kk = 0; kk < GW_BK; kk += 4) {
+        cplx a[2], bb[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = as[(kk + t) * GW_PM + wm + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) bb[j] = bs[(wn + j * 8 + g) * GW_PK + kk + t];
+        double asum[2], bsum[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) asum[i] = a[i].x + a[i].y;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) bsum[j] = bb[j].x + bb[j].y;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            dmma(p1[i][j][0], p1[i][j][1], a[i].x, bb[j].x);
+            dmma(p2[i][j][0], p2[i][j][1], a[i].y, bb[j].y);
+            dmma(p3[i][j][0], p3[i][j][1], asum[i], bsum[j]);
+          }
+      }
+      __syncthreads();
+    }
+    const cplx cb = coef[b];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const cplx w = cmake(p1[i][j][c] - p2[i][j][c], (p3[i][j][c] - p1[i][j][c]) - p2[i][j][c]);
+          sacc[i][j][c] = cfma(cmul(cb, gv[i][j][c]), w, sacc[i][j][c]);
+        }
+  }
+  cplx *P = part + MN * blockIdx.z;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int row = m0 + wm + i * 8 + g, col = n0 + wn + j * 8 + 2 * t + c;
+        if (row < M && col < N) P[(long)row + (long)col * M] = sacc[i][j][c];
+      }
+}
+
+// acc = sum_z part_z in a fixed order (deterministic)
+__global__ void k_gw_reduce(long n, int nz, const cplx *__restrict__ part, cplx *__restrict__ acc) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cplx s = part[i];
+  for (int z = 1; z < nz; ++z) s = cadd(s, part[i + n * z]);
+  acc[i] = s;
+}
+
+// ---------------------------------------------------------------- host helpers
+static int symm_mesh(const sgw_freqbins *f, std::vector<cplx> *z, std::vector<int> *src, std::vector<int> *dst) {
+  // freqbins_symm (freqbins.f90:243-305)
+  const int nf = f->num_solver;
+  z->clear();
+  if (src) { src->clear(); dst->clear(); }
+  if (f->freq_symm_coul == 0 || f->freq_symm_coul == 2) {
+    for (int i = 0; i < nf; ++i) {
+      const cplx s = cmake(f->solver[i].re, f->solver[i].im);
+      z->push_back(f->freq_symm_coul == 2 ? cmul(s, s) : s);
+    }
+    return SGW_OK;
+  }
+  int num_zero = 0;
+  for (int i = 0; i < nf; ++i) num_zero += hypot(f->solver[i].re, f->solver[i].im) < 1e-14;
+  if (num_zero > 1) return SGW_E_ARG;
+  z->resize(2 * nf - num_zero);
+  int ifs = nf;
+  for (int i = 0; i < nf; ++i) {
+    (*z)[i] = cmake(f->solver[i].re, f->solver[i].im);
+    if (hypot(f->solver[i].re, f->solver[i].im) >= 1e-14) {
+      (*z)[ifs] = cmake(-f->solver[i].re, -f->solver[i].im);
+      if (src) { src->push_back(i); dst->push_back(ifs); }
+      ++ifs;
+    }
+  }
+  return SGW_OK;
+}
+
+static int check_freq(sgw_ctx *ctx, const sgw_freqbins *f, int model) {
+  SGW_ARG(f && f->num_solver > 0 && f->solver, "freqbins: solver frequencies missing");
+  SGW_ARG(f->freq_symm_coul >= 0 && f->freq_symm_coul <= 2, "freqbins: freq_symm_coul must be 0, 1 or 2");
+  if (model == SGW_PADE_ROBUST || model == SGW_AAA_APPROX || model == SGW_AAA_POLE) {
+    ctx->err = "model_coul 'pade robust' / 'aaa' / 'aaa pole' are not built (SURVEY 8 f3 covers 'pade' and 'godby-needs')";
+    return SGW_E_UNSUPPORTED;
+  }
+  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX, "No screening model chosen!");   // analytic.f90:186
+  return SGW_OK;
+}
+
+// device part of analytic_eval: coefficients and gmapsym already resident
+static int analytic_eval_dev(sgw_ctx *ctx, int model, int ngc, int N, const int *d_gmap, const cplx *d_z, const cplx *d_coeff,
+                             int nout, const cplx *d_wout, cplx *d_out) {
+  dim3 grid((ngc + 63) / 64, ngc, nout);
+  ProfScope prof(ctx, PC_OTHER);
+  k_analytic_eval<<<grid, 64, 0, ctx->stream>>>(model, ngc, N, d_gmap, d_z, d_coeff, d_wout, d_out);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+// f(r, r') = 1/omega Ec fg ET for nb G-space blocks fg_b(ngm, ngm) stored back to back -> fr_b(nnr, nnr)
+static int invfft6_dev(sgw_ctx *ctx, double omega, int nb, const cplx *fg, cplx *fr) {
+  const CorrGrid &c = ctx->corr;
+  cplx *X = nullptr;
+  SGW_CHECK(ws(ctx, "sg_x", (size_t)c.nnr * c.ngm * nb, &X));
+  SGW_CHECK(gemm_n_n(ctx, c.nnr, c.ngm * nb, c.ngm, cmake(1.0 / omega, 0.0), c.d_Ec, c.nnr, fg, c.ngm, cmake(0, 0), X, c.nnr));
+  for (int b = 0; b < nb; ++b)
+    SGW_CHECK(gemm_n_n(ctx, c.nnr, c.nnr, c.ngm, cmake(1, 0), X + (size_t)c.nnr * c.ngm * b, c.nnr, c.d_ET, c.ngm, cmake(0, 0),
+                       fr + (size_t)c.nnr * c.nnr * b, c.nnr));
+  return SGW_OK;
+}
+
+// fg(ngm, ngm) = beta fg + scale * omega / nnr^2 ET fr Ec
+static int fwfft6_dev(sgw_ctx *ctx, double omega, const cplx *fr, cplx beta, cplx *fg, long ldg) {
+  const CorrGrid &c = ctx->corr;
+  cplx *U = nullptr;
+  SGW_CHECK(ws(ctx, "sg_u", (size_t)c.nnr * c.ngm, &U));
+  SGW_CHECK(gemm_n_n(ctx, c.nnr, c.ngm, c.nnr, cmake(1, 0), fr, c.nnr, c.d_Ec, c.nnr, cmake(0, 0), U, c.nnr));
+  const double s = omega / ((double)c.nnr * (double)c.nnr);
+  SGW_CHECK(gemm_n_n(ctx, c.ngm, c.ngm, c.nnr, cmake(s, 0.0), c.d_ET, c.ngm, U, c.nnr, beta, fg, ldg));
+  return SGW_OK;
+}
+
+}  // namespace sgw
+
+extern "C" {
+
+int sgw_freqbins_num_freq(const sgw_freqbins *freq) {
+  if (!freq || freq->num_solver <= 0 || !freq->solver) return SGW_E_ARG;
+  std::vector<cplx> z;
+  if (symm_mesh(freq, &z, nullptr, nullptr) != SGW_OK) return SGW_E_ARG;
+  return (int)z.size();
+}
+
+int sgw_coulpade(sgw_ctx *ctx, int ngc, int nfreq, const double *factor, sgw_cplx *scrcoul_g) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ngc > 0 && nfreq > 0 && factor && scrcoul_g, "bad argument");
+  begin_call(ctx);
+  const long total = (long)ngc * ngc * nfreq;
+  cplx *d = nullptr;
+  double *df = nullptr;
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)total, &d));
+  SGW_CHECK(ws(ctx, "an_fac", (size_t)ngc, &df));
+  SGW_CUDA(cudaMemcpyAsync(d, scrcoul_g, sizeof(cplx) * total, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(df, factor, sizeof(double) * ngc, cudaMemcpyHostToDevice, ctx->stream));
+  k_coulpade<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ngc, total, df, d);
+  SGW_LAUNCH_CHECK();
+  SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d, sizeof(cplx) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_freqbins *freq, int ngc, sgw_cplx *scrcoul_g) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  (void)thres;   // only read by the AAA and robust-Pade models
+  SGW_CHECK(check_freq(ctx, freq, model_coul));
+  SGW_ARG(ngc > 0 && scrcoul_g, "bad argument");
+  std::vector<cplx> z;
+  std::vector<int> src, dst;
+  if (symm_mesh(freq, &z, &src, &dst) != SGW_OK) {
+    ctx->err = "only a single frequency may be smaller than 1e-14";    // freqbins.f90:276
+    return SGW_E_ARG;
+  }
+  const int N = (int)z.size();
+  if (model_coul == SGW_GODBY_NEEDS) {
+    SGW_ARG(N == 2, "must provide exactly 2 frequencies");                                        // godby_needs.f90:50
+    SGW_ARG(freq->solver[1].im >= 0.0, "plasmon frequency must be positive");                     // godby_needs.f90:48
+  }
+  begin_call(ctx);
+  const long npair = (long)ngc * ngc, total = npair * N;
+  cplx *d = nullptr, *dz = nullptr;
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)total, &d));
+  SGW_CHECK(ws(ctx, "an_z", (size_t)N, &dz));
+  SGW_CUDA(cudaMemcpyAsync(d, scrcoul_g, sizeof(cplx) * total, cudaMemcpyHostToDevice, ctx->stream));
+  if (model_coul == SGW_GODBY_NEEDS) {
+    k_gn_coeff<<<(unsigned)((npair + 127) / 128), 128, 0, ctx->stream>>>(npair, freq->solver[1].im, d);
+    SGW_LAUNCH_CHECK();
+  } else {
+    SGW_CUDA(cudaMemcpyAsync(dz, z.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, ctx->stream));
+    if (!src.empty()) {
+      int *dsrc = nullptr, *ddst = nullptr;
+      SGW_CHECK(ws(ctx, "an_src", src.size(), &dsrc));
+      SGW_CHECK(ws(ctx, "an_dst", dst.size(), &ddst));
+      SGW_CUDA(cudaMemcpyAsync(dsrc, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice, ctx->stream));
+      SGW_CUDA(cudaMemcpyAsync(ddst, dst.data(), sizeof(int) * dst.size(), cudaMemcpyHostToDevice, ctx->stream));
+      dim3 grid((unsigned)((npair + 255) / 256), (unsigned)src.size());
+      k_mirror<<<grid, 256, 0, ctx->stream>>>(npair, (int)src.size(), dsrc, ddst, d);
+      SGW_LAUNCH_CHECK();
+    }
+    k_pade_coeff<<<(unsigned)((npair + 63) / 64), 64, 0, ctx->stream>>>(npair, N, dz, d);
+    SGW_LAUNCH_CHECK();
+  }
+  SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d, sizeof(cplx) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_analytic_eval(sgw_ctx *ctx, int model_coul, const sgw_freqbins *freq, int ngc, const int32_t *gmapsym,
+                      const sgw_cplx *scrcoul_coeff, int nout, const sgw_cplx *freq_out, sgw_cplx *scrcoul) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_CHECK(check_freq(ctx, freq, model_coul));
+  SGW_ARG(ngc > 0 && nout > 0 && gmapsym && scrcoul_coeff && freq_out && scrcoul, "bad argument");
+  for (int i = 0; i < ngc; ++i) SGW_ARG(gmapsym[i] >= 1 && gmapsym[i] <= ngc, "gmapsym entry outside 1..num_g_corr");
+  std::vector<cplx> z;
+  if (symm_mesh(freq, &z, nullptr, nullptr) != SGW_OK) { ctx->err = "only a single frequency may be smaller than 1e-14"; return SGW_E_ARG; }
+  const int N = (int)z.size();
+  if (model_coul == SGW_GODBY_NEEDS) SGW_ARG(N == 2, "must provide exactly 2 frequencies");
+  std::vector<cplx> w(nout);
+  for (int i = 0; i < nout; ++i) {                      // freq_in%symmetrize(freq_out) (analytic.f90:262)
+    const cplx f = cmake(freq_out[i].re, freq_out[i].im);
+    w[i] = freq->freq_symm_coul == 2 ? cmul(f, f) : f;
+  }
+  begin_call(ctx);
+  const long npair = (long)ngc * ngc;
+  cplx *d = nullptr, *dz = nullptr, *dw = nullptr, *dout = nullptr;
+  int *dg = nullptr;
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)npair * N, &d));
+  SGW_CHECK(ws(ctx, "an_z", (size_t)N, &dz));
+  SGW_CHECK(ws(ctx, "an_w", (size_t)nout, &dw));
+  SGW_CHECK(ws(ctx, "an_out", (size_t)npair * nout, &dout));
+  SGW_CHECK(ws(ctx, "an_gmap", (size_t)ngc, &dg));
+  SGW_CUDA(cudaMemcpyAsync(d, scrcoul_coeff, sizeof(cplx) * npair * N, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(dz, z.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(dw, w.data(), sizeof(cplx) * nout, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(dg, gmapsym, sizeof(int) * ngc, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CHECK(analytic_eval_dev(ctx, model_coul, ngc, N, dg, dz, d, nout, dw, dout));
+  SGW_CUDA(cudaMemcpyAsync(scrcoul, dout, sizeof(cplx) * npair * nout, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_set_corr_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int ngm_c, const int32_t *nl_c) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(nr1 > 0 && nr2 > 0 && nr3 > 0 && ngm_c > 0 && nl_c, "bad argument");
+  const long nnr = (long)nr1 * nr2 * nr3;
+  SGW_ARG(nnr <= 46340, "correlation box too large for the DFT-matrix transforms (nnr_c^2 must fit 31 bits)");
+  SGW_ARG(ngm_c <= nnr, "more G vectors than box points");
+  for (int i = 0; i < ngm_c; ++i) SGW_ARG(nl_c[i] >= 1 && nl_c[i] <= nnr, "nl entry outside the correlation box");
+  CorrGrid &c = ctx->corr;
+  if (c.d_Ec) { cudaFree(c.d_Ec); c.d_Ec = nullptr; }
+  if (c.d_ET) { cudaFree(c.d_ET); c.d_ET = nullptr; }
+  c.set = false;
+  c.n1 = nr1; c.n2 = nr2; c.n3 = nr3; c.nnr = (int)nnr; c.ngm = ngm_c;
+  SGW_CUDA(cudaMalloc((void **)&c.d_Ec, sizeof(cplx) * nnr * ngm_c));
+  SGW_CUDA(cudaMalloc((void **)&c.d_ET, sizeof(cplx) * nnr * ngm_c));
+  int *dnl = nullptr;
+  SGW_CHECK(ws(ctx, "sg_nl", (size_t)ngm_c, &dnl));
+  SGW_CUDA(cudaMemcpyAsync(dnl, nl_c, sizeof(int) * ngm_c, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((unsigned)((nnr + 127) / 128), ngm_c);
+  k_corr_tables<<<grid, 128, 0, ctx->stream>>>(nr1, nr2, nr3, ngm_c, dnl, c.d_Ec, c.d_ET);
+  ctx->launches++;
+  SGW_CUDA(cudaGetLastError());
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  c.set = true;
+  return SGW_OK;
+}
+
+int sgw_invfft6(sgw_ctx *ctx, double omega, sgw_cplx *f) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(f && omega != 0.0, "bad argument");
+  if (!ctx->corr.set) { ctx->err = "sgw_set_corr_grid missing"; return SGW_E_STATE; }
+  const CorrGrid &c = ctx->corr;
+  begin_call(ctx);
+  cplx *fr = nullptr, *fg = nullptr;
+  SGW_CHECK(ws(ctx, "sg_fr", (size_t)c.nnr * c.nnr, &fr));
+  SGW_CHECK(ws(ctx, "sg_fg", (size_t)c.ngm * c.ngm, &fg));
+  SGW_CUDA(cudaMemcpy2DAsync(fg, sizeof(cplx) * c.ngm, f, sizeof(cplx) * c.nnr, sizeof(cplx) * c.ngm, c.ngm, cudaMemcpyHostToDevice,
+                             ctx->stream));
+  SGW_CHECK(invfft6_dev(ctx, omega, 1, fg, fr));
+  SGW_CUDA(cudaMemcpyAsync(f, fr, sizeof(cplx) * c.nnr * c.nnr, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_fwfft6(sgw_ctx *ctx, double omega, sgw_cplx *f) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(f != nullptr, "bad argument");
+  if (!ctx->corr.set) { ctx->err = "sgw_set_corr_grid missing"; return SGW_E_STATE; }
+  const CorrGrid &c = ctx->corr;
+  begin_call(ctx);
+  cplx *fr = nullptr, *fg = nullptr;
+  SGW_CHECK(ws(ctx, "sg_fr", (size_t)c.nnr * c.nnr, &fr));
+  SGW_CHECK(ws(ctx, "sg_fg", (size_t)c.ngm * c.ngm, &fg));
+  SGW_CUDA(cudaMemcpyAsync(fr, f, sizeof(cplx) * c.nnr * c.nnr, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CHECK(fwfft6_dev(ctx, omega, fr, cmake(0, 0), fg, c.ngm));
+  SGW_CUDA(cudaMemcpy2DAsync(f, sizeof(cplx) * c.nnr, fg, sizeof(cplx) * c.ngm, sizeof(cplx) * c.ngm, c.ngm, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_sigma_correlation(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg_green, double omega_cell, double mu, sgw_cplx alpha,
+                          int model_coul, const sgw_freqbins *freq, int ngm_c, const int32_t *map, const int32_t *gmapsym,
+                          const sgw_cplx *coulomb, sgw_cplx *sigma, int32_t *ierr_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_CHECK(check_freq(ctx, freq, model_coul));
+  SGW_ARG(cfg_green && map && gmapsym && coulomb && sigma && ierr_out, "null argument");
+  SGW_ARG(freq->num_coul > 0 && freq->coul && freq->weight && freq->num_sigma > 0 && freq->sigma, "freqbins: convolution meshes missing");
+  SGW_ARG(omega_cell > 0.0, "cell volume must be positive");
+  SGW_ARG(alpha.re == alpha.re && alpha.im == alpha.im, "prefactor of the convolution is NaN");       // sigma.f90:466
+  if (!ctx->corr.set) { ctx->err = "sgw_set_corr_grid missing"; return SGW_E_STATE; }
+  const CorrGrid &c = ctx->corr;
+  SGW_ARG(ngm_c == c.ngm, "screened Coulomb and G-vector FFT type inconsistent");                     // sigma.f90:624
+  for (int i = 0; i < ngm_c; ++i) SGW_ARG(gmapsym[i] >= 1 && gmapsym[i] <= ngm_c, "gmapsym and FFT type are inconsistent");
+  std::vector<cplx> z;
+  if (symm_mesh(freq, &z, nullptr, nullptr) != SGW_OK) { ctx->err = "only a single frequency may be smaller than 1e-14"; return SGW_E_ARG; }
+  const int N = (int)z.size();
+  if (model_coul == SGW_GODBY_NEEDS) SGW_ARG(N == 2, "must provide exactly 2 frequencies");
+  const int ncoul = freq->num_coul, nb = 2 * ncoul, nsig = freq->num_sigma;
+  const int nnr = c.nnr, ng = c.ngm;
+  const long npair = (long)ng * ng;
+
+  // memory: G(r, r', omega_green) stays resident for all omega_sigma
+  {
+    size_t free_b = 0, total_b = 0, held = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    for (auto &kv : ctx->ws.bufs) held += kv.second.second;
+    const double need = 16.0 * ((double)nnr * nnr * (nb + 2 + 16) + (double)nnr * ng * nb * 2);
+    if (need > 0.9 * (double)(free_b + held)) {
+      ctx->err = "G(r,r',omega) of this correlation box does not fit on the device";
+      return SGW_E_UNSUPPORTED;
+    }
+  }
+
+  // ---- Green's function at freq%green(mu) (sigma.f90:650-655), left on the device
+  std::vector<sgw_cplx> fgreen(nb);
+  for (int i = 0; i < ncoul; ++i) {                                                                   // freqbins_green
+    fgreen[i].re = mu + freq->coul[i].re; fgreen[i].im = freq->coul[i].im;
+    fgreen[ncoul + i].re = mu - freq->coul[i].re; fgreen[ncoul + i].im = -freq->coul[i].im;
+  }
+  std::vector<int32_t> fft_map(ng);
+  for (int i = 0; i < ng; ++i) fft_map[i] = i + 1;
+  cplx *d_green = nullptr;
+  SGW_CHECK(green_function_core(ctx, slot, cfg_green, ng, map, ng, fft_map.data(), nb, fgreen.data(), nullptr, ierr_out, &d_green));
+  const sgw_stats st_green = ctx->stats;
+  if (*ierr_out != 0) return SGW_OK;                  // the reference aborts here (green.f90:208); sigma is left untouched
+
+  begin_call(ctx);
+  cudaStream_t st = ctx->stream;
+  cplx *d_gr = nullptr, *d_coeff = nullptr, *d_z = nullptr, *d_w = nullptr, *d_cf = nullptr, *d_wg = nullptr, *d_x = nullptr,
+       *d_part = nullptr, *d_acc = nullptr, *d_sigma = nullptr;
+  int *d_gmap = nullptr;
+  SGW_CHECK(ws(ctx, "sg_gr", (size_t)nnr * nnr * nb, &d_gr));
+  SGW_CHECK(invfft6_dev(ctx, omega_cell, nb, d_green, d_gr));                                         // sigma.f90:664-666
+
+  // ---- per (omega_sigma, omega_green): frequency of W and weight of the product (sigma.f90:680-704)
+  std::vector<cplx> wtab((size_t)nsig * nb), ctab((size_t)nsig * nb);
+  for (int is = 0; is < nsig; ++is)
+    for (int b = 0; b < nb; ++b) {
+      cplx fc = cmake(mu + freq->sigma[is].re - fgreen[b].re, freq->sigma[is].im - fgreen[b].im);
+      if (fc.x * fc.y < 0.0) fc = cconj(fc);                                                          // :688
+      wtab[(size_t)is * nb + b] = freq->freq_symm_coul == 2 ? cmul(fc, fc) : fc;                      // symmetrize
+      const double wgt = freq->weight[b % ncoul];
+      ctab[(size_t)is * nb + b] = cmake(alpha.re * wgt, alpha.im * wgt);
+    }
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)npair * N, &d_coeff));
+  SGW_CHECK(ws(ctx, "an_z", (size_t)N, &d_z));
+  SGW_CHECK(ws(ctx, "an_gmap", (size_t)ng, &d_gmap));
+  SGW_CHECK(ws(ctx, "sg_w", (size_t)nsig * nb, &d_w));
+  SGW_CHECK(ws(ctx, "sg_cf", (size_t)nsig * nb, &d_cf));
+  SGW_CHECK(ws(ctx, "sg_wg", (size_t)npair * nb, &d_wg));
+  SGW_CHECK(ws(ctx, "sg_x", (size_t)nnr * ng * nb, &d_x));
+  SGW_CHECK(ws(ctx, "sg_sigma", (size_t)npair * nsig, &d_sigma));
+  SGW_CUDA(cudaMemcpyAsync(d_coeff, coulomb, sizeof(cplx) * npair * N, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_z, z.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_gmap, gmapsym, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_w, wtab.data(), sizeof(cplx) * wtab.size(), cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_cf, ctab.data(), sizeof(cplx) * ctab.size(), cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_sigma, sigma, sizeof(cplx) * npair * nsig, cudaMemcpyHostToDevice, st));
+
+  // batch split of the product kernel: fill the machine when the tile grid alone is smaller than one wave
+  const int tiles = ((nnr + GW_BM - 1) / GW_BM) * ((nnr + GW_BN - 1) / GW_BN);
+  int nz = std::max(1, std::min(nb, (2 * ctx->sm_count + tiles - 1) / tiles));
+  nz = std::min(nz, 16);
+  const int bchunk = (nb + nz - 1) / nz;
+  nz = (nb + bchunk - 1) / bchunk;
+  SGW_CHECK(ws(ctx, "sg_part", (size_t)nnr * nnr * nz, &d_part));
+  SGW_CHECK(ws(ctx, "sg_acc", (size_t)nnr * nnr, &d_acc));
+  if (!ctx->gw_attr_set) {
+    SGW_CUDA(cudaFuncSetAttribute(k_gw_product, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GW_SMEM));
+    ctx->gw_attr_set = true;
+  }
+  for (int is = 0; is < nsig; ++is) {                                                                 // sigma.f90:680
+    SGW_CHECK(analytic_eval_dev(ctx, model_coul, ng, N, d_gmap, d_z, d_coeff, nb, d_w + (size_t)is * nb, d_wg));
+    // first half of invfft6 for all omega_green: X_b = Ec W_b / Omega
+    SGW_CHECK(gemm_n_n(ctx, nnr, ng * nb, ng, cmake(1.0 / omega_cell, 0.0), c.d_Ec, nnr, d_wg, ng, cmake(0, 0), d_x, nnr));
+    {
+      ProfScope prof(ctx, PC_GW_PROD);
+      dim3 grid((nnr + GW_BM - 1) / GW_BM, (nnr + GW_BN - 1) / GW_BN, nz);
+      k_gw_product<<<grid, GW_T, GW_SMEM, st>>>(nnr, nnr, ng, nb, bchunk, d_x, c.d_ET, d_gr, d_cf + (size_t)is * nb, d_part);
+      SGW_LAUNCH_CHECK();
+    }
+    const cplx *acc = d_part;
+    if (nz > 1) {
+      ProfScope prof(ctx, PC_OTHER);
+      const long n = (long)nnr * nnr;
+      k_gw_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, nz, d_part, d_acc);
+      SGW_LAUNCH_CHECK();
+      acc = d_acc;
+    }
+    SGW_CHECK(fwfft6_dev(ctx, omega_cell, acc, cmake(1, 0), d_sigma + (size_t)npair * is, ng));      // :717 sigma += work
+  }
+  SGW_CUDA(cudaMemcpyAsync(sigma, d_sigma, sizeof(cplx) * npair * nsig, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  end_call(ctx);
+  // one call = G + G*W: merge the counters of the Green's-function part
+  ctx->stats.n_linear_op += st_green.n_linear_op;
+  ctx->stats.n_kernel_launch += st_green.n_kernel_launch;
+  ctx->stats.n_outer_max = st_green.n_outer_max;
+  ctx->stats.n_fallback = st_green.n_fallback;
+  ctx->stats.ms_solver = st_green.ms_solver;
+  ctx->stats.ms_linear_op = st_green.ms_linear_op;
+  ctx->stats.ms_total += st_green.ms_total;
+  return SGW_OK;
+}
+
+}  // extern "C"

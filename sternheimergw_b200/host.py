@@ -32,6 +32,61 @@ class select_solver_type:
         return cfg
 
 
+# model_coul (analytic.f90:39-60) and freq_symm_coul (freqbins.f90:31-35)
+godby_needs, pade_approx, pade_robust, aaa_approx, aaa_pole = 1, 2, 3, 4, 5
+no_symmetry, even_symmetry, square_symmetry = 0, 1, 2
+
+
+@dataclass
+class freqbins_type:
+    """The members of freqbins_type (algo/grid/src/freqbins.f90:42-105) the continuation and the G W convolution read;
+    same names.  `num_freq`, `green` and `symmetrize` follow freqbins.f90:190,222,322."""
+    solver: np.ndarray
+    coul: np.ndarray = None
+    weight: np.ndarray = None
+    sigma: np.ndarray = None
+    freq_symm_coul: int = even_symmetry
+    imag_sigma: bool = True
+
+    def c(self):
+        """(sgw_freqbins, keep-alive list of the arrays it points to)."""
+        keep = [np.ascontiguousarray(self.solver, dtype=np.complex128)]
+        fb = _lib.Freqbins()
+        fb.imag_sigma, fb.freq_symm_coul = int(bool(self.imag_sigma)), int(self.freq_symm_coul)
+        fb.num_solver, fb.solver = keep[0].size, keep[0].ctypes.data
+        if self.coul is not None:
+            coul = np.ascontiguousarray(self.coul, dtype=np.complex128)
+            weight = np.ascontiguousarray(self.weight, dtype=np.float64)
+            if weight.size != coul.size:
+                raise SgwError("freqbins: one weight per integration frequency")
+            fb.num_coul, fb.coul, fb.weight = coul.size, coul.ctypes.data, weight.ctypes.data
+            keep += [coul, weight]
+        if self.sigma is not None:
+            sig = np.ascontiguousarray(self.sigma, dtype=np.complex128)
+            fb.num_sigma, fb.sigma = sig.size, sig.ctypes.data
+            keep.append(sig)
+        return fb, keep
+
+    def num_freq(self):
+        fb, _keep = self.c()
+        n = _lib.load().sgw_freqbins_num_freq(C.byref(fb))
+        if n < 0:
+            raise SgwError("only a single frequency may be smaller than 1e-14")       # freqbins.f90:276
+        return n
+
+    def num_coul(self):
+        return int(np.size(self.coul))
+
+    def num_sigma(self):
+        return int(np.size(self.sigma))
+
+    def green(self, freq_sigma):
+        return np.concatenate([freq_sigma + np.asarray(self.coul), freq_sigma - np.asarray(self.coul)])
+
+    def symmetrize(self, freq):
+        return freq ** 2 if self.freq_symm_coul == square_symmetry else freq
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -268,6 +323,79 @@ class Context:
         if ierr.value != 0:
             raise SgwError(f"the linear solver for G did not converge (ierr={ierr.value})")   # green.f90:208
         return green
+
+    # ---- algo/analytic -------------------------------------------------------------------
+    def coulpade(self, factor, scrcoul_g):
+        """coulpade.f90:36: scrcoul_g(ig,:,:) *= factor(ig); returns the scaled copy."""
+        scr = _c16(scrcoul_g).copy(order="F")
+        factor = np.ascontiguousarray(factor, dtype=np.float64)
+        ngc, ngc2, nf = scr.shape
+        if ngc2 != ngc:
+            raise SgwError("input array should have same dimension for G and G'")
+        self._chk(self._L.sgw_coulpade(self._h, ngc, nf, _p(factor), _p(scr)), "coulpade")
+        return scr
+
+    def analytic_coeff(self, model_coul, thres, freq: "freqbins_type", scrcoul_g):
+        """analytic.f90:50: returns the coefficient array (the reference overwrites scrcoul_g in place)."""
+        scr = _c16(scrcoul_g).copy(order="F")
+        ngc = scr.shape[0]
+        if scr.shape[1] != ngc:
+            raise SgwError("input array should have same dimension for G and G'")
+        if scr.shape[2] != freq.num_freq():
+            raise SgwError("frequency dimension of Coulomb inconsistent with frequency mesh")
+        fb, _keep = freq.c()
+        self._chk(self._L.sgw_analytic_coeff(self._h, int(model_coul), float(thres), C.byref(fb), ngc, _p(scr)), "analytic_coeff")
+        return scr
+
+    def analytic_eval(self, model_coul, gmapsym, freq_in: "freqbins_type", scrcoul_coeff, freq_out):
+        """analytic.f90:211 for one or several output frequencies: (ngc, ngc[, nout])."""
+        coeff = _c16(scrcoul_coeff)
+        gmapsym = np.ascontiguousarray(gmapsym, dtype=np.int32)
+        fo = _c16(np.atleast_1d(freq_out))
+        ngc = gmapsym.size
+        out = np.zeros((ngc, ngc, fo.size), dtype=np.complex128, order="F")
+        fb, _keep = freq_in.c()
+        self._chk(self._L.sgw_analytic_eval(self._h, int(model_coul), C.byref(fb), ngc, _p(gmapsym), _p(coeff), fo.size, _p(fo),
+                                            _p(out)), "analytic_eval")
+        return out[:, :, 0] if np.ndim(freq_out) == 0 else out
+
+    # ---- data/fft fft6 + phys/corr sigma (SURVEY 8 f2) ----------------------------------------------------
+    def set_corr_grid(self, nr, nl):
+        nl = np.ascontiguousarray(nl, dtype=np.int32)
+        self._chk(self._L.sgw_set_corr_grid(self._h, int(nr[0]), int(nr[1]), int(nr[2]), nl.size, _p(nl)), "set_corr_grid")
+
+    def invfft6(self, f, omega):
+        """fft6.f90:231 in place on f(nnr_c, nnr_c) (F-ordered complex128)."""
+        assert f.flags.f_contiguous and f.dtype == np.complex128
+        self._chk(self._L.sgw_invfft6(self._h, float(omega), _p(f)), "invfft6")
+
+    def fwfft6(self, f, omega):
+        """fft6.f90:84 in place; the result is f[:ngm_c, :ngm_c]."""
+        assert f.flags.f_contiguous and f.dtype == np.complex128
+        self._chk(self._L.sgw_fwfft6(self._h, float(omega), _p(f)), "fwfft6")
+
+    def sigma_correlation(self, omega, config: select_solver_type, slot, mu, alpha, model_coul, freq: "freqbins_type", map_,
+                          gmapsym, coulomb, sigma):
+        """sigma.f90:528: sigma(ngm_c, ngm_c, num_sigma) += G W convolution for the operator in `slot`; in place."""
+        map_ = np.ascontiguousarray(map_, dtype=np.int32)
+        gmapsym = np.ascontiguousarray(gmapsym, dtype=np.int32)
+        coulomb = _c16(coulomb)
+        ngc = map_.size
+        assert sigma.flags.f_contiguous and sigma.dtype == np.complex128
+        if sigma.shape[2] != freq.num_sigma():
+            raise SgwError("frequency dimension of self energy not correct size")         # sigma.f90:633
+        if coulomb.shape[0] != ngc or coulomb.shape[1] != ngc:
+            raise SgwError("screened Coulomb not a square matrix")                        # sigma.f90:626
+        fb, _keep = freq.c()
+        cfg = config.c()
+        ierr = C.c_int32(0)
+        a = _lib.Cplx(float(np.real(alpha)), float(np.imag(alpha)))
+        self._chk(self._L.sgw_sigma_correlation(self._h, slot, C.byref(cfg), float(omega), float(mu), a, int(model_coul),
+                                                C.byref(fb), ngc, _p(map_), _p(gmapsym), _p(coulomb), _p(sigma), C.byref(ierr)),
+                  "sigma_correlation")
+        if ierr.value != 0:
+            raise SgwError(f"the linear solver for G did not converge (ierr={ierr.value})")   # green.f90:208
+        return sigma
 
     def bench_linear_op(self, slot, nvec, reps=10):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

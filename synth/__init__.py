@@ -420,3 +420,11 @@ def preset(name: str, xq=None, nk=2):
 def imag_freqs(n):
     """gw_c/gw.in imaginary grid: i * 0.15 n (n+1) eV -> Ry."""
     return np.array([1j * 0.15 * k * (k + 1) for k in range(n)]) / RYTOEV
+
+
+def corr_grid(sys: SynthSystem, ngc: int):
+    """The custom FFT type grid%corr_fft of the correlation cutoff (algo/grid/src/sigma_grid.f90): the smallest good
+    FFT box that holds the first `ngc` G vectors of the global list, and their 1-based positions `nl` in it."""
+    mill = sys.mill[:ngc]
+    nr = tuple(good_fft_order(2 * int(np.abs(mill[:, i]).max()) + 1) for i in range(3))
+    return nr, _nl_of_mill(mill, np.asarray(nr))

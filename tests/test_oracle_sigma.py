@@ -1,0 +1,136 @@
+"""The numpy oracle of SURVEY 8 rows f2/f3 (oracle/sigma.py) against independent formulas.  The reference has no unit test
+for pade_coeff/pade_eval, godby_needs, fft6 or sigma_prod (algo/analytic/test/pade.pf covers pade_robust only), so
+these properties are what anchors the restatement."""
+import numpy as np
+import pytest
+
+from oracle import sigma as osg
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_gauleg_matches_numpy():
+    for n in (1, 2, 5, 12, 35):
+        x, w = osg.gauleg_grid(0.0, 7.3, n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.allclose(x, 3.65 + 3.65 * xr, atol=1e-12)
+        assert np.allclose(w, 3.65 * wr, atol=1e-12)
+
+
+def test_freqbins_symm():
+    solver = np.array([0.0, 0.3j, 0.9j])
+    arr = np.zeros((2, 2, 5), complex)
+    arr[:, :, :3] = np.arange(12).reshape(2, 2, 3)
+    z = osg.freqbins_symm(solver, osg.EVEN_SYMMETRY, arr)
+    assert np.allclose(z, [0, 0.3j, 0.9j, -0.3j, -0.9j])
+    assert np.allclose(arr[:, :, 3], arr[:, :, 1]) and np.allclose(arr[:, :, 4], arr[:, :, 2])
+    assert np.allclose(osg.freqbins_symm(solver, osg.SQUARE_SYMMETRY), solver ** 2)
+    assert np.allclose(osg.freqbins_symm(solver, osg.NO_SYMMETRY), solver)
+    z2 = osg.freqbins_symm(np.array([0.2j, 0.5j]), osg.EVEN_SYMMETRY)          # no zero frequency: mesh doubles
+    assert np.allclose(z2, [0.2j, 0.5j, -0.2j, -0.5j])
+    with pytest.raises(ValueError):
+        osg.freqbins_symm(np.array([0.0, 0.0]), osg.EVEN_SYMMETRY)
+    f = osg.freqbins_type(solver, np.array([0.1j, 0.2j]), np.ones(2), np.array([0.0j]))
+    assert f.num_freq() == 5
+    assert np.allclose(f.green(1.0 + 0j), [1 + 0.1j, 1 + 0.2j, 1 - 0.1j, 1 - 0.2j])
+
+
+def test_pade_interpolates_and_continues():
+    """The continued fraction passes through its nodes, and recovers a rational function off the axis."""
+    rng = np.random.default_rng(3)
+    z = 1j * np.array([0.0, 0.2, 0.5, 0.9, 1.4, 2.0, 2.7, 3.5])
+    poles = np.array([1.1, 1.9])                     # 2 pole pairs: representable by the 8-node fraction
+    res = rng.standard_normal((4, 3, 2)) + 0.3
+    f = lambda w: (res[..., None] * 2 * poles[:, None] / (np.asarray(w) ** 2 - poles[:, None] ** 2)).sum(axis=-2)
+    u = f(z)
+    a = osg.pade_coeff(z, u)
+    for i, zi in enumerate(z):
+        assert _rel(osg.pade_eval(z, a, zi), u[..., i]) < 1e-10
+    w = 0.7 + 0.4j
+    assert _rel(osg.pade_eval(z, a, w), f([w])[..., 0]) < 1e-6
+    # scalar transliteration of pade.f90 against the vectorised form
+    N = z.size
+    g = np.zeros((N, N), complex)
+    uu = u[1, 2]
+    prot = lambda x: x if abs(x) > 1e-24 else 1e-24 + 0j
+    for p in range(N):
+        for i in range(p, N):
+            g[p, i] = prot(uu[i]) if p == 0 else prot((g[p - 1, p - 1] / g[p - 1, i] - g[p - 1, i] / g[p - 1, i]) / (z[i] - z[p - 1]))
+    assert np.array_equal(np.diag(g), a[1, 2])
+
+
+def test_godby_needs_reproduces_inputs():
+    rng = np.random.default_rng(5)
+    wp = 1.3
+    w0 = -(rng.random((5, 5)) + 0.5)
+    w1 = w0 * (0.2 + 0.5 * rng.random((5, 5)))       # same sign, smaller magnitude: a valid plasmon-pole pair
+    w0[0, 1] = w1[0, 1] = 0.3                        # W(0) = W(i wp): coefficient set to zero (godby_needs.f90:62)
+    c = np.stack([w0, w1], axis=2).astype(complex)
+    osg.godby_needs_coeffs(wp, c)
+    m0 = osg.godby_needs_model(0.0j, c)
+    m1 = osg.godby_needs_model(1j * wp, c)
+    mask = np.ones((5, 5), bool)
+    mask[0, 1] = False
+    assert _rel(m0[mask], w0[mask]) < 1e-12 and _rel(m1[mask], w1[mask]) < 1e-12
+    assert m0[0, 1] == 0 and c[0, 1, 0] == 0 and c[0, 1, 1] == 0
+
+
+def _grid(nr, ngc, seed=0):
+    rng = np.random.default_rng(seed)
+    nnr = int(np.prod(nr))
+    nl = np.sort(rng.choice(nnr, ngc, replace=False)) + 1
+    return osg.corr_fft_type(tuple(nr), nl.astype(np.int32))
+
+
+def test_fft6_matches_numpy_6d():
+    d = _grid((3, 4, 5), 17)
+    rng = np.random.default_rng(1)
+    nnr, ng = d.nnr, d.ngm
+    omega = 2.7
+    fg = rng.standard_normal((ng, ng)) + 1j * rng.standard_normal((ng, ng))
+    f = np.zeros((nnr, nnr), complex)
+    f[:ng, :ng] = fg
+    osg.invfft6(f, d, d, omega)
+    # independent: f(r,r') = 1/omega sum_{G,G'} e^{-iGr} f(G,G') e^{+iG'r'}  as one 6-D transform
+    box = np.zeros((nnr, nnr), complex)
+    box[np.ix_(d.nl - 1, d.nl - 1)] = fg
+    b6 = box.reshape(d.nr + d.nr, order="F")
+    r6 = np.fft.fftn(b6, axes=(0, 1, 2))
+    r6 = np.fft.ifftn(r6, axes=(3, 4, 5)) * nnr / omega
+    assert _rel(f, r6.reshape(nnr, nnr, order="F")) < 1e-12
+    osg.fwfft6(f, d, d, omega)
+    assert _rel(f[:ng, :ng], fg) < 1e-12            # round trip
+
+
+def test_sigma_prod_is_a_convolution():
+    """alpha * fwfft6(G(r,r') W(r,r')) = alpha/omega sum G(G1,G1') W(G-G1, G'-G1') on the (aliased) box."""
+    nr = (3, 3, 2)
+    d = osg.corr_fft_type(nr, np.arange(1, 19, dtype=np.int32))       # every box point is a G vector: no pruning
+    nnr = d.nnr
+    rng = np.random.default_rng(2)
+    G = rng.standard_normal((nnr, nnr)) + 1j * rng.standard_normal((nnr, nnr))
+    W = rng.standard_normal((nnr, nnr)) + 1j * rng.standard_normal((nnr, nnr))
+    omega, alpha = 1.9, 0.3 - 0.2j
+    Gr = G.copy()
+    osg.invfft6(Gr, d, d, omega)
+    work = W.copy()
+    osg.sigma_prod(omega, d, d, alpha, Gr, work)
+    idx = np.array([[i, j, k] for k in range(nr[2]) for j in range(nr[1]) for i in range(nr[0])])
+    lin = lambda m: (m[..., 0] % nr[0]) + nr[0] * ((m[..., 1] % nr[1]) + nr[1] * (m[..., 2] % nr[2]))
+    ref = np.zeros((nnr, nnr), complex)
+    for a in range(nnr):
+        da = lin(idx[a][None, :] - idx)              # G - G1 for all G1
+        for b in range(nnr):
+            db = lin(idx[b][None, :] - idx)
+            ref[a, b] = (G * W[np.ix_(da, db)]).sum()
+    assert _rel(work, alpha / omega * ref) < 1e-12
+
+
+def test_qp_eigval_linearisation():
+    w = np.linspace(-2, 2, 41)
+    sig = 0.1 - 0.25 * w
+    e, z = osg.qp_eigval(w, sig, 0.33)
+    assert abs(z - 1 / 1.25) < 1e-12 and abs(e - (0.33 + z * (0.1 - 0.25 * 0.33))) < 1e-12
+    assert osg.qp_eigval(w, sig, 5.0) == (5.0, 1.0)
