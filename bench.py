@@ -212,6 +212,82 @@ def h2d_bytes(syn, fiu, igu):
     return int(n)
 
 
+# ----------------------------------------------------------------------------------------------------- Sigma_c leg
+def sigma_c_leg(device, f64_peak, reps=3):
+    """SURVEY 8 f2/f3 measured: one sigma_correlation call (sigma.f90:528) at the sizes of examples/example01_Si
+    (20^3 grid, npw ~ 283, 59 correlation G vectors on a 6^3 box, 51 integration frequencies -> 102 Green's-function
+    frequencies, 35 solver frequencies -> Pade on 69 points, 11 self-energy frequencies).  The reference prints
+    'G: 3.9-5.3 s  G*W: 7.0-7.9 s' per (k, q) configuration for this case (examples/example01_Si/gw.ref:10328)."""
+    import oracle
+    import synth
+    from oracle import sigma as osg
+    from sternheimergw_b200 import Context, freqbins_type, select_solver_type
+    syn = synth.preset("si", nk=1)
+    kq = syn.kpairs[0].kq
+    ngc, ncoul, nsig, nsolver = 59, 51, 11, 35
+    nr_c, nl_c = synth.corr_grid(syn, ngc, nr=(6, 6, 6))
+    nnr = int(np.prod(nr_c))
+    pos = {int(g): i + 1 for i, g in enumerate(kq.igk)}
+    map_ = np.array([pos.get(ig, 0) for ig in range(1, ngc + 1)], dtype=np.int32)
+    mu = 0.5 * (kq.et[syn.nbnd_occ - 1] + kq.et[syn.nbnd_occ])
+    fo = osg.freqbins(True, 0.0, 100.0 / synth.RYTOEV, nsig, 200.0 / synth.RYTOEV, ncoul, synth.imag_freqs(nsolver))
+    fh = freqbins_type(fo.solver, fo.coul, fo.weight, fo.sigma, fo.freq_symm_coul, True)
+    nsym = fo.num_freq()
+    rng = np.random.default_rng(synth.SEED)
+    poles = np.array([0.9, 1.7, 2.9])
+    res = rng.standard_normal((ngc, ngc, 3)) * 0.05 + np.eye(ngc)[:, :, None]
+    coul = np.zeros((ngc, ngc, nsym), complex, order="F")
+    coul[:, :, :nsolver] = -(res[..., None] * 2 * poles[:, None] / (fo.solver ** 2 - poles[:, None] ** 2)).sum(axis=-2)
+    gmapsym = np.arange(1, ngc + 1, dtype=np.int32)
+    alpha = -1.0 / (2 * np.pi)
+    ctx = Context(device)
+    ctx.install_system(syn)
+    ctx.set_corr_grid(nr_c, nl_c)
+    ctx.set_profiling(True)
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-5)            # thres_green default
+    coeff = ctx.analytic_coeff(osg.PADE_APPROX, 1e-4, fh, coul)
+    nb = 2 * ncoul
+    best = None
+    for _ in range(reps):
+        sig = np.zeros((ngc, ngc, nsig), complex, order="F")
+        t0 = time.perf_counter()
+        ctx.sigma_correlation(syn.omega_cell, cfg, 0, mu, alpha, osg.PADE_APPROX, fh, map_, gmapsym, coeff, sig)
+        wall = 1e3 * (time.perf_counter() - t0)
+        st, prof = ctx.stats(), ctx.profile()
+        if best is None or wall < best["wall_ms"]:
+            best = {"wall_ms": wall, "ms_total": st["ms_total"], "ms_green_solver": st["ms_solver"], "prof": prof,
+                    "launches": int(st["n_kernel_launch"]), "linear_op": int(st["n_linear_op"])}
+    gw = best["prof"].get("gw_product", {"ms": 0.0, "regions": 0})
+    flop = 8.0 * nnr * nnr * ngc * nb * nsig
+    out = {"workload": f"examples/example01_Si sizes: FFT 20^3, npw {kq.npw}, {ngc} correlation G on a {nr_c[0]}^3 box, {nb} Green "
+                       f"frequencies, {nsym}-point Pade of W, {nsig} Sigma frequencies; one (k, q) configuration",
+           "products": nsig * nb, "wall_ms": best["wall_ms"], "device_ms": best["ms_total"],
+           "green_solver_ms": best["ms_green_solver"], "gpu_launches": best["launches"], "linear_op": best["linear_op"],
+           "gw_product": {"kernel": "k_gw_product (second half of invfft6 + product with G(r,r') + sum over omega_green)",
+                          "bound": "tensor", "ms": gw["ms"], "launches": gw["regions"],
+                          "achieved": flop / (gw["ms"] * 1e-3) / 1e12 if gw["ms"] > 0 else None, "peak": f64_peak, "unit": "TFLOP/s",
+                          "frac": flop / (gw["ms"] * 1e-3) / 1e12 / f64_peak if gw["ms"] > 0 else None,
+                          "algorithmic_flop_per_launch": flop / max(1, gw["regions"])},
+           "reference_2017": "G: 3.9-5.3 s, G*W: 7.0-7.9 s per (k, q) configuration (examples/example01_Si/gw.ref:10328, CPU of that run)"}
+    del ctx
+    # CPU oracle (numpy restatement of sigma_prod with per-column FFTs, fft6.f90) on a bounded sample of the products
+    d = osg.corr_fft_type(tuple(nr_c), nl_c)
+    green_r = np.asfortranarray(rng.standard_normal((nnr, nnr)) + 1j * rng.standard_normal((nnr, nnr)))
+    nsample, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 5.0:
+        work = np.zeros((nnr, nnr), complex, order="F")
+        work[:ngc, :ngc] = osg.analytic_eval(osg.PADE_APPROX, gmapsym, fo, coeff, 0.3j + 0.01 * nsample)
+        osg.sigma_prod(syn.omega_cell, d, d, alpha, green_r, work)
+        nsample += 1
+    dt = time.perf_counter() - t0
+    out["cpu_oracle"] = {"products_per_s": nsample / dt, "kind": "port", "cores": 1,
+                         "sample": f"{nsample} analytic_eval + sigma_prod products in {dt:.1f} s (numpy, one thread)"}
+    gw_ms = best["ms_total"] - best["ms_green_solver"]
+    out["gw_products_per_s"] = nsig * nb / (gw_ms * 1e-3) if gw_ms > 0 else None
+    out["note"] = "gw_products_per_s counts everything after the Green's-function solve: 6-D transform of G, analytic_eval, products, forward transforms"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +296,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pert", type=int, default=8, help="perturbations per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sigma", action="store_true", help="skip the Sigma_c (SURVEY 8 f2/f3) leg")
+    ap.add_argument("--sigma-only", action="store_true", help="run only the Sigma_c leg and print its record (profiling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +311,9 @@ def main():
     from sternheimergw_b200 import Context, select_solver_type
     from sternheimergw_b200.dist import gather_columns
     torch.cuda.set_device(local_rank)
+    if args.sigma_only:
+        print(json.dumps({"sigma_c": sigma_c_leg(local_rank, zgemm_peak_tflops())}), flush=True)
+        return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its debug lines (the "NCCL version ..." banner at level >= VERSION) to stdout by default: route them
@@ -401,6 +482,13 @@ def main():
             "roofline": roofline, "kernels": kernels, "hpsi_fft": hpsi_fft, "fp64_zgemm_peak_tflops": f64_peak,
             "rho_grid": {"reduced": bool(ctx.rho_grid()[0]), "dims": list(ctx.rho_grid()[1]),
                          "note": "Delta-rho accumulated on the alias-free reduced box (sgw_get_rho_grid, DESIGN.md section 4)"}}
+    if world == 1 and not args.no_sigma:
+        del ctx
+        ctx = None
+        try:
+            line["sigma_c"] = sigma_c_leg(local_rank, f64_peak)
+        except Exception as e:                                  # the headline line must survive a failure of the extra leg
+            line["sigma_c"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         del ctx
         cb = cpu_sample(syn, fiu, ngc, igu, steps=1, warmup=0)

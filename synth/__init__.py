@@ -422,9 +422,12 @@ def imag_freqs(n):
     return np.array([1j * 0.15 * k * (k + 1) for k in range(n)]) / RYTOEV
 
 
-def corr_grid(sys: SynthSystem, ngc: int):
+def corr_grid(sys: SynthSystem, ngc: int, nr=None):
     """The custom FFT type grid%corr_fft of the correlation cutoff (algo/grid/src/sigma_grid.f90): the smallest good
-    FFT box that holds the first `ngc` G vectors of the global list, and their 1-based positions `nl` in it."""
+    FFT box that holds the first `ngc` G vectors of the global list (or the box `nr` given), and their 1-based
+    positions `nl` in it."""
     mill = sys.mill[:ngc]
-    nr = tuple(good_fft_order(2 * int(np.abs(mill[:, i]).max()) + 1) for i in range(3))
-    return nr, _nl_of_mill(mill, np.asarray(nr))
+    if nr is None:
+        nr = tuple(good_fft_order(2 * int(np.abs(mill[:, i]).max()) + 1) for i in range(3))
+    assert all(nr[i] >= 2 * int(np.abs(mill[:, i]).max()) + 1 for i in range(3)), "box too small for these G vectors"
+    return tuple(nr), _nl_of_mill(mill, np.asarray(nr))

@@ -48,3 +48,33 @@ def test_roundtrip_of_an_inverted_epsilon_through_the_oracle(tmp_path):
     back = wfile.read_w_record(path, 2, ngc, nfs)
     assert np.array_equal(back, w)
     assert np.count_nonzero(np.fromfile(path, dtype="<f8")[:wfile.lrcoul(ngc, nfs)]) == 0   # record 1 not written yet: zeros
+
+
+def test_sigma_and_wfc_records_roundtrip(tmp_path):
+    """Sigma_c records (sigma.f90:391-394: irec = (ikpt-1) num_sigma + ifreq, lrsigma = 2 ngc^2 reals) and the wavefunction
+    buffer (openfilq.f90:55: lrwfc = nbnd npwx npol complex words)."""
+    import numpy as np
+    from sternheimergw_b200 import wfile
+    rng = np.random.default_rng(0)
+    ngc, nsig = 5, 3
+    p = str(tmp_path / "_gw0" / "si.sigma1")
+    s1 = rng.standard_normal((ngc, ngc, nsig)) + 1j * rng.standard_normal((ngc, ngc, nsig))
+    s2 = rng.standard_normal((ngc, ngc, nsig)) + 1j * rng.standard_normal((ngc, ngc, nsig))
+    wfile.write_sigma_c(p, 2, s2)            # out of order, like images finishing at different times
+    wfile.write_sigma_c(p, 1, s1)
+    assert np.array_equal(wfile.read_sigma_c(p, 1, ngc, nsig), s1)
+    assert np.array_equal(wfile.read_sigma_c(p, 2, ngc, nsig), s2)
+    import os
+    assert os.path.getsize(p) == 2 * nsig * wfile.lrsigma(ngc) * 8
+    # raw layout: record 4 (= k 2, frequency 1) holds s2[:, :, 0] column-major
+    raw = np.fromfile(p, dtype="<c16")
+    assert np.array_equal(raw[3 * ngc * ngc:4 * ngc * ngc], s2[:, :, 0].ravel(order="F"))
+    w = str(tmp_path / "si.wfc")
+    npwx, nbnd = 7, 4
+    evc = rng.standard_normal((npwx, nbnd)) + 1j * rng.standard_normal((npwx, nbnd))
+    wfile.write_wfc_record(w, 3, evc)
+    assert np.array_equal(wfile.read_wfc_record(w, 3, npwx, nbnd), evc)
+    assert os.path.getsize(w) == 3 * wfile.lrwfc(nbnd, npwx) * 16
+    import pytest
+    with pytest.raises(IOError):
+        wfile.read_wfc_record(w, 4, npwx, nbnd)
