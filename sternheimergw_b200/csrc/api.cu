@@ -155,6 +155,8 @@ int sgw_destroy(sgw_ctx *ctx) {
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) if (ctx->ev_iter[i]) cudaEventDestroy(ctx->ev_iter[i]);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->corr.d_Ec) cudaFree(ctx->corr.d_Ec);
+  if (ctx->corr.d_ET) cudaFree(ctx->corr.d_ET);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SGW_OK;

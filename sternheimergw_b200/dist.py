@@ -84,3 +84,45 @@ def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, i
     if invert_fn is not None:
         scr_g = invert_fn(scr_g, lgamma=lgamma)                                    # :232
     return scr_g, (first, last, num_task)
+
+
+def root_sum(a: np.ndarray, root: int = 0, device=None):
+    """mp_root_sum(comm, root, array) (data/parallel/src/parallel.f90, used at sigma.f90:362,383): element-wise sum
+    over ranks, result on ``root`` (None elsewhere).  One reduce of the Sigma(k, omega) block per k-point: the only
+    collective of the Sigma stage (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return a
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.float64).copy()).to(dev)
+    dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+    if dist.get_rank() != root:
+        return None
+    return np.ascontiguousarray(t.cpu().numpy()).view(np.complex128).reshape(a.shape)
+
+
+def sigma_wrapper_k(sigma_correlation_fn, configs, num_g_corr, num_sigma, root: int = 0):
+    """The k-point loop body of sigma_wrapper (phys/corr/src/sigma.f90:319-362) over ranks.
+
+    ``configs``: the (k, q) configurations of this k-point (sigma.f90 ``config(:)``: index_kq, index_q, sym_op, weight).
+    The reference gives every pool the whole list and distributes G' over images inside each product; here the
+    configurations themselves are dealt to the ranks with ``parallel_task``'s block rule (one rank = one GPU, every
+    product runs entirely on one device), each rank accumulates its share into a local sigma and ``root_sum`` adds
+    the shares on the root -- the allreduce of Sigma(k, omega) contributions.
+
+    sigma_correlation_fn(config, sigma) accumulates one configuration in place (normally a closure around
+    ``Context.sigma_correlation``).  Returns (sigma on root | None, (first, last, num_task)).
+    """
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    first, last, num_task = parallel_task(world, rank, len(configs))
+    sigma = np.zeros((num_g_corr, num_g_corr, num_sigma), dtype=np.complex128, order="F")
+    for icon in range(first - 1, first - 1 + num_task[rank]):
+        sigma_correlation_fn(configs[icon], sigma)
+    total = root_sum(np.ascontiguousarray(np.transpose(sigma, (2, 1, 0))), root=root)
+    if total is None:
+        return None, (first, last, num_task)
+    return np.asfortranarray(np.transpose(total, (2, 1, 0))), (first, last, num_task)

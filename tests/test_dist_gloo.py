@@ -86,3 +86,53 @@ def test_do_stern_split_and_gather(world, ngmunique, expect):
             assert scr is not None and np.array_equal(scr, serial)          # bit-exact: a gather moves bytes only
         else:
             assert scr is None
+
+
+def _fake_sigma_correlation(config, sigma):
+    """Deterministic stand-in with integer-valued contributions, so that the rank-wise sum is bit-exact."""
+    ngc, _, nsig = sigma.shape
+    g = np.arange(ngc)
+    for i in range(nsig):
+        sigma[:, :, i] += (config["index_kq"] * 7 + i) * (np.add.outer(g, 2 * g) + 1j * np.subtract.outer(g, g)) * config["weight"]
+
+
+def _sigma_worker(rank, world, port, ncon, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sternheimergw_b200.dist import sigma_wrapper_k
+        configs = [{"index_kq": c + 1, "weight": 2 ** (c % 3)} for c in range(ncon)]
+        sig, (first, last, num_task) = sigma_wrapper_k(_fake_sigma_correlation, configs, 5, 3)
+        q.put((rank, first, last, num_task, None if sig is None else sig.copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ncon,expect", [(2, 7, [3, 4]), (3, 2, [0, 1, 1])])
+def test_sigma_configurations_dealt_and_summed(world, ncon, expect):
+    """Sigma stage over ranks: (k, q) configurations dealt with parallel_task's rule, shares added by root_sum
+    (mp_root_sum of sigma.f90:362) -- the only collective of that stage."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sigma_worker, args=(r, world, port, ncon, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    serial = np.zeros((5, 5, 3), dtype=np.complex128, order="F")
+    for c in range(ncon):
+        _fake_sigma_correlation({"index_kq": c + 1, "weight": 2 ** (c % 3)}, serial)
+    for r in range(world):
+        _, first, last, num_task, sig = res[r]
+        assert list(num_task) == expect
+        if r == 0:
+            assert sig is not None and np.array_equal(sig, serial)
+        else:
+            assert sig is None
