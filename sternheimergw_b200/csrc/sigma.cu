@@ -177,6 +177,7 @@ __global__ void k_block_copy(int ngm, long ld_src, long ld_dst, const cplx *__re
 // real-space W never exists in memory.  The G tile of entry b is prefetched into registers before the K loop of b.
 constexpr int GW_BM = 64, GW_BN = 32, GW_BK = 16, GW_T = 256;
 constexpr int GW_PK = GW_BK + 4, GW_PM = GW_BM + 2;
+constexpr int GW_CTA_PER_SM = 1;   // __launch_bounds__(GW_T, 1): 240 registers, no spills (2 per SM at 128 registers measured equal)
 constexpr size_t GW_SMEM = (size_t)2 * (GW_BK * GW_PM + GW_BN * GW_PK) * sizeof(cplx);
 
 __global__ void __launch_bounds__(GW_T, 1) k_gw_product(int M, int N, int K, int nb, int bchunk, const cplx *__restrict__ X,
@@ -635,12 +636,21 @@ int sgw_sigma_correlation(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg_gree
   SGW_CUDA(cudaMemcpyAsync(d_cf, ctab.data(), sizeof(cplx) * ctab.size(), cudaMemcpyHostToDevice, st));
   SGW_CUDA(cudaMemcpyAsync(d_sigma, sigma, sizeof(cplx) * npair * nsig, cudaMemcpyHostToDevice, st));
 
-  // batch split of the product kernel: fill the machine when the tile grid alone is smaller than one wave
+  // batch split of the product kernel in whole waves: CTA count = tiles x nz, GW_CTA_PER_SM resident CTAs per SM;
+  // a CTA handles ceil(nb / nz) entries, so the time is ~ waves(nz) x ceil(nb / nz) entry-times: take the minimum
   const int tiles = ((nnr + GW_BM - 1) / GW_BM) * ((nnr + GW_BN - 1) / GW_BN);
-  int nz = std::max(1, std::min(nb, (2 * ctx->sm_count + tiles - 1) / tiles));
-  nz = std::min(nz, 16);
-  const int bchunk = (nb + nz - 1) / nz;
-  nz = (nb + bchunk - 1) / bchunk;
+  int nz = 1, bchunk = nb;
+  {
+    long best = -1;
+    for (int cand = 1; cand <= std::min(nb, 64); ++cand) {
+      const int bc = (nb + cand - 1) / cand;
+      const int z = (nb + bc - 1) / bc;
+      const long slots = (long)ctx->sm_count * GW_CTA_PER_SM;
+      const long waves = ((long)tiles * z + slots - 1) / slots;
+      const long cost = waves * bc;
+      if (best < 0 || cost < best) { best = cost; nz = z; bchunk = bc; }
+    }
+  }
   SGW_CHECK(ws(ctx, "sg_part", (size_t)nnr * nnr * nz, &d_part));
   SGW_CHECK(ws(ctx, "sg_acc", (size_t)nnr * nnr, &d_acc));
   if (!ctx->gw_attr_set) {
