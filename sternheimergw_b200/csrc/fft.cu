@@ -105,63 +105,76 @@ __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zp
   }
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, bool ONE>
 __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
                                                      cplx *__restrict__ Tout, const double *__restrict__ vperm,
                                                      const cplx *__restrict__ field, int vec_per_field, cplx *R,
-                                                     int in_mod, const int *__restrict__ active) {
+                                                     int in_mod, const int *__restrict__ active, int Prt) {
+  const int P = ONE ? 1 : Prt;        // ONE: single-plane instantiation (large boxes), plane loops fold away
+  // One CTA = P consecutive z-planes of one vector, stacked in shared memory (plane p at offset p * ny * pitch, so the
+  // rows of all planes form ONE set of np * ny lines with stride `pitch` and the potential rows v[pz0 * nxy + l * nx]
+  // stay contiguous).  P = 1 for large boxes (72^2 fills the CTA); small boxes (15^2..24^2) pack up to 8 planes so that
+  // the radix stages have enough butterflies for every thread.
   // in_mod > 0: the INPUT (Tin or R) of vector `vec` is input vector vec % in_mod (one set of bands shared by
   // every perturbation, dvqpsi_us.f90:99-130)
-  const int vec = blockIdx.y, pz = blockIdx.x;
+  const int vec = blockIdx.y, pz0 = blockIdx.x * P;
+  const int np = ONE ? 1 : min(P, g.nz - pz0);
   const int vin = in_mod > 0 ? vec % in_mod : vec;
   if (active && !active[vec]) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   extern __shared__ cplx sm[];
   const int pitch = g.pitchx, nx = g.nx, ny = g.ny;
+  const int psz = ny * pitch;
   cplx *plane = sm;
-  cplx *twx = sm + ny * pitch;
+  cplx *twx = sm + P * psz;
   cplx *twy = twx + nx;
-  int *xs_in = (int *)(twy + ny), *xs_out = xs_in + nx;     // x columns that hold data, staged on chip
+  int *ids_in = (int *)(twy + ny), *ids_out = ids_in + P * nx;   // line starts of the x columns that hold data, all planes
   for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
   for (int i = tid; i < ny; i += nt) twy[i] = g.twy[i];
-  if (MODE != PLANE_FROM_R) for (int i = tid; i < sin.nxs; i += nt) xs_in[i] = sin.xs[i];
-  if (MODE != PLANE_TO_R) for (int i = tid; i < sout.nxs; i += nt) xs_out[i] = sout.xs[i];
+  if (MODE != PLANE_FROM_R)
+    for (int i = tid; i < np * sin.nxs; i += nt) ids_in[i] = ONE ? sin.xs[i] : (i / sin.nxs) * psz + sin.xs[i % sin.nxs];
+  if (MODE != PLANE_TO_R)
+    for (int i = tid; i < np * sout.nxs; i += nt) ids_out[i] = ONE ? sout.xs[i] : (i / sout.nxs) * psz + sout.xs[i % sout.nxs];
   const long nxy = (long)nx * ny;
+  const int nrows = np * ny;
 
   if (MODE != PLANE_FROM_R) {
-    for (int i = tid; i < ny * pitch; i += nt) plane[i] = cmake(0.0, 0.0);
+    for (int i = tid; i < np * psz; i += nt) plane[i] = cmake(0.0, 0.0);
     __syncthreads();
-    const cplx *row = Tin + ((long)vin * g.nz + pz) * sin.ncol;
-    for (int c = tid; c < sin.ncol; c += nt) plane[sin.col_off[c]] = row[c];
+    const cplx *row = Tin + ((long)vin * g.nz + pz0) * sin.ncol;
+    for (int i = tid; i < np * sin.ncol; i += nt) {
+      const int p = ONE ? 0 : i / sin.ncol, c = i - p * sin.ncol;
+      plane[p * psz + sin.col_off[c]] = row[i];
+    }
     __syncthreads();
     // inverse along y for the x columns that hold data (x still in natural order)
-    run_strided<+1>(g.ry1, plane, sin.nxs, xs_in, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
+    run_strided<+1>(g.ry1, plane, np * sin.nxs, ids_in, 1, pitch, g.ry2, twy, g.ry2 > 1, tid, nt);
     __syncthreads();
     if (g.ry2 > 1) {
-      run_contig<+1>(g.ry2, plane, sin.nxs, xs_in, 1, pitch, g.ry1, twy, false, tid, nt);
+      run_contig<+1>(g.ry2, plane, np * sin.nxs, ids_in, 1, pitch, g.ry1, twy, false, tid, nt);
       __syncthreads();
     }
     if (MODE == PLANE_VLOC || MODE == PLANE_FIELD) {
       // inverse along x, x v(r), forward along x: the last inverse stage, the product and the first forward stage
       // touch the same contiguous radix group of a row -> one register round trip (fft_core.h stage_mid)
-      const double *v = MODE == PLANE_VLOC ? vperm + (long)pz * nxy : nullptr;
-      const cplx *f = MODE == PLANE_FIELD ? field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy : nullptr;
+      const double *v = MODE == PLANE_VLOC ? vperm + (long)pz0 * nxy : nullptr;
+      const cplx *f = MODE == PLANE_FIELD ? field + ((long)(vec / vec_per_field) * g.nz + pz0) * nxy : nullptr;
       if (g.rx2 > 1) {
-        run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, true, tid, nt);
+        run_strided<+1>(g.rx1, plane, nrows, nullptr, pitch, 1, g.rx2, twx, true, tid, nt);
         __syncthreads();
-        run_mid<MODE == PLANE_FIELD>(g.rx2, plane, ny, pitch, g.rx1, twx, true, v, f, nx, tid, nt);
+        run_mid<MODE == PLANE_FIELD>(g.rx2, plane, nrows, pitch, g.rx1, twx, true, v, f, nx, tid, nt);
         __syncthreads();
-        run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
+        run_strided<-1>(g.rx1, plane, nrows, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
       } else {
-        run_mid<MODE == PLANE_FIELD>(g.rx1, plane, ny, pitch, 1, twx, false, v, f, nx, tid, nt);
+        run_mid<MODE == PLANE_FIELD>(g.rx1, plane, nrows, pitch, 1, twx, false, v, f, nx, tid, nt);
       }
       __syncthreads();
     } else {
       // inverse along x for all rows
-      run_strided<+1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
+      run_strided<+1>(g.rx1, plane, nrows, nullptr, pitch, 1, g.rx2, twx, g.rx2 > 1, tid, nt);
       __syncthreads();
       if (g.rx2 > 1) {
-        run_contig<+1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
+        run_contig<+1>(g.rx2, plane, nrows, nullptr, pitch, 1, g.rx1, twx, false, tid, nt);
         __syncthreads();
       }
     }
@@ -172,22 +185,22 @@ __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, Spher
   if (MODE == PLANE_VLOC || MODE == PLANE_FIELD) {
     // x transforms and the product are done (fused above)
   } else if (MODE == PLANE_TO_R) {
-    cplx *r = R + ((long)vec * g.nz + pz) * nxy;
-    for (int i = tid; i < nx * ny; i += nt) {
+    cplx *r = R + ((long)vec * g.nz + pz0) * nxy;
+    for (int i = tid; i < nx * nrows; i += nt) {
       const int ix = i % nx, iy = i / nx;
       r[i] = plane[iy * pitch + ix];
     }
     return;
   } else {  // PLANE_FROM_R (optionally times a complex field: dV_bare(r) psi(r))
-    const cplx *r = R + ((long)vin * g.nz + pz) * nxy;
+    const cplx *r = R + ((long)vin * g.nz + pz0) * nxy;
     if (field) {
-      const cplx *f = field + ((long)(vec / vec_per_field) * g.nz + pz) * nxy;
-      for (int i = tid; i < nx * ny; i += nt) {
+      const cplx *f = field + ((long)(vec / vec_per_field) * g.nz + pz0) * nxy;
+      for (int i = tid; i < nx * nrows; i += nt) {
         const int ix = i % nx, iy = i / nx;
         plane[iy * pitch + ix] = cmul(f[i], r[i]);
       }
     } else {
-      for (int i = tid; i < nx * ny; i += nt) {
+      for (int i = tid; i < nx * nrows; i += nt) {
         const int ix = i % nx, iy = i / nx;
         plane[iy * pitch + ix] = r[i];
       }
@@ -197,25 +210,26 @@ __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, Spher
     __syncthreads();
     // forward along x (permuted in -> natural out), all rows
     if (g.rx2 > 1) {
-      run_contig<-1>(g.rx2, plane, ny, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
+      run_contig<-1>(g.rx2, plane, nrows, nullptr, pitch, 1, g.rx1, twx, true, tid, nt);
       __syncthreads();
     }
-    run_strided<-1>(g.rx1, plane, ny, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
+    run_strided<-1>(g.rx1, plane, nrows, nullptr, pitch, 1, g.rx2, twx, false, tid, nt);
     __syncthreads();
   }
   // forward along y only for the x columns of the output sphere
   if (g.ry2 > 1) {
-    run_contig<-1>(g.ry2, plane, sout.nxs, xs_out, 1, pitch, g.ry1, twy, true, tid, nt);
+    run_contig<-1>(g.ry2, plane, np * sout.nxs, ids_out, 1, pitch, g.ry1, twy, true, tid, nt);
     __syncthreads();
   }
-  run_strided<-1>(g.ry1, plane, sout.nxs, xs_out, 1, pitch, g.ry2, twy, false, tid, nt);
+  run_strided<-1>(g.ry1, plane, np * sout.nxs, ids_out, 1, pitch, g.ry2, twy, false, tid, nt);
   __syncthreads();
-  cplx *orow = Tout + ((long)vec * g.nz + pz) * sout.ncol;
-  for (int c = tid; c < sout.ncol; c += nt) orow[c] = plane[sout.col_off[c]];
+  cplx *orow = Tout + ((long)vec * g.nz + pz0) * sout.ncol;
+  for (int i = tid; i < np * sout.ncol; i += nt) {
+    const int p = ONE ? 0 : i / sout.ncol, c = i - p * sout.ncol;
+    orow[i] = plane[p * psz + sout.col_off[c]];
+  }
 }
 
-// Last inverse stage along x fused with the accumulation  acc(r) += conj(psi_v(r)) dpsi(r)  ([QE] incdrhoscf):
-// the R outputs of a contiguous radix group stay in registers; dpsi(r) itself is never stored.
 template <int R>
 __device__ __forceinline__ void stage_acc(const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
                                           int tid, int nthreads) {
@@ -351,7 +365,14 @@ static int plane_threads() {
 }
 static size_t zpass_smem(const GridDev &g, int zcb) { return (size_t)(zcb * (g.nz | 1) + g.nz) * sizeof(cplx); }
 static size_t plane_smem(const GridDev &g, int nplanes) {
-  return (size_t)(nplanes * g.ny * g.pitchx + g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)g.nx * sizeof(int);
+  return (size_t)(nplanes * g.ny * g.pitchx + g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)nplanes * g.nx * sizeof(int);
+}
+// z-planes per CTA of k_plane: enough points (~4096) for every thread of the radix stages, at most 8 planes
+static int planes_per_cta(const GridDev &g) {
+  static int forced = -1;                                       // SGW_PPC: tuning knob (1..8)
+  if (forced < 0) { const char *e = getenv("SGW_PPC"); forced = e ? atoi(e) : 0; }
+  int p = forced >= 1 && forced <= 8 ? forced : std::max(1, std::min(8, 4096 / (g.nx * g.ny)));
+  return std::min(p, g.nz);
 }
 
 template <typename K>
@@ -407,15 +428,21 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
               const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
   GridDev g = grid_dev(ctx, gr);
-  const size_t smem = plane_smem(g, 1);
-  dim3 grid(g.nz, nvec);
+  const int P = planes_per_cta(g);
+  const size_t smem = plane_smem(g, P);
+  dim3 grid((g.nz + P - 1) / P, nvec);
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
   ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
 #define SGW_PLANE_LAUNCH(M, NT)                                                                                          \
   do {                                                                                                                  \
-    SGW_CHECK(set_smem(ctx, k_plane<M, NT>, smem));                                                                     \
-    k_plane<M, NT><<<grid, NT, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active); \
+    if (P == 1) {                                                                                                       \
+      SGW_CHECK(set_smem(ctx, k_plane<M, NT, true>, smem));                                                             \
+      k_plane<M, NT, true><<<grid, NT, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active, 1); \
+    } else {                                                                                                            \
+      SGW_CHECK(set_smem(ctx, k_plane<M, NT, false>, smem));                                                            \
+      k_plane<M, NT, false><<<grid, NT, smem, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, active, P); \
+    }                                                                                                                   \
   } while (0)
   const int nt = plane_threads();
   switch (mode) {

@@ -267,7 +267,10 @@ int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int m
       if (*h_count == 0) break;
       rc = apply_operator(ctx, sb.slot, sb.alpha_pv, s.nrhs, s.Rv, n, s.sigma + ishift, s.nshift, s.New, n, s.act);
       if (rc != SGW_OK) break;
-      if (total_cols + 1 > s.cap) {   // grow the subspace storage (the reference reallocates every iteration, :424-433)
+      // grow the subspace storage (the reference reallocates every iteration, :424-433).  total_cols is an upper bound over
+      // the batch; no right-hand side can hold more than n basis vectors (k_sub_residual stops it at m == n, :376-378), so
+      // a capacity of n columns never needs to grow
+      if (total_cols + 1 > s.cap && s.cap < s.n) {
         int ncap = s.cap * 2;
         if (ncap > s.n) ncap = s.n;
         if (ncap <= s.cap || (size_t)(ncap + 1) * sizeof(cplx) > ctx->smem_optin) {
