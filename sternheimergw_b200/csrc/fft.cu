@@ -22,12 +22,12 @@ namespace sgw {
 
 constexpr int ZCB_DEFAULT = 16; // columns per CTA in the z passes (template parameter ZCB of the kernels)
 constexpr int ZTHREADS = 256;   // launch bound; the launch uses zpass_threads()
-constexpr int ZMINB = 2;        // resident CTAs per SM the register allocation must allow
+constexpr int ZMINB16 = 6;      // resident CTAs per SM the register allocation of the ZCB <= 16 z-pass kernels must allow
 
 constexpr int PTHREADS = 256;
 
 template <int ZCB>
-__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
+__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16) k_zpass_g2r(GridDev g, SphereDev s, const cplx *__restrict__ in, long ld,
                                                          cplx *__restrict__ T, const int *__restrict__ active) {
   const int vec = blockIdx.y;
   if (active && !active[vec]) return;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zp
 }
 
 template <int ZCB>
-__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 2 : 4) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
+__global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
                                                          cplx *__restrict__ out, long ld, ZEpilogue epi, double scale,
                                                          const int *__restrict__ active) {
   const int vec = blockIdx.y;
@@ -356,7 +356,7 @@ static int zpass_threads(const sgw_ctx *ctx) {
   if (forced < 0) { const char *e = getenv("SGW_ZTHREADS"); forced = e ? atoi(e) : 0; }
   if (forced >= 32 && forced <= (zpass_zcb() >= 32 ? 256 : 160)) return forced;
   (void)ctx;
-  return 96;   // measured on B200 (Si64): 96 -> 58 ms, 128 -> 63 ms, 160 -> 73 ms per step; small CTAs keep more loads in flight
+  return 128;  // measured on B200 (Si64, 64-register build, >= 6 CTAs per SM): 96 -> 51.6 ms, 128 -> 49.6 ms, 160 -> 56.5 ms per step
 }
 static int plane_threads() {
   static int forced = -1;                                       // SGW_PTHREADS: tuning knob (256 | 384 | 512), default 384
