@@ -233,27 +233,56 @@ __global__ void __launch_bounds__(128) k_scal_alpha(BicgState s, int jj) {
 
 // ---------------------------------------------------------------- bicg_part vector updates
 // L8: u_i = r_i - beta u_i (i <= jj)     [ZSCAL(-beta) then ZAXPY(1, r_i)]
-__global__ void __launch_bounds__(BT) k_seed_u(BicgState s, int jj) {
+// JT >= 0: step index known at compile time (L <= 4): the loop unrolls and all loads of a thread are issued before the
+// first store (more bytes in flight for these pure HBM streams); JT = -1: generic
+template <int JT>
+__global__ void __launch_bounds__(BT) k_seed_u(BicgState s, int jj_rt) {
+  const int jj = JT >= 0 ? JT : jj_rt;
   const int b = blockIdx.y;
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n || !s.active[b]) return;
   const cplx mbeta = cneg(s.seed[b].beta);
+  if (JT >= 0) {
+    cplx uu[JT >= 0 ? JT + 1 : 1], rr[JT >= 0 ? JT + 1 : 1];
+#pragma unroll
+    for (int i = 0; i <= JT; ++i) { uu[i] = seedU(s, b, i)[e]; rr[i] = seedR(s, b, i)[e]; }
+#pragma unroll
+    for (int i = 0; i <= JT; ++i) seedU(s, b, i)[e] = cadd(cmul(mbeta, uu[i]), rr[i]);
+    return;
+  }
   for (int i = 0; i <= jj; ++i) {
     cplx *u = seedU(s, b, i);
     u[e] = cadd(cmul(mbeta, u[e]), seedR(s, b, i)[e]);
   }
 }
-
-// Seed part of step jj between the two operator applications: L22 r_i -= alpha u_{i+1} (i<=jj); L25 x += alpha u_0.
-// The residuals the shifted systems will need for THIS step (r_i before the update, and r_{L-1} after the last
-// one) are kept as snapshots; the shifted updates themselves are deferred to k_shift_fused.
-__global__ void __launch_bounds__(BT) k_bicg_update(BicgState s, int jj) {
+template <int JT>
+__global__ void __launch_bounds__(BT) k_bicg_update(BicgState s, int jj_rt) {
+  const int jj = JT >= 0 ? JT : jj_rt;
   const int b = blockIdx.y;
   if (!s.active[b]) return;
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n) return;
   const cplx alpha = s.seed[b].alpha, malpha = cneg(alpha);
   const bool keep = s.ns > 0;
+  if (JT >= 0) {
+    cplx ro[JT >= 0 ? JT + 1 : 1], un[JT >= 0 ? JT + 2 : 1];
+#pragma unroll
+    for (int i = 0; i <= JT + 1; ++i) un[i] = seedU(s, b, i)[e];
+#pragma unroll
+    for (int i = 0; i <= JT; ++i) ro[i] = seedR(s, b, i)[e];
+    const cplx x_old = seedX(s, b)[e];
+#pragma unroll
+    for (int i = 0; i <= JT; ++i) {
+      const cplx r_new = cfma(malpha, un[i + 1], ro[i]);                      // :676
+      seedR(s, b, i)[e] = r_new;
+      if (keep) {
+        snap(s, b, JT * (JT + 1) / 2 + i)[e] = ro[i];
+        if (JT == s.L - 1 && i == JT) snap(s, b, s.nsnap - 1)[e] = r_new;
+      }
+    }
+    seedX(s, b)[e] = cfma(alpha, un[0], x_old);                                // :685
+    return;
+  }
   for (int i = 0; i <= jj; ++i) {
     cplx *r = seedR(s, b, i);
     const cplx r_old = r[e];
@@ -573,7 +602,7 @@ __global__ void __launch_bounds__(128) k_shift_coef(BicgState s, ShiftCoef<LT> *
 
 constexpr int CSHIFT_CHUNK = 32;
 template <int LT>
-__global__ void __launch_bounds__(BT) k_shift_apply(BicgState s, const ShiftCoef<LT> *__restrict__ coef, int chunk) {
+__global__ void __launch_bounds__(BT, 2) k_shift_apply(BicgState s, const ShiftCoef<LT> *__restrict__ coef, int chunk) {
   constexpr int NSN = LT * (LT + 1) / 2 + 1;
   const int b = blockIdx.y;
   const int stage = s.stage[b];
@@ -599,24 +628,38 @@ __global__ void __launch_bounds__(BT) k_shift_apply(BicgState s, const ShiftCoef
     for (int j = 0; j < LT; ++j) rr[j] = seedR(s, b, j)[e];
   }
   cplx *pu0 = shiftU0(s, b, is0) + e, *px = shiftX(s, b, is0) + e;
-  // software pipeline: the loads of shift il+1 are issued before the arithmetic of shift il
-  cplx u0n = pu0[0], xn = px[0];
-  for (int il = 0; il < nsl; ++il) {
-    const cplx u0 = u0n, x0 = xn;
-    if (il + 1 < nsl) { u0n = pu0[(long)(il + 1) * n]; xn = px[(long)(il + 1) * n]; }
-    const ShiftCoef<LT> &c = sc[il];
-    cplx x = cfma(c.xu0, u0, x0);
+  // software pipeline: shifts are processed in groups of G and the loads of the NEXT group are issued before the arithmetic
+  // of the current one, so every thread keeps 2 G independent 16-byte loads in flight (the kernel is a pure HBM stream:
+  // 2 CTAs x 256 threads per SM need ~4 loads per thread to cover the DRAM latency-bandwidth product)
+  constexpr int G = 2;   // measured (Si64 step): G = 1 -> 98.7 ms, G = 2 -> 81.6 ms, G = 4 -> 85.0 ms (spills at the 128-register cap)
+  cplx u0n[G], xn[G];
 #pragma unroll
-    for (int jj = 0; jj < LT; ++jj) x = cfma(c.xs[jj], sn[jj * (jj + 1) / 2], x);
-    if (stage == 2) {
+  for (int g = 0; g < G; ++g)
+    if (g < nsl) { u0n[g] = pu0[(long)g * n]; xn[g] = px[(long)g * n]; }
+  for (int il = 0; il < nsl; il += G) {
+    cplx u0[G], x0[G];
 #pragma unroll
-      for (int j = 0; j < LT; ++j) x = cfma(c.xr[j], rr[j], x);
-      cplx u = cmul(c.uu0, u0);
+    for (int g = 0; g < G; ++g) { u0[g] = u0n[g]; x0[g] = xn[g]; }
 #pragma unroll
-      for (int k = 0; k < NSN; ++k) u = cfma(c.us[k], sn[k], u);
-      pu0[(long)il * n] = u;
+    for (int g = 0; g < G; ++g)
+      if (il + G + g < nsl) { u0n[g] = pu0[(long)(il + G + g) * n]; xn[g] = px[(long)(il + G + g) * n]; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (il + g >= nsl) break;
+      const ShiftCoef<LT> &c = sc[il + g];
+      cplx x = cfma(c.xu0, u0[g], x0[g]);
+#pragma unroll
+      for (int jj = 0; jj < LT; ++jj) x = cfma(c.xs[jj], sn[jj * (jj + 1) / 2], x);
+      if (stage == 2) {
+#pragma unroll
+        for (int j = 0; j < LT; ++j) x = cfma(c.xr[j], rr[j], x);
+        cplx u = cmul(c.uu0, u0[g]);
+#pragma unroll
+        for (int k = 0; k < NSN; ++k) u = cfma(c.us[k], sn[k], u);
+        pu0[(long)(il + g) * n] = u;
+      }
+      px[(long)(il + g) * n] = x;
     }
-    px[(long)il * n] = x;
   }
 }
 
@@ -763,7 +806,13 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
         SGW_LAUNCH_CHECK();
         k_scal_beta<<<gb, 128, 0, st>>>(s, jj);
         SGW_LAUNCH_CHECK();
-        k_seed_u<<<gvec, BT, 0, st>>>(s, jj);
+        switch (jj) {
+          case 0: k_seed_u<0><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 1: k_seed_u<1><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 2: k_seed_u<2><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 3: k_seed_u<3><<<gvec, BT, 0, st>>>(s, jj); break;
+          default: k_seed_u<-1><<<gvec, BT, 0, st>>>(s, jj); break;
+        }
         SGW_LAUNCH_CHECK();
       }
       // u_{j+1} = A u_j   (bicgstab.f90:611)
@@ -777,7 +826,13 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
         SGW_LAUNCH_CHECK();
         k_scal_alpha<<<(unsigned)nr, 128, 0, st>>>(s, jj);
         SGW_LAUNCH_CHECK();
-        k_bicg_update<<<gvec, BT, 0, st>>>(s, jj);
+        switch (jj) {
+          case 0: k_bicg_update<0><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 1: k_bicg_update<1><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 2: k_bicg_update<2><<<gvec, BT, 0, st>>>(s, jj); break;
+          case 3: k_bicg_update<3><<<gvec, BT, 0, st>>>(s, jj); break;
+          default: k_bicg_update<-1><<<gvec, BT, 0, st>>>(s, jj); break;
+        }
         SGW_LAUNCH_CHECK();
       }
       // r_{j+1} = A r_j   (bicgstab.f90:682)
