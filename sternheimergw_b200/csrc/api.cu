@@ -11,6 +11,51 @@ using namespace sgw;
 
 namespace sgw {
 
+namespace {
+struct DevPool {
+  std::multimap<std::pair<int, size_t>, void *> parked;   // (device, bytes) -> block
+  std::map<void *, std::pair<int, size_t>> live;
+  int contexts = 0;
+};
+DevPool &pool() { static DevPool p; return p; }
+}  // namespace
+
+cudaError_t dev_malloc(void **p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevPool &dp = pool();
+  auto it = dp.parked.find({dev, bytes});
+  if (it != dp.parked.end()) {
+    *p = it->second;
+    dp.parked.erase(it);
+  } else {
+    const cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {          // give parked memory back and retry once
+      cudaGetLastError();
+      dev_pool_trim();
+      const cudaError_t e2 = cudaMalloc(p, bytes);
+      if (e2 != cudaSuccess) return e2;
+    }
+  }
+  dp.live[*p] = {dev, bytes};
+  return cudaSuccess;
+}
+
+void dev_free(void *p) {
+  if (!p) return;
+  DevPool &dp = pool();
+  auto it = dp.live.find(p);
+  if (it == dp.live.end()) { cudaFree(p); return; }
+  dp.parked.insert({it->second, p});
+  dp.live.erase(it);
+}
+
+void dev_pool_trim() {
+  DevPool &dp = pool();
+  for (auto &kv : dp.parked) cudaFree(kv.second);
+  dp.parked.clear();
+}
+
 int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out) {
   if (bytes == 0) bytes = 16;
   auto it = ctx->ws.bufs.find(name);
@@ -49,16 +94,16 @@ void ws_free_all(sgw_ctx *ctx) {
 
 static void free_slot(KSlot &k) {
   free_sphere(&k.sph);
-  if (k.d_g2kin) cudaFree(k.d_g2kin);
-  if (k.d_P) cudaFree(k.d_P);
-  if (k.d_dion) cudaFree(k.d_dion);
-  if (k.d_A) cudaFree(k.d_A);
+  if (k.d_g2kin) dev_free(k.d_g2kin);
+  if (k.d_P) dev_free(k.d_P);
+  if (k.d_dion) dev_free(k.d_dion);
+  if (k.d_A) dev_free(k.d_A);
   k = KSlot();
 }
 
 static void free_pair(KPair &p) {
   free_sphere(&p.sph_k);
-  if (p.d_evc) cudaFree(p.d_evc);
+  if (p.d_evc) dev_free(p.d_evc);
   p = KPair();
 }
 
@@ -130,6 +175,7 @@ int sgw_create(int device, sgw_ctx **out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGW_E_CUDA; }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
+  pool().contexts++;
   *out = ctx;
   return SGW_OK;
 }
@@ -146,19 +192,20 @@ int sgw_destroy(sgw_ctx *ctx) {
   for (auto &sp : ctx->pair_kq_c) free_sphere(&sp);
   free_fft_grid(&ctx->rho_grid);
   ws_free_all(ctx);
-  if (ctx->d_twx) cudaFree(ctx->d_twx);
-  if (ctx->d_twy) cudaFree(ctx->d_twy);
-  if (ctx->d_twz) cudaFree(ctx->d_twz);
-  if (ctx->d_vperm) cudaFree(ctx->d_vperm);
+  if (ctx->d_twx) dev_free(ctx->d_twx);
+  if (ctx->d_twy) dev_free(ctx->d_twy);
+  if (ctx->d_twz) dev_free(ctx->d_twz);
+  if (ctx->d_vperm) dev_free(ctx->d_vperm);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
   for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) if (ctx->ev_iter[i]) cudaEventDestroy(ctx->ev_iter[i]);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-  if (ctx->corr.d_Ec) cudaFree(ctx->corr.d_Ec);
-  if (ctx->corr.d_ET) cudaFree(ctx->corr.d_ET);
+  if (ctx->corr.d_Ec) dev_free(ctx->corr.d_Ec);
+  if (ctx->corr.d_ET) dev_free(ctx->corr.d_ET);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+  if (--pool().contexts <= 0) { pool().contexts = 0; dev_pool_trim(); }
   return SGW_OK;
 }
 
@@ -222,9 +269,9 @@ int make_fft_grid(sgw_ctx *ctx, int n1, int n2, int n3, FftGrid *gr) {
   return SGW_OK;
 }
 void free_fft_grid(FftGrid *gr) {
-  if (gr->d_twx) cudaFree(gr->d_twx);
-  if (gr->d_twy) cudaFree(gr->d_twy);
-  if (gr->d_twz) cudaFree(gr->d_twz);
+  if (gr->d_twx) dev_free(gr->d_twx);
+  if (gr->d_twy) dev_free(gr->d_twy);
+  if (gr->d_twz) dev_free(gr->d_twz);
   *gr = FftGrid();
 }
 }  // namespace sgw
@@ -310,8 +357,8 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
     cplx *stage = nullptr;
     const int mmax = std::max(nkb, nbnd_occ);
     SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * mmax, &stage));
-    if (k->d_P) { cudaFree(k->d_P); k->d_P = nullptr; }
-    SGW_CUDA(cudaMalloc((void **)&k->d_P, sizeof(cplx) * (size_t)npwx * m));
+    if (k->d_P) { dev_free(k->d_P); k->d_P = nullptr; }
+    SGW_CUDA(dev_malloc((void **)&k->d_P, sizeof(cplx) * (size_t)npwx * m));
     if (nkb > 0) {
       SGW_CUDA(cudaMemcpyAsync(stage, vkb, sizeof(cplx) * (size_t)npwx * nkb, cudaMemcpyHostToDevice, ctx->stream));
       SGW_CHECK(permute_in(ctx, k->sph, nkb, stage, npwx, k->d_P, npwx, npwx));

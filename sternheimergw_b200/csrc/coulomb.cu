@@ -848,7 +848,7 @@ int sgw_set_nksq(sgw_ctx *ctx, int nksq) {
   ctx->tables_version++;
   for (auto &p : ctx->pairs) {
     free_sphere(&p.sph_k);
-    if (p.d_evc) cudaFree(p.d_evc);
+    if (p.d_evc) dev_free(p.d_evc);
   }
   ctx->pairs.assign(nksq, KPair());
   return SGW_OK;
@@ -868,13 +868,13 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   KPair &kp = ctx->pairs[ik];
   ctx->tables_version++;
   free_sphere(&kp.sph_k);
-  if (kp.d_evc) { cudaFree(kp.d_evc); kp.d_evc = nullptr; }
+  if (kp.d_evc) { dev_free(kp.d_evc); kp.d_evc = nullptr; }
   SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
   const int npwx = ks.npwx;
   {
     cplx *stage = nullptr;
     SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * nbnd, &stage));
-    SGW_CUDA(cudaMalloc((void **)&kp.d_evc, sizeof(cplx) * (size_t)npwx * nbnd));
+    SGW_CUDA(dev_malloc((void **)&kp.d_evc, sizeof(cplx) * (size_t)npwx * nbnd));
     SGW_CUDA(cudaMemcpyAsync(stage, evc, sizeof(cplx) * (size_t)npwx * nbnd, cudaMemcpyHostToDevice, ctx->stream));
     SGW_CHECK(permute_in(ctx, kp.sph_k, nbnd, stage, npwx, kp.d_evc, npwx, npwx));     // rows >= npw_k are zeroed
     SGW_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -589,7 +589,7 @@ int remap_sphere(sgw_ctx *ctx, const Sphere &fine, const FftGrid &gr, Sphere *ou
 void free_sphere(Sphere *s) {
   int **ptrs[] = {&s->d_col_x, &s->d_col_y, &s->d_col_ptr, &s->d_colof, &s->d_zof, &s->d_xs, &s->d_perm, &s->d_col_off};
   for (auto p : ptrs) {
-    if (*p) cudaFree(*p);
+    if (*p) dev_free(*p);
     *p = nullptr;
   }
   s->npw = s->ncol = s->nxs = 0;

@@ -213,6 +213,14 @@ namespace sgw {
     SGW_CUDA(cudaGetLastError());          \
   } while (0)
 
+// Table buffers (operator data, spheres, twiddles) come from a small size-keyed cache: a Fortran host re-installs the same
+// tables for every q-point, and cudaFree / cudaMalloc on a process that holds tens of GB of solver workspace were measured
+// at 7..350 ms per re-installation (they synchronise the device and edit its page tables).  dev_free parks the block,
+// dev_malloc hands out a parked block of the same size; sgw_destroy of the last context returns everything to the driver.
+cudaError_t dev_malloc(void **p, size_t bytes);
+void dev_free(void *p);
+void dev_pool_trim();
+
 // workspace: named growable device buffers owned by the context
 int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out);
 template <typename T>
@@ -226,9 +234,9 @@ void ws_free_all(sgw_ctx *ctx);
 
 template <typename T>
 inline int upload(sgw_ctx *ctx, T **dptr, const T *h, size_t count) {
-  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  if (*dptr) { dev_free(*dptr); *dptr = nullptr; }
   if (count == 0) return SGW_OK;
-  SGW_CUDA(cudaMalloc((void **)dptr, count * sizeof(T)));
+  SGW_CUDA(dev_malloc((void **)dptr, count * sizeof(T)));
   SGW_CUDA(cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   SGW_CUDA(cudaStreamSynchronize(ctx->stream));
   return SGW_OK;

@@ -500,12 +500,12 @@ int sgw_set_corr_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int ngm_c, const 
   SGW_ARG(ngm_c <= nnr, "more G vectors than box points");
   for (int i = 0; i < ngm_c; ++i) SGW_ARG(nl_c[i] >= 1 && nl_c[i] <= nnr, "nl entry outside the correlation box");
   CorrGrid &c = ctx->corr;
-  if (c.d_Ec) { cudaFree(c.d_Ec); c.d_Ec = nullptr; }
-  if (c.d_ET) { cudaFree(c.d_ET); c.d_ET = nullptr; }
+  if (c.d_Ec) { dev_free(c.d_Ec); c.d_Ec = nullptr; }
+  if (c.d_ET) { dev_free(c.d_ET); c.d_ET = nullptr; }
   c.set = false;
   c.n1 = nr1; c.n2 = nr2; c.n3 = nr3; c.nnr = (int)nnr; c.ngm = ngm_c;
-  SGW_CUDA(cudaMalloc((void **)&c.d_Ec, sizeof(cplx) * nnr * ngm_c));
-  SGW_CUDA(cudaMalloc((void **)&c.d_ET, sizeof(cplx) * nnr * ngm_c));
+  SGW_CUDA(dev_malloc((void **)&c.d_Ec, sizeof(cplx) * nnr * ngm_c));
+  SGW_CUDA(dev_malloc((void **)&c.d_ET, sizeof(cplx) * nnr * ngm_c));
   int *dnl = nullptr;
   SGW_CHECK(ws(ctx, "sg_nl", (size_t)ngm_c, &dnl));
   SGW_CUDA(cudaMemcpyAsync(dnl, nl_c, sizeof(int) * ngm_c, cudaMemcpyHostToDevice, ctx->stream));
