@@ -306,13 +306,21 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Native libraries write to the process's stdout (NCCL prints its version banner there whenever NCCL_DEBUG is set on the
+    # box, and NCCL_DEBUG_FILE does not cover that line): point fd 1 at stderr for the whole run and keep the original
+    # stdout for the ONE JSON line rank 0 prints at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+
     import torch
     import torch.distributed as dist
     from sternheimergw_b200 import Context, select_solver_type
     from sternheimergw_b200.dist import gather_columns
     torch.cuda.set_device(local_rank)
     if args.sigma_only:
-        print(json.dumps({"sigma_c": sigma_c_leg(local_rank, zgemm_peak_tflops())}), flush=True)
+        print(json.dumps({"sigma_c": sigma_c_leg(local_rank, zgemm_peak_tflops())}), file=json_out, flush=True)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -506,7 +514,7 @@ def main():
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
