@@ -218,10 +218,9 @@ def sigma_c_leg(device, f64_peak, reps=3):
     (20^3 grid, npw ~ 283, 59 correlation G vectors on a 6^3 box, 51 integration frequencies -> 102 Green's-function
     frequencies, 35 solver frequencies -> Pade on 69 points, 11 self-energy frequencies).  The reference prints
     'G: 3.9-5.3 s  G*W: 7.0-7.9 s' per (k, q) configuration for this case (examples/example01_Si/gw.ref:10328)."""
-    import oracle
     import synth
-    from oracle import sigma as osg
-    from sternheimergw_b200 import Context, freqbins_type, select_solver_type
+    from sternheimergw_b200 import Context, freqbins, select_solver_type
+    from sternheimergw_b200.host import pade_approx
     syn = synth.preset("si", nk=1)
     kq = syn.kpairs[0].kq
     ngc, ncoul, nsig, nsolver = 59, 51, 11, 35
@@ -230,14 +229,13 @@ def sigma_c_leg(device, f64_peak, reps=3):
     pos = {int(g): i + 1 for i, g in enumerate(kq.igk)}
     map_ = np.array([pos.get(ig, 0) for ig in range(1, ngc + 1)], dtype=np.int32)
     mu = 0.5 * (kq.et[syn.nbnd_occ - 1] + kq.et[syn.nbnd_occ])
-    fo = osg.freqbins(True, 0.0, 100.0 / synth.RYTOEV, nsig, 200.0 / synth.RYTOEV, ncoul, synth.imag_freqs(nsolver))
-    fh = freqbins_type(fo.solver, fo.coul, fo.weight, fo.sigma, fo.freq_symm_coul, True)
-    nsym = fo.num_freq()
+    fh = freqbins(True, 0.0, 100.0 / synth.RYTOEV, nsig, 200.0 / synth.RYTOEV, ncoul, synth.imag_freqs(nsolver))
+    nsym = fh.num_freq()
     rng = np.random.default_rng(synth.SEED)
     poles = np.array([0.9, 1.7, 2.9])
     res = rng.standard_normal((ngc, ngc, 3)) * 0.05 + np.eye(ngc)[:, :, None]
     coul = np.zeros((ngc, ngc, nsym), complex, order="F")
-    coul[:, :, :nsolver] = -(res[..., None] * 2 * poles[:, None] / (fo.solver ** 2 - poles[:, None] ** 2)).sum(axis=-2)
+    coul[:, :, :nsolver] = -(res[..., None] * 2 * poles[:, None] / (fh.solver ** 2 - poles[:, None] ** 2)).sum(axis=-2)
     gmapsym = np.arange(1, ngc + 1, dtype=np.int32)
     alpha = -1.0 / (2 * np.pi)
     ctx = Context(device)
@@ -245,13 +243,13 @@ def sigma_c_leg(device, f64_peak, reps=3):
     ctx.set_corr_grid(nr_c, nl_c)
     ctx.set_profiling(True)
     cfg = select_solver_type(priority=(1, 3), threshold=1e-5)            # thres_green default
-    coeff = ctx.analytic_coeff(osg.PADE_APPROX, 1e-4, fh, coul)
+    coeff = ctx.analytic_coeff(pade_approx, 1e-4, fh, coul)
     nb = 2 * ncoul
     best = None
     for _ in range(reps):
         sig = np.zeros((ngc, ngc, nsig), complex, order="F")
         t0 = time.perf_counter()
-        ctx.sigma_correlation(syn.omega_cell, cfg, 0, mu, alpha, osg.PADE_APPROX, fh, map_, gmapsym, coeff, sig)
+        ctx.sigma_correlation(syn.omega_cell, cfg, 0, mu, alpha, pade_approx, fh, map_, gmapsym, coeff, sig)
         wall = 1e3 * (time.perf_counter() - t0)
         st, prof = ctx.stats(), ctx.profile()
         if best is None or wall < best["wall_ms"]:
@@ -270,7 +268,10 @@ def sigma_c_leg(device, f64_peak, reps=3):
                           "algorithmic_flop_per_launch": flop / max(1, gw["regions"])},
            "reference_2017": "G: 3.9-5.3 s, G*W: 7.0-7.9 s per (k, q) configuration (examples/example01_Si/gw.ref:10328, CPU of that run)"}
     del ctx
-    # CPU oracle (numpy restatement of sigma_prod with per-column FFTs, fft6.f90) on a bounded sample of the products
+    # CPU oracle (numpy restatement of sigma_prod with per-column FFTs, fft6.f90) on a bounded sample of the products: the
+    # only place of this leg that touches oracle/ (as the timed CPU baseline, never on the GPU path)
+    from oracle import sigma as osg
+    fo = osg.freqbins_type(fh.solver, np.asarray(fh.coul), np.asarray(fh.weight), np.asarray(fh.sigma), fh.freq_symm_coul, True)
     d = osg.corr_fft_type(tuple(nr_c), nl_c)
     green_r = np.asfortranarray(rng.standard_normal((nnr, nnr)) + 1j * rng.standard_normal((nnr, nnr)))
     nsample, t0 = 0, time.perf_counter()

@@ -9,7 +9,7 @@ Host-side mirror (Python, over the C ABI of include/sgw_b200.h) of the reference
     unfold_w / invert_epsilon            algo/symmetry/src/unfold_w.f90:23, phys/coul/src/invert_epsilon.f90:23
     green_function                       phys/green/src/green.f90:105
     parallel_task                        data/parallel/src/parallel.f90:80
-    freqbins_type                        algo/grid/src/freqbins.f90:42
+    freqbins_type / freqbins             algo/grid/src/freqbins.f90:42,109 (+ gauleg_grid.f90)
     coulpade                             phys/coul/src/coulpade.f90:36
     analytic_coeff / analytic_eval       algo/analytic/src/analytic.f90:50,211 ('pade', 'godby-needs')
     invfft6 / fwfft6                     data/fft/src/fft6.f90:231,84
@@ -18,6 +18,6 @@ Host-side mirror (Python, over the C ABI of include/sgw_b200.h) of the reference
 Everything computes on the GPU through libsgw_b200.so; there is no CPU fallback -- importing works
 without a GPU, creating a `Context` does not.
 """
-from .host import Context, SgwError, freqbins_type, parallel_task, select_solver_type  # noqa: F401
+from .host import Context, SgwError, freqbins, freqbins_type, parallel_task, select_solver_type  # noqa: F401
 
-__all__ = ["Context", "SgwError", "select_solver_type", "parallel_task", "freqbins_type"]
+__all__ = ["Context", "SgwError", "select_solver_type", "parallel_task", "freqbins_type", "freqbins"]

@@ -87,6 +87,47 @@ class freqbins_type:
         return freq ** 2 if self.freq_symm_coul == square_symmetry else freq
 
 
+def gauleg_grid(x1, x2, n):
+    """Gauss-Legendre abscissas and weights on [x1, x2] (algo/grid/src/gauleg_grid.f90:23: Newton iteration on P_n with the
+    Chebyshev starting guess, relative precision 3e-14); host logic of the frequency meshes, numpy only."""
+    i = np.arange(1, (n + 1) // 2 + 1)
+    z = np.cos(np.pi * (i - 0.25) / (n + 0.5))
+    pp = np.ones_like(z)
+    todo = np.ones(z.shape, dtype=bool)              # every root stops on its own criterion, like the reference's scalar loop
+    for _ in range(100):
+        p1, p2 = np.ones_like(z), np.zeros_like(z)
+        for j in range(1, n + 1):
+            p1, p2 = ((2.0 * j - 1.0) * z * p1 - (j - 1.0) * p2) / j, p1
+        ppn = n * (z * p1 - p2) / (z * z - 1.0)
+        zn = z - p1 / ppn
+        step = np.abs(zn - z)
+        pp = np.where(todo, ppn, pp)
+        z = np.where(todo, zn, z)
+        todo = todo & (step > 3e-14)
+        if not todo.any():
+            break
+    xm, xl = 0.5 * (x2 + x1), 0.5 * (x2 - x1)
+    x, w = np.zeros(n), np.zeros(n)
+    wz = 2.0 * xl / ((1.0 - z * z) * pp * pp)
+    x[i - 1], x[n - i] = xm - xl * z, xm + xl * z
+    w[i - 1], w[n - i] = wz, wz
+    return x, w
+
+
+def freqbins(imag_sigma, min_sigma, max_sigma, num_sigma, max_coul, num_coul, solver, freq_symm_coul=even_symmetry, eta=0.0):
+    """freqbins (algo/grid/src/freqbins.f90:109-180): the self-energy mesh (equidistant) and the integration mesh of the
+    G W convolution -- Gauss-Legendre nodes on the imaginary axis, or an equidistant mesh shifted by i eta on the real axis
+    with the trapezoid-like weights of :156-158 -- as a `freqbins_type`."""
+    grid = min_sigma + (max_sigma - min_sigma) / (num_sigma - 1) * np.arange(num_sigma)
+    if imag_sigma:
+        g, weight = gauleg_grid(0.0, max_coul, num_coul)
+        return freqbins_type(np.asarray(solver, dtype=complex), 1j * g, weight, 1j * grid, freq_symm_coul, True)
+    g = max_coul / (num_coul - 1) * np.arange(num_coul)
+    weight = np.full(num_coul, 2.0 * max_coul / float(2 * num_coul - 1))
+    weight[0] *= 0.5
+    return freqbins_type(np.asarray(solver, dtype=complex), g + 1j * eta, weight, grid.astype(complex), freq_symm_coul, False)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

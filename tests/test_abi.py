@@ -51,3 +51,39 @@ def test_no_cpu_fallback():
     from sternheimergw_b200 import Context, SgwError
     with pytest.raises(SgwError):
         Context(0)
+
+
+def test_freqbins_num_freq_host_entry_point():
+    """sgw_freqbins_num_freq is pure host logic (freqbins_symm, freqbins.f90:243-305): same answers as the oracle, and the
+    reference's error for two zero frequencies."""
+    import numpy as np
+    from oracle import sigma as osg
+    from sternheimergw_b200 import SgwError, freqbins_type
+    for solver in ([0.0, 0.3j, 0.9j], [0.2j, 0.5j], [0.0], [1e-15, 0.4j, 2.0 + 0.1j]):
+        for symm in (0, 1, 2):
+            assert freqbins_type(np.array(solver, dtype=complex), freq_symm_coul=symm).num_freq() == \
+                osg.freqbins_symm(np.array(solver, dtype=complex), symm).size
+    with pytest.raises(SgwError):
+        freqbins_type(np.array([0.0, 0.0, 0.5j])).num_freq()
+    f = freqbins_type(np.array([0.0, 0.5j]), coul=np.array([0.1j, 0.3j]), weight=np.ones(2), sigma=np.array([0j, 1j]))
+    assert f.num_coul() == 2 and f.num_sigma() == 2
+    assert np.allclose(f.green(1.0), [1 + 0.1j, 1 + 0.3j, 1 - 0.1j, 1 - 0.3j])
+    assert f.symmetrize(2j) == 2j and freqbins_type(np.array([0j]), freq_symm_coul=2).symmetrize(2j) == -4
+
+
+def test_host_frequency_meshes_match_oracle_and_numpy():
+    """Host mirror of freqbins / gauleg_grid (freqbins.f90:109-180, gauleg_grid.f90:23) vs the oracle and numpy's leggauss."""
+    import numpy as np
+    from oracle import sigma as osg
+    from sternheimergw_b200.host import freqbins, gauleg_grid
+    for n in (1, 2, 5, 12, 35, 51):
+        x, w = gauleg_grid(0.0, 7.3, n)
+        xo, wo = osg.gauleg_grid(0.0, 7.3, n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.array_equal(x, xo) and np.array_equal(w, wo)
+        assert np.allclose(x, 3.65 + 3.65 * xr, atol=1e-12) and np.allclose(w, 3.65 * wr, atol=1e-12)
+    for imag, eta in ((True, 0.0), (False, 0.07)):
+        a = freqbins(imag, -0.5 if not imag else 0.0, 1.0, 6, 3.0, 9, [0.0, 0.3j, 0.9j], eta=eta)
+        b = osg.freqbins(imag, -0.5 if not imag else 0.0, 1.0, 6, 3.0, 9, [0.0, 0.3j, 0.9j], eta=eta)
+        assert np.array_equal(a.coul, b.coul) and np.array_equal(a.weight, b.weight) and np.array_equal(a.sigma, b.sigma)
+        assert a.imag_sigma == b.imag_sigma and a.num_freq() == b.num_freq() == 5
