@@ -260,7 +260,7 @@ __device__ __noinline__ void run_acc(int R, const cplx *x, cplx *acc, int nlines
 
 // incdrhoscf: one CTA per (pf = perturbation x frequency, z-plane); bands are summed on chip
 template <int NT>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : 2) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 3)) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
                                                          const cplx *__restrict__ Tin, const cplx *__restrict__ psir,
                                                          double wgt, cplx *__restrict__ Tout, int accumulate) {
   const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
@@ -468,7 +468,16 @@ int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, 
   dim3 grid(npf, g.nz);
   ProfScope prof(ctx, PC_RHO_PLANE);
   // small planes (the reduced Delta-rho box): 256 threads fill the butterfly stages better and two CTAs fit on an SM
-  if (g.nx * g.ny <= 3072) {
+  static int rho_nt = -1;                                        // SGW_RHO_NT: tuning knob (128 | 192 | 256)
+  if (rho_nt < 0) { const char *e = getenv("SGW_RHO_NT"); rho_nt = e ? atoi(e) : 0; }
+  // measured on B200 (Si64, reduced 45^3 box): 256 threads / 2 CTAs per SM -> 48 ms per step, 192 -> 50 ms, 128 threads / 3 CTAs -> 40 ms
+  if (g.nx * g.ny <= 3072 && (rho_nt == 128 || rho_nt == 0)) {
+    SGW_CHECK(set_smem(ctx, k_plane_rho<128>, smem));
+    k_plane_rho<128><<<grid, 128, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  } else if (g.nx * g.ny <= 3072 && rho_nt == 192) {
+    SGW_CHECK(set_smem(ctx, k_plane_rho<192>, smem));
+    k_plane_rho<192><<<grid, 192, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
+  } else if (g.nx * g.ny <= 3072) {   // SGW_RHO_NT=256
     SGW_CHECK(set_smem(ctx, k_plane_rho<256>, smem));
     k_plane_rho<256><<<grid, 256, smem, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate);
   } else {
