@@ -97,6 +97,9 @@ static void free_slot(KSlot &k) {
   if (k.d_g2kin) dev_free(k.d_g2kin);
   if (k.d_P) dev_free(k.d_P);
   if (k.d_dion) dev_free(k.d_dion);
+  if (k.d_dion_ptr) dev_free(k.d_dion_ptr);
+  if (k.d_dion_col) dev_free(k.d_dion_col);
+  if (k.d_dion_val) dev_free(k.d_dion_val);
   if (k.d_A) dev_free(k.d_A);
   k = KSlot();
 }
@@ -369,7 +372,27 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
     }
     SGW_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  if (nkb > 0) SGW_CHECK(upload(ctx, &k->d_dion, dion, (size_t)nkb * nkb));
+  if (nkb > 0) {
+    SGW_CHECK(upload(ctx, &k->d_dion, dion, (size_t)nkb * nkb));
+    // compressed rows of D (column-major input): used when at most a quarter of the entries is non-zero
+    std::vector<int> ptr(nkb + 1, 0), col;
+    std::vector<double> val;
+    for (int i = 0; i < nkb; ++i) {
+      for (int j = 0; j < nkb; ++j) {
+        const double d = dion[i + (size_t)nkb * j];
+        if (d != 0.0) { col.push_back(j); val.push_back(d); }
+      }
+      ptr[i + 1] = (int)col.size();
+    }
+    if (k->d_dion_ptr) { dev_free(k->d_dion_ptr); k->d_dion_ptr = nullptr; }
+    if (k->d_dion_col) { dev_free(k->d_dion_col); k->d_dion_col = nullptr; }
+    if (k->d_dion_val) { dev_free(k->d_dion_val); k->d_dion_val = nullptr; }
+    if (col.size() * 4 <= (size_t)nkb * nkb && !col.empty()) {
+      SGW_CHECK(upload(ctx, &k->d_dion_ptr, ptr.data(), ptr.size()));
+      SGW_CHECK(upload(ctx, &k->d_dion_col, col.data(), col.size()));
+      SGW_CHECK(upload(ctx, &k->d_dion_val, val.data(), val.size()));
+    }
+  }
   k->set = true;
   k->dense = false;
   return SGW_OK;

@@ -160,7 +160,8 @@ static int zgemm_init(sgw_ctx *ctx) {
 
 // coef'(:, v) = blockdiag(D, alpha I) * sum_z partial_z(:, v)
 __global__ void k_coef_finish(int m, int nkb, int nvec, int nsplit, const cplx *__restrict__ part, long split_stride,
-                              const double *__restrict__ dion, double alpha_pv, cplx *__restrict__ coef,
+                              const double *__restrict__ dion, const int *__restrict__ dptr, const int *__restrict__ dcol,
+                              const double *__restrict__ dval, double alpha_pv, cplx *__restrict__ coef,
                               const int *__restrict__ active) {
   const int v = blockIdx.x;
   if (active && !active[v]) return;
@@ -175,10 +176,19 @@ __global__ void k_coef_finish(int m, int nkb, int nvec, int nsplit, const cplx *
     cplx r;
     if (i < nkb) {
       r = cmake(0.0, 0.0);
-      for (int j = 0; j < nkb; ++j) {
-        const double d = dion[i + (long)nkb * j];
-        r.x += d * c[j].x;
-        r.y += d * c[j].y;
+      if (dptr) {                      // compressed row: same terms in the same (column) order, exact zeros skipped
+        for (int e = dptr[i]; e < dptr[i + 1]; ++e) {
+          const double d = dval[e];
+          const cplx cj = c[dcol[e]];
+          r.x += d * cj.x;
+          r.y += d * cj.y;
+        }
+      } else {
+        for (int j = 0; j < nkb; ++j) {
+          const double d = dion[i + (long)nkb * j];
+          r.x += d * c[j].x;
+          r.y += d * c[j].y;
+        }
       }
     } else {
       r = cscale(alpha_pv, c[i]);
@@ -248,7 +258,7 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
   }
   {
     ProfScope prof(ctx, PC_OTHER);
-    k_coef_finish<<<nvec, 128, (size_t)m * sizeof(cplx), ctx->stream>>>(m, ks.nkb, nvec, nsplit, part, split_stride, ks.d_dion,
+    k_coef_finish<<<nvec, 128, (size_t)m * sizeof(cplx), ctx->stream>>>(m, ks.nkb, nvec, nsplit, part, split_stride, ks.d_dion, ks.d_dion_ptr, ks.d_dion_col, ks.d_dion_val,
                                                                       alpha_pv, coef, active);
     SGW_LAUNCH_CHECK();
   }

@@ -100,6 +100,9 @@ struct KSlot {
   double *d_g2kin = nullptr;   // npwx (column order, zero padded)
   cplx *d_P = nullptr;         // npwx x (nkb + nbnd): [vkb | evq] rows in column order
   double *d_dion = nullptr;    // nkb x nkb
+  // the same matrix by rows, exact zeros dropped (QE's deeq is block diagonal per atom): row i = entries d_dion_ptr[i] .. [i+1]
+  int *d_dion_ptr = nullptr, *d_dion_col = nullptr;
+  double *d_dion_val = nullptr;
   cplx *d_A = nullptr;         // dense backend n x n
 };
 
