@@ -169,7 +169,9 @@ __global__ void k_init_scal(BicgState s, const cplx *__restrict__ sigma /* nshif
 }
 
 // r0 = rt0 = b ; u0 = 0 ; x = 0 ; shifted u0 = 0, x = 0
-__global__ void __launch_bounds__(BT) k_init_vec(BicgState s, const cplx *__restrict__ bvec, long ldb) {
+// init_shift = 0: u^sigma_0 and x^sigma are NOT zeroed here -- the collapsed shifted update treats them as zero in the first
+// outer iteration of a right-hand side instead of reading them (saves writing and re-reading 2 ns vectors per RHS)
+__global__ void __launch_bounds__(BT) k_init_vec(BicgState s, const cplx *__restrict__ bvec, long ldb, int init_shift) {
   const int b = blockIdx.y;
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n || !s.active[b]) return;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(BT) k_init_vec(BicgState s, const cplx *__rest
   s.RT[(long)b * s.n + e] = v;
   seedU(s, b, 0)[e] = z;
   seedX(s, b)[e] = z;
+  if (!init_shift) return;
   for (int is = 0; is < s.ns; ++is) {
     shiftU0(s, b, is)[e] = z;
     shiftX(s, b, is)[e] = z;
@@ -628,6 +631,9 @@ __global__ void __launch_bounds__(BT, 2) k_shift_apply(BicgState s, const ShiftC
     for (int j = 0; j < LT; ++j) rr[j] = seedR(s, b, j)[e];
   }
   cplx *pu0 = shiftU0(s, b, is0) + e, *px = shiftX(s, b, is0) + e;
+  // first outer iteration of this right-hand side: u^sigma_0 = x^sigma = 0 (bicgstab.f90 init_shift), not read from memory
+  const bool first = s.iters[b] == 1;
+  const cplx zero = cmake(0.0, 0.0);
   // software pipeline: shifts are processed in groups of G and the loads of the NEXT group are issued before the arithmetic
   // of the current one, so every thread keeps 2 G independent 16-byte loads in flight (the kernel is a pure HBM stream:
   // 2 CTAs x 256 threads per SM need ~4 loads per thread to cover the DRAM latency-bandwidth product)
@@ -635,14 +641,17 @@ __global__ void __launch_bounds__(BT, 2) k_shift_apply(BicgState s, const ShiftC
   cplx u0n[G], xn[G];
 #pragma unroll
   for (int g = 0; g < G; ++g)
-    if (g < nsl) { u0n[g] = pu0[(long)g * n]; xn[g] = px[(long)g * n]; }
+    if (g < nsl) { u0n[g] = first ? zero : pu0[(long)g * n]; xn[g] = first ? zero : px[(long)g * n]; }
   for (int il = 0; il < nsl; il += G) {
     cplx u0[G], x0[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { u0[g] = u0n[g]; x0[g] = xn[g]; }
 #pragma unroll
     for (int g = 0; g < G; ++g)
-      if (il + G + g < nsl) { u0n[g] = pu0[(long)(il + G + g) * n]; xn[g] = px[(long)(il + G + g) * n]; }
+      if (il + G + g < nsl) {
+        u0n[g] = first ? zero : pu0[(long)(il + G + g) * n];
+        xn[g] = first ? zero : px[(long)(il + G + g) * n];
+      }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       if (il + g >= nsl) break;
@@ -790,10 +799,11 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
 
   k_init_scal<<<gb, 128, 0, st>>>(s, sb.d_sigma, d_todo);
   SGW_LAUNCH_CHECK();
-  k_init_vec<<<gvec, BT, 0, st>>>(s, sb.d_b, sb.ldb);
+  const bool faithful = shift_faithful();
+  const bool collapsed = s.ns > 0 && !faithful && (lmax == 2 || lmax == 4);
+  k_init_vec<<<gvec, BT, 0, st>>>(s, sb.d_b, sb.ldb, collapsed ? 0 : 1);
   SGW_LAUNCH_CHECK();
 
-  const bool faithful = shift_faithful();
   const long ldv = n;   // vectors inside U/R are contiguous with stride (L+1)*n between RHS
   int rc = SGW_OK;
   for (int iter = 1; iter <= max_iter && rc == SGW_OK; ++iter) {
@@ -851,7 +861,7 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
       k_mr_mgs<<<(unsigned)nr, 1024, 0, st>>>(s);
       SGW_LAUNCH_CHECK();
     }
-    if (s.ns > 0 && !faithful && (lmax == 2 || lmax == 4)) {
+    if (collapsed) {
       rc = lmax == 4 ? launch_shift_collapsed<4>(ctx, s) : launch_shift_collapsed<2>(ctx, s);
       if (rc != SGW_OK) break;
     } else if (s.ns > 0) {
