@@ -11,7 +11,8 @@ numpy restatement, in the reference's execution order, of SURVEY.md section 8 ro
                                    data/fft/src/fft6.f90:84 (fwfft6), :231 (invfft6)
 
 The reference cannot be compiled here (Fortran 2003 + QE 6.3).  Its only unit test in this area (algo/analytic/test/pade.pf)
-covers `pade_robust`, which is not restated (no BASELINE config uses it), so for these routines **parity is unpinned** by
+covers `pade_robust`, which is not restated (no BASELINE config uses it), so for these routines (incl. the 'aaa' model of
+vendor/analytic/src/aaa.f90) **parity is unpinned** by
 reference tests; tests/test_oracle_sigma.py anchors them by independent properties instead: the Pade approximant
 interpolates its input, the Godby-Needs model reproduces its two input frequencies, fft6 equals numpy's 6-D fftn, and
 sigma_prod equals the explicit G-space convolution.
@@ -227,8 +228,11 @@ def analytic_coeff(model_coul, thres, freq: freqbins_type, scrcoul_g):
     elif model_coul == PADE_APPROX:
         z = freqbins_symm(freq.solver, freq.freq_symm_coul, scrcoul_g)
         scrcoul_g[:, :, :] = pade_coeff(z, scrcoul_g)
+    elif model_coul == AAA_APPROX:
+        z = freqbins_symm(freq.solver, freq.freq_symm_coul, scrcoul_g)
+        scrcoul_g[:, :, :] = aaa_coeff_pack(thres, freq.num_freq() // 3, z, scrcoul_g)
     else:
-        raise NotImplementedError("only 'godby-needs' and 'pade' are restated (the BASELINE configs use these two)")
+        raise NotImplementedError("'pade robust' and 'aaa pole' are not restated")
 
 
 def analytic_eval(model_coul, gmapsym, freq_in: freqbins_type, scrcoul_coeff, freq_out, fft_map=None):
@@ -244,6 +248,12 @@ def analytic_eval(model_coul, gmapsym, freq_in: freqbins_type, scrcoul_coeff, fr
         return pade_eval(z, coeff, freq_sym)
     if model_coul == GODBY_NEEDS:
         return godby_needs_model(freq_sym, coeff)
+    if model_coul == AAA_APPROX:
+        out = np.zeros(coeff.shape[:2], dtype=complex)
+        for i in range(coeff.shape[0]):
+            for j in range(coeff.shape[1]):
+                out[i, j] = aaa_approx_eval(freq_sym, coeff[i, j, :])
+        return out
     raise NotImplementedError
 
 
@@ -356,3 +366,81 @@ def qp_eigval(w, sig, et):
     sig_der = (s2 - s1) / (w2 - w1)
     zfac = 1.0 / (1.0 - sig_der)
     return et + zfac * sig_et, zfac
+
+
+# ----------------------------------------------------------------------------- vendor/analytic/src/aaa.f90 ('aaa' model)
+def _cauchy_matrix(xx, yy):
+    """aaa.f90 construct_Cauchy_matrix: 1 / (x - y) with |denominator| <= eps14 replaced by eps14."""
+    den = np.asarray(xx, dtype=complex)[:, None] - np.asarray(yy, dtype=complex)[None, :]
+    den = np.where(np.abs(den) <= EPS14, EPS14 + 0j, den)
+    return 1.0 / den
+
+
+def _aaa_evaluate_raw(position, value, weight, zz):
+    """aaa.f90 evaluate_analytic_cont: barycentric form, numerator and denominator as Cauchy-matrix products."""
+    c = _cauchy_matrix(zz, position)
+    return (c @ (weight * value)) / (c @ weight)
+
+
+def aaa_generate(thres, max_point, zz, ff):
+    """aaa.f90 aaa_generate / determine_analytic_cont: greedy AAA.  Returns (position, value, weight); the support points are
+    kept in mesh order (PACK), the weights are the right singular vector of the smallest singular value of the Loewner
+    submatrix (rows: non-support points, columns: support points)."""
+    zz, ff = np.asarray(zz, dtype=complex), np.asarray(ff, dtype=complex)
+    n = ff.size
+    if zz.size != n:
+        raise ValueError("input_error")
+    thr = thres * np.abs(ff).max()                                    # absolute_threshold
+    max_point = n if max_point == -1 else max_point
+    fit = np.full(n, ff.sum() / n)                                    # setup_work_type: average
+    sup = np.zeros(n, dtype=bool)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        loewner = (ff[:, None] - ff[None, :]) / (zz[:, None] - zz[None, :])
+    np.fill_diagonal(loewner, 0.0)
+    while True:
+        new = int(np.argmax(np.abs(ff - fit)))                        # MAXLOC: first maximum
+        fit[new] = ff[new]
+        sup[new] = True
+        position, value = zz[sup], ff[sup]
+        sub = loewner[~sup][:, sup]
+        if sub.size == 0:                                             # lapack_module trivial_case: V^dagger = identity
+            weight = np.zeros(position.size, dtype=complex)
+            weight[-1] = 1.0
+        else:
+            vh = np.linalg.svd(sub, full_matrices=True)[2]
+            weight = np.conj(vh[-1, :])
+        ev = _aaa_evaluate_raw(position, value, weight, zz)           # update_fit
+        fit = np.where(sup, fit, ev)
+        if np.all(np.abs(fit - ff) <= thr) or position.size >= max_point:
+            return position, value, weight
+
+
+def aaa_evaluate(position, value, weight, zz):
+    """aaa.f90 aaa_evaluate: barycentric value, replaced by the tabulated value within eps14 of a support point."""
+    zz = np.atleast_1d(np.asarray(zz, dtype=complex))
+    out = _aaa_evaluate_raw(position, value, weight, zz)
+    dist = np.abs(zz[:, None] - position[None, :])
+    idx = dist.argmin(axis=1)
+    close = dist[np.arange(zz.size), idx] < EPS14
+    return np.where(close, value[idx], out)
+
+
+def aaa_coeff_pack(thres, mmax, z, u):
+    """analytic.f90:150-172 (aaa_approx): coefficient layout [position | value | weight], each block mmax long, zero padded."""
+    out = np.zeros(u.shape, dtype=complex)
+    ngc = u.shape[0]
+    for igp in range(ngc):
+        for ig in range(ngc):
+            p, v, w = aaa_generate(thres, mmax, z, u[ig, igp, :])
+            mm = p.size
+            out[ig, igp, 0:mm] = p
+            out[ig, igp, mmax:mmax + mm] = v
+            out[ig, igp, 2 * mmax:2 * mmax + mm] = w
+    return out
+
+
+def aaa_approx_eval(freq_sym, coeff):
+    """analytic.f90:312-343: mm = number of weights above eps12; the first mm entries of each block are used."""
+    mmax = coeff.size // 3
+    mm = int(np.count_nonzero(np.abs(coeff[2 * mmax:3 * mmax]) > 1e-12))
+    return aaa_evaluate(coeff[:mm], coeff[mmax:mmax + mm], coeff[2 * mmax:2 * mmax + mm], freq_sym)[0]

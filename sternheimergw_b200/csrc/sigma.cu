@@ -133,6 +133,25 @@ __global__ void k_analytic_eval(int model, int ngc, int N, const int *__restrict
       am2 = am1; am1 = a; bm2 = bm1; bm1 = b;
     }
     res = cdiv_nf(am1, bm1);
+  } else if (model == SGW_AAA_APPROX) {                // aaa_approx_eval (analytic.f90:312-343) + aaa_evaluate (aaa.f90)
+    const int mmax = N / 3;
+    int mm = 0;
+    for (int j = 0; j < mmax; ++j) { const cplx wj = c[npair * (2 * mmax + j)]; mm += hypot(wj.x, wj.y) > 1e-12; }
+    cplx num = cmake(0.0, 0.0), den = cmake(0.0, 0.0);
+    double dmin = 1e300;
+    int jclose = 0;
+    for (int j = 0; j < mm; ++j) {
+      const cplx pj = c[npair * j], vj = c[npair * (mmax + j)], wj = c[npair * (2 * mmax + j)];
+      cplx d = csub(w, pj);
+      const double dist = hypot(d.x, d.y);
+      if (dist < dmin) { dmin = dist; jclose = j; }          // MINLOC: first minimum
+      if (dist <= 1e-14) d = cmake(1e-14, 0.0);
+      const cplx cm = cdiv_nf(cmake(1.0, 0.0), d);
+      num = cadd(num, cmul(cm, cmul(wj, vj)));
+      den = cadd(den, cmul(cm, wj));
+    }
+    res = cdiv_nf(num, den);
+    if (mm > 0 && dmin < 1e-14) res = c[npair * (mmax + jclose)];
   } else {                                             // godby_needs_model (godby_needs.f90:108-135)
     const cplx c1 = c[0], c2 = c[npair];
     if (hypot(c1.x, c1.y) > 1e-8) {
@@ -143,6 +162,163 @@ __global__ void k_analytic_eval(int model, int ngc, int N, const int *__restrict
     }
   }
   out[ig + (long)ngc * (igp + (long)ngc * io)] = res;
+}
+
+// ---------------------------------------------------------------- AAA ('aaa', vendor/analytic/src/aaa.f90 via analytic.f90:150-172)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Greedy AAA fit of one (G, G') pair per warp (aaa_generate): support point = first maximum of |f - fit|, weights = right
+// singular vector of the smallest singular value of the Loewner submatrix (rows: non-support points, columns: support
+// points).  The reference calls LAPACK's SVD; here the R x m submatrix (R = N - m >= 2 m) lives in shared memory and a
+// one-sided (Hestenes) Jacobi iteration orthogonalises its columns while accumulating V -- it delivers the small singular
+// vectors to high relative accuracy, which is what the barycentric weights need.  The weights are defined up to a
+// common phase (the approximant does not depend on it), so coefficient arrays are not comparable entry by entry with a
+// LAPACK-based fit; positions, values and the evaluated approximant are.
+// Shared memory: zz, ff, fit [N] | A [N x mmax] | V [mmax x mmax] | w [mmax] | sup [N] (int) | supidx [mmax] | rowidx [N]
+__global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, double thres, const cplx *__restrict__ z,
+                                                  cplx *__restrict__ scr, int *__restrict__ info) {
+  const long pair = blockIdx.x;
+  if (pair >= npair) return;
+  const int lane = threadIdx.x;
+  extern __shared__ cplx aaa_sm[];
+  cplx *zz = aaa_sm, *ff = zz + N, *fit = ff + N;
+  cplx *A = fit + N;
+  cplx *V = A + (long)N * mmax;
+  cplx *w = V + (long)mmax * mmax;
+  int *sup = (int *)(w + mmax), *supidx = sup + N, *rowidx = supidx + mmax;
+  for (int i = lane; i < N; i += 32) { zz[i] = z[i]; ff[i] = scr[pair + npair * i]; sup[i] = 0; }
+  __syncwarp();
+  // average and absolute threshold (setup_work_type)
+  double fmax = 0.0;
+  for (int i = lane; i < N; i += 32) fmax = fmax > hypot(ff[i].x, ff[i].y) ? fmax : hypot(ff[i].x, ff[i].y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, fmax, o); fmax = fmax > t ? fmax : t; }
+  const double thr = thres * fmax;
+  cplx avg = cmake(0.0, 0.0);
+  for (int i = 0; i < N; ++i) avg = cadd(avg, ff[i]);
+  avg = cmake(avg.x / N, avg.y / N);
+  for (int i = lane; i < N; i += 32) fit[i] = avg;
+  __syncwarp();
+  int m = 0, bad = 0;
+  for (;;) {
+    // ---- update_support_point: first maximum of |ff - fit|
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    for (int i = lane; i < N; i += 32) {
+      const cplx d = csub(ff[i], fit[i]);
+      const double a = hypot(d.x, d.y);
+      if (a > best) { best = a; bidx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { fit[bidx] = ff[bidx]; sup[bidx] = 1; }
+    ++m;
+    __syncwarp();
+    if (lane == 0) {                         // support points and the remaining rows in mesh order (PACK)
+      int a = 0, b = 0;
+      for (int i = 0; i < N; ++i) { if (sup[i]) supidx[a++] = i; else rowidx[b++] = i; }
+    }
+    __syncwarp();
+    const int R = N - m;
+    // ---- Loewner submatrix (construct_Loewner_matrix + extract_submatrix) and V = 1
+    for (int c = 0; c < m; ++c) {
+      const int jc = supidx[c];
+      for (int r = lane; r < R; r += 32) {
+        const int ir = rowidx[r];
+        A[r + (long)R * c] = cdiv_nf(csub(ff[ir], ff[jc]), csub(zz[ir], zz[jc]));
+      }
+    }
+    for (int i = lane; i < m * m; i += 32) V[i] = (i % m == i / m) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+    __syncwarp();
+    // ---- one-sided Jacobi on the columns of A
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      int rotated = 0;
+      for (int p = 0; p < m - 1; ++p)
+        for (int q = p + 1; q < m; ++q) {
+          cplx *ap = A + (long)R * p, *aq = A + (long)R * q;
+          double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+          for (int r = lane; r < R; r += 32) {
+            const cplx x = ap[r], y = aq[r];
+            al += x.x * x.x + x.y * x.y;
+            be += y.x * y.x + y.y * y.y;
+            gr += x.x * y.x + x.y * y.y;          // conj(x) * y
+            gi += x.x * y.y - x.y * y.x;
+          }
+          al = warp_sum_d(al); be = warp_sum_d(be); gr = warp_sum_d(gr); gi = warp_sum_d(gi);
+          const double g2 = gr * gr + gi * gi;
+          if (!(g2 > 1e-30 * al * be) || g2 == 0.0) continue;
+          rotated = 1;
+          const double gabs = sqrt(g2);
+          const cplx phc = cmake(gr / gabs, -gi / gabs);            // conj(gamma / |gamma|)
+          const double zeta = (be - al) / (2.0 * gabs);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+          for (int r = lane; r < R; r += 32) {
+            const cplx x = ap[r], y = cmul(aq[r], phc);
+            ap[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+            aq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+          }
+          cplx *vp = V + (long)m * p, *vq = V + (long)m * q;
+          for (int r = lane; r < m; r += 32) {
+            const cplx x = vp[r], y = cmul(vq[r], phc);
+            vp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+            vq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+          }
+          __syncwarp();
+        }
+      if (!rotated) break;
+      if (sweep == 59) bad = 1;
+    }
+    // ---- weights = column of V that belongs to the smallest column norm
+    int jmin = 0;
+    double smin = 1e300;
+    for (int c = 0; c < m; ++c) {
+      double nn = 0.0;
+      for (int r = lane; r < R; r += 32) { const cplx x = A[r + (long)R * c]; nn += x.x * x.x + x.y * x.y; }
+      nn = warp_sum_d(nn);
+      if (nn < smin) { smin = nn; jmin = c; }
+    }
+    for (int r = lane; r < m; r += 32) w[r] = V[r + (long)m * jmin];
+    __syncwarp();
+    // ---- update_fit: barycentric value at the non-support points (Cauchy-matrix products, support order)
+    int notconv = 0;
+    for (int r = lane; r < R; r += 32) {
+      const int ir = rowidx[r];
+      cplx num = cmake(0.0, 0.0), den = cmake(0.0, 0.0);
+      for (int c = 0; c < m; ++c) {
+        const int jc = supidx[c];
+        cplx d = csub(zz[ir], zz[jc]);
+        if (hypot(d.x, d.y) <= 1e-14) d = cmake(1e-14, 0.0);
+        const cplx cm = cdiv_nf(cmake(1.0, 0.0), d);
+        num = cadd(num, cmul(cm, cmul(w[c], ff[jc])));
+        den = cadd(den, cmul(cm, w[c]));
+      }
+      const cplx fv = cdiv_nf(num, den);
+      fit[ir] = fv;
+      const cplx e = csub(fv, ff[ir]);
+      if (!(hypot(e.x, e.y) <= thr)) notconv = 1;
+    }
+    notconv = __any_sync(0xffffffffu, notconv);
+    __syncwarp();
+    if (!notconv || m >= mmax) break;
+  }
+  // ---- analytic.f90:160-167: [position | value | weight], each block mmax long, zero padded
+  for (int i = lane; i < N; i += 32) scr[pair + npair * i] = cmake(0.0, 0.0);
+  __syncwarp();
+  for (int c = lane; c < m; c += 32) {
+    scr[pair + npair * c] = zz[supidx[c]];
+    scr[pair + npair * (mmax + c)] = ff[supidx[c]];
+    scr[pair + npair * (2 * mmax + c)] = w[c];
+  }
+  if (bad && lane == 0) atomicExch(info, 1);
 }
 
 // Ec(r, G) = exp(-i G r) (nnr x ngm) and ET(G, r) = exp(+i G r) (ngm x nnr); r = i1 + n1 (i2 + n2 i3) (QE column-major box),
@@ -336,11 +512,11 @@ static int symm_mesh(const sgw_freqbins *f, std::vector<cplx> *z, std::vector<in
 static int check_freq(sgw_ctx *ctx, const sgw_freqbins *f, int model) {
   SGW_ARG(f && f->num_solver > 0 && f->solver, "freqbins: solver frequencies missing");
   SGW_ARG(f->freq_symm_coul >= 0 && f->freq_symm_coul <= 2, "freqbins: freq_symm_coul must be 0, 1 or 2");
-  if (model == SGW_PADE_ROBUST || model == SGW_AAA_APPROX || model == SGW_AAA_POLE) {
-    ctx->err = "model_coul 'pade robust' / 'aaa' / 'aaa pole' are not built (SURVEY 8 f3 covers 'pade' and 'godby-needs')";
+  if (model == SGW_PADE_ROBUST || model == SGW_AAA_POLE) {
+    ctx->err = "model_coul 'pade robust' / 'aaa pole' are not built (SURVEY 8 f3 covers 'pade', 'godby-needs' and 'aaa')";
     return SGW_E_UNSUPPORTED;
   }
-  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX, "No screening model chosen!");   // analytic.f90:186
+  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX || model == SGW_AAA_APPROX, "No screening model chosen!");   // analytic.f90:186
   return SGW_OK;
 }
 
@@ -411,7 +587,6 @@ int sgw_coulpade(sgw_ctx *ctx, int ngc, int nfreq, const double *factor, sgw_cpl
 int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_freqbins *freq, int ngc, sgw_cplx *scrcoul_g) {
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
-  (void)thres;   // only read by the AAA and robust-Pade models
   SGW_CHECK(check_freq(ctx, freq, model_coul));
   SGW_ARG(ngc > 0 && scrcoul_g, "bad argument");
   std::vector<cplx> z;
@@ -435,6 +610,7 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
     k_gn_coeff<<<(unsigned)((npair + 127) / 128), 128, 0, ctx->stream>>>(npair, freq->solver[1].im, d);
     SGW_LAUNCH_CHECK();
   } else {
+    if (model_coul == SGW_AAA_APPROX && N / 3 < 1) { ctx->err = "'aaa' needs at least 3 frequencies"; return SGW_E_ARG; }
     SGW_CUDA(cudaMemcpyAsync(dz, z.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, ctx->stream));
     if (!src.empty()) {
       int *dsrc = nullptr, *ddst = nullptr;
@@ -446,8 +622,25 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
       k_mirror<<<grid, 256, 0, ctx->stream>>>(npair, (int)src.size(), dsrc, ddst, d);
       SGW_LAUNCH_CHECK();
     }
-    k_pade_coeff<<<(unsigned)((npair + 63) / 64), 64, 0, ctx->stream>>>(npair, N, dz, d);
-    SGW_LAUNCH_CHECK();
+    if (model_coul == SGW_AAA_APPROX) {
+      const int mmax = N / 3;                                                                   // analytic.f90:148
+      const size_t smem = sizeof(cplx) * ((size_t)3 * N + (size_t)N * mmax + (size_t)mmax * mmax + mmax) +
+                          sizeof(int) * ((size_t)2 * N + mmax);
+      if (smem > ctx->smem_optin) { ctx->err = "'aaa': frequency mesh too large for the shared-memory fit"; return SGW_E_UNSUPPORTED; }
+      if (smem > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_aaa_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int *dinfo = nullptr;
+      SGW_CHECK(ws(ctx, "an_info", (size_t)1, &dinfo));
+      SGW_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+      k_aaa_coeff<<<(unsigned)npair, 32, smem, ctx->stream>>>(npair, N, mmax, thres, dz, d, dinfo);
+      SGW_LAUNCH_CHECK();
+      int hinfo = 0;
+      SGW_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hinfo != 0) { ctx->err = "error occured in AAA approximation (singular value decomposition did not converge)"; return SGW_E_ARG; }
+    } else {
+      k_pade_coeff<<<(unsigned)((npair + 63) / 64), 64, 0, ctx->stream>>>(npair, N, dz, d);
+      SGW_LAUNCH_CHECK();
+    }
   }
   SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d, sizeof(cplx) * total, cudaMemcpyDeviceToHost, ctx->stream));
   SGW_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -134,3 +134,26 @@ def test_qp_eigval_linearisation():
     e, z = osg.qp_eigval(w, sig, 0.33)
     assert abs(z - 1 / 1.25) < 1e-12 and abs(e - (0.33 + z * (0.1 - 0.25 * 0.33))) < 1e-12
     assert osg.qp_eigval(w, sig, 5.0) == (5.0, 1.0)
+
+
+def test_aaa_recovers_a_rational_function():
+    """vendor/analytic/src/aaa.f90 restated: degree-3 rational data are fitted with 4 support points, interpolated at the
+    support points and continued off the mesh; the packed coefficient layout of analytic.f90:160-167 round-trips."""
+    z = 1j * 0.07 * np.arange(14) * (np.arange(14) + 1)
+    poles = np.array([0.9 + 0.3j, -1.7 + 0.2j, 0.4 - 2.9j])
+    res = np.array([1.0, -0.4 + 0.2j, 0.3])
+    f = lambda w: (res / (np.atleast_1d(w)[:, None] - poles)).sum(-1)
+    p, v, w = osg.aaa_generate(1e-10, z.size // 3, z, f(z))
+    assert p.size == 4 and np.all(np.diff(np.abs(p)) > 0)                  # mesh order (PACK)
+    assert _rel(osg.aaa_evaluate(p, v, w, z), f(z)) < 1e-12
+    assert _rel(osg.aaa_evaluate(p, v, w, [0.3 + 0.8j, -1.0j]), f([0.3 + 0.8j, -1.0j])) < 1e-11
+    assert np.array_equal(osg.aaa_evaluate(p, v, w, p), v)                # tabulated value at a support point
+    fo = osg.freqbins_type(z, np.array([0.1j]), np.ones(1), np.array([0j]), osg.NO_SYMMETRY)
+    scr = np.zeros((2, 2, z.size), complex, order="F")
+    scr[:, :, :] = f(z)[None, None, :] * np.array([[1.0, 2.0], [0.5j, -1.0]])[:, :, None]
+    data = scr.copy()
+    osg.analytic_coeff(osg.AAA_APPROX, 1e-10, fo, scr)
+    mmax = z.size // 3
+    assert np.count_nonzero(np.abs(scr[0, 1, 2 * mmax:]) > 1e-12) == 4 and np.all(scr[:, :, 3 * mmax:] == 0)
+    got = osg.analytic_eval(osg.AAA_APPROX, np.array([1, 2]), fo, scr, z[5])
+    assert _rel(got, data[:, :, 5]) < 1e-12
