@@ -180,7 +180,7 @@ def _sigma_setup(name, ngc, model, ncoul, nsig, nsolver=8, real_axis=False):
     import synth
     from oracle import sigma as osg
     from sternheimergw_b200 import freqbins_type
-    syn = synth.preset(name, nk=1 if name == "si" else 2)
+    syn = synth.preset(name, nk=1 if name in ("si", "bn") else 2)
     kq = syn.kpairs[0].kq
     nr_c, nl_c = synth.corr_grid(syn, ngc)
     pos = {int(g): i + 1 for i, g in enumerate(kq.igk)}
@@ -202,7 +202,7 @@ def _sigma_setup(name, ngc, model, ncoul, nsig, nsolver=8, real_axis=False):
 
 
 @pytest.mark.parametrize("name,ngc,model,real_axis", [("tiny", 9, 2, False), ("tiny", 15, 1, False), ("si", 15, 2, False),
-                                                      ("si", 59, 2, False), ("tiny", 9, 2, True), ("c", 15, 2, False), ("tiny", 9, 4, False)])
+                                                      ("si", 59, 2, False), ("tiny", 9, 2, True), ("c", 15, 2, False), ("tiny", 9, 4, False), ("bn", 11, 1, False)])
 def test_sigma_correlation_matches_oracle(ctx, name, ngc, model, real_axis):
     """Sigma_c(G, G', omega) for one (k, q) configuration: G solved to 1e-12 on both sides, W coefficients shared.
     Covers both models, the imaginary- and the real-axis convolution (conjugation rule sigma.f90:688) and a
