@@ -64,6 +64,12 @@ const char *sgw_last_error(const sgw_ctx *ctx);
 int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out);        /* stats of the last solver-level call */
 int sgw_set_profiling(sgw_ctx *ctx, int on);                  /* time H.psi separately (adds syncs) */
 int sgw_device_synchronize(sgw_ctx *ctx);
+/* The reference writes solver warnings to stdout ("WARNING: BiCGstab algorithm did not converge in N iterations."
+ * bicgstab.f90:250, "First choice of solver did not converge, try a different one" select_solver.f90:126, "WARNING:
+ * SternheimerGW linear solver did not converge" linear_solver.f90:177).  The library never prints: it hands the same lines
+ * (once per batch, with the number of right-hand sides concerned) to this callback, if one is set. */
+typedef void (*sgw_message_fn)(const char *message, void *user);
+int sgw_set_message_callback(sgw_ctx *ctx, sgw_message_fn fn, void *user);
 /* per-kernel-class device time of the last solver-level call (needs sgw_set_profiling(ctx, 1)): class i took ms[i]
  * milliseconds in regions[i] timed regions (one region = one kernel launch for fft_plane, gemm_project, gemm_expand,
  * shift_fused and rho_plane).  Labels via sgw_profile_class_name; the reference's clocks `linear operator` /

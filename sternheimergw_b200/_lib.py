@@ -12,7 +12,7 @@ c_int, c_double, c_void_p, c_int64 = C.c_int, C.c_double, C.c_void_p, C.c_int64
 # every symbol of include/sgw_b200.h (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "sgw_create", "sgw_destroy", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_device_synchronize",
-    "sgw_get_profile", "sgw_profile_class_name",
+    "sgw_get_profile", "sgw_profile_class_name", "sgw_set_message_callback",
     "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
     "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
     "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
@@ -31,6 +31,9 @@ class SolverCfg(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_linear_op", c_int64), ("n_kernel_launch", c_int64), ("n_outer_max", C.c_int32),
                 ("n_fallback", C.c_int32), ("ms_solver", c_double), ("ms_linear_op", c_double), ("ms_total", c_double)]
+
+
+MESSAGE_FN = C.CFUNCTYPE(None, C.c_char_p, c_void_p)      # sgw_message_fn
 
 
 class Cplx(C.Structure):
@@ -62,6 +65,7 @@ def load():
         L.sgw_get_stats.argtypes = [c_void_p, C.POINTER(Stats)]
         L.sgw_set_profiling.argtypes = [c_void_p, c_int]
         L.sgw_device_synchronize.argtypes = [c_void_p]
+        L.sgw_set_message_callback.argtypes = [c_void_p, MESSAGE_FN, c_void_p]
         L.sgw_get_profile.argtypes = [c_void_p, c_int, c_void_p, c_void_p, C.POINTER(c_int)]
         L.sgw_profile_class_name.restype = C.c_char_p
         L.sgw_profile_class_name.argtypes = [c_int]

@@ -239,6 +239,13 @@ const char *sgw_profile_class_name(int cls) {
   return cls >= 0 && cls < PC_N ? names[cls] : "";
 }
 
+int sgw_set_message_callback(sgw_ctx *ctx, sgw_message_fn fn, void *user) {
+  if (!ctx) return SGW_E_ARG;
+  ctx->msg_fn = fn;
+  ctx->msg_user = user;
+  return SGW_OK;
+}
+
 int sgw_device_synchronize(sgw_ctx *ctx) {
   if (!ctx) return SGW_E_ARG;
   SGW_CUDA(cudaStreamSynchronize(ctx->stream));

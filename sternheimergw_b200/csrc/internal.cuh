@@ -179,6 +179,8 @@ struct sgw_ctx {
   int gemm_cta_per_sm = 0;                       // resident k_zgemm CTAs per SM (0 = attributes not set yet)
   int sm_count = 148;
   size_t smem_optin = 0;
+  sgw_message_fn msg_fn = nullptr;               // sgw_set_message_callback: the reference's stdout warnings
+  void *msg_user = nullptr;
   sgw::CorrGrid corr;                            // sigma.cu
   bool gw_attr_set = false;
 };

@@ -349,6 +349,16 @@ int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_c
     SGW_CUDA(cudaMemcpyAsync(&h, nleft, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SGW_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h == 0) break;
+    if (ctx->msg_fn) {       // the reference writes these lines to stdout once per right-hand side; here once per batch
+      char buf[256];
+      if (cfg->priority[is] == 3)
+        snprintf(buf, sizeof buf, "WARNING: SternheimerGW linear solver did not converge (%d of %d right-hand sides)", h, sb.nrhs);   // linear_solver.f90:177
+      else
+        snprintf(buf, sizeof buf, "WARNING: BiCGstab algorithm did not converge in %d iterations. (%d of %d right-hand sides)",
+                 cfg->max_iter, h, sb.nrhs);                                                                                          // bicgstab.f90:250
+      ctx->msg_fn(buf, ctx->msg_user);
+      if (is + 1 < cfg->npriority) ctx->msg_fn("First choice of solver did not converge, try a different one", ctx->msg_user);       // select_solver.f90:126
+    }
     if (is + 1 < cfg->npriority) ctx->stats.n_fallback += h;
   }
   return SGW_OK;

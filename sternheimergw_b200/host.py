@@ -192,6 +192,12 @@ class Context:
         self._chk(self._L.sgw_get_profile(self._h, 16, ms, cnt, C.byref(n)), "get_profile")
         return {self._L.sgw_profile_class_name(i).decode(): {"ms": ms[i], "regions": int(cnt[i])} for i in range(n.value)}
 
+    def set_message_callback(self, fn):
+        """fn(str) receives the solver warnings the reference writes to stdout (bicgstab.f90:250, select_solver.f90:126,
+        linear_solver.f90:177); None removes the callback."""
+        self._msg_cb = _lib.MESSAGE_FN(lambda msg, _user: fn(msg.decode())) if fn is not None else _lib.MESSAGE_FN()
+        self._chk(self._L.sgw_set_message_callback(self._h, self._msg_cb, None), "set_message_callback")
+
     def synchronize(self):
         self._chk(self._L.sgw_device_synchronize(self._h), "synchronize")
 

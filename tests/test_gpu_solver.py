@@ -103,9 +103,15 @@ def test_select_solver_error_codes_and_fallback(ctx, lin_prob):
     assert np.abs(x).max() > 0          # the reference still copies the unconverged x out (bicgstab.f90:258)
     x, ierr = ctx.select_solver(select_solver_type(priority=(1, 3), threshold=1e-10, max_iter=40), 0, b, sigma)
     assert ierr == 0
+    msgs = []
+    ctx.set_message_callback(msgs.append)        # the reference's stdout warnings arrive through the callback
     x, ierr = ctx.select_solver(select_solver_type(priority=(1, 3), threshold=1e-10, max_iter=2), 0, b, sigma)
     st = ctx.stats()
+    ctx.set_message_callback(None)
     assert ierr == 1 and st["n_fallback"] == 1
+    assert len(msgs) == 3 and msgs[0].startswith("WARNING: BiCGstab algorithm did not converge in 2 iterations.")   # bicgstab.f90:250
+    assert msgs[1] == "First choice of solver did not converge, try a different one"                                 # select_solver.f90:126
+    assert msgs[2].startswith("WARNING: SternheimerGW linear solver did not converge")                              # linear_solver.f90:177
     x2, ierr2 = ctx.select_solver(select_solver_type(priority=(2,), threshold=1e-8), 0, b, sigma)
     assert ierr2 == 0
     for i, s in enumerate(sigma):
