@@ -60,6 +60,9 @@ typedef struct {
 /* ---- context (once per MPI rank / GPU, after mp_startup, main/src/gw.f90:83) ---- */
 int sgw_create(int device, sgw_ctx **ctx);
 int sgw_destroy(sgw_ctx *ctx);
+/* Run the library's kernels on a caller-owned CUDA stream (a cudaStream_t passed as void*) instead of the context's own
+ * non-blocking stream; NULL restores the context's stream.  The caller keeps ownership; calls stay blocking. */
+int sgw_set_stream(sgw_ctx *ctx, void *cuda_stream);
 const char *sgw_last_error(const sgw_ctx *ctx);
 int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out);        /* stats of the last solver-level call */
 int sgw_set_profiling(sgw_ctx *ctx, int on);                  /* time H.psi separately (adds syncs) */

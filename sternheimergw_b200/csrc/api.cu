@@ -176,6 +176,7 @@ int sgw_create(int device, sgw_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SGW_E_CUDA; }
+  ctx->own_stream = ctx->stream;
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   pool().contexts++;
@@ -206,7 +207,7 @@ int sgw_destroy(sgw_ctx *ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->corr.d_Ec) dev_free(ctx->corr.d_Ec);
   if (ctx->corr.d_ET) dev_free(ctx->corr.d_ET);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   if (--pool().contexts <= 0) { pool().contexts = 0; dev_pool_trim(); }
   return SGW_OK;
@@ -237,6 +238,14 @@ const char *sgw_profile_class_name(int cls) {
   static const char *names[PC_N] = {"fft_zpass", "fft_plane", "gemm_project", "gemm_expand", "shift_fused", "seed_blas1",
                                     "rho_plane", "other", "gw_product"};
   return cls >= 0 && cls < PC_N ? names[cls] : "";
+}
+
+int sgw_set_stream(sgw_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SGW_OK;
 }
 
 int sgw_set_message_callback(sgw_ctx *ctx, sgw_message_fn fn, void *user) {

@@ -137,6 +137,7 @@ struct Workspace {
 struct sgw_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;             // created by sgw_create; `stream` may point at a caller's stream (sgw_set_stream)
   std::string err;
   // grid
   bool grid_set = false, vloc_set = false, system_set = false;

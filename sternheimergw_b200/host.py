@@ -192,6 +192,11 @@ class Context:
         self._chk(self._L.sgw_get_profile(self._h, 16, ms, cnt, C.byref(n)), "get_profile")
         return {self._L.sgw_profile_class_name(i).decode(): {"ms": ms[i], "regions": int(cnt[i])} for i in range(n.value)}
 
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned CUDA stream (an integer handle such as torch.cuda.Stream.cuda_stream); None restores the
+        context's own stream."""
+        self._chk(self._L.sgw_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None), "set_stream")
+
     def set_message_callback(self, fn):
         """fn(str) receives the solver warnings the reference writes to stdout (bicgstab.f90:250, select_solver.f90:126,
         linear_solver.f90:177); None removes the callback."""

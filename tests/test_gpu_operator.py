@@ -77,3 +77,28 @@ def test_errors_are_loud(ctx):
         ctx.set_grid(7, 7, 7)                      # 7 is not a supported radix product
     with pytest.raises(SgwError):
         ctx.linear_op(999, [0.0], 0.0, np.zeros(10, complex))   # slot not set
+
+
+def test_caller_owned_stream_gives_identical_results():
+    """sgw_set_stream: the kernels run on a caller-owned CUDA stream; same bits as on the context's own stream."""
+    import torch
+    import synth
+    from sternheimergw_b200 import Context
+    syn = synth.preset("tiny")
+    c = Context(0)
+    try:
+        c.install_system(syn)
+        kq = syn.kpairs[0].kq
+        rng = np.random.default_rng(2)
+        psi = np.zeros((kq.npwx, 3), complex, order="F")
+        psi[:kq.npw] = rng.standard_normal((kq.npw, 3)) + 1j * rng.standard_normal((kq.npw, 3))
+        om = np.array([0.1, 0.2j, -0.3])
+        ref = c.linear_op(0, om, kq.alpha_pv, psi)
+        st = torch.cuda.Stream()
+        c.set_stream(st.cuda_stream)
+        got = c.linear_op(0, om, kq.alpha_pv, psi)
+        c.set_stream(None)
+        again = c.linear_op(0, om, kq.alpha_pv, psi)
+        assert np.array_equal(got, ref) and np.array_equal(again, ref)
+    finally:
+        c.close()
