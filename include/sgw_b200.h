@@ -175,7 +175,7 @@ typedef struct {
 #define SGW_PADE_APPROX 2
 #define SGW_PADE_ROBUST 3   /* not built: SGW_E_UNSUPPORTED */
 #define SGW_AAA_APPROX 4    /* 'aaa' (vendor/analytic/src/aaa.f90): greedy AAA fit, coefficients [position | value | weight] */
-#define SGW_AAA_POLE 5      /* not built: SGW_E_UNSUPPORTED */
+#define SGW_AAA_POLE 5      /* 'aaa pole': AAA fit, then poles and residues; coefficients [pole | residue] */
 /* freq%num_freq() = size of the symmetrised mesh (freqbins_symm, freqbins.f90:243-305); < 0 on error
  * (more than one frequency below 1e-14 with even symmetry, as the reference's errore). */
 int sgw_freqbins_num_freq(const sgw_freqbins *freq);
@@ -183,7 +183,8 @@ int sgw_freqbins_num_freq(const sgw_freqbins *freq);
 int sgw_coulpade(sgw_ctx *ctx, int ngc, int nfreq, const double *factor /* ngc */, sgw_cplx *scrcoul_g);
 /* analytic_coeff (analytic.f90:50): scrcoul_g(ngc, ngc, num_freq()) in place -> coefficients of the model
  * (Godby-Needs godby_needs.f90:34, Pade pade.f90 pade_coeff incl. the mirrored frequencies of freqbins_symm, AAA aaa.f90
- * with max_point = num_freq() / 3 and the relative threshold `thres`; the AAA weights are defined up to a common phase) */
+ * with max_point = num_freq() / 3 and the relative threshold `thres`; the AAA weights are defined up to a common phase;
+ * 'aaa pole': the same fit followed by aaa_pole_residual + pole_correction, poles in no particular order) */
 int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_freqbins *freq, int ngc, sgw_cplx *scrcoul_g);
 /* analytic_eval (analytic.f90:211) at nout frequencies at once: scrcoul(ig, igp, iout) =
  * model(coeff(gmapsym(ig), gmapsym(igp), :), freq%symmetrize(freq_out(iout))) -- the G-space block the reference

@@ -231,8 +231,15 @@ def analytic_coeff(model_coul, thres, freq: freqbins_type, scrcoul_g):
     elif model_coul == AAA_APPROX:
         z = freqbins_symm(freq.solver, freq.freq_symm_coul, scrcoul_g)
         scrcoul_g[:, :, :] = aaa_coeff_pack(thres, freq.num_freq() // 3, z, scrcoul_g)
+    elif model_coul == AAA_POLE:                                       # analytic.f90:141-172 with mmax = num_freq()
+        z = freqbins_symm(freq.solver, freq.freq_symm_coul, scrcoul_g)
+        n = freq.num_freq()
+        for igp in range(ngc):
+            for ig in range(ngc):
+                p, v, w = aaa_generate(thres, n, z, scrcoul_g[ig, igp, :].copy())
+                scrcoul_g[ig, igp, :] = pole_correction(thres, p, v, w, n)
     else:
-        raise NotImplementedError("'pade robust' and 'aaa pole' are not restated")
+        raise NotImplementedError("'pade robust' is not restated")
 
 
 def analytic_eval(model_coul, gmapsym, freq_in: freqbins_type, scrcoul_coeff, freq_out, fft_map=None):
@@ -248,6 +255,15 @@ def analytic_eval(model_coul, gmapsym, freq_in: freqbins_type, scrcoul_coeff, fr
         return pade_eval(z, coeff, freq_sym)
     if model_coul == GODBY_NEEDS:
         return godby_needs_model(freq_sym, coeff)
+    if model_coul == AAA_POLE:
+        half = coeff.shape[2] // 2
+        n = np.count_nonzero(np.abs(coeff[:, :, half:]) > 0.0, axis=2)
+        out = np.zeros(coeff.shape[:2], dtype=complex)
+        for k in range(half):
+            use = k < n
+            den = np.where(use, freq_sym - coeff[:, :, k], 1.0)
+            out += np.where(use, coeff[:, :, half + k] / den, 0.0)
+        return out
     if model_coul == AAA_APPROX:
         out = np.zeros(coeff.shape[:2], dtype=complex)
         for i in range(coeff.shape[0]):
@@ -444,3 +460,46 @@ def aaa_approx_eval(freq_sym, coeff):
     mmax = coeff.size // 3
     mm = int(np.count_nonzero(np.abs(coeff[2 * mmax:3 * mmax]) > 1e-12))
     return aaa_evaluate(coeff[:mm], coeff[mmax:mmax + mm], coeff[2 * mmax:2 * mmax + mm], freq_sym)[0]
+
+
+# ----------------------------------------------------------------------------- 'aaa pole' (aaa.f90 aaa_pole_residual, analytic.f90:345-400)
+def aaa_pole_residual(position, value, weight):
+    """aaa.f90 find_pole + calculate_residual: poles = finite eigenvalues of the arrowhead pencil (A, B) (ZGGEV), residues
+    from the four-point average sum_k f(pole + d_k) d_k / 4 with d = 1e-6 (1, i, -1, -i)."""
+    import scipy.linalg
+    m = position.size
+    a = np.zeros((m + 1, m + 1), dtype=complex)
+    b = np.zeros((m + 1, m + 1), dtype=complex)
+    a[0, 1:] = 1.0
+    a[1:, 0] = weight
+    a[np.arange(1, m + 1), np.arange(1, m + 1)] = position
+    b[np.arange(1, m + 1), np.arange(1, m + 1)] = 1.0
+    lam = scipy.linalg.eig(a, b, right=False, homogeneous_eigvals=True)
+    num, den = lam[0], lam[1]
+    fin = np.abs(den) > EPS14
+    pole = num[fin] / den[fin]
+    shift = 1e-6 * np.array([1.0, 1j, -1.0, -1j])
+    near = (pole[:, None] + shift[None, :]).ravel()
+    fnear = aaa_evaluate(position, value, weight, near).reshape(-1, 4)
+    return pole, (fnear * shift[None, :]).sum(axis=1) / 4.0
+
+
+def pole_correction(thres, position, value, weight, ncoeff):
+    """analytic.f90:345-377: keep the poles whose residue exceeds thres; layout [pole | residue], halves of ncoeff // 2."""
+    pole, res = aaa_pole_residual(position, value, weight)
+    half = ncoeff // 2
+    keep = np.abs(res) > thres
+    if np.count_nonzero(keep) > half:
+        raise ValueError("two many relevant poles, try reducing the coulomb threshold or increasing the number of frequencies")
+    out = np.zeros(ncoeff, dtype=complex)
+    k = int(np.count_nonzero(keep))
+    out[:k] = pole[keep]
+    out[half:half + k] = res[keep]
+    return out
+
+
+def aaa_pole_eval(freq_sym, coeff):
+    """analytic.f90:379-400: sum of residue / (freq - pole) over the stored poles."""
+    half = coeff.size // 2
+    n = int(np.count_nonzero(np.abs(coeff[half:]) > 0.0))
+    return (coeff[half:half + n] / (freq_sym - coeff[:n])).sum()

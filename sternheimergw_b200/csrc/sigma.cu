@@ -133,6 +133,12 @@ __global__ void k_analytic_eval(int model, int ngc, int N, const int *__restrict
       am2 = am1; am1 = a; bm2 = bm1; bm1 = b;
     }
     res = cdiv_nf(am1, bm1);
+  } else if (model == SGW_AAA_POLE) {                  // aaa_pole_eval (analytic.f90:379-400)
+    const int half = N / 2;
+    int npl = 0;
+    for (int j = 0; j < N - half; ++j) { const cplx rj = c[npair * (half + j)]; npl += (rj.x != 0.0 || rj.y != 0.0); }
+    res = cmake(0.0, 0.0);
+    for (int j = 0; j < npl; ++j) res = cadd(res, cdiv_nf(c[npair * (half + j)], csub(w, c[npair * j])));
   } else if (model == SGW_AAA_APPROX) {                // aaa_approx_eval (analytic.f90:312-343) + aaa_evaluate (aaa.f90)
     const int mmax = N / 3;
     int mm = 0;
@@ -179,8 +185,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // common phase (the approximant does not depend on it), so coefficient arrays are not comparable entry by entry with a
 // LAPACK-based fit; positions, values and the evaluated approximant are.
 // Shared memory: zz, ff, fit [N] | A [N x mmax] | V [mmax x mmax] | w [mmax] | sup [N] (int) | supidx [mmax] | rowidx [N]
+// pole_mode ('aaa pole', analytic.f90:345-377 + aaa.f90 aaa_pole_residual): after the fit, the m - 1 poles of the barycentric
+// form -- the roots of d(x) = sum_j w_j / (x - z_j), which the reference obtains as the finite eigenvalues of an arrowhead
+// pencil with ZGGEV -- are found by Aberth-Ehrlich iteration on p(x) = d(x) prod_j (x - z_j) (all roots at once, one lane per
+// root, p'/p = d'/d + sum_j 1/(x - z_j)); residues by the reference's four-point average around each pole; poles with
+// |residue| > thres are stored as [pole | residue] in halves of N / 2.
 __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, double thres, const cplx *__restrict__ z,
-                                                  cplx *__restrict__ scr, int *__restrict__ info) {
+                                                  cplx *__restrict__ scr, int *__restrict__ info, int pole_mode) {
   const long pair = blockIdx.x;
   if (pair >= npair) return;
   const int lane = threadIdx.x;
@@ -193,11 +204,11 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
   for (int i = lane; i < N; i += 32) { zz[i] = z[i]; ff[i] = scr[pair + npair * i]; sup[i] = 0; }
   __syncwarp();
   // average and absolute threshold (setup_work_type)
-  double fmax = 0.0;
-  for (int i = lane; i < N; i += 32) fmax = fmax > hypot(ff[i].x, ff[i].y) ? fmax : hypot(ff[i].x, ff[i].y);
+  double ffmax = 0.0;
+  for (int i = lane; i < N; i += 32) ffmax = ffmax > hypot(ff[i].x, ff[i].y) ? ffmax : hypot(ff[i].x, ff[i].y);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, fmax, o); fmax = fmax > t ? fmax : t; }
-  const double thr = thres * fmax;
+  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, ffmax, o); ffmax = ffmax > t ? ffmax : t; }
+  const double thr = thres * ffmax;
   cplx avg = cmake(0.0, 0.0);
   for (int i = 0; i < N; ++i) avg = cadd(avg, ff[i]);
   avg = cmake(avg.x / N, avg.y / N);
@@ -308,7 +319,113 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
     }
     notconv = __any_sync(0xffffffffu, notconv);
     __syncwarp();
-    if (!notconv || m >= mmax) break;
+    if (!notconv) break;
+    if (m >= mmax) {
+      if (pole_mode) bad = 2;        // the reference would go on up to N support points; the device fit stops at mmax = N / 2
+      break;
+    }
+  }
+  if (pole_mode) {
+    cplx *xk = A, *xn = A + mmax, *rs = A + 2 * mmax;      // the Loewner workspace is free now (N * mmax >= 3 * mmax entries)
+    const int npole = m - 1;
+    cplx cen = cmake(0.0, 0.0);
+    for (int c = 0; c < m; ++c) cen = cadd(cen, zz[supidx[c]]);
+    cen = cmake(cen.x / m, cen.y / m);
+    double rad = 0.0;
+    for (int c = 0; c < m; ++c) { const cplx d = csub(zz[supidx[c]], cen); rad = fmax(rad, hypot(d.x, d.y)); }
+    if (rad == 0.0) rad = 1.0;
+    for (int k = lane; k < npole; k += 32) {
+      double sn, cs;
+      sincos(6.283185307179586 * k / (npole > 0 ? npole : 1) + 0.35, &sn, &cs);
+      xk[k] = cmake(cen.x + 0.7 * rad * cs, cen.y + 0.7 * rad * sn);
+    }
+    __syncwarp();
+    const double scale = hypot(cen.x, cen.y) + rad;
+    for (int it = 0; it < 400 && npole > 0; ++it) {
+      double dmax = 0.0;
+      for (int k = lane; k < npole; k += 32) {
+        const cplx x = xk[k];
+        cplx d = cmake(0.0, 0.0), dp = cmake(0.0, 0.0), sz = cmake(0.0, 0.0);
+        for (int c = 0; c < m; ++c) {
+          cplx dz = csub(x, zz[supidx[c]]);
+          if (dz.x == 0.0 && dz.y == 0.0) dz = cmake(1e-300, 0.0);
+          const cplx t = cdiv_nf(cmake(1.0, 0.0), dz);
+          const cplx wt = cmul(w[c], t);
+          d = cadd(d, wt);
+          dp = csub(dp, cmul(wt, t));
+          sz = cadd(sz, t);
+        }
+        cplx rep = cmake(0.0, 0.0);
+        for (int l = 0; l < npole; ++l)
+          if (l != k) {
+            cplx dx = csub(x, xk[l]);
+            if (dx.x == 0.0 && dx.y == 0.0) dx = cmake(1e-300, 0.0);
+            rep = cadd(rep, cdiv_nf(cmake(1.0, 0.0), dx));
+          }
+        // Newton step p / p' = d / (d' + d sum_j 1/(x - z_j)), Aberth correction with the other roots
+        const cplx pden = cadd(dp, cmul(d, sz));
+        cplx delta = cmake(0.0, 0.0);
+        if (pden.x != 0.0 || pden.y != 0.0) {
+          const cplx nw = cdiv_nf(d, pden);
+          const cplx one_m = csub(cmake(1.0, 0.0), cmul(nw, rep));
+          delta = (one_m.x != 0.0 || one_m.y != 0.0) ? cdiv_nf(nw, one_m) : nw;
+        }
+        xn[k] = csub(x, delta);
+        dmax = fmax(dmax, hypot(delta.x, delta.y));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+      __syncwarp();
+      for (int k = lane; k < npole; k += 32) xk[k] = xn[k];
+      __syncwarp();
+      // converged to rounding level; ill-conditioned roots (pole-zero doublets with residues far below any threshold) keep
+      // moving by ~1e-12 of the scale, which is irrelevant for the approximant: accept 1e-12 at once, anything below 1e-8 at the end
+      if (!(dmax > 1e-12 * scale)) break;
+      if (it == 399 && dmax > 1e-8 * scale) bad = 1;
+    }
+    // residues: (1/4) sum_k f(pole + d_k) d_k, d = 1e-6 (1, i, -1, -i) (aaa.f90 calculate_residual / average_residual)
+    for (int k = lane; k < npole; k += 32) {
+      const cplx sh[4] = {cmake(1e-6, 0.0), cmake(0.0, 1e-6), cmake(-1e-6, 0.0), cmake(0.0, -1e-6)};
+      cplx acc = cmake(0.0, 0.0);
+      for (int q = 0; q < 4; ++q) {
+        const cplx x = cadd(xk[k], sh[q]);
+        cplx num = cmake(0.0, 0.0), den = cmake(0.0, 0.0);
+        double dmin = 1e300;
+        int jc = 0;
+        for (int c = 0; c < m; ++c) {
+          cplx dz = csub(x, zz[supidx[c]]);
+          const double dist = hypot(dz.x, dz.y);
+          if (dist < dmin) { dmin = dist; jc = c; }
+          if (dist <= 1e-14) dz = cmake(1e-14, 0.0);
+          const cplx cm = cdiv_nf(cmake(1.0, 0.0), dz);
+          num = cadd(num, cmul(cm, cmul(w[c], ff[supidx[c]])));
+          den = cadd(den, cmul(cm, w[c]));
+        }
+        cplx fv = cdiv_nf(num, den);
+        if (dmin < 1e-14) fv = ff[supidx[jc]];
+        acc = cadd(acc, cmul(fv, sh[q]));
+      }
+      rs[k] = cmake(0.25 * acc.x, 0.25 * acc.y);
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) scr[pair + npair * i] = cmake(0.0, 0.0);
+    __syncwarp();
+    if (lane == 0) {
+      const int half = N / 2;
+      int idx = 0;
+      for (int k = 0; k < npole; ++k) {
+        const cplx x = xk[k], r = rs[k];
+        const cplx dc = csub(x, cen);
+        const bool finite = (x.x == x.x) && (x.y == x.y) && hypot(dc.x, dc.y) < 1e8 * rad;   // ZGGEV: |denominator| > eps14
+        if (finite && hypot(r.x, r.y) > thres) {
+          if (idx < half) { scr[pair + npair * idx] = x; scr[pair + npair * (half + idx)] = r; }
+          ++idx;
+        }
+      }
+      if (idx > half) bad = 3;        // analytic.f90:362: two many relevant poles
+      if (bad) atomicMax(info, bad);
+    }
+    return;
   }
   // ---- analytic.f90:160-167: [position | value | weight], each block mmax long, zero padded
   for (int i = lane; i < N; i += 32) scr[pair + npair * i] = cmake(0.0, 0.0);
@@ -318,7 +435,7 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
     scr[pair + npair * (mmax + c)] = ff[supidx[c]];
     scr[pair + npair * (2 * mmax + c)] = w[c];
   }
-  if (bad && lane == 0) atomicExch(info, 1);
+  if (bad && lane == 0) atomicMax(info, bad);
 }
 
 // Ec(r, G) = exp(-i G r) (nnr x ngm) and ET(G, r) = exp(+i G r) (ngm x nnr); r = i1 + n1 (i2 + n2 i3) (QE column-major box),
@@ -512,11 +629,12 @@ static int symm_mesh(const sgw_freqbins *f, std::vector<cplx> *z, std::vector<in
 static int check_freq(sgw_ctx *ctx, const sgw_freqbins *f, int model) {
   SGW_ARG(f && f->num_solver > 0 && f->solver, "freqbins: solver frequencies missing");
   SGW_ARG(f->freq_symm_coul >= 0 && f->freq_symm_coul <= 2, "freqbins: freq_symm_coul must be 0, 1 or 2");
-  if (model == SGW_PADE_ROBUST || model == SGW_AAA_POLE) {
-    ctx->err = "model_coul 'pade robust' / 'aaa pole' are not built (SURVEY 8 f3 covers 'pade', 'godby-needs' and 'aaa')";
+  if (model == SGW_PADE_ROBUST) {
+    ctx->err = "model_coul 'pade robust' is not built (SURVEY 8 f3 covers 'pade', 'godby-needs', 'aaa' and 'aaa pole')";
     return SGW_E_UNSUPPORTED;
   }
-  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX || model == SGW_AAA_APPROX, "No screening model chosen!");   // analytic.f90:186
+  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX || model == SGW_AAA_APPROX || model == SGW_AAA_POLE,
+          "No screening model chosen!");                                                           // analytic.f90:186
   return SGW_OK;
 }
 
@@ -610,7 +728,8 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
     k_gn_coeff<<<(unsigned)((npair + 127) / 128), 128, 0, ctx->stream>>>(npair, freq->solver[1].im, d);
     SGW_LAUNCH_CHECK();
   } else {
-    if (model_coul == SGW_AAA_APPROX && N / 3 < 1) { ctx->err = "'aaa' needs at least 3 frequencies"; return SGW_E_ARG; }
+    const bool aaa = model_coul == SGW_AAA_APPROX || model_coul == SGW_AAA_POLE;
+    if (aaa && N / 3 < 1) { ctx->err = "'aaa' needs at least 3 frequencies"; return SGW_E_ARG; }
     SGW_CUDA(cudaMemcpyAsync(dz, z.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, ctx->stream));
     if (!src.empty()) {
       int *dsrc = nullptr, *ddst = nullptr;
@@ -622,8 +741,10 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
       k_mirror<<<grid, 256, 0, ctx->stream>>>(npair, (int)src.size(), dsrc, ddst, d);
       SGW_LAUNCH_CHECK();
     }
-    if (model_coul == SGW_AAA_APPROX) {
-      const int mmax = N / 3;                                                                   // analytic.f90:148
+    if (aaa) {
+      // analytic.f90:146-148: max_point = num_freq() / 3 for 'aaa'; 'aaa pole' allows num_freq() -- the device fit stops at
+      // num_freq() / 2 (beyond that the Loewner submatrix has fewer rows than columns) and reports it
+      const int mmax = model_coul == SGW_AAA_APPROX ? N / 3 : N / 2;
       const size_t smem = sizeof(cplx) * ((size_t)3 * N + (size_t)N * mmax + (size_t)mmax * mmax + mmax) +
                           sizeof(int) * ((size_t)2 * N + mmax);
       if (smem > ctx->smem_optin) { ctx->err = "'aaa': frequency mesh too large for the shared-memory fit"; return SGW_E_UNSUPPORTED; }
@@ -631,12 +752,20 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
       int *dinfo = nullptr;
       SGW_CHECK(ws(ctx, "an_info", (size_t)1, &dinfo));
       SGW_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
-      k_aaa_coeff<<<(unsigned)npair, 32, smem, ctx->stream>>>(npair, N, mmax, thres, dz, d, dinfo);
+      k_aaa_coeff<<<(unsigned)npair, 32, smem, ctx->stream>>>(npair, N, mmax, thres, dz, d, dinfo, model_coul == SGW_AAA_POLE ? 1 : 0);
       SGW_LAUNCH_CHECK();
       int hinfo = 0;
       SGW_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       SGW_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (hinfo != 0) { ctx->err = "error occured in AAA approximation (singular value decomposition did not converge)"; return SGW_E_ARG; }
+      if (hinfo == 3) {
+        ctx->err = "two many relevant poles, try reducing the coulomb threshold or increasing the number of frequencies";   // analytic.f90:362
+        return SGW_E_ARG;
+      }
+      if (hinfo == 2) {
+        ctx->err = "'aaa pole': fit not converged with num_freq() / 2 support points (the reference continues up to num_freq())";
+        return SGW_E_UNSUPPORTED;
+      }
+      if (hinfo != 0) { ctx->err = "error occured in AAA approximation (iteration for the singular vector / the poles did not converge)"; return SGW_E_ARG; }
     } else {
       k_pade_coeff<<<(unsigned)((npair + 63) / 64), 64, 0, ctx->stream>>>(npair, N, dz, d);
       SGW_LAUNCH_CHECK();

@@ -157,3 +157,21 @@ def test_aaa_recovers_a_rational_function():
     assert np.count_nonzero(np.abs(scr[0, 1, 2 * mmax:]) > 1e-12) == 4 and np.all(scr[:, :, 3 * mmax:] == 0)
     got = osg.analytic_eval(osg.AAA_APPROX, np.array([1, 2]), fo, scr, z[5])
     assert _rel(got, data[:, :, 5]) < 1e-12
+
+
+def test_aaa_pole_recovers_poles_and_residues():
+    """'aaa pole' restated (aaa.f90 aaa_pole_residual via ZGGEV, analytic.f90 pole_correction / aaa_pole_eval): the three poles
+    and residues of a rational function come back, the stored sum reproduces the function."""
+    z = 1j * 0.07 * np.arange(14) * (np.arange(14) + 1)
+    poles = np.array([0.9 + 0.3j, -1.7 + 0.2j, 0.4 - 2.9j])
+    res = np.array([1.0, -0.4 + 0.2j, 0.3])
+    f = lambda w: (res / (np.atleast_1d(w)[:, None] - poles)).sum(-1)
+    p, v, w = osg.aaa_generate(1e-10, z.size, z, f(z))
+    pl, rs = osg.aaa_pole_residual(p, v, w)
+    o, o0 = np.argsort(pl.real), np.argsort(poles.real)
+    assert np.abs(pl[o] - poles[o0]).max() < 1e-9 and np.abs(rs[o] - res[o0]).max() < 1e-8
+    c = osg.pole_correction(1e-8, p, v, w, z.size)
+    assert np.count_nonzero(c[z.size // 2:]) == 3
+    assert abs(osg.aaa_pole_eval(0.3 + 0.8j, c) - f(0.3 + 0.8j)[0]) < 1e-8
+    with pytest.raises(ValueError):                    # analytic.f90:362: more relevant poles than half the array can hold
+        osg.pole_correction(1e-8, p, v, w, 4)
