@@ -503,3 +503,125 @@ def aaa_pole_eval(freq_sym, coeff):
     half = coeff.size // 2
     n = int(np.count_nonzero(np.abs(coeff[half:]) > 0.0))
     return (coeff[half:half + n] / (freq_sym - coeff[:n])).sum()
+
+
+# ----------------------------------------------------------------------------- 'pade robust' (algo/analytic/src/pade_robust.f90)
+def pade_derivative(radius, func, tol, num_deriv):
+    """pade_robust.f90:448-536: Taylor coefficients from samples on the circle of `radius` (cft_1z backward = forward DFT / N),
+    rescaled by radius^-k, small entries zeroed, imaginary parts dropped when they are all noise."""
+    func = np.asarray(func, dtype=complex)
+    n = func.size
+    work = np.fft.fft(func) / n
+    deriv = np.zeros(num_deriv, dtype=complex)
+    m = min(num_deriv, n)
+    deriv[:m] = work[:m]
+    if abs(radius - 1.0) > EPS14:
+        rescale = 1.0
+        for k in range(1, m):
+            rescale = rescale / radius
+            deriv[k] = deriv[k] * rescale
+    abs_tol = tol * np.linalg.norm(deriv)
+    deriv[np.abs(deriv) < abs_tol] = 0.0
+    if np.abs(deriv.imag).max() < abs_tol:
+        deriv = deriv.real.astype(complex)
+    return deriv
+
+
+def _toeplitz_nonsym(col, row):
+    """pade_robust.f90:539-587 (column wins the diagonal)."""
+    nr, nc = col.size, row.size
+    i, j = np.indices((nr, nc))
+    return np.where(i < j, row[np.clip(j - i, 0, nc - 1)], col[np.clip(i - j, 0, nr - 1)])
+
+
+def pade_robust(radius, func, deg_num, deg_den, tol_coeff=None, tol_fft=None):
+    """pade_robust.f90:177-443 (Gonnet, Guettel, Trefethen): returns (deg_num, deg_den, coeff_num, coeff_den)."""
+    if radius <= 0:
+        raise ValueError("radius in the complex plane must be > 0")
+    rel_tol = EPS14 if tol_coeff is None else tol_coeff
+    rel_tol_fft = rel_tol if tol_fft is None else tol_fft
+    coeff = pade_derivative(radius, func, rel_tol_fft, deg_num + deg_den + 1)
+    abs_tol = rel_tol * np.linalg.norm(coeff)
+    if np.abs(coeff[:deg_num + 1]).max() <= rel_tol * np.abs(coeff).max():
+        return 0, 0, np.zeros(1, complex), np.ones(1, complex)
+    row = np.zeros(deg_den + 1, dtype=complex)
+    row[0] = coeff[0]
+    col = coeff
+    cmat = zmat = None
+    while True:
+        if deg_den == 0:
+            return_num, return_den = coeff[:deg_num + 1].copy(), np.ones(1, complex)
+            break
+        zmat = _toeplitz_nonsym(col[:deg_num + deg_den + 1], row[:deg_den + 1])
+        cmat = zmat[deg_num + 1:deg_num + deg_den + 1, :]
+        sigma = np.linalg.svd(cmat, compute_uv=False)
+        rho = int(np.count_nonzero(sigma > abs_tol))
+        if rho == deg_den:
+            return_num = return_den = None
+            break
+        deg_num -= deg_den - rho
+        deg_den = rho
+    coeff_num, coeff_den = return_num, return_den
+    if deg_den > 0 and deg_num > 1:                                    # :386 (with deg_den == 0 the reference has no cmat left)
+        vh = np.linalg.svd(cmat, full_matrices=True)[2]
+        coeff_den = vh[deg_den, :].copy()                              # last row of V^H (:389); only |.| of it is used
+        dmat = np.abs(coeff_den) + np.sqrt(np.finfo(float).eps)
+        work = (cmat * dmat[None, :]).T                                # matmul_transpose: plain transpose of C diag(d)
+        q = np.linalg.qr(work, mode="complete")[0]
+        coeff_den = dmat * q[:, deg_den]
+        coeff_den = coeff_den / np.linalg.norm(coeff_den)
+        coeff_num = zmat[:deg_num + 1, :deg_den + 1] @ coeff_den
+        nz = np.nonzero(np.abs(coeff_den) > rel_tol)[0]
+        lam = int(nz[0])                                               # first_nonzero - 1
+        if lam > 0:
+            deg_num -= lam
+            deg_den -= lam
+            coeff_num, coeff_den = coeff_num[lam:], coeff_den[lam:]
+        nz = np.nonzero(np.abs(coeff_den) > rel_tol)[0]
+        lam = int(nz[-1])                                              # last_nonzero - 1
+        if lam != deg_den:
+            deg_den = lam
+            coeff_den = coeff_den[:deg_den + 1]
+    elif coeff_den is None:
+        # deg_num <= 1 with deg_den > 0: the reference leaves coeff_num / coeff_den unallocated (:386 guards their only
+        # assignment); undefined there, and it does not occur for the degrees pade_coeff_robust requests
+        raise NotImplementedError("pade_robust with deg_num <= 1 and deg_den > 0 is undefined in the reference")
+    nz = np.nonzero(np.abs(coeff_num) > abs_tol)[0]
+    lam = int(nz[-1]) if nz.size else -1                               # last_nonzero - 1
+    if lam != deg_num:
+        deg_num = lam
+        coeff_num = coeff_num[:deg_num + 1]
+    coeff_num = coeff_num / coeff_den[0]
+    coeff_den = coeff_den / coeff_den[0]
+    return deg_num, deg_den, coeff_num, coeff_den
+
+
+def pade_coeff_robust(freq, func):
+    """pade_robust.f90:91-162: frequencies on a circle; coefficient layout [deg_num, deg_den, numerator, denominator]."""
+    freq = np.asarray(freq, dtype=complex)
+    if freq.size < 10:
+        raise ValueError("use at least 10 frequencies to form the circle")
+    radius = freq[0].real
+    if np.any(np.abs(np.abs(freq) - radius) > 1e-12):
+        raise ValueError("frequencies must span circle in the complex plane")
+    n = func.shape[2]
+    for jj in range(func.shape[1]):
+        for ii in range(func.shape[0]):
+            dn, dd, cn, cd = pade_robust(radius, func[ii, jj, :].copy(), n // 2 - 2, n // 2 - 2)
+            func[ii, jj, :] = 0.0          # (the reference leaves the tail untouched; it is never read)
+            func[ii, jj, 0] = dn
+            func[ii, jj, 1] = dd
+            func[ii, jj, 2:4 + dn + dd] = np.concatenate([cn, cd])
+
+
+def pade_eval_robust(coeff, freq):
+    """pade_robust.f90:38-88: Horner evaluation of numerator and denominator."""
+    dn = int(np.rint(abs(coeff[0])))
+    dd = int(np.rint(abs(coeff[1])))
+    num = 0j
+    for c in coeff[2:3 + dn][::-1]:
+        num = c + num * freq
+    den = 0j
+    for c in coeff[3 + dn:4 + dn + dd][::-1]:
+        den = c + den * freq
+    return num / den

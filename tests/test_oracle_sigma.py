@@ -175,3 +175,35 @@ def test_aaa_pole_recovers_poles_and_residues():
     assert abs(osg.aaa_pole_eval(0.3 + 0.8j, c) - f(0.3 + 0.8j)[0]) < 1e-8
     with pytest.raises(ValueError):                    # analytic.f90:362: more relevant poles than half the array can hold
         osg.pole_correction(1e-8, p, v, w, 4)
+
+
+def test_pade_robust_reproduces_the_reference_golden_numbers():
+    """algo/analytic/test/pade.pf:120-200 -- the reference's own known-answer test of pade_robust (exp on the unit circle,
+    degrees (4, 4); cos on the circle of radius 2, degrees (5, 11) reduced to (4, 10)), same numbers, same thresholds.
+    This is the one golden vector the reference holds in algo/analytic; it pins the restated pade_robust.f90."""
+    circle = lambda radius, n: radius * np.exp(2j * np.pi * np.arange(n) / n)       # pade_problem_evaluate
+    dn, dd, cn, cd = osg.pade_robust(1.0, np.exp(circle(1.0, 25)), 4, 4)
+    assert (dn, dd, cn.size, cd.size) == (4, 4, 5, 5)
+    for got, want in zip(cn, [1.000000000000000, 0.499999999987559, 0.107142857136564, 0.011904761903482, 5.952380951286663e-4]):
+        assert abs(got - want) < 1e-10
+    for got, want in zip(cd, [1.000000000000000, -0.500000000012441, 0.107142857149005, -0.011904761905969, 5.952380953354424e-4]):
+        assert abs(got - want) < 1e-10
+    dn, dd, cn, cd = osg.pade_robust(2.0, np.cos(circle(2.0, 25)), 5, 11, 1e-10, 1e-15)
+    assert (dn, dd, cn.size, cd.size) == (4, 10, 5, 11)
+    for got, want in zip(cn, [1.0, -5.736142091971364e-19, -0.450639141234688, 2.325721027857943e-19, 0.018381449098078]):
+        assert abs(got - want) < 1e-8
+    for got, want in zip(cd, [1.0, -5.736142091971364e-19, 0.049360858765312, -5.423500181277404e-20, 0.001395211814067,
+                              -3.222944976341087e-21, 2.979234736799848e-05, -1.468353270738426e-22, 5.175090814695919e-07,
+                              -3.717349899090172e-24, 6.546464226759871e-09]):
+        assert abs(got - want) < 1e-8
+    # the coefficient layout of pade_coeff_robust and its evaluation
+    z = circle(1.5, 24)
+    f = np.zeros((1, 2, 24), complex)
+    f[0, 0, :] = np.exp(z)
+    g = lambda w: (1.0 + w + w * w) / (w - 3.0)       # [2/1]: (a numerator of degree <= 1 is undefined in the reference, :386)
+    f[0, 1, :] = g(z)
+    osg.pade_coeff_robust(z, f)
+    for w in (0.3 + 0.2j, -0.7j):
+        assert abs(osg.pade_eval_robust(f[0, 0, :], w) - np.exp(w)) < 1e-9
+        assert abs(osg.pade_eval_robust(f[0, 1, :], w) - g(w)) < 1e-5      # FFT aliasing (r / 3)^24 of the Taylor coefficients
+    assert (int(f[0, 1, 0].real), int(f[0, 1, 1].real)) == (2, 1)      # the robust algorithm finds the true degrees
