@@ -173,7 +173,7 @@ typedef struct {
 } sgw_freqbins;
 #define SGW_GODBY_NEEDS 1   /* analytic.f90:39-60 model_coul values */
 #define SGW_PADE_APPROX 2
-#define SGW_PADE_ROBUST 3   /* not built: SGW_E_UNSUPPORTED */
+#define SGW_PADE_ROBUST 3   /* 'pade robust' (pade_robust.f90): solver frequencies on a circle, coefficients [deg_num, deg_den, num, den] */
 #define SGW_AAA_APPROX 4    /* 'aaa' (vendor/analytic/src/aaa.f90): greedy AAA fit, coefficients [position | value | weight] */
 #define SGW_AAA_POLE 5      /* 'aaa pole': AAA fit, then poles and residues; coefficients [pole | residue] */
 /* freq%num_freq() = size of the symmetrised mesh (freqbins_symm, freqbins.f90:243-305); < 0 on error
@@ -186,6 +186,12 @@ int sgw_coulpade(sgw_ctx *ctx, int ngc, int nfreq, const double *factor /* ngc *
  * with max_point = num_freq() / 3 and the relative threshold `thres`; the AAA weights are defined up to a common phase;
  * 'aaa pole': the same fit followed by aaa_pole_residual + pole_correction, poles in no particular order) */
 int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_freqbins *freq, int ngc, sgw_cplx *scrcoul_g);
+/* pade_robust (algo/analytic/src/pade_robust.f90:177; the routine the reference's unit test algo/analytic/test/pade.pf
+ * exercises): func(num_point) sampled on the circle radius * exp(2 pi i j / num_point); deg_num / deg_den in: requested, out:
+ * found; coeff_num / coeff_den need room for the requested degrees + 1; tol_coeff, tol_fft <= 0 select the reference's defaults
+ * (1e-14, tol_coeff). */
+int sgw_pade_robust(sgw_ctx *ctx, double radius, int num_point, const sgw_cplx *func, int *deg_num, int *deg_den,
+                    sgw_cplx *coeff_num, sgw_cplx *coeff_den, double tol_coeff, double tol_fft);
 /* analytic_eval (analytic.f90:211) at nout frequencies at once: scrcoul(ig, igp, iout) =
  * model(coeff(gmapsym(ig), gmapsym(igp), :), freq%symmetrize(freq_out(iout))) -- the G-space block the reference
  * stores in the corner of scrcoul(nnr_c, nnr_c'). */

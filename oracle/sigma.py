@@ -11,8 +11,8 @@ numpy restatement, in the reference's execution order, of SURVEY.md section 8 ro
                                    data/fft/src/fft6.f90:84 (fwfft6), :231 (invfft6)
 
 The reference cannot be compiled here (Fortran 2003 + QE 6.3).  Its only unit test in this area (algo/analytic/test/pade.pf)
-covers `pade_robust`, which is not restated (no BASELINE config uses it), so for these routines (incl. the 'aaa' model of
-vendor/analytic/src/aaa.f90) **parity is unpinned** by
+covers `pade_robust`: that routine is restated below and PINNED by the test's known-answer numbers.  For the other routines
+(incl. the 'aaa' models of vendor/analytic/src/aaa.f90) **parity is unpinned** by
 reference tests; tests/test_oracle_sigma.py anchors them by independent properties instead: the Pade approximant
 interpolates its input, the Godby-Needs model reproduces its two input frequencies, fft6 equals numpy's 6-D fftn, and
 sigma_prod equals the explicit G-space convolution.

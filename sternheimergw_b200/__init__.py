@@ -11,7 +11,7 @@ Host-side mirror (Python, over the C ABI of include/sgw_b200.h) of the reference
     parallel_task                        data/parallel/src/parallel.f90:80
     freqbins_type / freqbins             algo/grid/src/freqbins.f90:42,109 (+ gauleg_grid.f90)
     coulpade                             phys/coul/src/coulpade.f90:36
-    analytic_coeff / analytic_eval       algo/analytic/src/analytic.f90:50,211 ('pade', 'godby-needs', 'aaa', 'aaa pole')
+    analytic_coeff / analytic_eval       algo/analytic/src/analytic.f90:50,211 (all five model_coul values)
     invfft6 / fwfft6                     data/fft/src/fft6.f90:231,84
     sigma_correlation                    phys/corr/src/sigma.f90:528
 

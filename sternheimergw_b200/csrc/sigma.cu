@@ -133,6 +133,12 @@ __global__ void k_analytic_eval(int model, int ngc, int N, const int *__restrict
       am2 = am1; am1 = a; bm2 = bm1; bm1 = b;
     }
     res = cdiv_nf(am1, bm1);
+  } else if (model == SGW_PADE_ROBUST) {               // pade_eval_robust (pade_robust.f90:38-88): Horner, numerator / denominator
+    const int dn = (int)rint(hypot(c[0].x, c[0].y)), dd = (int)rint(hypot(c[npair].x, c[npair].y));
+    cplx nu = cmake(0.0, 0.0), de = cmake(0.0, 0.0);
+    for (int i = 2 + dn; i >= 2; --i) nu = cadd(c[npair * i], cmul_nf(nu, w));
+    for (int i = 3 + dn + dd; i >= 3 + dn; --i) de = cadd(c[npair * i], cmul_nf(de, w));
+    res = cdiv_nf(nu, de);
   } else if (model == SGW_AAA_POLE) {                  // aaa_pole_eval (analytic.f90:379-400)
     const int half = N / 2;
     int npl = 0;
@@ -175,6 +181,60 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// One-sided (Hestenes) Jacobi on the columns of the R x m matrix A (column-major, shared memory), executed by one warp:
+// on return the columns are mutually orthogonal (their norms are the singular values, zero columns span the null space) and
+// V (m x m, must hold the identity on entry) accumulates the rotations: A_in V = A_out.  Returns 1 if 60 sweeps were not enough.
+__device__ int warp_jacobi(cplx *A, int R, int m, cplx *V, int lane) {
+  // columns that have become numerically zero (norm below 1e-14 of the largest column: the null space of a rank-deficient or
+  // wide matrix) are left alone: their inner products with the other columns are rounding noise of the same relative size as
+  // their norm, so the relative criterion below would rotate them for ever
+  double s2max = 0.0;
+  for (int c = 0; c < m; ++c) {
+    double nn = 0.0;
+    for (int r = lane; r < R; r += 32) { const cplx x = A[r + (long)R * c]; nn += x.x * x.x + x.y * x.y; }
+    s2max = fmax(s2max, warp_sum_d(nn));
+  }
+  const double floor2 = 1e-28 * s2max;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    int rotated = 0;
+    for (int p = 0; p < m - 1; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        cplx *ap = A + (long)R * p, *aq = A + (long)R * q;
+        double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+        for (int r = lane; r < R; r += 32) {
+          const cplx x = ap[r], y = aq[r];
+          al += x.x * x.x + x.y * x.y;
+          be += y.x * y.x + y.y * y.y;
+          gr += x.x * y.x + x.y * y.y;          // conj(x) * y
+          gi += x.x * y.y - x.y * y.x;
+        }
+        al = warp_sum_d(al); be = warp_sum_d(be); gr = warp_sum_d(gr); gi = warp_sum_d(gi);
+        const double g2 = gr * gr + gi * gi;
+        if (!(g2 > 1e-30 * al * be) || g2 == 0.0 || al <= floor2 || be <= floor2) continue;
+        rotated = 1;
+        const double gabs = sqrt(g2);
+        const cplx phc = cmake(gr / gabs, -gi / gabs);            // conj(gamma / |gamma|)
+        const double zeta = (be - al) / (2.0 * gabs);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int r = lane; r < R; r += 32) {
+          const cplx x = ap[r], y = cmul(aq[r], phc);
+          ap[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+          aq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+        }
+        cplx *vp = V + (long)m * p, *vq = V + (long)m * q;
+        for (int r = lane; r < m; r += 32) {
+          const cplx x = vp[r], y = cmul(vq[r], phc);
+          vp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+          vq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+        }
+        __syncwarp();
+      }
+    if (!rotated) return 0;
+  }
+  return 1;
 }
 
 // Greedy AAA fit of one (G, G') pair per warp (aaa_generate): support point = first maximum of |f - fit|, weights = right
@@ -250,44 +310,7 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
     for (int i = lane; i < m * m; i += 32) V[i] = (i % m == i / m) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
     __syncwarp();
     // ---- one-sided Jacobi on the columns of A
-    for (int sweep = 0; sweep < 60; ++sweep) {
-      int rotated = 0;
-      for (int p = 0; p < m - 1; ++p)
-        for (int q = p + 1; q < m; ++q) {
-          cplx *ap = A + (long)R * p, *aq = A + (long)R * q;
-          double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
-          for (int r = lane; r < R; r += 32) {
-            const cplx x = ap[r], y = aq[r];
-            al += x.x * x.x + x.y * x.y;
-            be += y.x * y.x + y.y * y.y;
-            gr += x.x * y.x + x.y * y.y;          // conj(x) * y
-            gi += x.x * y.y - x.y * y.x;
-          }
-          al = warp_sum_d(al); be = warp_sum_d(be); gr = warp_sum_d(gr); gi = warp_sum_d(gi);
-          const double g2 = gr * gr + gi * gi;
-          if (!(g2 > 1e-30 * al * be) || g2 == 0.0) continue;
-          rotated = 1;
-          const double gabs = sqrt(g2);
-          const cplx phc = cmake(gr / gabs, -gi / gabs);            // conj(gamma / |gamma|)
-          const double zeta = (be - al) / (2.0 * gabs);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-          for (int r = lane; r < R; r += 32) {
-            const cplx x = ap[r], y = cmul(aq[r], phc);
-            ap[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
-            aq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
-          }
-          cplx *vp = V + (long)m * p, *vq = V + (long)m * q;
-          for (int r = lane; r < m; r += 32) {
-            const cplx x = vp[r], y = cmul(vq[r], phc);
-            vp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
-            vq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
-          }
-          __syncwarp();
-        }
-      if (!rotated) break;
-      if (sweep == 59) bad = 1;
-    }
+    if (warp_jacobi(A, R, m, V, lane)) bad = 1;
     // ---- weights = column of V that belongs to the smallest column norm
     int jmin = 0;
     double smin = 1e300;
@@ -434,6 +457,179 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
     scr[pair + npair * c] = zz[supidx[c]];
     scr[pair + npair * (mmax + c)] = ff[supidx[c]];
     scr[pair + npair * (2 * mmax + c)] = w[c];
+  }
+  if (bad && lane == 0) atomicMax(info, bad);
+}
+
+// ---------------------------------------------------------------- robust Pade ('pade robust', algo/analytic/src/pade_robust.f90)
+// One warp per function (Gonnet-Guettel-Trefethen as coded in pade_robust.f90:177-443): Taylor coefficients from the samples on
+// the circle (pade_derivative :448, a DFT here), the rank of the Toeplitz block by the singular values (column norms after
+// warp_jacobi) with the degree reduction loop (:343-372), the null vector of C and of C diag(|b| + sqrt(eps)) (the reference's
+// SVD + QR of the transposed weighted matrix :386-397: its Q(:, n+1) is the conjugate of that null vector up to a phase, which
+// the final division by coeff_den(1) removes), trimming of leading / trailing zeros, normalisation.
+// Shared memory: fs [N] | cf [K] | C [dmax x (dmax+1)] | V [(dmax+1)^2] | den [dmax+1] | num [K] | dm (double) [dmax+1]
+// Output per function: out[0] = deg_num, out[1] = deg_den, out[2 ..] = numerator then denominator (pade_coeff_robust :150-152).
+__global__ void __launch_bounds__(32) k_pade_robust(long nfun, int N, double radius, int deg_num0, int deg_den0, double rel_tol,
+                                                    double rel_tol_fft, cplx *__restrict__ scr, long fstride, long estride,
+                                                    int *__restrict__ info) {
+  const long fun = blockIdx.x;
+  if (fun >= nfun) return;
+  const int lane = threadIdx.x;
+  const int K = deg_num0 + deg_den0 + 1, dmx = deg_den0;
+  extern __shared__ cplx pr_sm[];
+  cplx *fs = pr_sm, *cf = fs + N, *C = cf + K, *V = C + (long)dmx * (dmx + 1), *den = V + (long)(dmx + 1) * (dmx + 1), *num = den + dmx + 1;
+  double *dm = (double *)(num + K);
+  cplx *f = scr + fun * fstride;
+  for (int i = lane; i < N; i += 32) fs[i] = f[(long)i * estride];
+  __syncwarp();
+  // ---- pade_derivative: cf_k = (1/N) sum_j f_j exp(-2 pi i j k / N), rescaled by radius^-k
+  for (int k = lane; k < K; k += 32) {
+    cplx acc = cmake(0.0, 0.0);
+    if (k < N)
+      for (int j = 0; j < N; ++j) {
+        double sn, cs;
+        sincospi(-2.0 * (double)(((long)j * k) % N) / N, &sn, &cs);
+        acc = cfma(fs[j], cmake(cs, sn), acc);
+      }
+    cf[k] = cmake(acc.x / N, acc.y / N);
+  }
+  __syncwarp();
+  if (lane == 0 && fabs(radius - 1.0) > 1e-14) {
+    double rescale = 1.0;
+    for (int k = 1; k < min(K, N); ++k) { rescale = rescale / radius; cf[k] = cscale(rescale, cf[k]); }
+  }
+  __syncwarp();
+  double n2 = 0.0;
+  for (int k = lane; k < K; k += 32) n2 += cf[k].x * cf[k].x + cf[k].y * cf[k].y;
+  n2 = warp_sum_d(n2);
+  const double tol_fft_abs = rel_tol_fft * sqrt(n2);
+  for (int k = lane; k < K; k += 32) if (hypot(cf[k].x, cf[k].y) < tol_fft_abs) cf[k] = cmake(0.0, 0.0);
+  __syncwarp();
+  double imax = 0.0;
+  for (int k = lane; k < K; k += 32) imax = fmax(imax, fabs(cf[k].y));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) imax = fmax(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+  if (imax < tol_fft_abs) for (int k = lane; k < K; k += 32) cf[k].y = 0.0;
+  __syncwarp();
+  // ---- tolerances of the coefficient stage
+  n2 = 0.0;
+  double amax = 0.0, amax_num = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const double a = hypot(cf[k].x, cf[k].y);
+    n2 += cf[k].x * cf[k].x + cf[k].y * cf[k].y;
+    amax = fmax(amax, a);
+    if (k <= deg_num0) amax_num = fmax(amax_num, a);
+  }
+  n2 = warp_sum_d(n2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o)); amax_num = fmax(amax_num, __shfl_xor_sync(0xffffffffu, amax_num, o)); }
+  const double abs_tol = rel_tol * sqrt(n2);
+  int dn = deg_num0, dd = deg_den0, trivial = 0, have_c = 0, bad = 0;
+  if (amax_num <= rel_tol * amax) { dn = 0; dd = 0; trivial = 1; }          // :326-334
+  // ---- degree reduction by the rank of the Toeplitz block (:343-372)
+  while (!trivial && dd > 0) {
+    for (int i = lane; i < dd * (dd + 1); i += 32) {
+      const int a = i % dd, j = i / dd, idx = dn + 1 + a - j;
+      C[i] = idx >= 0 ? cf[idx] : cmake(0.0, 0.0);
+    }
+    for (int i = lane; i < (dd + 1) * (dd + 1); i += 32) V[i] = (i % (dd + 1) == i / (dd + 1)) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+    __syncwarp();
+    if (warp_jacobi(C, dd, dd + 1, V, lane)) bad = 1;
+    int rho = 0;
+    for (int c = 0; c <= dd; ++c) {
+      double nn = 0.0;
+      for (int r = lane; r < dd; r += 32) { const cplx x = C[r + (long)dd * c]; nn += x.x * x.x + x.y * x.y; }
+      nn = warp_sum_d(nn);
+      rho += sqrt(nn) > abs_tol;
+    }
+    have_c = 1;
+    if (rho >= dd) break;
+    dn -= dd - rho;
+    dd = rho;
+    have_c = 0;
+    if (dn < 0) { bad = 2; dn = 0; break; }
+  }
+  if (trivial) {
+    if (lane == 0) { num[0] = cmake(0.0, 0.0); den[0] = cmake(1.0, 0.0); }
+  } else if (dd == 0) {
+    for (int k = lane; k <= dn; k += 32) num[k] = cf[k];
+    if (lane == 0) den[0] = cmake(1.0, 0.0);
+  } else if (dn > 1 && have_c) {
+    // null vector of C (column of V with the smallest column norm) -> weights d = |b| + sqrt(eps)
+    int jmin = 0;
+    double smin = 1e300;
+    for (int c = 0; c <= dd; ++c) {
+      double nn = 0.0;
+      for (int r = lane; r < dd; r += 32) { const cplx x = C[r + (long)dd * c]; nn += x.x * x.x + x.y * x.y; }
+      nn = warp_sum_d(nn);
+      if (nn < smin) { smin = nn; jmin = c; }
+    }
+    for (int j = lane; j <= dd; j += 32) { const cplx b = V[j + (long)(dd + 1) * jmin]; dm[j] = hypot(b.x, b.y) + 1.4901161193847656e-08; }
+    __syncwarp();
+    // null vector of C diag(d)
+    for (int i = lane; i < dd * (dd + 1); i += 32) {
+      const int a = i % dd, j = i / dd, idx = dn + 1 + a - j;
+      C[i] = idx >= 0 ? cscale(dm[j], cf[idx]) : cmake(0.0, 0.0);
+    }
+    for (int i = lane; i < (dd + 1) * (dd + 1); i += 32) V[i] = (i % (dd + 1) == i / (dd + 1)) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+    __syncwarp();
+    if (warp_jacobi(C, dd, dd + 1, V, lane)) bad = 1;
+    jmin = 0; smin = 1e300;
+    for (int c = 0; c <= dd; ++c) {
+      double nn = 0.0;
+      for (int r = lane; r < dd; r += 32) { const cplx x = C[r + (long)dd * c]; nn += x.x * x.x + x.y * x.y; }
+      nn = warp_sum_d(nn);
+      if (nn < smin) { smin = nn; jmin = c; }
+    }
+    double dn2 = 0.0;
+    for (int j = lane; j <= dd; j += 32) {                                 // coeff_den = d * Q(:, n+1), Q(:, n+1) = conj(null vector)
+      den[j] = cscale(dm[j], cconj(V[j + (long)(dd + 1) * jmin]));
+      dn2 += den[j].x * den[j].x + den[j].y * den[j].y;
+    }
+    dn2 = warp_sum_d(dn2);
+    const double inv = 1.0 / sqrt(dn2);
+    for (int j = lane; j <= dd; j += 32) den[j] = cscale(inv, den[j]);
+    __syncwarp();
+    for (int i = lane; i <= dn; i += 32) {                                  // coeff_num = zmat(1:deg_num+1, 1:deg_den+1) coeff_den
+      cplx acc = cmake(0.0, 0.0);
+      for (int j = 0; j <= min(i, dd); ++j) acc = cfma(cf[i - j], den[j], acc);
+      num[i] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {                                                         // :402-424 leading / trailing zeros of the denominator
+      int lam = 0;
+      while (lam <= dd && !(hypot(den[lam].x, den[lam].y) > rel_tol)) ++lam;
+      if (lam > dd) { bad = 2; lam = 0; }
+      if (lam > 0) {
+        dn -= lam; dd -= lam;
+        for (int i = 0; i <= dn; ++i) num[i] = num[i + lam];
+        for (int i = 0; i <= dd; ++i) den[i] = den[i + lam];
+      }
+      int last = dd;
+      while (last > 0 && !(hypot(den[last].x, den[last].y) > rel_tol)) --last;
+      dd = last;
+      if (dn < 0) { bad = 2; dn = 0; }
+    }
+    dn = __shfl_sync(0xffffffffu, dn, 0); dd = __shfl_sync(0xffffffffu, dd, 0); bad = __shfl_sync(0xffffffffu, bad, 0);
+  } else {
+    bad = 2;      // deg_num <= 1 with deg_den > 0: coeff_num / coeff_den are never assigned in the reference (:386)
+  }
+  __syncwarp();
+  if (lane == 0 && bad != 2) {
+    if (!trivial) {                                                          // :426-432 trailing zeros of the numerator
+      int last = dn;
+      while (last >= 0 && !(hypot(num[last].x, num[last].y) > abs_tol)) --last;
+      if (last < 0) last = 0;
+      dn = last;
+    }
+    const cplx d0 = den[0];                                                  // :434-435
+    for (int i = 0; i <= dn; ++i) num[i] = cdiv_nf(num[i], d0);
+    for (int i = 0; i <= dd; ++i) den[i] = cdiv_nf(den[i], d0);
+    for (int i = 0; i < N; ++i) f[(long)i * estride] = cmake(0.0, 0.0);
+    f[0] = cmake((double)dn, 0.0);
+    f[estride] = cmake((double)dd, 0.0);
+    for (int i = 0; i <= dn; ++i) f[(long)(2 + i) * estride] = num[i];
+    for (int i = 0; i <= dd; ++i) f[(long)(3 + dn + i) * estride] = den[i];
   }
   if (bad && lane == 0) atomicMax(info, bad);
 }
@@ -629,12 +825,7 @@ static int symm_mesh(const sgw_freqbins *f, std::vector<cplx> *z, std::vector<in
 static int check_freq(sgw_ctx *ctx, const sgw_freqbins *f, int model) {
   SGW_ARG(f && f->num_solver > 0 && f->solver, "freqbins: solver frequencies missing");
   SGW_ARG(f->freq_symm_coul >= 0 && f->freq_symm_coul <= 2, "freqbins: freq_symm_coul must be 0, 1 or 2");
-  if (model == SGW_PADE_ROBUST) {
-    ctx->err = "model_coul 'pade robust' is not built (SURVEY 8 f3 covers 'pade', 'godby-needs', 'aaa' and 'aaa pole')";
-    return SGW_E_UNSUPPORTED;
-  }
-  SGW_ARG(model == SGW_GODBY_NEEDS || model == SGW_PADE_APPROX || model == SGW_AAA_APPROX || model == SGW_AAA_POLE,
-          "No screening model chosen!");                                                           // analytic.f90:186
+  SGW_ARG(model >= SGW_GODBY_NEEDS && model <= SGW_AAA_POLE, "No screening model chosen!");        // analytic.f90:186
   return SGW_OK;
 }
 
@@ -671,9 +862,82 @@ static int fwfft6_dev(sgw_ctx *ctx, double omega, const cplx *fr, cplx beta, cpl
   return SGW_OK;
 }
 
+// launch k_pade_robust for nfun functions stored with strides (fstride between functions, estride between samples)
+static int pade_robust_dev(sgw_ctx *ctx, long nfun, int N, double radius, int deg_num, int deg_den, double tol, double tol_fft,
+                           cplx *d, long fstride, long estride) {
+  SGW_ARG(radius > 0.0, "radius in the complex plane must be > 0");                               // pade_robust.f90:290
+  SGW_ARG(deg_num >= 0 && deg_den >= 0, "degree of numerator / denominator must be positive");     // :292-295
+  SGW_ARG(3 + deg_num + deg_den <= N, "coefficient layout [deg_num, deg_den, num, den] needs 4 + deg_num + deg_den entries");
+  const int K = deg_num + deg_den + 1;
+  const size_t smem = sizeof(cplx) * ((size_t)N + 2 * (size_t)K + (size_t)deg_den * (deg_den + 1) + (size_t)(deg_den + 1) * (deg_den + 1) +
+                                      deg_den + 1) + sizeof(double) * (deg_den + 2);
+  if (smem > ctx->smem_optin) { ctx->err = "'pade robust': too many frequencies for the shared-memory fit"; return SGW_E_UNSUPPORTED; }
+  if (smem > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_pade_robust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int *dinfo = nullptr;
+  SGW_CHECK(ws(ctx, "an_info", (size_t)1, &dinfo));
+  SGW_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+  k_pade_robust<<<(unsigned)nfun, 32, smem, ctx->stream>>>(nfun, N, radius, deg_num, deg_den, tol, tol_fft, d, fstride, estride, dinfo);
+  SGW_LAUNCH_CHECK();
+  int hinfo = 0;
+  SGW_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hinfo == 2) {
+    ctx->err = "'pade robust': the degree reduction left a numerator of degree <= 1 with a non-trivial denominator, which "
+               "pade_robust.f90:386 leaves undefined";
+    return SGW_E_UNSUPPORTED;
+  }
+  if (hinfo != 0) { ctx->err = "'pade robust': singular value iteration did not converge"; return SGW_E_ARG; }
+  return SGW_OK;
+}
+
 }  // namespace sgw
 
 extern "C" {
+
+int sgw_pade_robust(sgw_ctx *ctx, double radius, int num_point, const sgw_cplx *func, int *deg_num, int *deg_den,
+                    sgw_cplx *coeff_num, sgw_cplx *coeff_den, double tol_coeff, double tol_fft) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(func && deg_num && deg_den && coeff_num && coeff_den && num_point > 0, "bad argument");
+  const double tol = tol_coeff > 0.0 ? tol_coeff : 1e-14;                                         // pade_robust.f90:298-308
+  const double tfft = tol_fft > 0.0 ? tol_fft : tol;
+  begin_call(ctx);
+  // the kernel writes [deg_num, deg_den, numerator, denominator] over the samples: give it room for both
+  const int len = std::max(num_point, 4 + *deg_num + *deg_den);
+  cplx *d = nullptr;
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)len, &d));
+  SGW_CUDA(cudaMemsetAsync(d, 0, sizeof(cplx) * len, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(d, func, sizeof(cplx) * num_point, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const int dn0 = *deg_num, dd0 = *deg_den;
+    SGW_ARG(radius > 0.0 && dn0 >= 0 && dd0 >= 0, "radius must be > 0 and the degrees >= 0");
+    const int K = dn0 + dd0 + 1;
+    const size_t smem = sizeof(cplx) * ((size_t)num_point + 2 * (size_t)K + (size_t)dd0 * (dd0 + 1) + (size_t)(dd0 + 1) * (dd0 + 1) + dd0 + 1) +
+                        sizeof(double) * (dd0 + 2);
+    if (smem > ctx->smem_optin) { ctx->err = "'pade robust': too many frequencies for the shared-memory fit"; return SGW_E_UNSUPPORTED; }
+    if (smem > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_pade_robust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int *dinfo = nullptr;
+    SGW_CHECK(ws(ctx, "an_info", (size_t)1, &dinfo));
+    SGW_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+    // the output needs len entries: run with N = num_point samples but let the kernel clear / write up to len via a padded view
+    k_pade_robust<<<1, 32, smem, ctx->stream>>>(1, num_point, radius, dn0, dd0, tol, tfft, d, len, 1, dinfo);
+    SGW_LAUNCH_CHECK();
+    int hinfo = 0;
+    SGW_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hinfo == 2) { ctx->err = "'pade robust': numerator of degree <= 1 with a non-trivial denominator is undefined in pade_robust.f90:386"; return SGW_E_UNSUPPORTED; }
+    if (hinfo != 0) { ctx->err = "'pade robust': singular value iteration did not converge"; return SGW_E_ARG; }
+  }
+  std::vector<cplx> h(len);
+  SGW_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(cplx) * len, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int dn = (int)std::lround(h[0].x), dd = (int)std::lround(h[1].x);
+  for (int i = 0; i <= dn; ++i) { coeff_num[i].re = h[2 + i].x; coeff_num[i].im = h[2 + i].y; }
+  for (int i = 0; i <= dd; ++i) { coeff_den[i].re = h[3 + dn + i].x; coeff_den[i].im = h[3 + dn + i].y; }
+  *deg_num = dn; *deg_den = dd;
+  end_call(ctx);
+  return SGW_OK;
+}
 
 int sgw_freqbins_num_freq(const sgw_freqbins *freq) {
   if (!freq || freq->num_solver <= 0 || !freq->solver) return SGW_E_ARG;
@@ -724,7 +988,14 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
   SGW_CHECK(ws(ctx, "an_coeff", (size_t)total, &d));
   SGW_CHECK(ws(ctx, "an_z", (size_t)N, &dz));
   SGW_CUDA(cudaMemcpyAsync(d, scrcoul_g, sizeof(cplx) * total, cudaMemcpyHostToDevice, ctx->stream));
-  if (model_coul == SGW_GODBY_NEEDS) {
+  if (model_coul == SGW_PADE_ROBUST) {                                                           // pade_coeff_robust (pade_robust.f90:91-162)
+    SGW_ARG(freq->freq_symm_coul == 0, "'pade robust' works on the solver frequencies themselves (no symmetrisation, gwq_readin.f90:371)");
+    SGW_ARG(N >= 10, "use at least 10 frequencies to form the circle");
+    const double radius = freq->solver[0].re;
+    for (int i = 0; i < N; ++i)
+      SGW_ARG(fabs(hypot(freq->solver[i].re, freq->solver[i].im) - radius) <= 1e-12, "frequencies must span circle in the complex plane");
+    SGW_CHECK(pade_robust_dev(ctx, npair, N, radius, N / 2 - 2, N / 2 - 2, 1e-14, 1e-14, d, 1, npair));
+  } else if (model_coul == SGW_GODBY_NEEDS) {
     k_gn_coeff<<<(unsigned)((npair + 127) / 128), 128, 0, ctx->stream>>>(npair, freq->solver[1].im, d);
     SGW_LAUNCH_CHECK();
   } else {

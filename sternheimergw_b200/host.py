@@ -387,6 +387,16 @@ class Context:
         self._chk(self._L.sgw_coulpade(self._h, ngc, nf, _p(factor), _p(scr)), "coulpade")
         return scr
 
+    def pade_robust(self, radius, func, deg_num, deg_den, tol_coeff=None, tol_fft=None):
+        """pade_robust (pade_robust.f90:177): returns (deg_num, deg_den, coeff_num, coeff_den)."""
+        func = _c16(func)
+        dn, dd = C.c_int(int(deg_num)), C.c_int(int(deg_den))
+        cn = np.zeros(int(deg_num) + 1, dtype=np.complex128)
+        cd = np.zeros(int(deg_den) + 1, dtype=np.complex128)
+        self._chk(self._L.sgw_pade_robust(self._h, float(radius), func.size, _p(func), C.byref(dn), C.byref(dd), _p(cn), _p(cd),
+                                          float(tol_coeff or 0.0), float(tol_fft or 0.0)), "pade_robust")
+        return dn.value, dd.value, cn[:dn.value + 1].copy(), cd[:dd.value + 1].copy()
+
     def analytic_coeff(self, model_coul, thres, freq: "freqbins_type", scrcoul_g):
         """analytic.f90:50: returns the coefficient array (the reference overwrites scrcoul_g in place)."""
         scr = _c16(scrcoul_g).copy(order="F")

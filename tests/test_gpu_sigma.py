@@ -174,6 +174,60 @@ def test_aaa_pole_matches_oracle(ctx, symm):
         assert _rel(ev_got, ev_ref) < 1e3 * thres, _rel(ev_got, ev_ref)
 
 
+def test_pade_robust_reference_golden_numbers_on_the_gpu(ctx):
+    """The reference's own known-answer test of pade_robust (algo/analytic/test/pade.pf:120-200) through the C ABI:
+    same inputs, same expected coefficients, same thresholds as the pFUnit test."""
+    circle = lambda radius, n: radius * np.exp(2j * np.pi * np.arange(n) / n)
+    dn, dd, cn, cd = ctx.pade_robust(1.0, np.exp(circle(1.0, 25)), 4, 4)
+    assert (dn, dd) == (4, 4)
+    for got, want in zip(cn, [1.000000000000000, 0.499999999987559, 0.107142857136564, 0.011904761903482, 5.952380951286663e-4]):
+        assert abs(got - want) < 1e-10
+    for got, want in zip(cd, [1.000000000000000, -0.500000000012441, 0.107142857149005, -0.011904761905969, 5.952380953354424e-4]):
+        assert abs(got - want) < 1e-10
+    dn, dd, cn, cd = ctx.pade_robust(2.0, np.cos(circle(2.0, 25)), 5, 11, 1e-10, 1e-15)
+    assert (dn, dd) == (4, 10)
+    for got, want in zip(cn, [1.0, -5.736142091971364e-19, -0.450639141234688, 2.325721027857943e-19, 0.018381449098078]):
+        assert abs(got - want) < 1e-8
+    for got, want in zip(cd, [1.0, -5.736142091971364e-19, 0.049360858765312, -5.423500181277404e-20, 0.001395211814067,
+                              -3.222944976341087e-21, 2.979234736799848e-05, -1.468353270738426e-22, 5.175090814695919e-07,
+                              -3.717349899090172e-24, 6.546464226759871e-09]):
+        assert abs(got - want) < 1e-8
+
+
+def test_pade_robust_model_matches_oracle(ctx):
+    """model_coul = 'pade robust' through analytic_coeff / analytic_eval (pade_coeff_robust, pade_eval_robust): solver
+    frequencies on a circle, degrees found and normalised coefficients vs the oracle, evaluated W."""
+    from oracle import sigma as osg
+    from sternheimergw_b200 import freqbins_type
+    n, radius, ngc = 24, 1.5, 3
+    z = radius * np.exp(2j * np.pi * np.arange(n) / n)
+    fo = osg.freqbins_type(z, np.array([0.1j]), np.ones(1), np.array([0j]), osg.NO_SYMMETRY)
+    fh = freqbins_type(z, freq_symm_coul=0)
+    rng = np.random.default_rng(12)
+    scr = np.zeros((ngc, ngc, n), complex, order="F")
+    for i in range(ngc):
+        for j in range(ngc):
+            a, b, c = rng.standard_normal(3)
+            p = 3.0 + rng.random() + 1j * rng.standard_normal()
+            scr[i, j, :] = (1.0 + a * z + b * z * z) / (z - p) + c * np.exp(0.3 * z) if (i + j) % 2 else np.exp((0.5 + 0.1 * a) * z)
+    ref = scr.copy(order="F")
+    osg.pade_coeff_robust(z, ref)
+    got = ctx.analytic_coeff(osg.PADE_ROBUST, 0.0, fh, scr)
+    assert np.array_equal(got[:, :, :2], ref[:, :, :2])                      # the same degrees were found
+    # the [6/6] coefficients themselves are ill-conditioned (the requested [10/10] block is numerically rank deficient by
+    # construction: that is what the robust algorithm detects); the approximant they define is not
+    assert _rel(got, ref) < 1e-4, _rel(got, ref)
+    gmapsym = np.array([3, 1, 2], dtype=np.int32)
+    wout = np.array([0.3 + 0.2j, -0.7j, 1.0])
+    ev_ref = np.zeros((ngc, ngc, wout.size), complex)
+    for k, w in enumerate(wout):
+        for i in range(ngc):
+            for j in range(ngc):
+                ev_ref[i, j, k] = osg.pade_eval_robust(ref[gmapsym[i] - 1, gmapsym[j] - 1, :], w)
+    assert _rel(ctx.analytic_eval(osg.PADE_ROBUST, gmapsym, fh, ref, wout), ev_ref) < 1e-12
+    assert _rel(ctx.analytic_eval(osg.PADE_ROBUST, gmapsym, fh, got, wout), ev_ref) < 1e-8
+
+
 def test_coulpade_and_unsupported_models(ctx):
     from oracle import sigma as osg
     from sternheimergw_b200 import SgwError, freqbins_type
@@ -184,9 +238,11 @@ def test_coulpade_and_unsupported_models(ctx):
     osg.coulpade(fac, ref)
     assert _rel(ctx.coulpade(fac, scr), ref) < 1e-15
     fh = freqbins_type(np.array([0.0, 0.5j]))
-    for model in (3,):                               # 'pade robust': loud, not silent
+    for model in (0, 6):                             # no such screening model (analytic.f90:186): loud, not silent
         with pytest.raises(SgwError):
             ctx.analytic_coeff(model, 1e-4, fh, np.zeros((5, 5, 3), complex, order="F"))
+    with pytest.raises(SgwError):                    # 'pade robust' needs >= 10 frequencies on a circle (pade_robust.f90:128-134)
+        ctx.analytic_coeff(3, 1e-4, freqbins_type(np.array([0.0, 0.5j, 1.0j]), freq_symm_coul=0), np.zeros((2, 2, 3), complex, order="F"))
     with pytest.raises(SgwError):                    # freqbins.f90:276
         freqbins_type(np.array([0.0, 0.0])).num_freq()
 
