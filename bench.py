@@ -432,6 +432,8 @@ def main():
         "gemm_project": ("tensor", nop * 8.0 * npw * m, "TFLOP/s"),
         "gemm_expand": ("tensor", nop * 8.0 * n * m, "TFLOP/s"),
         "shift_fused": ("hbm", outer_rhs * (4.0 * ns + (L * (L + 1) // 2 + 1) + L) * 16.0 * n, "GB/s"),
+        # seed recurrences: SURVEY 8d fused floor of the seed part, 3L(L+1)+4L + (3L+7) = 95 vector passes at L = 4
+        "seed_blas1": ("hbm", outer_rhs * (3.0 * L * (L + 1) + 4 * L + 3 * L + 7) * 16.0 * n, "GB/s"),
     }
     # measured DRAM bytes per vector (ncu --set full, profiles/traffic.json; per right-hand side and outer iteration for shift_fused)
     traffic = {}
@@ -439,7 +441,8 @@ def main():
         traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text())
     except Exception:
         pass
-    units_per_class = {"fft_plane": nop, "fft_zpass": 2 * nop, "gemm_project": nop, "gemm_expand": nop, "shift_fused": outer_rhs}
+    units_per_class = {"fft_plane": nop, "fft_zpass": 2 * nop, "gemm_project": nop, "gemm_expand": nop, "shift_fused": outer_rhs,
+                       "seed_blas1": outer_rhs}
     tot_prof = sum(v["ms"] for v in prof_tot.values()) or 1.0
     kernels = {}
     for k, v in prof_tot.items():
