@@ -26,3 +26,30 @@ def lin_prob():
 def tiny_sys():
     import synth
     return synth.preset("tiny")
+
+
+def _gpu_usable():
+    """True if a CUDA device and the in-tree library are both usable (the GPU tests go through libsgw_b200.so)."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return False
+        from sternheimergw_b200 import _lib
+        _lib.load()
+        return True
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """a plain `pytest tests` on a GPU-less machine skips the gpu-marked tests instead of erroring in
+    Context(0).  On a GPU box nothing is skipped: a missing library still fails loudly there (`_lib.load()` raises)."""
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items:
+        return
+    import torch
+    if torch.cuda.is_available():
+        return                                        # GPU box: run everything, no silent skips
+    skip = pytest.mark.skip(reason="no CUDA device in this machine (run on the B200 box: pytest -m gpu)")
+    for it in gpu_items:
+        it.add_marker(skip)

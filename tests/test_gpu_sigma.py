@@ -420,3 +420,71 @@ def test_qp_energies_within_1_meV(ctx):
     assert shift_mev > 1.0, "the synthetic Sigma_c must move the levels, otherwise the check is vacuous"
     assert d_mev < 1.0, d_mev
     assert _rel(sig_gpu, sig_cpu) < 1e-6
+
+
+# ----------------------------------------------------------------------------- the reference's own AAA known answers on the GPU
+def _aaa_golden():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "testAAA.npz")
+
+
+def test_aaa_pole_reference_golden_example_on_the_gpu(ctx):
+    """vendor/analytic/test/testAAA.pf:22-74 (make_realistic_example: W of a GW run on 35 imaginary frequencies) through
+    model_coul = 'aaa pole' on the device: the greedy fit must pick the reference's 14 support points, and the Aberth pole
+    finder + four-point residues must give the reference's 13 poles (eps6, as the pFUnit test) and residues (3e-6: the
+    four-point rule's own rounding noise, see tests/test_oracle_aaa_golden.py)."""
+    from oracle import sigma as osg
+    from sternheimergw_b200 import freqbins_type
+    g = _aaa_golden()
+    zz, ff, thres = g["real_zz"], g["real_ff"], float(g["real_threshold"])
+    fh = freqbins_type(zz, freq_symm_coul=0)
+    assert fh.num_freq() == 35
+    ngc = 2
+    scr = np.zeros((ngc, ngc, 35), complex, order="F")
+    scr[:, :, :] = ff[None, None, :]
+    scr[0, 1, :] = 2.0 * ff                                       # a second, scaled copy: residues scale, poles do not
+    got = ctx.analytic_coeff(osg.AAA_POLE, thres, fh, scr)
+    half = 35 // 2
+    for (i, j), scale in (((0, 0), 1.0), ((1, 1), 1.0), ((0, 1), 2.0)):
+        res = got[i, j, half:2 * half]
+        keep = np.abs(res) > 0
+        pole, res = got[i, j, :half][keep], res[keep]
+        assert pole.size == 13, pole.size
+        order = np.argsort(1.0 / np.abs(pole), kind="stable")
+        assert np.abs(pole[order] - g["real_pole"]).max() <= 1e-6, np.abs(pole[order] - g["real_pole"]).max()
+        assert np.abs(res[order] / scale - g["real_residual"]).max() <= 3e-6, np.abs(res[order] / scale - g["real_residual"]).max()
+
+
+def test_aaa_evaluate_reference_golden_tangent_on_the_gpu(ctx):
+    """testAAA.pf:272-310 (test_evaluate_tangent): the evaluation kernel on the reference's support points, values and
+    weights of tan(pi z / 2) reproduces the reference's 11 numbers to eps12."""
+    from oracle import sigma as osg
+    from sternheimergw_b200 import freqbins_type
+    g = _aaa_golden()
+    nf, mmax = 18, 6                                              # coefficient layout [position | value | weight], mmax = nf / 3
+    fh = freqbins_type(1j * np.linspace(0.0, 1.7, nf), freq_symm_coul=0)
+    coeff = np.zeros((1, 1, nf), complex, order="F")
+    coeff[0, 0, 0:mmax] = g["tan_pos"]
+    coeff[0, 0, mmax:2 * mmax] = g["tan_val"]
+    coeff[0, 0, 2 * mmax:3 * mmax] = g["tan_weight"]
+    out = ctx.analytic_eval(osg.AAA_APPROX, np.array([1], dtype=np.int32), fh, coeff, g["tan_eval_zz"])
+    assert np.abs(out[0, 0, :] - g["tan_eval_ff"]).max() <= 1e-12, np.abs(out[0, 0, :] - g["tan_eval_ff"]).max()
+
+
+def test_aaa_fit_reference_golden_support_points_on_the_gpu(ctx):
+    """testAAA.pf:22-43 through model_coul = 'aaa' (max_point = num_freq / 3 = 11 of the reference's 14 support points,
+    analytic.f90:163): the greedy selection is nested, so the device must pick the FIRST 11 points the reference's own
+    sequence picks -- checked against the oracle, which is pinned to the full 14-point answer."""
+    from oracle import sigma as osg
+    from sternheimergw_b200 import freqbins_type
+    g = _aaa_golden()
+    zz, ff, thres = g["real_zz"], g["real_ff"], float(g["real_threshold"])
+    fh = freqbins_type(zz, freq_symm_coul=0)
+    scr = np.zeros((1, 1, 35), complex, order="F")
+    scr[0, 0, :] = ff
+    got = ctx.analytic_coeff(osg.AAA_APPROX, thres, fh, scr)
+    p, v, w = osg.aaa_generate(thres, 11, zz, ff)
+    assert p.size == 11 and set(p).issubset(set(zz[g["real_selection"] - 1]))
+    assert np.array_equal(got[0, 0, :11], p) and np.array_equal(got[0, 0, 11:22], v)
+    phase = got[0, 0, 22] / w[0]
+    assert abs(abs(phase) - 1.0) < 1e-9 and np.abs(got[0, 0, 22:33] - phase * w).max() <= 1e-6
