@@ -192,6 +192,12 @@ int sgw_analytic_coeff(sgw_ctx *ctx, int model_coul, double thres, const sgw_fre
  * (1e-14, tol_coeff). */
 int sgw_pade_robust(sgw_ctx *ctx, double radius, int num_point, const sgw_cplx *func, int *deg_num, int *deg_den,
                     sgw_cplx *coeff_num, sgw_cplx *coeff_den, double tol_coeff, double tol_fft);
+/* aaa_pole_residual (vendor/analytic/src/aaa.f90:93; the routine vendor/analytic/test/testAAA.pf:45-74,387-422 exercises) on a
+ * GIVEN barycentric approximant of m support points: the m - 1 finite poles (the reference: ZGGEV on the arrowhead pencil
+ * find_pole:388; here Aberth-Ehrlich on the same polynomial) and their four-point residues (calculate_residual:464).
+ * pole / residual need room for m - 1 entries; *num_pole out.  Poles come in no particular order. */
+int sgw_aaa_pole_residual(sgw_ctx *ctx, int m, const sgw_cplx *position, const sgw_cplx *value, const sgw_cplx *weight,
+                          sgw_cplx *pole, sgw_cplx *residual, int *num_pole);
 /* analytic_eval (analytic.f90:211) at nout frequencies at once: scrcoul(ig, igp, iout) =
  * model(coeff(gmapsym(ig), gmapsym(igp), :), freq%symmetrize(freq_out(iout))) -- the G-space block the reference
  * stores in the corner of scrcoul(nnr_c, nnr_c'). */

@@ -17,7 +17,7 @@ SYMBOLS = [
     "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
     "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
     "sgw_parallel_task", "sgw_bench_linear_op",
-    "sgw_freqbins_num_freq", "sgw_pade_robust", "sgw_coulpade", "sgw_analytic_coeff", "sgw_analytic_eval", "sgw_set_corr_grid", "sgw_invfft6",
+    "sgw_freqbins_num_freq", "sgw_pade_robust", "sgw_aaa_pole_residual", "sgw_coulpade", "sgw_analytic_coeff", "sgw_analytic_eval", "sgw_set_corr_grid", "sgw_invfft6",
     "sgw_fwfft6", "sgw_sigma_correlation",
 ]
 
@@ -101,6 +101,7 @@ def load():
         L.sgw_freqbins_num_freq.argtypes = [C.POINTER(Freqbins)]
         L.sgw_pade_robust.argtypes = [c_void_p, c_double, c_int, c_void_p, C.POINTER(c_int), C.POINTER(c_int), c_void_p, c_void_p,
                                       c_double, c_double]
+        L.sgw_aaa_pole_residual.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_int)]
         L.sgw_coulpade.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
         L.sgw_analytic_coeff.argtypes = [c_void_p, c_int, c_double, C.POINTER(Freqbins), c_int, c_void_p]
         L.sgw_analytic_eval.argtypes = [c_void_p, c_int, C.POINTER(Freqbins), c_int, c_void_p, c_void_p, c_int, c_void_p,

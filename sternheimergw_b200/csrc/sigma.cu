@@ -275,7 +275,21 @@ __global__ void __launch_bounds__(32) k_aaa_coeff(long npair, int N, int mmax, d
   for (int i = lane; i < N; i += 32) fit[i] = avg;
   __syncwarp();
   int m = 0, bad = 0;
-  for (;;) {
+  if (pole_mode == 2) {
+    // aaa_pole_residual on a GIVEN approximant (aaa.f90:93): the input holds [position | value | weight] in blocks of mmax
+    // (the 'aaa' coefficient layout, analytic.f90:160-167); no fit
+    for (int c = 0; c < mmax; ++c) {
+      const cplx wc = ff[2 * mmax + c];
+      if (hypot(wc.x, wc.y) > 1e-12) m = c + 1;                   // analytic.f90:330 counts the weights above eps12
+    }
+    __syncwarp();
+    cplx pz = cmake(0, 0), pv = cmake(0, 0), pw = cmake(0, 0);
+    if (lane < m) { pz = ff[lane]; pv = ff[mmax + lane]; pw = ff[2 * mmax + lane]; }     // mmax <= 32 in this mode (host checks)
+    __syncwarp();
+    if (lane < m) { zz[lane] = pz; ff[lane] = pv; w[lane] = pw; supidx[lane] = lane; }
+    __syncwarp();
+  }
+  for (; pole_mode != 2;) {
     // ---- update_support_point: first maximum of |ff - fit|
     double best = -1.0;
     int bidx = 0x7fffffff;
@@ -893,6 +907,52 @@ static int pade_robust_dev(sgw_ctx *ctx, long nfun, int N, double radius, int de
 }  // namespace sgw
 
 extern "C" {
+
+int sgw_aaa_pole_residual(sgw_ctx *ctx, int m, const sgw_cplx *position, const sgw_cplx *value, const sgw_cplx *weight,
+                          sgw_cplx *pole, sgw_cplx *residual, int *num_pole) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(position && value && weight && pole && residual && num_pole, "bad argument");
+  SGW_ARG(m >= 1 && m <= 32, "aaa_pole_residual: 1 <= number of support points <= 32 on the device");
+  for (int c = 0; c < m; ++c) SGW_ARG(hypot(weight[c].re, weight[c].im) > 1e-12, "aaa_pole_residual: zero weight");
+  begin_call(ctx);
+  const int mmax = m, N = 3 * m;            // the 'aaa' coefficient layout [position | value | weight] the kernel reads
+  std::vector<cplx> h((size_t)N);
+  for (int c = 0; c < m; ++c) {
+    h[c] = cmake(position[c].re, position[c].im);
+    h[mmax + c] = cmake(value[c].re, value[c].im);
+    h[2 * mmax + c] = cmake(weight[c].re, weight[c].im);
+  }
+  cplx *d = nullptr, *dz = nullptr;
+  int *dinfo = nullptr;
+  SGW_CHECK(ws(ctx, "an_coeff", (size_t)N, &d));
+  SGW_CHECK(ws(ctx, "an_z", (size_t)N, &dz));
+  SGW_CHECK(ws(ctx, "an_info", (size_t)1, &dinfo));
+  SGW_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(cplx) * N, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CUDA(cudaMemsetAsync(dz, 0, sizeof(cplx) * N, ctx->stream));
+  SGW_CUDA(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+  const size_t smem = sizeof(cplx) * ((size_t)3 * N + (size_t)N * mmax + (size_t)mmax * mmax + mmax) + sizeof(int) * ((size_t)2 * N + mmax);
+  if (smem > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_aaa_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_aaa_coeff<<<1, 32, smem, ctx->stream>>>(1, N, mmax, 0.0, dz, d, dinfo, 2);
+  SGW_LAUNCH_CHECK();
+  int hinfo = 0;
+  SGW_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(cplx) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  end_call(ctx);
+  if (hinfo != 0) { ctx->err = "error occured in AAA approximation (the pole iteration did not converge)"; return SGW_E_ARG; }
+  const int half = N / 2;
+  int np = 0;
+  for (int k = 0; k < half && k < m - 1; ++k) {
+    const cplx r = h[half + k];
+    if (r.x == 0.0 && r.y == 0.0) break;       // pole_correction keeps |residual| > thres = 0: stored entries are contiguous
+    pole[np].re = h[k].x; pole[np].im = h[k].y;
+    residual[np].re = r.x; residual[np].im = r.y;
+    ++np;
+  }
+  *num_pole = np;
+  return SGW_OK;
+}
 
 int sgw_pade_robust(sgw_ctx *ctx, double radius, int num_point, const sgw_cplx *func, int *deg_num, int *deg_den,
                     sgw_cplx *coeff_num, sgw_cplx *coeff_den, double tol_coeff, double tol_fft) {

@@ -397,6 +397,19 @@ class Context:
                                           float(tol_coeff or 0.0), float(tol_fft or 0.0)), "pade_robust")
         return dn.value, dd.value, cn[:dn.value + 1].copy(), cd[:dd.value + 1].copy()
 
+    def aaa_pole_residual(self, position, value, weight):
+        """aaa_pole_residual (vendor/analytic/src/aaa.f90:93) of a given barycentric approximant: returns (pole, residual)."""
+        position, value, weight = _c16(position), _c16(value), _c16(weight)
+        m = position.size
+        if value.size != m or weight.size != m:
+            raise SgwError("position, value and weight must have the same size")
+        pole = np.zeros(max(m - 1, 1), dtype=np.complex128)
+        res = np.zeros(max(m - 1, 1), dtype=np.complex128)
+        n = C.c_int(0)
+        self._chk(self._L.sgw_aaa_pole_residual(self._h, m, _p(position), _p(value), _p(weight), _p(pole), _p(res), C.byref(n)),
+                  "aaa_pole_residual")
+        return pole[:n.value].copy(), res[:n.value].copy()
+
     def analytic_coeff(self, model_coul, thres, freq: "freqbins_type", scrcoul_g):
         """analytic.f90:50: returns the coefficient array (the reference overwrites scrcoul_g in place)."""
         scr = _c16(scrcoul_g).copy(order="F")
