@@ -142,6 +142,9 @@ static void prof_collect(sgw_ctx *ctx) {
 }
 
 void begin_call(sgw_ctx *ctx) {
+  // records left behind by a call that returned early with an error (its end_call never ran) must not be billed to this one
+  for (auto &r : ctx->prof_recs) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+  ctx->prof_recs.clear();
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->launches = 0;
   memset(ctx->prof_ms, 0, sizeof(ctx->prof_ms));
@@ -561,6 +564,7 @@ int sgw_bench_linear_op(sgw_ctx *ctx, int slot, int nvec, int reps, double *ms_t
   SGW_CHECK(ws(ctx, "fft_T1", tsz, &T1));
   SGW_CHECK(ws(ctx, "fft_T2", tsz, &T2));
   float ms = 0.f;
+  begin_call(ctx);
   // warm-up
   for (int r = 0; r < 3; ++r) SGW_CHECK(apply_operator(ctx, slot, k.alpha_pv, nvec, d_psi, n, d_om, 1, d_out, n, nullptr));
   SGW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -588,6 +592,7 @@ int sgw_bench_linear_op(sgw_ctx *ctx, int slot, int nvec, int reps, double *ms_t
   SGW_CUDA(cudaEventSynchronize(ctx->ev3));
   cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
   if (ms_gemm) *ms_gemm = ms / reps;
+  end_call(ctx);
   return SGW_OK;
 }
 

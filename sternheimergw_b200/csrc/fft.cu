@@ -230,6 +230,230 @@ __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, Spher
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent VLOC plane kernel
+// H.psi local part, one (vector, z-plane) item at a time on a PERSISTENT CTA (2 per SM), compile-time radix plan:
+//   * the item's input row T[vec][pz][0..ncol) (one contiguous 16 B x ncol segment) is fetched by the TMA engine
+//     (cp.async.bulk global -> shared, completion on an mbarrier) into a staging buffer while the previous item is still
+//     being transformed: the fetch of item i+1 is issued as soon as the first stage of item i has consumed the buffer;
+//   * the first inverse y stage reads its inputs straight from the staged row through a per-task index table (int16,
+//     built with the sphere) and the last forward y stage writes its outputs straight to the output row in global memory:
+//     no zero fill of the plane, no scatter / gather sweeps;
+//   * the two strided x stages skip the x columns that hold no sphere data (loads of the inverse stage, stores of the
+//     forward stage) with one bit mask per sub-index, uniform over (almost) every warp;
+//   * twiddles, tables and masks are loaded once per CTA, not once per plane.
+// Arithmetic per element is that of k_plane<PLANE_VLOC> (same codelets, same twiddle products, same order): results are
+// bit-identical, which tests/test_gpu_operator.py checks against the generic kernel.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); bytes must be a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct PlaneVArgs {
+  const cplx *twx, *twy;
+  const cplx *Tin;
+  cplx *Tout;
+  const double *vperm;
+  const int *active;
+  const int *xs;            // x columns that hold sphere data (ascending)
+  const short *ytab;        // [(j2 * nxs + l) * RY1 + k] -> column index of (x = xs[l], y = j2 + RY2 k) in a T row, or -1
+  int nz, nvec, ncol, nxs;
+};
+
+template <int RX1, int RX2, int RY1, int RY2, int NT, bool XMASK>
+__global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1;
+  const int tid = threadIdx.x;
+  extern __shared__ __align__(128) unsigned char psm[];
+  cplx *plane = (cplx *)psm;
+  cplx *stage = plane + NY * PITCH;
+  const int ncol_pad = (a.ncol + 7) & ~7;
+  cplx *twx = stage + ncol_pad;
+  cplx *twy = twx + NX;
+  short *ytab = (short *)(twy + NY);
+  const int ntab = (a.nxs * NY + 7) & ~7;
+  int *xs = (int *)(ytab + ntab);
+  int *xz = xs + NX;                       // complement of xs (columns without data)
+  unsigned *xmask = (unsigned *)(xz + NX); // per sub-index j2 < RX2: bit k set <=> column j2 + RX2 k holds data
+  unsigned long long *bar = (unsigned long long *)(xmask + ((RX2 + 1) & ~1));
+  const int nxs = a.nxs, nxz = NX - nxs;
+  for (int i = tid; i < NX; i += NT) twx[i] = a.twx[i];
+  for (int i = tid; i < NY; i += NT) twy[i] = a.twy[i];
+  for (int i = tid; i < nxs * NY; i += NT) ytab[i] = a.ytab[i];
+  for (int i = tid; i < nxs; i += NT) xs[i] = a.xs[i];
+  if (tid == 0) {
+    int j = 0, q = 0;
+    for (int x = 0; x < NX; ++x) {
+      if (j < nxs && a.xs[j] == x) ++j; else xz[q++] = x;
+    }
+    for (int j2 = 0; j2 < RX2; ++j2) {
+      unsigned m = 0;
+      for (int k = 0; k < RX1; ++k) {
+        const int x = j2 + RX2 * k;
+        bool used = false;
+        for (int i = 0; i < nxs; ++i) used |= (a.xs[i] == x);
+        if (used) m |= 1u << k;
+      }
+      xmask[j2] = m;
+    }
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const long nitems = (long)a.nvec * a.nz;
+  const unsigned row_bytes = (unsigned)a.ncol * (unsigned)sizeof(cplx);
+  auto next_active = [&](long it) {
+    while (it < nitems && a.active && !a.active[it / a.nz]) it += gridDim.x;
+    return it;
+  };
+  long item = next_active(blockIdx.x);
+  if (tid == 0 && item < nitems) {
+    mbar_expect_tx(bar, row_bytes);
+    tma_load_1d(stage, a.Tin + item * a.ncol, row_bytes, bar);
+  }
+  unsigned parity = 0;
+  const cplx zero = cmake(0.0, 0.0);
+  while (item < nitems) {
+    const int pz = (int)(item % a.nz);
+    if (!XMASK) {
+      // columns without sphere data: the x stages read them as zeros
+      for (int i = tid; i < nxz * NY; i += NT) plane[xz[i % nxz] + (i / nxz) * PITCH] = zero;
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    {  // ---- inverse y, stage 1 (strided DFT_RY1 + twiddle), inputs from the staged row
+      const int ntask = nxs * RY2;
+      TaskIter it(tid, NT, nxs);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int l = it.l, j2 = it.j;
+        const short *tb = ytab + (j2 * nxs + l) * RY1;
+        double re[RY1], im[RY1];
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) {
+          const int idx = tb[k];
+          const cplx v = idx >= 0 ? stage[idx] : zero;
+          re[k] = v.x; im[k] = v.y;
+        }
+        dft_fwd<RY1>(im, re);
+#pragma unroll
+        for (int k = 1; k < RY1; ++k) {
+          const cplx w = twy[j2 * k];
+          const double c = w.x, sn = -w.y;
+          const double p = re[k], q = im[k];
+          re[k] = p * c - q * sn;
+          im[k] = p * sn + q * c;
+        }
+        cplx *base = plane + xs[l] + j2 * PITCH;
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) base[k * (RY2 * PITCH)] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    // the staging buffer is free: fetch the next item's row while this one is transformed
+    const long next = next_active(item + gridDim.x);
+    if (tid == 0 && next < nitems) {
+      mbar_expect_tx(bar, row_bytes);
+      tma_load_1d(stage, a.Tin + next * a.ncol, row_bytes, bar);
+    }
+    // ---- inverse y, stage 2 (contiguous DFT_RY2)
+    stage_contig<RY2, +1>(plane, nxs, xs, 1, PITCH, RY1, twy, false, tid, NT);
+    __syncthreads();
+    {  // ---- inverse x, stage 1 (strided DFT_RX1 + twiddle), all rows; columns without data are not read
+      const int ntask = NY * RX2;
+      TaskIter it(tid, NT, NY);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int j2 = it.j;
+        cplx *base = plane + it.l * PITCH + j2;
+        const unsigned m = XMASK ? xmask[j2] : 0xffffffffu;
+        double re[RX1], im[RX1];
+#pragma unroll
+        for (int k = 0; k < RX1; ++k) {
+          const cplx v = (m >> k) & 1u ? base[k * RX2] : zero;
+          re[k] = v.x; im[k] = v.y;
+        }
+        dft_fwd<RX1>(im, re);
+#pragma unroll
+        for (int k = 1; k < RX1; ++k) {
+          const cplx w = twx[j2 * k];
+          const double c = w.x, sn = -w.y;
+          const double p = re[k], q = im[k];
+          re[k] = p * c - q * sn;
+          im[k] = p * sn + q * c;
+        }
+#pragma unroll
+        for (int k = 0; k < RX1; ++k) base[k * RX2] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    // ---- last inverse x stage, x v(r), first forward x stage: one register round trip
+    stage_mid<RX2, false>(plane, NY, PITCH, RX1, twx, true, a.vperm + (long)pz * (NX * NY), nullptr, NX, tid, NT);
+    __syncthreads();
+    {  // ---- forward x, last stage (strided DFT_RX1): only the columns of the output sphere are stored
+      const int ntask = NY * RX2;
+      TaskIter it(tid, NT, NY);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int j2 = it.j;
+        cplx *base = plane + it.l * PITCH + j2;
+        const unsigned m = XMASK ? xmask[j2] : 0xffffffffu;
+        double re[RX1], im[RX1];
+#pragma unroll
+        for (int k = 0; k < RX1; ++k) { const cplx v = base[k * RX2]; re[k] = v.x; im[k] = v.y; }
+        dft_fwd<RX1>(re, im);
+#pragma unroll
+        for (int k = 0; k < RX1; ++k)
+          if ((m >> k) & 1u) base[k * RX2] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    // ---- forward y, stage 1 (contiguous DFT_RY2 + twiddle)
+    stage_contig<RY2, -1>(plane, nxs, xs, 1, PITCH, RY1, twy, true, tid, NT);
+    __syncthreads();
+    {  // ---- forward y, stage 2 (strided DFT_RY1): sphere entries go straight to the output row
+      cplx *orow = a.Tout + item * a.ncol;
+      const int ntask = nxs * RY2;
+      TaskIter it(tid, NT, nxs);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int l = it.l, j2 = it.j;
+        const cplx *base = plane + xs[l] + j2 * PITCH;
+        double re[RY1], im[RY1];
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) { const cplx v = base[k * (RY2 * PITCH)]; re[k] = v.x; im[k] = v.y; }
+        dft_fwd<RY1>(re, im);
+        const short *tb = ytab + (j2 * nxs + l) * RY1;
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) {
+          const int idx = tb[k];
+          if (idx >= 0) orow[idx] = cmake(re[k], im[k]);
+        }
+      }
+    }
+    __syncthreads();
+    item = next;
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void stage_acc(const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
                                           int tid, int nthreads) {
@@ -424,6 +648,53 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
   return SGW_OK;
 }
 
+
+// ---- launch of the persistent VLOC kernel; returns SGW_OK and sets *done when an instantiation matches the grid
+static int plane_vloc_variant() {
+  // SGW_PLANE: 0 = generic k_plane, 1 = persistent + zero fill, 2 = persistent + x masks (default); read per call so
+  // that the parity test can compare the variants inside one process
+  const char *e = getenv("SGW_PLANE");
+  return e ? atoi(e) : 2;
+}
+template <int RX1, int RX2, int RY1, int RY2>
+static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
+                             bool *done) {
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384;
+  const int ncol_pad = (s.ncol + 7) & ~7, ntab = (s.nxs * NY + 7) & ~7;
+  const size_t smem = sizeof(cplx) * ((size_t)NY * PITCH + ncol_pad + NX + NY) + sizeof(short) * ntab + sizeof(int) * 2 * NX +
+                      sizeof(unsigned) * ((RX2 + 1) & ~1) + 16;
+  if (smem > ctx->smem_optin) return SGW_OK;                    // not done: the generic kernel reports the limit
+  PlaneVArgs a;
+  a.twx = g.twx; a.twy = g.twy; a.Tin = Tin; a.Tout = Tout; a.vperm = ctx->d_vperm; a.active = active;
+  a.xs = s.d_xs; a.ytab = s.d_ytab; a.nz = g.nz; a.nvec = nvec; a.ncol = s.ncol; a.nxs = s.nxs;
+  const long nitems = (long)nvec * g.nz;
+  auto go = [&](auto kern) -> int {
+    SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long ctas = std::min<long>(nitems, (long)per_sm * ctx->sm_count);
+    kern<<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
+    return SGW_OK;
+  };
+  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, false>));
+  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, true>));
+  *done = true;
+  return SGW_OK;
+}
+
+static int try_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
+                          bool *done) {
+  *done = false;
+  if (plane_vloc_variant() == 0 || !s.d_ytab || s.ytab_ry1 != g.ry1 || s.ytab_ry2 != g.ry2) return SGW_OK;
+#define SGW_PV(a, b, c, d) \
+  if (g.rx1 == a && g.rx2 == b && g.ry1 == c && g.ry2 == d) return launch_plane_vloc<a, b, c, d>(ctx, g, s, nvec, Tin, Tout, active, done);
+  SGW_PV(8, 9, 8, 9)        // 72 x 72 (Si64)
+  SGW_PV(8, 8, 8, 8)        // 64 x 64
+  SGW_PV(8, 12, 8, 12)      // 96 x 96
+#undef SGW_PV
+  return SGW_OK;
+}
+
 int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sout, int nvec, const cplx *Tin, cplx *Tout,
               const cplx *field, int vec_per_field, cplx *R, const int *active, int in_mod, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
@@ -434,6 +705,14 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
   ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
+  if (mode == PLANE_VLOC && sin == sout && sin && P == 1 && !gr) {
+    bool done = false;
+    SGW_CHECK(try_plane_vloc(ctx, g, *sin, nvec, Tin, Tout, active, &done));
+    if (done) {
+      SGW_LAUNCH_CHECK();
+      return SGW_OK;
+    }
+  }
 #define SGW_PLANE_LAUNCH(M, NT)                                                                                          \
   do {                                                                                                                  \
     if (P == 1) {                                                                                                       \
@@ -547,6 +826,22 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   SGW_CHECK(upload(ctx, &sph->d_zof, zof.data(), zof.size()));
   SGW_CHECK(upload(ctx, &sph->d_xs, xs.data(), xs.size()));
   SGW_CHECK(upload(ctx, &sph->d_perm, order.data(), order.size()));
+  // index table of the persistent plane kernel (k_plane_vloc): for x column l, sub-index j2 and butterfly leg k of the
+  // first y stage, the position of (xs[l], y = j2 + ry2 k) in a T row, or -1 outside the sphere
+  sph->ytab_ry1 = sph->ytab_ry2 = 0;
+  if (ctx->py.r2 > 1 && col_x.size() < 32768) {
+    const int ry1 = ctx->py.r1, ry2 = ctx->py.r2, nxs = (int)xs.size();
+    std::vector<int> xpos(nx, -1);
+    for (int l = 0; l < nxs; ++l) xpos[xs[l]] = l;
+    std::vector<short> ytab((size_t)nxs * ny, (short)-1);
+    for (size_t c = 0; c < col_x.size(); ++c) {
+      const int l = xpos[col_x[c]], y = col_y[c];
+      const int j2 = y % ry2, k = y / ry2;
+      ytab[((size_t)j2 * nxs + l) * ry1 + k] = (short)c;
+    }
+    SGW_CHECK(upload(ctx, &sph->d_ytab, ytab.data(), ytab.size()));
+    sph->ytab_ry1 = ry1; sph->ytab_ry2 = ry2;
+  }
   return SGW_OK;
 }
 
@@ -601,6 +896,9 @@ void free_sphere(Sphere *s) {
     if (*p) dev_free(*p);
     *p = nullptr;
   }
+  if (s->d_ytab) dev_free(s->d_ytab);
+  s->d_ytab = nullptr;
+  s->ytab_ry1 = s->ytab_ry2 = 0;
   s->npw = s->ncol = s->nxs = 0;
   s->perm.clear();
   s->h_col_x.clear(); s->h_col_y.clear(); s->h_col_ptr.clear(); s->h_zof.clear();

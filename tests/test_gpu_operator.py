@@ -102,3 +102,39 @@ def test_caller_owned_stream_gives_identical_results():
         assert np.array_equal(got, ref) and np.array_equal(again, ref)
     finally:
         c.close()
+
+
+def test_persistent_plane_kernel_is_bit_identical_to_the_generic_one(monkeypatch):
+    """k_plane_vloc (persistent CTAs, TMA-staged rows, fused scatter/gather, x-column masks; csrc/fft.cu) does the arithmetic
+    of the generic k_plane<PLANE_VLOC> in the same order: H.psi at the Si64 size must agree BIT FOR BIT between the generic
+    kernel (SGW_PLANE=0), the persistent kernel with a zero-filled plane (1) and the masked variant (2, default), also with
+    an `active` mask (multishift solve) -- and the generic kernel is the one test_linear_op_matches_oracle pins to 1e-12."""
+    import synth
+    from sternheimergw_b200 import Context, select_solver_type
+    syn = synth.preset("si64")
+    c = Context(0)
+    try:
+        c.install_system(syn)
+        kq = syn.kpairs[0].kq
+        rng = np.random.default_rng(5)
+        nvec = 37
+        psi = np.zeros((kq.npwx, nvec), complex, order="F")
+        psi[:kq.npw] = rng.standard_normal((kq.npw, nvec)) + 1j * rng.standard_normal((kq.npw, nvec))
+        om = rng.standard_normal(nvec) + 0.3j
+        outs = {}
+        for variant in ("0", "1", "2"):
+            monkeypatch.setenv("SGW_PLANE", variant)
+            outs[variant] = c.linear_op(0, om, kq.alpha_pv, psi)
+        assert np.array_equal(outs["0"], outs["1"]) and np.array_equal(outs["0"], outs["2"])
+        # through the solver (per-vector active masks, converged right-hand sides drop out of the batch)
+        b = np.asfortranarray(psi[:, :6] - kq.evq @ (kq.evq.conj().T @ psi[:, :6]))
+        b /= np.linalg.norm(b, axis=0)
+        sigma = np.asfortranarray(-(kq.et[:6][None, :] + np.array([0.0, 0.2j, -0.2j])[:, None]))
+        xs = {}
+        for variant in ("0", "2"):
+            monkeypatch.setenv("SGW_PLANE", variant)
+            xs[variant], ierr = c.select_solver(select_solver_type(priority=(1,), threshold=1e-6), 0, b, sigma)
+            assert np.all(ierr == 0)
+        assert np.array_equal(xs["0"], xs["2"])
+    finally:
+        c.close()
