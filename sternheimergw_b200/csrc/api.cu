@@ -203,6 +203,7 @@ int sgw_destroy(sgw_ctx *ctx) {
   if (ctx->d_twy) dev_free(ctx->d_twy);
   if (ctx->d_twz) dev_free(ctx->d_twz);
   if (ctx->d_vperm) dev_free(ctx->d_vperm);
+  if (ctx->d_vperm_t) dev_free(ctx->d_vperm_t);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
   for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -343,6 +344,15 @@ int sgw_set_vloc(sgw_ctx *ctx, const double *vrs) {
       for (int pxi = 0; pxi < nx; ++pxi)
         vp[((size_t)pz * ny + py) * nx + pxi] = vrs[ctx->permx[pxi] + (size_t)nx * (ctx->permy[py] + (size_t)ny * ctx->permz[pz])];
   SGW_CHECK(upload(ctx, &ctx->d_vperm, vp.data(), vp.size()));
+  {
+    // the same potential with y fastest, [pz][px][py]: in the fused middle x stage consecutive lanes work on consecutive
+    // rows (y) of the same x group, so this layout makes their 8-byte loads of v coalesce (k_plane_vloc, fft.cu)
+    std::vector<double> vt(vp.size());
+    for (int pz = 0; pz < nz; ++pz)
+      for (int py = 0; py < ny; ++py)
+        for (int pxi = 0; pxi < nx; ++pxi) vt[((size_t)pz * nx + pxi) * ny + py] = vp[((size_t)pz * ny + py) * nx + pxi];
+    SGW_CHECK(upload(ctx, &ctx->d_vperm_t, vt.data(), vt.size()));
+  }
   ctx->vloc_set = true;
   return SGW_OK;
 }

@@ -270,21 +270,68 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, un
                : "memory");
 }
 
+// stage_mid (fft_core.h) with the potential stored y-fastest: v of (row l, x = a R + j) at vt[(a R + j) * vts + l].
+// Same arithmetic; only the addresses of the 8-byte loads differ (coalesced over the rows a warp works on).
+template <int R>
+__device__ __forceinline__ void stage_mid_vt(cplx *x, int nlines, int ls, int r_other, const cplx *tw, const double *vt, int vts,
+                                             int tid, int nthreads) {
+  const int ntasks = nlines * r_other;
+  TaskIter it(tid, nthreads, nlines);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    const int l = it.l, a = it.j;
+    cplx *base = x + (l * ls + a * R);
+    const double *vr = vt + (a * R) * vts + l;
+    double q[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) q[j] = vr[j * vts];
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const cplx w = base[j]; re[j] = w.x; im[j] = w.y; }
+    dft_fwd<R>(im, re);
+#pragma unroll
+    for (int j = 0; j < R; ++j) { re[j] *= q[j]; im[j] *= q[j]; }
+    dft_fwd<R>(re, im);
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+      const cplx w = tw[a * k];
+      const double c = w.x, s = w.y;
+      const double p = re[k], qq = im[k];
+      re[k] = p * c - qq * s;
+      im[k] = p * s + qq * c;
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) base[k] = cmake(re[k], im[k]);
+  }
+}
+
 struct PlaneVArgs {
   const cplx *twx, *twy;
   const cplx *Tin;
   cplx *Tout;
-  const double *vperm;
+  const double *vperm;      // y-fastest copy of the potential, [pz][px][py]
   const int *active;
   const int *xs;            // x columns that hold sphere data (ascending)
-  const short *ytab;        // [(j2 * nxs + l) * RY1 + k] -> column index of (x = xs[l], y = j2 + RY2 k) in a T row, or -1
+  const short *ytab;        // [(j2 * nxs + l) * RY1P + k] -> column index of (x = xs[l], y = j2 + RY2 k) in a T row, or -1
   int nz, nvec, ncol, nxs;
 };
 
-template <int RX1, int RX2, int RY1, int RY2, int NT, bool XMASK>
+// named barrier over one thread group (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// The CTA is split into G groups of NT / G threads.  A group owns NY / G consecutive rows during the x transforms and a
+// contiguous share of the data-holding x columns during the y transforms: the 1-D transforms of a line only touch that line,
+// so the stages of one direction are separated by GROUP barriers (bar.sync id, NT / G) and the whole CTA meets only twice
+// per item, where the direction changes (y -> x and x -> y).
+template <int RX1, int RX2, int RY1, int RY2, int NT, int G, bool XMASK>
 __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
   constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1;
+  constexpr int GS = NT / G, ROWS = NY / G;
+  constexpr int RY1P = (RY1 + 7) & ~7;        // table entries per task, padded to whole 16-byte loads
+  static_assert(NT % G == 0 && GS % 32 == 0 && NY % G == 0, "group split");
   const int tid = threadIdx.x;
+  const int grp = tid / GS, gt = tid - grp * GS;
   extern __shared__ __align__(128) unsigned char psm[];
   cplx *plane = (cplx *)psm;
   cplx *stage = plane + NY * PITCH;
@@ -292,15 +339,15 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
   cplx *twx = stage + ncol_pad;
   cplx *twy = twx + NX;
   short *ytab = (short *)(twy + NY);
-  const int ntab = (a.nxs * NY + 7) & ~7;
+  const int nxs = a.nxs, nxz = NX - nxs;
+  const int ntab = nxs * RY2 * RY1P;
   int *xs = (int *)(ytab + ntab);
   int *xz = xs + NX;                       // complement of xs (columns without data)
   unsigned *xmask = (unsigned *)(xz + NX); // per sub-index j2 < RX2: bit k set <=> column j2 + RX2 k holds data
   unsigned long long *bar = (unsigned long long *)(xmask + ((RX2 + 1) & ~1));
-  const int nxs = a.nxs, nxz = NX - nxs;
   for (int i = tid; i < NX; i += NT) twx[i] = a.twx[i];
   for (int i = tid; i < NY; i += NT) twy[i] = a.twy[i];
-  for (int i = tid; i < nxs * NY; i += NT) ytab[i] = a.ytab[i];
+  for (int i = tid; i < ntab / 8; i += NT) ((uint4 *)ytab)[i] = ((const uint4 *)a.ytab)[i];
   for (int i = tid; i < nxs; i += NT) xs[i] = a.xs[i];
   if (tid == 0) {
     int j = 0, q = 0;
@@ -322,6 +369,12 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
   }
   __syncthreads();
 
+  // this group's share of the data columns [c0, c0 + ncg) and rows [r0, r0 + ROWS)
+  const int cper = (nxs + G - 1) / G;
+  const int c0 = min(nxs, grp * cper), ncg = min(nxs, c0 + cper) - c0;
+  const int r0 = grp * ROWS;
+  const int bid = 1 + grp;
+
   const long nitems = (long)a.nvec * a.nz;
   const unsigned row_bytes = (unsigned)a.ncol * (unsigned)sizeof(cplx);
   auto next_active = [&](long it) {
@@ -338,17 +391,19 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
   while (item < nitems) {
     const int pz = (int)(item % a.nz);
     if (!XMASK) {
-      // columns without sphere data: the x stages read them as zeros
-      for (int i = tid; i < nxz * NY; i += NT) plane[xz[i % nxz] + (i / nxz) * PITCH] = zero;
+      // columns without sphere data: the x stages read them as zeros (rows of this group; read again after the y -> x barrier)
+      for (int i = gt; i < nxz * ROWS; i += GS) plane[xz[i % nxz] + (r0 + i / nxz) * PITCH] = zero;
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    {  // ---- inverse y, stage 1 (strided DFT_RY1 + twiddle), inputs from the staged row
-      const int ntask = nxs * RY2;
-      TaskIter it(tid, NT, nxs);
-      for (int t = tid; t < ntask; t += NT, it.next()) {
-        const int l = it.l, j2 = it.j;
-        const short *tb = ytab + (j2 * nxs + l) * RY1;
+    if (ncg > 0) {  // ---- inverse y, stage 1 (strided DFT_RY1 + twiddle), inputs from the staged row
+      const int ntask = ncg * RY2;
+      TaskIter it(gt, GS, ncg);
+      for (int t = gt; t < ntask; t += GS, it.next()) {
+        const int l = c0 + it.l, j2 = it.j;
+        short tb[RY1P];
+#pragma unroll
+        for (int q = 0; q < RY1P / 8; ++q) *(uint4 *)(tb + 8 * q) = *(const uint4 *)(ytab + (j2 * nxs + l) * RY1P + 8 * q);
         double re[RY1], im[RY1];
 #pragma unroll
         for (int k = 0; k < RY1; ++k) {
@@ -370,22 +425,23 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
         for (int k = 0; k < RY1; ++k) base[k * (RY2 * PITCH)] = cmake(re[k], im[k]);
       }
     }
-    __syncthreads();
+    group_sync(bid, GS);
+    // ---- inverse y, stage 2 (contiguous DFT_RY2)
+    stage_contig<RY2, +1>(plane, ncg, xs + c0, 1, PITCH, RY1, twy, false, gt, GS);
+    __syncthreads();                                   // y -> x: every column is needed by every row
     // the staging buffer is free: fetch the next item's row while this one is transformed
     const long next = next_active(item + gridDim.x);
     if (tid == 0 && next < nitems) {
       mbar_expect_tx(bar, row_bytes);
       tma_load_1d(stage, a.Tin + next * a.ncol, row_bytes, bar);
     }
-    // ---- inverse y, stage 2 (contiguous DFT_RY2)
-    stage_contig<RY2, +1>(plane, nxs, xs, 1, PITCH, RY1, twy, false, tid, NT);
-    __syncthreads();
-    {  // ---- inverse x, stage 1 (strided DFT_RX1 + twiddle), all rows; columns without data are not read
-      const int ntask = NY * RX2;
-      TaskIter it(tid, NT, NY);
-      for (int t = tid; t < ntask; t += NT, it.next()) {
+    cplx *rows = plane + r0 * PITCH;
+    {  // ---- inverse x, stage 1 (strided DFT_RX1 + twiddle), rows of this group; columns without data are not read
+      constexpr int ntask = ROWS * RX2;
+      TaskIter it(gt, GS, ROWS);
+      for (int t = gt; t < ntask; t += GS, it.next()) {
         const int j2 = it.j;
-        cplx *base = plane + it.l * PITCH + j2;
+        cplx *base = rows + it.l * PITCH + j2;
         const unsigned m = XMASK ? xmask[j2] : 0xffffffffu;
         double re[RX1], im[RX1];
 #pragma unroll
@@ -406,16 +462,16 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
         for (int k = 0; k < RX1; ++k) base[k * RX2] = cmake(re[k], im[k]);
       }
     }
-    __syncthreads();
+    group_sync(bid, GS);
     // ---- last inverse x stage, x v(r), first forward x stage: one register round trip
-    stage_mid<RX2, false>(plane, NY, PITCH, RX1, twx, true, a.vperm + (long)pz * (NX * NY), nullptr, NX, tid, NT);
-    __syncthreads();
+    stage_mid_vt<RX2>(rows, ROWS, PITCH, RX1, twx, a.vperm + (long)pz * (NX * NY) + r0, NY, gt, GS);
+    group_sync(bid, GS);
     {  // ---- forward x, last stage (strided DFT_RX1): only the columns of the output sphere are stored
-      const int ntask = NY * RX2;
-      TaskIter it(tid, NT, NY);
-      for (int t = tid; t < ntask; t += NT, it.next()) {
+      constexpr int ntask = ROWS * RX2;
+      TaskIter it(gt, GS, ROWS);
+      for (int t = gt; t < ntask; t += GS, it.next()) {
         const int j2 = it.j;
-        cplx *base = plane + it.l * PITCH + j2;
+        cplx *base = rows + it.l * PITCH + j2;
         const unsigned m = XMASK ? xmask[j2] : 0xffffffffu;
         double re[RX1], im[RX1];
 #pragma unroll
@@ -426,22 +482,24 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
           if ((m >> k) & 1u) base[k * RX2] = cmake(re[k], im[k]);
       }
     }
-    __syncthreads();
+    __syncthreads();                                   // x -> y
     // ---- forward y, stage 1 (contiguous DFT_RY2 + twiddle)
-    stage_contig<RY2, -1>(plane, nxs, xs, 1, PITCH, RY1, twy, true, tid, NT);
-    __syncthreads();
-    {  // ---- forward y, stage 2 (strided DFT_RY1): sphere entries go straight to the output row
+    stage_contig<RY2, -1>(plane, ncg, xs + c0, 1, PITCH, RY1, twy, true, gt, GS);
+    group_sync(bid, GS);
+    if (ncg > 0) {  // ---- forward y, stage 2 (strided DFT_RY1): sphere entries go straight to the output row
       cplx *orow = a.Tout + item * a.ncol;
-      const int ntask = nxs * RY2;
-      TaskIter it(tid, NT, nxs);
-      for (int t = tid; t < ntask; t += NT, it.next()) {
-        const int l = it.l, j2 = it.j;
+      const int ntask = ncg * RY2;
+      TaskIter it(gt, GS, ncg);
+      for (int t = gt; t < ntask; t += GS, it.next()) {
+        const int l = c0 + it.l, j2 = it.j;
         const cplx *base = plane + xs[l] + j2 * PITCH;
         double re[RY1], im[RY1];
 #pragma unroll
         for (int k = 0; k < RY1; ++k) { const cplx v = base[k * (RY2 * PITCH)]; re[k] = v.x; im[k] = v.y; }
         dft_fwd<RY1>(re, im);
-        const short *tb = ytab + (j2 * nxs + l) * RY1;
+        short tb[RY1P];
+#pragma unroll
+        for (int q = 0; q < RY1P / 8; ++q) *(uint4 *)(tb + 8 * q) = *(const uint4 *)(ytab + (j2 * nxs + l) * RY1P + 8 * q);
 #pragma unroll
         for (int k = 0; k < RY1; ++k) {
           const int idx = tb[k];
@@ -449,7 +507,7 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
         }
       }
     }
-    __syncthreads();
+    group_sync(bid, GS);                               // the group's columns are rewritten by the next item's first stage
     item = next;
   }
 }
@@ -659,13 +717,13 @@ static int plane_vloc_variant() {
 template <int RX1, int RX2, int RY1, int RY2>
 static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
                              bool *done) {
-  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384;
-  const int ncol_pad = (s.ncol + 7) & ~7, ntab = (s.nxs * NY + 7) & ~7;
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384, G = 3;
+  const int ncol_pad = (s.ncol + 7) & ~7, ntab = s.nxs * RY2 * ((RY1 + 7) & ~7);
   const size_t smem = sizeof(cplx) * ((size_t)NY * PITCH + ncol_pad + NX + NY) + sizeof(short) * ntab + sizeof(int) * 2 * NX +
                       sizeof(unsigned) * ((RX2 + 1) & ~1) + 16;
   if (smem > ctx->smem_optin) return SGW_OK;                    // not done: the generic kernel reports the limit
   PlaneVArgs a;
-  a.twx = g.twx; a.twy = g.twy; a.Tin = Tin; a.Tout = Tout; a.vperm = ctx->d_vperm; a.active = active;
+  a.twx = g.twx; a.twy = g.twy; a.Tin = Tin; a.Tout = Tout; a.vperm = ctx->d_vperm_t; a.active = active;
   a.xs = s.d_xs; a.ytab = s.d_ytab; a.nz = g.nz; a.nvec = nvec; a.ncol = s.ncol; a.nxs = s.nxs;
   const long nitems = (long)nvec * g.nz;
   auto go = [&](auto kern) -> int {
@@ -676,8 +734,8 @@ static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, in
     kern<<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
     return SGW_OK;
   };
-  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, false>));
-  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, true>));
+  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, G, false>));
+  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, G, true>));
   *done = true;
   return SGW_OK;
 }
@@ -688,9 +746,7 @@ static int try_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int n
   if (plane_vloc_variant() == 0 || !s.d_ytab || s.ytab_ry1 != g.ry1 || s.ytab_ry2 != g.ry2) return SGW_OK;
 #define SGW_PV(a, b, c, d) \
   if (g.rx1 == a && g.rx2 == b && g.ry1 == c && g.ry2 == d) return launch_plane_vloc<a, b, c, d>(ctx, g, s, nvec, Tin, Tout, active, done);
-  SGW_PV(8, 9, 8, 9)        // 72 x 72 (Si64)
-  SGW_PV(8, 8, 8, 8)        // 64 x 64
-  SGW_PV(8, 12, 8, 12)      // 96 x 96
+  SGW_PV(8, 9, 8, 9)        // 72 x 72 (Si64); other grids run the generic k_plane
 #undef SGW_PV
   return SGW_OK;
 }
@@ -833,11 +889,12 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
     const int ry1 = ctx->py.r1, ry2 = ctx->py.r2, nxs = (int)xs.size();
     std::vector<int> xpos(nx, -1);
     for (int l = 0; l < nxs; ++l) xpos[xs[l]] = l;
-    std::vector<short> ytab((size_t)nxs * ny, (short)-1);
+    const int ry1p = (ry1 + 7) & ~7;                                // whole 16-byte loads per task
+    std::vector<short> ytab((size_t)nxs * ry2 * ry1p, (short)-1);
     for (size_t c = 0; c < col_x.size(); ++c) {
       const int l = xpos[col_x[c]], y = col_y[c];
       const int j2 = y % ry2, k = y / ry2;
-      ytab[((size_t)j2 * nxs + l) * ry1 + k] = (short)c;
+      ytab[((size_t)j2 * nxs + l) * ry1p + k] = (short)c;
     }
     SGW_CHECK(upload(ctx, &sph->d_ytab, ytab.data(), ytab.size()));
     sph->ytab_ry1 = ry1; sph->ytab_ry2 = ry2;

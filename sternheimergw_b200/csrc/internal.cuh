@@ -147,6 +147,7 @@ struct sgw_ctx {
   sgw::Plan1D px, py, pz;
   sgw::cplx *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
   double *d_vperm = nullptr;    // local potential in permuted real-space order [pz][py][px]
+  double *d_vperm_t = nullptr;  // the same with y fastest: [pz][px][py]
   std::vector<int> permx, permy, permz;  // position -> natural index
   std::vector<sgw::KSlot> slots;
   std::vector<sgw::KPair> pairs;
