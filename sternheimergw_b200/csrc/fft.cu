@@ -304,6 +304,37 @@ __device__ __forceinline__ void stage_mid_vt(cplx *x, int nlines, int ls, int r_
   }
 }
 
+// stage_contig (fft_core.h) over x columns (line start = line_ids[l], element stride es) with the line count padded to a
+// multiple of 8 in the task mapping (see the y stages of k_plane_vloc); same arithmetic
+template <int R, int DIR>
+__device__ __forceinline__ void stage_contig_pad(cplx *x, int nlines, const int *line_ids, int es, int r_other, const cplx *tw,
+                                                 bool do_tw, int tid, int nthreads, int pad) {
+  const int nlp = pad ? (nlines + 7) & ~7 : nlines;
+  const int ntasks = nlp * r_other;
+  TaskIter it(tid, nthreads, nlp);
+  for (int t = tid; t < ntasks; t += nthreads, it.next()) {
+    if (it.l >= nlines) continue;
+    const int a = it.j;
+    cplx *base = x + (line_ids[it.l] + a * R * es);
+    double re[R], im[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const cplx v = base[j * es]; re[j] = v.x; im[j] = v.y; }
+    if (DIR < 0) dft_fwd<R>(re, im); else dft_fwd<R>(im, re);
+    if (do_tw) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) {
+        const cplx w = tw[a * k];
+        const double c = w.x, s = DIR < 0 ? w.y : -w.y;
+        const double p = re[k], q = im[k];
+        re[k] = p * c - q * s;
+        im[k] = p * s + q * c;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) base[k * es] = cmake(re[k], im[k]);
+  }
+}
+
 struct PlaneVArgs {
   const cplx *twx, *twy;
   const cplx *Tin;
@@ -312,7 +343,7 @@ struct PlaneVArgs {
   const int *active;
   const int *xs;            // x columns that hold sphere data (ascending)
   const short *ytab;        // [(j2 * nxs + l) * RY1P + k] -> column index of (x = xs[l], y = j2 + RY2 k) in a T row, or -1
-  int nz, nvec, ncol, nxs;
+  int nz, nvec, ncol, nxs, ypad;
 };
 
 // named barrier over one thread group (ids 1..15; 0 is __syncthreads)
@@ -350,9 +381,11 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
   for (int i = tid; i < ntab / 8; i += NT) ((uint4 *)ytab)[i] = ((const uint4 *)a.ytab)[i];
   for (int i = tid; i < nxs; i += NT) xs[i] = a.xs[i];
   if (tid == 0) {
-    int j = 0, q = 0;
+    int q = 0;
     for (int x = 0; x < NX; ++x) {
-      if (j < nxs && a.xs[j] == x) ++j; else xz[q++] = x;
+      bool used = false;
+      for (int i = 0; i < nxs; ++i) used |= (a.xs[i] == x);
+      if (!used) xz[q++] = x;
     }
     for (int j2 = 0; j2 < RX2; ++j2) {
       unsigned m = 0;
@@ -397,9 +430,13 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
     mbar_wait(bar, parity);
     parity ^= 1u;
     if (ncg > 0) {  // ---- inverse y, stage 1 (strided DFT_RY1 + twiddle), inputs from the staged row
-      const int ntask = ncg * RY2;
-      TaskIter it(gt, GS, ncg);
+      // lines are padded to a multiple of 8 per sub-index: every quarter-warp then works on 8 consecutive columns of ONE
+      // sub-index, i.e. on 8 distinct 16-byte bank groups (the padding lanes idle)
+      const int ncp = a.ypad ? (ncg + 7) & ~7 : ncg;
+      const int ntask = ncp * RY2;
+      TaskIter it(gt, GS, ncp);
       for (int t = gt; t < ntask; t += GS, it.next()) {
+        if (it.l >= ncg) continue;
         const int l = c0 + it.l, j2 = it.j;
         short tb[RY1P];
 #pragma unroll
@@ -427,7 +464,7 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
     }
     group_sync(bid, GS);
     // ---- inverse y, stage 2 (contiguous DFT_RY2)
-    stage_contig<RY2, +1>(plane, ncg, xs + c0, 1, PITCH, RY1, twy, false, gt, GS);
+    stage_contig_pad<RY2, +1>(plane, ncg, xs + c0, PITCH, RY1, twy, false, gt, GS, a.ypad);
     __syncthreads();                                   // y -> x: every column is needed by every row
     // the staging buffer is free: fetch the next item's row while this one is transformed
     const long next = next_active(item + gridDim.x);
@@ -484,13 +521,15 @@ __global__ void __launch_bounds__(NT, 2) k_plane_vloc(PlaneVArgs a) {
     }
     __syncthreads();                                   // x -> y
     // ---- forward y, stage 1 (contiguous DFT_RY2 + twiddle)
-    stage_contig<RY2, -1>(plane, ncg, xs + c0, 1, PITCH, RY1, twy, true, gt, GS);
+    stage_contig_pad<RY2, -1>(plane, ncg, xs + c0, PITCH, RY1, twy, true, gt, GS, a.ypad);
     group_sync(bid, GS);
     if (ncg > 0) {  // ---- forward y, stage 2 (strided DFT_RY1): sphere entries go straight to the output row
       cplx *orow = a.Tout + item * a.ncol;
-      const int ntask = ncg * RY2;
-      TaskIter it(gt, GS, ncg);
+      const int ncp = a.ypad ? (ncg + 7) & ~7 : ncg;
+      const int ntask = ncp * RY2;
+      TaskIter it(gt, GS, ncp);
       for (int t = gt; t < ntask; t += GS, it.next()) {
+        if (it.l >= ncg) continue;
         const int l = c0 + it.l, j2 = it.j;
         const cplx *base = plane + xs[l] + j2 * PITCH;
         double re[RY1], im[RY1];
@@ -717,7 +756,7 @@ static int plane_vloc_variant() {
 template <int RX1, int RX2, int RY1, int RY2>
 static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
                              bool *done) {
-  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384, G = 3;
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384;
   const int ncol_pad = (s.ncol + 7) & ~7, ntab = s.nxs * RY2 * ((RY1 + 7) & ~7);
   const size_t smem = sizeof(cplx) * ((size_t)NY * PITCH + ncol_pad + NX + NY) + sizeof(short) * ntab + sizeof(int) * 2 * NX +
                       sizeof(unsigned) * ((RX2 + 1) & ~1) + 16;
@@ -725,6 +764,7 @@ static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, in
   PlaneVArgs a;
   a.twx = g.twx; a.twy = g.twy; a.Tin = Tin; a.Tout = Tout; a.vperm = ctx->d_vperm_t; a.active = active;
   a.xs = s.d_xs; a.ytab = s.d_ytab; a.nz = g.nz; a.nvec = nvec; a.ncol = s.ncol; a.nxs = s.nxs;
+  { const char *e = getenv("SGW_YPAD"); a.ypad = e ? atoi(e) : 0; }
   const long nitems = (long)nvec * g.nz;
   auto go = [&](auto kern) -> int {
     SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -734,8 +774,12 @@ static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, in
     kern<<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
     return SGW_OK;
   };
-  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, G, false>));
-  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, G, true>));
+  const char *eg = getenv("SGW_PLANE_G");                       // tuning knob: thread groups per CTA (1 | 3 | 6), default 1 (measured: 2.76 / 2.91 / 3.26 ms per 1024 vectors)
+  const int G = eg ? atoi(eg) : 1;
+  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 3, false>));
+  else if (G == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 1, true>));
+  else if (G == 6) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 6, true>));
+  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 3, true>));
   *done = true;
   return SGW_OK;
 }
@@ -865,6 +909,19 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   std::vector<int> xs;
   for (int x = 0; x < nx; ++x)
     if (xused[x]) xs.push_back(x);
+  {
+    // start the list after the largest (cyclic) gap: a sphere occupies x = -r..r, i.e. [nx-r..nx-1, 0..r]; in that order
+    // consecutive entries are consecutive mod nx, so the lanes of a warp that walk the list touch consecutive 16-byte
+    // bank groups across the wrap as well (nx = 0 mod 8 on the usual grids)
+    size_t best = 0;
+    int gap = -1;
+    for (size_t i = 0; i < xs.size(); ++i) {
+      const int prev = xs[(i + xs.size() - 1) % xs.size()];
+      const int d = ((xs[i] - prev) % nx + nx) % nx;
+      if (d > gap) { gap = d; best = i; }
+    }
+    { const char *e = getenv("SGW_XROT"); if (!e || atoi(e)) std::rotate(xs.begin(), xs.begin() + best, xs.end()); }
+  }
   sph->npw = npw;
   sph->ncol = (int)col_x.size();
   sph->nxs = (int)xs.size();
