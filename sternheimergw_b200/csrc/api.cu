@@ -240,7 +240,7 @@ int sgw_get_profile(const sgw_ctx *ctx, int max_classes, double *ms, int64_t *re
 
 const char *sgw_profile_class_name(int cls) {
   static const char *names[PC_N] = {"fft_zpass", "fft_plane", "gemm_project", "gemm_expand", "shift_fused", "seed_blas1",
-                                    "rho_plane", "other", "gw_product"};
+                                    "rho_plane", "other", "gw_product", "shift_gemm"};
   return cls >= 0 && cls < PC_N ? names[cls] : "";
 }
 

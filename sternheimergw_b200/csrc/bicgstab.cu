@@ -66,6 +66,16 @@ struct BicgState {
   int *active;             // [nrhs]
   int *iters;              // [nrhs] outer iterations done
   int *nactive;            // [1]
+  // ---- lazy (coefficient-space) shifted update, see k_shift_coef / k_shift_gemm
+  int lazy;                // 1: the shifted systems are carried as coefficients over the stored basis
+  int Tc, slot, base;      // basis slots per RHS, slot of this outer iteration, outer iteration of the last flush
+  int nv, kcap;            // vectors per slot (nsnap + L), Tc * nv
+  cplx *BAS;               // [nrhs][Tc][nv][n]: per outer iteration the nsnap residual snapshots, then r_0..r_{L-1} of the MR part
+  cplx *CX, *CU;           // [nrhs][kcap][ns] (shift index fastest): x^sigma = XB + cxb U0B + sum_k CX_k BAS_k ; u^sigma_0 = cub U0B + sum_k CU_k BAS_k
+  cplx *cxb, *cub;         // [nrhs][ns]
+  int *flushed;            // [nrhs] XB (= XO) and U0B (= US0) hold a materialised state
+  int *last_stage;         // [nrhs] stage of the last outer iteration the RHS took part in
+  int *base_b;             // [nrhs] outer iteration of the last flush of THIS right-hand side (only active ones are flushed)
 };
 
 __device__ __forceinline__ cplx *seedU(const BicgState &s, int b, int i) { return s.U + ((long)b * (s.L + 1) + i) * s.n; }
@@ -73,7 +83,10 @@ __device__ __forceinline__ cplx *seedR(const BicgState &s, int b, int i) { retur
 __device__ __forceinline__ cplx *seedX(const BicgState &s, int b) { return s.XO + ((long)b * (s.ns + 1)) * s.n; }
 __device__ __forceinline__ cplx *shiftU0(const BicgState &s, int b, int is) { return s.US0 + ((long)b * s.ns + is) * s.n; }
 __device__ __forceinline__ cplx *shiftX(const BicgState &s, int b, int is) { return s.XO + ((long)b * (s.ns + 1) + is + 1) * s.n; }
-__device__ __forceinline__ cplx *snap(const BicgState &s, int b, int k) { return s.SNAP + ((long)b * s.nsnap + k) * s.n; }
+__device__ __forceinline__ cplx *snap(const BicgState &s, int b, int k) {
+  if (s.lazy) return s.BAS + (((long)b * s.Tc + s.slot) * s.nv + k) * s.n;
+  return s.SNAP + ((long)b * s.nsnap + k) * s.n;
+}
 
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ cplx block_reduce(cplx v, cplx *sm /* >= 32 */) {
@@ -329,7 +342,10 @@ __global__ void k_check(BicgState s, double threshold, int outer_iter, int phase
   const double nrm = sqrt(p.x + p.y);
   s.iters[b] = outer_iter;
   const bool conv = nrm < threshold;        // :299 strict '<'
-  if (phase == 1) s.stage[b] = conv ? 1 : 2;
+  if (phase == 1) {
+    s.stage[b] = conv ? 1 : 2;
+    if (s.lazy) s.last_stage[b] = conv ? 1 : 2;
+  }
   if (conv) s.active[b] = 0;
   else atomicAdd(s.nactive, 1);
 }
@@ -601,6 +617,169 @@ __global__ void __launch_bounds__(128) k_shift_coef(BicgState s, ShiftCoef<LT> *
 #pragma unroll
     for (int k = 0; k < NSN; ++k) o.us[k] = U0[1 + k];
   }
+  if (!s.lazy) return;
+  // ---- lazy mode: fold this outer iteration into the coefficients over the stored basis instead of streaming the vectors
+  //   x  += xu0 u0_old + sum_jj xs[jj] snap[jj(jj+1)/2] (+ sum_j xr[j] r_j)        u0 <- uu0 u0_old + sum_k us[k] snap[k]
+  // with u0_old = cub U0B + sum_{k < K0} CU_k BAS_k (K0 = slot * nv entries of the earlier slots)
+  // coefficient arrays are [rhs][k][shift]: the threads of a warp (consecutive shifts of one RHS) touch consecutive entries
+  const long ldc = s.ns;
+  cplx *cx = s.CX + (long)b * s.kcap * ldc + is, *cu = s.CU + (long)b * s.kcap * ldc + is;
+  const int K0 = s.slot * s.nv;
+  const cplx xu0 = o.xu0;
+  s.cxb[idx] = cfma(xu0, s.cub[idx], s.cxb[idx]);
+  for (int k = 0; k < K0; ++k) cx[k * ldc] = cfma(xu0, cu[k * ldc], cx[k * ldc]);
+  for (int k = 0; k < s.nv; ++k) cx[(K0 + k) * ldc] = zero;
+#pragma unroll
+  for (int jj = 0; jj < LT; ++jj) cx[(K0 + jj * (jj + 1) / 2) * ldc] = o.xs[jj];
+  if (stage == 2) {
+#pragma unroll
+    for (int j = 0; j < LT; ++j) cx[(K0 + NSN + j) * ldc] = o.xr[j];
+    const cplx uu0 = o.uu0;
+    s.cub[idx] = cmul(uu0, s.cub[idx]);
+    for (int k = 0; k < K0; ++k) cu[k * ldc] = cmul(uu0, cu[k * ldc]);
+#pragma unroll
+    for (int k = 0; k < NSN; ++k) cu[(K0 + k) * ldc] = o.us[k];
+#pragma unroll
+    for (int j = 0; j < LT; ++j) cu[(K0 + NSN + j) * ldc] = zero;
+  } else {
+    for (int k = 0; k < s.nv; ++k) cu[(K0 + k) * ldc] = zero;
+  }
+}
+
+// ---------------------------------------------------------------- lazy shifted update: materialisation
+// X_b (n x ns) = BAS_b (n x K_b) CX_b (K_b x ns)  [+ XB + U0B diag(cxb) when the RHS has been flushed before], and at a flush
+// also U0_b = BAS_b CU_b + U0B diag(cub): one batched complex DMMA GEMM over the right-hand sides (3M product, cp.async double
+// buffer, the tiling of k_zgemm<false,false> in gemm.cu).  K_b = basis vectors of RHS b since the last flush.
+constexpr int LG_BM = 64, LG_BN = 32, LG_BK = 16, LG_T = 256, LG_PK = LG_BK + 4, LG_PM = LG_BM + 2;
+constexpr size_t LG_SMEM = 2 * (size_t)(LG_BK * LG_PM + LG_BN * LG_PK) * sizeof(cplx);
+// what = 0: x^sigma at the end (every right-hand side that has unmaterialised iterations) ; 1: u^sigma_0 and 2: x^sigma at a flush
+// (only the right-hand sides that are still active: the others keep their coefficients until the end).  K is short (15 vectors per outer iteration), so one CTA walks LG_TM consecutive 64-row tiles
+// times all column tiles of its right-hand side in ONE continuous cp.async pipeline: the first chunk of the next tile is in flight
+// while the last chunk of the current one is multiplied, and the fill / drain of the pipeline is paid once per CTA, not per tile.
+constexpr int LG_TM = 8;
+__global__ void __launch_bounds__(LG_T, 3) k_shift_gemm(BicgState s, int what) {
+  const int b = blockIdx.y;
+  const int itb = s.iters[b], baseb = s.base_b[b];
+  if (itb <= baseb || (what != 0 && !s.active[b])) return;
+  const int K = s.nv * (itb - baseb - 1) + (s.last_stage[b] == 2 ? s.nv : s.nsnap);
+  const int M = s.n, N = s.ns;
+  const int ntn = (N + LG_BN - 1) / LG_BN, ntm_all = (M + LG_BM - 1) / LG_BM;
+  const int mt0 = blockIdx.x * LG_TM, ntm = min(LG_TM, ntm_all - mt0);
+  const int nk = (K + LG_BK - 1) / LG_BK;
+  const int ntile = ntm * ntn, nstep = ntile * nk;
+  const cplx *A = s.BAS + (long)b * s.Tc * s.nv * s.n;                       // M x K, column k at A + k n
+  const cplx *B = (what != 1 ? s.CX : s.CU) + (long)b * s.ns * s.kcap;       // K x N stored [k][is]
+  const long lda = s.n, ldb = s.ns;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ cplx lgsm[];
+  constexpr int ASZ = LG_BK * LG_PM, BSZ = LG_BN * LG_PK;
+  cplx *As = lgsm, *Bs = lgsm + 2 * ASZ;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
+  const int g = lane >> 2, t = lane & 3;
+  double p1[2][2][2], p2[2][2][2], p3[2][2][2];
+  auto stage_load = [&](int st, int step) {
+    const int tile = step / nk, k0 = (step - tile * nk) * LG_BK;
+    const int m0 = (mt0 + tile / ntn) * LG_BM, n0 = (tile % ntn) * LG_BN;
+    cplx *as = As + st * ASZ, *bs = Bs + st * BSZ;
+#pragma unroll
+    for (int r = 0; r < LG_BM * LG_BK / LG_T; ++r) {
+      const int i = tid + r * LG_T;
+      const int m = i % LG_BM, k = i / LG_BM;
+      const bool ok = (k0 + k < K) && (m0 + m < M);
+      cp_async16(as + k * LG_PM + m, ok ? A + (long)(m0 + m) + (long)(k0 + k) * lda : A, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int r = 0; r < LG_BN * LG_BK / LG_T; ++r) {
+      const int i = tid + r * LG_T;
+      const int nn = i % LG_BN, k = i / LG_BN;
+      const bool ok = (k0 + k < K) && (n0 + nn < N);
+      cp_async16(bs + nn * LG_PK + k, ok ? B + (long)(k0 + k) * ldb + (long)(n0 + nn) : B, ok ? 16 : 0);
+    }
+  };
+  const bool fl = s.flushed[b] != 0;
+  cplx *C = what != 1 ? s.XO + ((long)b * (s.ns + 1) + 1) * s.n : s.US0 + (long)b * s.ns * s.n;
+  const cplx *U0B = s.US0 + (long)b * s.ns * s.n;
+  if (nstep > 0) stage_load(0, 0);
+  cp_async_commit();
+  for (int step = 0; step < nstep; ++step) {
+    const int tile = step / nk, kc = step - tile * nk;
+    if (kc == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) p1[i][j][c] = p2[i][j][c] = p3[i][j][c] = 0.0;
+    }
+    if (step + 1 < nstep) stage_load((step + 1) & 1, step + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const cplx *as = As + (step & 1) * ASZ, *bs = Bs + (step & 1) * BSZ;
+#pragma unroll
+    for (int kk = 0; kk < LG_BK; kk += 4) {
+      cplx a[2], bb[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = as[(kk + t) * LG_PM + wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bb[j] = bs[(wn + j * 8 + g) * LG_PK + kk + t];
+      double asum[2], bsum[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) asum[i] = a[i].x + a[i].y;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bsum[j] = bb[j].x + bb[j].y;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(p1[i][j][0], p1[i][j][1], a[i].x, bb[j].x);
+          dmma(p2[i][j][0], p2[i][j][1], a[i].y, bb[j].y);
+          dmma(p3[i][j][0], p3[i][j][1], asum[i], bsum[j]);
+        }
+    }
+    __syncthreads();
+    if (kc == nk - 1) {
+      const int m0 = (mt0 + tile / ntn) * LG_BM, n0 = (tile % ntn) * LG_BN;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int row = m0 + wm + i * 8 + g;
+            const int col = n0 + wn + j * 8 + 2 * t + c;
+            if (row < M && col < N) {
+              cplx acc = cmake(p1[i][j][c] - p2[i][j][c], (p3[i][j][c] - p1[i][j][c]) - p2[i][j][c]);
+              const long off = (long)row + (long)col * s.n;
+              if (fl) {
+                if (what != 1) acc = cadd(cfma(s.cxb[(long)b * s.ns + col], U0B[off], acc), C[off]);
+                else acc = cfma(s.cub[(long)b * s.ns + col], C[off], acc);
+              }
+              C[off] = acc;
+            }
+          }
+    }
+  }
+}
+
+// after a flush: the materialised state is the new base of every right-hand side that took part since the last one
+__global__ void k_lazy_reset(BicgState s) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)s.nrhs * s.ns) return;
+  const int b = (int)(idx / s.ns);
+  if (!s.active[b]) return;
+  s.cxb[idx] = cmake(0.0, 0.0);
+  s.cub[idx] = cmake(1.0, 0.0);
+}
+__global__ void k_lazy_mark(BicgState s, int new_base) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.nrhs) return;
+  if (s.active[b]) { s.flushed[b] = 1; s.base_b[b] = new_base; }
+}
+__global__ void k_lazy_init(BicgState s) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (long)s.nrhs * s.ns) { s.cxb[idx] = cmake(0.0, 0.0); s.cub[idx] = cmake(1.0, 0.0); }
+  if (idx < s.nrhs) { s.flushed[idx] = 0; s.last_stage[idx] = 0; s.base_b[idx] = 0; }
 }
 
 constexpr int CSHIFT_CHUNK = 32;
@@ -684,6 +863,10 @@ __global__ void __launch_bounds__(BT) k_mr_seed(BicgState s) {
   const int e = blockIdx.x * BT + threadIdx.x;
   if (e >= s.n) return;
   cplx r0 = seedR(s, b, 0)[e];
+  if (s.lazy) {   // r_0 (before :919-925) and r_1..r_{L-1} (after the Gram-Schmidt) are basis vectors of the shifted x updates (:889,:905)
+    snap(s, b, s.nsnap)[e] = r0;
+    for (int jj = 1; jj <= L - 1; ++jj) snap(s, b, s.nsnap + jj)[e] = seedR(s, b, jj)[e];
+  }
   cplx *px = seedX(s, b) + e;
   cplx x = cfma(sg[0], r0, *px);                                                  // :833
   cplx u0 = cfma(cneg(sg[L - 1]), seedU(s, b, L)[e], seedU(s, b, 0)[e]);          // :835
@@ -740,6 +923,7 @@ static int launch_shift_collapsed(sgw_ctx *ctx, const BicgState &s) {
   const long tot = (long)s.nrhs * s.ns;
   k_shift_coef<LT><<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(s, coef);
   SGW_LAUNCH_CHECK();
+  if (s.lazy) return SGW_OK;            // the vectors are touched once, at the flush / at the end (lazy_materialise)
   const int nchunks = (s.ns + CSHIFT_CHUNK - 1) / CSHIFT_CHUNK;     // equal-sized chunks of <= 32 shifts per CTA
   const int chunk = (s.ns + nchunks - 1) / nchunks;
   dim3 grid((unsigned)((s.n + BT - 1) / BT), (unsigned)s.nrhs, (unsigned)((s.ns + chunk - 1) / chunk));
@@ -751,6 +935,52 @@ static int launch_shift_collapsed(sgw_ctx *ctx, const BicgState &s) {
 static bool shift_faithful() {
   const char *e = getenv("SGW_SHIFT");
   return e && strcmp(e, "faithful") == 0;
+}
+// SGW_SHIFT=stream keeps the collapsed update that streams u^sigma_0 / x^sigma every outer iteration (k_shift_apply)
+static bool shift_stream() {
+  const char *e = getenv("SGW_SHIFT");
+  return e && strcmp(e, "stream") == 0;
+}
+// basis slots (outer iterations) kept per right-hand side before the lazy shifted update is flushed (SGW_LAZY_TC)
+static int lazy_period() {
+  const char *e = getenv("SGW_LAZY_TC");
+  const int v = e ? atoi(e) : 6;
+  return std::max(1, std::min(v, 64));
+}
+static bool lazy_shift(int lmax, int nshift) { return nshift > 1 && (lmax == 2 || lmax == 4) && !shift_faithful() && !shift_stream(); }
+
+// device bytes of solver state per right-hand side (the batch sizing of coulomb.cu / green uses this)
+size_t bicgstab_bytes_per_rhs(int n, int lmax, int nshift) {
+  const size_t L1 = lmax + 1, ns = nshift - 1, nsnap = (size_t)lmax * (lmax + 1) / 2 + 1;
+  size_t v = 2 * L1 + 1;                                         // U, R, RT
+  v += ns;                                                       // u^sigma_0
+  if (lazy_shift(lmax, nshift)) v += (size_t)lazy_period() * (nsnap + lmax);
+  else if (ns > 0) v += nsnap;
+  return v * (size_t)n * sizeof(cplx);
+}
+
+// flush_iter > 0: flush of the still active right-hand sides after outer iteration flush_iter; 0: final materialisation
+static int lazy_materialise(sgw_ctx *ctx, const BicgState &s, int flush_iter) {
+  static bool attr = false;
+  if (!attr) {
+    SGW_CUDA(cudaFuncSetAttribute(k_shift_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
+    attr = true;
+  }
+  ProfScope prof(ctx, PC_SHIFT_GEMM);
+  const int ntm = (s.n + LG_BM - 1) / LG_BM;
+  dim3 grid((unsigned)((ntm + LG_TM - 1) / LG_TM), (unsigned)s.nrhs);
+  k_shift_gemm<<<grid, LG_T, LG_SMEM, ctx->stream>>>(s, flush_iter > 0 ? 2 : 0);
+  SGW_LAUNCH_CHECK();
+  if (flush_iter > 0) {
+    k_shift_gemm<<<grid, LG_T, LG_SMEM, ctx->stream>>>(s, 1);
+    SGW_LAUNCH_CHECK();
+    const long tot = (long)s.nrhs * s.ns;
+    k_lazy_reset<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(s);
+    SGW_LAUNCH_CHECK();
+    k_lazy_mark<<<(unsigned)((s.nrhs + 127) / 128), 128, 0, ctx->stream>>>(s, flush_iter);
+    SGW_LAUNCH_CHECK();
+  }
+  return SGW_OK;
 }
 
 int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo) {
@@ -768,7 +998,18 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   SGW_CHECK(ws(ctx, "bi_R", (size_t)(nr * L1 * n), &s.R));
   SGW_CHECK(ws(ctx, "bi_RT", (size_t)(nr * n), &s.RT));
   SGW_CHECK(ws(ctx, "bi_US0", (size_t)(nr * s.ns * n) + 1, &s.US0));
-  SGW_CHECK(ws(ctx, "bi_SNAP", s.ns > 0 ? (size_t)(nr * s.nsnap * n) : 1, &s.SNAP));
+  s.lazy = lazy_shift(lmax, sb.nshift) ? 1 : 0;
+  s.Tc = lazy_period(); s.slot = 0; s.base = 0;
+  s.nv = s.nsnap + lmax; s.kcap = s.Tc * s.nv;
+  SGW_CHECK(ws(ctx, "bi_SNAP", (s.ns > 0 && !s.lazy) ? (size_t)(nr * s.nsnap * n) : 1, &s.SNAP));
+  SGW_CHECK(ws(ctx, "bi_BAS", s.lazy ? (size_t)(nr * s.Tc * s.nv * n) : 1, &s.BAS));
+  SGW_CHECK(ws(ctx, "bi_CX", s.lazy ? (size_t)(nr * s.ns * s.kcap) : 1, &s.CX));
+  SGW_CHECK(ws(ctx, "bi_CU", s.lazy ? (size_t)(nr * s.ns * s.kcap) : 1, &s.CU));
+  SGW_CHECK(ws(ctx, "bi_cxb", (size_t)(nr * s.ns) + 1, &s.cxb));
+  SGW_CHECK(ws(ctx, "bi_cub", (size_t)(nr * s.ns) + 1, &s.cub));
+  SGW_CHECK(ws(ctx, "bi_flushed", (size_t)nr, &s.flushed));
+  SGW_CHECK(ws(ctx, "bi_lstage", (size_t)nr, &s.last_stage));
+  SGW_CHECK(ws(ctx, "bi_baseb", (size_t)nr, &s.base_b));
   SGW_CHECK(ws(ctx, "bi_seed", (size_t)nr, &s.seed));
   SGW_CHECK(ws(ctx, "bi_shift", (size_t)(nr * s.ns) + 1, &s.shift));
   SGW_CHECK(ws(ctx, "bi_step", (size_t)(nr * s.ns * lmax) + 1, &s.step));
@@ -803,10 +1044,16 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   const bool collapsed = s.ns > 0 && !faithful && (lmax == 2 || lmax == 4);
   k_init_vec<<<gvec, BT, 0, st>>>(s, sb.d_b, sb.ldb, collapsed ? 0 : 1);
   SGW_LAUNCH_CHECK();
+  if (s.lazy) {
+    const long tot = std::max<long>(nr * s.ns, nr);
+    k_lazy_init<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(s);
+    SGW_LAUNCH_CHECK();
+  }
 
   const long ldv = n;   // vectors inside U/R are contiguous with stride (L+1)*n between RHS
   int rc = SGW_OK;
   for (int iter = 1; iter <= max_iter && rc == SGW_OK; ++iter) {
+    s.slot = iter - 1 - s.base;
     // ---- bicg_part (seed system; the shifted systems only record their step scalars)
     for (int jj = 0; jj < lmax && rc == SGW_OK; ++jj) {
       DotSpec d; d.nd = 1; d.ka[0] = 0; d.ia[0] = jj; d.kb[0] = 2; d.ib[0] = 0;     // (r_j, rt0)
@@ -883,6 +1130,11 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
       k_check<<<gb, 128, 0, st>>>(s, threshold, iter, 2);                           // :245
       SGW_LAUNCH_CHECK();
     }
+    if (s.lazy && iter - s.base == s.Tc) {   // basis slots exhausted: materialise x^sigma and u^sigma_0, start a new window
+      rc = lazy_materialise(ctx, s, iter);
+      if (rc != SGW_OK) break;
+      s.base = iter;
+    }
     SGW_CUDA(cudaMemcpyAsync((void *)&h_nactive[iter & 1], s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
     SGW_CUDA(cudaEventRecord(ctx->ev_iter[iter & 1], st));
     if (iter >= 2) {
@@ -891,6 +1143,7 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
     }
   }
   if (rc != SGW_OK) return rc;
+  if (s.lazy) SGW_CHECK(lazy_materialise(ctx, s, 0));
   k_set_ierr<<<gb, 128, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();
   k_nan_scan<<<gvec, BT, 0, st>>>(s, sb.d_ierr, d_todo);

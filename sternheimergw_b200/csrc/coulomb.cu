@@ -276,9 +276,8 @@ static FreqList make_omega(int nfreq, const sgw_cplx *freq) {   // solve_linter.
 }
 
 static size_t solver_bytes_per_rhs(const sgw_ctx *ctx, const KSlot &ks, int lmax, int nshift) {
-  const size_t n = ks.npwx, L1 = lmax + 1, ns = nshift - 1;
-  const size_t nsnap = (size_t)lmax * (lmax + 1) / 2 + 1;
-  size_t v = 2 * L1 * n + n + nsnap * n + ns * n + (size_t)nshift * n + n;                // bicgstab state + sv_x + rhs
+  const size_t n = ks.npwx;
+  size_t v = bicgstab_bytes_per_rhs((int)n, lmax, nshift) / sizeof(cplx) + (size_t)nshift * n + n;   // bicgstab state + sv_x + rhs
   v += 2 * (size_t)ctx->nr3 * ks.sph.ncol;                                                // H.psi column buffers
   v += 4 * (size_t)(ks.nkb + ks.nbnd);                                                    // projector coefficients
   return v * sizeof(cplx);

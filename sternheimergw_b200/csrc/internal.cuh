@@ -118,7 +118,7 @@ struct KPair {
 };
 
 // kernel classes timed separately (CUDA events on the library's stream) when profiling is on
-enum ProfClass { PC_FFT_Z = 0, PC_FFT_PLANE, PC_GEMM_PROJ, PC_GEMM_OUT, PC_SHIFT, PC_SEED, PC_RHO_PLANE, PC_OTHER, PC_GW_PROD, PC_N };
+enum ProfClass { PC_FFT_Z = 0, PC_FFT_PLANE, PC_GEMM_PROJ, PC_GEMM_OUT, PC_SHIFT, PC_SEED, PC_RHO_PLANE, PC_OTHER, PC_GW_PROD, PC_SHIFT_GEMM, PC_N };
 struct ProfRec { int cls; cudaEvent_t a, b; };
 
 // grid%corr_fft of the correlation cutoff (sgw_set_corr_grid): the 6-D transforms of fft6.f90 act on ngm_c <= ~100 G vectors
@@ -322,6 +322,7 @@ struct SolveBatch {
   int *d_ierr;               // device nrhs
 };
 int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double threshold, int max_iter, const int *d_todo);
+size_t bicgstab_bytes_per_rhs(int n, int lmax, int nshift);   // solver state per right-hand side (without x and b)
 int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo);
 int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_cfg *cfg);
 
