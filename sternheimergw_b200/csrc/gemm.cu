@@ -29,15 +29,17 @@ template <bool A_KCONTIG, bool CONJA>
 __global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
                                                const cplx *__restrict__ B, long ldb, cplx *__restrict__ C, long ldc,
                                                cplx alpha, cplx beta, int kchunk, long split_stride,
-                                               const int *__restrict__ active) {
+                                               const int *__restrict__ list, const int *__restrict__ count, int list_mode) {
+  // Compacted batches: with `list` the problem has *count columns; list_mode bit 0: column j of B is B's column list[j]
+  // (gather), list_mode bit 1: column j of C is C's column list[j] (scatter); both bits may be set.  Tiles beyond the
+  // count exit at once, so a batch in which most right-hand sides have converged costs what its active columns cost.
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (list) {
+    N = min(N, *count);
+    if (n0 >= N) return;
+  }
   const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (active) {
-    bool any = false;
-    for (int n = n0; n < min(N, n0 + BN); ++n) any |= (active[n] != 0);
-    if (!any) return;
-  }
   constexpr int ASZ = a_tile_elems<A_KCONTIG>();
   extern __shared__ cplx gsm[];
   cplx *As = gsm;                      // [NSTAGE][ASZ]
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx
       const int i = tid + r * GT;
       const int k = i % BK, n = i / BK;
       const bool ok = (k0 + k < kend) && (n0 + n < N);
-      cp_async16(bs + n * PK + k, ok ? B + (long)(k0 + k) + (long)(n0 + n) * ldb : B, ok ? 16 : 0);
+      const long bcol = ok ? ((list_mode & 1) ? list[n0 + n] : n0 + n) : 0;
+      cp_async16(bs + n * PK + k, ok ? B + (long)(k0 + k) + bcol * ldb : B, ok ? 16 : 0);
     }
   };
 
@@ -129,8 +132,9 @@ __global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx
         if (row < M && col < N) {
           cplx acc = cmake(p1[i][j][c] - p2[i][j][c], (p3[i][j][c] - p1[i][j][c]) - p2[i][j][c]);
           cplx r = cmul(alpha, acc);
-          if (has_beta) r = cfma(beta, Cz[(long)row + (long)col * ldc], r);
-          Cz[(long)row + (long)col * ldc] = r;
+          const long ccol = (list_mode & 2) ? list[col] : col;
+          if (has_beta) r = cfma(beta, Cz[(long)row + ccol * ldc], r);
+          Cz[(long)row + ccol * ldc] = r;
         }
       }
 }
@@ -140,10 +144,13 @@ static int zgemm_init(sgw_ctx *ctx);
 
 template <bool A_KCONTIG, bool CONJA>
 static int launch_zgemm(sgw_ctx *ctx, dim3 grid, int M, int N, int K, const cplx *A, long lda, const cplx *B, long ldb, cplx *C,
-                        long ldc, cplx alpha, cplx beta, int kchunk, long split_stride, const int *active) {
+                        long ldc, cplx alpha, cplx beta, int kchunk, long split_stride, const int *list = nullptr,
+                        const int *count = nullptr, int list_mode = 0) {
   constexpr size_t smem = zgemm_smem<A_KCONTIG>();
   SGW_CHECK(zgemm_init(ctx));
-  k_zgemm<A_KCONTIG, CONJA><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, active);
+  if (!list) list_mode = 0;
+  k_zgemm<A_KCONTIG, CONJA><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, list, count,
+                                                             list_mode);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
@@ -162,9 +169,9 @@ static int zgemm_init(sgw_ctx *ctx) {
 __global__ void k_coef_finish(int m, int nkb, int nvec, int nsplit, const cplx *__restrict__ part, long split_stride,
                               const double *__restrict__ dion, const int *__restrict__ dptr, const int *__restrict__ dcol,
                               const double *__restrict__ dval, double alpha_pv, cplx *__restrict__ coef,
-                              const int *__restrict__ active) {
+                              const int *__restrict__ count) {
   const int v = blockIdx.x;
-  if (active && !active[v]) return;
+  if (count && v >= *count) return;
   extern __shared__ cplx c[];
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     cplx s = cmake(0.0, 0.0);
@@ -207,17 +214,52 @@ __global__ void k_add_sigma(int n, int nvec, const cplx *__restrict__ psi, long 
   out[(long)v * ldout + i] = cfma(sg, psi[(long)v * ldpsi + i], out[(long)v * ldout + i]);
 }
 
+// list[j] = index of the j-th active vector (ascending), *count = how many: one CTA, ballot + prefix over warps
+__global__ void __launch_bounds__(1024) k_compact_active(int nvec, const int *__restrict__ active, int *__restrict__ list,
+                                                         int *__restrict__ count) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int v0 = 0; v0 < nvec; v0 += 1024) {
+    const int v = v0 + threadIdx.x;
+    const bool on = v < nvec && active[v] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int i = 0; i < w; ++i) off += wsum[i];
+    if (on) list[off + __popc(bal & ((1u << lane) - 1u))] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
 int gemm_ch_n(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, const cplx *B, long ldb, cplx *C, long ldc) {
   if (m <= 0 || n <= 0) return SGW_OK;
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, 1);
-  return launch_zgemm<true, true>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, cmake(1, 0), cmake(0, 0), k > 0 ? k : 1, 0, nullptr);
+  return launch_zgemm<true, true>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, cmake(1, 0), cmake(0, 0), k > 0 ? k : 1, 0);
 }
 
 int gemm_n_n(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, const cplx *B, long ldb, cplx beta,
              cplx *C, long ldc) {
   if (m <= 0 || n <= 0) return SGW_OK;
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, 1);
-  return launch_zgemm<false, false>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k > 0 ? k : 1, 0, nullptr);
+  return launch_zgemm<false, false>(ctx, grid, m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k > 0 ? k : 1, 0);
+}
+
+// compact list of the active vectors of a batch (nullptr list = all active)
+static int active_list(sgw_ctx *ctx, int nvec, const int *active, int **list, int **count) {
+  *list = *count = nullptr;
+  if (!active) return SGW_OK;
+  SGW_CHECK(ws(ctx, "nl_list", (size_t)nvec, list));
+  SGW_CHECK(ws(ctx, "nl_count", (size_t)1, count));
+  k_compact_active<<<1, 1024, 0, ctx->stream>>>(nvec, active, *list, *count);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
 }
 
 int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, const cplx *psi, long ldpsi, cplx *out,
@@ -247,6 +289,11 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
     if (best < 0 || cost < best * 0.98) { best = cost; nsplit = ns; kchunk = kc; }
   }
   cplx *part = nullptr, *coef = nullptr;
+  int *list = nullptr, *count = nullptr;
+  {
+    ProfScope prof(ctx, PC_OTHER);
+    SGW_CHECK(active_list(ctx, nvec, active, &list, &count));
+  }
   const long split_stride = (long)m * nvec;
   SGW_CHECK(ws(ctx, "nl_part", (size_t)split_stride * nsplit, &part));
   SGW_CHECK(ws(ctx, "nl_coef", (size_t)split_stride, &coef));
@@ -254,19 +301,19 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
     dim3 grid((m + BM - 1) / BM, (nvec + BN - 1) / BN, nsplit);
     ProfScope prof(ctx, PC_GEMM_PROJ);
     SGW_CHECK((launch_zgemm<true, true>(ctx, grid, m, nvec, ks.npw, ks.d_P, ks.npwx, psi, ldpsi, part, m, cmake(1, 0),
-                                         cmake(0, 0), kchunk, split_stride, active)));
+                                         cmake(0, 0), kchunk, split_stride, list, count, 1)));
   }
   {
     ProfScope prof(ctx, PC_OTHER);
     k_coef_finish<<<nvec, 128, (size_t)m * sizeof(cplx), ctx->stream>>>(m, ks.nkb, nvec, nsplit, part, split_stride, ks.d_dion, ks.d_dion_ptr, ks.d_dion_col, ks.d_dion_val,
-                                                                      alpha_pv, coef, active);
+                                                                      alpha_pv, coef, count);
     SGW_LAUNCH_CHECK();
   }
   {
     dim3 grid((ks.npwx + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
     ProfScope prof(ctx, PC_GEMM_OUT);
     SGW_CHECK((launch_zgemm<false, false>(ctx, grid, ks.npwx, nvec, m, ks.d_P, ks.npwx, coef, m, out, ldout, cmake(1, 0),
-                                           cmake(0, 0), m, 0, active)));
+                                           cmake(0, 0), m, 0, list, count, 2)));
   }
   return SGW_OK;
 }
@@ -276,8 +323,10 @@ int dense_apply(sgw_ctx *ctx, const KSlot &ks, int nvec, const cplx *psi, long l
   if (nvec <= 0) return SGW_OK;
   const int n = ks.npw;
   dim3 grid((n + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
+  int *list = nullptr, *count = nullptr;
+  SGW_CHECK(active_list(ctx, nvec, active, &list, &count));
   SGW_CHECK((launch_zgemm<false, false>(ctx, grid, n, nvec, n, ks.d_A, n, psi, ldpsi, out, ldout, cmake(1, 0), cmake(0, 0), n, 0,
-                                         active)));
+                                         list, count, 3)));
   dim3 g2((n + 255) / 256, nvec);
   k_add_sigma<<<g2, 256, 0, ctx->stream>>>(n, nvec, psi, ldpsi, sigma, sigma_stride, out, ldout, active);
   SGW_LAUNCH_CHECK();
