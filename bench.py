@@ -13,7 +13,11 @@ exact eigenvectors of the synthetic Hamiltonian the operator applies.
 value      : whole-job solves/s, operator tables resident in HBM, device time (CUDA events on the library's stream)
 e2e        : same metric through the C ABI with HOST buffers: every step re-installs all operator tables (H2D),
              runs sgw_coulomb and reads scrcoul back (D2H), wall clock around the blocking calls
-roofline   : the kernel class with the largest share of the timed region, timed live with CUDA events
+roofline   : the ONE kernel class with the largest share of the timed region: its own algorithmic bytes / flops per launch
+              / CUDA-event time / measured peak; `traffic` = ncu DRAM bytes per launch
+time_to_W  : BASELINE's second metric on a fixed block: tables H2D + sgw_coulomb of NTW perturbations (split over the ranks,
+             do_stern.f90:199) + gather + unfold_w + invert_epsilon + result on the host, wall clock (strong scaling over N)
+parity     : in-run check of the timed workload against oracle/ (H.psi and one 63-shift solve at the bench threshold)
 cpu_baseline: the oracle (kind "port": the Fortran reference cannot be built here) on a bounded sample, host cores
 """
 from __future__ import annotations
@@ -37,6 +41,8 @@ UNIT = "solves/s"
 NFS = 32               # imaginary frequencies -> 63 shifts (solve_linter.f90:238-252)
 NGC = 1900             # G-perturbations of the q-point (~59 x 32)
 THRESHOLD = 1e-4       # thres_coul default (main/src/gw_input.yml)
+NTW = 64               # perturbations (= G vectors kept) of the fixed time-to-W block
+DMMA_PIPE_TFLOPS = 37.05   # FP64 MMA pipe of one B200, register-only mma.sync loop (tools/micro/dmma_peak.cu, round 1)
 
 
 def workload(name="si64"):
@@ -289,6 +295,98 @@ def sigma_c_leg(device, f64_peak, reps=3):
     return out
 
 
+
+# ----------------------------------------------------------------------------------------------------- time-to-W, parity
+def time_to_w_block(ctx, syn, cfg, fiu, rank, world, barrier):
+    """BASELINE metric (ii), driver-visible: one q-point that keeps NTW G vectors (NTW perturbations, all 32 frequencies,
+    128 bands x 63 shifts each): operator tables host -> device on every rank, `coulomb` on the rank's block of
+    perturbations (parallel_task's rule, do_stern.f90:199), gather of the eps columns (:211), unfold_w + invert_epsilon
+    with the frequencies shared among the ranks, result eps^-1 - 1 on the root's host.  Total work is FIXED, so the
+    figure at N GPUs against N = 1 is the strong scaling of time-to-W.  Wall clock between two barriers."""
+    from sternheimergw_b200.dist import do_stern_q
+    ngc = NTW
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    t = {}
+    barrier()
+    t0 = time.perf_counter()
+    ctx.install_system(syn)
+    t["install_s"] = time.perf_counter() - t0
+    stat = {}
+
+    def coulomb_fn(config, igstart, num_g_corr, num_task, ig_unique, fiu_):
+        tc = time.perf_counter()
+        scr = ctx.coulomb(config, igstart, num_g_corr, num_task, ig_unique, fiu_)
+        stat["coulomb_s"] = time.perf_counter() - tc
+        stat["h_psi"] = int(ctx.stats()["n_linear_op"])
+        return scr
+
+    tm = {}
+    w, (first, last, num_task) = do_stern_q(coulomb_fn, cfg, ngc, igu, fiu, unfold_fn=ctx.unfold_w,
+                                            invert_fn=lambda a, lgamma=False: ctx.invert_epsilon(a, lgamma=lgamma),
+                                            shard_invert=True, timings=tm)
+    t_rank = time.perf_counter() - t0
+    barrier()
+    total = time.perf_counter() - t0
+    if rank != 0:
+        return None
+    solves = ngc * syn.nbnd_occ * (2 * NFS - 1)
+    out = {"what": f"one q-point keeping {ngc} G vectors: {ngc} perturbations x {syn.nbnd_occ} bands x {2 * NFS - 1} shifts, "
+                   "tables H2D + coulomb + gather + unfold_w + invert_epsilon + eps^-1 - 1 on the host (fixed total work: strong scaling)",
+           "n_gpus": world, "perturbations": ngc, "solves": int(solves), "seconds": total, "solves_per_s": solves / total,
+           "rank0": {"install_s": t["install_s"], "coulomb_s": stat.get("coulomb_s"), **tm, "total_s": t_rank},
+           "tasks_per_rank": [int(x) for x in num_task],
+           "eps_inv_minus_1_00_w0": [float(w[0, 0, 0].real), float(w[0, 0, 0].imag)]}
+    return out
+
+
+def invert_epsilon_full(ctx, ngc=NGC, nfs=NFS):
+    """invert_epsilon.f90:23 at the size of a full Si64 q-point (ngc x ngc x nfs), on a synthetic diagonally dominant eps."""
+    rng = np.random.default_rng(3)
+    eps = np.asfortranarray((rng.standard_normal((ngc, ngc, nfs)) + 1j * rng.standard_normal((ngc, ngc, nfs))) * (0.3 / np.sqrt(ngc)))
+    eps[np.arange(ngc), np.arange(ngc), :] += 1.5
+    t0 = time.perf_counter()
+    w = ctx.invert_epsilon(eps)
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.stats()["ms_total"]
+    resid = float(np.abs((w[:, :, 1] + np.eye(ngc)) @ eps[:, :, 1] - np.eye(ngc)).max())
+    flop = 8.0 * ngc ** 3 * nfs
+    return {"ngc": ngc, "nfs": nfs, "wall_s": wall, "device_ms": dev_ms, "tflops_device": flop / (dev_ms * 1e-3) / 1e12 if dev_ms > 0 else None,
+            "residual_max": resid, "note": "wall includes the H2D / D2H of the 2 x 1.85 GB matrices from pageable host memory"}
+
+
+def parity_check(ctx, syn, cfg):
+    """In-run parity of the timed workload against oracle/ (the C restatement of the reference): (a) linear_op on two random
+    vectors, (b) one right-hand side of the bench step -- all 63 shifts, bench threshold -- through select_solver on both
+    sides.  Tolerances: SURVEY 8d (1e-12; same outer-iteration count +-1 and 10 x threshold at production thresholds)."""
+    import oracle
+    import synth
+    ps = oracle.PwSystem(syn)
+    kq = syn.kpairs[0].kq
+    rng = np.random.default_rng(synth.SEED)
+    psi = np.zeros((kq.npwx, 2), dtype=complex, order="F")
+    psi[:kq.npw] = rng.standard_normal((kq.npw, 2)) + 1j * rng.standard_normal((kq.npw, 2))
+    om = np.array([0.13 + 0.2j, -0.4 + 0.05j])
+    out = ctx.linear_op(0, om, kq.alpha_pv, psi)
+    err_op = 0.0
+    for v in range(2):
+        ref = ps.linear_op(0, om[v], kq.alpha_pv, psi[:, v])
+        err_op = max(err_op, float(np.abs(out[:, v] - ref).max() / np.abs(ref).max()))
+    b = psi[:, :1] - kq.evq @ (kq.evq.conj().T @ psi[:, :1])
+    b = np.asfortranarray(b / np.linalg.norm(b))
+    fiu = synth.imag_freqs(NFS)
+    omega = np.concatenate([fiu, -fiu[1:]])
+    sigma = np.asfortranarray(-(kq.et[0] + omega).reshape(-1, 1))
+    x, ierr = ctx.select_solver(cfg, 0, b, sigma)
+    it_gpu = int(ctx.stats()["n_outer_max"])
+    xo, ierr_o, so = ps.select_solver(0, b[:kq.npw, 0], sigma[:, 0], oracle.make_cfg(priority=(1, 3), threshold=THRESHOLD))
+    err_x = float(np.abs(x[:kq.npw, :, 0] - xo).max() / np.abs(xo).max())
+    ok = bool(err_op < 1e-12 and int(ierr[0]) == 0 and ierr_o == 0 and abs(it_gpu - so["n_outer"]) <= 1 and
+              (err_x < 10 * THRESHOLD or it_gpu != so["n_outer"]))
+    return {"ok": ok, "linear_op_rel_err": err_op, "linear_op_tol": 1e-12, "solve_rel_err_63_shifts": err_x,
+            "solve_tol": 10 * THRESHOLD, "outer_iterations": {"gpu": it_gpu, "oracle": int(so["n_outer"])},
+            "against": "oracle/ (C restatement of the reference, kind 'port'), same inputs, in this run"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,10 +468,12 @@ def main():
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    dev_ms, launches, nop, solver_ms = 0.0, 0, 0, 0.0
+    dev_ms, launches, nop, solver_ms, coll_ms, step_ms = 0.0, 0, 0, 0.0, 0.0, []
     for s in range(args.warmup, args.warmup + args.steps):
         scr, st, prof, t_coll = step(s)
         dev_ms += st["ms_total"] + t_coll
+        coll_ms += t_coll
+        step_ms.append(st["ms_total"])
         launches += st["n_kernel_launch"]
         solver_ms += st["ms_solver"]
         nop += st["n_linear_op"]
@@ -400,10 +500,14 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e0)
 
-    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    # ---- time-to-W(q, omega) of a FIXED block (strong scaling): NTW perturbations of a q-point that keeps NTW G vectors
+    ttw = time_to_w_block(ctx, syn, cfg, fiu, rank, world, barrier)
+    my_step = float(np.mean(step_ms))
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms, coll_ms, my_step, -my_step], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms = [float(x) for x in t.cpu()]
+    dev_ms, wall_ms, e2e_ms, coll_ms, step_max, step_min = [float(x) for x in t.cpu()]
+    step_min = -step_min
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,30 +523,38 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     f64_peak = zgemm_peak_tflops()
+    f64_src = "cuBLAS ZGEMM 4096^3 via torch.matmul(complex128), measured in this run (no FP64 entry in MEASURED_PEAKS.json)"
     kq = syn.kpairs[0].kq
     n, npw, m = kq.npwx, kq.npw, kq.vkb.shape[1] + nocc
     nnr = syn.nnr
     L, ns = 4, nshift - 1
     ncol = int(len(set(((kq.nl_igk - 1) % (syn.nr[0] * syn.nr[1])).tolist())))
     outer_rhs = nop / (2.0 * L)                      # sum over RHS of outer iterations they took part in
-    # algorithmic work per unit
+    nrhs_step = P * nocc * args.steps
+    nsnap = L * (L + 1) // 2 + 1
+    kbar = (nsnap + L) * outer_rhs / max(1, nrhs_step)   # basis vectors per right-hand side at the materialisation
+    # ALGORITHMIC work of every kernel class over the timed steps; one unit = one H.psi (vector)
+    # unless stated.  HBM classes in bytes, tensor classes in flop (8 flop per complex multiply-add: the cuBLAS convention).
     alg = {
-        "fft_plane": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16 + 0.0), "GB/s"),
+        "fft_plane": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16), "GB/s"),
         "fft_zpass": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16 + 4 * 16.0 * n), "GB/s"),
         "gemm_project": ("tensor", nop * 8.0 * npw * m, "TFLOP/s"),
         "gemm_expand": ("tensor", nop * 8.0 * n * m, "TFLOP/s"),
-        "shift_fused": ("hbm", outer_rhs * (4.0 * ns + (L * (L + 1) // 2 + 1) + L) * 16.0 * n, "GB/s"),
+        "shift_gemm": ("tensor", nrhs_step * 8.0 * n * kbar * ns, "TFLOP/s"),
+        # the streaming shifted update exists only with SGW_SHIFT=stream; in the default (lazy) mode the class holds the tiny
+        # coefficient kernels and has no roofline
+        **({} if prof_tot.get("shift_gemm", {"ms": 0})["ms"] > 0 else {"shift_fused": ("hbm", outer_rhs * (4.0 * ns + nsnap + L) * 16.0 * n, "GB/s")}),
         # seed recurrences: SURVEY 8d fused floor of the seed part, 3L(L+1)+4L + (3L+7) = 95 vector passes at L = 4
         "seed_blas1": ("hbm", outer_rhs * (3.0 * L * (L + 1) + 4 * L + 3 * L + 7) * 16.0 * n, "GB/s"),
     }
-    # measured DRAM bytes per vector (ncu --set full, profiles/traffic.json; per right-hand side and outer iteration for shift_fused)
+    # measured DRAM bytes per unit (ncu --set full, profiles/traffic.json)
     traffic = {}
     try:
         traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text())
     except Exception:
         pass
     units_per_class = {"fft_plane": nop, "fft_zpass": 2 * nop, "gemm_project": nop, "gemm_expand": nop, "shift_fused": outer_rhs,
-                       "seed_blas1": outer_rhs}
+                       "seed_blas1": outer_rhs, "shift_gemm": nrhs_step}
     tot_prof = sum(v["ms"] for v in prof_tot.values()) or 1.0
     kernels = {}
     for k, v in prof_tot.items():
@@ -454,47 +566,54 @@ def main():
             per_launch = units_per_class[k] / max(1, v["regions"])
             tr = traffic.get(k, {}).get("dram_bytes_per_unit")
             ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "peak_source": hbm_src if bound == "hbm" else f64_src,
                         "algorithmic_per_launch": work / max(1, v["regions"]), "avg_launch_ms": v["ms"] / max(1, v["regions"]),
                         "traffic": tr * per_launch if tr else None})
-            for extra in ("fp64_pipe_pct", "tensor_pipe_pct", "dram_pct"):
+            if bound == "tensor":
+                # the kernels use the 3-multiplication complex product: 6 real flop per complex multiply-add actually run on the pipe
+                ent["dmma_pipe"] = {"achieved_real_tflops": 0.75 * ach, "peak": DMMA_PIPE_TFLOPS, "frac": 0.75 * ach / DMMA_PIPE_TFLOPS,
+                                    "peak_source": "register-only mma.sync f64 loop, tools/micro/dmma_peak.cu (round 1)"}
+            for extra in ("fp64_pipe_pct", "tensor_pipe_pct", "dram_pct", "smem_pipe_pct"):
                 if extra in traffic.get(k, {}):
                     ent[extra + "_ncu"] = traffic[k][extra]
         kernels[k] = ent
     fft_ms = prof_tot.get("fft_plane", {"ms": 0})["ms"] + prof_tot.get("fft_zpass", {"ms": 0})["ms"]
-    gemm_ms = prof_tot.get("gemm_project", {"ms": 0})["ms"] + prof_tot.get("gemm_expand", {"ms": 0})["ms"]
     hpsi_fft = None
     if fft_ms > 0:
-        surv = nop * (192.0 * nnr + 32.0 * npw)       # six unfused 1-D passes over the full box
+        own = alg["fft_plane"][1] + alg["fft_zpass"][1]          # the pipeline's own algorithmic bytes (sphere columns only)
         tr = sum(traffic.get(k, {}).get("dram_bytes_per_unit", 0.0) * (2 if k == "fft_zpass" else 1) for k in ("fft_plane", "fft_zpass"))
-        hpsi_fft = {"kernel": "hpsi_fft_pipeline (k_zpass_g2r + k_plane<VLOC> + k_zpass_r2g, 3 launches per batch)", "bound": "hbm",
-                    "achieved": surv / (fft_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": surv / (fft_ms * 1e-3) / 1e9 / hbm_peak, "frac_of_8TBps": surv / (fft_ms * 1e-3) / 8e12,
-                    "traffic": tr * nop / max(1, prof_tot["fft_plane"]["regions"]) if tr else None,
-                    "algorithmic_bytes_per_vector": 192.0 * nnr + 32.0 * npw, "us_per_vector": 1e3 * fft_ms / nop,
-                    "peak_source": hbm_src, "share_of_step": fft_ms / prof_dev_ms,
-                    "note": "algorithmic bytes = SURVEY 8d figure for an UNFUSED 3-D FFT (six 1-D passes over the full box, "
-                            "72.4 MB/vector); the fused sphere-pruned pipeline moves ~5.8 MB/vector (traffic, ncu), so frac > 1 "
-                            "means the unfused roofline was beaten by fusion -- the parity tests are the proof of work. "
-                            "Per-kernel fractions against each kernel's own algorithmic bytes are in `kernels`."}
-    # dominant class of the step: the H.psi FFT pipeline, the projector GEMM pair, or a single kernel
-    cand = {"hpsi_fft": fft_ms, "gemm": gemm_ms}
-    for k in ("shift_fused",):
-        cand[k] = prof_tot.get(k, {"ms": 0})["ms"]
-    dom = max(cand, key=cand.get)
-    if dom == "hpsi_fft":
-        roofline = {k: hpsi_fft[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "peak_source", "share_of_step", "note")}
-    else:
-        top = "gemm_project" if dom == "gemm" else dom
-        roofline = {"kernel": top, **{k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
-                    "peak_source": hbm_src if kernels[top]["bound"] == "hbm" else
-                    "cuBLAS ZGEMM 4096^3 via torch.matmul(complex128), measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
-                    "share_of_step": kernels[top]["ms_per_step"] / (prof_dev_ms / args.steps)}
+        hpsi_fft = {"kernel": "hpsi_fft_pipeline (k_zpass_g2r + k_plane_vloc + k_zpass_r2g, 3 launches per batch)", "bound": "hbm",
+                    "us_per_vector": 1e3 * fft_ms / nop, "share_of_step": fft_ms / prof_dev_ms,
+                    "achieved": own / (fft_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": own / (fft_ms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": hbm_src, "algorithmic_bytes_per_vector": own / nop,
+                    "measured_dram_bytes_per_vector": tr or None,
+                    "frac_on_measured_dram_bytes": (tr * nop / (fft_ms * 1e-3) / 1e9 / hbm_peak) if tr else None,
+                    "unfused_3d_fft": {"bytes_per_vector": 192.0 * nnr + 32.0 * npw, "us_per_vector_at_hbm_peak": (192.0 * nnr + 32.0 * npw) / hbm_peak / 1e3,
+                                       "note": "SURVEY 8d figure for an UNFUSED 3-D FFT (six 1-D passes over the full box); quoted as a "
+                                               "time, not as a fraction: the fused sphere-pruned pipeline does not move those bytes"},
+                    "note": "the pipeline is bound by shared memory / FP64 in k_plane_vloc, not by HBM: see kernels.fft_plane"}
+    # `roofline` = the single kernel class with the largest share of the profiled step
+    top = max((k for k in kernels if "frac" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"kernel": {"fft_plane": "k_plane_vloc (persistent 2-D FFT x v(r) x 2-D FFT per z-plane)", "gemm_project": "k_zgemm<1,1> (coef = P^H psi)",
+                           "gemm_expand": "k_zgemm<0,0> (out = P coef)", "fft_zpass": "k_zpass_g2r / k_zpass_r2g", "shift_gemm": "k_shift_gemm",
+                           "seed_blas1": "seed BLAS-1 kernels", "shift_fused": "k_shift_apply"}.get(top, top), "class": top,
+                **{k: kernels[top][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "peak_source")},
+                "share_of_step": kernels[top]["ms_per_step"] / (prof_dev_ms / args.steps),
+                "algorithmic_per_launch": kernels[top]["algorithmic_per_launch"], "avg_launch_ms": kernels[top]["avg_launch_ms"]}
+    if "dmma_pipe" in kernels[top]:
+        roofline["dmma_pipe"] = kernels[top]["dmma_pipe"]
+    if top == "fft_plane":
+        roofline["note"] = ("HBM fraction of the kernel's own algorithmic bytes (it reads and writes only the sphere columns of every z-plane); "
+                            "the kernel is bound by shared-memory bandwidth and the FP64 pipe (ncu: *_ncu fields in kernels.fft_plane), "
+                            "its DRAM traffic is 2.3 MB per vector")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(syn, P, world),
-            "wall_ms_per_step": wall_ms / args.steps, "time_to_W_block_ms": dev_ms / args.steps,
+            "wall_ms_per_step": wall_ms / args.steps,
             "solves_per_step": solves_per_step * world, "linear_op_per_step": nop / args.steps,
             "coul_solver_ms_per_step": solver_ms / args.steps,
+            "collective_ms_per_step": coll_ms / args.steps,
+            "rank_step_ms": {"min": step_min, "max": step_max, "note": "mean device time of sgw_coulomb per step, slowest and fastest rank"},
             "profiled_ms_per_step": prof_dev_ms / args.steps,
             "profiled_note": "`kernels`/`roofline` come from a second pass over the same steps with CUDA events around every launch "
                              "of the library's stream; the timed pass runs without them",
@@ -503,8 +622,22 @@ def main():
                     "d2h_bytes_per_step": int(ngc * NFS * P * 16 + 4), "ms_per_step": e2e_ms / args.steps,
                     "note": "host (pageable, caller-owned) arrays -> sgw_set_* + sgw_coulomb -> scrcoul on host, wall clock"},
             "roofline": roofline, "kernels": kernels, "hpsi_fft": hpsi_fft, "fp64_zgemm_peak_tflops": f64_peak,
+            "time_to_W": ttw,
             "rho_grid": {"reduced": bool(ctx.rho_grid()[0]), "dims": list(ctx.rho_grid()[1]),
                          "note": "Delta-rho accumulated on the alias-free reduced box (sgw_get_rho_grid, DESIGN.md section 4)"}}
+    if world == 1:
+        try:
+            ctx.release_workspace()
+            line["invert_epsilon_full"] = invert_epsilon_full(ctx)
+            ctx.release_workspace()
+        except Exception as e:
+            line["invert_epsilon_full"] = {"error": repr(e)}
+        if not args.no_cpu_baseline:
+            try:
+                ctx.install_system(syn)
+                line["parity"] = parity_check(ctx, syn, cfg)
+            except Exception as e:
+                line["parity"] = {"ok": False, "error": repr(e)}
     if world == 1 and not args.no_sigma:
         del ctx
         ctx = None

@@ -66,6 +66,9 @@ int sgw_set_stream(sgw_ctx *ctx, void *cuda_stream);
 const char *sgw_last_error(const sgw_ctx *ctx);
 int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out);        /* stats of the last solver-level call */
 int sgw_set_profiling(sgw_ctx *ctx, int on);                  /* time H.psi separately (adds syncs) */
+/* return the solver workspace and the parked table buffers to the driver (the library keeps its scratch buffers between
+ * calls and sizes its batches from the free memory; a host that needs device memory for something else calls this) */
+int sgw_release_workspace(sgw_ctx *ctx);
 int sgw_device_synchronize(sgw_ctx *ctx);
 /* The reference writes solver warnings to stdout ("WARNING: BiCGstab algorithm did not converge in N iterations."
  * bicgstab.f90:250, "First choice of solver did not converge, try a different one" select_solver.f90:126, "WARNING:

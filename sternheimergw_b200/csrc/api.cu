@@ -2,6 +2,8 @@
 // the batched select_solver replacement.  Host arrays in, host arrays out; all device memory is owned here.
 #include "internal.cuh"
 
+#include <mutex>
+
 #include <string.h>
 
 #include <algorithm>
@@ -16,14 +18,22 @@ struct DevPool {
   std::multimap<std::pair<int, size_t>, void *> parked;   // (device, bytes) -> block
   std::map<void *, std::pair<int, size_t>> live;
   int contexts = 0;
+  std::mutex mu;                                           // contexts of several host threads share the pool
 };
 DevPool &pool() { static DevPool p; return p; }
+void pool_trim_locked(DevPool &dp) {
+  for (auto &kv : dp.parked) cudaFree(kv.second);
+  dp.parked.clear();
+}
 }  // namespace
 
+// A parked block is handed out again without a stream dependency: callers free table buffers only after synchronising their
+// stream (upload() and the sgw_set_* entry points do), so no queued work can still touch a parked block.
 cudaError_t dev_malloc(void **p, size_t bytes) {
   int dev = 0;
   cudaGetDevice(&dev);
   DevPool &dp = pool();
+  std::lock_guard<std::mutex> lock(dp.mu);
   auto it = dp.parked.find({dev, bytes});
   if (it != dp.parked.end()) {
     *p = it->second;
@@ -32,7 +42,7 @@ cudaError_t dev_malloc(void **p, size_t bytes) {
     const cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) {          // give parked memory back and retry once
       cudaGetLastError();
-      dev_pool_trim();
+      pool_trim_locked(dp);
       const cudaError_t e2 = cudaMalloc(p, bytes);
       if (e2 != cudaSuccess) return e2;
     }
@@ -44,6 +54,7 @@ cudaError_t dev_malloc(void **p, size_t bytes) {
 void dev_free(void *p) {
   if (!p) return;
   DevPool &dp = pool();
+  std::lock_guard<std::mutex> lock(dp.mu);
   auto it = dp.live.find(p);
   if (it == dp.live.end()) { cudaFree(p); return; }
   dp.parked.insert({it->second, p});
@@ -52,8 +63,8 @@ void dev_free(void *p) {
 
 void dev_pool_trim() {
   DevPool &dp = pool();
-  for (auto &kv : dp.parked) cudaFree(kv.second);
-  dp.parked.clear();
+  std::lock_guard<std::mutex> lock(dp.mu);
+  pool_trim_locked(dp);
 }
 
 int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out) {
@@ -74,6 +85,11 @@ int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out) {
   if (e != cudaSuccess) {
     cudaGetLastError();
     want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {          // give the parked table buffers back to the driver and try once more
+    cudaGetLastError();
+    dev_pool_trim();
     e = cudaMalloc(&p, want);
   }
   if (e != cudaSuccess) {
@@ -182,7 +198,7 @@ int sgw_create(int device, sgw_ctx **out) {
   ctx->own_stream = ctx->stream;
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
-  pool().contexts++;
+  { std::lock_guard<std::mutex> lock(pool().mu); pool().contexts++; }
   *out = ctx;
   return SGW_OK;
 }
@@ -213,7 +229,13 @@ int sgw_destroy(sgw_ctx *ctx) {
   if (ctx->corr.d_ET) dev_free(ctx->corr.d_ET);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
-  if (--pool().contexts <= 0) { pool().contexts = 0; dev_pool_trim(); }
+  bool last = false;
+  {
+    std::lock_guard<std::mutex> lock(pool().mu);
+    last = --pool().contexts <= 0;
+    if (last) pool().contexts = 0;
+  }
+  if (last) dev_pool_trim();
   return SGW_OK;
 }
 
@@ -228,6 +250,15 @@ int sgw_get_stats(const sgw_ctx *ctx, sgw_stats *out) {
 int sgw_set_profiling(sgw_ctx *ctx, int on) {
   if (!ctx) return SGW_E_ARG;
   ctx->profiling = on != 0;
+  return SGW_OK;
+}
+
+int sgw_release_workspace(sgw_ctx *ctx) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  ws_free_all(ctx);
+  dev_pool_trim();
   return SGW_OK;
 }
 

@@ -19,7 +19,7 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
-def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None):
+def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None, all_ranks: bool = False):
     """mp_gatherv(inter_image_comm, root, num_task, scrcoul_loc, scrcoul_root) (do_stern.f90:211, parallel.f90:1130).
 
     scr_loc: (ngc, nfs, ntask_loc) complex128 of this rank; num_task: tasks of every rank.  Returns the
@@ -44,7 +44,7 @@ def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None):
     mine = torch.from_numpy(buf).to(dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
-    if rank != root:
+    if rank != root and not all_ranks:
         return None
     out = np.zeros((ngc, nfs, int(sum(num_task))), dtype=np.complex128, order="F")
     off = 0
@@ -57,8 +57,38 @@ def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None):
     return out
 
 
+def gather_frequencies(w_loc: np.ndarray, num_freq, root: int = 0, device=None):
+    """Gather of the frequency slices (ngc, ngc, nfs_loc) every rank inverted into (ngc, ngc, sum(num_freq)) on ``root``."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return w_loc
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ngc = w_loc.shape[0]
+    nmax = max(num_freq)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+    buf = np.zeros((nmax, ngc, ngc, 2), dtype=np.float64)
+    if w_loc.shape[2]:
+        buf[:w_loc.shape[2]] = np.ascontiguousarray(np.transpose(w_loc, (2, 1, 0))).view(np.float64).reshape(w_loc.shape[2], ngc, ngc, 2)
+    mine = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == root else None
+    dist.gather(mine, parts, dst=root)
+    if rank != root:
+        return None
+    out = np.zeros((ngc, ngc, int(sum(num_freq))), dtype=np.complex128, order="F")
+    off = 0
+    for r in range(world):
+        n = num_freq[r]
+        if n:
+            blk = parts[r][:n].cpu().numpy()
+            out[:, :, off:off + n] = np.transpose(blk[..., 0] + 1j * blk[..., 1], (2, 1, 0))
+        off += n
+    return out
+
+
 def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, invert_fn=None, eps_head=None,
-               lgamma=False, root: int = 0):
+               lgamma=False, root: int = 0, shard_invert: bool = False, timings: dict | None = None):
     """One q-point of do_stern: split -> coulomb on the local block -> gather -> (root) unfold, head, invert.
 
     coulomb_fn(config, igstart, num_g_corr, num_task, ig_unique, fiu) -> (ngc, nfs, num_task) is normally
@@ -75,7 +105,33 @@ def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, i
         scr_loc = coulomb_fn(config, first, num_g_corr, ntask_loc, ig_unique, fiu)   # :209
     else:
         scr_loc = np.zeros((num_g_corr, len(fiu), 0), dtype=np.complex128, order="F")
+    import time
+    t0 = time.perf_counter()
+    if shard_invert and world > 1 and unfold_fn is not None:
+        # The reference unfolds and inverts all frequencies on the root image (do_stern.f90:220-232) -- a serial tail of
+        # O(ngc^3 nfs) that holds strong scaling back.  The frequencies are independent, so every rank takes a contiguous
+        # share of them (parallel_task's rule again), unfolds and inverts its slices on its own GPU and the root gathers.
+        scr_all = gather_columns(scr_loc, num_task, root=root, all_ranks=True)
+        t1 = time.perf_counter()
+        f_first, f_last, num_freq = parallel_task(world, rank, len(fiu))
+        sl = slice(f_first - 1, f_first - 1 + num_freq[rank])
+        if num_freq[rank] > 0:
+            w_loc = unfold_fn(num_g_corr, ig_unique, np.asfortranarray(scr_all[:, sl, :]))
+            if eps_head is not None:
+                w_loc[0, 0, :] = np.asarray(eps_head)[sl]
+            if invert_fn is not None:
+                w_loc = invert_fn(w_loc, lgamma=lgamma)
+        else:
+            w_loc = np.zeros((num_g_corr, num_g_corr, 0), dtype=np.complex128, order="F")
+        t2 = time.perf_counter()
+        out = gather_frequencies(w_loc, num_freq, root=root)
+        if timings is not None:
+            timings.update(gather_s=t1 - t0, unfold_invert_s=t2 - t1, gather_w_s=time.perf_counter() - t2)
+        return out, (first, last, num_task)
     scr_root = gather_columns(scr_loc, num_task, root=root)                        # :211
+    t1 = time.perf_counter()
+    if timings is not None:
+        timings.update(gather_s=t1 - t0)
     if rank != root or unfold_fn is None:
         return (scr_root if rank == root else None), (first, last, num_task)
     scr_g = unfold_fn(num_g_corr, ig_unique, scr_root)                             # :220 (identity symmetry)
@@ -83,6 +139,8 @@ def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, i
         scr_g[0, 0, :] = eps_head                                                  # :224
     if invert_fn is not None:
         scr_g = invert_fn(scr_g, lgamma=lgamma)                                    # :232
+    if timings is not None:
+        timings.update(unfold_invert_s=time.perf_counter() - t1)
     return scr_g, (first, last, num_task)
 
 

@@ -472,6 +472,10 @@ class Context:
             raise SgwError(f"the linear solver for G did not converge (ierr={ierr.value})")   # green.f90:208
         return sigma
 
+    def release_workspace(self):
+        """sgw_release_workspace: give the solver scratch memory back to the driver."""
+        self._chk(self._L.sgw_release_workspace(self._h), "release_workspace")
+
     def bench_linear_op(self, slot, nvec, reps=10):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._chk(self._L.sgw_bench_linear_op(self._h, slot, nvec, reps, C.byref(a), C.byref(b), C.byref(c)), "bench_linear_op")

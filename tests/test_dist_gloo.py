@@ -136,3 +136,52 @@ def test_sigma_configurations_dealt_and_summed(world, ncon, expect):
             assert sig is not None and np.array_equal(sig, serial)
         else:
             assert sig is None
+
+
+def _invert_fake(scr, lgamma=False):
+    out = np.zeros_like(scr)
+    for iw in range(scr.shape[2]):
+        out[:, :, iw] = np.linalg.inv(scr[:, :, iw] + 5000.0 * np.eye(scr.shape[0])) - np.eye(scr.shape[0])
+    return np.asfortranarray(out)
+
+
+def _worker_shard(rank, world, port, ngmunique, ngc, nfs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sternheimergw_b200.dist import do_stern_q
+        ig_unique = np.arange(1, ngmunique + 1, dtype=np.int32)
+        fiu = 0.5j * np.arange(nfs)
+        tm = {}
+        w, _ = do_stern_q(_fake_coulomb, None, ngc, ig_unique, fiu, unfold_fn=_unfold_identity, invert_fn=_invert_fake,
+                          shard_invert=True, timings=tm)
+        q.put((rank, None if w is None else w.copy(), sorted(tm)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nfs", [(2, 3), (3, 2), (3, 5)])
+def test_do_stern_frequency_sharded_unfold_and_invert(world, nfs):
+    """shard_invert: every rank unfolds + inverts a contiguous share of the frequencies (parallel_task's rule, ranks with
+    zero frequencies included) and the root gathers; the result equals the root-only path of do_stern.f90:220-232."""
+    ngmunique = ngc = 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shard, args=(r, world, port, ngmunique, ngc, nfs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ig_unique = np.arange(1, ngmunique + 1, dtype=np.int32)
+    fiu = 0.5j * np.arange(nfs)
+    serial = _invert_fake(_unfold_identity(ngc, ig_unique, _fake_coulomb(None, 1, ngc, ngmunique, ig_unique, fiu)))
+    assert res[0][1] is not None and np.allclose(res[0][1], serial, rtol=0, atol=1e-14)
+    assert all(res[r][1] is None for r in range(1, world))
+    assert res[0][2] == ["gather_s", "gather_w_s", "unfold_invert_s"]
