@@ -76,6 +76,11 @@ struct BicgState {
   int *flushed;            // [nrhs] XB (= XO) and U0B (= US0) hold a materialised state
   int *last_stage;         // [nrhs] stage of the last outer iteration the RHS took part in
   int *base_b;             // [nrhs] outer iteration of the last flush of THIS right-hand side (only active ones are flushed)
+  // ---- +-omega average inside the solver (AvgSpec): y = pair averages of x^sigma, nothing else is materialised
+  int avg;                 // 1: on
+  int a_nfreq, a_zero, a_group;
+  cplx *Y, *CA;            // output (AvgSpec layout) ; combined coefficients [nrhs][kcap][a_nfreq]
+  int *ierr;               // [nrhs] for the NaN check of the materialised vectors (bicgstab.f90:264-267)
 };
 
 __device__ __forceinline__ cplx *seedU(const BicgState &s, int b, int i) { return s.U + ((long)b * (s.L + 1) + i) * s.n; }
@@ -657,19 +662,46 @@ constexpr size_t LG_SMEM = 2 * (size_t)(LG_BK * LG_PM + LG_BN * LG_PK) * sizeof(
 // times all column tiles of its right-hand side in ONE continuous cp.async pipeline: the first chunk of the next tile is in flight
 // while the last chunk of the current one is multiplied, and the fill / drain of the pipeline is paid once per CTA, not per tile.
 constexpr int LG_TM = 8;
+__device__ __forceinline__ cplx *avg_col(const BicgState &s, int b, int f) {
+  return s.Y + (((long)(b / s.a_group) * s.a_nfreq + f) * s.a_group + b % s.a_group) * s.n;
+}
+// coefficient columns of the pair averages: CA[b][k][f] = 1/2 CX[k][f - 1] + 1/2 CX[k][nfreq + f - first - 1]  (global shift g <-> is = g - 1;
+// the seed system g = 0 has no coefficients: its x is added in the epilogue of the final materialisation)
+__global__ void k_lazy_combine(BicgState s, int what) {
+  const int b = blockIdx.y;
+  const int itb = s.iters[b], baseb = s.base_b[b];
+  if (itb <= baseb || (what != 0 && !s.active[b])) return;
+  const int K = s.nv * (itb - baseb - 1) + (s.last_stage[b] == 2 ? s.nv : s.nsnap);
+  const int nf = s.a_nfreq, first = s.a_zero ? 1 : 0;
+  const cplx *cx = s.CX + (long)b * s.ns * s.kcap;
+  cplx *ca = s.CA + (long)b * nf * s.kcap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * nf; i += gridDim.x * blockDim.x) {
+    const int k = i / nf, f = i - k * nf;
+    cplx v = cmake(0.0, 0.0);
+    if (f >= first) {
+      const int g2 = nf + f - first;
+      const cplx w = cx[(long)k * s.ns + g2 - 1];
+      v = cmake(0.5 * w.x, 0.5 * w.y);
+      if (f >= 1) { const cplx u = cx[(long)k * s.ns + f - 1]; v = cmake(v.x + 0.5 * u.x, v.y + 0.5 * u.y); }
+    }
+    ca[(long)k * nf + f] = v;
+  }
+}
 __global__ void __launch_bounds__(LG_T, 3) k_shift_gemm(BicgState s, int what) {
   const int b = blockIdx.y;
   const int itb = s.iters[b], baseb = s.base_b[b];
   if (itb <= baseb || (what != 0 && !s.active[b])) return;
   const int K = s.nv * (itb - baseb - 1) + (s.last_stage[b] == 2 ? s.nv : s.nsnap);
-  const int M = s.n, N = s.ns;
+  const bool avg = s.avg && what != 1;
+  const int M = s.n, N = avg ? s.a_nfreq : s.ns;
   const int ntn = (N + LG_BN - 1) / LG_BN, ntm_all = (M + LG_BM - 1) / LG_BM;
   const int mt0 = blockIdx.x * LG_TM, ntm = min(LG_TM, ntm_all - mt0);
   const int nk = (K + LG_BK - 1) / LG_BK;
   const int ntile = ntm * ntn, nstep = ntile * nk;
   const cplx *A = s.BAS + (long)b * s.Tc * s.nv * s.n;                       // M x K, column k at A + k n
-  const cplx *B = (what != 1 ? s.CX : s.CU) + (long)b * s.ns * s.kcap;       // K x N stored [k][is]
-  const long lda = s.n, ldb = s.ns;
+  const cplx *B = avg ? s.CA + (long)b * s.a_nfreq * s.kcap                  // K x nfreq stored [k][f]
+                      : (what != 1 ? s.CX : s.CU) + (long)b * s.ns * s.kcap; // K x N stored [k][is]
+  const long lda = s.n, ldb = N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   extern __shared__ cplx lgsm[];
   constexpr int ASZ = LG_BK * LG_PM, BSZ = LG_BN * LG_PK;
@@ -750,12 +782,33 @@ __global__ void __launch_bounds__(LG_T, 3) k_shift_gemm(BicgState s, int what) {
             const int col = n0 + wn + j * 8 + 2 * t + c;
             if (row < M && col < N) {
               cplx acc = cmake(p1[i][j][c] - p2[i][j][c], (p3[i][j][c] - p1[i][j][c]) - p2[i][j][c]);
-              const long off = (long)row + (long)col * s.n;
-              if (fl) {
-                if (what != 1) acc = cadd(cfma(s.cxb[(long)b * s.ns + col], U0B[off], acc), C[off]);
-                else acc = cfma(s.cub[(long)b * s.ns + col], C[off], acc);
+              if (avg) {
+                // column = frequency f: pair (global shifts f and g2), see AvgSpec
+                const int first = s.a_zero ? 1 : 0;
+                cplx *yc = avg_col(s, b, col) + row;
+                if (fl) {
+                  if (col >= first) {
+                    const int g2 = s.a_nfreq + col - first;
+                    cplx t = cmul(s.cxb[(long)b * s.ns + g2 - 1], U0B[(long)row + (long)(g2 - 1) * s.n]);
+                    if (col >= 1) t = cadd(t, cmul(s.cxb[(long)b * s.ns + col - 1], U0B[(long)row + (long)(col - 1) * s.n]));
+                    acc = cmake(acc.x + 0.5 * t.x, acc.y + 0.5 * t.y);
+                  }
+                  acc = cadd(acc, *yc);
+                }
+                if (what == 0 && col == 0) {       // the seed system's x (global shift 0) enters once, at the end
+                  const cplx xs = seedX(s, b)[row];
+                  acc = first ? cadd(acc, xs) : cmake(acc.x + 0.5 * xs.x, acc.y + 0.5 * xs.y);
+                }
+                if (what == 0 && ((acc.x != acc.x) || (acc.y != acc.y))) atomicMax(&s.ierr[b], 2);   // bicgstab.f90:264-267
+                *yc = acc;
+              } else {
+                const long off = (long)row + (long)col * s.n;
+                if (fl) {
+                  if (what != 1) acc = cadd(cfma(s.cxb[(long)b * s.ns + col], U0B[off], acc), C[off]);
+                  else acc = cfma(s.cub[(long)b * s.ns + col], C[off], acc);
+                }
+                C[off] = acc;
               }
-              C[off] = acc;
             }
           }
     }
@@ -886,7 +939,7 @@ __global__ void __launch_bounds__(BT) k_nan_scan(BicgState s, int *__restrict__ 
   const int b = blockIdx.y;
   if (todo && !todo[b]) return;
   const int e = blockIdx.x * BT + threadIdx.x;
-  const int nshift = s.ns + 1;
+  const int nshift = s.avg ? 1 : s.ns + 1;      // average mode: the shifted solutions were checked when they were materialised
   bool bad = false;
   if (e < s.n) {
     for (int is = 0; is < nshift; ++is) {
@@ -895,6 +948,13 @@ __global__ void __launch_bounds__(BT) k_nan_scan(BicgState s, int *__restrict__ 
     }
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicMax(&ierr[b], 2);
+}
+
+__global__ void k_avg_done(BicgState s, const int *__restrict__ ierr, const int *__restrict__ todo, int *__restrict__ done) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.nrhs) return;
+  if (todo && !todo[b]) return;
+  done[b] = ierr[b] == 0 ? 1 : 0;
 }
 
 __global__ void k_set_ierr(BicgState s, int *__restrict__ ierr, const int *__restrict__ todo) {
@@ -969,6 +1029,11 @@ static int lazy_materialise(sgw_ctx *ctx, const BicgState &s, int flush_iter) {
   ProfScope prof(ctx, PC_SHIFT_GEMM);
   const int ntm = (s.n + LG_BM - 1) / LG_BM;
   dim3 grid((unsigned)((ntm + LG_TM - 1) / LG_TM), (unsigned)s.nrhs);
+  if (s.avg) {
+    dim3 gc((unsigned)std::max(1, std::min(16, (s.kcap * s.a_nfreq + 255) / 256)), (unsigned)s.nrhs);
+    k_lazy_combine<<<gc, 256, 0, ctx->stream>>>(s, flush_iter > 0 ? 2 : 0);
+    SGW_LAUNCH_CHECK();
+  }
   k_shift_gemm<<<grid, LG_T, LG_SMEM, ctx->stream>>>(s, flush_iter > 0 ? 2 : 0);
   SGW_LAUNCH_CHECK();
   if (flush_iter > 0) {
@@ -1010,6 +1075,10 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
   SGW_CHECK(ws(ctx, "bi_flushed", (size_t)nr, &s.flushed));
   SGW_CHECK(ws(ctx, "bi_lstage", (size_t)nr, &s.last_stage));
   SGW_CHECK(ws(ctx, "bi_baseb", (size_t)nr, &s.base_b));
+  s.avg = (s.lazy && sb.avg.d_y && sb.avg.nfreq > 0 && (2 * sb.avg.nfreq - (sb.avg.zero_freq ? 1 : 0)) == sb.nshift) ? 1 : 0;
+  s.a_nfreq = sb.avg.nfreq; s.a_zero = sb.avg.zero_freq; s.a_group = std::max(1, sb.avg.group);
+  s.Y = sb.avg.d_y; s.ierr = sb.d_ierr;
+  SGW_CHECK(ws(ctx, "bi_CA", s.avg ? (size_t)(nr * s.kcap * s.a_nfreq) : 1, &s.CA));
   SGW_CHECK(ws(ctx, "bi_seed", (size_t)nr, &s.seed));
   SGW_CHECK(ws(ctx, "bi_shift", (size_t)(nr * s.ns) + 1, &s.shift));
   SGW_CHECK(ws(ctx, "bi_step", (size_t)(nr * s.ns * lmax) + 1, &s.step));
@@ -1143,11 +1212,15 @@ int bicgstab_batched(sgw_ctx *ctx, const SolveBatch &sb, int lmax, double thresh
     }
   }
   if (rc != SGW_OK) return rc;
-  if (s.lazy) SGW_CHECK(lazy_materialise(ctx, s, 0));
   k_set_ierr<<<gb, 128, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();
+  if (s.lazy) SGW_CHECK(lazy_materialise(ctx, s, 0));      // average mode: NaN check of the shifted solutions in its epilogue
   k_nan_scan<<<gvec, BT, 0, st>>>(s, sb.d_ierr, d_todo);
   SGW_LAUNCH_CHECK();
+  if (s.avg && sb.avg.d_done) {
+    k_avg_done<<<gb, 128, 0, st>>>(s, sb.d_ierr, d_todo, sb.avg.d_done);
+    SGW_LAUNCH_CHECK();
+  }
   // statistics: every RHS did 2*L operator applications per outer iteration it took part in
   {
     std::vector<int> it(nr);

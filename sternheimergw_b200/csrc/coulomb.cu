@@ -278,6 +278,7 @@ static FreqList make_omega(int nfreq, const sgw_cplx *freq) {   // solve_linter.
 static size_t solver_bytes_per_rhs(const sgw_ctx *ctx, const KSlot &ks, int lmax, int nshift) {
   const size_t n = ks.npwx;
   size_t v = bicgstab_bytes_per_rhs((int)n, lmax, nshift) / sizeof(cplx) + (size_t)nshift * n + n;   // bicgstab state + sv_x + rhs
+  v += (size_t)((nshift + 1) / 2) * n;                                                    // +-omega averages (co_davg_all)
   v += 2 * (size_t)ctx->nr3 * ks.sph.ncol;                                                // H.psi column buffers
   v += 4 * (size_t)(ks.nkb + ks.nbnd);                                                    // projector coefficients
   return v * sizeof(cplx);
@@ -424,9 +425,16 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     }
     SGW_CHECK(ws(ctx, "sv_x", (size_t)n * nshift * nrhs, &d_x));
     SGW_CHECK(ws(ctx, "sv_ierr", (size_t)nrhs, &d_ierr));
+    // the +-omega average (:464-480) is formed by the solver: dpsi_avg[(p * nfreq + ifreq) * nocc + ib], the order the
+    // Delta-rho stage consumes
+    cplx *davg_all = nullptr;
+    int *d_done = nullptr;
+    SGW_CHECK(ws(ctx, "co_davg_all", (size_t)npf * nocc * n, &davg_all));
+    SGW_CHECK(ws(ctx, "co_done", (size_t)nrhs, &d_done));
     SolveBatch sb;
     sb.slot = kp.slot; sb.alpha_pv = ks.alpha_pv; sb.nrhs = nrhs; sb.nshift = nshift; sb.n = n;
     sb.d_b = dvpsi; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
+    sb.avg.d_y = davg_all; sb.avg.nfreq = nfreq; sb.avg.zero_freq = fl.zero_freq; sb.avg.group = nocc; sb.avg.d_done = d_done;
     cudaEventRecord(ctx->ev2, st);
     SGW_CHECK(select_solver_batched(ctx, sb, cfg));
     cudaEventRecord(ctx->ev3, st);
@@ -445,14 +453,11 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     size_t budget = (size_t)2 << 30;
     int pfc = (int)std::max<size_t>(1, std::min<size_t>(npf, budget / per_pf));
     pfc = std::min(pfc, std::max(1, 65535 / nocc));
-    cplx *davg = nullptr, *Td = nullptr;
-    SGW_CHECK(ws(ctx, "co_davg", (size_t)pfc * nocc * n, &davg));
+    cplx *Td = nullptr;
     SGW_CHECK(ws(ctx, "co_Td", (size_t)pfc * nocc * rnz * sq.ncol, &Td));
     for (int pf0 = 0; pf0 < npf; pf0 += pfc) {
       const int c = std::min(pfc, npf - pf0);
-      dim3 ga((n + 255) / 256, nocc, c);
-      k_average<<<ga, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, pf0, d_x, davg);
-      SGW_LAUNCH_CHECK();
+      const cplx *davg = davg_all + (size_t)pf0 * nocc * n;
       SGW_CHECK(fft_zpass_g2r(ctx, sq, c * nocc, davg, n, Td, nullptr, rg));
       SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Trho + (size_t)pf0 * rnz * rho.ncol, ik > 0, rg));
     }

@@ -312,7 +312,19 @@ int permute_in(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *src, long ld
 int permute_out(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *src, long lds, cplx *dst, long ldd);
 
 // ---- bicgstab.cu / subspace.cu / select.cu ----
+// Optional +-omega average of solve_linter.f90:464-480 done inside the solver: for right-hand side b and frequency f
+//   y(b, f) = x_f                                   (f = 0 when the list starts with the static frequency)
+//           = 1/2 x_f + 1/2 x_{nfreq + f - first}   otherwise (first = zero_freq)
+// written to d_y + (((b / group) * nfreq + f) * group + b % group) * n.  The multishift solver in lazy mode never forms the
+// individual x^sigma then: it combines the coefficient columns and materialises nfreq vectors instead of nshift - 1.
+struct AvgSpec {
+  cplx *d_y = nullptr;
+  int nfreq = 0, zero_freq = 0, group = 1;
+  int *d_done = nullptr;     // [nrhs] 1: y written by the solver; 0: the caller-side average from x still has to run
+};
+
 struct SolveBatch {
+  AvgSpec avg;
   int slot;
   double alpha_pv;
   int nrhs, nshift, n;       // n = vector length used (npwx of the slot or dense n)

@@ -321,8 +321,31 @@ __global__ void k_sel_update(int nrhs, const int *ierr, int *todo, int *nleft) {
   if (todo[b]) atomicAdd(nleft, 1);
 }
 
+// solve_linter.f90:464-480 for the right-hand sides whose average the solver did not form itself (AvgSpec.d_done == 0)
+__global__ void k_average_masked(int n, int nshift, AvgSpec a, const cplx *__restrict__ x) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y, f = blockIdx.z;
+  if (e >= n || a.d_done[b]) return;
+  const cplx *xr = x + (long)b * nshift * n;
+  cplx v = xr[(long)f * n + e];
+  const int first = a.zero_freq ? 1 : 0;
+  if (f >= first) {
+    const cplx w = xr[(long)(a.nfreq + f - first) * n + e];
+    v = cscale(0.5, v);                          // ZSCAL 0.5 then ZAXPY 0.5 (:469-478)
+    v = cmake(v.x + 0.5 * w.x, v.y + 0.5 * w.y);
+  }
+  a.d_y[(((long)(b / a.group) * a.nfreq + f) * a.group + b % a.group) * n + e] = v;
+}
+
 int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_cfg *cfg) {
   int *todo = nullptr, *nleft = nullptr;
+  if (sb.avg.d_y) {
+    if (!sb.avg.d_done || sb.avg.group < 1 || 2 * sb.avg.nfreq - (sb.avg.zero_freq ? 1 : 0) != sb.nshift) {
+      ctx->err = "select_solver: inconsistent average specification";
+      return SGW_E_ARG;
+    }
+    SGW_CUDA(cudaMemsetAsync(sb.avg.d_done, 0, sizeof(int) * sb.nrhs, ctx->stream));
+  }
   SGW_CHECK(ws(ctx, "sel_todo", (size_t)sb.nrhs, &todo));
   SGW_CHECK(ws(ctx, "sel_nleft", (size_t)1, &nleft));
   const int gb = (sb.nrhs + 127) / 128;
@@ -360,6 +383,18 @@ int select_solver_batched(sgw_ctx *ctx, const SolveBatch &sb, const sgw_solver_c
       if (is + 1 < cfg->npriority) ctx->msg_fn("First choice of solver did not converge, try a different one", ctx->msg_user);       // select_solver.f90:126
     }
     if (is + 1 < cfg->npriority) ctx->stats.n_fallback += h;
+  }
+  if (sb.avg.d_y) {
+    const int bstep = std::max(1, 65535 / sb.avg.group) * sb.avg.group;   // grid.y limit, group-aligned so that the layout formula holds per chunk
+    for (int b0 = 0; b0 < sb.nrhs; b0 += bstep) {
+      const int nb = std::min(bstep, sb.nrhs - b0);
+      AvgSpec a = sb.avg;
+      a.d_y = sb.avg.d_y + (long)(b0 / a.group) * a.nfreq * a.group * sb.n;
+      a.d_done = sb.avg.d_done + b0;
+      dim3 grid((unsigned)((sb.n + 255) / 256), (unsigned)nb, (unsigned)a.nfreq);
+      k_average_masked<<<grid, 256, 0, ctx->stream>>>(sb.n, sb.nshift, a, sb.d_x + (long)b0 * sb.nshift * sb.n);
+      SGW_LAUNCH_CHECK();
+    }
   }
   return SGW_OK;
 }
