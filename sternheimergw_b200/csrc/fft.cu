@@ -14,6 +14,7 @@
 // box sweeps of an unfused 3-D FFT (SURVEY.md section 8d counts 192*nnr + 32*N algorithmic bytes).
 #include "internal.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -647,6 +648,220 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 3)) k_pla
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent z passes (TMA)
+// The z transforms are pure HBM streams (2 x 16 B x nz x ncol + the vector per H.psi).  One CTA owns ONE block of ZB = 16
+// sphere columns (its index tables, twiddles and kinetic energies are loaded once) and walks over the vectors of the batch:
+//   g2r: the block's entries of vector v+1 -- one contiguous range of the column-ordered vector -- are fetched by a 1-D bulk
+//        copy (cp.async.bulk + mbarrier) while vector v is transformed; the first stage gathers its inputs from that staged
+//        range through an index table (no zero fill, no scatter pass); the finished [nz][16] tile leaves through ONE 3-D
+//        tensor-map store (cp.async.bulk.tensor, SASS UTMASTG) that overlaps the next vector's work (two tile buffers,
+//        cp.async.bulk.wait_group.read before a buffer is reused);
+//   r2g: the [nz][16] tile of vector v+1 is fetched by a tensor-map load (UTMALDG) into the other buffer while vector v is
+//        transformed; psi / the non-local part of the epilogue are prefetched into registers before the wait.
+// Tile layout [z][c]: element stride 16, line stride 1 -- the lanes of a quarter-warp work on 8 consecutive columns, i.e. on 8
+// distinct 16-byte bank groups, and the tile is exactly the dense box the tensor map describes.
+constexpr int ZB = 16;
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const void *tmap, const void *smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(tmap), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, int c0, int c1, int c2, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+
+struct ZTArgs {
+  const cplx *twz;
+  const int *col_ptr;
+  const short *ztab;        // [(c * RZ2 + j2) * RZ1P + k] -> offset of (column c, z = j2 + RZ2 k) from the column's first entry, or -1
+  const cplx *vec;          // g2r: input vectors ; r2g: psi of the epilogue
+  cplx *out;                // r2g: output vectors
+  long ld;
+  const int *active;
+  int ncol, nvec, nz, maxlen;   // maxlen: largest number of entries of a column block, rounded up to a multiple of 8
+  // r2g epilogue (ZEpilogue)
+  int mode, keep_out;
+  const double *g2kin;
+  const cplx *sigma;
+  long sigma_stride;
+  double scale;
+};
+
+template <int RZ1, int RZ2, int NT>
+__global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__ CUtensorMap tmap, ZTArgs a) {
+  constexpr int NZ = RZ1 * RZ2, RZ1P = (RZ1 + 7) & ~7, TILE = NZ * ZB;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * ZB, nc = min(ZB, a.ncol - c0);
+  extern __shared__ __align__(128) unsigned char zsm[];
+  cplx *tile = (cplx *)zsm;                       // [NZ][ZB]
+  cplx *in = tile + TILE;                         // [maxlen] staged entries of the block
+  cplx *tw = in + a.maxlen;
+  short *ztab = (short *)(tw + NZ);               // [ZB][RZ2][RZ1P], rebased to the block's first entry
+  unsigned long long *bar = (unsigned long long *)(ztab + ZB * RZ2 * RZ1P);
+  const int p0 = a.col_ptr[c0], p1 = a.col_ptr[c0 + nc];
+  const unsigned bytes = (unsigned)(p1 - p0) * (unsigned)sizeof(cplx);
+  for (int i = tid; i < NZ; i += NT) tw[i] = a.twz[i];
+  for (int i = tid; i < ZB * RZ2 * RZ1P; i += NT) {
+    const int c = i / (RZ2 * RZ1P);
+    short v = -1;
+    if (c < nc) {
+      v = a.ztab[(long)(c0 + c) * (RZ2 * RZ1P) + (i - c * (RZ2 * RZ1P))];
+      if (v >= 0) v = (short)(v + a.col_ptr[c0 + c] - p0);
+    }
+    ztab[i] = v;
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  auto next_active = [&](int v) {
+    while (v < a.nvec && a.active && !a.active[v]) v += gridDim.y;
+    return v;
+  };
+  int v = next_active(blockIdx.y);
+  if (tid == 0 && v < a.nvec && bytes) {
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(in, a.vec + (long)v * a.ld + p0, bytes, bar);
+  }
+  unsigned parity = 0u;
+  const cplx zero = cmake(0.0, 0.0);
+  while (v < a.nvec) {
+    const int vn = next_active(v + gridDim.y);
+    if (tid == 0) bulk_wait_read<0>();            // the previous vector's store has finished reading the tile
+    __syncthreads();
+    if (bytes) { mbar_wait(bar, parity); parity ^= 1u; }
+    {  // inverse z, stage 1 (strided DFT_RZ1 + twiddle): inputs gathered from the staged range; all ZB columns are written
+      constexpr int ntask = ZB * RZ2;
+      for (int task = tid; task < ntask; task += NT) {
+        const int c = task % ZB, j2 = task / ZB;
+        short tb[RZ1P];
+#pragma unroll
+        for (int q = 0; q < RZ1P / 8; ++q) *(uint4 *)(tb + 8 * q) = *(const uint4 *)(ztab + (c * RZ2 + j2) * RZ1P + 8 * q);
+        double re[RZ1], im[RZ1];
+#pragma unroll
+        for (int k = 0; k < RZ1; ++k) {
+          const int idx = tb[k];
+          const cplx x = idx >= 0 ? in[idx] : zero;
+          re[k] = x.x; im[k] = x.y;
+        }
+        dft_fwd<RZ1>(im, re);
+#pragma unroll
+        for (int k = 1; k < RZ1; ++k) {
+          const cplx w = tw[j2 * k];
+          const double cs = w.x, sn = -w.y;
+          const double p = re[k], q = im[k];
+          re[k] = p * cs - q * sn;
+          im[k] = p * sn + q * cs;
+        }
+        cplx *base = tile + j2 * ZB + c;
+#pragma unroll
+        for (int k = 0; k < RZ1; ++k) base[k * (RZ2 * ZB)] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && vn < a.nvec && bytes) {       // the staging buffer is free: fetch the next vector's entries
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(in, a.vec + (long)vn * a.ld + p0, bytes, bar);
+    }
+    stage_contig<RZ2, +1>(tile, ZB, nullptr, 1, ZB, RZ1, tw, false, tid, NT);
+    fence_proxy_async();                          // generic-proxy writes of the tile -> visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&tmap, tile, 2 * c0, 0, v);
+      bulk_commit();
+    }
+    v = vn;
+  }
+  if (tid == 0) bulk_wait_read<0>();              // shared memory must stay alive until the last store has read it
+}
+
+template <int RZ1, int RZ2, int NT, int EPT>
+__global__ void __launch_bounds__(NT, 6) k_zpass_r2g_tma(const __grid_constant__ CUtensorMap tmap, ZTArgs a) {
+  constexpr int NZ = RZ1 * RZ2, TILE = NZ * ZB;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * ZB, nc = min(ZB, a.ncol - c0);
+  extern __shared__ __align__(128) unsigned char zsm[];
+  cplx *tile = (cplx *)zsm;                       // [NZ][ZB]
+  cplx *tw = tile + TILE;
+  double *g2 = (double *)(tw + NZ);               // [maxlen] kinetic energies of the block's entries
+  short *pos = (short *)(g2 + a.maxlen);          // [maxlen] z * ZB + c of every entry
+  unsigned long long *bar = (unsigned long long *)(pos + a.maxlen);
+  const int p0 = a.col_ptr[c0], p1 = a.col_ptr[c0 + nc], len = p1 - p0;
+  for (int i = tid; i < NZ; i += NT) tw[i] = a.twz[i];
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  // entry -> tile position, from the gather table of the forward pass (same table: offset of (c, z) inside column c)
+  for (int i = tid; i < nc * NZ; i += NT) {
+    const int c = i / NZ, z = i - c * NZ;
+    const int j2 = z % RZ2, k = z / RZ2;
+    const short off = a.ztab[((long)(c0 + c) * RZ2 + j2) * ((RZ1 + 7) & ~7) + k];
+    if (off >= 0) pos[off + a.col_ptr[c0 + c] - p0] = (short)(z * ZB + c);
+  }
+  if (a.mode == 1)
+    for (int i = tid; i < len; i += NT) g2[i] = a.g2kin[p0 + i];
+  __syncthreads();
+  auto next_active = [&](int v) {
+    while (v < a.nvec && a.active && !a.active[v]) v += gridDim.y;
+    return v;
+  };
+  constexpr unsigned tile_bytes = TILE * sizeof(cplx);
+  int v = next_active(blockIdx.y);
+  if (tid == 0 && v < a.nvec) {
+    mbar_expect_tx(bar, tile_bytes);
+    tma_load_3d(tile, &tmap, 2 * c0, 0, v, bar);
+  }
+  unsigned parity = 0u;
+  while (v < a.nvec) {
+    const int vn = next_active(v + gridDim.y);
+    cplx sg = cmake(0.0, 0.0);
+    cplx *dst = a.out + (long)v * a.ld + p0;
+    const cplx *psi = a.vec + (long)v * a.ld + p0;
+    if (a.mode == 1 && a.sigma) sg = a.sigma[(long)v * a.sigma_stride];
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    stage_contig<RZ2, -1>(tile, ZB, nullptr, 1, ZB, RZ1, tw, true, tid, NT);
+    __syncthreads();
+    stage_strided<RZ1, -1>(tile, ZB, nullptr, 1, ZB, RZ2, tw, false, tid, NT);
+    __syncthreads();
+    cplx res[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      const int i = tid + q * NT;
+      if (i < len) res[q] = tile[pos[i]];
+    }
+    __syncthreads();                              // the tile has been read: fetch the next vector's tile while the epilogue runs
+    if (tid == 0 && vn < a.nvec) {
+      mbar_expect_tx(bar, tile_bytes);
+      tma_load_3d(tile, &tmap, 2 * c0, 0, vn, bar);
+    }
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      const int i = tid + q * NT;
+      if (i < len) {
+        cplx val = cscale(a.scale, res[q]);
+        if (a.mode == 0) {
+          dst[i] = val;
+        } else if (a.mode == 1) {
+          // (H + sigma) psi = g2kin psi + V_loc psi + [non-local, already in out] + sigma psi   (order of k_zpass_r2g)
+          const cplx ps = psi[i];
+          const cplx nl = a.keep_out ? dst[i] : cmake(0.0, 0.0);
+          val = cadd(cscale(g2[i], ps), val);
+          val = cadd(val, nl);
+          dst[i] = cfma(sg, ps, val);
+        } else {
+          dst[i] = cadd(dst[i], val);
+        }
+      }
+    }
+    v = vn;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr) {
   GridDev g;
@@ -706,6 +921,99 @@ static int set_smem(sgw_ctx *ctx, K kernel, size_t bytes) {
   return SGW_OK;
 }
 
+
+// ---- host side of the TMA z passes
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_tiled_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// T[vec][pz][col] (complex FP64) as a rank-3 tensor of doubles {2 ncol, nz, nvec}; box = {2 ZB, nz, 1}: the [nz][ZB] tile of one vector
+static bool make_tmap_T(CUtensorMap *tm, const cplx *T, int ncol, int nz, int nvec) {
+  PFN_encodeTiled enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)2 * ncol, (cuuint64_t)nz, (cuuint64_t)nvec};
+  const cuuint64_t strides[2] = {(cuuint64_t)ncol * 16, (cuuint64_t)ncol * 16 * nz};
+  const cuuint32_t box[3] = {2 * ZB, (cuuint32_t)nz, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)T, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// SGW_ZPASS: 0 = generic kernels, 1 = persistent TMA kernels for both passes, 2 = TMA for G -> r only (default), 3 = r -> G only.
+// Measured at Si64, 1024 vectors per launch (us per launch, G -> r / r -> G): generic 475 / 510, TMA 447 / 610 -- the tensor-map
+// LOAD of [nz][16] boxes (256-byte rows, 16 KB apart) is slower than the per-thread loads of the generic kernel, the bulk-copy
+// staged input + tensor-map STORE of the forward pass is faster.
+static int zpass_variant() {
+  const char *e = getenv("SGW_ZPASS");
+  return e ? atoi(e) : 2;
+}
+static bool zpass_tma_ok(const GridDev &g, const Sphere &s) {
+  if (zpass_variant() == 0 || !s.d_ztab || s.ztab_rz1 != g.rz1 || s.ztab_rz2 != g.rz2 || g.nz > 256 || s.ncol < 1) return false;
+  return (g.rz1 == 8 && g.rz2 == 9) || (g.rz1 == 5 && g.rz2 == 9);
+}
+template <int RZ1, int RZ2>
+static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const ZTArgs &a) {
+  constexpr int NZ = RZ1 * RZ2, NT = 128;
+  const int ncb = (a.ncol + ZB - 1) / ZB;
+  const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB + (size_t)a.maxlen + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
+                          : sizeof(cplx) * ((size_t)NZ * ZB + NZ) + (sizeof(double) + sizeof(short)) * (size_t)a.maxlen + 32;
+  auto go = [&](auto kern) -> int {
+    SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int vg = std::max(1, std::min(a.nvec, (per_sm * ctx->sm_count + ncb - 1) / ncb));
+    dim3 grid((unsigned)ncb, (unsigned)vg);
+    kern<<<grid, NT, smem, ctx->stream>>>(tm, a);
+    return SGW_OK;
+  };
+  if (g2r) return go(k_zpass_g2r_tma<RZ1, RZ2, NT>);
+  if (a.maxlen <= 5 * NT) return go(k_zpass_r2g_tma<RZ1, RZ2, NT, 5>);
+  return go(k_zpass_r2g_tma<RZ1, RZ2, NT, (ZB * NZ + NT - 1) / NT>);
+}
+static int zpass_tma(sgw_ctx *ctx, bool g2r, const GridDev &g, const Sphere &s, int nvec, const cplx *T, ZTArgs a, bool *done) {
+  *done = false;
+  if (!zpass_tma_ok(g, s)) return SGW_OK;
+  const int var = zpass_variant();               // 1: both passes, 2: G -> r only, 3: r -> G only
+  if ((var == 2 && !g2r) || (var == 3 && g2r)) return SGW_OK;
+  CUtensorMap tm;
+  if (!make_tmap_T(&tm, T, s.ncol, g.nz, nvec)) return SGW_OK;
+  a.twz = g.twz; a.col_ptr = s.d_col_ptr; a.ztab = s.d_ztab; a.ncol = s.ncol; a.nvec = nvec; a.nz = g.nz; a.maxlen = s.zmaxlen;
+  if (g.rz1 == 8) SGW_CHECK((launch_zpass_tma<8, 9>(ctx, g2r, tm, a)));
+  else SGW_CHECK((launch_zpass_tma<5, 9>(ctx, g2r, tm, a)));
+  *done = true;
+  return SGW_OK;
+}
+
+// index table of the TMA z passes: offset of entry (column c, z) from the column's first entry, or -1 (upload; host arrays of `s`)
+static int build_ztab(sgw_ctx *ctx, Sphere *s, int nz, int rz1, int rz2) {
+  if (s->d_ztab) { dev_free(s->d_ztab); s->d_ztab = nullptr; }
+  s->ztab_rz1 = s->ztab_rz2 = 0;
+  if (rz2 <= 1 || nz != rz1 * rz2 || nz > 256) return SGW_OK;
+  const int rz1p = (rz1 + 7) & ~7;
+  std::vector<short> tab((size_t)s->ncol * rz2 * rz1p, (short)-1);
+  int maxlen = 0;
+  for (int c = 0; c < s->ncol; ++c)
+    for (int p = s->h_col_ptr[c]; p < s->h_col_ptr[c + 1]; ++p) {
+      const int z = s->h_zof[p];
+      tab[((size_t)c * rz2 + z % rz2) * rz1p + z / rz2] = (short)(p - s->h_col_ptr[c]);
+    }
+  for (int c0 = 0; c0 < s->ncol; c0 += ZB) maxlen = std::max(maxlen, s->h_col_ptr[std::min(s->ncol, c0 + ZB)] - s->h_col_ptr[c0]);
+  s->zmaxlen = (maxlen + 7) & ~7;
+  SGW_CHECK(upload(ctx, &s->d_ztab, tab.data(), tab.size()));
+  s->ztab_rz1 = rz1; s->ztab_rz2 = rz2;
+  return SGW_OK;
+}
+
 int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long ld, cplx *T, const int *active,
                   const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
@@ -714,6 +1022,13 @@ int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long 
   const size_t smem = zpass_smem(g, zcb);
   dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
   ProfScope prof(ctx, PC_FFT_Z);
+  {
+    ZTArgs a = {};
+    a.vec = in; a.ld = ld; a.active = active;
+    bool done = false;
+    SGW_CHECK(zpass_tma(ctx, true, g, s, nvec, T, a, &done));
+    if (done) { SGW_LAUNCH_CHECK(); return SGW_OK; }
+  }
 #define SGW_Z(Z)                                                                                       \
   do {                                                                                                 \
     SGW_CHECK(set_smem(ctx, k_zpass_g2r<Z>, smem));                                                    \
@@ -734,6 +1049,14 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
   dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
   const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
   ProfScope prof(ctx, PC_FFT_Z);
+  {
+    ZTArgs a = {};
+    a.vec = epi.psi; a.out = out; a.ld = ld; a.active = active;
+    a.mode = epi.mode; a.keep_out = epi.keep_out; a.g2kin = epi.g2kin; a.sigma = epi.sigma; a.sigma_stride = epi.sigma_stride; a.scale = scale;
+    bool done = false;
+    SGW_CHECK(zpass_tma(ctx, false, g, s, nvec, T, a, &done));
+    if (done) { SGW_LAUNCH_CHECK(); return SGW_OK; }
+  }
 #define SGW_Z(Z)                                                                                                  \
   do {                                                                                                            \
     SGW_CHECK(set_smem(ctx, k_zpass_r2g<Z>, smem));                                                               \
@@ -956,6 +1279,7 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
     SGW_CHECK(upload(ctx, &sph->d_ytab, ytab.data(), ytab.size()));
     sph->ytab_ry1 = ry1; sph->ytab_ry2 = ry2;
   }
+  SGW_CHECK(build_ztab(ctx, sph, nz, ctx->pz.r1, ctx->pz.r2));
   return SGW_OK;
 }
 
@@ -1001,6 +1325,7 @@ int remap_sphere(sgw_ctx *ctx, const Sphere &fine, const FftGrid &gr, Sphere *ou
   SGW_CHECK(upload(ctx, &out->d_zof, zof.data(), zof.size()));
   SGW_CHECK(upload(ctx, &out->d_xs, xs.data(), xs.size()));
   SGW_CHECK(upload(ctx, &out->d_perm, fine.perm.data(), fine.perm.size()));
+  SGW_CHECK(build_ztab(ctx, out, gr.n3, gr.pz.r1, gr.pz.r2));
   return SGW_OK;
 }
 
@@ -1012,6 +1337,9 @@ void free_sphere(Sphere *s) {
   }
   if (s->d_ytab) dev_free(s->d_ytab);
   s->d_ytab = nullptr;
+  if (s->d_ztab) dev_free(s->d_ztab);
+  s->d_ztab = nullptr;
+  s->ztab_rz1 = s->ztab_rz2 = 0;
   s->ytab_ry1 = s->ytab_ry2 = 0;
   s->npw = s->ncol = s->nxs = 0;
   s->perm.clear();

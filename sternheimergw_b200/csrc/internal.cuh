@@ -88,6 +88,8 @@ struct Sphere {
       *d_xs = nullptr, *d_perm = nullptr, *d_col_off = nullptr;
   short *d_ytab = nullptr;         // k_plane_vloc index table (fft.cu build_sphere), valid for the y plan (ytab_ry1, ytab_ry2)
   int ytab_ry1 = 0, ytab_ry2 = 0;
+  short *d_ztab = nullptr;         // TMA z-pass gather table (fft.cu build_ztab), valid for the z plan (ztab_rz1, ztab_rz2)
+  int ztab_rz1 = 0, ztab_rz2 = 0, zmaxlen = 0;
   SphereDev dev() const {
     SphereDev s; s.npw = npw; s.ncol = ncol; s.nxs = nxs; s.col_x = d_col_x; s.col_y = d_col_y;
     s.col_ptr = d_col_ptr; s.colof = d_colof; s.zof = d_zof; s.xs = d_xs; s.col_off = d_col_off; return s;

@@ -136,5 +136,21 @@ def test_persistent_plane_kernel_is_bit_identical_to_the_generic_one(monkeypatch
             xs[variant], ierr = c.select_solver(select_solver_type(priority=(1,), threshold=1e-6), 0, b, sigma)
             assert np.all(ierr == 0)
         assert np.array_equal(xs["0"], xs["2"])
+        monkeypatch.delenv("SGW_PLANE")
+        # the persistent TMA z passes (bulk-copy staged input, tensor-map stores / loads) against the generic kernels:
+        # same butterflies on a transposed tile -> same bits, on the 72^3 box (H.psi) and on the reduced 45^3 Delta-rho box
+        zo = {}
+        for variant in ("0", "1", "2"):
+            monkeypatch.setenv("SGW_ZPASS", variant)
+            zo[variant] = c.linear_op(0, om, kq.alpha_pv, psi)
+        assert np.array_equal(zo["0"], zo["1"]) and np.array_equal(zo["1"], outs["2"]) and np.array_equal(zo["2"], zo["0"])
+        fiu = synth.imag_freqs(3)
+        igu = np.arange(1, 41, dtype=np.int32)
+        sc = {}
+        for variant in ("0", "1"):
+            monkeypatch.setenv("SGW_ZPASS", variant)
+            sc[variant] = c.coulomb(select_solver_type(priority=(1, 3), threshold=1e-6), 3, 40, 2, igu, fiu)
+            assert c.rho_grid()[0]
+        assert np.array_equal(sc["0"], sc["1"])
     finally:
         c.close()
