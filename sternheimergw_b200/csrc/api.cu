@@ -484,6 +484,7 @@ int sgw_linear_op(sgw_ctx *ctx, int slot, int nvec, const sgw_cplx *omega, doubl
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
   SGW_ARG(nvec > 0 && omega && psi && apsi, "null argument");
+  SGW_ARG(nvec <= 65535, "at most 65535 vectors per call (grid limit of the batched kernels): split the batch");
   if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
   const KSlot &k = ctx->slots[slot];
   SGW_ARG(ldpsi >= k.npw && ldapsi >= k.npw, "leading dimension smaller than npw");
@@ -515,6 +516,7 @@ int sgw_solve_multishift(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, int 
   cudaSetDevice(ctx->device);
   SGW_ARG(cfg && b && sigma && x && ierr, "null argument");
   SGW_ARG(nrhs > 0 && nshift > 0, "need nrhs > 0 and nshift > 0");
+  SGW_ARG(nrhs <= 65535, "at most 65535 right-hand sides per call (grid limit of the batched kernels): split the batch");
   SGW_ARG(cfg->npriority >= 1 && cfg->npriority <= 4, "priority of the solvers not specified");   // select_solver.f90:116-118
   if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].set) { ctx->err = "operator slot not set"; return SGW_E_STATE; }
   const KSlot &k = ctx->slots[slot];

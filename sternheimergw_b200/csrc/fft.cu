@@ -834,6 +834,7 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_r2g_tma(const __grid_constant__
       const int i = tid + q * NT;
       if (i < len) res[q] = tile[pos[i]];
     }
+    fence_proxy_async();                          // this thread's generic-proxy accesses of the tile are ordered before the TMA write
     __syncthreads();                              // the tile has been read: fetch the next vector's tile while the epilogue runs
     if (tid == 0 && vn < a.nvec) {
       mbar_expect_tx(bar, tile_bytes);

@@ -227,7 +227,89 @@ __global__ void k_copy_cols(int n, int ncol, const cplx *__restrict__ src, long 
     dst[(long)b * dst_rhs_stride + i] = src[(long)b * src_rhs_stride + i];
 }
 
+static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo);
+
+// dense sub-batch <-> batch (right-hand sides list[0..c) of the caller's batch)
+__global__ void k_sub_gather(int n, int nshift, const int *__restrict__ list, const cplx *__restrict__ b, long ldb,
+                             const cplx *__restrict__ sigma, cplx *__restrict__ bc, cplx *__restrict__ sc) {
+  const int j = blockIdx.y, src = list[j];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) bc[(long)j * n + e] = b[(long)src * ldb + e];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nshift; i += blockDim.x) sc[(long)j * nshift + i] = sigma[(long)src * nshift + i];
+}
+__global__ void k_sub_scatter(int n, int nshift, const int *__restrict__ list, const cplx *__restrict__ xc, const int *__restrict__ ic,
+                              cplx *__restrict__ x, int *__restrict__ ierr) {
+  const int j = blockIdx.y, dst = list[j];
+  const long tot = (long)n * nshift;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x)
+    x[(long)dst * tot + e] = xc[(long)j * tot + e];
+  if (blockIdx.x == 0 && threadIdx.x == 0) ierr[dst] = ic[j];
+}
+
+// SGW subspace solver for the right-hand sides flagged in d_todo (all if null).  The basis of every right-hand side costs
+// 2 x m x n complex numbers, so the flagged systems -- usually a handful that fell through from the BiCGStab solver
+// (select_solver.f90:157) -- are COMPACTED into dense sub-batches whose size is bounded by the free device memory, instead of
+// allocating a basis for every right-hand side of the caller's batch.
 int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
+  if (sb.nrhs <= 0) return SGW_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<int> list;
+  if (d_todo) {
+    std::vector<int> h(sb.nrhs);
+    SGW_CUDA(cudaMemcpyAsync(h.data(), d_todo, sizeof(int) * sb.nrhs, cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < sb.nrhs; ++b) if (h[b]) list.push_back(b);
+  } else {
+    list.resize(sb.nrhs);
+    for (int b = 0; b < sb.nrhs; ++b) list[b] = b;
+  }
+  if (list.empty()) return SGW_OK;
+  // chunk size: a basis of up to `mguess` vectors per system next to everything else that is already allocated
+  size_t free_b = 0, total_b = 0, held = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)4 << 30;
+  for (const char *nm : {"ss_V", "ss_W", "ss_V2", "ss_W2", "ss_R", "ss_New", "ss_bc", "ss_xc"}) {
+    auto it = ctx->ws.bufs.find(nm);
+    if (it != ctx->ws.bufs.end()) held += it->second.second;
+  }
+  const size_t n = sb.n;
+  const size_t mguess = std::min<size_t>(n, 96);
+  const size_t per = (2 * mguess + 3 + (size_t)sb.nshift) * n * sizeof(cplx);
+  const double avail = 0.8 * (double)(free_b + held);
+  int chunk = (int)std::max(1.0, std::min((double)list.size(), avail / (double)per));
+  chunk = std::min(chunk, 65535);
+  const bool whole = !d_todo && chunk >= sb.nrhs;
+  if (whole) return subspace_core(ctx, sb, threshold, max_iter, nullptr);     // nothing to compact
+  int *d_list = nullptr, *d_ic = nullptr;
+  cplx *bc = nullptr, *sc = nullptr, *xc = nullptr;
+  SGW_CHECK(ws(ctx, "ss_list", (size_t)chunk, &d_list));
+  SGW_CHECK(ws(ctx, "ss_ic", (size_t)chunk, &d_ic));
+  SGW_CHECK(ws(ctx, "ss_bc", (size_t)chunk * n, &bc));
+  SGW_CHECK(ws(ctx, "ss_sc", (size_t)chunk * sb.nshift, &sc));
+  SGW_CHECK(ws(ctx, "ss_xc", (size_t)chunk * sb.nshift * n, &xc));
+  for (size_t i0 = 0; i0 < list.size(); i0 += chunk) {
+    const int c = (int)std::min<size_t>(chunk, list.size() - i0);
+    SGW_CUDA(cudaMemcpyAsync(d_list, list.data() + i0, sizeof(int) * c, cudaMemcpyHostToDevice, st));
+    dim3 g(16, (unsigned)c);
+    k_sub_gather<<<g, 256, 0, st>>>(sb.n, sb.nshift, d_list, sb.d_b, sb.ldb, sb.d_sigma, bc, sc);
+    SGW_LAUNCH_CHECK();
+    SolveBatch sub = sb;
+    sub.avg = AvgSpec();
+    sub.nrhs = c; sub.d_b = bc; sub.ldb = (long)n; sub.d_sigma = sc; sub.d_x = xc; sub.d_ierr = d_ic;
+    {
+      const std::vector<int> ones(c, 1);           // select_solver.f90:121: ierr = 1 until a solver reports success
+      SGW_CUDA(cudaMemcpyAsync(d_ic, ones.data(), sizeof(int) * c, cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+    }
+    SGW_CHECK(subspace_core(ctx, sub, threshold, max_iter, nullptr));
+    dim3 g2(64, (unsigned)c);
+    k_sub_scatter<<<g2, 256, 0, st>>>(sb.n, sb.nshift, d_list, xc, d_ic, sb.d_x, sb.d_ierr);
+    SGW_LAUNCH_CHECK();
+    SGW_CUDA(cudaStreamSynchronize(st));          // d_list is rewritten by the next chunk
+  }
+  return SGW_OK;
+}
+
+static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
   if (sb.nrhs <= 0) return SGW_OK;
   SubState s;
   s.n = sb.n; s.nrhs = sb.nrhs; s.nshift = sb.nshift; s.max_iter = max_iter;
