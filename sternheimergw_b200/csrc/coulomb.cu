@@ -399,6 +399,10 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
       SGW_CHECK(fft_zpass_g2r(ctx, sk, nocc, kp.d_evc, n, Tk, nullptr, rg));
       SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &sk, nullptr, nocc, Tk, nullptr, nullptr, 1, psir_rho, nullptr, 0, rg));
     }
+    // y-fastest copy of psi_v(r) on the Delta-rho grid for the accumulation stage of k_plane_rho_v2
+    cplx *psir_t = nullptr;
+    SGW_CHECK(ws(ctx, "co_psir_t", (size_t)nocc * rnnr, &psir_t));
+    SGW_CHECK(fft_transpose_planes(ctx, rg, (long)nocc * rnz, psir_rho, psir_t));
     // dvqpsi_us.f90:99-130: dvpsi = fwfft(dvbare(r) psi(r)) on the k+q sphere (only the bands the solver uses)
     SGW_CHECK(ws(ctx, "co_Tq", (size_t)nrhs * ctx->nr3 * ks.sph.ncol, &Tq));
     SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nrhs * n, &dvpsi));
@@ -459,7 +463,7 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
       const int c = std::min(pfc, npf - pf0);
       const cplx *davg = davg_all + (size_t)pf0 * nocc * n;
       SGW_CHECK(fft_zpass_g2r(ctx, sq, c * nocc, davg, n, Td, nullptr, rg));
-      SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Trho + (size_t)pf0 * rnz * rho.ncol, ik > 0, rg));
+      SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Trho + (size_t)pf0 * rnz * rho.ncol, ik > 0, rg, psir_t));
     }
   }
   // mp_sum over pools (:521) is the caller's (one pool per context); fwfft of drho on the density sphere

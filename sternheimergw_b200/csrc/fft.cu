@@ -649,6 +649,199 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 3)) k_pla
 }
 
 
+
+// ------------------------------------------------------------------------------------------------ Delta-rho plane kernel, v2
+// incdrhoscf for one (perturbation x frequency, z-plane) per CTA, compile-time radix plan, the structure of k_plane_vloc:
+//   * the band's input row arrives by cp.async.bulk + mbarrier, the next band's row is in flight while this one is transformed;
+//   * the first inverse y stage gathers from the staged row through the index table (no zero fill, no scatter), the strided x
+//     stage skips empty columns;
+//   * the last inverse x stage is fused with the accumulation  acc += conj(psi_v(r)) dpsi_v(r)  and the accumulator lives in
+//     REGISTERS: with NT >= NY * RX1 every thread owns at most one (row, x group) task, the same one for every band, so the
+//     per-band read-modify-write of an accumulator plane in shared memory disappears;
+//   * psi_v(r) is read from a copy stored y-fastest, so consecutive lanes (consecutive rows) read consecutive addresses.
+// Same butterflies and the same band order as k_plane_rho: bit-identical result (GPU test).
+struct PlaneRhoArgs {
+  const cplx *twx, *twy;
+  const cplx *Tin;           // [(pf * nocc + ib) * nz + pz][ncol_in]
+  const cplx *psir_t;        // [ib][pz][x][y]
+  cplx *Tout;                // [pf * nz + pz][ncol_out]
+  const int *xs_in, *xs_out; // data-holding x columns of the two spheres
+  const short *ytab_in;      // gather table of the input sphere (build_ytab)
+  const int *col_off_out;    // plane offset of every column of the output sphere
+  int nz, nocc, ncol_in, nxs_in, ncol_out, nxs_out, accumulate;
+  double wgt;
+};
+
+template <int RX1, int RX2, int RY1, int RY2, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_plane_rho_v2(PlaneRhoArgs a) {
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1;
+  constexpr int RY1P = (RY1 + 7) & ~7;
+  static_assert(NT >= NY * RX1, "one accumulation task per thread");
+  const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
+  const int tid = threadIdx.x;
+  extern __shared__ __align__(128) unsigned char psm[];
+  cplx *plane = (cplx *)psm;
+  cplx *stage = plane + NY * PITCH;
+  const int ncol_pad = (a.ncol_in + 7) & ~7;
+  cplx *twx = stage + ncol_pad;
+  cplx *twy = twx + NX;
+  short *ytab = (short *)(twy + NY);
+  const int nxs = a.nxs_in;
+  const int ntab = nxs * RY2 * RY1P;
+  int *xs = (int *)(ytab + ntab);
+  int *xso = xs + NX;
+  unsigned *xmask = (unsigned *)(xso + NX);
+  unsigned long long *bar = (unsigned long long *)(xmask + ((RX2 + 1) & ~1));
+  for (int i = tid; i < NX; i += NT) twx[i] = a.twx[i];
+  for (int i = tid; i < NY; i += NT) twy[i] = a.twy[i];
+  for (int i = tid; i < ntab / 8; i += NT) ((uint4 *)ytab)[i] = ((const uint4 *)a.ytab_in)[i];
+  for (int i = tid; i < nxs; i += NT) xs[i] = a.xs_in[i];
+  for (int i = tid; i < a.nxs_out; i += NT) xso[i] = a.xs_out[i];
+  if (tid < RX2) {
+    unsigned m = 0;
+    for (int k = 0; k < RX1; ++k) {
+      const int x = tid + RX2 * k;
+      bool used = false;
+      for (int i = 0; i < nxs; ++i) used |= (a.xs_in[i] == x);
+      if (used) m |= 1u << k;
+    }
+    xmask[tid] = m;
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  const unsigned row_bytes = (unsigned)a.ncol_in * (unsigned)sizeof(cplx);
+  const cplx *rows = a.Tin + ((long)pf * a.nocc * a.nz + pz) * a.ncol_in;     // band ib at + ib * nz * ncol_in
+  const long band_stride = (long)a.nz * a.ncol_in;
+  if (tid == 0) {
+    mbar_expect_tx(bar, row_bytes);
+    tma_load_1d(stage, rows, row_bytes, bar);
+  }
+  // the accumulation task of this thread: row l, x group g (contiguous DFT_RX2 over x = g RX2 .. g RX2 + RX2 - 1)
+  const bool has_acc = tid < NY * RX1;
+  const int al = tid % NY, ag = tid / NY;
+  double accr[RX2], acci[RX2];
+#pragma unroll
+  for (int j = 0; j < RX2; ++j) accr[j] = acci[j] = 0.0;
+  unsigned parity = 0;
+  const cplx zero = cmake(0.0, 0.0);
+  for (int ib = 0; ib < a.nocc; ++ib) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    {  // inverse y, stage 1 (strided DFT_RY1 + twiddle) from the staged row
+      const int ntask = nxs * RY2;
+      TaskIter it(tid, NT, nxs);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int l = it.l, j2 = it.j;
+        short tb[RY1P];
+#pragma unroll
+        for (int q = 0; q < RY1P / 8; ++q) *(uint4 *)(tb + 8 * q) = *(const uint4 *)(ytab + (j2 * nxs + l) * RY1P + 8 * q);
+        double re[RY1], im[RY1];
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) {
+          const int idx = tb[k];
+          const cplx v = idx >= 0 ? stage[idx] : zero;
+          re[k] = v.x; im[k] = v.y;
+        }
+        dft_fwd<RY1>(im, re);
+#pragma unroll
+        for (int k = 1; k < RY1; ++k) {
+          const cplx w = twy[j2 * k];
+          const double c = w.x, sn = -w.y;
+          const double p = re[k], q = im[k];
+          re[k] = p * c - q * sn;
+          im[k] = p * sn + q * c;
+        }
+        cplx *base = plane + xs[l] + j2 * PITCH;
+#pragma unroll
+        for (int k = 0; k < RY1; ++k) base[k * (RY2 * PITCH)] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && ib + 1 < a.nocc) {          // the staging buffer is free: fetch the next band's row
+      mbar_expect_tx(bar, row_bytes);
+      tma_load_1d(stage, rows + (long)(ib + 1) * band_stride, row_bytes, bar);
+    }
+    stage_contig<RY2, +1>(plane, nxs, xs, 1, PITCH, RY1, twy, false, tid, NT);
+    __syncthreads();
+    {  // inverse x, stage 1 (strided DFT_RX1 + twiddle), all rows; columns without data are read as zeros
+      const int ntask = NY * RX2;
+      TaskIter it(tid, NT, NY);
+      for (int t = tid; t < ntask; t += NT, it.next()) {
+        const int j2 = it.j;
+        cplx *base = plane + it.l * PITCH + j2;
+        const unsigned m = xmask[j2];
+        double re[RX1], im[RX1];
+#pragma unroll
+        for (int k = 0; k < RX1; ++k) {
+          const cplx v = (m >> k) & 1u ? base[k * RX2] : zero;
+          re[k] = v.x; im[k] = v.y;
+        }
+        dft_fwd<RX1>(im, re);
+#pragma unroll
+        for (int k = 1; k < RX1; ++k) {
+          const cplx w = twx[j2 * k];
+          const double c = w.x, sn = -w.y;
+          const double p = re[k], q = im[k];
+          re[k] = p * c - q * sn;
+          im[k] = p * sn + q * c;
+        }
+#pragma unroll
+        for (int k = 0; k < RX1; ++k) base[k * RX2] = cmake(re[k], im[k]);
+      }
+    }
+    __syncthreads();
+    if (has_acc) {  // last inverse x stage (contiguous DFT_RX2) fused with acc += conj(psi_v(r)) dpsi_v(r), accumulator in registers
+      const cplx *base = plane + al * PITCH + ag * RX2;
+      const cplx *pr = a.psir_t + (((long)ib * a.nz + pz) * NX + ag * RX2) * NY + al;
+      cplx pv[RX2];
+#pragma unroll
+      for (int j = 0; j < RX2; ++j) pv[j] = pr[(long)j * NY];
+      double re[RX2], im[RX2];
+#pragma unroll
+      for (int j = 0; j < RX2; ++j) { const cplx w = base[j]; re[j] = w.x; im[j] = w.y; }
+      dft_fwd<RX2>(im, re);
+#pragma unroll
+      for (int j = 0; j < RX2; ++j) {
+        const cplx r = cfma(cconj(pv[j]), cmake(re[j], im[j]), cmake(accr[j], acci[j]));   // drho += conj(psi) dpsi
+        accr[j] = r.x; acci[j] = r.y;
+      }
+    }
+    __syncthreads();                             // the next band's first stage rewrites the data columns
+  }
+  if (has_acc) {
+    cplx *base = plane + al * PITCH + ag * RX2;
+#pragma unroll
+    for (int j = 0; j < RX2; ++j) base[j] = cscale(a.wgt, cmake(accr[j], acci[j]));
+  }
+  __syncthreads();
+  // forward 2-D transform of the sum, only the columns of the density sphere; then its columns -> Tout
+  stage_contig<RX2, -1>(plane, NY, nullptr, PITCH, 1, RX1, twx, true, tid, NT);
+  __syncthreads();
+  stage_strided<RX1, -1>(plane, NY, nullptr, PITCH, 1, RX2, twx, false, tid, NT);
+  __syncthreads();
+  stage_contig<RY2, -1>(plane, a.nxs_out, xso, 1, PITCH, RY1, twy, true, tid, NT);
+  __syncthreads();
+  stage_strided<RY1, -1>(plane, a.nxs_out, xso, 1, PITCH, RY2, twy, false, tid, NT);
+  __syncthreads();
+  cplx *orow = a.Tout + ((long)pf * a.nz + pz) * a.ncol_out;
+  if (a.accumulate) {
+    for (int c = tid; c < a.ncol_out; c += NT) orow[c] = cadd(orow[c], plane[a.col_off_out[c]]);
+  } else {
+    for (int c = tid; c < a.ncol_out; c += NT) orow[c] = plane[a.col_off_out[c]];
+  }
+}
+
+// out[p][x][y] = in[p][y][x] for nplanes planes (the y-fastest copy of psi_v(r) the accumulation stage reads)
+__global__ void k_transpose_planes(int nx, int ny, const cplx *__restrict__ in, cplx *__restrict__ out) {
+  __shared__ cplx tile[16][17];
+  const long p = blockIdx.z;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (x0 + tx < nx && y0 + ty < ny) tile[ty][tx] = in[(p * ny + y0 + ty) * nx + x0 + tx];
+  __syncthreads();
+  if (x0 + ty < nx && y0 + tx < ny) out[(p * nx + x0 + ty) * ny + y0 + tx] = tile[tx][ty];
+}
+
 // ------------------------------------------------------------------------------------------------ persistent z passes (TMA)
 // The z transforms are pure HBM streams (2 x 16 B x nz x ncol + the vector per H.psi).  One CTA owns ONE block of ZB = 16
 // sphere columns (its index tables, twiddles and kinetic energies are loaded once) and walks over the vectors of the batch:
@@ -995,6 +1188,28 @@ static int zpass_tma(sgw_ctx *ctx, bool g2r, const GridDev &g, const Sphere &s, 
   return SGW_OK;
 }
 
+
+// index table of the persistent plane kernels (k_plane_vloc, k_plane_rho_v2): for x column l (position in `xs`), sub-index j2 and
+// butterfly leg k of the first y stage, the position of (xs[l], y = j2 + ry2 k) in a T row, or -1 outside the sphere
+static int build_ytab(sgw_ctx *ctx, Sphere *sph, int nx, int ry1, int ry2, const std::vector<int> &xs) {
+  if (sph->d_ytab) { dev_free(sph->d_ytab); sph->d_ytab = nullptr; }
+  sph->ytab_ry1 = sph->ytab_ry2 = 0;
+  if (ry2 <= 1 || sph->h_col_x.size() >= 32768) return SGW_OK;
+  const int nxs = (int)xs.size();
+  std::vector<int> xpos(nx, -1);
+  for (int l = 0; l < nxs; ++l) xpos[xs[l]] = l;
+  const int ry1p = (ry1 + 7) & ~7;                                // whole 16-byte loads per task
+  std::vector<short> ytab((size_t)nxs * ry2 * ry1p, (short)-1);
+  for (size_t c = 0; c < sph->h_col_x.size(); ++c) {
+    const int l = xpos[sph->h_col_x[c]], y = sph->h_col_y[c];
+    const int j2 = y % ry2, k = y / ry2;
+    ytab[((size_t)j2 * nxs + l) * ry1p + k] = (short)c;
+  }
+  SGW_CHECK(upload(ctx, &sph->d_ytab, ytab.data(), ytab.size()));
+  sph->ytab_ry1 = ry1; sph->ytab_ry2 = ry2;
+  return SGW_OK;
+}
+
 // index table of the TMA z passes: offset of entry (column c, z) from the column's first entry, or -1 (upload; host arrays of `s`)
 static int build_ztab(sgw_ctx *ctx, Sphere *s, int nz, int rz1, int rz2) {
   if (s->d_ztab) { dev_free(s->d_ztab); s->d_ztab = nullptr; }
@@ -1163,13 +1378,62 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   return SGW_OK;
 }
 
+int fft_transpose_planes(sgw_ctx *ctx, const FftGrid *gr, long nplanes, const cplx *in, cplx *out) {
+  const GridDev g = grid_dev(ctx, gr);
+  for (long p0 = 0; p0 < nplanes; p0 += 65535) {
+    const unsigned np = (unsigned)std::min<long>(65535, nplanes - p0);
+    dim3 grid((g.nx + 15) / 16, (g.ny + 15) / 16, np);
+    k_transpose_planes<<<grid, 256, 0, ctx->stream>>>(g.nx, g.ny, in + p0 * g.nx * g.ny, out + p0 * g.nx * g.ny);
+    SGW_LAUNCH_CHECK();
+  }
+  return SGW_OK;
+}
+
+template <int RX1, int RX2, int RY1, int RY2>
+static int launch_plane_rho_v2(sgw_ctx *ctx, const GridDev &g, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin,
+                               const cplx *psir_t, double wgt, cplx *Tout, int accumulate) {
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 256;
+  const int ncol_pad = (sin.ncol + 7) & ~7, ntab = sin.nxs * RY2 * ((RY1 + 7) & ~7);
+  const size_t smem = sizeof(cplx) * ((size_t)NY * PITCH + ncol_pad + NX + NY) + sizeof(short) * ntab + sizeof(int) * 2 * NX +
+                      sizeof(unsigned) * ((RX2 + 1) & ~1) + 16;
+  if (smem > ctx->smem_optin) return 1;          // not done
+  PlaneRhoArgs a;
+  a.twx = g.twx; a.twy = g.twy; a.Tin = Tin; a.psir_t = psir_t; a.Tout = Tout; a.xs_in = sin.d_xs; a.xs_out = sout.d_xs;
+  a.ytab_in = sin.d_ytab; a.col_off_out = sout.d_col_off; a.nz = g.nz; a.nocc = nocc; a.ncol_in = sin.ncol; a.nxs_in = sin.nxs;
+  a.ncol_out = sout.ncol; a.nxs_out = sout.nxs; a.accumulate = accumulate; a.wgt = wgt;
+  dim3 grid(npf, g.nz);
+  // SGW_RHO_MINB: resident CTAs per SM the register allocation must allow.  Measured (Si64 step): 3 (80 registers, spills)
+  // 25.4 ms, 2 (no spills) 20.5 ms; the generic k_plane_rho takes 40 ms
+  const char *e = getenv("SGW_RHO_MINB");
+  if (!(e && atoi(e) == 3)) {
+    auto kern = k_plane_rho_v2<RX1, RX2, RY1, RY2, NT, 2>;
+    SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, ctx->stream>>>(a);
+  } else {
+    auto kern = k_plane_rho_v2<RX1, RX2, RY1, RY2, NT, 3>;
+    SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, ctx->stream>>>(a);
+  }
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
 int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
-                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr) {
+                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr, const cplx *psir_t) {
   if (npf <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
   const size_t smem = plane_smem(g, 2);
   dim3 grid(npf, g.nz);
   ProfScope prof(ctx, PC_RHO_PLANE);
+  {
+    const char *e = getenv("SGW_RHO_V2");          // 0: generic k_plane_rho (A/B testing)
+    const bool want = !(e && atoi(e) == 0);
+    if (want && psir_t && sin.d_ytab && sin.ytab_ry1 == g.ry1 && sin.ytab_ry2 == g.ry2 && g.rx1 == 5 && g.rx2 == 9 && g.ry1 == 5 &&
+        g.ry2 == 9 && npf <= 2147483647 && g.nz <= 65535) {
+      const int rc = launch_plane_rho_v2<5, 9, 5, 9>(ctx, g, sin, sout, npf, nocc, Tin, psir_t, wgt, Tout, accumulate);
+      if (rc <= 0) return rc;
+    }
+  }
   // small planes (the reduced Delta-rho box): 256 threads fill the butterfly stages better and two CTAs fit on an SM
   static int rho_nt = -1;                                        // SGW_RHO_NT: tuning knob (128 | 192 | 256)
   if (rho_nt < 0) { const char *e = getenv("SGW_RHO_NT"); rho_nt = e ? atoi(e) : 0; }
@@ -1263,23 +1527,7 @@ int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl, Sphere *sph) {
   SGW_CHECK(upload(ctx, &sph->d_zof, zof.data(), zof.size()));
   SGW_CHECK(upload(ctx, &sph->d_xs, xs.data(), xs.size()));
   SGW_CHECK(upload(ctx, &sph->d_perm, order.data(), order.size()));
-  // index table of the persistent plane kernel (k_plane_vloc): for x column l, sub-index j2 and butterfly leg k of the
-  // first y stage, the position of (xs[l], y = j2 + ry2 k) in a T row, or -1 outside the sphere
-  sph->ytab_ry1 = sph->ytab_ry2 = 0;
-  if (ctx->py.r2 > 1 && col_x.size() < 32768) {
-    const int ry1 = ctx->py.r1, ry2 = ctx->py.r2, nxs = (int)xs.size();
-    std::vector<int> xpos(nx, -1);
-    for (int l = 0; l < nxs; ++l) xpos[xs[l]] = l;
-    const int ry1p = (ry1 + 7) & ~7;                                // whole 16-byte loads per task
-    std::vector<short> ytab((size_t)nxs * ry2 * ry1p, (short)-1);
-    for (size_t c = 0; c < col_x.size(); ++c) {
-      const int l = xpos[col_x[c]], y = col_y[c];
-      const int j2 = y % ry2, k = y / ry2;
-      ytab[((size_t)j2 * nxs + l) * ry1p + k] = (short)c;
-    }
-    SGW_CHECK(upload(ctx, &sph->d_ytab, ytab.data(), ytab.size()));
-    sph->ytab_ry1 = ry1; sph->ytab_ry2 = ry2;
-  }
+  SGW_CHECK(build_ytab(ctx, sph, nx, ctx->py.r1, ctx->py.r2, xs));
   SGW_CHECK(build_ztab(ctx, sph, nz, ctx->pz.r1, ctx->pz.r2));
   return SGW_OK;
 }
@@ -1327,6 +1575,7 @@ int remap_sphere(sgw_ctx *ctx, const Sphere &fine, const FftGrid &gr, Sphere *ou
   SGW_CHECK(upload(ctx, &out->d_xs, xs.data(), xs.size()));
   SGW_CHECK(upload(ctx, &out->d_perm, fine.perm.data(), fine.perm.size()));
   SGW_CHECK(build_ztab(ctx, out, gr.n3, gr.pz.r1, gr.pz.r2));
+  SGW_CHECK(build_ytab(ctx, out, nc[0], gr.py.r1, gr.py.r2, xs));
   return SGW_OK;
 }
 

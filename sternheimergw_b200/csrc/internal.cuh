@@ -282,7 +282,9 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
 // bands: 2-D inverse of dpsi, acc += conj(psi_v(r)) dpsi(r); then wgt*acc -> 2-D forward -> columns of the density
 // sphere `sout` (Tout[pf][pz][col], += if accumulate) or, when Rout != null, the real-space planes Rout[pf][pz][nxy]
 int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, int nocc, const cplx *Tin, const cplx *psir,
-                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr = nullptr);
+                  double wgt, cplx *Tout, int accumulate, const FftGrid *gr = nullptr, const cplx *psir_t = nullptr);
+// out[p][x][y] = in[p][y][x]: the y-fastest copy of psi_v(r) that k_plane_rho_v2 reads (psir_t above)
+int fft_transpose_planes(sgw_ctx *ctx, const FftGrid *gr, long nplanes, const cplx *in, cplx *out);
 // epilogue modes of the final z pass
 struct ZEpilogue {
   int mode;              // 0: out = val ; 1: out = out*keep + g2kin*psi + sigma*psi + val (H.psi) ; 2: out += val

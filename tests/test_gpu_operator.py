@@ -154,3 +154,24 @@ def test_persistent_plane_kernel_is_bit_identical_to_the_generic_one(monkeypatch
         assert np.array_equal(sc["0"], sc["1"])
     finally:
         c.close()
+
+
+def test_rho_plane_v2_is_bit_identical_to_the_generic_kernel(monkeypatch):
+    """k_plane_rho_v2 (TMA-staged rows, index-table gather, register accumulator, y-fastest psi_v(r); csrc/fft.cu) against
+    the generic k_plane_rho on the reduced 45^3 Delta-rho box of the Si64 workload: the same eps columns bit for bit."""
+    import synth
+    from sternheimergw_b200 import Context, select_solver_type
+    syn = synth.preset("si64")
+    c = Context(0)
+    try:
+        c.install_system(syn)
+        fiu = synth.imag_freqs(3)
+        igu = np.arange(1, 1901, dtype=np.int32)
+        out = {}
+        for variant in ("0", "1"):
+            monkeypatch.setenv("SGW_RHO_V2", variant)
+            out[variant] = c.coulomb(select_solver_type(priority=(1, 3), threshold=1e-6), 5, 1900, 3, igu, fiu)
+            assert c.rho_grid()[0] and tuple(c.rho_grid()[1]) == (45, 45, 45)
+        assert np.array_equal(out["0"], out["1"])
+    finally:
+        c.close()
