@@ -307,6 +307,10 @@ def time_to_w_block(ctx, syn, cfg, fiu, rank, world, barrier):
     ngc = NTW
     igu = np.arange(1, ngc + 1, dtype=np.int32)
     t = {}
+    if world > 1:        # warm the collectives this block uses (communicator setup is not part of a q-point's time)
+        from sternheimergw_b200.dist import gather_columns, gather_frequencies
+        gather_columns(np.zeros((4, 2, 1), complex, order="F"), [1] * world, all_ranks=True)
+        gather_frequencies(np.zeros((4, 4, 1), complex, order="F"), [1] * world)
     barrier()
     t0 = time.perf_counter()
     ctx.install_system(syn)
@@ -540,7 +544,8 @@ def main():
         "fft_zpass": ("hbm", nop * (2.0 * syn.nr[2] * ncol * 16 + 4 * 16.0 * n), "GB/s"),
         "gemm_project": ("tensor", nop * 8.0 * npw * m, "TFLOP/s"),
         "gemm_expand": ("tensor", nop * 8.0 * n * m, "TFLOP/s"),
-        "shift_gemm": ("tensor", nrhs_step * 8.0 * n * kbar * ns, "TFLOP/s"),
+        # materialisation of the +-omega averaged solutions: (n x K)(K x nfreq) per right-hand side (AvgSpec, csrc/bicgstab.cu)
+        "shift_gemm": ("tensor", nrhs_step * 8.0 * n * kbar * NFS, "TFLOP/s"),
         # the streaming shifted update exists only with SGW_SHIFT=stream; in the default (lazy) mode the class holds the tiny
         # coefficient kernels and has no roofline
         **({} if prof_tot.get("shift_gemm", {"ms": 0})["ms"] > 0 else {"shift_fused": ("hbm", outer_rhs * (4.0 * ns + nsnap + L) * 16.0 * n, "GB/s")}),

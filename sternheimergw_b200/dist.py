@@ -19,72 +19,75 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+def _device(dist, device):
+    import torch
+    if device is not None:
+        return device
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _gather_blocks(blocks_c: np.ndarray, counts, root: int, all_ranks: bool, device=None):
+    """Gather of per-rank blocks that are C-contiguous along their first axis (counts[r] leading entries on rank r): ONE
+    padded all_gather (or gather) of raw float64 pairs, no transposes and no per-element Python work; returns the concatenated
+    (sum(counts), ...) complex array on the root (on every rank with all_ranks), None elsewhere."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    tail = blocks_c.shape[1:]
+    per = int(np.prod(tail)) if tail else 1
+    nmax = max(counts)
+    dev = _device(dist, device)
+    pin = dev.type == "cuda"
+    mine_h = torch.zeros((nmax, per, 2), dtype=torch.float64, pin_memory=pin)
+    if blocks_c.shape[0]:
+        mine_h[:blocks_c.shape[0]] = torch.from_numpy(np.ascontiguousarray(blocks_c).view(np.float64).reshape(blocks_c.shape[0], per, 2))
+    mine = mine_h.to(dev, non_blocking=True)
+    if all_ranks or dist.get_backend() == "nccl":
+        full = torch.empty((world, nmax, per, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full.view(-1), mine.view(-1))
+        have = all_ranks or rank == root
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == root else None
+        dist.gather(mine, parts, dst=root)
+        full = torch.stack(parts) if rank == root else None
+        have = rank == root
+    if not have:
+        return None
+    full_h = full.cpu().numpy().view(np.complex128).reshape((world, nmax) + tail)
+    out = np.empty((int(sum(counts)),) + tail, dtype=np.complex128)
+    off = 0
+    for r in range(world):
+        n = counts[r]
+        if n:
+            out[off:off + n] = full_h[r, :n]
+        off += n
+    return out
+
+
 def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None, all_ranks: bool = False):
     """mp_gatherv(inter_image_comm, root, num_task, scrcoul_loc, scrcoul_root) (do_stern.f90:211, parallel.f90:1130).
 
     scr_loc: (ngc, nfs, ntask_loc) complex128 of this rank; num_task: tasks of every rank.  Returns the
-    (ngc, nfs, sum(num_task)) array on ``root`` and None elsewhere.  Without an initialised process group
-    (single rank) the input is returned unchanged.
+    (ngc, nfs, sum(num_task)) array on ``root`` (on every rank with ``all_ranks``) and None elsewhere.  Without an initialised
+    process group (single rank) the input is returned unchanged.  A Fortran-ordered (ngc, nfs, ntask) array IS a C-ordered
+    (ntask, nfs, ngc) one, so the blocks travel as they lie in memory.
     """
-    import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return scr_loc
-    rank, world = dist.get_rank(), dist.get_world_size()
-    ngc, nfs = scr_loc.shape[0], scr_loc.shape[1]
-    nmax = max(num_task)
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
-    # pad every block to the largest one: all_gather needs equal shapes (the remainder rule gives blocks that
-    # differ by at most one column)
-    buf = np.zeros((nmax, nfs, ngc, 2), dtype=np.float64)
-    if scr_loc.shape[2]:
-        t = np.ascontiguousarray(np.transpose(scr_loc, (2, 1, 0)))
-        buf[:scr_loc.shape[2]] = t.view(np.float64).reshape(scr_loc.shape[2], nfs, ngc, 2)
-    mine = torch.from_numpy(buf).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    if rank != root and not all_ranks:
-        return None
-    out = np.zeros((ngc, nfs, int(sum(num_task))), dtype=np.complex128, order="F")
-    off = 0
-    for r in range(world):
-        n = num_task[r]
-        if n:
-            blk = parts[r][:n].cpu().numpy().reshape(n, nfs, ngc, 2)
-            out[:, :, off:off + n] = np.transpose(blk[..., 0] + 1j * blk[..., 1], (2, 1, 0))
-        off += n
-    return out
+    blocks = np.ascontiguousarray(np.asfortranarray(scr_loc).T)          # a view for Fortran-ordered input
+    out = _gather_blocks(blocks, [int(x) for x in num_task], root, all_ranks, device)
+    return None if out is None else out.T                                 # (ngc, nfs, ntot), Fortran order, no copy
 
 
 def gather_frequencies(w_loc: np.ndarray, num_freq, root: int = 0, device=None):
     """Gather of the frequency slices (ngc, ngc, nfs_loc) every rank inverted into (ngc, ngc, sum(num_freq)) on ``root``."""
-    import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return w_loc
-    rank, world = dist.get_rank(), dist.get_world_size()
-    ngc = w_loc.shape[0]
-    nmax = max(num_freq)
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
-    buf = np.zeros((nmax, ngc, ngc, 2), dtype=np.float64)
-    if w_loc.shape[2]:
-        buf[:w_loc.shape[2]] = np.ascontiguousarray(np.transpose(w_loc, (2, 1, 0))).view(np.float64).reshape(w_loc.shape[2], ngc, ngc, 2)
-    mine = torch.from_numpy(buf).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)] if rank == root else None
-    dist.gather(mine, parts, dst=root)
-    if rank != root:
-        return None
-    out = np.zeros((ngc, ngc, int(sum(num_freq))), dtype=np.complex128, order="F")
-    off = 0
-    for r in range(world):
-        n = num_freq[r]
-        if n:
-            blk = parts[r][:n].cpu().numpy()
-            out[:, :, off:off + n] = np.transpose(blk[..., 0] + 1j * blk[..., 1], (2, 1, 0))
-        off += n
-    return out
+    blocks = np.ascontiguousarray(np.asfortranarray(w_loc).T)
+    out = _gather_blocks(blocks, [int(x) for x in num_freq], root, False, device)
+    return None if out is None else out.T
 
 
 def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, invert_fn=None, eps_head=None,
@@ -152,8 +155,7 @@ def root_sum(a: np.ndarray, root: int = 0, device=None):
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return a
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
-                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+    dev = _device(dist, device)
     t = torch.from_numpy(np.ascontiguousarray(a).view(np.float64).copy()).to(dev)
     dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
     if dist.get_rank() != root:
