@@ -26,6 +26,19 @@ def _device(dist, device):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
+_PINNED = {}
+
+
+def _pinned(key, shape):
+    """Page-locked staging buffers are expensive to create (cudaHostAlloc): keep one per (role, shape)."""
+    import torch
+    t = _PINNED.get((key, shape))
+    if t is None:
+        t = torch.zeros(shape, dtype=torch.float64, pin_memory=True)
+        _PINNED[(key, shape)] = t
+    return t
+
+
 def _gather_blocks(blocks_c: np.ndarray, counts, root: int, all_ranks: bool, device=None):
     """Gather of per-rank blocks that are C-contiguous along their first axis (counts[r] leading entries on rank r): ONE
     padded all_gather (or gather) of raw float64 pairs, no transposes and no per-element Python work; returns the concatenated
@@ -38,7 +51,7 @@ def _gather_blocks(blocks_c: np.ndarray, counts, root: int, all_ranks: bool, dev
     nmax = max(counts)
     dev = _device(dist, device)
     pin = dev.type == "cuda"
-    mine_h = torch.zeros((nmax, per, 2), dtype=torch.float64, pin_memory=pin)
+    mine_h = _pinned("send", (nmax, per, 2)) if pin else torch.zeros((nmax, per, 2), dtype=torch.float64)
     if blocks_c.shape[0]:
         mine_h[:blocks_c.shape[0]] = torch.from_numpy(np.ascontiguousarray(blocks_c).view(np.float64).reshape(blocks_c.shape[0], per, 2))
     mine = mine_h.to(dev, non_blocking=True)
@@ -53,7 +66,12 @@ def _gather_blocks(blocks_c: np.ndarray, counts, root: int, all_ranks: bool, dev
         have = rank == root
     if not have:
         return None
-    full_h = full.cpu().numpy().view(np.complex128).reshape((world, nmax) + tail)
+    if pin:
+        recv = _pinned("recv", (world, nmax, per, 2))
+        recv.copy_(full, non_blocking=False)
+        full_h = recv.numpy().view(np.complex128).reshape((world, nmax) + tail)
+    else:
+        full_h = full.cpu().numpy().view(np.complex128).reshape((world, nmax) + tail)
     out = np.empty((int(sum(counts)),) + tail, dtype=np.complex128)
     off = 0
     for r in range(world):
