@@ -25,8 +25,9 @@ def f(x):
         return float("nan")
 
 
-CLASS_OF = {"k_plane<0": "fft_plane", "k_zpass_g2r": "fft_zpass", "k_zpass_r2g": "fft_zpass", "k_zgemm<1, 1>": "gemm_project",
-            "k_zgemm<0, 0>": "gemm_expand", "k_shift_fused": "shift_fused", "k_shift_apply": "shift_fused"}
+CLASS_OF = {"k_plane<0": "fft_plane", "k_plane_vloc": "fft_plane", "k_zpass_g2r": "fft_zpass", "k_zpass_r2g": "fft_zpass",
+            "k_zgemm<1, 1>": "gemm_project", "k_zgemm<0, 0>": "gemm_expand", "k_shift_fused": "shift_fused",
+            "k_shift_apply": "shift_fused", "k_shift_gemm": "shift_gemm", "k_plane_rho": "rho_plane"}
 
 
 def traffic(rep, units_per_launch):
@@ -37,24 +38,27 @@ def traffic(rep, units_per_launch):
     ix = {h: i for i, h in enumerate(hdr)}
     acc = {}
     for d in data:
-        name = d[ix["Kernel Name"]].replace("void ", "")
+        name = d[ix["Kernel Name"]].replace("void ", "").replace("sgw::", "")
         cls = next((c for k, c in CLASS_OF.items() if name.startswith(k)), None)
         if cls is None:
             continue
         def byt(m):
             return f(d[ix[m]]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[ix[m]], 1.0)
-        a = acc.setdefault(cls, {"n": 0, "bytes": 0.0, "fp64": 0.0, "tensor": 0.0, "dram": 0.0})
+        a = acc.setdefault(cls, {"n": 0, "bytes": 0.0, "fp64": 0.0, "tensor": 0.0, "dram": 0.0, "smem": 0.0})
         a["n"] += 1
         a["bytes"] += byt("dram__bytes_read.sum") + byt("dram__bytes_write.sum")
         a["fp64"] += f(d[ix["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]])
         a["tensor"] += f(d[ix["TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"]])
         a["dram"] += f(d[ix["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])
+        if "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed" in ix:
+            a["smem"] += f(d[ix["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]])
     out = {}
     for cls, a in acc.items():
         out[cls] = {"dram_bytes_per_unit": a["bytes"] / a["n"] / units_per_launch, "fp64_pipe_pct": a["fp64"] / a["n"],
-                    "tensor_pipe_pct": a["tensor"] / a["n"], "dram_pct": a["dram"] / a["n"], "launches_captured": a["n"],
+                    "tensor_pipe_pct": a["tensor"] / a["n"], "dram_pct": a["dram"] / a["n"], "smem_pipe_pct": a["smem"] / a["n"],
+                    "launches_captured": a["n"],
                     "source": rep.split("/")[-1], "units_per_launch": units_per_launch}
-    print(json.dumps(out, indent=1))
+    print(json.dumps(out, indent=1).replace('NaN', 'null'))
 
 
 def main():
