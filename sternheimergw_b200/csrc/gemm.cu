@@ -7,6 +7,8 @@
 // out = P coef'.  tcgen05 has no f64 kind, so the legacy mma.sync DMMA path is the FP64 tensor route on sm_100a.
 #include "internal.cuh"
 
+#include <stdlib.h>
+
 namespace sgw {
 
 constexpr int BM = 64, BN = 32, BK = 16, GT = 256;
@@ -33,7 +35,10 @@ __global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx
   // Compacted batches: with `list` the problem has *count columns; list_mode bit 0: column j of B is B's column list[j]
   // (gather), list_mode bit 1: column j of C is C's column list[j] (scatter); both bits may be set.  Tiles beyond the
   // count exit at once, so a batch in which most right-hand sides have converged costs what its active columns cost.
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // list_mode bit 2: column tiles run fastest (blockIdx.x = n tile, blockIdx.y = m tile): the CTAs that are resident together
+  // then share ONE tile of A, which matters when A (the npwx x m projector panel, 148 MB at Si64) does not fit in L2
+  const bool nfast = (list_mode & 4) != 0;
+  const int m0 = (nfast ? blockIdx.y : blockIdx.x) * BM, n0 = (nfast ? blockIdx.x : blockIdx.y) * BN;
   if (list) {
     N = min(N, *count);
     if (n0 >= N) return;
@@ -148,7 +153,7 @@ static int launch_zgemm(sgw_ctx *ctx, dim3 grid, int M, int N, int K, const cplx
                         const int *count = nullptr, int list_mode = 0) {
   constexpr size_t smem = zgemm_smem<A_KCONTIG>();
   SGW_CHECK(zgemm_init(ctx));
-  if (!list) list_mode = 0;
+  if (!list) list_mode &= 4;
   k_zgemm<A_KCONTIG, CONJA><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, list, count,
                                                              list_mode);
   SGW_LAUNCH_CHECK();
@@ -310,10 +315,14 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &ks, double alpha_pv, int nvec, con
     SGW_LAUNCH_CHECK();
   }
   {
-    dim3 grid((ks.npwx + BM - 1) / BM, (nvec + BN - 1) / BN, 1);
+    static int nfast = -1;                                      // SGW_GEMM_NFAST=0: row tiles fastest (A/B testing)
+    if (nfast < 0) { const char *e = getenv("SGW_GEMM_NFAST"); nfast = e ? atoi(e) : 1; }
+    const int mt = (ks.npwx + BM - 1) / BM, nt = (nvec + BN - 1) / BN;
+    const bool nf = nfast && mt <= 65535;
+    dim3 grid(nf ? nt : mt, nf ? mt : nt, 1);
     ProfScope prof(ctx, PC_GEMM_OUT);
     SGW_CHECK((launch_zgemm<false, false>(ctx, grid, ks.npwx, nvec, m, ks.d_P, ks.npwx, coef, m, out, ldout, cmake(1, 0),
-                                           cmake(0, 0), m, 0, list, count, 2)));
+                                           cmake(0, 0), m, 0, list, count, 2 | (nf ? 4 : 0))));
   }
   return SGW_OK;
 }

@@ -13,9 +13,11 @@
 // (dot + two axpys) between two block barriers; the dependency order is the reference's MGS order.
 #include "internal.cuh"
 
+#include <stdlib.h>
+
 namespace sgw {
 
-constexpr int ST = 512;   // threads per RHS CTA
+constexpr int ST = 1024;  // largest CTA of the one-CTA-per-RHS kernels (see sub_threads)
 
 struct SubState {
   int n, nrhs, nshift, cap, max_iter;
@@ -229,6 +231,16 @@ __global__ void k_copy_cols(int n, int ncol, const cplx *__restrict__ src, long 
 
 static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo);
 
+// threads of the one-CTA-per-RHS kernels: the Gram-Schmidt chains are sequences of block reductions, whose latency grows
+// with the number of warps, so short vectors get small CTAs (SGW_SUB_THREADS overrides)
+static int sub_threads(int n) {
+  static int forced = -1;
+  if (forced < 0) { const char *e = getenv("SGW_SUB_THREADS"); forced = e ? atoi(e) : 0; }
+  if (forced >= 32 && forced <= ST && forced % 32 == 0) return forced;
+  (void)n;
+  return 512;   // measured on the gw_licl stand-in (n = 544, 102 shifts): 64 -> 4.4 s, 128 -> 2.4 s, 256 -> 2.1 s, 512 -> 1.45 s
+}
+
 // dense sub-batch <-> batch (right-hand sides list[0..c) of the caller's batch)
 __global__ void k_sub_gather(int n, int nshift, const int *__restrict__ list, const cplx *__restrict__ b, long ldb,
                              const cplx *__restrict__ sigma, cplx *__restrict__ bc, cplx *__restrict__ sc) {
@@ -331,18 +343,18 @@ static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, i
   SGW_CUDA(cudaMemsetAsync(s.nop, 0, sizeof(long), st));
   int *h_count = nullptr;
   SGW_CUDA(cudaMallocHost((void **)&h_count, sizeof(int)));
-  k_sub_init<<<(unsigned)nr, ST, 0, st>>>(s, threshold, d_todo);
+  k_sub_init<<<(unsigned)nr, sub_threads(s.n), 0, st>>>(s, threshold, d_todo);
   SGW_LAUNCH_CHECK();
   int total_cols = 0;   // upper bound of the basis size of any RHS
   int rc = SGW_OK;
   for (int ishift = 0; ishift < s.nshift && rc == SGW_OK; ++ishift) {
-    k_sub_shift<<<(unsigned)nr, ST, 0, st>>>(s, ishift);
+    k_sub_shift<<<(unsigned)nr, sub_threads(s.n), 0, st>>>(s, ishift);
     SGW_LAUNCH_CHECK();
     for (int it = 0; it <= max_iter; ++it) {
       SGW_CUDA(cudaMemsetAsync(s.count, 0, sizeof(int), st));
       const size_t dyn = (size_t)(s.cap + 1) * sizeof(cplx);
       if (dyn > 48 * 1024) SGW_CUDA(cudaFuncSetAttribute(k_sub_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      k_sub_residual<<<(unsigned)nr, ST, dyn, st>>>(s, ishift);
+      k_sub_residual<<<(unsigned)nr, sub_threads(s.n), dyn, st>>>(s, ishift);
       SGW_LAUNCH_CHECK();
       SGW_CUDA(cudaMemcpyAsync(h_count, s.count, sizeof(int), cudaMemcpyDeviceToHost, st));
       SGW_CUDA(cudaStreamSynchronize(st));
@@ -373,7 +385,7 @@ static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, i
         SGW_LAUNCH_CHECK();
         s.V = nV; s.W = nW; s.cap = ncap;
       }
-      k_sub_expand<<<(unsigned)nr, ST, 0, st>>>(s);
+      k_sub_expand<<<(unsigned)nr, sub_threads(s.n), 0, st>>>(s);
       SGW_LAUNCH_CHECK();
       ++total_cols;
     }
