@@ -152,6 +152,16 @@ int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw
  * (phys/coul/src/invert_epsilon.f90:23): scrcoul_g(ngc, ngc, nfs) in place */
 int sgw_unfold_w(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *ig_unique,
                  const sgw_cplx *scrcoul_in /* ngc x nfs x ngmunique */, sgw_cplx *scrcoul_out /* ngc x ngc x nfs */);
+/* unfold_w with use_symm (algo/symmetry/src/unfold_w.f90:23-131, the default of main/src/gw_input.yml:138): the rows of the
+ * symmetry-unique G (ig_unique, from stern_symm.f90) are filled as above, every other row ig is the row of sym_friend(ig) rotated by
+ * the operation sym_ig(ig): out(ig, gmapsym(igp, invs(R)), iw) = out(sym_friend(ig), igp, iw) eigv(sym_friend(ig), R) CONJG(eigv(igp, R)).
+ * sym_ig, sym_friend: num_g_corr entries (1-based, entries of unique G ignored); gmapsym, eigv: num_g_corr x nsym column-major as
+ * gmap_sym.f90 returns them; invs: nsym (1-based).  scrcoul_out is fully overwritten.  Call with the identity only (nsymq = 1) is
+ * sgw_unfold_w. */
+int sgw_unfold_w_symm(sgw_ctx *ctx, int num_g_corr, int nfs, int ngmunique, const int32_t *ig_unique, int nsym,
+                      const int32_t *sym_ig, const int32_t *sym_friend, const int32_t *gmapsym, const sgw_cplx *eigv,
+                      const int32_t *invs, const sgw_cplx *scrcoul_in, sgw_cplx *scrcoul_out);
+
 int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrcoul_g, int lgamma);
 
 /* ---- L2': Green's function (phys/green/src/green.f90:105) ----

@@ -11,7 +11,7 @@ c_int, c_double, c_void_p, c_int64 = C.c_int, C.c_double, C.c_void_p, C.c_int64
 
 # every symbol of include/sgw_b200.h (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
-    "sgw_create", "sgw_destroy", "sgw_set_stream", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_release_workspace", "sgw_device_synchronize",
+    "sgw_create", "sgw_destroy", "sgw_set_stream", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_release_workspace", "sgw_unfold_w_symm", "sgw_device_synchronize",
     "sgw_get_profile", "sgw_profile_class_name", "sgw_set_message_callback",
     "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
     "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
@@ -101,6 +101,8 @@ def load():
         L.sgw_freqbins_num_freq.argtypes = [C.POINTER(Freqbins)]
         L.sgw_pade_robust.argtypes = [c_void_p, c_double, c_int, c_void_p, C.POINTER(c_int), C.POINTER(c_int), c_void_p, c_void_p,
                                       c_double, c_double]
+        L.sgw_unfold_w_symm.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]
         L.sgw_aaa_pole_residual.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_int)]
         L.sgw_coulpade.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p]
         L.sgw_analytic_coeff.argtypes = [c_void_p, c_int, c_double, C.POINTER(Freqbins), c_int, c_void_p]

@@ -115,6 +115,22 @@ __global__ void k_unfold(int ngc, int nfs, int nuniq, const int *__restrict__ ig
   out[(long)row + (long)ngc * (igp + (long)ngc * iw)] = cconj(in[(long)igp + (long)ngc * (iw + (long)nfs * ig)]);
 }
 
+// unfold_w.f90:104-129: row ig that is not symmetry-unique is the row of its sym_friend, rotated by R = sym_ig(ig):
+//   out(ig, gmapsym(igp, invs(R)), iw) = out(sym_friend(ig), igp, iw) * eigv(sym_friend(ig), R) * CONJG(eigv(igp, R))
+// sym_friend(ig) is always a unique G (stern_symm.f90:94), whose row k_unfold has already filled, so the rows are independent.
+__global__ void k_unfold_symm(int ngc, int nfs, const int *__restrict__ is_unique, const int *__restrict__ sym_ig,
+                              const int *__restrict__ sym_friend, const int *__restrict__ gmapsym, const cplx *__restrict__ eigv,
+                              const int *__restrict__ invs, cplx *__restrict__ out) {
+  const int igp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iw = blockIdx.y, ig = blockIdx.z;
+  if (igp >= ngc || is_unique[ig]) return;
+  const int fr = sym_friend[ig] - 1, isym = sym_ig[ig] - 1;
+  const int ism1 = invs[isym] - 1;
+  const int col = gmapsym[igp + (long)ngc * ism1] - 1;
+  const cplx phase = cmul(eigv[fr + (long)ngc * isym], cconj(eigv[igp + (long)ngc * isym]));
+  out[(long)ig + (long)ngc * (col + (long)ngc * iw)] = cmul(out[(long)fr + (long)ngc * (igp + (long)ngc * iw)], phase);
+}
+
 // ---------------------------------------------------------------- invert_epsilon: batched in-place Gauss-Jordan
 // (ZGETRF/ZGETRI semantics: partial pivoting with the IZAMAX |re|+|im| criterion), one matrix per frequency.
 __global__ void k_eps_wings(int n, cplx *__restrict__ a) {          // invert_epsilon.f90:46-56, :72-81
@@ -1158,6 +1174,69 @@ int sgw_unfold_w(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *i
   dim3 gr((ngc + 127) / 128, nfs, ngmunique);
   k_unfold<<<gr, 128, 0, st>>>(ngc, nfs, ngmunique, d_iu, d_in, d_out);
   SGW_LAUNCH_CHECK();
+  SGW_CUDA(cudaMemcpyAsync(scrcoul_out, d_out, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  end_call(ctx);
+  return SGW_OK;
+}
+
+int sgw_unfold_w_symm(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *ig_unique, int nsym, const int32_t *sym_ig,
+                      const int32_t *sym_friend, const int32_t *gmapsym, const sgw_cplx *eigv, const int32_t *invs,
+                      const sgw_cplx *scrcoul_in, sgw_cplx *scrcoul_out) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ngc > 0 && nfs > 0 && ngmunique > 0 && nsym > 0 && ig_unique && sym_ig && sym_friend && gmapsym && eigv && invs && scrcoul_in &&
+              scrcoul_out, "bad argument");
+  std::vector<int> uniq(ngc, 0);
+  for (int i = 0; i < ngmunique; ++i) {
+    SGW_ARG(ig_unique[i] >= 1 && ig_unique[i] <= ngc, "ig_unique outside 1..num_g_corr");
+    uniq[ig_unique[i] - 1] = 1;
+  }
+  for (int i = 0; i < nsym; ++i) SGW_ARG(invs[i] >= 1 && invs[i] <= nsym, "invs outside 1..nsym");
+  for (int ig = 0; ig < ngc; ++ig) {
+    if (uniq[ig]) continue;
+    SGW_ARG(sym_ig[ig] >= 1 && sym_ig[ig] <= nsym, "sym_ig of a non-unique G outside 1..nsym");
+    SGW_ARG(sym_friend[ig] >= 1 && sym_friend[ig] <= ngc && uniq[sym_friend[ig] - 1], "sym_friend of a non-unique G is not a unique G");
+    const int ism1 = invs[sym_ig[ig] - 1] - 1;
+    for (int igp = 0; igp < ngc; ++igp) {
+      const int c = gmapsym[igp + (size_t)ngc * ism1];
+      SGW_ARG(c >= 1 && c <= ngc, "gmapsym maps a G vector outside the correlation list (not closed under the small group of q)");
+    }
+  }
+  begin_call(ctx);
+  cudaStream_t st = ctx->stream;
+  cplx *d_in = nullptr, *d_out = nullptr, *d_eig = nullptr;
+  int *d_iu = nullptr, *d_uq = nullptr, *d_sig = nullptr, *d_sfr = nullptr, *d_gm = nullptr, *d_inv = nullptr;
+  const size_t nin = (size_t)ngc * nfs * ngmunique, nout = (size_t)ngc * ngc * nfs;
+  SGW_CHECK(ws(ctx, "uf_in", nin, &d_in));
+  SGW_CHECK(ws(ctx, "uf_out", nout, &d_out));
+  SGW_CHECK(ws(ctx, "uf_iu", (size_t)ngmunique, &d_iu));
+  SGW_CHECK(ws(ctx, "uf_uq", (size_t)ngc, &d_uq));
+  SGW_CHECK(ws(ctx, "uf_sig", (size_t)ngc, &d_sig));
+  SGW_CHECK(ws(ctx, "uf_sfr", (size_t)ngc, &d_sfr));
+  SGW_CHECK(ws(ctx, "uf_gm", (size_t)ngc * nsym, &d_gm));
+  SGW_CHECK(ws(ctx, "uf_eig", (size_t)ngc * nsym, &d_eig));
+  SGW_CHECK(ws(ctx, "uf_inv", (size_t)nsym, &d_inv));
+  SGW_CUDA(cudaMemcpyAsync(d_in, scrcoul_in, sizeof(cplx) * nin, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemsetAsync(d_out, 0, sizeof(cplx) * nout, st));
+  SGW_CUDA(cudaMemcpyAsync(d_iu, ig_unique, sizeof(int) * ngmunique, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_uq, uniq.data(), sizeof(int) * ngc, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_sig, sym_ig, sizeof(int) * ngc, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_sfr, sym_friend, sizeof(int) * ngc, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_gm, gmapsym, sizeof(int) * (size_t)ngc * nsym, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_eig, eigv, sizeof(cplx) * (size_t)ngc * nsym, cudaMemcpyHostToDevice, st));
+  SGW_CUDA(cudaMemcpyAsync(d_inv, invs, sizeof(int) * nsym, cudaMemcpyHostToDevice, st));
+  {
+    dim3 gr((ngc + 127) / 128, nfs, ngmunique);
+    k_unfold<<<gr, 128, 0, st>>>(ngc, nfs, ngmunique, d_iu, d_in, d_out);
+    SGW_LAUNCH_CHECK();
+  }
+  for (int g0 = 0; g0 < ngc; g0 += 65535) {       // grid.z limit
+    const int ng = std::min(65535, ngc - g0);
+    dim3 gr((ngc + 127) / 128, nfs, ng);
+    k_unfold_symm<<<gr, 128, 0, st>>>(ngc, nfs, d_uq + g0, d_sig + g0, d_sfr + g0, d_gm, d_eig, d_inv, d_out + g0);
+    SGW_LAUNCH_CHECK();
+  }
   SGW_CUDA(cudaMemcpyAsync(scrcoul_out, d_out, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, st));
   SGW_CUDA(cudaStreamSynchronize(st));
   end_call(ctx);

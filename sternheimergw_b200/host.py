@@ -356,6 +356,21 @@ class Context:
         self._chk(self._L.sgw_unfold_w(self._h, num_g_corr, nfs, ig_unique.size, _p(ig_unique), _p(scr_in), _p(out)), "unfold_w")
         return out
 
+    def unfold_w_symm(self, num_g_corr, ig_unique, sym_ig, sym_friend, gmapsym, eigv, invs, scrcoul_in):
+        """unfold_w with use_symm = .TRUE. (unfold_w.f90:23-131); the symmetry tables are gmap_sym's / stern_symm's."""
+        scr_in = _c16(scrcoul_in)
+        ig_unique = np.ascontiguousarray(ig_unique, dtype=np.int32)
+        sym_ig = np.ascontiguousarray(sym_ig, dtype=np.int32)
+        sym_friend = np.ascontiguousarray(sym_friend, dtype=np.int32)
+        gm = np.asfortranarray(gmapsym, dtype=np.int32)
+        ev = np.asfortranarray(eigv, dtype=np.complex128)
+        invs = np.ascontiguousarray(invs, dtype=np.int32)
+        nfs = scr_in.shape[1]
+        out = np.zeros((num_g_corr, num_g_corr, nfs), dtype=np.complex128, order="F")
+        self._chk(self._L.sgw_unfold_w_symm(self._h, num_g_corr, nfs, ig_unique.size, _p(ig_unique), invs.size, _p(sym_ig),
+                                            _p(sym_friend), _p(gm), _p(ev), _p(invs), _p(scr_in), _p(out)), "unfold_w_symm")
+        return out
+
     def invert_epsilon(self, scrcoul_g, lgamma=False):
         scr = _c16(scrcoul_g).copy(order="F")
         ngc, _, nfs = scr.shape

@@ -240,3 +240,33 @@ def test_green_function_matches_oracle(ctx, name):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_unfold_w_symmetric_matches_oracle(ctx):
+    """unfold_w with use_symm = .TRUE. (unfold_w.f90:86-131) through sgw_unfold_w_symm against oracle/symm.py (which is pinned by
+    the invariance property in tests/test_oracle_symm.py): the full cubic group, with a fractional translation on some
+    operations so that the eigv phases (gmap_sym.f90:112-134) take part; and the invariant matrix is recovered on the GPU too."""
+    from oracle import symm as osy
+    from symm_util import cubic_group, g_shell_list
+    from sternheimergw_b200 import SgwError
+    ops, invs = cubic_group()
+    mill = g_shell_list(6)
+    ngc, nsym, nfs = len(mill), len(ops), 3
+    rng = np.random.default_rng(4)
+    for frac in (False, True):
+        ftau = np.zeros((nsym, 3), int)
+        if frac:
+            ftau[3] = (6, 0, 12); ftau[17] = (0, 12, 6); ftau[40] = (12, 12, 12)
+        gmapsym, eigv = osy.gmap_sym(mill, ops, ftau, (24, 24, 24))
+        ig_unique, sym_ig, sym_friend = osy.stern_symm(ngc, nsym, gmapsym, invs)
+        scr_in = np.asfortranarray(rng.standard_normal((ngc, nfs, ig_unique.size)) + 1j * rng.standard_normal((ngc, nfs, ig_unique.size)))
+        ref = osy.unfold_w(ngc, nfs, ig_unique, scr_in, use_symm=True, nsymq=nsym, sym_ig=sym_ig, sym_friend=sym_friend,
+                           gmapsym=gmapsym, eigv=eigv, invs=invs)
+        got = ctx.unfold_w_symm(ngc, ig_unique, sym_ig, sym_friend, gmapsym, eigv, invs, scr_in)
+        assert np.abs(got - ref).max() <= 1e-15 * np.abs(ref).max(), (frac, np.abs(got - ref).max())
+        assert np.abs(ref).min() > 0                         # every element of W was filled
+    # a table that maps outside the list is refused, not silently dropped
+    bad = gmapsym.copy()
+    bad[5, 2] = 0
+    with pytest.raises(SgwError):
+        ctx.unfold_w_symm(ngc, ig_unique, sym_ig, sym_friend, bad, eigv, invs, scr_in)
