@@ -165,6 +165,52 @@ def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, i
     return scr_g, (first, last, num_task)
 
 
+def pool_sum_eps(scr_loc: np.ndarray, igstart: int, ig_unique, device=None):
+    """mp_sum(drhoscf, inter_pool_comm) of solve_linter.f90:521 for k-points shared among ranks (the reference's pools).
+
+    Every rank runs ``coulomb`` for the SAME perturbations with only its share of the (k, k+q) pairs installed
+    (``Context.install_system(syn, kpairs=...)``, weights wk unchanged).  The eps column the library returns is affine in the
+    density response, scrcoul = delta - v_c Delta-rho (coulomb.f90:143-157), and Delta-rho is a sum over k, so the allreduce
+    can act on the columns: sum over ranks, then remove the (world - 1) surplus copies of the delta on the perturbation's own G.
+    scr_loc: (ngc, nfs, ntask) of this rank, tasks igstart .. igstart + ntask - 1 of ig_unique (1-based).  Returns the full
+    columns on every rank."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return scr_loc
+    world = dist.get_world_size()
+    dev = _device(dist, device)
+    a = np.asfortranarray(scr_loc, dtype=np.complex128)
+    t = torch.from_numpy(np.ascontiguousarray(a.T).view(np.float64).copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)                       # ncclAllReduce over NVLink on the GPU box
+    out = np.ascontiguousarray(t.cpu().numpy()).view(np.complex128).reshape(a.T.shape).T
+    out = np.asfortranarray(out)
+    for it in range(out.shape[2]):
+        ig = int(ig_unique[igstart - 1 + it])
+        if ig <= out.shape[0]:
+            out[ig - 1, :, it] -= float(world - 1)
+    return out
+
+
+def coulomb_pools(ctx, syn, config, igstart: int, num_g_corr: int, num_task: int, ig_unique, fiu):
+    """`coulomb` with the k-points of `syn` shared among the ranks like the reference's pools (k loop of solve_linter.f90:300,
+    mp_sum over inter_pool_comm at :521): rank r installs its contiguous share of the (k, k+q) pairs (parallel_task's rule),
+    runs the same perturbations and ``pool_sum_eps`` adds the density responses.  A rank without k-points contributes the
+    bare delta.  Returns the full eps columns on every rank."""
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    first, last, num = parallel_task(world, rank, len(syn.kpairs))
+    if num[rank] > 0:
+        ctx.install_system(syn, kpairs=list(range(first - 1, first - 1 + num[rank])))
+        scr = ctx.coulomb(config, igstart, num_g_corr, num_task, ig_unique, fiu)
+    else:
+        scr = np.zeros((num_g_corr, len(fiu), num_task), dtype=np.complex128, order="F")
+        for it in range(num_task):
+            scr[int(ig_unique[igstart - 1 + it]) - 1, :, it] = 1.0
+    return pool_sum_eps(scr, igstart, ig_unique)
+
+
 def root_sum(a: np.ndarray, root: int = 0, device=None):
     """mp_root_sum(comm, root, array) (data/parallel/src/parallel.f90, used at sigma.f90:362,383): element-wise sum
     over ranks, result on ``root`` (None elsewhere).  One reduce of the Sigma(k, omega) block per k-point: the only

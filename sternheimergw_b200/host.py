@@ -233,16 +233,18 @@ class Context:
         self._chk(self._L.sgw_set_dense_operator(self._h, slot, n, _p(A), n), "set_dense_operator")
         self.npw[slot], self.npwx[slot] = n, n
 
-    def install_system(self, syn):
-        """Install a synth.SynthSystem the way the Fortran host would (gwq_setup, solve_linter.f90:300-316)."""
+    def install_system(self, syn, kpairs=None):
+        """Install a synth.SynthSystem the way the Fortran host would (gwq_setup, solve_linter.f90:300-316).
+        kpairs: indices of the (k, k+q) pairs THIS context works on (a pool of the reference, solve_linter.f90:521); default all."""
         self.set_grid(*syn.nr)
         self.set_vloc(syn.vrs)
         self._chk(self._L.sgw_set_system(self._h, syn.omega_cell, syn.tpiba2, syn.ngm,
                                          _p(np.ascontiguousarray(syn.g.T, dtype=np.float64)),
                                          _p(np.ascontiguousarray(syn.nl, dtype=np.int32))), "set_system")
         self.set_q(syn.xq)
-        self._chk(self._L.sgw_set_nksq(self._h, len(syn.kpairs)), "set_nksq")
-        for ik, kp in enumerate(syn.kpairs):
+        pairs = list(syn.kpairs) if kpairs is None else [syn.kpairs[i] for i in kpairs]
+        self._chk(self._L.sgw_set_nksq(self._h, len(pairs)), "set_nksq")
+        for ik, kp in enumerate(pairs):
             kq = kp.kq
             self.set_kpoint(ik, kq.npw, kq.npwx, kq.nl_igk, kq.g2kin, kq.vkb, kq.dion, kq.evq, kq.alpha_pv)
             evc = _c16(kp.evc)

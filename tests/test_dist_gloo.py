@@ -185,3 +185,50 @@ def test_do_stern_frequency_sharded_unfold_and_invert(world, nfs):
     assert res[0][1] is not None and np.allclose(res[0][1], serial, rtol=0, atol=1e-14)
     assert all(res[r][1] is None for r in range(1, world))
     assert res[0][2] == ["gather_s", "gather_w_s", "unfold_invert_s"]
+
+
+def _fake_coulomb_k(kset, igstart, ngc, ntask, ig_unique, nfs):
+    """eps columns of a fake system whose density response is a sum over k-points: scr = delta - sum_k drho_k."""
+    out = np.zeros((ngc, nfs, ntask), dtype=np.complex128, order="F")
+    for t in range(ntask):
+        ig = int(ig_unique[igstart - 1 + t])
+        out[ig - 1, :, t] = 1.0
+        for k in kset:
+            for iw in range(nfs):
+                out[:, iw, t] -= (0.1 * (k + 1) + 0.01j * iw) * np.cos(np.arange(ngc) * (ig + k))
+    return out
+
+
+def _pool_worker(rank, world, port, nk, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sternheimergw_b200.dist import pool_sum_eps
+        from sternheimergw_b200.host import parallel_task
+        first, last, num = parallel_task(world, rank, nk)
+        kset = list(range(first - 1, first - 1 + num[rank]))
+        ig_unique = np.array([2, 5, 1, 4], dtype=np.int32)
+        loc = _fake_coulomb_k(kset, 2, 6, 3, ig_unique, 2)
+        q.put((rank, pool_sum_eps(loc, 2, ig_unique).copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nk", [(2, 5), (3, 4), (3, 2)])
+def test_pool_sum_of_eps_columns_over_k_shards(world, nk):
+    """k-points shared among ranks (pools, solve_linter.f90:521): allreduce of the affine eps columns == all k on one rank,
+    including a rank that holds no k-point at all."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pool_worker, args=(r, world, port, nk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    serial = _fake_coulomb_k(list(range(nk)), 2, 6, 3, np.array([2, 5, 1, 4], dtype=np.int32), 2)
+    for r in range(world):
+        assert np.abs(res[r] - serial).max() < 1e-14

@@ -7,6 +7,8 @@
    rank 0.
 2. sigma_wrapper_k (sigma.f90:319-362): (k, q) configurations dealt to the ranks, Sigma_c = G W of every configuration by
    sgw_sigma_correlation on the rank's GPU, mp_root_sum of Sigma(k, omega) by ONE ncclReduce -- compared with the serial sum.
+3. coulomb_pools: the k-points of one q shared among the ranks (the reference's pools), Delta-rho summed by ncclAllReduce
+   (solve_linter.f90:521) -- compared with all k-points on one rank.
 Prints one JSON record (rank 0)."""
 import json
 import os
@@ -24,7 +26,7 @@ def main():
     import torch
     import torch.distributed as dist
     from sternheimergw_b200 import Context, freqbins, select_solver_type
-    from sternheimergw_b200.dist import do_stern_q, sigma_wrapper_k
+    from sternheimergw_b200.dist import coulomb_pools, do_stern_q, sigma_wrapper_k
     from sternheimergw_b200.host import pade_approx
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -49,6 +51,14 @@ def main():
         scr = ctx.coulomb(cfg, 1, ngc, ngc, igu, fiu)
         ref = ctx.invert_epsilon(ctx.unfold_w(ngc, igu, scr))
         rec["do_stern_q"]["rel_err_vs_single_rank"] = float(np.abs(w - ref).max() / np.abs(ref).max())
+    # ---- 1b. k-points shared among the ranks (pools): ncclAllReduce of the density response (solve_linter.f90:521)
+    t0 = time.perf_counter()
+    scr_pool = coulomb_pools(ctx, syn, cfg, 2, ngc, 5, igu, fiu)
+    rec["coulomb_pools"] = {"k_points": len(syn.kpairs), "seconds": time.perf_counter() - t0}
+    if rank == 0:
+        ctx.install_system(syn)
+        ref = ctx.coulomb(cfg, 2, ngc, 5, igu, fiu)
+        rec["coulomb_pools"]["rel_err_vs_all_k_on_one_rank"] = float(np.abs(scr_pool - ref).max() / np.abs(ref).max())
     # ---- 2. Sigma_c(k, omega) summed over the ranks
     syn1 = synth.preset("si", nk=1)
     ctx.install_system(syn1)
@@ -82,7 +92,8 @@ def main():
         for c in configs:
             one(c, ref)
         rec["sigma_wrapper_k"]["rel_err_vs_serial_sum"] = float(np.abs(sig - ref).max() / np.abs(ref).max())
-        rec["ok"] = bool(rec["do_stern_q"]["rel_err_vs_single_rank"] < 1e-9 and rec["sigma_wrapper_k"]["rel_err_vs_serial_sum"] < 1e-12)
+        rec["ok"] = bool(rec["do_stern_q"]["rel_err_vs_single_rank"] < 1e-9 and rec["sigma_wrapper_k"]["rel_err_vs_serial_sum"] < 1e-12 and
+                         rec["coulomb_pools"]["rel_err_vs_all_k_on_one_rank"] < 1e-9)
         print(json.dumps(rec), flush=True)
     dist.barrier()
     dist.destroy_process_group()
