@@ -1292,10 +1292,10 @@ static int plane_vloc_variant() {
   const char *e = getenv("SGW_PLANE");
   return e ? atoi(e) : 2;
 }
-template <int RX1, int RX2, int RY1, int RY2>
-static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
-                             bool *done) {
-  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1, NT = 384;
+template <int RX1, int RX2, int RY1, int RY2, int NT>
+static int launch_plane_vloc_nt(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
+                                bool *done) {
+  constexpr int NX = RX1 * RX2, NY = RY1 * RY2, PITCH = NX | 1;
   const int ncol_pad = (s.ncol + 7) & ~7, ntab = s.nxs * RY2 * ((RY1 + 7) & ~7);
   const size_t smem = sizeof(cplx) * ((size_t)NY * PITCH + ncol_pad + NX + NY) + sizeof(short) * ntab + sizeof(int) * 2 * NX +
                       sizeof(unsigned) * ((RX2 + 1) & ~1) + 16;
@@ -1313,14 +1313,21 @@ static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, in
     kern<<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
     return SGW_OK;
   };
-  const char *eg = getenv("SGW_PLANE_G");                       // tuning knob: thread groups per CTA (1 | 3 | 6), default 1 (measured: 2.76 / 2.91 / 3.26 ms per 1024 vectors)
-  const int G = eg ? atoi(eg) : 1;
-  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 3, false>));
-  else if (G == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 1, true>));
-  else if (G == 6) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 6, true>));
-  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 3, true>));
+  if (plane_vloc_variant() == 1) SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 1, false>));
+  else SGW_CHECK(go(k_plane_vloc<RX1, RX2, RY1, RY2, NT, 1, true>));
   *done = true;
   return SGW_OK;
+}
+template <int RX1, int RX2, int RY1, int RY2>
+static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
+                             bool *done) {
+  const char *e = getenv("SGW_PLANE_NT");                       // tuning knob: threads per CTA (320 | 352 | 384), default 384
+  const int nt = e ? atoi(e) : 384;
+  if (nt == 256) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 256>(ctx, g, s, nvec, Tin, Tout, active, done);
+  if (nt == 288) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 288>(ctx, g, s, nvec, Tin, Tout, active, done);
+  if (nt == 320) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 320>(ctx, g, s, nvec, Tin, Tout, active, done);
+  if (nt == 352) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 352>(ctx, g, s, nvec, Tin, Tout, active, done);
+  return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 384>(ctx, g, s, nvec, Tin, Tout, active, done);
 }
 
 static int try_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,

@@ -27,8 +27,8 @@ constexpr size_t zgemm_smem() { return (size_t)NSTAGE * (a_tile_elems<A_KCONTIG>
 // C(M x N) = alpha * op(A) * B + beta * C ; op(A) = A^H (A_KCONTIG: A is K x M, column-major) or A (M x K).
 // B is K x N column-major.  blockIdx.z selects a K range (split-K): partial results go to C + z * split_stride.
 // Global -> shared staging is double buffered with cp.async so that the DMMA pipe does not wait on HBM/L2.
-template <bool A_KCONTIG, bool CONJA>
-__global__ void __launch_bounds__(GT, 3) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
+template <bool A_KCONTIG, bool CONJA, int MINB>
+__global__ void __launch_bounds__(GT, MINB) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
                                                const cplx *__restrict__ B, long ldb, cplx *__restrict__ C, long ldc,
                                                cplx alpha, cplx beta, int kchunk, long split_stride,
                                                const int *__restrict__ list, const int *__restrict__ count, int list_mode) {
@@ -154,18 +154,26 @@ static int launch_zgemm(sgw_ctx *ctx, dim3 grid, int M, int N, int K, const cplx
   constexpr size_t smem = zgemm_smem<A_KCONTIG>();
   SGW_CHECK(zgemm_init(ctx));
   if (!list) list_mode &= 4;
-  k_zgemm<A_KCONTIG, CONJA><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, list, count,
-                                                             list_mode);
+  static int minb = -1;                                         // SGW_GEMM_MINB: resident CTAs per SM the register allocation must allow (2 | 3)
+  if (minb < 0) { const char *e = getenv("SGW_GEMM_MINB"); minb = e ? atoi(e) : 3; }
+  if (minb == 2)
+    k_zgemm<A_KCONTIG, CONJA, 2><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, list,
+                                                                  count, list_mode);
+  else
+    k_zgemm<A_KCONTIG, CONJA, 3><<<grid, GT, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, kchunk, split_stride, list,
+                                                                  count, list_mode);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
 
 static int zgemm_init(sgw_ctx *ctx) {
   if (ctx->gemm_cta_per_sm > 0) return SGW_OK;
-  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
-  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zgemm<true, true>, GT, zgemm_smem<true>()) != cudaSuccess || n < 1) n = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zgemm<true, true, 3>, GT, zgemm_smem<true>()) != cudaSuccess || n < 1) n = 1;
   ctx->gemm_cta_per_sm = n;
   return SGW_OK;
 }
