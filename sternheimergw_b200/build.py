@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsgw_b200.so"
-SOURCES = ["api.cu", "fft.cu", "gemm.cu", "operator.cu", "bicgstab.cu", "subspace.cu", "coulomb.cu", "sigma.cu"]
+SOURCES = ["api.cu", "fft.cu", "gemm.cu", "operator.cu", "bicgstab.cu", "subspace.cu", "coulomb.cu", "invert.cu", "sigma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]

@@ -3,7 +3,7 @@
 //   coulomb        phys/coul/src/coulomb.f90:29-176                        -> sgw_coulomb
 //   coulomb_q0G0   phys/coul/src/coulomb_q0G0.f90:31-158                   -> sgw_coulomb_q0G0
 //   unfold_w       algo/symmetry/src/unfold_w.f90:84 (identity symmetry)   -> sgw_unfold_w
-//   invert_epsilon phys/coul/src/invert_epsilon.f90:23-90                  -> sgw_invert_epsilon
+//   invert_epsilon phys/coul/src/invert_epsilon.f90:23-90                  -> sgw_invert_epsilon (invert.cu)
 //   green_function phys/green/src/green.f90:105-226                        -> sgw_green_function
 // One call handles a whole block of perturbations: dV_bare psi (dvqpsi_us.f90:99-130), -P_c^+ ([QE] orthogonalize),
 // the multishift solves batched over perturbations x bands, the +-omega average (solve_linter.f90:464-480),
@@ -129,103 +129,6 @@ __global__ void k_unfold_symm(int ngc, int nfs, const int *__restrict__ is_uniqu
   const int col = gmapsym[igp + (long)ngc * ism1] - 1;
   const cplx phase = cmul(eigv[fr + (long)ngc * isym], cconj(eigv[igp + (long)ngc * isym]));
   out[(long)ig + (long)ngc * (col + (long)ngc * iw)] = cmul(out[(long)fr + (long)ngc * (igp + (long)ngc * iw)], phase);
-}
-
-// ---------------------------------------------------------------- invert_epsilon: batched in-place Gauss-Jordan
-// (ZGETRF/ZGETRI semantics: partial pivoting with the IZAMAX |re|+|im| criterion), one matrix per frequency.
-__global__ void k_eps_wings(int n, cplx *__restrict__ a) {          // invert_epsilon.f90:46-56, :72-81
-  cplx *m = a + (long)blockIdx.y * n * n;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || i == 0) return;
-  m[i] = cmake(0.0, 0.0);
-  m[(long)n * i] = cmake(0.0, 0.0);
-}
-__global__ void k_eps_diag(int n, cplx *__restrict__ a) {           // :84-88
-  cplx *m = a + (long)blockIdx.y * n * n;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  m[(long)i + (long)n * i].x -= 1.0;
-}
-__global__ void __launch_bounds__(1024) k_gj_pivot(int n, int k, cplx *__restrict__ a, int *__restrict__ piv,
-                                                    cplx *__restrict__ colk, int *__restrict__ info) {
-  cplx *m = a + (long)blockIdx.x * n * n;
-  int *pv = piv + (long)blockIdx.x * n;
-  cplx *ck = colk + (long)blockIdx.x * n;
-  __shared__ double sval[32];
-  __shared__ int sidx[32];
-  __shared__ int s_p;
-  __shared__ cplx s_inv;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
-  double best = -1.0;
-  int bi = n;
-  for (int i = k + tid; i < n; i += blockDim.x) {
-    const cplx v = m[(long)i + (long)n * k];
-    const double s = fabs(v.x) + fabs(v.y);
-    if (s > best) { best = s; bi = i; }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-  }
-  if (lane == 0) { sval[w] = best; sidx[w] = bi; }
-  __syncthreads();
-  if (w == 0) {
-    best = lane < nw ? sval[lane] : -1.0;
-    bi = lane < nw ? sidx[lane] : n;
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) {
-      s_p = bi;
-      pv[k] = bi;
-      if (!(best > 0.0)) { atomicMax(info, k + 1); s_inv = cmake(0.0, 0.0); }
-      else s_inv = cdiv(cmake(1.0, 0.0), m[(long)bi + (long)n * k]);
-    }
-  }
-  __syncthreads();
-  const int p = s_p;
-  const cplx inv = s_inv;
-  for (int j = tid; j < n; j += blockDim.x) {                 // swap rows k <-> p, scale row k
-    cplx akj = m[(long)p + (long)n * j];
-    if (p != k) m[(long)p + (long)n * j] = m[(long)k + (long)n * j];
-    m[(long)k + (long)n * j] = (j == k) ? inv : cmul(akj, inv);
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {                 // multipliers; column k of the other rows restarts at 0
-    if (i == k) { ck[i] = cmake(0.0, 0.0); continue; }
-    ck[i] = m[(long)i + (long)n * k];
-    m[(long)i + (long)n * k] = cmake(0.0, 0.0);
-  }
-}
-__global__ void __launch_bounds__(256) k_gj_elim(int n, int k, cplx *__restrict__ a, const cplx *__restrict__ colk) {
-  cplx *m = a + (long)blockIdx.z * n * n;
-  const cplx *ck = colk + (long)blockIdx.z * n;
-  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int j0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * 8;
-  if (i >= n || i == k) return;
-  const cplx f = cneg(ck[i]);
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const int j = j0 + jj;
-    if (j < n) m[(long)i + (long)n * j] = cfma(f, m[(long)k + (long)n * j], m[(long)i + (long)n * j]);
-  }
-}
-__global__ void k_gj_colswap(int n, cplx *__restrict__ a, const int *__restrict__ piv) {
-  cplx *m = a + (long)blockIdx.y * n * n;
-  const int *pv = piv + (long)blockIdx.y * n;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int k = n - 1; k >= 0; --k) {
-    const int p = pv[k];
-    if (p != k) {
-      const cplx t = m[(long)i + (long)n * k];
-      m[(long)i + (long)n * k] = m[(long)i + (long)n * p];
-      m[(long)i + (long)n * p] = t;
-    }
-  }
 }
 
 // ---------------------------------------------------------------- green_function helpers
@@ -1240,48 +1143,6 @@ int sgw_unfold_w_symm(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32
   SGW_CUDA(cudaMemcpyAsync(scrcoul_out, d_out, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, st));
   SGW_CUDA(cudaStreamSynchronize(st));
   end_call(ctx);
-  return SGW_OK;
-}
-
-int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrcoul_g, int lgamma) {
-  if (!ctx) return SGW_E_ARG;
-  cudaSetDevice(ctx->device);
-  SGW_ARG(ngc > 0 && nfs > 0 && scrcoul_g, "bad argument");
-  begin_call(ctx);
-  cudaStream_t st = ctx->stream;
-  cplx *d_a = nullptr, *d_colk = nullptr;
-  int *d_piv = nullptr, *d_info = nullptr;
-  const size_t tot = (size_t)ngc * ngc * nfs;
-  SGW_CHECK(ws(ctx, "ie_a", tot, &d_a));
-  SGW_CHECK(ws(ctx, "ie_colk", (size_t)ngc * nfs, &d_colk));
-  SGW_CHECK(ws(ctx, "ie_piv", (size_t)ngc * nfs + 1, &d_piv));
-  d_info = d_piv + (size_t)ngc * nfs;
-  SGW_CUDA(cudaMemcpyAsync(d_a, scrcoul_g, sizeof(cplx) * tot, cudaMemcpyHostToDevice, st));
-  SGW_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
-  const dim3 g1((ngc + 127) / 128, nfs);
-  if (lgamma) { k_eps_wings<<<g1, 128, 0, st>>>(ngc, d_a); SGW_LAUNCH_CHECK(); }            // :46-56
-  const int pt = ngc >= 1024 ? 1024 : (ngc >= 256 ? 256 : 64);
-  const dim3 ge((ngc + 63) / 64, (ngc + 31) / 32, nfs);
-  for (int k = 0; k < ngc; ++k) {                                                           // :59-66
-    k_gj_pivot<<<nfs, pt, 0, st>>>(ngc, k, d_a, d_piv, d_colk, d_info);
-    SGW_LAUNCH_CHECK();
-    k_gj_elim<<<ge, 256, 0, st>>>(ngc, k, d_a, d_colk);
-    SGW_LAUNCH_CHECK();
-  }
-  k_gj_colswap<<<g1, 128, 0, st>>>(ngc, d_a, d_piv);
-  SGW_LAUNCH_CHECK();
-  if (lgamma) { k_eps_wings<<<g1, 128, 0, st>>>(ngc, d_a); SGW_LAUNCH_CHECK(); }            // :72-81
-  k_eps_diag<<<g1, 128, 0, st>>>(ngc, d_a);                                                 // :84-88
-  SGW_LAUNCH_CHECK();
-  int info = 0;
-  SGW_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d_a, sizeof(cplx) * tot, cudaMemcpyDeviceToHost, st));
-  SGW_CUDA(cudaStreamSynchronize(st));
-  end_call(ctx);
-  if (info != 0) {                                                                          // :61,:64 errore
-    ctx->err = "invert_epsilon: matrix is singular (zero pivot in column " + std::to_string(info) + ")";
-    return SGW_E_ARG;
-  }
   return SGW_OK;
 }
 

@@ -27,11 +27,14 @@ constexpr size_t zgemm_smem() { return (size_t)NSTAGE * (a_tile_elems<A_KCONTIG>
 // C(M x N) = alpha * op(A) * B + beta * C ; op(A) = A^H (A_KCONTIG: A is K x M, column-major) or A (M x K).
 // B is K x N column-major.  blockIdx.z selects a K range (split-K): partial results go to C + z * split_stride.
 // Global -> shared staging is double buffered with cp.async so that the DMMA pipe does not wait on HBM/L2.
-template <bool A_KCONTIG, bool CONJA, int MINB>
+// BATCH: blockIdx.z selects one of several independent products instead (A += z * bsA, B += z * bsB, C += z * split_stride,
+// the whole K range per CTA); used by the blocked inversion of invert.cu.
+template <bool A_KCONTIG, bool CONJA, int MINB, bool BATCH = false>
 __global__ void __launch_bounds__(GT, MINB) k_zgemm(int M, int N, int K, const cplx *__restrict__ A, long lda,
                                                const cplx *__restrict__ B, long ldb, cplx *__restrict__ C, long ldc,
                                                cplx alpha, cplx beta, int kchunk, long split_stride,
-                                               const int *__restrict__ list, const int *__restrict__ count, int list_mode) {
+                                               const int *__restrict__ list, const int *__restrict__ count, int list_mode,
+                                               long bsA = 0, long bsB = 0) {
   // Compacted batches: with `list` the problem has *count columns; list_mode bit 0: column j of B is B's column list[j]
   // (gather), list_mode bit 1: column j of C is C's column list[j] (scatter); both bits may be set.  Tiles beyond the
   // count exit at once, so a batch in which most right-hand sides have converged costs what its active columns cost.
@@ -43,7 +46,8 @@ __global__ void __launch_bounds__(GT, MINB) k_zgemm(int M, int N, int K, const c
     N = min(N, *count);
     if (n0 >= N) return;
   }
-  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  const int kbeg = BATCH ? 0 : blockIdx.z * kchunk, kend = BATCH ? K : min(K, kbeg + kchunk);
+  if (BATCH) { A += (long)blockIdx.z * bsA; B += (long)blockIdx.z * bsB; }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int ASZ = a_tile_elems<A_KCONTIG>();
   extern __shared__ cplx gsm[];
@@ -172,9 +176,25 @@ static int zgemm_init(sgw_ctx *ctx) {
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zgemm<true, true, 3>, GT, zgemm_smem<true>()) != cudaSuccess || n < 1) n = 1;
   ctx->gemm_cta_per_sm = n;
+  return SGW_OK;
+}
+
+// nbatch independent products C_z = alpha A_z B_z + beta C_z (A_z is M x K, column-major) over the columns list[0 .. *count)
+// of B_z and C_z (nullptr list: all N columns)
+int gemm_n_n_batched(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, long bsA, const cplx *B, long ldb,
+                     long bsB, cplx beta, cplx *C, long ldc, long bsC, int nbatch, const int *list, const int *count) {
+  if (m <= 0 || n <= 0 || nbatch <= 0) return SGW_OK;
+  SGW_ARG(nbatch <= 65535, "gemm_n_n_batched: more than 65535 matrices");
+  constexpr size_t smem = zgemm_smem<false>();
+  SGW_CHECK(zgemm_init(ctx));
+  dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, nbatch);
+  k_zgemm<false, false, 3, true><<<grid, GT, smem, ctx->stream>>>(m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k, bsC, list, count,
+                                                                    list ? 3 : 0, bsA, bsB);
+  SGW_LAUNCH_CHECK();
   return SGW_OK;
 }
 

@@ -305,6 +305,8 @@ int nonlocal_apply(sgw_ctx *ctx, const KSlot &k, double alpha_pv, int nvec, cons
 int gemm_ch_n(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, const cplx *B, long ldb, cplx *C, long ldc);
 int gemm_n_n(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, const cplx *B, long ldb, cplx beta,
              cplx *C, long ldc);
+int gemm_n_n_batched(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, long bsA, const cplx *B, long ldb,
+                     long bsB, cplx beta, cplx *C, long ldc, long bsC, int nbatch, const int *list, const int *count);
 int dense_apply(sgw_ctx *ctx, const KSlot &k, int nvec, const cplx *psi, long ldpsi, const cplx *sigma, long sigma_stride,
                 cplx *out, long ldout, const int *active);
 

@@ -202,6 +202,29 @@ def test_unfold_and_invert_epsilon(ctx, ngc, nfs):
         assert np.abs(inv[:, :, iw] + np.eye(ngc) - np.linalg.inv(a[:, :, iw])).max() < 1e-10
 
 
+@pytest.mark.parametrize("n,nfs,env", [
+    (300, 3, {}),                                              # default plan: NB = 64, SB = 16, sub-panels in shared memory
+    (333, 2, {"SGW_GJ_NB": "48", "SGW_GJ_SB": "4"}),           # ragged panels and sub-panels
+    (150, 2, {"SGW_GJ_PANEL": "global", "SGW_GJ_NB": "32"}),   # sub-panel steps in global memory
+    (97, 2, {"SGW_GJ_UNBLOCKED": "1"}),                        # a single panel
+    (1100, 2, {}),                                             # SB = 8
+])
+def test_invert_epsilon_blocked(ctx, monkeypatch, n, nfs, env):
+    """The blocked Gauss-Jordan of csrc/invert.cu against LAPACK (numpy), which is what invert_epsilon.f90:59-66 calls;
+    rows are scaled so that partial pivoting interchanges rows in almost every step."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n, nfs)) + 1j * rng.standard_normal((n, n, nfs))
+    a[np.arange(n), np.arange(n), :] += 2.0 * np.sqrt(n) * (1.0 + np.abs(rng.standard_normal((n, 1))))
+    a = np.asfortranarray(a[rng.permutation(n)])
+    inv = ctx.invert_epsilon(a)
+    for iw in range(nfs):
+        ref = np.linalg.inv(a[:, :, iw])
+        err = np.abs(inv[:, :, iw] + np.eye(n) - ref).max() / np.abs(ref).max()
+        assert err < 1e-11, (iw, err)
+
+
 def test_invert_epsilon_singular_is_loud(ctx):
     from sternheimergw_b200 import SgwError
     a = np.zeros((4, 4, 1), complex)
