@@ -168,6 +168,21 @@ void begin_call(sgw_ctx *ctx) {
   cudaEventRecord(ctx->ev0, ctx->stream);
 }
 
+void lanes_destroy(sgw_ctx *ctx) {
+  for (sgw_ctx *l : ctx->lanes) {
+    cudaStreamSynchronize(l->own_stream);
+    ws_free_all(l);
+    cudaEventDestroy(l->ev0); cudaEventDestroy(l->ev1); cudaEventDestroy(l->ev2); cudaEventDestroy(l->ev3);
+    for (auto &r : l->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : l->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) if (l->ev_iter[i]) cudaEventDestroy(l->ev_iter[i]);
+    if (l->h_flags) cudaFreeHost(l->h_flags);
+    cudaStreamDestroy(l->own_stream);
+    delete l;                                   // the tables it points to belong to the parent
+  }
+  ctx->lanes.clear();
+}
+
 void end_call(sgw_ctx *ctx) {
   cudaEventRecord(ctx->ev1, ctx->stream);
   cudaEventSynchronize(ctx->ev1);
@@ -207,6 +222,7 @@ int sgw_destroy(sgw_ctx *ctx) {
   if (!ctx) return SGW_E_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  lanes_destroy(ctx);
   for (auto &k : ctx->slots) free_slot(k);
   for (auto &p : ctx->pairs) free_pair(p);
   for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
@@ -258,6 +274,7 @@ int sgw_release_workspace(sgw_ctx *ctx) {
   cudaSetDevice(ctx->device);
   SGW_CUDA(cudaStreamSynchronize(ctx->stream));
   ws_free_all(ctx);
+  lanes_destroy(ctx);
   dev_pool_trim();
   return SGW_OK;
 }

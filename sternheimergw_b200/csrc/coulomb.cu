@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 using namespace sgw;
 
@@ -277,6 +278,87 @@ static int rho_grid_prepare(sgw_ctx *ctx, int ngc, const Sphere &rho_fine, bool 
   return SGW_OK;
 }
 
+// ---- k-point lanes (see drho_block) ---------------------------------------------------------------------------
+__global__ void k_vadd(long n, cplx *__restrict__ a, const cplx *__restrict__ b) {            // a += b
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] = cadd(a[i], b[i]);
+}
+
+// how many k-points of one sgw_coulomb block run concurrently: only where one k-point cannot fill the GPU (few, short vectors)
+// and where a workspace per lane is cheap.  SGW_KLANES overrides (1 = off).
+static int klanes_wanted(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, int nshift, int nfreq, size_t trho_bytes) {
+  const size_t nk = ctx->pairs.size();
+  if (nk < 2 || ctx->profiling || ctx->is_lane) return 1;      // per-class event timing assumes one stream
+  const char *env = getenv("SGW_KLANES");
+  const int forced = env ? atoi(env) : 0;
+  int want = forced > 0 ? forced : 8;
+  want = (int)std::min<size_t>((size_t)want, nk);
+  if (want <= 1) return 1;
+  size_t work = 0, bytes = 0;
+  const size_t nnr = (size_t)ctx->nr1 * ctx->nr2 * ctx->nr3;
+  for (auto &kp : ctx->pairs) {
+    if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size() || !ctx->slots[kp.slot].set) return 1;
+    const KSlot &ks = ctx->slots[kp.slot];
+    const size_t nrhs = (size_t)np * ks.nbnd;
+    work = std::max(work, nrhs * (size_t)ks.npwx);
+    size_t b = nrhs * solver_bytes_per_rhs(ctx, ks, cfg->bicg_lmax, nshift);
+    if (cfg->npriority > 0 && cfg->priority[0] == 3) b += nrhs * (size_t)ks.npwx * sizeof(cplx) * 2 * 128;   // subspace bases
+    b += 4 * (size_t)ks.nbnd * nnr * sizeof(cplx) + trho_bytes * 2;
+    bytes = std::max(bytes, b);
+  }
+  if (forced <= 0 && work > ((size_t)1 << 22)) return 1;      // big batches fill the machine on their own
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  size_t held = 0;
+  for (sgw_ctx *l : ctx->lanes) for (auto &kv : l->ws.bufs) held += kv.second.second;
+  while (want > 1 && (double)bytes * (want - 1) > 0.5 * (double)(free_b + held)) --want;
+  return want;
+}
+
+// make lanes 1 .. nlanes-1 exist and mirror the parent's tables (lane 0 is the parent itself)
+static int klanes_prepare(sgw_ctx *ctx, int nlanes) {
+  while ((int)ctx->lanes.size() < nlanes - 1) {
+    sgw_ctx *l = new sgw_ctx();
+    l->device = ctx->device;
+    l->is_lane = true;
+    if (cudaStreamCreateWithFlags(&l->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; ctx->err = "lane stream"; return SGW_E_CUDA; }
+    cudaEventCreate(&l->ev0); cudaEventCreate(&l->ev1); cudaEventCreate(&l->ev2); cudaEventCreate(&l->ev3);
+    ctx->lanes.push_back(l);
+  }
+  for (int i = 0; i < nlanes - 1; ++i) {
+    sgw_ctx *l = ctx->lanes[i];
+    // what the lane owns survives the copy of the parent's state
+    cudaStream_t st = l->own_stream;
+    Workspace w = std::move(l->ws);
+    cudaEvent_t e0 = l->ev0, e1 = l->ev1, e2 = l->ev2, e3 = l->ev3, ei0 = l->ev_iter[0], ei1 = l->ev_iter[1];
+    int *hf = l->h_flags;
+    std::vector<cudaEvent_t> pool = std::move(l->ev_pool);
+    *l = *ctx;
+    l->is_lane = true;
+    l->lanes.clear();
+    l->stream = l->own_stream = st;
+    l->ws = std::move(w);
+    l->ev0 = e0; l->ev1 = e1; l->ev2 = e2; l->ev3 = e3; l->ev_iter[0] = ei0; l->ev_iter[1] = ei1;
+    l->h_flags = hf;
+    l->ev_pool = std::move(pool);
+    l->prof_recs.clear();
+    l->profiling = false;
+    l->err.clear();
+    l->launches = 0;
+    memset(&l->stats, 0, sizeof(l->stats));
+  }
+  return SGW_OK;
+}
+
+static void klane_merge(sgw_ctx *ctx, sgw_ctx *l) {
+  ctx->launches += l->launches;
+  ctx->stats.n_linear_op += l->stats.n_linear_op;
+  ctx->stats.n_fallback += l->stats.n_fallback;
+  ctx->stats.n_outer_max = std::max(ctx->stats.n_outer_max, l->stats.n_outer_max);
+  ctx->stats.ms_solver += l->stats.ms_solver;           // summed over lanes: concurrent lanes overlap in wall time
+  l->launches = 0;
+  memset(&l->stats, 0, sizeof(l->stats));
+}
+
 // Delta-rho of `np` perturbations whose dvbare(r) sit in d_field (permuted order): d_drhoG[(p*nfreq+ifreq)*rho.npw + pos]
 // = fwfft(drho)(G) in the column order of `rho`, summed over the k-points of this pool.
 static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cplx *d_field, const FreqList &fl,
@@ -291,8 +373,11 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
   const long rnnr = coarse ? (long)ctx->rho_grid.n1 * ctx->rho_grid.n2 * ctx->rho_grid.n3 : nnr;
   cplx *Trho = nullptr;
   SGW_CHECK(ws(ctx, "co_Trho", (size_t)npf * rnz * rho.ncol, &Trho));
-  cudaStream_t st = ctx->stream;
-  for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {                                     // solve_linter.f90:288
+  // one k-point (solve_linter.f90:288 loop body) on the context `c` (the caller's, or one of its lanes): accumulates into Tacc
+  auto one_k = [&](sgw_ctx *ctx, size_t ik, cplx *Tacc, bool accumulate, int *ierr_any) -> int {
+    cudaStream_t st = ctx->stream;
+    const FftGrid *rg = coarse ? &ctx->rho_grid : nullptr;
+    const Sphere &rho = coarse ? ctx->rho_sph_c : rho_fine;
     const KPair &kp = ctx->pairs[ik];
     if (!kp.set || kp.slot < 0 || kp.slot >= (int)ctx->slots.size() || !ctx->slots[kp.slot].set) {
       ctx->err = "k-point pair not set (sgw_set_kpair / sgw_set_kpoint)";
@@ -382,7 +467,52 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
       const int c = std::min(pfc, npf - pf0);
       const cplx *davg = davg_all + (size_t)pf0 * nocc * n;
       SGW_CHECK(fft_zpass_g2r(ctx, sq, c * nocc, davg, n, Td, nullptr, rg));
-      SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Trho + (size_t)pf0 * rnz * rho.ncol, ik > 0, rg, psir_t));
+      SGW_CHECK(fft_plane_rho(ctx, sq, rho, c, nocc, Td, psir_rho, wgt, Tacc + (size_t)pf0 * rnz * rho.ncol, accumulate, rg, psir_t));
+    }
+    return SGW_OK;
+  };
+  cudaStream_t st = ctx->stream;
+  const size_t nk = ctx->pairs.size();
+  const int nlanes = klanes_wanted(ctx, cfg, np, nshift, nfreq, (size_t)npf * rnz * rho.ncol * sizeof(cplx));
+  if (nlanes <= 1) {
+    for (size_t ik = 0; ik < nk; ++ik) SGW_CHECK(one_k(ctx, ik, Trho, ik > 0, ierr_any));          // solve_linter.f90:288
+  } else {
+    // Small systems (a few hundred plane waves, a handful of bands): the kernels of one k-point fill a fraction of the GPU and
+    // the solve is a chain of short dependent launches.  The k-points of the loop :288 are independent until the Delta-rho
+    // sum, so they run concurrently: lane l (own stream, own workspace, own host thread) takes k = l, l + L, ... and
+    // accumulates its own Delta-rho; the lanes' sums are added in lane order afterwards (deterministic).
+    SGW_CUDA(cudaStreamSynchronize(st));                                                    // d_field is ready
+    SGW_CHECK(klanes_prepare(ctx, nlanes));
+    std::vector<int> rcs(nlanes, SGW_OK), ierrs(nlanes, 0);
+    std::vector<cplx *> Tl(nlanes, nullptr);
+    Tl[0] = Trho;
+    for (int l = 1; l < nlanes; ++l) SGW_CHECK(ws(ctx->lanes[l - 1], "co_Trho", (size_t)npf * rnz * rho.ncol, &Tl[l]));
+    auto run_lane = [&](int l) {
+      sgw_ctx *c = l == 0 ? ctx : ctx->lanes[l - 1];
+      cudaSetDevice(c->device);
+      bool first = true;
+      for (size_t ik = l; ik < nk && rcs[l] == SGW_OK; ik += nlanes) {
+        rcs[l] = one_k(c, ik, Tl[l], !first, &ierrs[l]);
+        first = false;
+      }
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess && rcs[l] == SGW_OK) { c->err = "lane stream failed"; rcs[l] = SGW_E_CUDA; }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int l = 1; l < nlanes; ++l) th.emplace_back(run_lane, l);
+      run_lane(0);
+      for (auto &t : th) t.join();
+    }
+    for (int l = 0; l < nlanes; ++l) {
+      if (l > 0) klane_merge(ctx, ctx->lanes[l - 1]);
+      if (ierrs[l]) *ierr_any = ierrs[l];
+    }
+    for (int l = 0; l < nlanes; ++l)
+      if (rcs[l] != SGW_OK) { if (l > 0) ctx->err = ctx->lanes[l - 1]->err; return rcs[l]; }
+    const long tot = (long)npf * rnz * rho.ncol;
+    for (int l = 1; l < nlanes; ++l) {
+      k_vadd<<<(unsigned)std::min<long>((tot + 255) / 256, 65535L * 16), 256, 0, st>>>(tot, Trho, Tl[l]);
+      SGW_LAUNCH_CHECK();
     }
   }
   // mp_sum over pools (:521) is the caller's (one pool per context); fwfft of drho on the density sphere

@@ -27,20 +27,23 @@ struct Plan1D {
 
 inline bool radix_ok(int r) {
   switch (r) {
-    case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 9: case 10: case 12: case 15: case 16: return true;
+    case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 9: case 10: case 12: case 15: case 16:
+    case 18: case 20: case 24: case 25: case 27: case 30: case 32: return true;
     default: return false;
   }
 }
 
-// balanced two-radix plan; returns false if n is not representable (n <= 256, factors 2,3,5)
+// balanced two-radix plan; returns false if n is not representable.  Every n = 2^a 3^b 5^c <= 960 is (radices up to 32);
+// the radices above 16 only serve lengths that have no plan without them: their codelets need more registers than the
+// kernels' launch bounds leave, so they are correct but slower per point.
 inline bool make_plan(int n, Plan1D* p) {
   p->n = n;
   if (n <= 16 && radix_ok(n)) { p->r1 = n; p->r2 = 1; return true; }
   int best = -1, bestmax = 1 << 30;
-  for (int r1 = 2; r1 <= 16; ++r1) {
+  for (int r1 = 2; r1 <= 32; ++r1) {
     if (n % r1 || !radix_ok(r1)) continue;
     int r2 = n / r1;
-    if (r2 > 16 || !radix_ok(r2) || r2 < 2) continue;
+    if (r2 > 32 || !radix_ok(r2) || r2 < 2) continue;
     int m = r1 > r2 ? r1 : r2;
     if (m < bestmax || (m == bestmax && r1 < r2)) { bestmax = m; best = r1; }
   }
@@ -167,52 +170,77 @@ SGW_HD void stage_mid(double2* x, int nlines, int ls, int r_other, const double2
   }
 }
 
-// runtime radix dispatch (uniform across the block)
-template <int DIR>
+// runtime radix dispatch (uniform across the block).  The radices above 16 live in their own functions: their codelets
+// spill under the kernels' register caps, and keeping them out of the common dispatchers leaves those unchanged.
 #ifdef __CUDACC__
-__host__ __device__ __noinline__
+#define SGW_DISPATCH __host__ __device__ __noinline__
 #else
-inline
+#define SGW_DISPATCH inline
 #endif
-void run_strided(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
-                 const double2* tw, bool do_tw, int tid, int nthreads) {
+
+template <int DIR>
+SGW_DISPATCH void run_strided_big(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                                  const double2* tw, bool do_tw, int tid, int nthreads) {
   switch (R) {
 #define SGW_CASE(r) case r: stage_strided<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
-    SGW_FOR_EACH_RADIX(SGW_CASE)
+    SGW_FOR_EACH_BIG_RADIX(SGW_CASE)
 #undef SGW_CASE
     default: break;
   }
 }
 
 template <int DIR>
-#ifdef __CUDACC__
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-void run_contig(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
-                const double2* tw, bool do_tw, int tid, int nthreads) {
+SGW_DISPATCH void run_strided(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                              const double2* tw, bool do_tw, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_strided<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+    SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: run_strided_big<DIR>(R, x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+  }
+}
+
+template <int DIR>
+SGW_DISPATCH void run_contig_big(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                                 const double2* tw, bool do_tw, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_contig<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+    SGW_FOR_EACH_BIG_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
+}
+
+template <int DIR>
+SGW_DISPATCH void run_contig(int R, double2* x, int nlines, const int* line_ids, int ls, int es, int r_other,
+                             const double2* tw, bool do_tw, int tid, int nthreads) {
   switch (R) {
 #define SGW_CASE(r) case r: stage_contig<r, DIR>(x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
     SGW_FOR_EACH_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: run_contig_big<DIR>(R, x, nlines, line_ids, ls, es, r_other, tw, do_tw, tid, nthreads); break;
+  }
+}
+
+template <bool CPLX>
+SGW_DISPATCH void run_mid_big(int R, double2* x, int nlines, int ls, int r_other, const double2* tw, bool do_tw, const double* v,
+                              const double2* f, int vls, int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_mid<r, CPLX>(x, nlines, ls, r_other, tw, do_tw, v, f, vls, tid, nthreads); break;
+    SGW_FOR_EACH_BIG_RADIX(SGW_CASE)
 #undef SGW_CASE
     default: break;
   }
 }
 
 template <bool CPLX>
-#ifdef __CUDACC__
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-void run_mid(int R, double2* x, int nlines, int ls, int r_other, const double2* tw, bool do_tw, const double* v,
-             const double2* f, int vls, int tid, int nthreads) {
+SGW_DISPATCH void run_mid(int R, double2* x, int nlines, int ls, int r_other, const double2* tw, bool do_tw, const double* v,
+                          const double2* f, int vls, int tid, int nthreads) {
   switch (R) {
 #define SGW_CASE(r) case r: stage_mid<r, CPLX>(x, nlines, ls, r_other, tw, do_tw, v, f, vls, tid, nthreads); break;
     SGW_FOR_EACH_RADIX(SGW_CASE)
 #undef SGW_CASE
-    default: break;
+    default: run_mid_big<CPLX>(R, x, nlines, ls, r_other, tw, do_tw, v, f, vls, tid, nthreads); break;
   }
 }
 

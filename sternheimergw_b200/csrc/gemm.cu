@@ -177,6 +177,7 @@ static int zgemm_init(sgw_ctx *ctx) {
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
   SGW_CUDA(cudaFuncSetAttribute(k_zgemm<false, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<false>()));
+  SGW_CUDA(cudaFuncSetAttribute(k_zgemm<true, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zgemm_smem<true>()));
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_zgemm<true, true, 3>, GT, zgemm_smem<true>()) != cudaSuccess || n < 1) n = 1;
   ctx->gemm_cta_per_sm = n;
@@ -194,6 +195,20 @@ int gemm_n_n_batched(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *
   dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, nbatch);
   k_zgemm<false, false, 3, true><<<grid, GT, smem, ctx->stream>>>(m, n, k, A, lda, B, ldb, C, ldc, alpha, beta, k, bsC, list, count,
                                                                     list ? 3 : 0, bsA, bsB);
+  SGW_LAUNCH_CHECK();
+  return SGW_OK;
+}
+
+// nbatch independent products C_z = A_z^H B_z (A_z is K x M, B_z is K x N, column-major)
+int gemm_ch_n_batched(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, long bsA, const cplx *B, long ldb, long bsB, cplx *C,
+                      long ldc, long bsC, int nbatch) {
+  if (m <= 0 || n <= 0 || nbatch <= 0) return SGW_OK;
+  SGW_ARG(nbatch <= 65535, "gemm_ch_n_batched: more than 65535 matrices");
+  constexpr size_t smem = zgemm_smem<true>();
+  SGW_CHECK(zgemm_init(ctx));
+  dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, nbatch);
+  k_zgemm<true, true, 3, true><<<grid, GT, smem, ctx->stream>>>(m, n, k, A, lda, B, ldb, C, ldc, cmake(1, 0), cmake(0, 0), k, bsC, nullptr,
+                                                                  nullptr, 0, bsA, bsB);
   SGW_LAUNCH_CHECK();
   return SGW_OK;
 }

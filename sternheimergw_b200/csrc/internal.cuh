@@ -189,6 +189,10 @@ struct sgw_ctx {
   void *msg_user = nullptr;
   sgw::CorrGrid corr;                            // sigma.cu
   bool gw_attr_set = false;
+  // k-point lanes of sgw_coulomb (coulomb.cu: klanes_prepare): shallow copies of this context that share its device tables
+  // but own a stream, a workspace, events and statistics, so that independent k-points run concurrently on small systems
+  std::vector<sgw_ctx *> lanes;
+  bool is_lane = false;
 };
 
 namespace sgw {
@@ -262,6 +266,7 @@ struct ProfScope {
 };
 void begin_call(sgw_ctx *ctx);
 void end_call(sgw_ctx *ctx);
+void lanes_destroy(sgw_ctx *ctx);              // api.cu: frees what the lanes own (streams, workspaces, events)
 GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr = nullptr);
 int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl_1based, Sphere *sph);
 // same entries, same order and same column partition as `fine` (built on the context's grid), re-expressed in the box `gr`
@@ -307,6 +312,8 @@ int gemm_n_n(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long 
              cplx *C, long ldc);
 int gemm_n_n_batched(sgw_ctx *ctx, int m, int n, int k, cplx alpha, const cplx *A, long lda, long bsA, const cplx *B, long ldb,
                      long bsB, cplx beta, cplx *C, long ldc, long bsC, int nbatch, const int *list, const int *count);
+int gemm_ch_n_batched(sgw_ctx *ctx, int m, int n, int k, const cplx *A, long lda, long bsA, const cplx *B, long ldb, long bsB, cplx *C,
+                      long ldc, long bsC, int nbatch);
 int dense_apply(sgw_ctx *ctx, const KSlot &k, int nvec, const cplx *psi, long ldpsi, const cplx *sigma, long sigma_stride,
                 cplx *out, long ldout, const int *active);
 

@@ -11,9 +11,25 @@
 //   k_sub_expand   : append (new, r), gram_schmidt(m+1, W, V)                           (:391-440)
 // Inside the re-orthonormalisation the columns j > i are independent, so each warp takes its own columns
 // (dot + two axpys) between two block barriers; the dependency order is the reference's MGS order.
+//
+// Default path (SGW_SUB=mgs selects the kernels above, which keep the reference's operation order):
+//   * re-orthonormalisation at a new shift by Cholesky-QR: G = W^H W from per-row-block partial Gram matrices
+//     (k_sub_gram, which also applies W += dsigma V), G = R^H R and T = R^-1 in shared memory (k_sub_chol),
+//     W <- W T, V <- V T in place (k_sub_tri); a second sweep runs for the right-hand sides whose first factor was
+//     ill conditioned.  QR with a positive diagonal is unique, so this is the factorisation MGS computes, in O(1)
+//     dependent steps over the vector length instead of m(m-1)/2 dependent dot/axpy pairs.
+//   * k_sub_step: one kernel per iteration appends (A r, r), orthogonalises the new pair against the basis by
+//     classical Gram-Schmidt with the "twice is enough" re-orthogonalisation (all m dots at once, warp per column),
+//     and updates the residual INCREMENTALLY: the overlaps <w_i|b> of the old columns do not change inside a shift
+//     (:367 recomputes them), so r <- r - w_m <w_m|b>.
+//   * the host runs one iteration ahead of the device (count of active systems read back with one iteration lag),
+//     so there is no stream synchronisation per iteration.
 #include "internal.cuh"
 
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 namespace sgw {
 
@@ -30,6 +46,9 @@ struct SubState {
   double *absthr;           // [nrhs]
   int *m, *act, *alive, *done, *iter, *ierr, *count;
   long *nop;                // [1] operator applications
+  cplx *c;                  // [nrhs][n] overlaps <w_i|b> of the current shift
+  cplx *G;                  // [nrhs][ldg*ldg] Gram matrices W^H W, then T = R^-1 (upper triangle)
+  int *again;               // [nrhs] second Cholesky-QR sweep wanted
 };
 
 __device__ __forceinline__ cplx *colV(const SubState &s, int b, int i) { return s.V + ((long)b * s.cap + i) * s.n; }
@@ -104,11 +123,12 @@ __device__ void gs_full(const SubState &s, int b, int m, cplx *sm) {
   }
 }
 
-__global__ void __launch_bounds__(ST) k_sub_shift(SubState s, int ishift) {
+__global__ void __launch_bounds__(ST) k_sub_shift(SubState s, int ishift, int only_above) {
   const int b = blockIdx.x;
   if (!s.alive[b]) return;
   __shared__ cplx sm[32];
   const int m = s.m[b], n = s.n;
+  if (m <= only_above) return;                          // those bases are re-orthonormalised by Cholesky-QR
   const cplx sg = s.sigma[(long)b * s.nshift + ishift];
   const cplx d = csub(sg, s.sig_old[b]);                // :289
   for (int i = 0; i < m; ++i) {
@@ -143,7 +163,7 @@ __global__ void __launch_bounds__(ST) k_sub_residual(SubState s, int ishift) {
     cplx acc = cmake(0.0, 0.0);
     for (int e = lane; e < n; e += 32) acc = cfma(cconj(wi[e]), bb[e], acc);
     acc = warp_sum(acc);
-    if (lane == 0) dyn[i] = acc;
+    if (lane == 0) { dyn[i] = acc; if (s.c) s.c[(long)b * s.n + i] = acc; }
   }
   __syncthreads();
   cplx *r = s.Rv + (long)b * n;
@@ -212,6 +232,193 @@ __global__ void __launch_bounds__(ST) k_sub_expand(SubState s) {
   const double inv = 1.0 / block_norm(wm, n, sm);        // :114
   for (int e = threadIdx.x; e < n; e += blockDim.x) { wm[e] = cscale(inv, wm[e]); vm[e] = cscale(inv, vm[e]); }
   if (threadIdx.x == 0) s.m[b] = m + 1;
+}
+
+
+// ---------------------------------------------------------------- default path: Cholesky-QR + fused iteration step
+constexpr int MCH = 96;      // largest basis the Cholesky-QR path handles (R lives in shared memory); larger ones use gs_full
+constexpr int TRI_R = 32;    // rows per tile of k_sub_tri
+
+__global__ void k_sub_wshift(SubState s, int ishift, int mmax) {          // W += (sigma - sigma_old) V   (:289-292)
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (!s.alive[b] || i >= s.m[b] || s.m[b] > MCH) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  const cplx d = csub(s.sigma[(long)b * s.nshift + ishift], s.sig_old[b]);
+  cplx *wi = colW(s, b, i);
+  wi[e] = cfma(d, colV(s, b, i)[e], wi[e]);
+}
+
+// G = R^H R (upper R) of the leading m x m block of the Gram matrix, then T = R^-1 written over G (upper triangle, leading
+// dimension ldg).  pass 0 flags the right-hand sides whose factor is far from the identity for a second sweep.
+__global__ void __launch_bounds__(256) k_sub_chol(SubState s, int ldg, int pass) {
+  const int b = blockIdx.x;
+  if (!s.alive[b]) return;
+  const int m = s.m[b];
+  if (m == 0 || m > MCH) return;
+  if (pass == 1 && !s.again[b]) return;
+  extern __shared__ cplx R[];                    // [m][m], column-major: R(i,j) at i + m*j
+  __shared__ double s_d;
+  cplx *G = s.G + (long)b * ldg * ldg;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int idx = tid; idx < m * m; idx += nt) { const int i = idx % m, j = idx / m; R[idx] = G[i + (long)ldg * j]; }
+  __syncthreads();
+  double dmin = 1e300, dmax = 0.0;
+  for (int k = 0; k < m; ++k) {
+    if (tid == 0) s_d = sqrt(R[k + m * k].x);
+    __syncthreads();
+    const double d = s_d, inv = 1.0 / d;
+    dmin = fmin(dmin, d); dmax = fmax(dmax, d);
+    for (int j = k + tid; j < m; j += nt) R[k + m * j] = (j == k) ? cmake(d, 0.0) : cscale(inv, R[k + m * j]);
+    __syncthreads();
+    const int t = m - k - 1;                     // trailing block: G(i,j) -= conj(R(k,i)) R(k,j), k < i <= j
+    for (int idx = tid; idx < t * t; idx += nt) {
+      const int i = k + 1 + idx % t, j = k + 1 + idx / t;
+      if (i <= j) R[i + m * j] = cfma(cneg(cconj(R[k + m * i])), R[k + m * j], R[i + m * j]);
+    }
+    __syncthreads();
+  }
+  // T = R^-1 by columns (independent): T(j,j) = 1/R(j,j); T(i,j) = -sum_{k=i+1..j} R(i,k) T(k,j) / R(i,i); stored in the
+  // strictly lower triangle of the shared array (T(i,j) at (j,i)) until every column is done
+  for (int j = tid; j < m; j += nt) {
+    const double tjj = 1.0 / R[j + m * j].x;
+    for (int i = j - 1; i >= 0; --i) {
+      cplx acc = cscale(tjj, R[i + m * j]);      // k = j term
+      for (int k = i + 1; k < j; ++k) acc = cfma(R[i + m * k], R[j + m * k], acc);   // T(k,j) sits at (j,k)
+      R[j + m * i] = cscale(-1.0 / R[i + m * i].x, acc);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < m * m; idx += nt) {
+    const int i = idx % m, j = idx / m;
+    if (i < j) G[i + (long)ldg * j] = R[j + m * i];
+    else if (i == j) G[i + (long)ldg * j] = cmake(1.0 / R[i + m * i].x, 0.0);
+  }
+  if (tid == 0 && pass == 0) s.again[b] = !(dmin > 0.5 * dmax);   // NaN counts as ill conditioned
+}
+
+// X <- X T in place for X = W (blockIdx.z = 0) and X = V (1): rows of a tile are staged in shared memory, T is read through L1
+__global__ void __launch_bounds__(256) k_sub_tri(SubState s, int ldg, int pass) {
+  const int b = blockIdx.y;
+  if (!s.alive[b]) return;
+  const int m = s.m[b], n = s.n;
+  if (m == 0 || m > MCH) return;
+  if (pass == 1 && !s.again[b]) return;
+  extern __shared__ cplx tile[];                 // [m][TRI_R]
+  cplx *X = blockIdx.z == 0 ? colW(s, b, 0) : colV(s, b, 0);
+  const cplx *T = s.G + (long)b * ldg * ldg;
+  const int r0 = blockIdx.x * TRI_R, tid = threadIdx.x;
+  for (int idx = tid; idx < m * TRI_R; idx += blockDim.x) {
+    const int i = idx / TRI_R, e = r0 + idx % TRI_R;
+    tile[idx] = e < n ? X[(long)i * n + e] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  const int r = tid % TRI_R, e = r0 + r;
+  if (e >= n) return;
+  for (int j = tid / TRI_R; j < m; j += blockDim.x / TRI_R) {
+    const cplx *tj = T + (long)ldg * j;
+    cplx acc = cmake(0.0, 0.0);
+    for (int i = 0; i <= j; ++i) acc = cfma(tile[i * TRI_R + r], __ldg(&tj[i]), acc);
+    X[(long)j * n + e] = acc;
+  }
+}
+
+__global__ void k_sub_shift_done(SubState s, int ishift) {                // :298 and the per-shift counters
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.nrhs || !s.alive[b] || s.m[b] > MCH) return;
+  s.sig_old[b] = s.sigma[(long)b * s.nshift + ishift];
+  s.done[b] = 0;
+  s.iter[b] = 0;
+}
+
+// One iteration for the right-hand sides with act != 0: append (new, r) to (W, V) with the Gram-Schmidt step of
+// gram_schmidt.f90:94-114 (classical projections, repeated when the norm dropped: "twice is enough"), then the residual of
+// linear_solver.f90:361-374 updated by the new column only, the convergence test, and on convergence obtain_result (:486-501).
+__global__ void __launch_bounds__(ST) k_sub_step(SubState s, int ishift) {
+  const int b = blockIdx.x;
+  if (!s.act[b]) return;
+  extern __shared__ cplx hs[];                   // [cap] projections of the new column
+  __shared__ cplx sm[32];
+  const int m = s.m[b], n = s.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  cplx *wm = colW(s, b, m), *vm = colV(s, b, m);
+  cplx *r = s.Rv + (long)b * n;
+  const cplx *nv = s.New + (long)b * n, *bb = s.b + (long)b * s.ldb;
+  cplx a2 = cmake(0.0, 0.0);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {                     // :426, :432
+    const cplx x = nv[e];
+    wm[e] = x; vm[e] = r[e];
+    a2.x += x.x * x.x; a2.y += x.y * x.y;
+  }
+  a2 = block_sum(a2, sm);
+  double before = a2.x + a2.y;
+  for (int pass = 0; pass < 2 && m > 0; ++pass) {
+    for (int j = w; j < m; j += nw) {
+      const cplx *wj = colW(s, b, j);
+      cplx acc = cmake(0.0, 0.0);
+      for (int e = lane; e < n; e += 32) acc = cfma(cconj(wj[e]), wm[e], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) hs[j] = cneg(acc);
+    }
+    __syncthreads();
+    cplx q = cmake(0.0, 0.0);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      cplx x = wm[e], y = vm[e];
+      for (int j = 0; j < m; ++j) { const cplx h = hs[j]; x = cfma(h, colW(s, b, j)[e], x); y = cfma(h, colV(s, b, j)[e], y); }
+      wm[e] = x; vm[e] = y;
+      q.x += x.x * x.x; q.y += x.y * x.y;
+    }
+    q = block_sum(q, sm);                        // (its barriers also order the hs reuse of the next pass)
+    const double after = q.x + q.y;
+    if (after > 0.5 * before) { before = after; break; }
+    before = after;
+  }
+  const double inv = 1.0 / sqrt(before);                                  // :114
+  cplx cm = cmake(0.0, 0.0);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) cm = cfma(cconj(wm[e]), bb[e], cm);
+  cm = cscale(inv, block_sum(cm, sm));                                    // <w_m | b>  (:367)
+  cplx acc = cmake(0.0, 0.0);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const cplx x = cscale(inv, wm[e]);
+    wm[e] = x; vm[e] = cscale(inv, vm[e]);
+    const cplx v = cfma(cneg(cm), x, r[e]);                                // :368 for the new column
+    r[e] = v;
+    acc.x += v.x * v.x; acc.y += v.y * v.y;
+  }
+  acc = block_sum(acc, sm);
+  const double nrm = sqrt(acc.x + acc.y);                                  // :373
+  cplx *c = s.c + (long)b * s.n;
+  if (threadIdx.x == 0) { c[m] = cm; s.m[b] = m + 1; }
+  __syncthreads();
+  const int m1 = m + 1;
+  if (s.iter[b] >= s.max_iter) {                                          // the loop :159 ran out (:176-180): no further test
+    if (threadIdx.x == 0) { s.ierr[b] = 1; s.alive[b] = 0; s.act[b] = 0; }
+    return;
+  }
+  if (nrm < s.absthr[b]) {                                                // :374 -> obtain_result, NaN scan (:186-190)
+    cplx *x = s.x + ((long)b * s.nshift + ishift) * n;
+    int bad = 0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      cplx v = cmake(0.0, 0.0);
+      for (int i = 0; i < m1; ++i) v = cfma(c[i], colV(s, b, i)[e], v);
+      x[e] = v;
+      bad |= (v.x != v.x) || (v.y != v.y);
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+      s.done[b] = 1; s.act[b] = 0;
+      if (bad) { s.ierr[b] = 2; s.alive[b] = 0; }
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    if (n == m1) {                                                        // :376-378 sets 3, :176-180 overwrites it with 1
+      s.ierr[b] = 1; s.alive[b] = 0; s.act[b] = 0;
+    } else {
+      s.iter[b] += 1;
+      atomicAdd(s.count, 1);
+      atomicAdd((unsigned long long *)s.nop, 1ull);
+    }
+  }
 }
 
 __global__ void k_sub_finish(SubState s, const int *__restrict__ todo) {
@@ -321,9 +528,10 @@ int subspace_batched(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int m
   return SGW_OK;
 }
 
-static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
+static int subspace_core_mgs(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
   if (sb.nrhs <= 0) return SGW_OK;
   SubState s;
+  s.c = nullptr; s.G = nullptr; s.again = nullptr;
   s.n = sb.n; s.nrhs = sb.nrhs; s.nshift = sb.nshift; s.max_iter = max_iter;
   s.b = sb.d_b; s.ldb = sb.ldb; s.sigma = sb.d_sigma; s.x = sb.d_x; s.ierr = sb.d_ierr;
   const long n = s.n, nr = s.nrhs;
@@ -348,7 +556,7 @@ static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, i
   int total_cols = 0;   // upper bound of the basis size of any RHS
   int rc = SGW_OK;
   for (int ishift = 0; ishift < s.nshift && rc == SGW_OK; ++ishift) {
-    k_sub_shift<<<(unsigned)nr, sub_threads(s.n), 0, st>>>(s, ishift);
+    k_sub_shift<<<(unsigned)nr, sub_threads(s.n), 0, st>>>(s, ishift, -1);
     SGW_LAUNCH_CHECK();
     for (int it = 0; it <= max_iter; ++it) {
       SGW_CUDA(cudaMemsetAsync(s.count, 0, sizeof(int), st));
@@ -393,6 +601,141 @@ static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, i
   cudaFreeHost(h_count);
   if (rc != SGW_OK) return rc;
   k_sub_finish<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(s, d_todo);
+  SGW_LAUNCH_CHECK();
+  long nop = 0;
+  SGW_CUDA(cudaMemcpyAsync(&nop, s.nop, sizeof(long), cudaMemcpyDeviceToHost, st));
+  SGW_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.n_linear_op += nop;
+  return SGW_OK;
+}
+
+
+static bool sub_mgs() {
+  const char *e = getenv("SGW_SUB");
+  return e && strcmp(e, "mgs") == 0;
+}
+
+static int subspace_core(sgw_ctx *ctx, const SolveBatch &sb, double threshold, int max_iter, const int *d_todo) {
+  if (sb.nrhs <= 0) return SGW_OK;
+  if (sub_mgs()) return subspace_core_mgs(ctx, sb, threshold, max_iter, d_todo);
+  SubState s;
+  s.n = sb.n; s.nrhs = sb.nrhs; s.nshift = sb.nshift; s.max_iter = max_iter;
+  s.b = sb.d_b; s.ldb = sb.ldb; s.sigma = sb.d_sigma; s.x = sb.d_x; s.ierr = sb.d_ierr;
+  const long n = s.n, nr = s.nrhs;
+  s.cap = std::min(32, s.n);
+  cudaStream_t st = ctx->stream;
+  SGW_CHECK(ws(ctx, "ss_V", (size_t)(nr * s.cap * n), &s.V));
+  SGW_CHECK(ws(ctx, "ss_W", (size_t)(nr * s.cap * n), &s.W));
+  // columns beyond a system's basis are read (and ignored) by the batched Gram product: they must hold finite numbers
+  SGW_CUDA(cudaMemsetAsync(s.V, 0, sizeof(cplx) * (size_t)(nr * s.cap * n), st));
+  SGW_CUDA(cudaMemsetAsync(s.W, 0, sizeof(cplx) * (size_t)(nr * s.cap * n), st));
+  SGW_CHECK(ws(ctx, "ss_R", (size_t)(nr * n), &s.Rv));
+  SGW_CHECK(ws(ctx, "ss_New", (size_t)(nr * n), &s.New));
+  SGW_CHECK(ws(ctx, "ss_c", (size_t)(nr * n), &s.c));
+  SGW_CHECK(ws(ctx, "ss_G", (size_t)nr * MCH * MCH, &s.G));
+  SGW_CHECK(ws(ctx, "ss_sig", (size_t)nr, &s.sig_old));
+  SGW_CHECK(ws(ctx, "ss_thr", (size_t)nr, &s.absthr));
+  int *ints = nullptr;
+  SGW_CHECK(ws(ctx, "ss_int", (size_t)(6 * nr + 1), &ints));
+  s.m = ints; s.act = ints + nr; s.alive = ints + 2 * nr; s.done = ints + 3 * nr; s.iter = ints + 4 * nr; s.again = ints + 5 * nr;
+  s.count = ints + 6 * nr;
+  SGW_CHECK(ws(ctx, "ss_nop", (size_t)1, &s.nop));
+  SGW_CUDA(cudaMemsetAsync(s.nop, 0, sizeof(long), st));
+  SGW_CUDA(cudaMemsetAsync(s.again, 0, sizeof(int) * nr, st));
+  if (!ctx->h_flags) SGW_CUDA(cudaMallocHost((void **)&ctx->h_flags, 4 * sizeof(int)));
+  volatile int *h_count = ctx->h_flags + 2;
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->ev_iter[i]) SGW_CUDA(cudaEventCreateWithFlags(&ctx->ev_iter[i], cudaEventDisableTiming));
+  SGW_CUDA(cudaFuncSetAttribute(k_sub_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MCH * MCH * sizeof(cplx))));
+  SGW_CUDA(cudaFuncSetAttribute(k_sub_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MCH * TRI_R * sizeof(cplx))));
+  const int nt = sub_threads(s.n);
+  const unsigned gb = (unsigned)((nr + 127) / 128);
+  k_sub_init<<<(unsigned)nr, nt, 0, st>>>(s, threshold, d_todo);
+  SGW_LAUNCH_CHECK();
+  int total_cols = 0;   // upper bound of the basis size of any RHS
+  for (int ishift = 0; ishift < s.nshift; ++ishift) {
+    // ---- orthogonal_subspace (:272-300)
+    if (total_cols > 0) {
+      ProfScope prof(ctx, PC_OTHER);
+      const int mg = std::min(total_cols, MCH);
+      dim3 gw((unsigned)((n + 255) / 256), (unsigned)mg, (unsigned)nr);
+      k_sub_wshift<<<gw, 256, 0, st>>>(s, ishift, mg);
+      SGW_LAUNCH_CHECK();
+      for (int pass = 0; pass < 2; ++pass) {
+        SGW_CHECK(gemm_ch_n_batched(ctx, mg, mg, s.n, s.W, n, (long)s.cap * n, s.W, n, (long)s.cap * n, s.G, mg, (long)mg * mg, (int)nr));
+        k_sub_chol<<<(unsigned)nr, 256, (size_t)mg * mg * sizeof(cplx), st>>>(s, mg, pass);
+        SGW_LAUNCH_CHECK();
+        dim3 gt((unsigned)((n + TRI_R - 1) / TRI_R), (unsigned)nr, 2);
+        k_sub_tri<<<gt, 256, (size_t)mg * TRI_R * sizeof(cplx), st>>>(s, mg, pass);
+        SGW_LAUNCH_CHECK();
+      }
+      if (total_cols > MCH) {                      // bases too large for the shared-memory factorisation
+        k_sub_shift<<<(unsigned)nr, nt, 0, st>>>(s, ishift, MCH);
+        SGW_LAUNCH_CHECK();
+      }
+    }
+    k_sub_shift_done<<<gb, 128, 0, st>>>(s, ishift);
+    SGW_LAUNCH_CHECK();
+    // ---- first residual of the shift from all overlaps (:312-383); later ones are updated by k_sub_step
+    const size_t dyn = (size_t)(s.cap + 1) * sizeof(cplx);
+    if (dyn > 48 * 1024) {
+      SGW_CUDA(cudaFuncSetAttribute(k_sub_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      SGW_CUDA(cudaFuncSetAttribute(k_sub_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    }
+    SGW_CUDA(cudaMemsetAsync(s.count, 0, sizeof(int), st));
+    k_sub_residual<<<(unsigned)nr, nt, dyn, st>>>(s, ishift);
+    SGW_LAUNCH_CHECK();
+    int k = 0;                                     // counts read back so far; the host stays one iteration ahead of the device
+    SGW_CUDA(cudaMemcpyAsync((void *)&h_count[0], s.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaEventRecord(ctx->ev_iter[0], st));
+    for (;;) {
+      SGW_CUDA(cudaMemsetAsync(s.count, 0, sizeof(int), st));
+      SGW_CHECK(apply_operator(ctx, sb.slot, sb.alpha_pv, s.nrhs, s.Rv, n, s.sigma + ishift, s.nshift, s.New, n, s.act));
+      // grow the subspace storage (the reference reallocates every iteration, :424-433).  total_cols is an upper bound over
+      // the batch; no right-hand side can hold more than n basis vectors (:376-378), so a capacity of n columns never grows
+      if (total_cols + 1 > s.cap && s.cap < s.n) {
+        const int ncap = std::min(s.cap * 2, s.n);
+        if ((size_t)(ncap + 1) * sizeof(cplx) > ctx->smem_optin) {
+          ctx->err = "subspace solver: basis capacity exhausted";
+          return SGW_E_UNSUPPORTED;
+        }
+        cplx *nV = nullptr, *nW = nullptr;
+        const char *nameV = (s.V == (cplx *)ctx->ws.bufs["ss_V"].first) ? "ss_V2" : "ss_V";
+        const char *nameW = (s.W == (cplx *)ctx->ws.bufs["ss_W"].first) ? "ss_W2" : "ss_W";
+        SGW_CHECK(ws(ctx, nameV, (size_t)(nr * ncap * n), &nV));
+        SGW_CHECK(ws(ctx, nameW, (size_t)(nr * ncap * n), &nW));
+        SGW_CUDA(cudaMemsetAsync(nV, 0, sizeof(cplx) * (size_t)(nr * ncap * n), st));
+        SGW_CUDA(cudaMemsetAsync(nW, 0, sizeof(cplx) * (size_t)(nr * ncap * n), st));
+        dim3 g(64, (unsigned)nr);
+        k_copy_cols<<<g, 256, 0, st>>>(s.n, s.cap, s.V, (long)s.cap * n, nV, (long)ncap * n);
+        SGW_LAUNCH_CHECK();
+        k_copy_cols<<<g, 256, 0, st>>>(s.n, s.cap, s.W, (long)s.cap * n, nW, (long)ncap * n);
+        SGW_LAUNCH_CHECK();
+        s.V = nV; s.W = nW; s.cap = ncap;
+      }
+      const size_t dyn2 = (size_t)(s.cap + 1) * sizeof(cplx);
+      if (dyn2 > 48 * 1024) {
+        SGW_CUDA(cudaFuncSetAttribute(k_sub_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+        SGW_CUDA(cudaFuncSetAttribute(k_sub_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
+      }
+      {
+        ProfScope prof(ctx, PC_OTHER);
+        k_sub_step<<<(unsigned)nr, nt, dyn2, st>>>(s, ishift);
+        SGW_LAUNCH_CHECK();
+      }
+      ++total_cols;
+      ++k;
+      SGW_CUDA(cudaMemcpyAsync((void *)&h_count[k & 1], s.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SGW_CUDA(cudaEventRecord(ctx->ev_iter[k & 1], st));
+      SGW_CUDA(cudaEventSynchronize(ctx->ev_iter[(k - 1) & 1]));
+      if (h_count[(k - 1) & 1] == 0) {             // nothing was active in the iteration enqueued last: it was a no-op
+        --total_cols;
+        break;
+      }
+      if (k > max_iter + 1) break;
+    }
+  }
+  k_sub_finish<<<gb, 128, 0, st>>>(s, d_todo);
   SGW_LAUNCH_CHECK();
   long nop = 0;
   SGW_CUDA(cudaMemcpyAsync(&nop, s.nop, sizeof(long), cudaMemcpyDeviceToHost, st));

@@ -71,10 +71,14 @@ def test_fixture_known_answers(ctx, lin_prob):
     assert np.max(np.linalg.norm(x - xd, axis=0) / np.linalg.norm(xd, axis=0)) < 1e-12
 
 
-def test_fixture_subspace_solver(ctx, lin_prob):
-    """linear_solver.pf:265-345 (default config: relative threshold 1e-4) + parity with the oracle."""
+@pytest.mark.parametrize("path", ["cholqr", "mgs"])
+def test_fixture_subspace_solver(ctx, lin_prob, monkeypatch, path):
+    """linear_solver.pf:265-345 (default config: relative threshold 1e-4) + parity with the oracle, for the default path
+    (Cholesky-QR re-orthonormalisation, incremental residual) and for the kernels that keep the reference's MGS order."""
     import oracle
     from sternheimergw_b200 import select_solver_type
+    if path == "mgs":
+        monkeypatch.setenv("SGW_SUB", "mgs")
     A, b, sigma = lin_prob["A"], lin_prob["b"], lin_prob["sigma"]
     ctx.set_dense_operator(0, A)
     x, ierr = ctx.select_solver(select_solver_type(priority=(3,), threshold=1e-4), 0, b, sigma)
@@ -186,3 +190,40 @@ def test_planewave_solves_match_oracle(ctx, name):
                 err = np.abs(x[:kq.npw, :, r] - xo).max() / np.abs(xo).max()
                 assert err < (tol if tol else 10 * thr * 50), (thr, use_pv, r, err)
             assert abs(st["n_outer_max"] - nouter) <= 1
+
+
+@pytest.mark.parametrize("path", ["cholqr", "mgs"])
+def test_planewave_subspace_many_shifts(ctx, monkeypatch, path):
+    """SGW subspace solver (priority 3) on the gw_licl stand-in with a frequency mesh like its 102 shifts: the basis is
+    carried from shift to shift and re-orthonormalised at each one (linear_solver.f90:272-300).  Both device paths against
+    the oracle: <= 1e-8 at threshold 1e-11, same operator count at the production threshold."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    if path == "mgs":
+        monkeypatch.setenv("SGW_SUB", "mgs")
+    syn = synth.preset("licl", nk=1)
+    ctx.install_system(syn)
+    kq = syn.kpairs[0].kq
+    ps = oracle.PwSystem(syn)
+    rng = np.random.default_rng(11)
+    nrhs = 3
+    bb = np.zeros((kq.npwx, nrhs), dtype=complex, order="F")
+    raw = rng.standard_normal((kq.npw, nrhs)) + 1j * rng.standard_normal((kq.npw, nrhs))
+    ev = kq.evq[:kq.npw]
+    bb[:kq.npw] = -(raw - ev @ (ev.conj().T @ raw))
+    freq = (np.linspace(2.5, 12.5, 12) + 0.3j) / 13.605698066
+    omega = np.concatenate([freq, -freq])
+    sg = np.asfortranarray(np.stack([-(syn.kpairs[0].et[r] + omega) for r in range(nrhs)], axis=1))
+    for thr, tol in ((1e-11, 1e-8), (1e-4, None)):
+        x, ierr = ctx.select_solver(select_solver_type(priority=(3,), threshold=thr), 0, bb, sg)
+        nop = ctx.stats()["n_linear_op"]
+        assert (ierr == 0).all()
+        nop_o = 0
+        for r in range(nrhs):
+            xo, ie, so = ps.select_solver(0, bb[:kq.npw, r], sg[:, r], oracle.make_cfg(priority=(3,), threshold=thr))
+            assert ie == 0
+            nop_o += so["n_op"]
+            err = np.abs(x[:kq.npw, :, r] - xo).max() / np.abs(xo).max()
+            assert err < (tol if tol else 10 * thr * 50), (thr, r, err)
+        assert abs(nop - nop_o) <= (0 if tol else 2), (nop, nop_o)

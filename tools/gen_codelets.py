@@ -14,7 +14,7 @@ same code is unit-tested on the CPU (tests/test_fft_core_cpu.py).
 import math
 from pathlib import Path
 
-RADICES = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16]
+RADICES = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30, 32]
 OUT = Path(__file__).resolve().parent.parent / "sternheimergw_b200" / "csrc" / "fft_codelets.h"
 
 
@@ -157,7 +157,10 @@ def main():
             out.append(f"  re[{k}] = {X[k][0]}; im[{k}] = {X[k][1]};")
         out.append("}")
         out.append("")
-    out.append("#define SGW_FOR_EACH_RADIX(X) " + " ".join(f"X({r})" for r in [1] + RADICES))
+    # the radices above 16 are dispatched by separate functions (fft_core.h run_*_big) so that their register pressure does
+    # not touch the code generated for the common ones
+    out.append("#define SGW_FOR_EACH_RADIX(X) " + " ".join(f"X({r})" for r in [1] + [r for r in RADICES if r <= 16]))
+    out.append("#define SGW_FOR_EACH_BIG_RADIX(X) " + " ".join(f"X({r})" for r in RADICES if r > 16))
     out.append("")
     out.append("}  // namespace sgw")
     OUT.parent.mkdir(parents=True, exist_ok=True)
