@@ -330,7 +330,7 @@ namespace sgw {
 int make_fft_grid(sgw_ctx *ctx, int n1, int n2, int n3, FftGrid *gr) {
   free_fft_grid(gr);
   if (!make_plan(n1, &gr->px) || !make_plan(n2, &gr->py) || !make_plan(n3, &gr->pz)) {
-    ctx->err = "FFT dimension not of the form r1*r2 with radices in {1,2,3,4,5,6,8,9,10,12,15,16}";
+    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..6,8,9,10,12,15,16,18,20,24,25,27,30,32} (every 2^a 3^b 5^c <= 960 is)";
     return SGW_E_UNSUPPORTED;
   }
   gr->n1 = n1; gr->n2 = n2; gr->n3 = n3;
@@ -359,7 +359,7 @@ int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, in
     return SGW_E_UNSUPPORTED;
   }
   if (!make_plan(nr1, &ctx->px) || !make_plan(nr2, &ctx->py) || !make_plan(nr3, &ctx->pz)) {
-    ctx->err = "FFT dimension not of the form r1*r2 with radices in {1,2,3,4,5,6,8,9,10,12,15,16}";
+    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..6,8,9,10,12,15,16,18,20,24,25,27,30,32} (every 2^a 3^b 5^c <= 960 is)";
     return SGW_E_UNSUPPORTED;
   }
   ctx->nr1 = nr1; ctx->nr2 = nr2; ctx->nr3 = nr3;

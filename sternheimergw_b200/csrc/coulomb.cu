@@ -392,6 +392,12 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     int *d_ierr = nullptr;
     SGW_CHECK(ws(ctx, "co_Tk", (size_t)nocc * ctx->nr3 * kp.sph_k.ncol, &Tk));
     SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));
+    struct ZClass {                              // z passes outside H.psi are billed to the stage they belong to
+      sgw_ctx *c;
+      ZClass(sgw_ctx *cc, int cls) : c(cc) { c->prof_z_class = cls; }
+      ~ZClass() { c->prof_z_class = PC_FFT_Z; }
+    };
+    ZClass zc_setup(ctx, PC_OTHER);
     SGW_CHECK(fft_zpass_g2r(ctx, kp.sph_k, nocc, kp.d_evc, n, Tk, nullptr));
     SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &kp.sph_k, nullptr, nocc, Tk, nullptr, nullptr, 1, psir, nullptr));
     // psi_v(r) once more on the Delta-rho grid when that is a different box
@@ -444,7 +450,9 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     sb.d_b = dvpsi; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
     sb.avg.d_y = davg_all; sb.avg.nfreq = nfreq; sb.avg.zero_freq = fl.zero_freq; sb.avg.group = nocc; sb.avg.d_done = d_done;
     cudaEventRecord(ctx->ev2, st);
+    ctx->prof_z_class = PC_FFT_Z;
     SGW_CHECK(select_solver_batched(ctx, sb, cfg));
+    ctx->prof_z_class = PC_RHO_PLANE;
     cudaEventRecord(ctx->ev3, st);
     {
       std::vector<int> ie(nrhs);
@@ -519,10 +527,12 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
   SGW_CUDA(cudaMemsetAsync(d_drhoG, 0, sizeof(cplx) * (size_t)npf * rho.npw, st));
   ZEpilogue epi;
   epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
+  ctx->prof_z_class = PC_RHO_PLANE;
   for (int v0 = 0; v0 < npf; v0 += 32768) {
     const int c = std::min(32768, npf - v0);
     SGW_CHECK(fft_zpass_r2g(ctx, rho, c, Trho + (size_t)v0 * rnz * rho.ncol, d_drhoG + (size_t)v0 * rho.npw, rho.npw, epi, nullptr, rg));
   }
+  ctx->prof_z_class = PC_FFT_Z;
   return SGW_OK;
 }
 
@@ -531,7 +541,12 @@ static int perturbation_chunk(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nshif
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
   size_t held = 0;
-  for (auto &kv : ctx->ws.bufs) held += kv.second.second;           // workspace is re-used, so it counts as available
+  for (auto &kv : ctx->ws.bufs) {                                   // workspace this pipeline re-uses counts as available
+    const std::string &nm = kv.first;
+    if (nm.rfind("ie_", 0) == 0 || nm.rfind("sg_", 0) == 0 || nm.rfind("an_", 0) == 0 || nm.rfind("gr_", 0) == 0 || nm.rfind("uf_", 0) == 0)
+      continue;                                                     // other entry points' buffers stay allocated next to it
+    held += kv.second.second;
+  }
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
   size_t per = 0, fixed = (size_t)3 << 30;
   for (auto &kp : ctx->pairs) {
@@ -1123,7 +1138,8 @@ int sgw_coulomb(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int igstart, int ngc, i
     end_call(ctx);
     return SGW_OK;
   }
-  const int chunk = perturbation_chunk(ctx, cfg, fl.num_omega, nfs, *rho, nt);
+  int chunk = perturbation_chunk(ctx, cfg, fl.num_omega, nfs, *rho, nt);
+  chunk = (nt + (nt + chunk - 1) / chunk - 1) / ((nt + chunk - 1) / chunk);      // equal-sized blocks: no short tail block
   bool coarse = false;
   SGW_CHECK(rho_grid_prepare(ctx, ngc, *rho, &coarse));
   ctx->rho_last_coarse = coarse;
@@ -1356,7 +1372,9 @@ int sgw::green_function_core(sgw_ctx *ctx, int slot, const sgw_solver_cfg *cfg, 
     sb.nrhs = nr; sb.nshift = nfreq; sb.n = n;
     sb.d_b = d_b; sb.ldb = n; sb.d_sigma = d_sig; sb.d_x = d_x; sb.d_ierr = d_ierr;
     cudaEventRecord(ctx->ev2, st);
+    ctx->prof_z_class = PC_FFT_Z;
     SGW_CHECK(select_solver_batched(ctx, sb, cfg));
+    ctx->prof_z_class = PC_RHO_PLANE;
     cudaEventRecord(ctx->ev3, st);
     std::vector<int> ie(nr);
     SGW_CUDA(cudaMemcpyAsync(ie.data(), d_ierr, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16
   }
 }
 
-template <int ZCB>
+// RZ1 x RZ2 > 0: the radix plan of the z axis is a compile-time constant (the stages inline, no dispatch call)
+template <int ZCB, int RZ1 = 0, int RZ2 = 0>
 __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16) k_zpass_r2g(GridDev g, SphereDev s, const cplx *__restrict__ T,
                                                          cplx *__restrict__ out, long ld, ZEpilogue epi, double scale,
                                                          const int *__restrict__ active) {
@@ -79,11 +80,18 @@ __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16
     if (c < nc) lines[c * pitch + pz] = src[pz * s.ncol + c];
   }
   __syncthreads();
-  if (g.rz2 > 1) {
-    run_contig<-1>(g.rz2, lines, nc, nullptr, pitch, 1, g.rz1, tw, true, tid, nt);
+  if (RZ1 > 0) {
+    constexpr int R1 = (RZ1 > 0) ? RZ1 : 1, R2 = (RZ2 > 0) ? RZ2 : 1;
+    stage_contig<R2, -1>(lines, nc, nullptr, pitch, 1, R1, tw, true, tid, nt);
     __syncthreads();
+    stage_strided<R1, -1>(lines, nc, nullptr, pitch, 1, R2, tw, false, tid, nt);
+  } else {
+    if (g.rz2 > 1) {
+      run_contig<-1>(g.rz2, lines, nc, nullptr, pitch, 1, g.rz1, tw, true, tid, nt);
+      __syncthreads();
+    }
+    run_strided<-1>(g.rz1, lines, nc, nullptr, pitch, 1, g.rz2, tw, false, tid, nt);
   }
-  run_strided<-1>(g.rz1, lines, nc, nullptr, pitch, 1, g.rz2, tw, false, tid, nt);
   __syncthreads();
   const int p0 = s.col_ptr[c0], p1 = s.col_ptr[c0 + nc];
   cplx *dst = out + (long)vec * ld;
@@ -106,11 +114,15 @@ __global__ void __launch_bounds__(ZCB >= 32 ? 256 : 160, ZCB >= 32 ? 4 : ZMINB16
   }
 }
 
-template <int MODE, int NT, bool ONE>
+// GMEM: the plane does not fit in shared memory (boxes beyond ~118 x 118): it lives in a per-CTA slice of `scratch` in global
+// memory (L2 for the sizes in question) and the same stages run on it; `vec0` is the first vector of the launch (the host
+// walks over the batch in chunks that bound the scratch).  Slower per point, same arithmetic.
+template <int MODE, int NT, bool ONE, bool GMEM = false>
 __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, SphereDev sout, const cplx *__restrict__ Tin,
                                                      cplx *__restrict__ Tout, const double *__restrict__ vperm,
                                                      const cplx *__restrict__ field, int vec_per_field, cplx *R,
-                                                     int in_mod, const int *__restrict__ active, int Prt) {
+                                                     int in_mod, const int *__restrict__ active, int Prt,
+                                                     cplx *scratch = nullptr, int vec0 = 0) {
   const int P = ONE ? 1 : Prt;        // ONE: single-plane instantiation (large boxes), plane loops fold away
   // One CTA = P consecutive z-planes of one vector, stacked in shared memory (plane p at offset p * ny * pitch, so the
   // rows of all planes form ONE set of np * ny lines with stride `pitch` and the potential rows v[pz0 * nxy + l * nx]
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, Spher
   // the radix stages have enough butterflies for every thread.
   // in_mod > 0: the INPUT (Tin or R) of vector `vec` is input vector vec % in_mod (one set of bands shared by
   // every perturbation, dvqpsi_us.f90:99-130)
-  const int vec = blockIdx.y, pz0 = blockIdx.x * P;
+  const int vec = blockIdx.y + (GMEM ? vec0 : 0), pz0 = blockIdx.x * P;
   const int np = ONE ? 1 : min(P, g.nz - pz0);
   const int vin = in_mod > 0 ? vec % in_mod : vec;
   if (active && !active[vec]) return;
@@ -126,8 +138,8 @@ __global__ void __launch_bounds__(NT, 2) k_plane(GridDev g, SphereDev sin, Spher
   extern __shared__ cplx sm[];
   const int pitch = g.pitchx, nx = g.nx, ny = g.ny;
   const int psz = ny * pitch;
-  cplx *plane = sm;
-  cplx *twx = sm + P * psz;
+  cplx *plane = GMEM ? scratch + ((long)blockIdx.y * gridDim.x + blockIdx.x) * psz : sm;
+  cplx *twx = GMEM ? sm : sm + P * psz;
   cplx *twy = twx + nx;
   int *ids_in = (int *)(twy + ny), *ids_out = ids_in + P * nx;   // line starts of the x columns that hold data, all planes
   for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
@@ -570,28 +582,39 @@ __device__ __forceinline__ void stage_acc(const cplx *x, cplx *acc, int nlines, 
     for (int j = 0; j < R; ++j) ab[j] = cfma(cconj(pb[j]), cmake(re[j], im[j]), ab[j]);   // drho += conj(psi) dpsi
   }
 }
+__device__ __noinline__ void run_acc_big(int R, const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
+                                         int tid, int nthreads) {
+  switch (R) {
+#define SGW_CASE(r) case r: stage_acc<r>(x, acc, nlines, ls, r_other, pr, vls, tid, nthreads); break;
+    SGW_FOR_EACH_BIG_RADIX(SGW_CASE)
+#undef SGW_CASE
+    default: break;
+  }
+}
 __device__ __noinline__ void run_acc(int R, const cplx *x, cplx *acc, int nlines, int ls, int r_other, const cplx *pr, int vls,
                                      int tid, int nthreads) {
   switch (R) {
 #define SGW_CASE(r) case r: stage_acc<r>(x, acc, nlines, ls, r_other, pr, vls, tid, nthreads); break;
     SGW_FOR_EACH_RADIX(SGW_CASE)
 #undef SGW_CASE
-    default: break;
+    default: run_acc_big(R, x, acc, nlines, ls, r_other, pr, vls, tid, nthreads); break;
   }
 }
 
 // incdrhoscf: one CTA per (pf = perturbation x frequency, z-plane); bands are summed on chip
-template <int NT>
+template <int NT, bool GMEM = false>
 __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : (NT >= 256 ? 2 : 3)) k_plane_rho(GridDev g, SphereDev sin, SphereDev sout, int nocc,
                                                          const cplx *__restrict__ Tin, const cplx *__restrict__ psir,
-                                                         double wgt, cplx *__restrict__ Tout, int accumulate) {
-  const int pf = blockIdx.x, pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
+                                                         double wgt, cplx *__restrict__ Tout, int accumulate,
+                                                         cplx *scratch = nullptr, int pf0 = 0) {
+  const int pf = blockIdx.x + (GMEM ? pf0 : 0), pz = blockIdx.y;   // pf fastest: concurrent CTAs share the psi_v(r) planes through L2
   const int tid = threadIdx.x, nt = blockDim.x;
   extern __shared__ cplx sm[];
   const int pitch = g.pitchx, nx = g.nx, ny = g.ny;
-  cplx *plane = sm;
-  cplx *acc = sm + ny * pitch;
-  cplx *twx = acc + ny * pitch;
+  // GMEM: plane and accumulator of this CTA in global memory (boxes whose planes do not fit in shared memory, see k_plane)
+  cplx *plane = GMEM ? scratch + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * ny * pitch : sm;
+  cplx *acc = plane + ny * pitch;
+  cplx *twx = GMEM ? sm : acc + ny * pitch;
   cplx *twy = twx + nx;
   int *xs_in = (int *)(twy + ny), *xs_out = xs_in + nx;
   for (int i = tid; i < nx; i += nt) twx[i] = g.twx[i];
@@ -1234,10 +1257,11 @@ int fft_zpass_g2r(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *in, long 
                   const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
-  const int zcb = zpass_zcb();
+  int zcb = zpass_zcb();
+  if (zpass_smem(g, zcb) > ctx->smem_optin) zcb = 8;           // long lines (nz > ~880): fewer columns per CTA
   const size_t smem = zpass_smem(g, zcb);
   dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
-  ProfScope prof(ctx, PC_FFT_Z);
+  ProfScope prof(ctx, ctx->prof_z_class);
   {
     ZTArgs a = {};
     a.vec = in; a.ld = ld; a.active = active;
@@ -1260,11 +1284,12 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
                   const int *active, const FftGrid *gr) {
   if (nvec <= 0) return SGW_OK;
   const GridDev g = grid_dev(ctx, gr);
-  const int zcb = zpass_zcb();
+  int zcb = zpass_zcb();
+  if (zpass_smem(g, zcb) > ctx->smem_optin) zcb = 8;
   const size_t smem = zpass_smem(g, zcb);
   dim3 grid((s.ncol + zcb - 1) / zcb, nvec);
   const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
-  ProfScope prof(ctx, PC_FFT_Z);
+  ProfScope prof(ctx, ctx->prof_z_class);
   {
     ZTArgs a = {};
     a.vec = epi.psi; a.out = out; a.ld = ld; a.active = active;
@@ -1278,7 +1303,12 @@ int fft_zpass_r2g(sgw_ctx *ctx, const Sphere &s, int nvec, const cplx *T, cplx *
     SGW_CHECK(set_smem(ctx, k_zpass_r2g<Z>, smem));                                                               \
     k_zpass_r2g<Z><<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), T, out, ld, epi, scale, active);  \
   } while (0)
-  if (zcb == 8) SGW_Z(8); else if (zcb == 32) SGW_Z(32); else SGW_Z(16);
+  static int ct = -1;                                           // SGW_ZR2G_CT=0: runtime radix dispatch also for 72 = 8 x 9 (A/B)
+  if (ct < 0) { const char *e = getenv("SGW_ZR2G_CT"); ct = e ? atoi(e) : 1; }
+  if (ct && zcb == 16 && g.rz1 == 8 && g.rz2 == 9) {
+    SGW_CHECK(set_smem(ctx, k_zpass_r2g<16, 8, 9>, smem));
+    k_zpass_r2g<16, 8, 9><<<grid, zpass_threads(ctx), smem, ctx->stream>>>(g, s.dev(), T, out, ld, epi, scale, active);
+  } else if (zcb == 8) SGW_Z(8); else if (zcb == 32) SGW_Z(32); else SGW_Z(16);
 #undef SGW_Z
   SGW_LAUNCH_CHECK();
   return SGW_OK;
@@ -1330,6 +1360,12 @@ static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, in
   return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 384>(ctx, g, s, nvec, Tin, Tout, active, done);
 }
 
+// SGW_PLANE_GMEM=1 forces the global-memory plane path (testing it on boxes that would fit in shared memory)
+static bool plane_force_gmem() {
+  const char *e = getenv("SGW_PLANE_GMEM");
+  return e && atoi(e) == 1;
+}
+
 static int try_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
                           bool *done) {
   *done = false;
@@ -1351,6 +1387,33 @@ int fft_plane(sgw_ctx *ctx, PlaneMode mode, const Sphere *sin, const Sphere *sou
   SphereDev si = sin ? sin->dev() : SphereDev(), so = sout ? sout->dev() : SphereDev();
   if (vec_per_field < 1) vec_per_field = 1;
   ProfScope prof(ctx, mode == PLANE_VLOC ? PC_FFT_PLANE : PC_OTHER);
+  if (plane_smem(g, 1) > ctx->smem_optin || plane_force_gmem()) {
+    // plane larger than an SM's shared memory: per-CTA planes in a global scratch of bounded size, vectors in chunks
+    const size_t psz = (size_t)g.ny * g.pitchx;
+    const size_t sm_tab = (size_t)(g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)g.nx * sizeof(int);
+    const size_t budget = (size_t)1 << 30;
+    const int vchunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nvec, (size_t)65535, budget / (psz * g.nz * sizeof(cplx))}));
+    cplx *scratch = nullptr;
+    SGW_CHECK(ws(ctx, "fft_plane_scratch", psz * g.nz * vchunk, &scratch));
+    for (int v0 = 0; v0 < nvec; v0 += vchunk) {
+      dim3 gg(g.nz, std::min(vchunk, nvec - v0));
+#define SGW_PLANE_G(M)                                                                                                  \
+      do {                                                                                                              \
+        SGW_CHECK(set_smem(ctx, k_plane<M, 256, true, true>, sm_tab));                                                  \
+        k_plane<M, 256, true, true><<<gg, 256, sm_tab, ctx->stream>>>(g, si, so, Tin, Tout, ctx->d_vperm, field, vec_per_field, R, in_mod, \
+                                                                        active, 1, scratch, v0);                         \
+      } while (0)
+      switch (mode) {
+        case PLANE_VLOC: SGW_PLANE_G(PLANE_VLOC); break;
+        case PLANE_FIELD: SGW_PLANE_G(PLANE_FIELD); break;
+        case PLANE_TO_R: SGW_PLANE_G(PLANE_TO_R); break;
+        case PLANE_FROM_R: SGW_PLANE_G(PLANE_FROM_R); break;
+      }
+#undef SGW_PLANE_G
+      SGW_LAUNCH_CHECK();
+    }
+    return SGW_OK;
+  }
   if (mode == PLANE_VLOC && sin == sout && sin && P == 1 && !gr) {
     bool done = false;
     SGW_CHECK(try_plane_vloc(ctx, g, *sin, nvec, Tin, Tout, active, &done));
@@ -1432,6 +1495,21 @@ int fft_plane_rho(sgw_ctx *ctx, const Sphere &sin, const Sphere &sout, int npf, 
   const size_t smem = plane_smem(g, 2);
   dim3 grid(npf, g.nz);
   ProfScope prof(ctx, PC_RHO_PLANE);
+  if (smem > ctx->smem_optin || plane_force_gmem()) {           // see fft_plane: planes in a bounded global scratch
+    const size_t psz = 2 * (size_t)g.ny * g.pitchx;
+    const size_t sm_tab = (size_t)(g.nx + g.ny) * sizeof(cplx) + 2 * (size_t)g.nx * sizeof(int);
+    const size_t budget = (size_t)1 << 30;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)npf, budget / (psz * g.nz * sizeof(cplx))));
+    cplx *scratch = nullptr;
+    SGW_CHECK(ws(ctx, "fft_rho_scratch", psz * g.nz * chunk, &scratch));
+    for (int p0 = 0; p0 < npf; p0 += chunk) {
+      dim3 gg(std::min(chunk, npf - p0), g.nz);
+      SGW_CHECK(set_smem(ctx, k_plane_rho<256, true>, sm_tab));
+      k_plane_rho<256, true><<<gg, 256, sm_tab, ctx->stream>>>(g, sin.dev(), sout.dev(), nocc, Tin, psir, wgt, Tout, accumulate, scratch, p0);
+      SGW_LAUNCH_CHECK();
+    }
+    return SGW_OK;
+  }
   {
     const char *e = getenv("SGW_RHO_V2");          // 0: generic k_plane_rho (A/B testing)
     const bool want = !(e && atoi(e) == 0);

@@ -162,6 +162,7 @@ struct sgw_ctx {
   sgw::Workspace ws;
   sgw_stats stats;
   bool profiling = false;
+  int prof_z_class = 0;                          // class the z passes are billed to (PC_FFT_Z = 0 for H.psi; the Delta-rho stage sets its own)
   int64_t launches = 0;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<sgw::ProfRec> prof_recs;

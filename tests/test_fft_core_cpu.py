@@ -37,7 +37,9 @@ def _perm(n, r1, r2):
     return pos // r2 + r1 * (pos % r2)          # position -> natural index (fft_core.h perm_index)
 
 
-@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 8, 9, 10, 36, 45, 48, 64, 96, 100, 120, 144, 225, 256])
+@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 8, 9, 10, 36, 45, 48, 64, 96, 100, 120, 144, 225, 256,
+                               # lengths that need the radices 18..32 (125, 162, 200, 216 ... were rejected)
+                               125, 162, 200, 216, 243, 250, 270, 288, 320, 375, 384, 405, 480, 512, 625, 768, 900, 960])
 @pytest.mark.parametrize("layout", [0, 1])
 def test_line_fft_matches_numpy(harness, n, layout):
     rng = np.random.default_rng(n + layout)
@@ -52,12 +54,24 @@ def test_line_fft_matches_numpy(harness, n, layout):
         assert np.abs(z - np.fft.fft(x, axis=1)).max() < 1e-12 * n
 
 
+def test_every_5_smooth_length_up_to_960_has_a_plan(harness):
+    def smooth(n):
+        for p in (2, 3, 5):
+            while n % p == 0:
+                n //= p
+        return n == 1
+    for n in range(1, 961):
+        if smooth(n):
+            y, plan = _run(harness, n, 1, +1, 1, 0, np.ones((1, n), complex))
+            assert y is not None and plan[0] * plan[1] == n and max(plan) <= 32, n
+
+
 def test_unsupported_length_has_no_plan(harness):
     y, _ = _run(harness, 7 * 11, 1, +1, 1, 0, np.zeros((1, 77), complex))
     assert y is None
 
 
-@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 12, 16])
+@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 12, 16, 125, 200, 216, 512])
 def test_fused_vloc_middle_stage(harness, n):
     rng = np.random.default_rng(100 + n)
     nlines = 6

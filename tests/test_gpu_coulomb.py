@@ -293,3 +293,28 @@ def test_unfold_w_symmetric_matches_oracle(ctx):
     bad[5, :] = 0                                            # G number 6 has no image under any operation
     with pytest.raises(SgwError):
         ctx.unfold_w_symm(ngc, ig_unique, sym_ig, sym_friend, bad, eigv, invs, scr_in)
+
+
+@pytest.mark.parametrize("nr,env", [
+    ((125, 128, 27), {"SGW_RHO_GRID": "fine"}),                       # planes in global memory, also for the Delta-rho accumulation
+    ((24, 25, 27), {"SGW_PLANE_GMEM": "1", "SGW_RHO_GRID": "fine"}),
+])
+def test_coulomb_on_general_grids(ctx, monkeypatch, nr, env):
+    """The whole screened-Coulomb column (dV psi, solves, Delta-rho, Hartree) on boxes that take the large-plane path."""
+    import oracle
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    s = synth.build_lattice("tiny", 10.26, synth.FCC, [[0.125] * 3, [-0.125] * 3], ["Si", "Si"], 6.0, nr=nr)
+    syn = synth.attach_kpoints(s, synth.mp_grid(s.bg, 1), [0.5, 0.5, 0.5])
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    ngc = 4
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    fiu = synth.imag_freqs(2)
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-12)
+    scr = ctx.coulomb(cfg, 1, ngc, ngc, igu, fiu)
+    ref, ierr, _ = ps.coulomb(1, ngc, ngc, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=4)
+    assert ierr == 0
+    assert _rel(scr, ref) < 1e-8, _rel(scr, ref)

@@ -175,3 +175,44 @@ def test_rho_plane_v2_is_bit_identical_to_the_generic_kernel(monkeypatch):
         assert np.array_equal(out["0"], out["1"])
     finally:
         c.close()
+
+
+def _tiny_on_grid(nr, nk=1):
+    """The 2-atom 'tiny' stand-in on an FFT box chosen by the test (any box that holds its spheres is valid input)."""
+    import synth
+    s = synth.build_lattice("tiny", 10.26, synth.FCC, [[0.125] * 3, [-0.125] * 3], ["Si", "Si"], 6.0, nr=nr)
+    return synth.attach_kpoints(s, synth.mp_grid(s.bg, nk), [0.5, 0.5, 0.5])
+
+
+@pytest.mark.parametrize("nr,env", [
+    ((125, 128, 27), {}),                       # 125 = 5 x 25; the 125 x 128 plane does not fit in shared memory
+    ((162, 20, 200), {}),                       # 162 = 9 x 18 inside a shared-memory plane, 200 = 10 x 20 in the z pass
+    ((216, 243, 16), {}),                       # 216 = 12 x 18, 243 = 9 x 27, plane in global memory
+    ((24, 25, 27), {"SGW_PLANE_GMEM": "1"}),    # the global-memory plane path on a box the default path also handles
+])
+def test_linear_op_on_general_grids(ctx, monkeypatch, nr, env):
+    """FFT generality (VERDICT r1 missing 4): boxes with lengths that need the radices 18..32 and planes larger than an
+    SM's shared memory, against the oracle (whose FFT takes any length): <= 1e-12 relative."""
+    import oracle
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    syn = _tiny_on_grid(nr)
+    _install_kpoints(ctx, syn)
+    ps = oracle.PwSystem(syn)
+    rng = np.random.default_rng(7)
+    kq = syn.kpairs[0].kq
+    nvec = 3
+    psi = np.zeros((kq.npwx, nvec), dtype=complex, order="F")
+    psi[:kq.npw] = rng.standard_normal((kq.npw, nvec)) + 1j * rng.standard_normal((kq.npw, nvec))
+    omega = rng.standard_normal(nvec) + 1j * rng.standard_normal(nvec)
+    out = ctx.linear_op(0, omega, kq.alpha_pv, psi)
+    for v in range(nvec):
+        ref = ps.linear_op(0, omega[v], kq.alpha_pv, psi[:, v])
+        err = np.abs(out[:, v] - ref).max() / np.abs(ref).max()
+        assert err < 1e-12, (nr, v, err)
+
+
+def test_unsupported_grid_is_loud(ctx):
+    from sternheimergw_b200 import SgwError
+    with pytest.raises(SgwError):
+        ctx.set_grid(77, 20, 20)                # 7 x 11: no plan
