@@ -911,17 +911,21 @@ struct ZTArgs {
   double scale;
 };
 
-template <int RZ1, int RZ2, int NT>
+// DB: two staging buffers for the input ranges, so that the bulk copy of the vector after next is in flight during a whole
+// iteration (with one buffer the copy can only be issued after stage 1 has consumed it and its latency is exposed: ncu showed
+// long_scoreboard 53 % in the mbarrier wait)
+template <int RZ1, int RZ2, int NT, bool DB>
 __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__ CUtensorMap tmap, ZTArgs a) {
   constexpr int NZ = RZ1 * RZ2, RZ1P = (RZ1 + 7) & ~7, TILE = NZ * ZB;
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * ZB, nc = min(ZB, a.ncol - c0);
   extern __shared__ __align__(128) unsigned char zsm[];
   cplx *tile = (cplx *)zsm;                       // [NZ][ZB]
-  cplx *in = tile + TILE;                         // [maxlen] staged entries of the block
-  cplx *tw = in + a.maxlen;
+  cplx *in0 = tile + TILE;                        // [maxlen] staged entries of the block (x 2 with DB)
+  cplx *in1 = DB ? in0 + a.maxlen : in0;
+  cplx *tw = in1 + a.maxlen;
   short *ztab = (short *)(tw + NZ);               // [ZB][RZ2][RZ1P], rebased to the block's first entry
-  unsigned long long *bar = (unsigned long long *)(ztab + ZB * RZ2 * RZ1P);
+  unsigned long long *bar = (unsigned long long *)(ztab + ZB * RZ2 * RZ1P);   // [2]
   const int p0 = a.col_ptr[c0], p1 = a.col_ptr[c0 + nc];
   const unsigned bytes = (unsigned)(p1 - p0) * (unsigned)sizeof(cplx);
   for (int i = tid; i < NZ; i += NT) tw[i] = a.twz[i];
@@ -934,24 +938,31 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__
     }
     ztab[i] = v;
   }
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_mbar_init(); }
   __syncthreads();
   auto next_active = [&](int v) {
     while (v < a.nvec && a.active && !a.active[v]) v += gridDim.y;
     return v;
   };
   int v = next_active(blockIdx.y);
-  if (tid == 0 && v < a.nvec && bytes) {
-    mbar_expect_tx(bar, bytes);
-    tma_load_1d(in, a.vec + (long)v * a.ld + p0, bytes, bar);
+  int v1 = v < a.nvec ? next_active(v + gridDim.y) : a.nvec;
+  if (tid == 0 && bytes) {
+    if (v < a.nvec) { mbar_expect_tx(bar, bytes); tma_load_1d(in0, a.vec + (long)v * a.ld + p0, bytes, bar); }
+    if (DB && v1 < a.nvec) { mbar_expect_tx(bar + 1, bytes); tma_load_1d(in1, a.vec + (long)v1 * a.ld + p0, bytes, bar + 1); }
   }
-  unsigned parity = 0u;
+  unsigned parity0 = 0u, parity1 = 0u;
+  int sb = 0;                                     // staging buffer of the current vector
   const cplx zero = cmake(0.0, 0.0);
   while (v < a.nvec) {
-    const int vn = next_active(v + gridDim.y);
+    const int vn = v1;
+    const int vnn = vn < a.nvec ? next_active(vn + gridDim.y) : a.nvec;
     if (tid == 0) bulk_wait_read<0>();            // the previous vector's store has finished reading the tile
     __syncthreads();
-    if (bytes) { mbar_wait(bar, parity); parity ^= 1u; }
+    const cplx *in = (DB && sb) ? in1 : in0;
+    if (bytes) {
+      if (DB && sb) { mbar_wait(bar + 1, parity1); parity1 ^= 1u; }
+      else { mbar_wait(bar, parity0); parity0 ^= 1u; }
+    }
     {  // inverse z, stage 1 (strided DFT_RZ1 + twiddle): inputs gathered from the staged range; all ZB columns are written
       constexpr int ntask = ZB * RZ2;
       for (int task = tid; task < ntask; task += NT) {
@@ -981,9 +992,17 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__
       }
     }
     __syncthreads();
-    if (tid == 0 && vn < a.nvec && bytes) {       // the staging buffer is free: fetch the next vector's entries
-      mbar_expect_tx(bar, bytes);
-      tma_load_1d(in, a.vec + (long)vn * a.ld + p0, bytes, bar);
+    if (tid == 0 && bytes) {                      // this staging buffer is free: fetch the entries of the next vector that uses it
+      if (DB) {
+        if (vnn < a.nvec) {
+          unsigned long long *bb = sb ? bar + 1 : bar;
+          mbar_expect_tx(bb, bytes);
+          tma_load_1d(sb ? in1 : in0, a.vec + (long)vnn * a.ld + p0, bytes, bb);
+        }
+      } else if (vn < a.nvec) {
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(in0, a.vec + (long)vn * a.ld + p0, bytes, bar);
+      }
     }
     stage_contig<RZ2, +1>(tile, ZB, nullptr, 1, ZB, RZ1, tw, false, tid, NT);
     fence_proxy_async();                          // generic-proxy writes of the tile -> visible to the TMA engine
@@ -993,6 +1012,8 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__
       bulk_commit();
     }
     v = vn;
+    v1 = vnn;
+    if (DB) sb ^= 1;
   }
   if (tid == 0) bulk_wait_read<0>();              // shared memory must stay alive until the last store has read it
 }
@@ -1182,7 +1203,9 @@ template <int RZ1, int RZ2>
 static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const ZTArgs &a) {
   constexpr int NZ = RZ1 * RZ2, NT = 128;
   const int ncb = (a.ncol + ZB - 1) / ZB;
-  const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB + (size_t)a.maxlen + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
+  const char *edb = getenv("SGW_ZG2R_DB");                      // 0: one input staging buffer (A/B)
+  const bool db = !(edb && atoi(edb) == 0);
+  const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB + (size_t)a.maxlen * (db ? 2 : 1) + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
                           : sizeof(cplx) * ((size_t)NZ * ZB + NZ) + (sizeof(double) + sizeof(short)) * (size_t)a.maxlen + 32;
   auto go = [&](auto kern) -> int {
     SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1193,7 +1216,7 @@ static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const
     kern<<<grid, NT, smem, ctx->stream>>>(tm, a);
     return SGW_OK;
   };
-  if (g2r) return go(k_zpass_g2r_tma<RZ1, RZ2, NT>);
+  if (g2r) return db ? go(k_zpass_g2r_tma<RZ1, RZ2, NT, true>) : go(k_zpass_g2r_tma<RZ1, RZ2, NT, false>);
   if (a.maxlen <= 5 * NT) return go(k_zpass_r2g_tma<RZ1, RZ2, NT, 5>);
   return go(k_zpass_r2g_tma<RZ1, RZ2, NT, (ZB * NZ + NT - 1) / NT>);
 }

@@ -72,6 +72,8 @@ def _gather_blocks(blocks_c: np.ndarray, counts, root: int, all_ranks: bool, dev
         full_h = recv.numpy().view(np.complex128).reshape((world, nmax) + tail)
     else:
         full_h = full.cpu().numpy().view(np.complex128).reshape((world, nmax) + tail)
+    if all(int(c) == nmax for c in counts):                # equal blocks: the received buffer already is the concatenation
+        return full_h.reshape((world * nmax,) + tail)
     out = np.empty((int(sum(counts)),) + tail, dtype=np.complex128)
     off = 0
     for r in range(world):
@@ -96,6 +98,34 @@ def gather_columns(scr_loc: np.ndarray, num_task, root: int = 0, device=None, al
     blocks = np.ascontiguousarray(np.asfortranarray(scr_loc).T)          # a view for Fortran-ordered input
     out = _gather_blocks(blocks, [int(x) for x in num_task], root, all_ranks, device)
     return None if out is None else out.T                                 # (ngc, nfs, ntot), Fortran order, no copy
+
+
+def exchange_frequencies(scr_loc: np.ndarray, num_task, num_freq, device=None):
+    """Columns of all perturbations for THIS rank's share of the frequencies: rank r holds scr_loc(ngc, nfs, num_task[r]) and
+    receives (ngc, num_freq[rank], sum(num_task)) -- one all_to_all (ncclSend/Recv pairs over NVLink on the GPU box) that moves
+    1/world of what an all_gather of every column to every rank would.  The pieces are C-contiguous (ntask, nf, ngc) blocks, so
+    the receive buffer IS the result: no assembly copy."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = _device(dist, device)
+    ngc, nfs, ntl = scr_loc.shape
+    blocks = np.asfortranarray(scr_loc).T                                  # (ntask_loc, nfs, ngc), C order, a view
+    f_off = np.concatenate([[0], np.cumsum(num_freq)]).astype(int)
+    nf_me = int(num_freq[rank])
+    send = np.empty(ntl * nfs * ngc, dtype=np.complex128)
+    in_splits, off = [], 0
+    for d in range(world):
+        piece = blocks[:, f_off[d]:f_off[d + 1], :]
+        send[off:off + piece.size] = piece.reshape(-1)
+        in_splits.append(2 * piece.size)
+        off += piece.size
+    out_splits = [2 * int(num_task[r]) * nf_me * ngc for r in range(world)]
+    ts = torch.from_numpy(send.view(np.float64)).to(dev)
+    tr = torch.empty(sum(out_splits), dtype=torch.float64, device=dev)
+    dist.all_to_all_single(tr, ts, out_splits, in_splits)
+    recv = tr.cpu().numpy().view(np.complex128).reshape(int(sum(num_task)), nf_me, ngc)
+    return recv.T                                                          # (ngc, nf_me, ntot), Fortran order
 
 
 def gather_frequencies(w_loc: np.ndarray, num_freq, root: int = 0, device=None):
@@ -132,12 +162,12 @@ def do_stern_q(coulomb_fn, config, num_g_corr, ig_unique, fiu, unfold_fn=None, i
         # The reference unfolds and inverts all frequencies on the root image (do_stern.f90:220-232) -- a serial tail of
         # O(ngc^3 nfs) that holds strong scaling back.  The frequencies are independent, so every rank takes a contiguous
         # share of them (parallel_task's rule again), unfolds and inverts its slices on its own GPU and the root gathers.
-        scr_all = gather_columns(scr_loc, num_task, root=root, all_ranks=True)
-        t1 = time.perf_counter()
         f_first, f_last, num_freq = parallel_task(world, rank, len(fiu))
         sl = slice(f_first - 1, f_first - 1 + num_freq[rank])
+        scr_me = exchange_frequencies(scr_loc, num_task, num_freq)           # this rank's frequencies of every column
+        t1 = time.perf_counter()
         if num_freq[rank] > 0:
-            w_loc = unfold_fn(num_g_corr, ig_unique, np.asfortranarray(scr_all[:, sl, :]))
+            w_loc = unfold_fn(num_g_corr, ig_unique, scr_me)
             if eps_head is not None:
                 w_loc[0, 0, :] = np.asarray(eps_head)[sl]
             if invert_fn is not None:
