@@ -120,6 +120,17 @@ int sgw_set_nksq(sgw_ctx *ctx, int nksq);
 int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *nl_igk_k, int nbnd,
                   const sgw_cplx *evc, const double *et, double wk);
 
+/* Metals.  [QE] klist (lgauss, degauss, ngauss) and ener (ef) as read by LR_Modules/orthogonalize.f90, which solve_linter.f90:337
+ * calls: with lgauss != 0 the right-hand sides are built with the smeared projector of S. de Gironcoli, PRB 51, 6773 (1995) and
+ * the solutions are scaled by wg(ibnd, ikk) / wk(ikk) (solve_linter.f90:373).  ngauss: -99 Fermi-Dirac, -1 Marzari-Vanderbilt,
+ * 0 Gaussian, n > 0 Methfessel-Paxton.  lgauss = 0 (default) is the insulator path.  Direct solver only. */
+int sgw_set_smearing(sgw_ctx *ctx, int lgauss, double ef, double degauss, int ngauss);
+/* per (k, k+q) pair, after sgw_set_kpair: ALL nbnd bands of evq (npwx x nbnd, the first nbnd_occ(ikq) of them are the ones
+ * given to sgw_set_kpoint) with et(:, ikq), the number of bands of the solver loop nbnd_occ(ikk) <= nbnd of sgw_set_kpair, and
+ * wg(ibnd, ikk) / wk(ikk) for those bands */
+int sgw_set_kpair_metal(sgw_ctx *ctx, int ik, int nbnd, const sgw_cplx *evq_all, const double *et_q, int nbnd_occ_k,
+                        const double *wg_over_wk);
+
 /* control_gw globals of the self-consistent branch (main/src/gw_input.yml: num_iter_coul -> niter_gw, alpha_mix,
  * tr2_gw, num_mix_coul -> nmix_gw <= 8 = maxter of mix_pot_c.f90:76): alpha_mix has niter_gw entries. */
 int sgw_set_mixing(sgw_ctx *ctx, int niter_gw, const double *alpha_mix, double tr2_gw, int nmix_gw);

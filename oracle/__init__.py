@@ -178,6 +178,29 @@ def fft3d(f, sign):
 
 
 # ------------------------------------------------------------------ plane-wave half
+class MetalPair(C.Structure):
+    _fields_ = [("nbnd", c_int), ("evq_all", c_void_p), ("et_q", c_void_p), ("nocc_k", c_int), ("wg_over_wk", c_void_p)]
+
+
+def wgauss(x, n):
+    L = lib()
+    L.orc_wgauss.restype = c_double
+    return float(L.orc_wgauss(c_double(x), c_int(n)))
+
+
+def w0gauss(x, n):
+    L = lib()
+    L.orc_w0gauss.restype = c_double
+    return float(L.orc_w0gauss(c_double(x), c_int(n)))
+
+
+def metal_weight(e_i, e_j, j_in_projector, alpha_pv, ef, degauss, ngauss):
+    L = lib()
+    L.orc_metal_weight.restype = c_double
+    return float(L.orc_metal_weight(c_double(e_i), c_double(e_j), c_int(1 if j_in_projector else 0), c_double(alpha_pv),
+                                    c_double(ef), c_double(degauss), c_int(ngauss)))
+
+
 class PwSystem:
     """Keeps numpy arrays alive and exposes the C structs for a synthetic system (see synth/)."""
 
@@ -208,6 +231,25 @@ class PwSystem:
         s.g = self._k(np.ascontiguousarray(syn.g.T, dtype=np.float64))  # (ngm,3) row-major == 3 x ngm col-major
         s.nl = self._k(np.ascontiguousarray(syn.nl, dtype=np.int32))
         self.sys = s
+        # metals: the oracle reads klist/ener like the reference does, from globals that `_smearing()` sets before every call
+        self.metal = getattr(syn, "metal", None)
+        if self.metal is not None:
+            self.metal_pairs = (MetalPair * len(syn.kpairs))()
+            for i, m in enumerate(self.metal.pairs):
+                self.metal_pairs[i].nbnd = m.evq_all.shape[1]
+                self.metal_pairs[i].evq_all = self._k(np.asfortranarray(m.evq_all, dtype=np.complex128))
+                self.metal_pairs[i].et_q = self._k(np.ascontiguousarray(m.et_q, dtype=np.float64))
+                self.metal_pairs[i].nocc_k = m.nocc_k
+                self.metal_pairs[i].wg_over_wk = self._k(np.ascontiguousarray(m.wg_over_wk, dtype=np.float64))
+
+    def _smearing(self):
+        L = lib(self.native)
+        L.orc_set_smearing.argtypes = [c_int, c_double, c_double, c_int, c_int, c_void_p]
+        if self.metal is None:
+            L.orc_set_smearing(0, 0.0, 0.0, 0, 0, None)
+        else:
+            L.orc_set_smearing(1, self.metal.ef, self.metal.degauss, self.metal.ngauss, len(self.metal.pairs),
+                               C.cast(self.metal_pairs, c_void_p))
 
     def _k(self, a):
         self._keep.append(a)
@@ -258,6 +300,7 @@ class PwSystem:
         return xx, ierr, {"n_op": st.n_op, "n_outer": st.n_outer, "solver_used": st.solver_used}
 
     def solve_linter(self, dvbare, freq, cfg: SolverCfg, nthreads=1):
+        self._smearing()
         L = lib(self.native)
         nnr = int(np.prod(self.syn.nr))
         dvbare, freq = _c16(np.ravel(dvbare, order="F")), _c16(freq)
@@ -269,6 +312,7 @@ class PwSystem:
 
     def solve_linter_iter(self, num_iter, alpha_mix, tr2_gw, nmix_gw, dvbare, freq, cfg: SolverCfg, nthreads=1):
         """solve_linter.f90 with num_iter > 1 (self-consistent branch + mix_potential_c): returns dvscfin(nnr, nfreq)."""
+        self._smearing()
         L = lib(self.native)
         nnr = int(np.prod(self.syn.nr))
         dvbare, freq = _c16(np.ravel(dvbare, order="F")), _c16(freq)
@@ -282,6 +326,7 @@ class PwSystem:
         return out, ierr, {"n_op": st.n_op, "n_outer": st.n_outer, "iter": it.value}
 
     def coulomb(self, igstart, ngc, ntask, ig_unique, fiu, cfg: SolverCfg, nthreads=1):
+        self._smearing()
         L = lib(self.native)
         fiu = _c16(fiu)
         ig_unique = np.ascontiguousarray(ig_unique, dtype=np.int32)
@@ -296,6 +341,7 @@ class PwSystem:
         lib(self.native).orc_set_band_window(c_int(lo), c_int(hi))
 
     def coulomb_q0G0(self, fiu, cfg: SolverCfg):
+        self._smearing()
         L = lib(self.native)
         fiu = _c16(fiu)
         eps = np.zeros(fiu.size, dtype=np.complex128)

@@ -369,6 +369,104 @@ static int mix_potential_c(orc_mix_state *m, size_t ndim, zcplx *vout, zcplx *vi
   return 0;
 }
 
+/* ---------------------------------------------------------------- metals ([QE] klist: lgauss, degauss, ngauss; ener: ef)
+ * The QE sources are not part of the reference tree, so this block restates the PUBLISHED algorithm -- S. de Gironcoli,
+ * PRB 51, 6773 (1995), eqs. (13)-(17), in the form of QE 6.3 LR_Modules/orthogonalize.f90 (lgauss branch), Modules/wgauss.f90 and
+ * Modules/w0gauss.f90 -- and is "parity unpinned" (no reference vector exists for it).  Anchors: tests/test_oracle_metal.py. */
+static int g_lgauss = 0, g_ngauss = 0, g_metal_nks = 0;
+static double g_ef = 0.0, g_degauss = 0.0;
+static const orc_metal_pair *g_metal = NULL;
+void orc_set_smearing(int lgauss, double ef, double degauss, int ngauss, int nks, const orc_metal_pair *pairs) {
+  g_lgauss = lgauss; g_ef = ef; g_degauss = degauss; g_ngauss = ngauss; g_metal_nks = nks; g_metal = pairs;
+}
+
+/* occupation function theta~(x), x = (ef - e)/degauss: ngauss = -99 Fermi-Dirac, -1 Marzari-Vanderbilt cold smearing,
+ * 0 Gaussian, n > 0 Methfessel-Paxton of order n */
+double orc_wgauss(double x, int n) {
+  const double maxarg = 200.0;
+  if (n == -99) {
+    if (x < -maxarg) return 0.0;
+    if (x > maxarg) return 1.0;
+    return 1.0 / (1.0 + exp(-x));
+  }
+  if (n == -1) {
+    const double xp = x - 1.0 / sqrt(2.0), arg = fmin(200.0, xp * xp);
+    return 0.5 * erf(xp) + 1.0 / sqrt(2.0 * M_PI) * exp(-arg) + 0.5;
+  }
+  double w = 0.5 * erfc(-x);                                   /* gauss_freq(x sqrt 2) */
+  if (n == 0) return w;
+  double hd = 0.0, hp = exp(-fmin(200.0, x * x)), a = 1.0 / sqrt(M_PI);
+  int ni = 0;
+  for (int i = 1; i <= n; ++i) {
+    hd = 2.0 * x * hp - 2.0 * ni * hd;
+    ++ni;
+    a = -a / (i * 4.0);
+    w -= a * hd;
+    hp = 2.0 * x * hd - 2.0 * ni * hp;
+    ++ni;
+  }
+  return w;
+}
+/* its derivative delta~(x) */
+double orc_w0gauss(double x, int n) {
+  const double sqrtpm1 = 1.0 / sqrt(M_PI);
+  if (n == -99) return fabs(x) <= 36.0 ? 1.0 / (2.0 + exp(-x) + exp(x)) : 0.0;
+  if (n == -1) {
+    const double xp = x - 1.0 / sqrt(2.0), arg = fmin(200.0, xp * xp);
+    return sqrtpm1 * exp(-arg) * (2.0 - sqrt(2.0) * x);
+  }
+  const double arg = fmin(200.0, x * x);
+  double w = exp(-arg) * sqrtpm1;
+  if (n == 0) return w;
+  double hd = 0.0, hp = exp(-arg), a = sqrtpm1;
+  int ni = 0;
+  for (int i = 1; i <= n; ++i) {
+    hd = 2.0 * x * hp - 2.0 * ni * hd;
+    ++ni;
+    a = -a / (i * 4.0);
+    hp = 2.0 * x * hd - 2.0 * ni * hp;
+    ++ni;
+    w += a * hp;
+  }
+  return w;
+}
+/* weight of <evq_j|dvpsi_i> in the metallic projector (orthogonalize.f90, lgauss): e_i = et(ibnd, ikk), e_j = et(jbnd, ikq) */
+double orc_metal_weight(double e_i, double e_j, int j_in_projector, double alpha_pv, double ef, double degauss, int ngauss) {
+  const double wg1 = orc_wgauss((ef - e_i) / degauss, ngauss);
+  const double w0g = orc_w0gauss((ef - e_i) / degauss, ngauss) / degauss;
+  const double wgp = orc_wgauss((ef - e_j) / degauss, ngauss);
+  const double deltae = e_j - e_i;
+  const double theta = orc_wgauss(deltae / degauss, 0);
+  double wwg = wg1 * (1.0 - theta) + wgp * theta;
+  if (j_in_projector) {
+    if (fabs(deltae) > 1.0e-5) wwg += alpha_pv * theta * (wgp - wg1) / deltae;
+    else wwg -= alpha_pv * theta * w0g;                          /* the limit of the 0/0 ratio */
+  }
+  return wwg;
+}
+/* metallic branch: ps(j, i) = wwg(j, i) <evq_j|dvpsi_i> over ALL nbnd bands at k+q, dvpsi_i *= theta~_F,i, dvpsi <- evq ps - dvpsi */
+static void orthogonalize_metal(const orc_kpair *kp, const orc_metal_pair *mp, zcplx *dvpsi) {
+  const orc_kpoint *kq = &kp->kq;
+  const int npwx = kq->npwx, npwq = kq->npw, nb = mp->nbnd, nocc_k = mp->nocc_k;
+  zcplx *ps = calloc((size_t)nb * nocc_k, sizeof(zcplx));
+  for (int ib = 0; ib < nocc_k; ++ib) {
+    const double wg1 = orc_wgauss((g_ef - kp->et[ib]) / g_degauss, g_ngauss);
+    for (int jb = 0; jb < nb; ++jb) {
+      zcplx sum = 0.0;
+      for (int ig = 0; ig < npwq; ++ig) sum += conj(mp->evq_all[ig + (size_t)npwx * jb]) * dvpsi[ig + (size_t)npwx * ib];
+      ps[jb + (size_t)nb * ib] = orc_metal_weight(kp->et[ib], mp->et_q[jb], jb < kq->nbnd_occ, kq->alpha_pv, g_ef, g_degauss, g_ngauss) * sum;
+    }
+    for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ib] *= wg1;
+  }
+  for (int ib = 0; ib < nocc_k; ++ib)
+    for (int ig = 0; ig < npwq; ++ig) {
+      zcplx sum = 0.0;
+      for (int jb = 0; jb < nb; ++jb) sum += mp->evq_all[ig + (size_t)npwx * jb] * ps[jb + (size_t)nb * ib];
+      dvpsi[ig + (size_t)npwx * ib] = sum - dvpsi[ig + (size_t)npwx * ib];
+    }
+  free(ps);
+}
+
 /* [QE] orthogonalize, insulator (solve_linter.f90:337,409): dvpsi <- evq (evq^H dvpsi) - dvpsi = -P_c^+ dvpsi */
 static void orthogonalize(const orc_kpoint *kq, zcplx *dvpsi) {
   const int npwx = kq->npwx, npwq = kq->npw, nocc = kq->nbnd_occ;
@@ -423,7 +521,9 @@ int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_globa
     for (int ik = 0; ik < sys->nks; ++ik) {                             /* :288 */
       const orc_kpair *kp = &sys->kp[ik];
       const orc_kpoint *kq = &kp->kq;
-      const int npwx = kq->npwx, npwq = kq->npw, nbnd = kp->nbnd, nocc = kq->nbnd_occ;
+      const orc_metal_pair *mp = (g_lgauss && g_metal && ik < g_metal_nks) ? &g_metal[ik] : NULL;
+      /* bands of the loop :367 = nbnd_occ(ikk); the projector inside the operator uses nbnd_occ(ikq) = kq->nbnd_occ */
+      const int npwx = kq->npwx, npwq = kq->npw, nbnd = kp->nbnd, nocc = mp ? mp->nocc_k : kq->nbnd_occ;
       zcplx *dpsi = calloc((size_t)npwx * nbnd * num_omega, sizeof(zcplx));
 
       if (first_iteration) {
@@ -444,7 +544,7 @@ int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_globa
           dvpsi_bare[ik] = malloc(sizeof(zcplx) * (size_t)npwx * nbnd);
           memcpy(dvpsi_bare[ik], dvpsi, sizeof(zcplx) * (size_t)npwx * nbnd);
         }
-        orthogonalize(kq, dvpsi);                                       /* :337 */
+        if (mp) orthogonalize_metal(kp, mp, dvpsi); else orthogonalize(kq, dvpsi);   /* :337 */
         config.threshold = direct_solver ? cfg_global->threshold : 1.0e-2;   /* :348-362 */
         /* band loop :367-374 */
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic) reduction(+ : nop_all) reduction(max : nouter_max)
@@ -466,6 +566,8 @@ int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_globa
             ierr_all = ierr;                                            /* :370 errore */
           }
           /* dpsi *= wg/wk (=1: fully occupied insulator bands)  :373 */
+          if (mp)
+            for (size_t i = 0; i < (size_t)npwq * num_omega; ++i) xx[i] *= mp->wg_over_wk[ibnd];
           for (int io = 0; io < num_omega; ++io)
             memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx + (size_t)npwq * io, sizeof(zcplx) * npwq);
           nop_all += s1.n_op;
@@ -489,7 +591,7 @@ int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_globa
             for (int ig = 0; ig < npwq; ++ig) dvpsi[ig + (size_t)npwx * ibnd] += aux[kq->nl_igk[ig] - 1];   /* cft_wave(-1) adds */
           }
           free(aux);
-          orthogonalize(kq, dvpsi);                                     /* :409 */
+          if (mp) orthogonalize_metal(kp, mp, dvpsi); else orthogonalize(kq, dvpsi);   /* :409 */
           const int iomega = zero_freq ? ifreq + nfreq - 1 : ifreq + nfreq;   /* :426-430 */
           orc_pw_op op;
           op.grid = g;

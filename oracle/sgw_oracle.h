@@ -135,6 +135,20 @@ typedef struct {
   const int32_t *nl;      /* ngm, 1-based dffts%nl */
 } orc_system;
 
+/* metals: what [QE] orthogonalize (lgauss) and solve_linter.f90:373 read beyond the insulator case, per (k, k+q) pair */
+typedef struct {
+  int nbnd;                 /* all bands of evq (>= nbnd_occ(ikq)) */
+  const zcplx *evq_all;     /* npwx x nbnd at k+q */
+  const double *et_q;       /* nbnd eigenvalues at k+q (Ry) */
+  int nocc_k;               /* nbnd_occ(ikk): bands of the solver loop */
+  const double *wg_over_wk; /* nocc_k: wg(ibnd, ikk) / wk(ikk) */
+} orc_metal_pair;
+/* klist/ener globals; lgauss = 0 restores the insulator path.  `pairs` (nks entries) must outlive the calls that use it. */
+void orc_set_smearing(int lgauss, double ef, double degauss, int ngauss, int nks, const orc_metal_pair *pairs);
+double orc_wgauss(double x, int n);
+double orc_w0gauss(double x, int n);
+double orc_metal_weight(double e_i, double e_j, int j_in_projector, double alpha_pv, double ef, double degauss, int ngauss);
+
 /* solve_linter.f90:55-624, direct branch (num_iter = 1).  drhoscf: nnr x nfreq */
 int orc_solve_linter(const orc_system *sys, const orc_solver_cfg *cfg, const zcplx *dvbarein, int nfreq,
                      const zcplx *freq, zcplx *drhoscf, orc_stats *st, int nthreads);

@@ -14,7 +14,7 @@ SYMBOLS = [
     "sgw_create", "sgw_destroy", "sgw_set_stream", "sgw_last_error", "sgw_get_stats", "sgw_set_profiling", "sgw_release_workspace", "sgw_unfold_w_symm", "sgw_device_synchronize",
     "sgw_get_profile", "sgw_profile_class_name", "sgw_set_message_callback",
     "sgw_set_grid", "sgw_set_vloc", "sgw_set_kpoint", "sgw_set_dense_operator", "sgw_linear_op",
-    "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
+    "sgw_solve_multishift", "sgw_set_system", "sgw_set_q", "sgw_set_nksq", "sgw_set_kpair", "sgw_set_smearing", "sgw_set_kpair_metal", "sgw_set_mixing", "sgw_set_solve_direct", "sgw_get_scf_iterations", "sgw_solve_linter",
     "sgw_coulomb", "sgw_get_rho_grid", "sgw_coulomb_q0G0", "sgw_unfold_w", "sgw_invert_epsilon", "sgw_green_function",
     "sgw_parallel_task", "sgw_bench_linear_op",
     "sgw_freqbins_num_freq", "sgw_pade_robust", "sgw_aaa_pole_residual", "sgw_coulpade", "sgw_analytic_coeff", "sgw_analytic_eval", "sgw_set_corr_grid", "sgw_invfft6",
@@ -82,6 +82,8 @@ def load():
         L.sgw_set_q.argtypes = [c_void_p, c_void_p]
         L.sgw_set_nksq.argtypes = [c_void_p, c_int]
         L.sgw_set_kpair.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_double]
+        L.sgw_set_smearing.argtypes = [c_void_p, c_int, c_double, c_double, c_int]
+        L.sgw_set_kpair_metal.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.sgw_set_mixing.argtypes = [c_void_p, c_int, c_void_p, c_double, c_int]
         L.sgw_set_solve_direct.argtypes = [c_void_p, c_int]
         L.sgw_get_scf_iterations.argtypes = [c_void_p]

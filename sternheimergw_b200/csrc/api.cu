@@ -123,6 +123,7 @@ static void free_slot(KSlot &k) {
 static void free_pair(KPair &p) {
   free_sphere(&p.sph_k);
   if (p.d_evc) dev_free(p.d_evc);
+  if (p.d_evq_all) dev_free(p.d_evq_all);
   p = KPair();
 }
 

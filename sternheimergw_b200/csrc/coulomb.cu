@@ -278,6 +278,58 @@ static int rho_grid_prepare(sgw_ctx *ctx, int ngc, const Sphere &rho_fine, bool 
   return SGW_OK;
 }
 
+// ---- metals: the smeared projector of [QE] LR_Modules/orthogonalize.f90 (lgauss branch) -------------------------------
+// occupation function theta~(x) and its derivative ([QE] Modules/wgauss.f90, w0gauss.f90): -99 Fermi-Dirac, -1 cold smearing,
+// 0 Gaussian, n > 0 Methfessel-Paxton
+static double wgauss(double x, int n) {
+  if (n == -99) return x < -200.0 ? 0.0 : (x > 200.0 ? 1.0 : 1.0 / (1.0 + exp(-x)));
+  if (n == -1) {
+    const double xp = x - 1.0 / sqrt(2.0), arg = std::min(200.0, xp * xp);
+    return 0.5 * erf(xp) + 1.0 / sqrt(2.0 * M_PI) * exp(-arg) + 0.5;
+  }
+  double w = 0.5 * erfc(-x);
+  double hd = 0.0, hp = exp(-std::min(200.0, x * x)), a = 1.0 / sqrt(M_PI);
+  int ni = 0;
+  for (int i = 1; i <= n; ++i) {
+    hd = 2.0 * x * hp - 2.0 * ni * hd; ++ni;
+    a = -a / (i * 4.0);
+    w -= a * hd;
+    hp = 2.0 * x * hd - 2.0 * ni * hp; ++ni;
+  }
+  return w;
+}
+static double w0gauss(double x, int n) {
+  const double sqrtpm1 = 1.0 / sqrt(M_PI);
+  if (n == -99) return fabs(x) <= 36.0 ? 1.0 / (2.0 + exp(-x) + exp(x)) : 0.0;
+  if (n == -1) {
+    const double xp = x - 1.0 / sqrt(2.0), arg = std::min(200.0, xp * xp);
+    return sqrtpm1 * exp(-arg) * (2.0 - sqrt(2.0) * x);
+  }
+  const double arg = std::min(200.0, x * x);
+  double w = exp(-arg) * sqrtpm1, hd = 0.0, hp = exp(-arg), a = sqrtpm1;
+  int ni = 0;
+  for (int i = 1; i <= n; ++i) {
+    hd = 2.0 * x * hp - 2.0 * ni * hd; ++ni;
+    a = -a / (i * 4.0);
+    hp = 2.0 * x * hd - 2.0 * ni * hp; ++ni;
+    w += a * hp;
+  }
+  return w;
+}
+// ps(j, r) *= wwg(j, band of r) ; dvpsi(:, r) *= theta~_F(band of r)   (band of r = r % nocc)
+__global__ void k_metal_scale(int nb, int nocc, int nrhs, int n, const double *__restrict__ wwg, const double *__restrict__ wg1,
+                              cplx *__restrict__ ps, cplx *__restrict__ dvpsi) {
+  const int r = blockIdx.y, ib = r % nocc;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nb) ps[(long)r * nb + e] = cscale(wwg[e + (long)nb * ib], ps[(long)r * nb + e]);
+  if (e < n) dvpsi[(long)r * n + e] = cscale(wg1[ib], dvpsi[(long)r * n + e]);
+}
+__global__ void k_band_scale(int n, int nocc, const double *__restrict__ f, cplx *__restrict__ v) {   // v(:, r) *= f(r % nocc)
+  const int r = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) v[(long)r * n + e] = cscale(f[r % nocc], v[(long)r * n + e]);
+}
+
 // ---- k-point lanes (see drho_block) ---------------------------------------------------------------------------
 __global__ void k_vadd(long n, cplx *__restrict__ a, const cplx *__restrict__ b) {            // a += b
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] = cadd(a[i], b[i]);
@@ -384,7 +436,10 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
       return SGW_E_STATE;
     }
     const KSlot &ks = ctx->slots[kp.slot];
-    const int n = ks.npwx, nocc = ks.nbnd;
+    // bands of the solver loop :367 = nbnd_occ(ikk); for insulators that is the nbnd_occ(ikq) of the projector panel
+    const bool metal = ctx->lgauss;
+    if (metal && (kp.nbnd_all <= 0 || !kp.d_evq_all)) { ctx->err = "lgauss is set but sgw_set_kpair_metal was not called for this pair"; return SGW_E_STATE; }
+    const int n = ks.npwx, nocc = metal ? kp.nocc_k : ks.nbnd;
     if (nocc > kp.nbnd) { ctx->err = "evc holds fewer bands than nbnd_occ"; return SGW_E_ARG; }
     const int nrhs = np * nocc;
     // psi_v(r) for the occupied bands: used by dV psi and again by the Delta-rho accumulation
@@ -422,10 +477,46 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     epi.mode = 0; epi.g2kin = nullptr; epi.psi = nullptr; epi.sigma = nullptr; epi.sigma_stride = 0; epi.keep_out = 0;
     SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nrhs, Tq, dvpsi, n, epi, nullptr));
     // [QE] orthogonalize (insulator): ps = evq^H dvpsi ; dvpsi <- evq ps - dvpsi   (solve_linter.f90:337)
-    const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
-    SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nrhs, &ps));
-    SGW_CHECK(gemm_ch_n(ctx, nocc, nrhs, ks.npw, evq, n, dvpsi, n, ps, nocc));
-    SGW_CHECK(gemm_n_n(ctx, n, nrhs, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), dvpsi, n));
+    double *d_wgk = nullptr;
+    if (!metal) {
+      const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
+      SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nrhs, &ps));
+      SGW_CHECK(gemm_ch_n(ctx, nocc, nrhs, ks.npw, evq, n, dvpsi, n, ps, nocc));
+      SGW_CHECK(gemm_n_n(ctx, n, nrhs, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), dvpsi, n));
+    } else {
+      // orthogonalize.f90, lgauss: ps(j, i) = wwg(j, i) <evq_j|dvpsi_i> over all nbnd bands at k+q, dvpsi_i *= theta~_F,i
+      const int nb = kp.nbnd_all;
+      std::vector<double> wwg((size_t)nb * nocc), wg1(nocc);
+      for (int ib = 0; ib < nocc; ++ib) {
+        wg1[ib] = wgauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss);
+        const double w0g = w0gauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss) / ctx->degauss;
+        for (int jb = 0; jb < nb; ++jb) {
+          const double wgp = wgauss((ctx->ef - kp.et_q[jb]) / ctx->degauss, ctx->ngauss);
+          const double deltae = kp.et_q[jb] - kp.et[ib];
+          const double theta = wgauss(deltae / ctx->degauss, 0);
+          double w = wg1[ib] * (1.0 - theta) + wgp * theta;
+          if (jb < ks.nbnd) w += fabs(deltae) > 1.0e-5 ? ks.alpha_pv * theta * (wgp - wg1[ib]) / deltae : -ks.alpha_pv * theta * w0g;
+          wwg[jb + (size_t)nb * ib] = w;
+        }
+      }
+      double *d_wwg = nullptr, *d_wg1 = nullptr;
+      SGW_CHECK(ws(ctx, "co_wwg", (size_t)nb * nocc, &d_wwg));
+      SGW_CHECK(ws(ctx, "co_wg1", (size_t)nocc, &d_wg1));
+      SGW_CHECK(ws(ctx, "co_wgk", (size_t)nocc, &d_wgk));
+      SGW_CUDA(cudaMemcpyAsync(d_wwg, wwg.data(), sizeof(double) * wwg.size(), cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaMemcpyAsync(d_wg1, wg1.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaMemcpyAsync(d_wgk, kp.wg_over_wk.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
+      SGW_CUDA(cudaStreamSynchronize(st));                                                   // host vectors go out of scope
+      SGW_CHECK(ws(ctx, "co_ps", (size_t)nb * nrhs, &ps));
+      SGW_CHECK(gemm_ch_n(ctx, nb, nrhs, ks.npw, kp.d_evq_all, n, dvpsi, n, ps, nb));
+      for (int r0 = 0; r0 < nrhs; r0 += 65535 / nocc * nocc) {
+        const int c = std::min(65535 / nocc * nocc, nrhs - r0);
+        dim3 gm((unsigned)((std::max(n, nb) + 255) / 256), (unsigned)c);
+        k_metal_scale<<<gm, 256, 0, st>>>(nb, nocc, c, n, d_wwg, d_wg1, ps + (size_t)r0 * nb, dvpsi + (size_t)r0 * n);
+        SGW_LAUNCH_CHECK();
+      }
+      SGW_CHECK(gemm_n_n(ctx, n, nrhs, nb, cmake(1.0, 0.0), kp.d_evq_all, n, ps, nb, cmake(-1.0, 0.0), dvpsi, n));
+    }
     // band loop :367-374 -> one batch; sigma = -(et + omega) :369
     {
       std::vector<cplx> sig((size_t)nshift * nrhs);
@@ -464,6 +555,16 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
       ctx->stats.ms_solver += ms;
     }
     // dpsi *= wg/wk (= 1 for fully occupied bands, :373); average +-omega; incdrhoscf with weight 2 wk / omega
+    if (metal) {
+      const long nv = (long)npf * nocc;
+      const int step = 65535 / nocc * nocc;
+      for (long v0 = 0; v0 < nv; v0 += step) {
+        const int c = (int)std::min<long>(step, nv - v0);
+        dim3 gs((unsigned)((n + 255) / 256), (unsigned)c);
+        k_band_scale<<<gs, 256, 0, st>>>(n, nocc, d_wgk, davg_all + (size_t)v0 * n);
+        SGW_LAUNCH_CHECK();
+      }
+    }
     const double wgt = 2.0 * kp.wk / ctx->omega_cell;
     const size_t per_pf = (size_t)nocc * ((size_t)rnz * sq.ncol + n) * sizeof(cplx);
     size_t budget = (size_t)2 << 30;
@@ -730,6 +831,10 @@ static int mix_potential_c_dev(sgw_ctx *ctx, MixState &m, long ndim, cplx *vout,
 static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global, int num_iter, const cplx *d_field,
                                   double meandvb, const FreqList &fl, const Sphere &rho, cplx *d_dvscfin, int *ierr_out,
                                   int *iter_done) {
+  if (ctx->lgauss) {
+    ctx->err = "metals (sgw_set_smearing) are supported by the direct solver only";
+    return SGW_E_UNSUPPORTED;
+  }
   const int nfreq = fl.nfreq, nshift = fl.num_omega;
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
   const long ndim = nnr * nfreq;
@@ -921,6 +1026,7 @@ int sgw_set_nksq(sgw_ctx *ctx, int nksq) {
   for (auto &p : ctx->pairs) {
     free_sphere(&p.sph_k);
     if (p.d_evc) dev_free(p.d_evc);
+    if (p.d_evq_all) dev_free(p.d_evq_all);
   }
   ctx->pairs.assign(nksq, KPair());
   return SGW_OK;
@@ -941,6 +1047,8 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   ctx->tables_version++;
   free_sphere(&kp.sph_k);
   if (kp.d_evc) { dev_free(kp.d_evc); kp.d_evc = nullptr; }
+  if (kp.d_evq_all) { dev_free(kp.d_evq_all); kp.d_evq_all = nullptr; }       // metal data belongs to the pair it was set for
+  kp.nbnd_all = kp.nocc_k = 0;
   SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
   const int npwx = ks.npwx;
   {
@@ -954,6 +1062,37 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   kp.slot = slot_kq; kp.npw_k = npw_k; kp.nbnd = nbnd; kp.wk = wk;
   kp.et.assign(et, et + nbnd);
   kp.set = true;
+  return SGW_OK;
+}
+
+int sgw_set_smearing(sgw_ctx *ctx, int lgauss, double ef, double degauss, int ngauss) {
+  if (!ctx) return SGW_E_ARG;
+  SGW_ARG(!lgauss || degauss > 0.0, "degauss must be positive for a metal");
+  SGW_ARG(ngauss == -99 || ngauss == -1 || (ngauss >= 0 && ngauss <= 10), "ngauss must be -99, -1 or 0..10");
+  ctx->lgauss = lgauss != 0; ctx->ef = ef; ctx->degauss = degauss; ctx->ngauss = ngauss;
+  return SGW_OK;
+}
+
+int sgw_set_kpair_metal(sgw_ctx *ctx, int ik, int nbnd, const sgw_cplx *evq_all, const double *et_q, int nbnd_occ_k,
+                        const double *wg_over_wk) {
+  if (!ctx) return SGW_E_ARG;
+  cudaSetDevice(ctx->device);
+  SGW_ARG(ik >= 0 && ik < (int)ctx->pairs.size() && ctx->pairs[ik].set, "pair not set (sgw_set_kpair comes first)");
+  KPair &kp = ctx->pairs[ik];
+  const KSlot &ks = ctx->slots[kp.slot];
+  SGW_ARG(nbnd >= ks.nbnd && evq_all && et_q && nbnd_occ_k > 0 && nbnd_occ_k <= kp.nbnd && wg_over_wk, "bad metal data for the pair");
+  ctx->tables_version++;
+  if (kp.d_evq_all) { dev_free(kp.d_evq_all); kp.d_evq_all = nullptr; }
+  const int npwx = ks.npwx;
+  cplx *stage = nullptr;
+  SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * nbnd, &stage));
+  SGW_CUDA(dev_malloc((void **)&kp.d_evq_all, sizeof(cplx) * (size_t)npwx * nbnd));
+  SGW_CUDA(cudaMemcpyAsync(stage, evq_all, sizeof(cplx) * (size_t)npwx * nbnd, cudaMemcpyHostToDevice, ctx->stream));
+  SGW_CHECK(permute_in(ctx, ks.sph, nbnd, stage, npwx, kp.d_evq_all, npwx, npwx));
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+  kp.nbnd_all = nbnd; kp.nocc_k = nbnd_occ_k;
+  kp.et_q.assign(et_q, et_q + nbnd);
+  kp.wg_over_wk.assign(wg_over_wk, wg_over_wk + nbnd_occ_k);
   return SGW_OK;
 }
 
@@ -1198,6 +1337,10 @@ int sgw_get_rho_grid(const sgw_ctx *ctx, int *dims) {
 
 int sgw_coulomb_q0G0(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int nfs, const sgw_cplx *fiu, sgw_cplx *eps_m,
                      int32_t *ierr_out) {
+  if (ctx && ctx->lgauss) {
+    ctx->err = "coulomb_q0G0 is the insulator treatment of the q -> 0 head (coulomb_q0G0.f90); not defined for lgauss";
+    return SGW_E_UNSUPPORTED;
+  }
   // coulomb_q0G0.f90:31-158: the G = G' = 0 element at the (shifted) q currently installed
   const int32_t one = 1;
   return sgw_coulomb(ctx, cfg, 1, 1, 1, &one, nfs, fiu, eps_m, ierr_out);

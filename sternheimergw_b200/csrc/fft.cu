@@ -1203,8 +1203,10 @@ template <int RZ1, int RZ2>
 static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const ZTArgs &a) {
   constexpr int NZ = RZ1 * RZ2, NT = 128;
   const int ncb = (a.ncol + ZB - 1) / ZB;
-  const char *edb = getenv("SGW_ZG2R_DB");                      // 0: one input staging buffer (A/B)
-  const bool db = !(edb && atoi(edb) == 0);
+  // SGW_ZG2R_DB=1: two input staging buffers.  Measured at Si64 (H.psi z passes per step): 36.1 ms with, 35.6 ms without -- the
+  // bulk copy's latency is not what limits the kernel, so the default keeps one buffer (less shared memory per CTA)
+  const char *edb = getenv("SGW_ZG2R_DB");
+  const bool db = edb && atoi(edb) == 1;
   const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB + (size_t)a.maxlen * (db ? 2 : 1) + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
                           : sizeof(cplx) * ((size_t)NZ * ZB + NZ) + (sizeof(double) + sizeof(short)) * (size_t)a.maxlen + 32;
   auto go = [&](auto kern) -> int {

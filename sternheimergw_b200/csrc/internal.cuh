@@ -117,6 +117,10 @@ struct KPair {
   Sphere sph_k;
   cplx *d_evc = nullptr;       // npwx x nbnd rows in sph_k column order
   std::vector<double> et;
+  // metals (sgw_set_kpair_metal): all bands of evq with their energies, nbnd_occ(ikk), wg(:, ikk) / wk(ikk)
+  int nbnd_all = 0, nocc_k = 0;
+  cplx *d_evq_all = nullptr;   // npwx x nbnd_all rows in the k+q slot's column order
+  std::vector<double> et_q, wg_over_wk;
 };
 
 // kernel classes timed separately (CUDA events on the library's stream) when profiling is on
@@ -179,6 +183,9 @@ struct sgw_ctx {
   // control_gw globals of the self-consistent branch (sgw_set_mixing): niter_gw, alpha_mix(:), tr2_gw, nmix_gw
   int mix_niter = 0, mix_nmix = 0, last_scf_iter = 0;
   bool solve_direct = true;                      // control_gw solve_direct (coulomb.f90:104)
+  bool lgauss = false;                           // [QE] klist lgauss / degauss / ngauss, ener ef (sgw_set_smearing)
+  double ef = 0.0, degauss = 0.0;
+  int ngauss = 0;
   std::vector<double> mix_alpha;
   double mix_tr2 = 0.0;
   cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // solver look-ahead (bicgstab.cu)

@@ -252,6 +252,26 @@ class Context:
             nl = np.ascontiguousarray(kp.nl_igk_k, dtype=np.int32)
             self._chk(self._L.sgw_set_kpair(self._h, ik, ik, kp.npw_k, _p(nl), evc.shape[1], _p(evc), _p(et), float(kp.wk)),
                       "set_kpair")
+        metal = getattr(syn, "metal", None)
+        if metal is None:
+            self.set_smearing(False)
+        else:                                   # klist lgauss/degauss/ngauss, ener ef + what orthogonalize's lgauss branch reads
+            self.set_smearing(True, metal.ef, metal.degauss, metal.ngauss)
+            sel = range(len(syn.kpairs)) if kpairs is None else kpairs
+            for ik, i in enumerate(sel):
+                m = metal.pairs[i]
+                self.set_kpair_metal(ik, m.evq_all, m.et_q, m.nocc_k, m.wg_over_wk)
+
+    def set_smearing(self, lgauss, ef=0.0, degauss=0.0, ngauss=0):
+        self._chk(self._L.sgw_set_smearing(self._h, 1 if lgauss else 0, float(ef), float(degauss), int(ngauss)), "set_smearing")
+
+    def set_kpair_metal(self, ik, evq_all, et_q, nocc_k, wg_over_wk):
+        evq_all = _c16(evq_all)
+        et_q = np.ascontiguousarray(et_q, dtype=np.float64)
+        w = np.ascontiguousarray(wg_over_wk, dtype=np.float64)
+        assert et_q.size == evq_all.shape[1] and w.size == nocc_k
+        self._chk(self._L.sgw_set_kpair_metal(self._h, ik, evq_all.shape[1], _p(evq_all), _p(et_q), int(nocc_k), _p(w)),
+                  "set_kpair_metal")
 
     def set_q(self, xq):
         xq = np.ascontiguousarray(xq, dtype=np.float64)

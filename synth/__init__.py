@@ -368,6 +368,55 @@ def attach_kpoints(sys: SynthSystem, klist, xq, nbnd=None, weights=None):
     return sys
 
 
+@dataclass
+class MetalPair:
+    evq_all: np.ndarray     # (npwx, nbnd) all bands at k+q
+    et_q: np.ndarray        # (nbnd,)
+    nocc_k: int             # nbnd_occ(ikk)
+    wg_over_wk: np.ndarray  # (nocc_k,) wg(ibnd, ikk) / wk(ikk)
+
+
+@dataclass
+class Metal:
+    ef: float
+    degauss: float
+    ngauss: int
+    pairs: list
+
+
+def wgauss(x, n):
+    """[QE] Modules/wgauss.f90 for ngauss = 0 (Gaussian) and -99 (Fermi-Dirac); the others live in the oracle and the library."""
+    from math import erfc, exp
+    if n == -99:
+        return 0.0 if x < -200 else (1.0 if x > 200 else 1.0 / (1.0 + exp(-x)))
+    assert n == 0
+    return 0.5 * erfc(-x)
+
+
+def make_metal(sys: SynthSystem, ef, degauss, ngauss=0, occ_fn=None, target=3.0):
+    """Turn a system built by attach_kpoints(sys, klist, xq, nbnd=nbnd_all) into a metallic one (klist lgauss): the Fermi level
+    `ef` lies inside the computed bands, nbnd_occ(ik) = number of bands below ef + target * degauss (setup_nbnd_occ), the
+    operator's projector keeps the first nbnd_occ(ikq) bands of evq, and `sys.metal` carries what orthogonalize's lgauss
+    branch and solve_linter.f90:373 read.  occ_fn(x, ngauss) = theta~(x); default: the oracle's orc_wgauss."""
+    if occ_fn is None:
+        import oracle
+        occ_fn = oracle.wgauss
+    pairs = []
+    for kp in sys.kpairs:
+        kq = kp.kq
+        nb = kq.evq.shape[1]
+        et_q = np.asarray(kq.et[:nb], dtype=float)
+        et_k = np.asarray(kp.et[:nb], dtype=float)
+        nocc_q = max(1, int(np.sum(et_q < ef + target * degauss)))
+        nocc_k = max(1, int(np.sum(et_k < ef + target * degauss)))
+        assert nocc_q < nb and nocc_k < nb, "raise nbnd: every computed band is (partially) occupied"
+        pairs.append(MetalPair(evq_all=kq.evq.copy(), et_q=et_q.copy(), nocc_k=nocc_k,
+                               wg_over_wk=np.array([occ_fn((ef - e) / degauss, ngauss) for e in et_k[:nocc_k]])))
+        kq.evq = np.ascontiguousarray(kq.evq[:, :nocc_q])
+    sys.metal = Metal(ef=float(ef), degauss=float(degauss), ngauss=int(ngauss), pairs=pairs)
+    return sys
+
+
 def mp_grid(bg, n):
     """Unshifted n1 x n2 x n3 Monkhorst-Pack grid in cartesian 2pi/alat units (no symmetry reduction)."""
     n = (n, n, n) if np.isscalar(n) else n

@@ -318,3 +318,26 @@ def test_coulomb_on_general_grids(ctx, monkeypatch, nr, env):
     ref, ierr, _ = ps.coulomb(1, ngc, ngc, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=4)
     assert ierr == 0
     assert _rel(scr, ref) < 1e-8, _rel(scr, ref)
+
+
+@pytest.mark.parametrize("ngauss,nk", [(0, 1), (-99, 2), (1, 2), (-1, 1)])
+def test_coulomb_metal_matches_oracle(ctx, ngauss, nk):
+    """Metals (sgw_set_smearing / sgw_set_kpair_metal): the smeared projector of [QE] orthogonalize (lgauss) and the wg/wk scaling
+    of solve_linter.f90:373 against the oracle, whose restatement is anchored by tests/test_oracle_metal.py: <= 1e-8 at thr 1e-12."""
+    import oracle
+    from metal_util import metal_system
+    from sternheimergw_b200 import select_solver_type
+    syn = metal_system(ngauss=ngauss, nk=nk)
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    ngc = 5
+    igu = np.arange(1, ngc + 1, dtype=np.int32)
+    fiu = np.array([0.0, 0.9j])
+    try:
+        scr = ctx.coulomb(select_solver_type(priority=(1, 3), threshold=1e-12), 1, ngc, ngc, igu, fiu)
+    finally:
+        ctx.set_smearing(False)
+    ref, ierr, _ = ps.coulomb(1, ngc, ngc, igu, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-12), nthreads=4)
+    assert ierr == 0
+    assert np.abs(ref - np.eye(ngc)[:, None, :]).max() > 1e-3
+    assert _rel(scr, ref) < 1e-8, (ngauss, nk, _rel(scr, ref))
