@@ -84,6 +84,9 @@ int sgw_get_profile(const sgw_ctx *ctx, int max_classes, double *ms, int64_t *re
 const char *sgw_profile_class_name(int cls);
 
 /* ---- L0: FFT grid and local potential (result of set_vrs, gwq_setup.f90:92; QE dffts) ---- */
+/* nr1, nr2, nr3: FFT dimensions (any 2^a 3^b 5^c <= 960, optionally times one 7 and/or 11); nr1x >= nr1 ...: physical
+ * dimensions of the caller's real-space arrays (dffts%nr1x; equal to nr except on padded builds).  With padding, vrs, dvbarein /
+ * drhoscf and every 1-based FFT index (nl, nl_igk) are in the padded layout, exactly as the Fortran host holds them. */
 int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, int nr3x);
 int sgw_set_vloc(sgw_ctx *ctx, const double *vrs /* nnr */);
 

@@ -331,7 +331,7 @@ namespace sgw {
 int make_fft_grid(sgw_ctx *ctx, int n1, int n2, int n3, FftGrid *gr) {
   free_fft_grid(gr);
   if (!make_plan(n1, &gr->px) || !make_plan(n2, &gr->py) || !make_plan(n3, &gr->pz)) {
-    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..6,8,9,10,12,15,16,18,20,24,25,27,30,32} (every 2^a 3^b 5^c <= 960 is)";
+    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..12, 14, 15, 16, 18, 20, 21, 22, 24, 25, 27, 28, 30, 32} (every 2^a 3^b 5^c <= 960 is, and those times one 7 and/or 11 up to 350)";
     return SGW_E_UNSUPPORTED;
   }
   gr->n1 = n1; gr->n2 = n2; gr->n3 = n3;
@@ -355,15 +355,13 @@ int sgw_set_grid(sgw_ctx *ctx, int nr1, int nr2, int nr3, int nr1x, int nr2x, in
   cudaSetDevice(ctx->device);
   ctx->tables_version++;
   SGW_ARG(nr1 > 0 && nr2 > 0 && nr3 > 0, "grid dimensions must be positive");
-  if (nr1x != nr1 || nr2x != nr2 || nr3x != nr3) {
-    ctx->err = "padded FFT boxes (nr1x != nr1) are not supported";
-    return SGW_E_UNSUPPORTED;
-  }
+  SGW_ARG(nr1x >= nr1 && nr2x >= nr2 && nr3x >= nr3, "physical dimensions nr1x, nr2x, nr3x must not be smaller than the FFT dimensions");
   if (!make_plan(nr1, &ctx->px) || !make_plan(nr2, &ctx->py) || !make_plan(nr3, &ctx->pz)) {
-    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..6,8,9,10,12,15,16,18,20,24,25,27,30,32} (every 2^a 3^b 5^c <= 960 is)";
+    ctx->err = "FFT dimension without a plan: it must be r1*r2 with radices from {1..12, 14, 15, 16, 18, 20, 21, 22, 24, 25, 27, 28, 30, 32} (every 2^a 3^b 5^c <= 960 is, and those times one 7 and/or 11 up to 350)";
     return SGW_E_UNSUPPORTED;
   }
   ctx->nr1 = nr1; ctx->nr2 = nr2; ctx->nr3 = nr3;
+  ctx->nr1x = nr1x; ctx->nr2x = nr2x; ctx->nr3x = nr3x;
   SGW_CHECK(upload_twiddle(ctx, nr1, &ctx->d_twx));
   SGW_CHECK(upload_twiddle(ctx, nr2, &ctx->d_twy));
   SGW_CHECK(upload_twiddle(ctx, nr3, &ctx->d_twz));
@@ -391,7 +389,7 @@ int sgw_set_vloc(sgw_ctx *ctx, const double *vrs) {
   for (int pz = 0; pz < nz; ++pz)
     for (int py = 0; py < ny; ++py)
       for (int pxi = 0; pxi < nx; ++pxi)
-        vp[((size_t)pz * ny + py) * nx + pxi] = vrs[ctx->permx[pxi] + (size_t)nx * (ctx->permy[py] + (size_t)ny * ctx->permz[pz])];
+        vp[((size_t)pz * ny + py) * nx + pxi] = vrs[ctx->permx[pxi] + (size_t)ctx->nr1x * (ctx->permy[py] + (size_t)ctx->nr2x * ctx->permz[pz])];
   SGW_CHECK(upload(ctx, &ctx->d_vperm, vp.data(), vp.size()));
   {
     // the same potential with y fastest, [pz][px][py]: in the fused middle x stage consecutive lanes work on consecutive
@@ -426,7 +424,11 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
   SGW_ARG(k != nullptr, "bad slot");
   free_slot(*k);
   ctx->tables_version++;
-  SGW_CHECK(build_sphere(ctx, npw, nl_igk, &k->sph));
+  {
+    std::vector<int32_t> nlc(nl_igk, nl_igk + npw);
+    if (grid_padded(ctx)) for (auto &v : nlc) v = unpad_index(ctx, v);
+    SGW_CHECK(build_sphere(ctx, npw, nlc.data(), &k->sph));
+  }
   k->npw = npw; k->npwx = npwx; k->nkb = nkb; k->nbnd = nbnd_occ; k->alpha_pv = alpha_pv;
   const std::vector<int> &perm = k->sph.perm;
   std::vector<double> g2(npwx, 0.0);

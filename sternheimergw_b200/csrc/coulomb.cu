@@ -1006,6 +1006,7 @@ int sgw_set_system(sgw_ctx *ctx, double omega_cell, double tpiba2, int ngm, cons
   ctx->ngm = ngm;
   ctx->g.assign(g, g + 3 * (size_t)ngm);
   ctx->nl.assign(nl, nl + ngm);
+  if (grid_padded(ctx)) for (auto &v : ctx->nl) v = unpad_index(ctx, v);
   for (auto &kv : ctx->rho_spheres) free_sphere(&kv.second);
   ctx->rho_spheres.clear();
   ctx->system_set = true;
@@ -1049,7 +1050,11 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
   if (kp.d_evc) { dev_free(kp.d_evc); kp.d_evc = nullptr; }
   if (kp.d_evq_all) { dev_free(kp.d_evq_all); kp.d_evq_all = nullptr; }       // metal data belongs to the pair it was set for
   kp.nbnd_all = kp.nocc_k = 0;
-  SGW_CHECK(build_sphere(ctx, npw_k, nl_igk_k, &kp.sph_k));
+  {
+    std::vector<int32_t> nlc(nl_igk_k, nl_igk_k + npw_k);
+    if (grid_padded(ctx)) for (auto &v : nlc) v = unpad_index(ctx, v);
+    SGW_CHECK(build_sphere(ctx, npw_k, nlc.data(), &kp.sph_k));
+  }
   const int npwx = ks.npwx;
   {
     cplx *stage = nullptr;
@@ -1132,15 +1137,44 @@ int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, cons
   cplx *d_nat = nullptr, *d_field = nullptr, *d_drhoG = nullptr, *Tr = nullptr;
   SGW_CHECK(ws(ctx, "sl_nat", (size_t)nnr * nfreq, &d_nat));
   SGW_CHECK(ws(ctx, "co_field", (size_t)nnr, &d_field));
-  SGW_CUDA(cudaMemcpyAsync(d_nat, dvbarein, sizeof(cplx) * nnr, cudaMemcpyHostToDevice, st));
+  // padded boxes: the caller's arrays have nr1x * nr2x * nr3x entries per frequency; the library's are compact
+  const bool pad = grid_padded(ctx);
+  const long nnrx = (long)ctx->nr1x * ctx->nr2x * ctx->nr3x;
+  std::vector<sgw_cplx> hbuf;
+  auto compact_index = [&](long i) {
+    const long x = i % ctx->nr1, y = (i / ctx->nr1) % ctx->nr2, z = i / ((long)ctx->nr1 * ctx->nr2);
+    return x + (long)ctx->nr1x * (y + (long)ctx->nr2x * z);
+  };
+  auto download = [&](const cplx *d_src) -> int {                  // d_src(nnr, nfreq) -> drhoscf(nnrx, nfreq)
+    if (!pad) {
+      SGW_CUDA(cudaMemcpyAsync(drhoscf, d_src, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
+      SGW_CUDA(cudaStreamSynchronize(st));
+      return SGW_OK;
+    }
+    hbuf.resize((size_t)nnr * nfreq);
+    SGW_CUDA(cudaMemcpyAsync(hbuf.data(), d_src, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+    memset(drhoscf, 0, sizeof(sgw_cplx) * (size_t)nnrx * nfreq);
+    for (int f = 0; f < nfreq; ++f)
+      for (long i = 0; i < nnr; ++i) drhoscf[(size_t)f * nnrx + compact_index(i)] = hbuf[(size_t)f * nnr + i];
+    return SGW_OK;
+  };
+  if (pad) {
+    hbuf.resize((size_t)nnr);
+    for (long i = 0; i < nnr; ++i) hbuf[i] = dvbarein[compact_index(i)];
+    SGW_CUDA(cudaMemcpyAsync(d_nat, hbuf.data(), sizeof(cplx) * nnr, cudaMemcpyHostToDevice, st));
+    SGW_CUDA(cudaStreamSynchronize(st));
+  } else {
+    SGW_CUDA(cudaMemcpyAsync(d_nat, dvbarein, sizeof(cplx) * nnr, cudaMemcpyHostToDevice, st));
+  }
   {
     dim3 gr((unsigned)((nnr + 255) / 256), 1);
     k_nat2perm<<<gr, 256, 0, st>>>(g, 1, d_nat, d_field);
     SGW_LAUNCH_CHECK();
   }
   double s2 = 0.0;                                                                         // solve_linter.f90:532
-  for (long i = 0; i < nnr; ++i) s2 += dvbarein[i].re * dvbarein[i].re + dvbarein[i].im * dvbarein[i].im;
-  const double meandvb = std::sqrt(s2) / (double)nnr;
+  for (long i = 0; i < nnrx; ++i) s2 += dvbarein[i].re * dvbarein[i].re + dvbarein[i].im * dvbarein[i].im;
+  const double meandvb = std::sqrt(s2) / (double)nnrx;
   if (num_iter > 1) {
     // self-consistent branch: drhoscf = dvscfin (solve_linter.f90:610)
     cplx *d_dvin = nullptr;
@@ -1151,8 +1185,7 @@ int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, cons
     dim3 gr((unsigned)((nnr + 255) / 256), nfreq);
     k_perm2nat<<<gr, 256, 0, st>>>(g, nfreq, d_dvin, d_nat, 1.0);
     SGW_LAUNCH_CHECK();
-    SGW_CUDA(cudaMemcpyAsync(drhoscf, d_nat, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
-    SGW_CUDA(cudaStreamSynchronize(st));
+    SGW_CHECK(download(d_nat));
     *ierr_out = ierr_it;
     end_call(ctx);
     return SGW_OK;
@@ -1181,8 +1214,7 @@ int sgw_solve_linter(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int num_iter, cons
     k_perm2nat<<<gr, 256, 0, st>>>(g, nfreq, d_R, d_nat, 1.0);
     SGW_LAUNCH_CHECK();
   }
-  SGW_CUDA(cudaMemcpyAsync(drhoscf, d_nat, sizeof(cplx) * (size_t)nnr * nfreq, cudaMemcpyDeviceToHost, st));
-  SGW_CUDA(cudaStreamSynchronize(st));
+  SGW_CHECK(download(d_nat));
   *ierr_out = ierr_any;
   end_call(ctx);
   return SGW_OK;

@@ -28,14 +28,17 @@ struct Plan1D {
 inline bool radix_ok(int r) {
   switch (r) {
     case 1: case 2: case 3: case 4: case 5: case 6: case 8: case 9: case 10: case 12: case 15: case 16:
-    case 18: case 20: case 24: case 25: case 27: case 30: case 32: return true;
+    case 18: case 20: case 24: case 25: case 27: case 30: case 32:
+    case 7: case 11: case 14: case 21: case 22: case 28: return true;
     default: return false;
   }
 }
 
-// balanced two-radix plan; returns false if n is not representable.  Every n = 2^a 3^b 5^c <= 960 is (radices up to 32);
-// the radices above 16 only serve lengths that have no plan without them: their codelets need more registers than the
-// kernels' launch bounds leave, so they are correct but slower per point.
+// balanced two-radix plan; returns false if n is not representable.  Every n = 2^a 3^b 5^c <= 960 is (radices up to 32), and
+// so are the lengths with ONE factor 7 and/or 11 that QE's good_fft_order hands out (14, 21, 22, 28, 42, 44, 56, 63, 66, 70, 77,
+// 84, 88, ...) through the radices 7, 11, 14, 21, 22, 28.  The radices above 16 and the 7/11 family only serve lengths that have
+// no plan without them: they are dispatched separately (run_*_big) and may spill under the kernels' register caps --
+// correct, slower per point.
 inline bool make_plan(int n, Plan1D* p) {
   p->n = n;
   if (n <= 16 && radix_ok(n)) { p->r1 = n; p->r2 = 1; return true; }

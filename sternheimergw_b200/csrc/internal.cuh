@@ -150,6 +150,7 @@ struct sgw_ctx {
   // grid
   bool grid_set = false, vloc_set = false, system_set = false;
   int nr1 = 0, nr2 = 0, nr3 = 0;
+  int nr1x = 0, nr2x = 0, nr3x = 0;              // physical dimensions of the caller's real-space arrays (dffts%nr1x ...; >= nr)
   sgw::Plan1D px, py, pz;
   sgw::cplx *d_twx = nullptr, *d_twy = nullptr, *d_twz = nullptr;
   double *d_vperm = nullptr;    // local potential in permuted real-space order [pz][py][px]
@@ -274,6 +275,15 @@ struct ProfScope {
 };
 void begin_call(sgw_ctx *ctx);
 void end_call(sgw_ctx *ctx);
+// Padded boxes (nr1x > nr1): the caller's 1-based linear FFT indices and real-space arrays use the physical dimensions; the
+// library works on the compact box, so indices are converted once when they come in
+inline bool grid_padded(const sgw_ctx *ctx) { return ctx->nr1x != ctx->nr1 || ctx->nr2x != ctx->nr2 || ctx->nr3x != ctx->nr3; }
+inline int32_t unpad_index(const sgw_ctx *ctx, int32_t idx1) {
+  if (!grid_padded(ctx)) return idx1;
+  const long i = (long)idx1 - 1;
+  const long x = i % ctx->nr1x, y = (i / ctx->nr1x) % ctx->nr2x, z = i / ((long)ctx->nr1x * ctx->nr2x);
+  return (int32_t)(x + (long)ctx->nr1 * (y + (long)ctx->nr2 * z) + 1);
+}
 void lanes_destroy(sgw_ctx *ctx);              // api.cu: frees what the lanes own (streams, workspaces, events)
 GridDev grid_dev(const sgw_ctx *ctx, const FftGrid *gr = nullptr);
 int build_sphere(sgw_ctx *ctx, int npw, const int32_t *nl_1based, Sphere *sph);

@@ -233,23 +233,39 @@ class Context:
         self._chk(self._L.sgw_set_dense_operator(self._h, slot, n, _p(A), n), "set_dense_operator")
         self.npw[slot], self.npwx[slot] = n, n
 
-    def install_system(self, syn, kpairs=None):
+    def install_system(self, syn, kpairs=None, nrx=None):
         """Install a synth.SynthSystem the way the Fortran host would (gwq_setup, solve_linter.f90:300-316).
-        kpairs: indices of the (k, k+q) pairs THIS context works on (a pool of the reference, solve_linter.f90:521); default all."""
-        self.set_grid(*syn.nr)
-        self.set_vloc(syn.vrs)
+        kpairs: indices of the (k, k+q) pairs THIS context works on (a pool of the reference, solve_linter.f90:521); default all.
+        nrx: physical dimensions (dffts%nr1x, nr2x, nr3x) of a padded box: the potential and every index array are then handed
+        over in the padded layout, as a host whose FFT descriptor pads would hold them."""
+        nr = tuple(int(x) for x in syn.nr)
+        if nrx is None:
+            padi = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+            self.set_grid(*nr)
+            self.set_vloc(syn.vrs)
+        else:
+            nrx = tuple(int(x) for x in nrx)
+
+            def padi(a):
+                i = np.asarray(a, dtype=np.int64) - 1
+                x, y, z = i % nr[0], (i // nr[0]) % nr[1], i // (nr[0] * nr[1])
+                return np.ascontiguousarray(x + nrx[0] * (y + nrx[1] * z) + 1, dtype=np.int32)
+            vp = np.zeros(nrx, dtype=np.float64, order="F")
+            vp[:nr[0], :nr[1], :nr[2]] = np.asarray(syn.vrs).reshape(nr, order="F")
+            self.set_grid(*nr, *nrx)
+            self.set_vloc(vp.ravel(order="F"))
         self._chk(self._L.sgw_set_system(self._h, syn.omega_cell, syn.tpiba2, syn.ngm,
                                          _p(np.ascontiguousarray(syn.g.T, dtype=np.float64)),
-                                         _p(np.ascontiguousarray(syn.nl, dtype=np.int32))), "set_system")
+                                         _p(padi(syn.nl))), "set_system")
         self.set_q(syn.xq)
         pairs = list(syn.kpairs) if kpairs is None else [syn.kpairs[i] for i in kpairs]
         self._chk(self._L.sgw_set_nksq(self._h, len(pairs)), "set_nksq")
         for ik, kp in enumerate(pairs):
             kq = kp.kq
-            self.set_kpoint(ik, kq.npw, kq.npwx, kq.nl_igk, kq.g2kin, kq.vkb, kq.dion, kq.evq, kq.alpha_pv)
+            self.set_kpoint(ik, kq.npw, kq.npwx, padi(kq.nl_igk), kq.g2kin, kq.vkb, kq.dion, kq.evq, kq.alpha_pv)
             evc = _c16(kp.evc)
             et = np.ascontiguousarray(kp.et, dtype=np.float64)
-            nl = np.ascontiguousarray(kp.nl_igk_k, dtype=np.int32)
+            nl = padi(kp.nl_igk_k)
             self._chk(self._L.sgw_set_kpair(self._h, ik, ik, kp.npw_k, _p(nl), evc.shape[1], _p(evc), _p(et), float(kp.wk)),
                       "set_kpair")
         metal = getattr(syn, "metal", None)

@@ -39,7 +39,9 @@ def _perm(n, r1, r2):
 
 @pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 8, 9, 10, 36, 45, 48, 64, 96, 100, 120, 144, 225, 256,
                                # lengths that need the radices 18..32 (125, 162, 200, 216 ... were rejected)
-                               125, 162, 200, 216, 243, 250, 270, 288, 320, 375, 384, 405, 480, 512, 625, 768, 900, 960])
+                               125, 162, 200, 216, 243, 250, 270, 288, 320, 375, 384, 405, 480, 512, 625, 768, 900, 960,
+                               # lengths with one factor 7 and/or 11 (QE's good_fft_order hands them out)
+                               7, 11, 14, 21, 22, 28, 42, 44, 56, 63, 66, 70, 77, 84, 88, 105, 112, 154, 231, 308])
 @pytest.mark.parametrize("layout", [0, 1])
 def test_line_fft_matches_numpy(harness, n, layout):
     rng = np.random.default_rng(n + layout)
@@ -67,11 +69,12 @@ def test_every_5_smooth_length_up_to_960_has_a_plan(harness):
 
 
 def test_unsupported_length_has_no_plan(harness):
-    y, _ = _run(harness, 7 * 11, 1, +1, 1, 0, np.zeros((1, 77), complex))
-    assert y is None
+    for n in (13, 26, 221):
+        y, _ = _run(harness, n, 1, +1, 1, 0, np.zeros((1, n), complex))
+        assert y is None
 
 
-@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 12, 16, 125, 200, 216, 512])
+@pytest.mark.parametrize("n", [15, 18, 20, 24, 60, 72, 12, 16, 125, 200, 216, 512, 14, 28, 42, 77])
 def test_fused_vloc_middle_stage(harness, n):
     rng = np.random.default_rng(100 + n)
     nlines = 6

@@ -341,3 +341,29 @@ def test_coulomb_metal_matches_oracle(ctx, ngauss, nk):
     assert ierr == 0
     assert np.abs(ref - np.eye(ngc)[:, None, :]).max() > 1e-3
     assert _rel(scr, ref) < 1e-8, (ngauss, nk, _rel(scr, ref))
+
+
+def test_padded_box_gives_the_compact_result(ctx):
+    """dffts%nr1x > nr1 (padded FFT descriptors): the potential, the index arrays and dvbarein / drhoscf cross the ABI in the
+    padded layout; the result is the compact one, entry for entry, and the padding comes back as zeros."""
+    import synth
+    from sternheimergw_b200 import select_solver_type
+    syn = synth.preset("tiny", nk=2)
+    nr = tuple(int(x) for x in syn.nr)
+    nrx = (nr[0] + 1, nr[1], nr[2] + 2)
+    rng = np.random.default_rng(5)
+    dv = rng.standard_normal(nr) + 1j * rng.standard_normal(nr)
+    freq = np.array([0.0, 0.8j])
+    cfg = select_solver_type(priority=(1, 3), threshold=1e-10)
+    igu = np.arange(1, 6, dtype=np.int32)
+    ctx.install_system(syn)
+    a = ctx.solve_linter(cfg, 1, dv.ravel(order="F"), freq).reshape(nr + (2,), order="F")
+    ca = ctx.coulomb(cfg, 1, 5, 5, igu, freq)
+    ctx.install_system(syn, nrx=nrx)
+    dvp = np.zeros(nrx, dtype=complex, order="F")
+    dvp[:nr[0], :nr[1], :nr[2]] = dv
+    b = ctx.solve_linter(cfg, 1, dvp.ravel(order="F"), freq).reshape(nrx + (2,), order="F")
+    cb = ctx.coulomb(cfg, 1, 5, 5, igu, freq)
+    assert np.array_equal(b[:nr[0], :nr[1], :nr[2]], a)
+    assert np.abs(b[nr[0]:]).max() == 0.0 and np.abs(b[:, :, nr[2]:]).max() == 0.0
+    assert np.array_equal(ca, cb)

@@ -14,7 +14,8 @@ same code is unit-tested on the CPU (tests/test_fft_core_cpu.py).
 import math
 from pathlib import Path
 
-RADICES = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30, 32]
+RADICES = [2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16, 18, 20, 24, 25, 27, 30, 32, 7, 11, 14, 21, 22, 28]
+BIG = {18, 20, 24, 25, 27, 30, 32, 7, 11, 14, 21, 22, 28}      # dispatched by the run_*_big functions of fft_core.h
 OUT = Path(__file__).resolve().parent.parent / "sternheimergw_b200" / "csrc" / "fft_codelets.h"
 
 
@@ -118,8 +119,31 @@ def dft(e: Emitter, x):
         X2 = (e.tmp(f"{A2[0]} + {B2[1]}"), e.tmp(f"{A2[1]} - {B2[0]}"))
         X3 = (e.tmp(f"{A2[0]} - {B2[1]}"), e.tmp(f"{A2[1]} + {B2[0]}"))
         return [X0, X1, X2, X3, X4]
+    if R in (7, 11, 13):
+        # odd prime p: X_k = x_0 + sum_{j=1..h} [ (x_j + x_{p-j}) cos(2 pi j k / p) - i (x_j - x_{p-j}) sin(2 pi j k / p) ], h = (p-1)/2;
+        # X_{p-k} is the same with the sign of the sine part flipped
+        p, h = R, (R - 1) // 2
+        sp = [e.add(x[j], x[p - j]) for j in range(1, h + 1)]
+        dm = [e.sub(x[j], x[p - j]) for j in range(1, h + 1)]
+        tot = x[0]
+        for t in sp:
+            tot = e.add(tot, t)
+        X = [None] * p
+        X[0] = tot
+        for k in range(1, h + 1):
+            A = x[0]
+            B = None
+            for j in range(1, h + 1):
+                c = math.cos(2 * math.pi * j * k / p)
+                sn = math.sin(2 * math.pi * j * k / p)
+                A = e.fma_c(A, c, sp[j - 1])
+                B = e.scale(dm[j - 1], sn) if B is None else e.fma_c(B, sn, dm[j - 1])
+            # X_k = A - i B ; X_{p-k} = A + i B        (-iB = (B_im, -B_re))
+            X[k] = (e.tmp(f"{A[0]} + {B[1]}"), e.tmp(f"{A[1]} - {B[0]}"))
+            X[p - k] = (e.tmp(f"{A[0]} - {B[1]}"), e.tmp(f"{A[1]} + {B[0]}"))
+        return X
     # composite: R = a*b, j = j2 + b*j1, k = k1 + a*k2
-    for a in (4, 2, 3, 5):
+    for a in (4, 2, 3, 5, 7, 11):
         if R % a == 0 and R // a > 1:
             break
     else:
@@ -159,8 +183,8 @@ def main():
         out.append("")
     # the radices above 16 are dispatched by separate functions (fft_core.h run_*_big) so that their register pressure does
     # not touch the code generated for the common ones
-    out.append("#define SGW_FOR_EACH_RADIX(X) " + " ".join(f"X({r})" for r in [1] + [r for r in RADICES if r <= 16]))
-    out.append("#define SGW_FOR_EACH_BIG_RADIX(X) " + " ".join(f"X({r})" for r in RADICES if r > 16))
+    out.append("#define SGW_FOR_EACH_RADIX(X) " + " ".join(f"X({r})" for r in [1] + [r for r in RADICES if r not in BIG]))
+    out.append("#define SGW_FOR_EACH_BIG_RADIX(X) " + " ".join(f"X({r})" for r in RADICES if r in BIG))
     out.append("")
     out.append("}  // namespace sgw")
     OUT.parent.mkdir(parents=True, exist_ok=True)
