@@ -261,7 +261,7 @@ static int rho_grid_prepare(sgw_ctx *ctx, int ngc, const Sphere &rho_fine, bool 
     nc[d] = nf[d];
     for (int n = need[d]; n < nf[d]; ++n) {
       Plan1D p;
-      if (make_plan(n, &p)) { nc[d] = n; break; }
+      if (make_plan(n, &p) && plan_is_fast(p)) { nc[d] = n; break; }      // 45 = 5 x 9 rather than 44 = 4 x 11
     }
   }
   if ((double)nc[0] * nc[1] * nc[2] > 0.7 * (double)nf[0] * nf[1] * nf[2]) return SGW_OK;   // not worth a second grid

@@ -55,6 +55,13 @@ inline bool make_plan(int n, Plan1D* p) {
   return true;
 }
 
+// plan made of the common radices only (the ones the kernels run without spills): what a grid the library is free to choose
+// (the reduced Delta-rho box) should have
+inline bool plan_is_fast(const Plan1D& p) {
+  auto common = [](int r) { return r <= 16 && r != 7 && r != 11 && r != 13 && r != 14; };
+  return common(p.r1) && common(p.r2);
+}
+
 SGW_HD int perm_index(int r1, int r2, int pos) { return pos / r2 + r1 * (pos % r2); }
 
 // ---- one stage over a set of lines; thread `tid` of `nthreads` takes tasks tid, tid+nthreads, ...

@@ -26,7 +26,7 @@ def f(x):
 
 
 CLASS_OF = {"k_plane<0": "fft_plane", "k_plane_vloc": "fft_plane", "k_zpass_g2r": "fft_zpass", "k_zpass_r2g": "fft_zpass",
-            "k_zgemm<1, 1>": "gemm_project", "k_zgemm<0, 0>": "gemm_expand", "k_shift_fused": "shift_fused",
+            "k_zgemm<1, 1": "gemm_project", "k_zgemm<0, 0": "gemm_expand", "k_shift_fused": "shift_fused",
             "k_shift_apply": "shift_fused", "k_shift_gemm": "shift_gemm", "k_plane_rho": "rho_plane"}
 
 
