@@ -914,14 +914,16 @@ struct ZTArgs {
 // DB: two staging buffers for the input ranges, so that the bulk copy of the vector after next is in flight during a whole
 // iteration (with one buffer the copy can only be issued after stage 1 has consumed it and its latency is exposed: ncu showed
 // long_scoreboard 53 % in the mbarrier wait)
-template <int RZ1, int RZ2, int NT, bool DB>
-__global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__ CUtensorMap tmap, ZTArgs a) {
+// DBT: two output tiles, so that the tensor-map store of vector v may still be reading its tile while vector v + 1 is
+// transformed into the other one (cp.async.bulk.wait_group.read 1 instead of 0)
+template <int RZ1, int RZ2, int NT, bool DB, bool DBT = false>
+__global__ void __launch_bounds__(NT, DBT ? 4 : 6) k_zpass_g2r_tma(const __grid_constant__ CUtensorMap tmap, ZTArgs a) {
   constexpr int NZ = RZ1 * RZ2, RZ1P = (RZ1 + 7) & ~7, TILE = NZ * ZB;
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * ZB, nc = min(ZB, a.ncol - c0);
   extern __shared__ __align__(128) unsigned char zsm[];
-  cplx *tile = (cplx *)zsm;                       // [NZ][ZB]
-  cplx *in0 = tile + TILE;                        // [maxlen] staged entries of the block (x 2 with DB)
+  cplx *tile0 = (cplx *)zsm;                      // [NZ][ZB] (x 2 with DBT)
+  cplx *in0 = tile0 + (DBT ? 2 : 1) * TILE;       // [maxlen] staged entries of the block (x 2 with DB)
   cplx *in1 = DB ? in0 + a.maxlen : in0;
   cplx *tw = in1 + a.maxlen;
   short *ztab = (short *)(tw + NZ);               // [ZB][RZ2][RZ1P], rebased to the block's first entry
@@ -952,11 +954,15 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__
   }
   unsigned parity0 = 0u, parity1 = 0u;
   int sb = 0;                                     // staging buffer of the current vector
+  int tb_sel = 0;                                 // output tile of the current vector (DBT)
   const cplx zero = cmake(0.0, 0.0);
   while (v < a.nvec) {
     const int vn = v1;
     const int vnn = vn < a.nvec ? next_active(vn + gridDim.y) : a.nvec;
-    if (tid == 0) bulk_wait_read<0>();            // the previous vector's store has finished reading the tile
+    cplx *tile = tile0 + (DBT && tb_sel ? TILE : 0);
+    if (tid == 0) {                               // the store that last used THIS tile has finished reading it
+      if (DBT) bulk_wait_read<1>(); else bulk_wait_read<0>();
+    }
     __syncthreads();
     const cplx *in = (DB && sb) ? in1 : in0;
     if (bytes) {
@@ -1014,6 +1020,7 @@ __global__ void __launch_bounds__(NT, 6) k_zpass_g2r_tma(const __grid_constant__
     v = vn;
     v1 = vnn;
     if (DB) sb ^= 1;
+    if (DBT) tb_sel ^= 1;
   }
   if (tid == 0) bulk_wait_read<0>();              // shared memory must stay alive until the last store has read it
 }
@@ -1207,7 +1214,9 @@ static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const
   // bulk copy's latency is not what limits the kernel, so the default keeps one buffer (less shared memory per CTA)
   const char *edb = getenv("SGW_ZG2R_DB");
   const bool db = edb && atoi(edb) == 1;
-  const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB + (size_t)a.maxlen * (db ? 2 : 1) + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
+  const char *edbt = getenv("SGW_ZG2R_DBT");                    // 1: two output tiles (A/B)
+  const bool dbt = edbt && atoi(edbt) == 1 && !db;
+  const size_t smem = g2r ? sizeof(cplx) * ((size_t)NZ * ZB * (dbt ? 2 : 1) + (size_t)a.maxlen * (db ? 2 : 1) + NZ) + sizeof(short) * ZB * RZ2 * ((RZ1 + 7) & ~7) + 32
                           : sizeof(cplx) * ((size_t)NZ * ZB + NZ) + (sizeof(double) + sizeof(short)) * (size_t)a.maxlen + 32;
   auto go = [&](auto kern) -> int {
     SGW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1218,7 +1227,7 @@ static int launch_zpass_tma(sgw_ctx *ctx, bool g2r, const CUtensorMap &tm, const
     kern<<<grid, NT, smem, ctx->stream>>>(tm, a);
     return SGW_OK;
   };
-  if (g2r) return db ? go(k_zpass_g2r_tma<RZ1, RZ2, NT, true>) : go(k_zpass_g2r_tma<RZ1, RZ2, NT, false>);
+  if (g2r) return db ? go(k_zpass_g2r_tma<RZ1, RZ2, NT, true>) : (dbt ? go(k_zpass_g2r_tma<RZ1, RZ2, NT, false, true>) : go(k_zpass_g2r_tma<RZ1, RZ2, NT, false>));
   if (a.maxlen <= 5 * NT) return go(k_zpass_r2g_tma<RZ1, RZ2, NT, 5>);
   return go(k_zpass_r2g_tma<RZ1, RZ2, NT, (ZB * NZ + NT - 1) / NT>);
 }
@@ -1376,8 +1385,10 @@ static int launch_plane_vloc_nt(sgw_ctx *ctx, const GridDev &g, const Sphere &s,
 template <int RX1, int RX2, int RY1, int RY2>
 static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
                              bool *done) {
-  const char *e = getenv("SGW_PLANE_NT");                       // tuning knob: threads per CTA (320 | 352 | 384), default 384
-  const int nt = e ? atoi(e) : 384;
+  // SGW_PLANE_NT: threads per CTA (256 | 288 | 320 | 352 | 384).  Measured at Si64 (fft_plane class per step, two CTAs per SM in
+  // every case): 256 -> 101.7 ms, 320 -> 102.1 ms, 352 -> 104.7 ms, 384 -> 106.2 ms: fewer warps at the block-wide barriers win
+  const char *e = getenv("SGW_PLANE_NT");
+  const int nt = e ? atoi(e) : 256;
   if (nt == 256) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 256>(ctx, g, s, nvec, Tin, Tout, active, done);
   if (nt == 288) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 288>(ctx, g, s, nvec, Tin, Tout, active, done);
   if (nt == 320) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 320>(ctx, g, s, nvec, Tin, Tout, active, done);
