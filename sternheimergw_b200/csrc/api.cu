@@ -3,7 +3,9 @@
 #include "internal.cuh"
 
 #include <mutex>
+#include <thread>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -66,6 +68,90 @@ void dev_pool_trim() {
   std::lock_guard<std::mutex> lock(dp.mu);
   pool_trim_locked(dp);
 }
+
+namespace {
+struct CopyLane {
+  void *pin = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+struct CopyPool {
+  std::mutex mu;                       // one staged transfer at a time per process
+  int device = -1;
+  std::vector<CopyLane> lanes;
+  size_t chunk = 0;
+};
+CopyPool &copy_pool() { static CopyPool p; return p; }
+int copy_threads() {
+  const char *e = getenv("SGW_COPY_THREADS");
+  const int n = e ? atoi(e) : 4;
+  return std::max(0, std::min(n, 16));
+}
+constexpr size_t COPY_CHUNK = (size_t)8 << 20, COPY_MIN = (size_t)32 << 20;
+
+// the pool's lanes for this device (created on first use; nullptr when page-locked memory cannot be had)
+CopyPool *copy_pool_for(int device, int nl) {
+  CopyPool &cp = copy_pool();
+  if (cp.device == device && (int)cp.lanes.size() == nl) return &cp;
+  for (auto &l : cp.lanes) { if (l.pin) cudaFreeHost(l.pin); if (l.st) cudaStreamDestroy(l.st); if (l.ev) cudaEventDestroy(l.ev); }
+  cp.lanes.assign(nl, CopyLane());
+  cp.device = device; cp.chunk = COPY_CHUNK;
+  for (auto &l : cp.lanes) {
+    if (cudaMallocHost(&l.pin, cp.chunk) != cudaSuccess || cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      for (auto &k : cp.lanes) { if (k.pin) cudaFreeHost(k.pin); if (k.st) cudaStreamDestroy(k.st); if (k.ev) cudaEventDestroy(k.ev); }
+      cp.lanes.clear(); cp.device = -1;
+      return nullptr;
+    }
+  }
+  return &cp;
+}
+}  // namespace
+
+static int staged_copy(sgw_ctx *ctx, void *dst, const void *src, size_t bytes, bool to_device) {
+  const int nl = copy_threads();
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  CopyPool *cp = nullptr;
+  std::unique_lock<std::mutex> lock(copy_pool().mu, std::defer_lock);
+  if (nl > 0 && bytes >= COPY_MIN) { lock.lock(); cp = copy_pool_for(ctx->device, nl); }
+  if (!cp) {
+    SGW_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
+    if (!to_device) SGW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SGW_OK;
+  }
+  SGW_CUDA(cudaStreamSynchronize(ctx->stream));      // earlier work on the context's stream (producers of src / consumers of dst)
+  const size_t nchunk = (bytes + cp->chunk - 1) / cp->chunk;
+  std::vector<int> rc(nl, 0);
+  auto work = [&](int t) {
+    cudaSetDevice(ctx->device);
+    CopyLane &l = cp->lanes[t];
+    for (size_t c = t; c < nchunk; c += nl) {
+      const size_t off = c * cp->chunk, len = std::min(cp->chunk, bytes - off);
+      if (to_device) {
+        memcpy(l.pin, (const char *)src + off, len);
+        if (cudaMemcpyAsync((char *)dst + off, l.pin, len, kind, l.st) != cudaSuccess) { rc[t] = 1; return; }
+        if (cudaStreamSynchronize(l.st) != cudaSuccess) { rc[t] = 1; return; }   // the buffer is re-used by the next chunk
+      } else {
+        if (cudaMemcpyAsync(l.pin, (const char *)src + off, len, kind, l.st) != cudaSuccess) { rc[t] = 1; return; }
+        if (cudaStreamSynchronize(l.st) != cudaSuccess) { rc[t] = 1; return; }
+        memcpy((char *)dst + off, l.pin, len);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nl; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+  }
+  for (int t = 0; t < nl; ++t)
+    if (rc[t]) { cudaGetLastError(); ctx->err = "staged host/device copy failed"; return SGW_E_CUDA; }
+  return SGW_OK;
+}
+
+int h2d_large(sgw_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) { return staged_copy(ctx, d_dst, h_src, bytes, true); }
+int d2h_large(sgw_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) { return staged_copy(ctx, h_dst, d_src, bytes, false); }
 
 int ws_get(sgw_ctx *ctx, const char *name, size_t bytes, void **out) {
   if (bytes == 0) bytes = 16;
@@ -443,11 +529,11 @@ int sgw_set_kpoint(sgw_ctx *ctx, int slot, int npw, int npwx, const int32_t *nl_
     if (k->d_P) { dev_free(k->d_P); k->d_P = nullptr; }
     SGW_CUDA(dev_malloc((void **)&k->d_P, sizeof(cplx) * (size_t)npwx * m));
     if (nkb > 0) {
-      SGW_CUDA(cudaMemcpyAsync(stage, vkb, sizeof(cplx) * (size_t)npwx * nkb, cudaMemcpyHostToDevice, ctx->stream));
+      SGW_CHECK(h2d_large(ctx, stage, vkb, sizeof(cplx) * (size_t)npwx * nkb));
       SGW_CHECK(permute_in(ctx, k->sph, nkb, stage, npwx, k->d_P, npwx, npwx));
     }
     if (nbnd_occ > 0) {
-      SGW_CUDA(cudaMemcpyAsync(stage, evq, sizeof(cplx) * (size_t)npwx * nbnd_occ, cudaMemcpyHostToDevice, ctx->stream));
+      SGW_CHECK(h2d_large(ctx, stage, evq, sizeof(cplx) * (size_t)npwx * nbnd_occ));
       SGW_CHECK(permute_in(ctx, k->sph, nbnd_occ, stage, npwx, k->d_P + (size_t)nkb * npwx, npwx, npwx));
     }
     SGW_CUDA(cudaStreamSynchronize(ctx->stream));

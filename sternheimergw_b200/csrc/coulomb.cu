@@ -1060,7 +1060,7 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
     cplx *stage = nullptr;
     SGW_CHECK(ws(ctx, "io_in", (size_t)npwx * nbnd, &stage));
     SGW_CUDA(dev_malloc((void **)&kp.d_evc, sizeof(cplx) * (size_t)npwx * nbnd));
-    SGW_CUDA(cudaMemcpyAsync(stage, evc, sizeof(cplx) * (size_t)npwx * nbnd, cudaMemcpyHostToDevice, ctx->stream));
+    SGW_CHECK(h2d_large(ctx, stage, evc, sizeof(cplx) * (size_t)npwx * nbnd));
     SGW_CHECK(permute_in(ctx, kp.sph_k, nbnd, stage, npwx, kp.d_evc, npwx, npwx));     // rows >= npw_k are zeroed
     SGW_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -1392,14 +1392,13 @@ int sgw_unfold_w(sgw_ctx *ctx, int ngc, int nfs, int ngmunique, const int32_t *i
   SGW_CHECK(ws(ctx, "uf_in", nin, &d_in));
   SGW_CHECK(ws(ctx, "uf_out", nout, &d_out));
   SGW_CHECK(ws(ctx, "uf_iu", (size_t)ngmunique, &d_iu));
-  SGW_CUDA(cudaMemcpyAsync(d_in, scrcoul_in, sizeof(cplx) * nin, cudaMemcpyHostToDevice, st));
-  SGW_CUDA(cudaMemcpyAsync(d_out, scrcoul_out, sizeof(cplx) * nout, cudaMemcpyHostToDevice, st));   // INTENT(INOUT)-like
+  SGW_CHECK(h2d_large(ctx, d_in, scrcoul_in, sizeof(cplx) * nin));
+  SGW_CHECK(h2d_large(ctx, d_out, scrcoul_out, sizeof(cplx) * nout));                                 // INTENT(INOUT)-like
   SGW_CUDA(cudaMemcpyAsync(d_iu, ig_unique, sizeof(int) * ngmunique, cudaMemcpyHostToDevice, st));
   dim3 gr((ngc + 127) / 128, nfs, ngmunique);
   k_unfold<<<gr, 128, 0, st>>>(ngc, nfs, ngmunique, d_iu, d_in, d_out);
   SGW_LAUNCH_CHECK();
-  SGW_CUDA(cudaMemcpyAsync(scrcoul_out, d_out, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, st));
-  SGW_CUDA(cudaStreamSynchronize(st));
+  SGW_CHECK(d2h_large(ctx, scrcoul_out, d_out, sizeof(cplx) * nout));
   end_call(ctx);
   return SGW_OK;
 }

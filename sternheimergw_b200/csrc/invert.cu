@@ -297,7 +297,7 @@ extern "C" int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrc
   SGW_CHECK(ws(ctx, "ie_a", tot, &d_a));
   SGW_CHECK(ws(ctx, "ie_piv", (size_t)ngc * nfs + 1, &d_piv));
   d_info = d_piv + (size_t)ngc * nfs;
-  SGW_CUDA(cudaMemcpyAsync(d_a, scrcoul_g, sizeof(cplx) * tot, cudaMemcpyHostToDevice, st));
+  SGW_CHECK(h2d_large(ctx, d_a, scrcoul_g, sizeof(cplx) * tot));
   SGW_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
   const dim3 g1((ngc + 127) / 128, nfs);
   if (lgamma) { k_eps_wings<<<g1, 128, 0, st>>>(ngc, d_a); SGW_LAUNCH_CHECK(); }            // :46-56
@@ -309,8 +309,8 @@ extern "C" int sgw_invert_epsilon(sgw_ctx *ctx, int ngc, int nfs, sgw_cplx *scrc
   SGW_LAUNCH_CHECK();
   int info = 0;
   SGW_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SGW_CUDA(cudaMemcpyAsync(scrcoul_g, d_a, sizeof(cplx) * tot, cudaMemcpyDeviceToHost, st));
   SGW_CUDA(cudaStreamSynchronize(st));
+  SGW_CHECK(d2h_large(ctx, scrcoul_g, d_a, sizeof(cplx) * tot));
   end_call(ctx);
   float ms_gj = 0.f;
   if (cudaEventElapsedTime(&ms_gj, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stats.ms_solver = ms_gj;   // the elimination alone (ms_total includes the copies)
