@@ -372,7 +372,9 @@ static int mix_potential_c(orc_mix_state *m, size_t ndim, zcplx *vout, zcplx *vi
 /* ---------------------------------------------------------------- metals ([QE] klist: lgauss, degauss, ngauss; ener: ef)
  * The QE sources are not part of the reference tree, so this block restates the PUBLISHED algorithm -- S. de Gironcoli,
  * PRB 51, 6773 (1995), eqs. (13)-(17), in the form of QE 6.3 LR_Modules/orthogonalize.f90 (lgauss branch), Modules/wgauss.f90 and
- * Modules/w0gauss.f90 -- and is "parity unpinned" (no reference vector exists for it).  Anchors: tests/test_oracle_metal.py. */
+ * Modules/w0gauss.f90 -- and is "parity unpinned" (no reference vector exists for it).  Anchors (tests/test_oracle_metal.py): the
+ * result equals finite-temperature perturbation theory summed over all pairs of states (tests/sos.py) for all four smearing
+ * types; the static response is independent of alpha_pv; w0gauss = d wgauss / dx; the insulator limit. */
 static int g_lgauss = 0, g_ngauss = 0, g_metal_nks = 0;
 static double g_ef = 0.0, g_degauss = 0.0;
 static const orc_metal_pair *g_metal = NULL;

@@ -393,7 +393,7 @@ def wgauss(x, n):
     return 0.5 * erfc(-x)
 
 
-def make_metal(sys: SynthSystem, ef, degauss, ngauss=0, occ_fn=None, target=3.0):
+def make_metal(sys: SynthSystem, ef, degauss, ngauss=0, occ_fn=None, target=None):
     """Turn a system built by attach_kpoints(sys, klist, xq, nbnd=nbnd_all) into a metallic one (klist lgauss): the Fermi level
     `ef` lies inside the computed bands, nbnd_occ(ik) = number of bands below ef + target * degauss (setup_nbnd_occ), the
     operator's projector keeps the first nbnd_occ(ikq) bands of evq, and `sys.metal` carries what orthogonalize's lgauss
@@ -401,6 +401,9 @@ def make_metal(sys: SynthSystem, ef, degauss, ngauss=0, occ_fn=None, target=3.0)
     if occ_fn is None:
         import oracle
         occ_fn = oracle.wgauss
+    if target is None:
+        # [QE] setup_nbnd_occ: bands up to ef + xmax * degauss, xmax = 3 (w0gauss < 6.96e-5 for a Gaussian), 9.57 for Fermi-Dirac
+        target = 9.57 if ngauss == -99 else 3.0
     pairs = []
     for kp in sys.kpairs:
         kq = kp.kq
