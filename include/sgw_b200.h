@@ -126,7 +126,8 @@ int sgw_set_kpair(sgw_ctx *ctx, int ik, int slot_kq, int npw_k, const int32_t *n
 /* Metals.  [QE] klist (lgauss, degauss, ngauss) and ener (ef) as read by LR_Modules/orthogonalize.f90, which solve_linter.f90:337
  * calls: with lgauss != 0 the right-hand sides are built with the smeared projector of S. de Gironcoli, PRB 51, 6773 (1995) and
  * the solutions are scaled by wg(ibnd, ikk) / wk(ikk) (solve_linter.f90:373).  ngauss: -99 Fermi-Dirac, -1 Marzari-Vanderbilt,
- * 0 Gaussian, n > 0 Methfessel-Paxton.  lgauss = 0 (default) is the insulator path.  Direct solver only. */
+ * 0 Gaussian, n > 0 Methfessel-Paxton.  lgauss = 0 (default) is the insulator path.  Direct and self-consistent branch;
+ * sgw_coulomb_q0G0 (the insulator treatment of the head) refuses lgauss. */
 int sgw_set_smearing(sgw_ctx *ctx, int lgauss, double ef, double degauss, int ngauss);
 /* per (k, k+q) pair, after sgw_set_kpair: ALL nbnd bands of evq (npwx x nbnd, the first nbnd_occ(ikq) of them are the ones
  * given to sgw_set_kpoint) with et(:, ikq), the number of bands of the solver loop nbnd_occ(ikk) <= nbnd of sgw_set_kpair, and

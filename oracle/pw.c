@@ -613,6 +613,8 @@ int orc_solve_linter_iter(const orc_system *sys, const orc_solver_cfg *cfg_globa
 #pragma omp critical(orc_ierr)
                 ierr_all = ierr;
               }
+              if (mp)                                                   /* dpsi *= wg / wk  :443-444, :454-455 */
+                for (int ig = 0; ig < npwq; ++ig) xx[ig] *= mp->wg_over_wk[ibnd];
               memcpy(dpsi + (size_t)npwx * (ibnd + (size_t)nbnd * io), xx, sizeof(zcplx) * npwq);
               nop_all += s1.n_op;
               if (s1.n_outer > nouter_max) nouter_max = s1.n_outer;

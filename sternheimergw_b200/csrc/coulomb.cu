@@ -330,6 +330,57 @@ __global__ void k_band_scale(int n, int nocc, const double *__restrict__ f, cplx
   if (e < n) v[(long)r * n + e] = cscale(f[r % nocc], v[(long)r * n + e]);
 }
 
+// [QE] orthogonalize (solve_linter.f90:337,409) for `nrhs` vectors whose band is (column % nocc): insulators
+// dvpsi <- evq (evq^H dvpsi) - dvpsi = -P_c^+ dvpsi; metals (lgauss) the smeared projector.  *d_wgk (metals): wg/wk of the bands
+static int orthogonalize_dev(sgw_ctx *ctx, const KPair &kp, const KSlot &ks, int nocc, int nrhs, cplx *dvpsi, double **d_wgk_out) {
+  cudaStream_t st = ctx->stream;
+  const bool metal = ctx->lgauss;
+  const int n = ks.npwx;
+  cplx *ps = nullptr;
+  double *d_wgk = nullptr;
+  if (!metal) {
+    const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
+    SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nrhs, &ps));
+    SGW_CHECK(gemm_ch_n(ctx, nocc, nrhs, ks.npw, evq, n, dvpsi, n, ps, nocc));
+    SGW_CHECK(gemm_n_n(ctx, n, nrhs, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), dvpsi, n));
+  } else {
+    // orthogonalize.f90, lgauss: ps(j, i) = wwg(j, i) <evq_j|dvpsi_i> over all nbnd bands at k+q, dvpsi_i *= theta~_F,i
+    const int nb = kp.nbnd_all;
+    std::vector<double> wwg((size_t)nb * nocc), wg1(nocc);
+    for (int ib = 0; ib < nocc; ++ib) {
+      wg1[ib] = wgauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss);
+      const double w0g = w0gauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss) / ctx->degauss;
+      for (int jb = 0; jb < nb; ++jb) {
+        const double wgp = wgauss((ctx->ef - kp.et_q[jb]) / ctx->degauss, ctx->ngauss);
+        const double deltae = kp.et_q[jb] - kp.et[ib];
+        const double theta = wgauss(deltae / ctx->degauss, 0);
+        double w = wg1[ib] * (1.0 - theta) + wgp * theta;
+        if (jb < ks.nbnd) w += fabs(deltae) > 1.0e-5 ? ks.alpha_pv * theta * (wgp - wg1[ib]) / deltae : -ks.alpha_pv * theta * w0g;
+        wwg[jb + (size_t)nb * ib] = w;
+      }
+    }
+    double *d_wwg = nullptr, *d_wg1 = nullptr;
+    SGW_CHECK(ws(ctx, "co_wwg", (size_t)nb * nocc, &d_wwg));
+    SGW_CHECK(ws(ctx, "co_wg1", (size_t)nocc, &d_wg1));
+    SGW_CHECK(ws(ctx, "co_wgk", (size_t)nocc, &d_wgk));
+    SGW_CUDA(cudaMemcpyAsync(d_wwg, wwg.data(), sizeof(double) * wwg.size(), cudaMemcpyHostToDevice, st));
+    SGW_CUDA(cudaMemcpyAsync(d_wg1, wg1.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
+    SGW_CUDA(cudaMemcpyAsync(d_wgk, kp.wg_over_wk.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
+    SGW_CUDA(cudaStreamSynchronize(st));                                                   // host vectors go out of scope
+    SGW_CHECK(ws(ctx, "co_ps", (size_t)nb * nrhs, &ps));
+    SGW_CHECK(gemm_ch_n(ctx, nb, nrhs, ks.npw, kp.d_evq_all, n, dvpsi, n, ps, nb));
+    for (int r0 = 0; r0 < nrhs; r0 += 65535 / nocc * nocc) {
+      const int c = std::min(65535 / nocc * nocc, nrhs - r0);
+      dim3 gm((unsigned)((std::max(n, nb) + 255) / 256), (unsigned)c);
+      k_metal_scale<<<gm, 256, 0, st>>>(nb, nocc, c, n, d_wwg, d_wg1, ps + (size_t)r0 * nb, dvpsi + (size_t)r0 * n);
+      SGW_LAUNCH_CHECK();
+    }
+    SGW_CHECK(gemm_n_n(ctx, n, nrhs, nb, cmake(1.0, 0.0), kp.d_evq_all, n, ps, nb, cmake(-1.0, 0.0), dvpsi, n));
+  }
+  if (d_wgk_out) *d_wgk_out = d_wgk;
+  return SGW_OK;
+}
+
 // ---- k-point lanes (see drho_block) ---------------------------------------------------------------------------
 __global__ void k_vadd(long n, cplx *__restrict__ a, const cplx *__restrict__ b) {            // a += b
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] = cadd(a[i], b[i]);
@@ -478,45 +529,7 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nrhs, Tq, dvpsi, n, epi, nullptr));
     // [QE] orthogonalize (insulator): ps = evq^H dvpsi ; dvpsi <- evq ps - dvpsi   (solve_linter.f90:337)
     double *d_wgk = nullptr;
-    if (!metal) {
-      const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
-      SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nrhs, &ps));
-      SGW_CHECK(gemm_ch_n(ctx, nocc, nrhs, ks.npw, evq, n, dvpsi, n, ps, nocc));
-      SGW_CHECK(gemm_n_n(ctx, n, nrhs, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), dvpsi, n));
-    } else {
-      // orthogonalize.f90, lgauss: ps(j, i) = wwg(j, i) <evq_j|dvpsi_i> over all nbnd bands at k+q, dvpsi_i *= theta~_F,i
-      const int nb = kp.nbnd_all;
-      std::vector<double> wwg((size_t)nb * nocc), wg1(nocc);
-      for (int ib = 0; ib < nocc; ++ib) {
-        wg1[ib] = wgauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss);
-        const double w0g = w0gauss((ctx->ef - kp.et[ib]) / ctx->degauss, ctx->ngauss) / ctx->degauss;
-        for (int jb = 0; jb < nb; ++jb) {
-          const double wgp = wgauss((ctx->ef - kp.et_q[jb]) / ctx->degauss, ctx->ngauss);
-          const double deltae = kp.et_q[jb] - kp.et[ib];
-          const double theta = wgauss(deltae / ctx->degauss, 0);
-          double w = wg1[ib] * (1.0 - theta) + wgp * theta;
-          if (jb < ks.nbnd) w += fabs(deltae) > 1.0e-5 ? ks.alpha_pv * theta * (wgp - wg1[ib]) / deltae : -ks.alpha_pv * theta * w0g;
-          wwg[jb + (size_t)nb * ib] = w;
-        }
-      }
-      double *d_wwg = nullptr, *d_wg1 = nullptr;
-      SGW_CHECK(ws(ctx, "co_wwg", (size_t)nb * nocc, &d_wwg));
-      SGW_CHECK(ws(ctx, "co_wg1", (size_t)nocc, &d_wg1));
-      SGW_CHECK(ws(ctx, "co_wgk", (size_t)nocc, &d_wgk));
-      SGW_CUDA(cudaMemcpyAsync(d_wwg, wwg.data(), sizeof(double) * wwg.size(), cudaMemcpyHostToDevice, st));
-      SGW_CUDA(cudaMemcpyAsync(d_wg1, wg1.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
-      SGW_CUDA(cudaMemcpyAsync(d_wgk, kp.wg_over_wk.data(), sizeof(double) * nocc, cudaMemcpyHostToDevice, st));
-      SGW_CUDA(cudaStreamSynchronize(st));                                                   // host vectors go out of scope
-      SGW_CHECK(ws(ctx, "co_ps", (size_t)nb * nrhs, &ps));
-      SGW_CHECK(gemm_ch_n(ctx, nb, nrhs, ks.npw, kp.d_evq_all, n, dvpsi, n, ps, nb));
-      for (int r0 = 0; r0 < nrhs; r0 += 65535 / nocc * nocc) {
-        const int c = std::min(65535 / nocc * nocc, nrhs - r0);
-        dim3 gm((unsigned)((std::max(n, nb) + 255) / 256), (unsigned)c);
-        k_metal_scale<<<gm, 256, 0, st>>>(nb, nocc, c, n, d_wwg, d_wg1, ps + (size_t)r0 * nb, dvpsi + (size_t)r0 * n);
-        SGW_LAUNCH_CHECK();
-      }
-      SGW_CHECK(gemm_n_n(ctx, n, nrhs, nb, cmake(1.0, 0.0), kp.d_evq_all, n, ps, nb, cmake(-1.0, 0.0), dvpsi, n));
-    }
+    SGW_CHECK(orthogonalize_dev(ctx, kp, ks, nocc, nrhs, dvpsi, &d_wgk));                  // solve_linter.f90:337
     // band loop :367-374 -> one batch; sigma = -(et + omega) :369
     {
       std::vector<cplx> sig((size_t)nshift * nrhs);
@@ -831,10 +844,6 @@ static int mix_potential_c_dev(sgw_ctx *ctx, MixState &m, long ndim, cplx *vout,
 static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global, int num_iter, const cplx *d_field,
                                   double meandvb, const FreqList &fl, const Sphere &rho, cplx *d_dvscfin, int *ierr_out,
                                   int *iter_done) {
-  if (ctx->lgauss) {
-    ctx->err = "metals (sgw_set_smearing) are supported by the direct solver only";
-    return SGW_E_UNSUPPORTED;
-  }
   const int nfreq = fl.nfreq, nshift = fl.num_omega;
   const long nnr = (long)ctx->nr1 * ctx->nr2 * ctx->nr3;
   const long ndim = nnr * nfreq;
@@ -869,7 +878,7 @@ static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global
       return SGW_E_STATE;
     }
     bare_off[ik] = bare_tot;
-    bare_tot += (size_t)ctx->slots[kp.slot].nbnd * ctx->slots[kp.slot].npwx;
+    bare_tot += (size_t)std::max(ctx->slots[kp.slot].nbnd, kp.nocc_k) * ctx->slots[kp.slot].npwx;   // nbnd_occ(ikk) bands (metals: may exceed nbnd_occ(ikq))
   }
   cplx *bare = nullptr;
   SGW_CHECK(ws(ctx, "it_bare", bare_tot, &bare));
@@ -883,16 +892,18 @@ static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global
     for (size_t ik = 0; ik < ctx->pairs.size(); ++ik) {                                    // :288
       const KPair &kp = ctx->pairs[ik];
       const KSlot &ks = ctx->slots[kp.slot];
-      const int n = ks.npwx, nocc = ks.nbnd;
+      const bool metal = ctx->lgauss;
+      if (metal && (kp.nbnd_all <= 0 || !kp.d_evq_all)) { ctx->err = "lgauss is set but sgw_set_kpair_metal was not called for this pair"; return SGW_E_STATE; }
+      const int n = ks.npwx, nocc = metal ? kp.nocc_k : ks.nbnd;                           // bands of the loop :367 = nbnd_occ(ikk)
       if (nocc > kp.nbnd) { ctx->err = "evc holds fewer bands than nbnd_occ"; return SGW_E_ARG; }
-      cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *rhs = nullptr, *ps = nullptr, *d_sig = nullptr, *d_x = nullptr,
+      double *d_wgk = nullptr;
+      cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *rhs = nullptr, *d_sig = nullptr, *d_x = nullptr,
            *b2 = nullptr, *davg = nullptr, *Td = nullptr;
       int *d_ierr = nullptr;
       SGW_CHECK(ws(ctx, "co_Tk", (size_t)nocc * ctx->nr3 * kp.sph_k.ncol, &Tk));
       SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));
       SGW_CHECK(fft_zpass_g2r(ctx, kp.sph_k, nocc, kp.d_evc, n, Tk, nullptr));
       SGW_CHECK(fft_plane(ctx, PLANE_TO_R, &kp.sph_k, nullptr, nocc, Tk, nullptr, nullptr, 1, psir, nullptr));
-      const cplx *evq = ks.d_P + (size_t)ks.nkb * n;
       cplx *bare_k = bare + bare_off[ik];
       const int nrhs = first ? nocc : nocc * nshift;
       SGW_CHECK(ws(ctx, "sv_sig", (size_t)nocc * nshift, &d_sig));
@@ -915,9 +926,7 @@ static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global
         SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nocc, Tq, bare_k, n, epi0, nullptr));
         SGW_CHECK(ws(ctx, "co_dvpsi", (size_t)nocc * n, &rhs));
         SGW_CUDA(cudaMemcpyAsync(rhs, bare_k, sizeof(cplx) * (size_t)nocc * n, cudaMemcpyDeviceToDevice, st));
-        SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nocc, &ps));
-        SGW_CHECK(gemm_ch_n(ctx, nocc, nocc, ks.npw, evq, n, rhs, n, ps, nocc));
-        SGW_CHECK(gemm_n_n(ctx, n, nocc, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), rhs, n));
+        SGW_CHECK(orthogonalize_dev(ctx, kp, ks, nocc, nocc, rhs, &d_wgk));                 // :337
         config.threshold = 1.0e-2;
         sb.nrhs = nocc; sb.nshift = nshift; sb.d_b = rhs;
         SGW_CHECK(select_solver_batched(ctx, sb, &config));
@@ -933,9 +942,7 @@ static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global
         ZEpilogue epi2 = epi0;
         epi2.mode = 2;                                                                     // cft_wave(-1) ADDS to dvpsi
         SGW_CHECK(fft_zpass_r2g(ctx, ks.sph, nv, Tq, rhs, n, epi2, nullptr));
-        SGW_CHECK(ws(ctx, "co_ps", (size_t)nocc * nv, &ps));
-        SGW_CHECK(gemm_ch_n(ctx, nocc, nv, ks.npw, evq, n, rhs, n, ps, nocc));
-        SGW_CHECK(gemm_n_n(ctx, n, nv, nocc, cmake(1.0, 0.0), evq, n, ps, nocc, cmake(-1.0, 0.0), rhs, n));
+        SGW_CHECK(orthogonalize_dev(ctx, kp, ks, nocc, nv, rhs, &d_wgk));                   // :409 (vector f * nocc + ib: band = column % nocc)
         SGW_CHECK(ws(ctx, "it_b2", (size_t)nocc * nshift * n, &b2));
         {
           dim3 gr((n + 255) / 256, nocc, nshift);
@@ -959,6 +966,11 @@ static int solve_linter_iter_core(sgw_ctx *ctx, const sgw_solver_cfg *cfg_global
       dim3 ga((n + 255) / 256, nocc, nfreq);
       k_average<<<ga, 256, 0, st>>>(n, nocc, nfreq, nshift, fl.zero_freq, 0, d_x, davg);
       SGW_LAUNCH_CHECK();
+      if (metal) {                                                                         // dpsi *= wg / wk (:373), linear: after the average
+        dim3 gs((unsigned)((n + 255) / 256), (unsigned)(nfreq * nocc));
+        k_band_scale<<<gs, 256, 0, st>>>(n, nocc, d_wgk, davg);
+        SGW_LAUNCH_CHECK();
+      }
       SGW_CHECK(fft_zpass_g2r(ctx, ks.sph, nfreq * nocc, davg, n, Td, nullptr));
       SGW_CHECK(fft_plane_rho(ctx, ks.sph, rho, nfreq, nocc, Td, psir, wgt, Trho, ik > 0));
     }

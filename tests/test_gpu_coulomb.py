@@ -367,3 +367,29 @@ def test_padded_box_gives_the_compact_result(ctx):
     assert np.array_equal(b[:nr[0], :nr[1], :nr[2]], a)
     assert np.abs(b[nr[0]:]).max() == 0.0 and np.abs(b[:, :, nr[2]:]).max() == 0.0
     assert np.array_equal(ca, cb)
+
+
+def test_solve_linter_selfconsistent_metal_matches_oracle(ctx):
+    """The self-consistent branch for a metal: both orthogonalize calls (solve_linter.f90:337 and :409) take the smeared
+    projector and the solutions of every iteration are scaled by wg/wk (:373); same iteration count and dV_scf as the oracle."""
+    import oracle
+    from metal_util import metal_system
+    from sternheimergw_b200 import select_solver_type
+    syn = metal_system(ngauss=0, nk=2)
+    ctx.install_system(syn)
+    ps = oracle.PwSystem(syn)
+    fiu = np.array([0.0, 0.6j])
+    nnr = int(np.prod(syn.nr))
+    dv = np.zeros(nnr, dtype=complex)
+    dv[syn.nl[3] - 1] = 1.0
+    dvr = (np.fft.ifftn(dv.reshape(syn.nr, order="F")) * nnr).reshape(-1, order="F")
+    niter, alpha, tr2, nmix = 60, 0.5, 1e-22, 4
+    try:
+        ref, ierr, st = ps.solve_linter_iter(niter, alpha, tr2, nmix, dvr, fiu, oracle.make_cfg(priority=(1, 3), threshold=1e-4), nthreads=8)
+        assert ierr == 0
+        ctx.set_mixing(niter, alpha, tr2, nmix)
+        out = ctx.solve_linter(select_solver_type(priority=(1, 3), threshold=1e-4), niter, dvr, fiu)
+    finally:
+        ctx.set_smearing(False)
+    assert abs(ctx.scf_iterations() - st["iter"]) <= 1, (ctx.scf_iterations(), st["iter"])
+    assert _rel(out, ref) < 1e-7, _rel(out, ref)
