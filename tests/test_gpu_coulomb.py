@@ -177,7 +177,7 @@ def test_solve_linter_matches_oracle(ctx):
         assert out.shape == ref.shape
         assert _rel(out, ref) < 1e-8, (prio, _rel(out, ref))
     with pytest.raises(SgwError):
-        ctx.solve_linter(select_solver_type(), 3, dvr, freq)        # iterative branch: not implemented, loud
+        ctx.solve_linter(select_solver_type(), 3, dvr, freq)        # num_iter > 1 without sgw_set_mixing for 3 iterations: refused, loud
 
 
 @pytest.mark.parametrize("ngc,nfs", [(7, 3), (59, 2), (130, 2)])
