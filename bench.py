@@ -412,6 +412,7 @@ def main():
     ap.add_argument("--pert", type=int, default=8, help="perturbations per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sigma", action="store_true", help="skip the Sigma_c (SURVEY 8 f2/f3) leg")
+    ap.add_argument("--no-small", action="store_true", help="skip the time-to-W of the small BASELINE configs (gw_si, gw_c, gw_bn, gw_licl)")
     ap.add_argument("--sigma-only", action="store_true", help="run only the Sigma_c leg and print its record (profiling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -670,6 +671,19 @@ def main():
             line["sigma_c"] = sigma_c_leg(local_rank, f64_peak)
         except Exception as e:                                  # the headline line must survive a failure of the extra leg
             line["sigma_c"] = {"error": repr(e)}
+    if world == 1 and not args.no_small and not args.no_cpu_baseline:
+        # BASELINE.json configs[0..3] (the reference's own CPU-runnable cases): one q-point each, time-to-W on this GPU next to
+        # the oracle on the box's cores in the same run, with the agreement of the two results (tools/config_times.py)
+        del ctx
+        ctx = None
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import config_times
+            keep = ("config", "fft_grid", "nk", "ngc", "nshift", "solver_priority", "solves", "gpu_time_to_W_s", "gpu_launches",
+                    "cpu_oracle_s", "cpu_cores", "speedup", "max_abs_diff_eps", "agrees_within_10_thr")
+            line["small_configs"] = [{k: r[k] for k in keep if k in r} for r in config_times.main(do_cpu=True, device=local_rank, quiet=True)]
+        except Exception as e:
+            line["small_configs"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         del ctx
         cb = cpu_sample(syn, fiu, ngc, igu, steps=1, warmup=0)

@@ -33,10 +33,11 @@ CASES = [
 ]
 
 
-def main():
-    do_cpu = "--no-cpu" not in sys.argv
+def main(do_cpu=None, device=0, quiet=False):
+    if do_cpu is None:
+        do_cpu = "--no-cpu" not in sys.argv
     cores = len(os.sched_getaffinity(0))
-    ctx = Context(0)
+    ctx = Context(device)
     out = []
     for name, preset, nk, ngc, fiu, prio, thr, ref in CASES:
         syn = synth.preset(preset, nk=nk)
@@ -68,7 +69,9 @@ def main():
                         "speedup": cpu_s / gpu_s, "max_abs_diff_eps": err, "agrees_within_10_thr": bool(err < 10 * thr * 10)})
         rec["eps_inv_00_w0"] = [float(eps[0, 0, 0].real), float(eps[0, 0, 0].imag)]
         out.append(rec)
-        print(json.dumps(rec), flush=True)
+        if not quiet:
+            print(json.dumps(rec), flush=True)
+    ctx.close()
     return out
 
 
