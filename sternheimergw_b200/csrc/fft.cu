@@ -1385,10 +1385,13 @@ static int launch_plane_vloc_nt(sgw_ctx *ctx, const GridDev &g, const Sphere &s,
 template <int RX1, int RX2, int RY1, int RY2>
 static int launch_plane_vloc(sgw_ctx *ctx, const GridDev &g, const Sphere &s, int nvec, const cplx *Tin, cplx *Tout, const int *active,
                              bool *done) {
-  // SGW_PLANE_NT: threads per CTA (256 | 288 | 320 | 352 | 384).  Measured at Si64 (fft_plane class per step, two CTAs per SM in
-  // every case): 256 -> 101.7 ms, 320 -> 102.1 ms, 352 -> 104.7 ms, 384 -> 106.2 ms: fewer warps at the block-wide barriers win
+  // SGW_PLANE_NT: threads per CTA (192 | 224 | 256 | 288 | 320 | 352 | 384).  Measured at Si64 (fft_plane class per step, two CTAs per SM in
+  // every case): 192 -> 100.2 ms, 224 -> 101.7 ms, 256 -> 101.6 ms, 320 -> 102.1 ms, 352 -> 104.7 ms, 384 -> 106.2 ms: fewer warps at
+  // the block-wide barriers win, flat below 256
   const char *e = getenv("SGW_PLANE_NT");
   const int nt = e ? atoi(e) : 256;
+  if (nt == 192) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 192>(ctx, g, s, nvec, Tin, Tout, active, done);
+  if (nt == 224) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 224>(ctx, g, s, nvec, Tin, Tout, active, done);
   if (nt == 256) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 256>(ctx, g, s, nvec, Tin, Tout, active, done);
   if (nt == 288) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 288>(ctx, g, s, nvec, Tin, Tout, active, done);
   if (nt == 320) return launch_plane_vloc_nt<RX1, RX2, RY1, RY2, 320>(ctx, g, s, nvec, Tin, Tout, active, done);
