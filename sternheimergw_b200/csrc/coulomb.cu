@@ -494,7 +494,7 @@ static int drho_block(sgw_ctx *ctx, const sgw_solver_cfg *cfg, int np, const cpl
     if (nocc > kp.nbnd) { ctx->err = "evc holds fewer bands than nbnd_occ"; return SGW_E_ARG; }
     const int nrhs = np * nocc;
     // psi_v(r) for the occupied bands: used by dV psi and again by the Delta-rho accumulation
-    cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *dvpsi = nullptr, *ps = nullptr, *d_sig = nullptr, *d_x = nullptr;
+    cplx *Tk = nullptr, *psir = nullptr, *Tq = nullptr, *dvpsi = nullptr, *d_sig = nullptr, *d_x = nullptr;
     int *d_ierr = nullptr;
     SGW_CHECK(ws(ctx, "co_Tk", (size_t)nocc * ctx->nr3 * kp.sph_k.ncol, &Tk));
     SGW_CHECK(ws(ctx, "co_psir", (size_t)nocc * nnr, &psir));

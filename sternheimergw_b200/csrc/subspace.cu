@@ -151,7 +151,6 @@ __global__ void __launch_bounds__(ST) k_sub_residual(SubState s, int ishift) {
   if (!s.alive[b] || s.done[b]) return;
   extern __shared__ cplx dyn[];       // overlaps c[cap]
   __shared__ cplx sm[32];
-  __shared__ int flag;
   const int m = s.m[b], n = s.n, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const cplx *bb = s.b + (long)b * s.ldb;
   if (s.iter[b] >= s.max_iter) {                        // loop ran out without convergence (:176-180)
@@ -195,7 +194,6 @@ __global__ void __launch_bounds__(ST) k_sub_residual(SubState s, int ishift) {
     return;
   }
   if (threadIdx.x == 0) {
-    flag = 0;
     if (n == m) {                                       // :376-378 sets 3, :176-180 overwrites it with 1
       s.ierr[b] = 1; s.alive[b] = 0;
     } else {
@@ -205,7 +203,6 @@ __global__ void __launch_bounds__(ST) k_sub_residual(SubState s, int ishift) {
       atomicAdd((unsigned long long *)s.nop, 1ull);
     }
   }
-  (void)flag;
 }
 
 __global__ void __launch_bounds__(ST) k_sub_expand(SubState s) {
