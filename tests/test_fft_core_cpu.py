@@ -87,3 +87,11 @@ def test_fused_vloc_middle_stage(harness, n):
         v_perm = v_nat[:, _perm(n, r1, r2)]                     # the library stores v(r) pre-permuted
         y, _ = _run(harness, n, nlines, 0, nthreads, 0, x, v_perm)
         assert np.abs(y - ref).max() < 1e-12 * n * n
+
+
+def test_tracked_codelets_are_what_the_generator_writes(tmp_path):
+    """csrc/fft_codelets.h is generated (tools/gen_codelets.py); the tracked copy must be the generator's output."""
+    import sys
+    out = tmp_path / "fft_codelets.h"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "gen_codelets.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == (ROOT / "sternheimergw_b200" / "csrc" / "fft_codelets.h").read_text()

@@ -187,9 +187,11 @@ def main():
     out.append("#define SGW_FOR_EACH_BIG_RADIX(X) " + " ".join(f"X({r})" for r in RADICES if r in BIG))
     out.append("")
     out.append("}  // namespace sgw")
-    OUT.parent.mkdir(parents=True, exist_ok=True)
-    OUT.write_text("\n".join(out) + "\n")
-    print("wrote", OUT, len(out), "lines")
+    import sys
+    dst = Path(sys.argv[1]) if len(sys.argv) > 1 else OUT        # optional output path (tests regenerate into a scratch file)
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    dst.write_text("\n".join(out) + "\n")
+    print("wrote", dst, len(out), "lines")
 
 
 if __name__ == "__main__":
